@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference (/root/reference/text-guided:
+`inversion_forward_process_ddpm` -> `make_controller` -> `register_attention_control` -> `h_Edit_p2p_implicit`)
+on the oracle's seeded random-init SD-1.x UNet restatement (no pretrained weights exist offline).
+
+Runs only in the build container (the GPU box has no /root/reference); the resulting tensors are committed so
+that tests on the GPU box can compare the CUDA path and the oracle port against the reference's own outputs.
+
+    python tools/make_golden.py --config tiny      # seconds
+    python tools/make_golden.py --config sd15      # BASELINE.json configs[0]: full SD-1.5 UNet, T=10, ~10 min CPU
+"""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle.pipeline import OraclePipeline  # noqa: E402
+from oracle.sd_unet import UNetConfig  # noqa: E402
+from refload import load_reference  # noqa: E402
+
+PROMPTS = ["a green lizard is sitting on a branch", "a brown lizard is sitting on a branch"]
+BLEND = ("lizard", "lizard")
+
+CASES = {
+    # name: (unet cfg, T, K, is_replace, blend)
+    "tiny_refine_blend": (UNetConfig.tiny(sample_size=64), 10, 1, False, True),
+    "tiny_replace_mos2": (UNetConfig.tiny(sample_size=64), 6, 2, True, True),
+    "tiny_refine_noblend": (UNetConfig.tiny(sample_size=64), 6, 1, False, False),
+    "sd15_config1": (UNetConfig.sd15(), 10, 1, False, True),
+}
+
+
+def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
+    torch.set_num_threads(os.cpu_count())
+    model = OraclePipeline(cfg, seed=0)
+    model.scheduler.set_timesteps(T)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    w0 = torch.randn(1, cfg.in_channels, cfg.sample_size, cfg.sample_size, generator=g) * 0.18215 * 5
+    torch.manual_seed(0)    # the reference draws its inversion noise from the global RNG (ddpm_inversion.py:48)
+    t0 = time.time()
+    _, zs, wts, _ = ref.ddpm_inversion.inversion_forward_process_ddpm(
+        model, w0, etas=1.0, prog_bar=False, prompt=PROMPTS[0], cfg_scale_src=1.0, num_inference_steps=T)
+    t_inv = time.time() - t0
+    blend_word = ((BLEND[0],), (BLEND[1],)) if blend else None
+    eq = {"words": (BLEND[1],), "values": (1.25 if K > 1 else 2.0,)} if blend else None    # main_p2p.py:196-201
+    controller = ref.ptp_controller_utils.make_controller(
+        prompts=PROMPTS, is_replace_controller=is_replace, cross_replace_steps=xa, self_replace_steps=sa,
+        blend_word=blend_word, equilizer_params=eq, num_steps=T, tokenizer=model.tokenizer, device=model.device)
+    ref.ptp_utils.register_attention_control(model, controller)
+    trace = []
+    orig_cb = controller.step_callback
+
+    def cb(x):
+        y = orig_cb(x)
+        trace.append(y.detach().clone())
+        return y
+
+    controller.step_callback = cb
+    t0 = time.time()
+    edited, recon = ref.p2p_h_edit.h_Edit_p2p_implicit(
+        model, xT=wts[T], eta=1.0, prompts=PROMPTS, cfg_scales=[1.0, 5.0, 7.5], prog_bar=False, zs=zs[:T],
+        controller=controller, weight_reconstruction=0.1, optimization_steps=K, after_skip_steps=T,
+        is_ddim_inversion=False)
+    t_edit = time.time() - t0
+    enc = ref.inversion_utils.encode_text
+    out = {
+        "meta": dict(name=name, T=T, K=K, is_replace=is_replace, blend=blend, xa=xa, sa=sa, prompts=PROMPTS,
+                     blend_words=BLEND, cfg_scales=[1.0, 5.0, 7.5], eta=1.0, weight_reconstruction=0.1,
+                     unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
+                               cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
+                     weights="oracle.sd_unet.seeded_init_(seed=0)", w0="randn(seed 0)*0.18215*5",
+                     generator="tools/make_golden.py", seconds=dict(inversion=t_inv, edit=t_edit),
+                     torch=torch.__version__, threads=torch.get_num_threads()),
+        "w0": w0, "zs": zs[:T].clone(), "xT": wts[T].clone(), "xts": wts.clone(),
+        "ctx_uncond": enc(model, [""]), "ctx_src": enc(model, [PROMPTS[0]]), "ctx_tar": enc(model, [PROMPTS[1]]),
+        "edited": edited.detach().clone(), "recon": recon.detach().clone(),
+        "trace": torch.stack(trace),
+        "tables": {
+            "alpha_words": controller.cross_replace_alpha.reshape(T + 1, 77).clone(),
+            "self_window": list(controller.num_self_replace),
+        },
+    }
+    inner = controller.prev_controller if hasattr(controller, "prev_controller") and controller.prev_controller is not None else controller
+    if is_replace:
+        out["tables"]["replace_matrix"] = inner.mapper[0].clone()
+    else:
+        out["tables"]["mapper"] = inner.mapper[0].clone()
+        out["tables"]["refine_alpha"] = inner.alphas.reshape(77).clone()
+    if hasattr(controller, "equalizer"):
+        out["tables"]["equalizer"] = controller.equalizer.reshape(77).clone()
+    if controller.local_blend is not None:
+        out["tables"]["blend_alpha"] = controller.local_blend.alpha_layers.reshape(2, 77).clone()
+        out["tables"]["start_blend"] = controller.local_blend.start_blend
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "all"])
+    args = ap.parse_args()
+    ref = load_reference()
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for name, (cfg, T, K, rep, blend) in CASES.items():
+        if args.config != "all" and not name.startswith(args.config):
+            continue
+        out = run_case(ref, name, cfg, T, K, rep, blend)
+        path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
+        torch.save(out, path)
+        print(name, "edit %.1fs" % out["meta"]["seconds"]["edit"], "->", path,
+              "|edited| %.4f" % out["edited"].abs().mean().item(), flush=True)
+
+
+if __name__ == "__main__":
+    main()
