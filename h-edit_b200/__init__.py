@@ -1,0 +1,14 @@
+"""hedit_b200 -- B200-native implementation of h-Edit's reverse-time bridge sampling loop (nktoan/h-edit hot path).
+
+Layout: csrc/ (hand-written sm_100a kernels + C ABI), _lib.py (ctypes binding), engine.py (engine handle),
+p2p.py (host-side Prompt-to-Prompt set-up -> device edit plan), schedule.py (per-step scalar tables),
+samplers.py (reference-compatible h_Edit_* callables)."""
+from .p2p import (EditController, LocalBlend, compile_edit_plan, get_equalizer, get_refinement_mapper,  # noqa: F401
+                  get_replacement_mapper, get_time_words_attention_alpha, get_word_inds, make_controller,
+                  register_attention_control)
+from .schedule import step_tables  # noqa: F401
+from .engine import UNetEngine, unet_config_of  # noqa: F401
+from .samplers import encode_text, get_engine, h_Edit_p2p_explicit, h_Edit_p2p_implicit, h_edit_p2p_batch  # noqa: F401
+
+__all__ = ["UNetEngine", "unet_config_of", "make_controller", "register_attention_control", "compile_edit_plan",
+           "h_Edit_p2p_implicit", "h_Edit_p2p_explicit", "h_edit_p2p_batch", "encode_text", "step_tables"]

@@ -1,0 +1,87 @@
+"""ctypes binding of libhedit_b200.so (C ABI declared in include/hedit_b200.h).
+
+There is NO CPU fallback: if the shared library (built by `__graft_entry__.build()` / `make -C h-edit_b200/csrc`)
+is missing, or no sm_100a device is visible when an engine is created, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhedit_b200.so")
+
+
+class UNetConfigC(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("out_channels", C.c_int32), ("sample_size", C.c_int32),
+                ("block_out_channels", C.c_int32 * 4), ("layers_per_block", C.c_int32), ("heads", C.c_int32),
+                ("cross_attention_dim", C.c_int32), ("norm_groups", C.c_int32), ("ctx_len", C.c_int32)]
+
+
+class StepCoefC(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("sqrt_1m_at", "sqrt_at", "sqrt_ap", "dir", "noise", "coeff")]
+
+
+class EditArgsC(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("steps", C.c_int32), ("opt_steps", C.c_int32), ("explicit_form", C.c_int32),
+        ("schedule", C.c_int32), ("buffers_on_host", C.c_int32),
+        ("xT", C.c_void_p), ("zs", C.c_void_p), ("ctx", C.c_void_p), ("timesteps", C.c_void_p), ("coef", C.c_void_p),
+        ("w_src", C.c_float), ("w_src_edit", C.c_float), ("w_tar", C.c_float), ("weight_reconstruction", C.c_float),
+        ("use_p2p", C.c_int32),
+        ("mapper", C.c_void_p), ("is_replace", C.c_void_p), ("replace_m", C.c_void_p), ("c_base", C.c_void_p), ("c_tar", C.c_void_p),
+        ("self_lo", C.c_int32), ("self_hi", C.c_int32), ("self_max_tokens", C.c_int32),
+        ("has_blend", C.c_void_p), ("blend_alpha", C.c_void_p), ("start_blend", C.c_int32), ("blend_th", C.c_float),
+        ("edited", C.c_void_p), ("recon", C.c_void_p), ("trace", C.c_void_p),
+        ("n_sample_forwards", C.c_int64), ("n_kernel_launches", C.c_int64),
+    ]
+
+
+# every symbol include/hedit_b200.h declares: (name, restype, argtypes)
+_P, _I, _F = C.c_void_p, C.c_int, C.c_float
+SYMBOLS = {
+    "hedit_last_error": (C.c_char_p, []),
+    "hedit_device_count": (_I, []),
+    "hedit_engine_create": (_P, [C.POINTER(UNetConfigC), _I, _I, _I]),
+    "hedit_engine_destroy": (None, [_P]),
+    "hedit_engine_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
+    "hedit_engine_finalize": (_I, [_P]),
+    "hedit_engine_flops_per_sample": (C.c_double, [_P]),
+    "hedit_unet_forward": (_I, [_P, _P, _P, _P, _I, _P, _P]),
+    "hedit_edit_p2p": (_I, [_P, C.POINTER(EditArgsC), _P]),
+    "hedit_op_linear": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "hedit_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "hedit_op_self_attention": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "hedit_op_cross_attention_p2p": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "hedit_op_group_norm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "hedit_op_layer_norm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and type every entry point.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"hedit_b200: native library not found at {LIB_PATH}. Build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` or `make -C h-edit_b200/csrc`. There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().hedit_last_error().decode()
+
+
+def check(rc: int, what: str) -> int:
+    if rc < 0:
+        raise RuntimeError(f"hedit_b200: {what} failed ({rc}): {last_error()}")
+    return rc

@@ -1,0 +1,478 @@
+// tcgen05 attention kernels for the SD-1.x UNet (8 heads, head dims 40/80/160; any d % 8 == 0 up to 192).
+//
+//  self_attn_kernel  : streaming (flash-style) softmax(Q K^T * scale) V.  S = Q K^T and O += P V run on the tensor
+//                      cores with TMEM accumulators; the 128 softmax threads own one query row each (TMEM lane ==
+//                      row), so row max / sum need no shuffles.  Probabilities are never written to HBM (the
+//                      reference materialises up to 2.1 GB of fp32 probs per layer call).
+//                      Per-sample (q,k,v) source indices implement the attention injections as pointer swaps:
+//                        P2P self-replace (ptp_classes.py:194-200,225): q,k <- source sample, v own
+//                        MasaCtrl (masactrl.py:53-69)                 : q own, k,v <- source sample
+//                        PnP (pnp_utils.py:52-55)                     : q,k <- source sample, v own
+//  cross_attn_kernel : N x 77 attention against the (cached) text K/V with the Prompt-to-Prompt cross-attention
+//                      edit fused between softmax and P V (ptp_classes.py:202-227,241-283): the CTA handles the
+//                      [source, target] pair of one image for one head / query tile, keeps the source probabilities
+//                      in shared memory, rewrites the target probabilities, and optionally accumulates the
+//                      LocalBlend word maps (ptp_classes.py:44-72,135-150) without storing the full maps.
+//
+// Head-dim padding is free: the TMA maps are (d, H, tokens, samples) with the innermost extent = d, so a 64-wide box
+// reads zeros beyond d (d=40 -> K padded to 48 for the MMA).
+#pragma once
+#include "ptx.cuh"
+
+namespace hedit {
+
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmV;      // 4-D (d, H, tokens, samples)
+  int H, d, Nq, Nkv;
+  float scale_log2;               // softmax scale * log2(e)
+  const int* q_idx;               // per sample: which sample's Q / K / V to read (null = own)
+  const int* k_idx;
+  const int* v_idx;
+  __nv_bfloat16* out;             // [S*Nq][ldo], head h at columns h*d
+  int ldo;
+  // ---- cross-attention only
+  const int* unit_s0;             // per work unit: first sample
+  const int* unit_s1;             // second sample (P2P target) or -1
+  const int* unit_img;            // image index for the edit tables
+  const int* ctx_idx;             // per sample: index into the cached text K/V
+  const int* mapper;              // [img][80]      refine gather index (clamped to [0,77))
+  const float* c_base;            // [img][80]      coefficient on mapped source prob (already includes alpha_words[step])
+  const float* c_tar;             // [img][80]      coefficient on the target's own prob
+  const float* replace_m;         // [img][77][80]  replacement matrix or null
+  const int* is_replace;          // [img]
+  float* blend_acc;               // [img][2][n_blend_layers][H][Nq] fp32 accumulators or null
+  const float* blend_alpha;       // [img][2][80]
+  int blend_layer, n_blend_layers;
+};
+
+HEDIT_DEVICE float ex2f(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// byte offset of (row, 16-byte unit u) inside a [rows][64 bf16] 128B-swizzled tile
+HEDIT_DEVICE uint32_t sw128_off(int row, int unit) { return uint32_t(row) * 128u + uint32_t((unit ^ (row & 7)) << 4); }
+
+template <int DCH, int BKV>
+struct SelfAttnCfg {
+  static constexpr int KSTAGES = 2;
+  static constexpr int PCH = (BKV + 63) / 64;
+  static constexpr uint32_t Q_BYTES = DCH * 128 * 128;
+  static constexpr uint32_t KV_BYTES = DCH * BKV * 128;         // one K (or V) block
+  static constexpr uint32_t P_BYTES = PCH * 128 * 128;
+  static constexpr uint32_t SMEM_BYTES = Q_BYTES + 2 * KSTAGES * KV_BYTES + P_BYTES + 128;   // + barriers
+  static constexpr uint32_t O_COL = (BKV <= 64) ? 64 : 128;     // S at [0,BKV), O at [O_COL, O_COL+DK)
+  static constexpr uint32_t TMEM_COLS = 256;
+  static_assert(O_COL + DCH * 64 <= 256 || (DCH == 3 && O_COL + 160 <= 256), "TMEM budget");
+};
+
+template <int DCH, int BKV>
+__global__ void __launch_bounds__(192) self_attn_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = SelfAttnCfg<DCH, BKV>;
+  constexpr int KSTAGES = Cfg::KSTAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();     // 128B-swizzle tiles need 1024-byte alignment
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + KSTAGES * Cfg::KV_BYTES;
+  uint8_t* sP = sV + KSTAGES * Cfg::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_full = bars;               // 1
+  uint64_t* k_full = bars + 1;           // KSTAGES
+  uint64_t* v_full = k_full + KSTAGES;   // KSTAGES
+  uint64_t* kv_empty = v_full + KSTAGES; // KSTAGES
+  uint64_t* s_full = kv_empty + KSTAGES; // 1
+  uint64_t* p_full = s_full + 1;         // 1 (4 arrivals)
+  uint64_t* o_full = p_full + 1;         // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, s = blockIdx.z;
+  const int sq = p.q_idx ? p.q_idx[s] : s;
+  const int sk = p.k_idx ? p.k_idx[s] : s;
+  const int sv = p.v_idx ? p.v_idx[s] : s;
+  const int nblk = (p.Nkv + BKV - 1) / BKV;
+  const int DK = (p.d + 15) & ~15;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + Cfg::O_COL;
+
+  if (warp == 5) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + c * 16384, &p.tmQ, q_full, c * 64, h, q0, sq);
+      int st = 0; uint32_t ph = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sK + st * Cfg::KV_BYTES + c * BKV * 128, &p.tmK, &k_full[st], c * 64, h, j * BKV, sk);
+        mbar_expect_tx(&v_full[st], Cfg::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sV + st * Cfg::KV_BYTES + c * BKV * 128, &p.tmV, &v_full[st], c * 64, h, j * BKV, sv);
+        if (++st == KSTAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, DK, 0, 1);     // B = V is MN-major (d contiguous)
+      const int ksteps_s = DK >> 4;
+      mbar_wait(q_full, 0);
+      int st = 0; uint32_t ph = 0;
+      for (int j = 0; j < nblk; ++j) {
+        // S_j = Q K_j^T
+        mbar_wait(&k_full[st], ph);
+        tc_fence_after();
+        const uint32_t kb = smem_u32(sK + st * Cfg::KV_BYTES);
+        for (int k = 0; k < ksteps_s; ++k) {
+          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sQ) + (k >> 2) * 16384) + 2 * (k & 3);
+          const uint64_t db = umma_desc_kmajor_sw128(kb + (k >> 2) * (BKV * 128)) + 2 * (k & 3);
+          umma_f16_ss(tS, da, db, idesc_s, k != 0);
+        }
+        umma_commit(s_full);
+        // O += P_j V_j  (after the softmax threads have published P_j and rescaled O)
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[st], ph);
+        tc_fence_after();
+        const uint32_t vb = smem_u32(sV + st * Cfg::KV_BYTES);
+        const int kv_valid = min(BKV, p.Nkv - j * BKV);
+        const int ksteps_o = (kv_valid + 15) >> 4;               // P columns beyond Nkv are zero
+        for (int k = 0; k < ksteps_o; ++k) {
+          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sP) + (k >> 2) * 16384) + 2 * (k & 3);
+          const uint64_t db = umma_smem_desc(vb + k * 2048, BKV * 128, 1024);
+          umma_f16_ss(tO, da, db, idesc_o, (j | k) != 0);
+        }
+        umma_commit(&kv_empty[st]);
+        if (j == nblk - 1) umma_commit(o_full);
+        if (++st == KSTAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax / correction / output (warps 0..3)
+    const int r = threadIdx.x;                       // query row inside the tile == TMEM lane
+    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kv_valid = min(BKV, p.Nkv - j * BKV);
+      // pass 1: block row max
+      float bmax = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        if (c >= kv_valid) break;
+        uint32_t raw[32];
+        tmem_ld32(tS + lane_sel + c, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < kv_valid) bmax = fmaxf(bmax, __uint_as_float(raw[i]));
+      }
+      bmax *= p.scale_log2;
+      // lazy rescale: keep the old reference max unless the new one exceeds it by > 2^8
+      float alpha = 1.f;
+      bool bump = false;
+      if (j == 0) {
+        m_used = bmax;
+      } else if (bmax > m_used + 8.f) {
+        alpha = ex2f(m_used - bmax);
+        m_used = bmax;
+        l *= alpha;
+        bump = true;
+      }
+      if (__any_sync(0xffffffffu, bump)) {            // previous P V has completed (s_full tracks all prior MMAs)
+#pragma unroll 1
+        for (int c = 0; c < DK; c += 16) {
+          uint32_t o[16];
+          tmem_ld16(tO + lane_sel + c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tO + lane_sel + c, o);
+        }
+        tmem_st_wait();
+      }
+      // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V)
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t pk[16];
+        if (c < kv_valid) {
+          uint32_t raw[32];
+          tmem_ld32(tS + lane_sel + c, raw);
+          tmem_ld_wait();
+          float e[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            e[i] = (c + i < kv_valid) ? ex2f(__uint_as_float(raw[i]) * p.scale_log2 - m_used) : 0.f;
+            l += e[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        }
+        uint8_t* tile = sP + (c >> 6) * 16384;
+        const int u0 = (c & 63) >> 3;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(tile + sw128_off(r, u0 + u)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- output: O / l
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int row = q0 + r;
+#pragma unroll 1
+    for (int c = 0; c < DK; c += 16) {
+      uint32_t o[16];
+      tmem_ld16(tO + lane_sel + c, o);
+      tmem_ld_wait();
+      if (row < p.Nq) {
+        __nv_bfloat16* dst = p.out + (size_t(s) * p.Nq + row) * p.ldo + h * p.d + c;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c + g * 8 < p.d) {
+            const int b = g * 8;
+            *reinterpret_cast<uint4*>(dst + b) = make_uint4(
+                pack_bf16x2(__uint_as_float(o[b]) * inv, __uint_as_float(o[b + 1]) * inv),
+                pack_bf16x2(__uint_as_float(o[b + 2]) * inv, __uint_as_float(o[b + 3]) * inv),
+                pack_bf16x2(__uint_as_float(o[b + 4]) * inv, __uint_as_float(o[b + 5]) * inv),
+                pack_bf16x2(__uint_as_float(o[b + 6]) * inv, __uint_as_float(o[b + 7]) * inv));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ======================================================================================================= cross
+template <int DCH>
+struct CrossAttnCfg {
+  static constexpr int BKV = 80;                                  // 77 text tokens padded to a multiple of 16
+  static constexpr uint32_t Q_BYTES = DCH * 128 * 128;
+  static constexpr uint32_t KV_BYTES = DCH * BKV * 128;
+  static constexpr uint32_t P_BYTES = 2 * 128 * 128;
+  static constexpr uint32_t PB_BYTES = BKV * 128 * 4;             // fp32 source probabilities [col][row]
+  static constexpr uint32_t SMEM_BYTES = Q_BYTES + 2 * KV_BYTES + P_BYTES + PB_BYTES + 128;   // + barriers
+  static constexpr uint32_t TMEM_COLS = (DCH == 3) ? 512 : 256;     // S at [0,80), O at [128, 128+DK)
+};
+
+template <int DCH>
+__global__ void __launch_bounds__(192) cross_attn_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = CrossAttnCfg<DCH>;
+  constexpr int BKV = Cfg::BKV;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();     // 128B-swizzle tiles need 1024-byte alignment
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + Cfg::KV_BYTES;
+  uint8_t* sP = sV + Cfg::KV_BYTES;
+  float* sPB = reinterpret_cast<float*>(sP + Cfg::P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPB) + Cfg::PB_BYTES);
+  uint64_t* ld_full = bars;      // Q,K,V landed
+  uint64_t* s_full = bars + 1;
+  uint64_t* p_full = bars + 2;   // 4 arrivals
+  uint64_t* o_full = bars + 3;
+  uint64_t* o_read = bars + 4;   // 4 arrivals: outputs read, smem/TMEM reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, unit = blockIdx.z;
+  const int s0 = p.unit_s0[unit];
+  const int s1 = p.unit_s1[unit];
+  const int nph = (s1 >= 0) ? 2 : 1;
+  const int img = p.unit_img[unit];
+  const int DK = (p.d + 15) & ~15;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
+    mbar_init(ld_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(o_read, 4);
+    fence_mbar_init();
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      for (int ph = 0; ph < nph; ++ph) {
+        const int s = ph ? s1 : s0;
+        const int ctx = p.ctx_idx[s];
+        if (ph) mbar_wait(o_read, 0);                 // phase-0 consumers done with Q/K/V smem
+        mbar_expect_tx(ld_full, Cfg::Q_BYTES + 2 * Cfg::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) {
+          tma_load_4d(sQ + c * 16384, &p.tmQ, ld_full, c * 64, h, q0, s);
+          tma_load_4d(sK + c * BKV * 128, &p.tmK, ld_full, c * 64, h, 0, ctx);
+          tma_load_4d(sV + c * BKV * 128, &p.tmV, ld_full, c * 64, h, 0, ctx);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, DK, 0, 1);
+      for (int ph = 0; ph < nph; ++ph) {
+        mbar_wait(ld_full, ph);
+        tc_fence_after();
+        for (int k = 0; k < (DK >> 4); ++k) {
+          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sQ) + (k >> 2) * 16384) + 2 * (k & 3);
+          const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sK) + (k >> 2) * (BKV * 128)) + 2 * (k & 3);
+          umma_f16_ss(tS, da, db, idesc_s, k != 0);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_full, ph);
+        tc_fence_after();
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sP) + (k >> 2) * 16384) + 2 * (k & 3);
+          const uint64_t db = umma_smem_desc(smem_u32(sV) + k * 2048, BKV * 128, 1024);
+          umma_f16_ss(tO, da, db, idesc_o, k != 0);
+        }
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    const int r = threadIdx.x;
+    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    const int row = q0 + r;
+    const int NKV = p.Nkv;                            // 77
+    for (int ph = 0; ph < nph; ++ph) {
+      const int s = ph ? s1 : s0;
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      // pass 1: max, pass 2: sum of exp
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 16) {
+        uint32_t raw[16];
+        tmem_ld16(tS + lane_sel + c, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c + i < NKV) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      }
+      mx *= p.scale_log2;
+      float l = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 16) {
+        uint32_t raw[16];
+        tmem_ld16(tS + lane_sel + c, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c + i < NKV) l += ex2f(__uint_as_float(raw[i]) * p.scale_log2 - mx);
+      }
+      const float inv = 1.f / l;
+      const bool edit = (ph == 1);
+      const bool do_blend = p.blend_acc != nullptr && row < p.Nq;
+      const float* bal = p.blend_alpha ? p.blend_alpha + (size_t(img) * 2 + ph) * BKV : nullptr;
+      float bsum = 0.f;
+      // pass 3: normalised probabilities (+ P2P edit for the target) -> bf16 P tile
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 16) {
+        uint32_t raw[16];
+        tmem_ld16(tS + lane_sel + c, raw);
+        tmem_ld_wait();
+        float pr[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int jc = c + i;
+          float v = (jc < NKV) ? ex2f(__uint_as_float(raw[i]) * p.scale_log2 - mx) * inv : 0.f;
+          if (edit && jc < NKV) {
+            float base;
+            if (p.is_replace && p.is_replace[img]) {
+              const float* M = p.replace_m + size_t(img) * 77 * BKV + jc;
+              base = 0.f;
+              for (int w = 0; w < 77; ++w) base = fmaf(sPB[w * 128 + r], M[w * BKV], base);
+            } else {
+              base = sPB[p.mapper[img * BKV + jc] * 128 + r];
+            }
+            v = base * p.c_base[img * BKV + jc] + v * p.c_tar[img * BKV + jc];
+          }
+          pr[i] = v;
+          if (bal && jc < NKV) bsum = fmaf(bal[jc], v, bsum);
+        }
+        if (nph == 2 && ph == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sPB[(c + i) * 128 + r] = pr[i];
+        }
+        uint8_t* tile = sP + (c >> 6) * 16384;
+        const int u0 = (c & 63) >> 3;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          *reinterpret_cast<uint4*>(tile + sw128_off(r, u0 + u)) =
+              make_uint4(pack_bf16x2(pr[8 * u], pr[8 * u + 1]), pack_bf16x2(pr[8 * u + 2], pr[8 * u + 3]),
+                         pack_bf16x2(pr[8 * u + 4], pr[8 * u + 5]), pack_bf16x2(pr[8 * u + 6], pr[8 * u + 7]));
+      }
+      if (do_blend && nph == 2) {
+        float* acc = p.blend_acc + (((size_t(img) * 2 + ph) * p.n_blend_layers + p.blend_layer) * p.H + h) * p.Nq + row;
+        *acc += bsum;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // ---- output
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < DK; c += 16) {
+        uint32_t o[16];
+        tmem_ld16(tO + lane_sel + c, o);
+        tmem_ld_wait();
+        if (row < p.Nq) {
+          __nv_bfloat16* dst = p.out + (size_t(s) * p.Nq + row) * p.ldo + h * p.d + c;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (c + g * 8 < p.d) {
+              const int b = g * 8;
+              *reinterpret_cast<uint4*>(dst + b) = make_uint4(
+                  pack_bf16x2(__uint_as_float(o[b]), __uint_as_float(o[b + 1])),
+                  pack_bf16x2(__uint_as_float(o[b + 2]), __uint_as_float(o[b + 3])),
+                  pack_bf16x2(__uint_as_float(o[b + 4]), __uint_as_float(o[b + 5])),
+                  pack_bf16x2(__uint_as_float(o[b + 6]), __uint_as_float(o[b + 7])));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_read);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+}  // namespace hedit

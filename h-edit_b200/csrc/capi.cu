@@ -1,0 +1,255 @@
+// extern "C" boundary (include/hedit_b200.h).  Plain pointers and sizes only.
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/hedit_b200.h"
+#include "elementwise.cuh"
+#include "engine.h"
+#include "tmap.h"
+
+namespace hedit {
+int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st);
+cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st);
+cudaError_t launch_self_attn(const AttnParams& a, int dch, int S, cudaStream_t st);
+cudaError_t launch_cross_attn(const AttnParams& a, int dch, int units, cudaStream_t st);
+}  // namespace hedit
+
+using namespace hedit;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m, int code = -1) { g_err = m; return code; }
+static int cuda_fail(cudaError_t e, const char* what) { return fail(std::string(what) + ": " + cudaGetErrorString(e)); }
+
+struct hedit_engine {
+  Engine* E;
+  int device;
+  int *d_ctx_idx = nullptr, *d_tidx = nullptr, *d_unit0 = nullptr, *d_unit1 = nullptr, *d_uimg = nullptr;
+  int cap = 0;
+};
+
+extern "C" {
+
+const char* hedit_last_error(void) { return g_err.c_str(); }
+
+int hedit_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+hedit_engine* hedit_engine_create(const hedit_unet_config* cfg, int max_samples, int max_contexts, int device) {
+  if (!cfg) { fail("null config"); return nullptr; }
+  if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor)); return nullptr; }
+  UNetCfg c;
+  c.in_ch = cfg->in_channels; c.out_ch = cfg->out_channels; c.sample = cfg->sample_size;
+  for (int i = 0; i < 4; ++i) c.boc[i] = cfg->block_out_channels[i];
+  c.layers = cfg->layers_per_block; c.heads = cfg->heads; c.ctx_dim = cfg->cross_attention_dim; c.groups = cfg->norm_groups; c.ctx_len = cfg->ctx_len;
+  if (c.in_ch != 4 || c.out_ch != 4 || c.layers != 2 || c.ctx_len != 77 || c.groups != 32) { fail("unsupported UNet config (need in/out 4, 2 layers per block, 77 tokens, 32 groups)"); return nullptr; }
+  for (int i = 0; i < 4; ++i)
+    if (c.boc[i] % 64 != 0 || (c.boc[i] / c.heads) % 8 != 0) { fail("block_out_channels must be multiples of 64 with head_dim % 8 == 0"); return nullptr; }
+  if (c.ctx_dim % 8 != 0) { fail("cross_attention_dim must be a multiple of 8"); return nullptr; }
+  hedit_engine* h = new hedit_engine();
+  h->device = device;
+  h->E = new Engine(c, max_samples, max_contexts);
+  if (!h->E->ok()) { fail(h->E->error()); delete h->E; delete h; return nullptr; }
+  h->cap = max_samples;
+  cudaMalloc(&h->d_ctx_idx, max_samples * sizeof(int)); cudaMalloc(&h->d_tidx, max_samples * sizeof(int));
+  cudaMalloc(&h->d_unit0, max_samples * sizeof(int)); cudaMalloc(&h->d_unit1, max_samples * sizeof(int)); cudaMalloc(&h->d_uimg, max_samples * sizeof(int));
+  return h;
+}
+
+void hedit_engine_destroy(hedit_engine* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_ctx_idx); cudaFree(h->d_tidx); cudaFree(h->d_unit0); cudaFree(h->d_unit1); cudaFree(h->d_uimg);
+  delete h->E;
+  delete h;
+}
+
+int hedit_engine_load_tensor(hedit_engine* h, const char* name, const float* data, const int64_t* dims, int ndim) {
+  if (!h) return fail("null engine");
+  cudaSetDevice(h->device);
+  const int r = h->E->load_tensor(name, data, dims, ndim, 0);
+  if (r) return fail(h->E->error(), r);
+  return 0;
+}
+
+int hedit_engine_finalize(hedit_engine* h) {
+  if (!h) return fail("null engine");
+  std::string missing;
+  const int r = h->E->finalize_weights(&missing);
+  if (r) return fail(h->E->error(), -1);
+  return 0;
+}
+
+double hedit_engine_flops_per_sample(hedit_engine* h) { return h ? h->E->flops_per_sample() : 0.0; }
+
+int hedit_unet_forward(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int S, float* eps, void* stream) {
+  if (!h) return fail("null engine");
+  cudaSetDevice(h->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Engine& E = *h->E;
+  if (S > h->cap) return fail("S exceeds max_samples");
+  // distinct timesteps -> table rows
+  std::vector<float> uniq; std::vector<int> tidx(S), ident(S), minus1(S, -1), zeros(S, 0);
+  for (int s = 0; s < S; ++s) {
+    int j = -1;
+    for (size_t k = 0; k < uniq.size(); ++k) if (uniq[k] == timesteps[s]) j = int(k);
+    if (j < 0) { uniq.push_back(timesteps[s]); j = int(uniq.size()) - 1; }
+    tidx[s] = j; ident[s] = s;
+  }
+  if (E.set_timesteps(uniq.data(), int(uniq.size()), st)) return fail(E.error());
+  if (E.set_contexts(ctx, S, st)) return fail(E.error());
+  cudaMemcpyAsync(h->d_tidx, tidx.data(), S * sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(h->d_ctx_idx, ident.data(), S * sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(h->d_unit0, ident.data(), S * sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(h->d_unit1, minus1.data(), S * sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(h->d_uimg, zeros.data(), S * sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);     // host vectors go out of scope
+  CallCtrl cc;
+  cc.ctx_idx = h->d_ctx_idx; cc.time_idx = h->d_tidx; cc.unit_s0 = h->d_unit0; cc.unit_s1 = h->d_unit1; cc.unit_img = h->d_uimg; cc.n_units = S;
+  const long r = E.forward(x, eps, S, cc, st);
+  if (r < 0) return fail(E.error());
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "unet forward");
+  return int(r);
+}
+
+int hedit_edit_p2p(hedit_engine* h, hedit_edit_args* args, void* stream) {
+  if (!h || !args) return fail("null engine/args");
+  cudaSetDevice(h->device);
+  const int r = run_edit(*h->E, *args, reinterpret_cast<cudaStream_t>(stream));
+  if (r) {
+    cudaError_t e = cudaGetLastError();
+    return fail(h->E->error().empty() ? std::string("edit failed: ") + cudaGetErrorString(e) : h->E->error());
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ single operators
+static int pick_bn_op(int M, int N) {
+  auto cost = [&](int bn) { const long tiles = long((M + 127) / 128) * ((N + bn - 1) / bn); return double((tiles + 147) / 148) * bn; };
+  return cost(256) < cost(160) ? 256 : 160;
+}
+
+int hedit_op_linear(const void* A, const void* W, const float* bias, const float* residual, float* out_f32, void* out_bf16, int M, int N,
+                    int K, void* stream) {
+  GemmParams g; memset(&g, 0, sizeof g);
+  const int bn = pick_bn_op(M, N);
+  g.M = M; g.N = N; g.num_kb = (K + 63) / 64; g.a_mode = A_LINEAR;
+  uint64_t da[2] = {uint64_t(K), uint64_t(M)}, sa[1] = {uint64_t(K) * 2}; uint32_t ba[2] = {64, 128};
+  uint64_t db[2] = {uint64_t(K), uint64_t(N)}, sb[1] = {uint64_t(K) * 2}; uint32_t bb[2] = {64, uint32_t(bn)};
+  if (!make_tmap_bf16(&g.tmA, A, 2, da, sa, ba) || !make_tmap_bf16(&g.tmB, W, 2, db, sb, bb)) return fail("tensor map encode failed");
+  g.ep.bias = bias; g.ep.residual = residual; g.ep.ldr = N; g.ep.out_f32 = out_f32; g.ep.ldo = N;
+  g.ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); g.ep.ldob = N; g.ep.rows_per_group = 1;
+  cudaError_t e = launch_gemm(g, bn, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "linear launch");
+  return 0;
+}
+
+int hedit_op_conv3x3(const void* x, const void* w, const float* bias, float* out, int S, int Hin, int Win, int C, int Cout, int stride,
+                     void* stream) {
+  GemmParams g; memset(&g, 0, sizeof g);
+  const int H = Hin / stride, Wd = Win / stride, M = S * H * Wd;
+  const int bn = pick_bn_op(M, Cout);
+  if (Wd > 128 || 128 % Wd != 0 || C % 64 != 0) return fail("conv geometry unsupported");
+  const int BH = std::min(H, 128 / Wd), BS = 128 / (Wd * BH);
+  if (H % BH) return fail("conv geometry unsupported (H)");
+  g.M = M; g.N = Cout; g.num_kb = 9 * C / 64; g.conv_W = Wd; g.conv_H = H; g.conv_cin = C; g.cin_blocks = C / 64;
+  bool ok;
+  if (stride == 1) {
+    g.a_mode = A_CONV3X3;
+    uint64_t d[4] = {uint64_t(C), uint64_t(Wd), uint64_t(H), uint64_t(S)}, s[3] = {uint64_t(C) * 2, uint64_t(Wd) * C * 2, uint64_t(H) * Wd * C * 2};
+    uint32_t b[4] = {64, uint32_t(Wd), uint32_t(BH), uint32_t(BS)};
+    ok = make_tmap_bf16(&g.tmA, x, 4, d, s, b);
+  } else {
+    g.a_mode = A_CONV3X3S2;
+    uint64_t d[5] = {uint64_t(2 * C), uint64_t(Wd), 2, uint64_t(H), uint64_t(S)};
+    uint64_t s[4] = {uint64_t(2 * C) * 2, uint64_t(Win) * C * 2, uint64_t(2) * Win * C * 2, uint64_t(Hin) * Win * C * 2};
+    uint32_t b[5] = {64, uint32_t(Wd), 1, uint32_t(BH), uint32_t(BS)};
+    ok = make_tmap_bf16(&g.tmA, x, 5, d, s, b);
+  }
+  uint64_t db[2] = {uint64_t(9 * C), uint64_t(Cout)}, sb[1] = {uint64_t(9 * C) * 2}; uint32_t bb[2] = {64, uint32_t(bn)};
+  if (!ok || !make_tmap_bf16(&g.tmB, w, 2, db, sb, bb)) return fail("tensor map encode failed");
+  g.ep.bias = bias; g.ep.out_f32 = out; g.ep.ldo = Cout; g.ep.rows_per_group = 1;
+  cudaError_t e = launch_gemm(g, bn, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "conv launch");
+  return 0;
+}
+
+static bool attn_maps(AttnParams& a, const void* q, int ldq, int Nq, int Sq, const void* k, const void* v, int ldkv, int Nkv, int Skv, int H,
+                      int d, int bkv) {
+  auto mk = [&](CUtensorMap* m, const void* base, int ld, int N, int S, int rows) {
+    uint64_t dims[4] = {uint64_t(d), uint64_t(H), uint64_t(N), uint64_t(S)};
+    uint64_t str[3] = {uint64_t(d) * 2, uint64_t(ld) * 2, uint64_t(N) * ld * 2};
+    uint32_t box[4] = {64, 1, uint32_t(rows), 1};
+    return make_tmap_bf16(m, base, 4, dims, str, box);
+  };
+  return mk(&a.tmQ, q, ldq, Nq, Sq, 128) && mk(&a.tmK, k, ldkv, Nkv, Skv, bkv) && mk(&a.tmV, v, ldkv, Nkv, Skv, bkv);
+}
+
+int hedit_op_self_attention(const void* q, const void* k, const void* v, int ldq, int ldkv, int S, int Nq, int Nkv, int H, int d,
+                            const int32_t* q_idx, const int32_t* k_idx, const int32_t* v_idx, void* out, void* stream) {
+  if (d % 8 || d > 192) return fail("head dim must be a multiple of 8 and <= 192");
+  AttnParams a; memset(&a, 0, sizeof a);
+  const int dch = d <= 64 ? 1 : (d <= 128 ? 2 : 3), bkv = d <= 128 ? 128 : 64;
+  if (!attn_maps(a, q, ldq, Nq, S, k, v, ldkv, Nkv, S, H, d, bkv)) return fail("tensor map encode failed");
+  a.H = H; a.d = d; a.Nq = Nq; a.Nkv = Nkv; a.scale_log2 = float(1.4426950408889634 / sqrt(double(d)));
+  a.q_idx = q_idx; a.k_idx = k_idx; a.v_idx = v_idx; a.out = reinterpret_cast<__nv_bfloat16*>(out); a.ldo = H * d;
+  cudaError_t e = launch_self_attn(a, dch, S, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "self attention launch");
+  return 0;
+}
+
+int hedit_op_cross_attention_p2p(const void* q, const void* kv, int S, int n_ctx, int Nq, int H, int d, int n_units, const int32_t* unit_s0,
+                                 const int32_t* unit_s1, const int32_t* unit_img, const int32_t* ctx_idx, const int32_t* mapper,
+                                 const float* c_base, const float* c_tar, const float* replace_m, const int32_t* is_replace,
+                                 float* blend_acc, const float* blend_alpha, int blend_layer, int n_blend_layers, void* out, void* stream) {
+  if (d % 8 || d > 192) return fail("head dim must be a multiple of 8 and <= 192");
+  AttnParams a; memset(&a, 0, sizeof a);
+  const int C = H * d;
+  const int dch = d <= 64 ? 1 : (d <= 128 ? 2 : 3);
+  const __nv_bfloat16* kvp = reinterpret_cast<const __nv_bfloat16*>(kv);
+  if (!attn_maps(a, q, C, Nq, S, kvp, kvp + C, 2 * C, 77, n_ctx, H, d, 80)) return fail("tensor map encode failed");
+  a.H = H; a.d = d; a.Nq = Nq; a.Nkv = 77; a.scale_log2 = float(1.4426950408889634 / sqrt(double(d)));
+  a.out = reinterpret_cast<__nv_bfloat16*>(out); a.ldo = C;
+  a.unit_s0 = unit_s0; a.unit_s1 = unit_s1; a.unit_img = unit_img; a.ctx_idx = ctx_idx; a.mapper = mapper; a.c_base = c_base; a.c_tar = c_tar;
+  a.replace_m = replace_m; a.is_replace = is_replace; a.blend_acc = blend_acc; a.blend_alpha = blend_alpha; a.blend_layer = blend_layer;
+  a.n_blend_layers = n_blend_layers;
+  cudaError_t e = launch_cross_attn(a, dch, n_units, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "cross attention launch");
+  return 0;
+}
+
+int hedit_op_group_norm(const float* x, const float* gamma, const float* beta, void* out, int S, int HW, int C, int groups, float eps, int silu,
+                        void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (groups > 32 || C % groups || (C / groups) % 2 || C % 4) return fail("group norm geometry unsupported");
+  const int chunk = std::max(16, HW / 64), nch = (HW + chunk - 1) / chunk;
+  float2* partial = nullptr;
+  if (cudaMalloc(&partial, size_t(S) * nch * groups * sizeof(float2)) != cudaSuccess) return fail("cudaMalloc");
+  GNStatsParams sp{x, nullptr, C, 0, HW, groups, chunk, partial};
+  gn_stats_kernel<<<dim3(nch, S), std::min(640, ((C / 2 + 31) / 32) * 32), 0, st>>>(sp);
+  GNApplyParams ap{x, nullptr, C, 0, HW, groups, 16, nch, partial, gamma, beta, eps, silu, reinterpret_cast<__nv_bfloat16*>(out), nullptr};
+  gn_apply_kernel<<<dim3((HW + 15) / 16, S), 256, 2 * C * sizeof(float), st>>>(ap);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(partial);
+  if (e != cudaSuccess) return cuda_fail(e, "group norm");
+  return 0;
+}
+
+int hedit_op_layer_norm(const float* x, const float* gamma, const float* beta, void* out, int rows, int C, float eps, void* stream) {
+  if (C % 64 || C > 2048) return fail("layer norm needs C % 64 == 0 and C <= 2048");
+  layernorm_kernel<32><<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), rows, C, eps);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "layer norm launch");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+// HBM-bound glue kernels of the UNet (coalesced, vectorised; fp32 residual stream in, bf16 GEMM operands out).
+// Activations are NHWC ("tokens x channels") everywhere inside the engine.
+#pragma once
+#include "ptx.cuh"
+
+namespace hedit {
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// Pass 1: per (sample, pixel-chunk, group) partial sums.  Thread <-> fixed channel pair, so loads are coalesced and a
+// thread's group never changes.  Input may be the channel-concatenation of two tensors (UNet skip connections).
+struct GNStatsParams {
+  const float* x1; const float* x2;   // [S][HW][C1], [S][HW][C2] (x2 may be null)
+  int C1, C2, HW, groups, chunk;      // chunk = pixels per CTA
+  float2* partial;                    // [S][nchunks][groups] (sum, sumsq)
+};
+
+static __global__ void gn_stats_kernel(const GNStatsParams p) {
+  __shared__ float ssum[32], ssq[32];
+  const int C = p.C1 + p.C2, half = C >> 1, cpg = C / p.groups;
+  const int s = blockIdx.y, ch = blockIdx.x, nch = gridDim.x;
+  if (threadIdx.x < 32) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int p0 = ch * p.chunk, p1 = min(p.HW, p0 + p.chunk);
+  for (int v = threadIdx.x; v < half; v += blockDim.x) {
+    const int c = 2 * v;
+    const float* base; int ld, cc;
+    if (c < p.C1) { base = p.x1 + size_t(s) * p.HW * p.C1; ld = p.C1; cc = c; }
+    else { base = p.x2 + size_t(s) * p.HW * p.C2; ld = p.C2; cc = c - p.C1; }
+    float a = 0.f, b = 0.f;
+#pragma unroll 4
+    for (int px = p0; px < p1; ++px) {
+      const float2 t = *reinterpret_cast<const float2*>(base + size_t(px) * ld + cc);
+      a += t.x + t.y;
+      b += t.x * t.x + t.y * t.y;
+    }
+    const int g = c / cpg;
+    atomicAdd(&ssum[g], a);
+    atomicAdd(&ssq[g], b);
+  }
+  __syncthreads();
+  if (threadIdx.x < p.groups)
+    p.partial[(size_t(s) * nch + ch) * p.groups + threadIdx.x] = make_float2(ssum[threadIdx.x], ssq[threadIdx.x]);
+}
+
+// Pass 2: finalise statistics (double combine), then y = [silu](x * a_c + b_c) -> bf16, optionally also the raw
+// bf16 copy of x (operand of the 1x1 shortcut conv).
+struct GNApplyParams {
+  const float* x1; const float* x2;
+  int C1, C2, HW, groups, chunk, nstat_chunks;
+  const float2* partial;
+  const float* gamma; const float* beta;
+  float eps; int silu;
+  __nv_bfloat16* out;      // [S][HW][C]
+  __nv_bfloat16* raw_out;  // [S][HW][C] or null
+};
+
+static __global__ void gn_apply_kernel(const GNApplyParams p) {
+  extern __shared__ float sm[];       // a[C], b[C]
+  __shared__ float smean[32], srstd[32];
+  const int C = p.C1 + p.C2, cpg = C / p.groups;
+  const int s = blockIdx.y;
+  float* sa = sm; float* sb = sm + C;
+  if (threadIdx.x < p.groups) {
+    double su = 0.0, sq = 0.0;
+    for (int k = 0; k < p.nstat_chunks; ++k) {
+      const float2 t = p.partial[(size_t(s) * p.nstat_chunks + k) * p.groups + threadIdx.x];
+      su += t.x; sq += t.y;
+    }
+    const double n = double(p.HW) * cpg;
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    smean[threadIdx.x] = float(mean);
+    srstd[threadIdx.x] = float(1.0 / sqrt(var + double(p.eps)));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float a = srstd[g] * p.gamma[c];
+    sa[c] = a;
+    sb[c] = p.beta[c] - smean[g] * a;
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * p.chunk, p1 = min(p.HW, p0 + p.chunk);
+  const int quads = C >> 2;
+  const int total = (p1 - p0) * quads;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int px = p0 + i / quads, c = (i % quads) << 2;
+    float4 t;
+    if (c < p.C1) t = *reinterpret_cast<const float4*>(p.x1 + (size_t(s) * p.HW + px) * p.C1 + c);
+    else t = *reinterpret_cast<const float4*>(p.x2 + (size_t(s) * p.HW + px) * p.C2 + (c - p.C1));
+    float y0 = t.x * sa[c] + sb[c], y1 = t.y * sa[c + 1] + sb[c + 1];
+    float y2 = t.z * sa[c + 2] + sb[c + 2], y3 = t.w * sa[c + 3] + sb[c + 3];
+    if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+    const size_t o = (size_t(s) * p.HW + px) * C + c;
+    *reinterpret_cast<uint2*>(p.out + o) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    if (p.raw_out) *reinterpret_cast<uint2*>(p.raw_out + o) = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// One warp per token row (C <= 2048, C % 64 == 0): row held in registers, two-pass mean / variance, bf16 out.
+template <int MAXV>   // MAXV float2 per lane
+static __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 __nv_bfloat16* __restrict__ out, int rows, int C, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nv = C >> 6;       // float2 per lane
+  const float* xr = x + size_t(row) * C;
+  float2 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k)
+    if (k < nv) { v[k] = *reinterpret_cast<const float2*>(xr + 2 * (lane + 32 * k)); s += v[k].x + v[k].y; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k)
+    if (k < nv) { const float a = v[k].x - mean, b = v[k].y - mean; q += a * a + b * b; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  __nv_bfloat16* orow = out + size_t(row) * C;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k)
+    if (k < nv) {
+      const int c = 2 * (lane + 32 * k);
+      const float2 g = *reinterpret_cast<const float2*>(gamma + c);
+      const float2 b = *reinterpret_cast<const float2*>(beta + c);
+      *reinterpret_cast<uint32_t*>(orow + c) = pack_bf16x2((v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ casts / resampling
+static __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n4) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
+    const float4 t = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+  }
+}
+
+// nearest 2x upsample, fp32 NHWC -> bf16 NHWC (operand of the following 3x3 conv)
+static __global__ void upsample2x_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int S, int H, int W, int C) {
+  const int quads = C >> 2;
+  const size_t total = size_t(S) * (2 * H) * (2 * W) * quads;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int cq = int(i % quads);
+    size_t r = i / quads;
+    const int ox = int(r % (2 * W)); r /= (2 * W);
+    const int oy = int(r % (2 * H));
+    const int s = int(r / (2 * H));
+    const float4 t = *reinterpret_cast<const float4*>(x + ((size_t(s) * H + (oy >> 1)) * W + (ox >> 1)) * C + 4 * cq);
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ conv_in / conv_out
+// conv_in: 3x3, Cin=4 (NCHW fp32 latent) -> C0 channels (NHWC fp32).  fp32 CUDA-core math (47 MMAC / sample).
+// grid (H, S); weights [C0][4][3][3] fp32.
+static __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                               float* __restrict__ y, int H, int W, int C0) {
+  extern __shared__ float sm[];
+  float* sw = sm;                       // [36][C0] (transposed for conflict-free reads)
+  float* sx = sm + 36 * C0;             // [4][3][W+2]
+  const int yrow = blockIdx.x, s = blockIdx.y;
+  for (int i = threadIdx.x; i < 36 * C0; i += blockDim.x) { const int co = i / 36, k = i % 36; sw[k * C0 + co] = w[i]; }
+  for (int i = threadIdx.x; i < 12 * (W + 2); i += blockDim.x) {
+    const int xx = i % (W + 2) - 1, r = (i / (W + 2)) % 3, ci = i / (3 * (W + 2));
+    const int yy = yrow + r - 1;
+    sx[i] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? x[((size_t(s) * 4 + ci) * H + yy) * W + xx] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < W * C0; i += blockDim.x) {
+    const int co = i % C0, xo = i / C0;
+    float acc = bias[co];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc = fmaf(sx[(ci * 3 + r) * (W + 2) + xo + k], sw[(ci * 9 + r * 3 + k) * C0 + co], acc);
+    y[((size_t(s) * H + yrow) * W + xo) * C0 + co] = acc;
+  }
+}
+
+// conv_out: 3x3, C0 -> 4 channels; input bf16 NHWC (already GroupNorm+SiLU'd), output fp32 NCHW (the latent layout of the
+// reference).  One warp per output pixel; weights [4][C0][3][3] fp32 re-laid as [tap][C0][4] in shared memory.
+static __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                float* __restrict__ y, int S, int H, int W, int C0) {
+  extern __shared__ float sm[];          // [9][C0][4]
+  for (int i = threadIdx.x; i < 36 * C0; i += blockDim.x) {
+    const int co = i / (9 * C0), ci = (i / 9) % C0, tap = i % 9;
+    sm[(tap * C0 + ci) * 4 + co] = w[i];
+  }
+  __syncthreads();
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const size_t npix = size_t(S) * H * W;
+  for (size_t pix = blockIdx.x * size_t(warps) + (threadIdx.x >> 5); pix < npix; pix += size_t(gridDim.x) * warps) {
+    const int xo = int(pix % W), yo = int((pix / W) % H), s = int(pix / (size_t(W) * H));
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = yo + tap / 3 - 1, xx = xo + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const __nv_bfloat16* xr = x + ((size_t(s) * H + yy) * W + xx) * C0;
+      for (int c = 2 * lane; c < C0; c += 64) {
+        const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(xr + c);
+        const float x0 = __low2float(t), x1 = __high2float(t);
+        const float4 w0 = *reinterpret_cast<const float4*>(&sm[(tap * C0 + c) * 4]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&sm[(tap * C0 + c + 1) * 4]);
+        a0 = fmaf(x0, w0.x, fmaf(x1, w1.x, a0)); a1 = fmaf(x0, w0.y, fmaf(x1, w1.y, a1));
+        a2 = fmaf(x0, w0.z, fmaf(x1, w1.z, a2)); a3 = fmaf(x0, w0.w, fmaf(x1, w1.w, a3));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+    if (lane < 4) {
+      const float v = (lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3) + bias[lane];
+      y[((size_t(s) * 4 + lane) * H + yo) * W + xo] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ small linear (time MLP)
+// out[r][n] = act_out( sum_k act_in(in[r][k]) * W[n][k] + b[n] ), rows <= 64.  One warp per output feature n.
+// in_mode: 0 = as is, 1 = SiLU, 2 = sinusoidal timestep embedding of in[r][0] (flip_sin_to_cos, freq shift 0; K = dim).
+static __global__ void small_linear_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ W, const float* __restrict__ b,
+                                    float* __restrict__ out, int ld_out, int rows, int N, int K, int in_mode, int out_silu) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* wr = W + size_t(n) * K;
+  for (int r = 0; r < rows; ++r) {
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      float a;
+      if (in_mode == 2) {
+        const int half = K >> 1;
+        const int f = (k < half) ? k : k - half;
+        const float ang = in[r * ld_in] * expf(-9.210340371976184f * float(f) / float(half));
+        a = (k < half) ? cosf(ang) : sinf(ang);
+      } else {
+        a = in[size_t(r) * ld_in + k];
+        if (in_mode == 1) a = silu_f(a);
+      }
+      acc = fmaf(a, wr[k], acc);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float v = acc + (b ? b[n] : 0.f);
+      if (out_silu) v = silu_f(v);
+      out[size_t(r) * ld_out + n] = v;
+    }
+  }
+}
+
+// rows of a table gathered by index: out[r][:] = table[idx[r]][:]
+static __global__ void gather_rows_kernel(const float* __restrict__ table, const int* __restrict__ idx, float* __restrict__ out, int ld4) {
+  const int r = blockIdx.y;
+  const float4* src = reinterpret_cast<const float4*>(table) + size_t(idx[r]) * ld4;
+  float4* dst = reinterpret_cast<float4*>(out) + size_t(r) * ld4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ld4; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace hedit

@@ -1,0 +1,769 @@
+// Engine implementation: weight ingestion (reference state-dict names -> engine layouts), plan construction for the
+// SD-1.x UNet (diffusers-0.18 topology, see oracle/sd_unet.py for the restated reference), and the forward launcher.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "elementwise.cuh"
+#include "tmap.h"
+
+namespace hedit {
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char buf_[512];                                                                              \
+      snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      err_ = buf_;                                                                                 \
+      return -1;                                                                                   \
+    }                                                                                              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ weight conversion
+__global__ void cvt_rows_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int rows, int K, int geglu, int half_rows) {
+  const size_t total = size_t(rows) * K;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int r = int(i / K), k = int(i % K);
+    int sr = r;
+    if (geglu) {  // dst rows: 32-row chunks = 16 value rows | their 16 gate rows
+      const int ch = r >> 5, j = r & 31;
+      sr = (j < 16) ? (ch * 16 + j) : (half_rows + ch * 16 + (j - 16));
+    }
+    dst[i] = __float2bfloat16(src[size_t(sr) * K + k]);
+  }
+}
+__global__ void perm_geglu_vec_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int half_rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int ch = r >> 5, j = r & 31;
+  dst[r] = src[(j < 16) ? (ch * 16 + j) : (half_rows + ch * 16 + (j - 16))];
+}
+// [O][I][3][3] fp32 -> [O][3][3][I] bf16
+__global__ void cvt_conv3_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I) {
+  const size_t total = size_t(O) * I * 9;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int ci = int(i % I);
+    const int tap = int((i / I) % 9);
+    const int o = int(i / (size_t(I) * 9));
+    dst[i] = __float2bfloat16(src[(size_t(o) * I + ci) * 9 + tap]);
+  }
+}
+
+template <typename T>
+T* Engine::dalloc(size_t n) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) {
+    err_ = "cudaMalloc failed";
+    return nullptr;
+  }
+  owned_.push_back(p);
+  return reinterpret_cast<T*>(p);
+}
+void* Engine::scratch_alloc(size_t bytes) { return dalloc<uint8_t>(bytes); }
+
+void Engine::reg(const std::string& name, WeightSlot::Kind k, void* dst, size_t off, std::vector<int64_t> shape) {
+  WeightSlot s;
+  s.kind = k; s.dst = dst; s.dst_off_elems = off; s.shape = std::move(shape);
+  slots_[name] = s;
+}
+
+Engine::Engine(const UNetCfg& cfg, int max_samples, int max_ctx) : cfg_(cfg), maxS_(max_samples), maxCtx_(max_ctx) {
+  const int temb = cfg.boc[0] * 4;
+  const int G = cfg.groups;
+  (void)G;
+  // ---- module structure in forward order
+  struct RSpec { std::string name; int cin, cout; };
+  struct TSpec { std::string name; int C; int tokens; };
+  std::vector<RSpec> rs; std::vector<TSpec> ts;
+  int res = cfg.sample;
+  int cout = cfg.boc[0];
+  std::vector<int> skip_ch = {cfg.boc[0]};
+  for (int i = 0; i < 4; ++i) {
+    const int cin = cout; cout = cfg.boc[i];
+    for (int l = 0; l < cfg.layers; ++l) {
+      rs.push_back({"down_blocks." + std::to_string(i) + ".resnets." + std::to_string(l), l == 0 ? cin : cout, cout});
+      if (i < 3) ts.push_back({"down_blocks." + std::to_string(i) + ".attentions." + std::to_string(l), cout, res * res});
+      skip_ch.push_back(cout);
+    }
+    if (i < 3) { skip_ch.push_back(cout); res /= 2; }
+  }
+  rs.push_back({"mid_block.resnets.0", cfg.boc[3], cfg.boc[3]});
+  ts.push_back({"mid_block.attentions.0", cfg.boc[3], res * res});
+  rs.push_back({"mid_block.resnets.1", cfg.boc[3], cfg.boc[3]});
+  int prev = cfg.boc[3];
+  for (int i = 0; i < 4; ++i) {
+    const int oc = cfg.boc[3 - i];
+    for (int l = 0; l < cfg.layers + 1; ++l) {
+      const int sk = skip_ch.back(); skip_ch.pop_back();
+      const int rin = (l == 0 ? prev : oc) + sk;
+      rs.push_back({"up_blocks." + std::to_string(i) + ".resnets." + std::to_string(l), rin, oc});
+      if (i > 0) ts.push_back({"up_blocks." + std::to_string(i) + ".attentions." + std::to_string(l), oc, res * res});
+    }
+    prev = oc;
+    if (i < 3) res *= 2;
+  }
+  // ---- allocate + register
+  conv_in_w_ = dalloc<float>(size_t(cfg.boc[0]) * cfg.in_ch * 9); conv_in_b_ = dalloc<float>(cfg.boc[0]);
+  reg("conv_in.weight", WeightSlot::F32_COPY, conv_in_w_, 0, {cfg.boc[0], cfg.in_ch, 3, 3});
+  reg("conv_in.bias", WeightSlot::F32_COPY, conv_in_b_, 0, {cfg.boc[0]});
+  t_w1_ = dalloc<float>(size_t(temb) * cfg.boc[0]); t_b1_ = dalloc<float>(temb);
+  t_w2_ = dalloc<float>(size_t(temb) * temb); t_b2_ = dalloc<float>(temb);
+  reg("time_embedding.linear_1.weight", WeightSlot::F32_COPY, t_w1_, 0, {temb, cfg.boc[0]});
+  reg("time_embedding.linear_1.bias", WeightSlot::F32_COPY, t_b1_, 0, {temb});
+  reg("time_embedding.linear_2.weight", WeightSlot::F32_COPY, t_w2_, 0, {temb, temb});
+  reg("time_embedding.linear_2.bias", WeightSlot::F32_COPY, t_b2_, 0, {temb});
+  tproj_total_ = 0;
+  for (auto& r : rs) tproj_total_ += r.cout;
+  tproj_w_ = dalloc<float>(size_t(tproj_total_) * temb); tproj_b_ = dalloc<float>(tproj_total_);
+  int toff = 0;
+  for (auto& r : rs) {
+    ResW w; w.cin = r.cin; w.cout = r.cout; w.temb_off = toff;
+    w.n1g = dalloc<float>(r.cin); w.n1b = dalloc<float>(r.cin); w.n2g = dalloc<float>(r.cout); w.n2b = dalloc<float>(r.cout);
+    w.b1 = dalloc<float>(r.cout); w.b2 = dalloc<float>(r.cout);
+    w.w1 = dalloc<bf16>(size_t(r.cout) * 9 * r.cin); w.w2 = dalloc<bf16>(size_t(r.cout) * 9 * r.cout);
+    reg(r.name + ".norm1.weight", WeightSlot::F32_COPY, w.n1g, 0, {r.cin});
+    reg(r.name + ".norm1.bias", WeightSlot::F32_COPY, w.n1b, 0, {r.cin});
+    reg(r.name + ".conv1.weight", WeightSlot::BF16_CONV3, w.w1, 0, {r.cout, r.cin, 3, 3});
+    reg(r.name + ".conv1.bias", WeightSlot::F32_COPY, w.b1, 0, {r.cout});
+    reg(r.name + ".time_emb_proj.weight", WeightSlot::F32_COPY, tproj_w_, size_t(toff) * temb, {r.cout, temb});
+    reg(r.name + ".time_emb_proj.bias", WeightSlot::F32_COPY, tproj_b_, toff, {r.cout});
+    reg(r.name + ".norm2.weight", WeightSlot::F32_COPY, w.n2g, 0, {r.cout});
+    reg(r.name + ".norm2.bias", WeightSlot::F32_COPY, w.n2b, 0, {r.cout});
+    reg(r.name + ".conv2.weight", WeightSlot::BF16_CONV3, w.w2, 0, {r.cout, r.cout, 3, 3});
+    reg(r.name + ".conv2.bias", WeightSlot::F32_COPY, w.b2, 0, {r.cout});
+    if (r.cin != r.cout) {
+      w.wsc = dalloc<bf16>(size_t(r.cout) * r.cin); w.bsc = dalloc<float>(r.cout);
+      reg(r.name + ".conv_shortcut.weight", WeightSlot::BF16_ROWS, w.wsc, 0, {r.cout, r.cin, 1, 1});
+      reg(r.name + ".conv_shortcut.bias", WeightSlot::F32_COPY, w.bsc, 0, {r.cout});
+    }
+    toff += r.cout;
+    res_.push_back(w);
+  }
+  int ci = 0;
+  for (auto& t : ts) {
+    TfW w; w.C = t.C; w.cross_index = ci++;
+    const int C = t.C, D = cfg.ctx_dim;
+    auto f = [&](int n) { return dalloc<float>(n); };
+    w.gng = f(C); w.gnb = f(C); w.b_in = f(C); w.b_out = f(C);
+    w.ln1g = f(C); w.ln1b = f(C); w.ln2g = f(C); w.ln2b = f(C); w.ln3g = f(C); w.ln3b = f(C);
+    w.b_o1 = f(C); w.b_o2 = f(C); w.b_ff1 = f(8 * C); w.b_ff2 = f(C);
+    w.w_in = dalloc<bf16>(size_t(C) * C); w.w_out = dalloc<bf16>(size_t(C) * C);
+    w.w_qkv = dalloc<bf16>(size_t(3) * C * C); w.w_o1 = dalloc<bf16>(size_t(C) * C);
+    w.w_q2 = dalloc<bf16>(size_t(C) * C); w.w_kv2 = dalloc<bf16>(size_t(2) * C * D); w.w_o2 = dalloc<bf16>(size_t(C) * C);
+    w.w_ff1 = dalloc<bf16>(size_t(8) * C * C); w.w_ff2 = dalloc<bf16>(size_t(C) * 4 * C);
+    w.kv_cache = dalloc<bf16>(size_t(maxCtx_) * cfg.ctx_len * 2 * C);
+    const std::string P = t.name, B = t.name + ".transformer_blocks.0";
+    reg(P + ".norm.weight", WeightSlot::F32_COPY, w.gng, 0, {C});
+    reg(P + ".norm.bias", WeightSlot::F32_COPY, w.gnb, 0, {C});
+    reg(P + ".proj_in.weight", WeightSlot::BF16_ROWS, w.w_in, 0, {C, C, 1, 1});
+    reg(P + ".proj_in.bias", WeightSlot::F32_COPY, w.b_in, 0, {C});
+    reg(P + ".proj_out.weight", WeightSlot::BF16_ROWS, w.w_out, 0, {C, C, 1, 1});
+    reg(P + ".proj_out.bias", WeightSlot::F32_COPY, w.b_out, 0, {C});
+    reg(B + ".norm1.weight", WeightSlot::F32_COPY, w.ln1g, 0, {C}); reg(B + ".norm1.bias", WeightSlot::F32_COPY, w.ln1b, 0, {C});
+    reg(B + ".norm2.weight", WeightSlot::F32_COPY, w.ln2g, 0, {C}); reg(B + ".norm2.bias", WeightSlot::F32_COPY, w.ln2b, 0, {C});
+    reg(B + ".norm3.weight", WeightSlot::F32_COPY, w.ln3g, 0, {C}); reg(B + ".norm3.bias", WeightSlot::F32_COPY, w.ln3b, 0, {C});
+    reg(B + ".attn1.to_q.weight", WeightSlot::BF16_ROWS, w.w_qkv, 0, {C, C});
+    reg(B + ".attn1.to_k.weight", WeightSlot::BF16_ROWS, w.w_qkv, size_t(C) * C, {C, C});
+    reg(B + ".attn1.to_v.weight", WeightSlot::BF16_ROWS, w.w_qkv, size_t(2) * C * C, {C, C});
+    reg(B + ".attn1.to_out.0.weight", WeightSlot::BF16_ROWS, w.w_o1, 0, {C, C});
+    reg(B + ".attn1.to_out.0.bias", WeightSlot::F32_COPY, w.b_o1, 0, {C});
+    reg(B + ".attn2.to_q.weight", WeightSlot::BF16_ROWS, w.w_q2, 0, {C, C});
+    reg(B + ".attn2.to_k.weight", WeightSlot::BF16_ROWS, w.w_kv2, 0, {C, D});
+    reg(B + ".attn2.to_v.weight", WeightSlot::BF16_ROWS, w.w_kv2, size_t(C) * D, {C, D});
+    reg(B + ".attn2.to_out.0.weight", WeightSlot::BF16_ROWS, w.w_o2, 0, {C, C});
+    reg(B + ".attn2.to_out.0.bias", WeightSlot::F32_COPY, w.b_o2, 0, {C});
+    reg(B + ".ff.net.0.proj.weight", WeightSlot::BF16_GEGLU_ROWS, w.w_ff1, 0, {8 * C, C});
+    reg(B + ".ff.net.0.proj.bias", WeightSlot::F32_GEGLU_VEC, w.b_ff1, 0, {8 * C});
+    reg(B + ".ff.net.2.weight", WeightSlot::BF16_ROWS, w.w_ff2, 0, {C, 4 * C});
+    reg(B + ".ff.net.2.bias", WeightSlot::F32_COPY, w.b_ff2, 0, {C});
+    tfs_.push_back(w);
+    tf_tokens_.push_back(t.tokens);
+  }
+  for (int i = 0; i < 3; ++i) {
+    const int c = cfg.boc[i];
+    bf16* w = dalloc<bf16>(size_t(c) * 9 * c); float* b = dalloc<float>(c);
+    down_w_.push_back(w); down_b_.push_back(b);
+    reg("down_blocks." + std::to_string(i) + ".downsamplers.0.conv.weight", WeightSlot::BF16_CONV3, w, 0, {c, c, 3, 3});
+    reg("down_blocks." + std::to_string(i) + ".downsamplers.0.conv.bias", WeightSlot::F32_COPY, b, 0, {c});
+    const int cu = cfg.boc[3 - i];
+    bf16* wu = dalloc<bf16>(size_t(cu) * 9 * cu); float* bu = dalloc<float>(cu);
+    up_w_.push_back(wu); up_b_.push_back(bu);
+    reg("up_blocks." + std::to_string(i) + ".upsamplers.0.conv.weight", WeightSlot::BF16_CONV3, wu, 0, {cu, cu, 3, 3});
+    reg("up_blocks." + std::to_string(i) + ".upsamplers.0.conv.bias", WeightSlot::F32_COPY, bu, 0, {cu});
+  }
+  norm_out_g_ = dalloc<float>(cfg.boc[0]); norm_out_b_ = dalloc<float>(cfg.boc[0]);
+  conv_out_w_ = dalloc<float>(size_t(cfg.out_ch) * cfg.boc[0] * 9); conv_out_b_ = dalloc<float>(cfg.out_ch);
+  reg("conv_norm_out.weight", WeightSlot::F32_COPY, norm_out_g_, 0, {cfg.boc[0]});
+  reg("conv_norm_out.bias", WeightSlot::F32_COPY, norm_out_b_, 0, {cfg.boc[0]});
+  reg("conv_out.weight", WeightSlot::F32_COPY, conv_out_w_, 0, {cfg.out_ch, cfg.boc[0], 3, 3});
+  reg("conv_out.bias", WeightSlot::F32_COPY, conv_out_b_, 0, {cfg.out_ch});
+
+  temb_act_ = dalloc<float>(size_t(maxT_) * temb * 2);
+  temb_table_ = dalloc<float>(size_t(maxT_) * tproj_total_);
+  temb_rows_ = dalloc<float>(size_t(maxS_) * tproj_total_);
+  ts_dev_ = dalloc<float>(maxT_);
+  ctx_bf16_ = dalloc<bf16>(size_t(maxCtx_) * cfg.ctx_len * cfg.ctx_dim);
+  size_t mx = 0;
+  for (auto& kv : slots_) { size_t n = 1; for (auto d : kv.second.shape) n *= size_t(d); mx = std::max(mx, n); }
+  stage_elems_ = mx;
+  stage_ = dalloc<float>(mx);
+  // number of LocalBlend layers: cross-attention layers of the down/up path with 16x16 tokens
+  n_blend_layers_ = 0;
+  for (size_t i = 0; i < ts.size(); ++i)
+    if (ts[i].tokens == 256 && ts[i].name.rfind("mid_block", 0) != 0) ++n_blend_layers_;
+}
+
+Engine::~Engine() {
+  for (void* p : owned_) cudaFree(p);
+  if (arena_) cudaFree(arena_);
+}
+
+int Engine::load_tensor(const char* name, const float* src, const int64_t* dims, int ndim, cudaStream_t st) {
+  auto it = slots_.find(name);
+  if (it == slots_.end()) { err_ = std::string("unknown tensor ") + name; return -2; }
+  WeightSlot& s = it->second;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= size_t(dims[i]);
+  size_t want = 1;
+  for (auto d : s.shape) want *= size_t(d);
+  if (n != want) { err_ = std::string("shape mismatch for ") + name; return -3; }
+  CK(cudaMemcpyAsync(stage_, src, n * sizeof(float), cudaMemcpyDefault, st));
+  const int threads = 256;
+  const int blocks = int(std::min<size_t>((n + threads - 1) / threads, 4096));
+  switch (s.kind) {
+    case WeightSlot::F32_COPY:
+      CK(cudaMemcpyAsync(reinterpret_cast<float*>(s.dst) + s.dst_off_elems, stage_, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      break;
+    case WeightSlot::BF16_ROWS: {
+      const int rows = int(s.shape[0]); const int K = int(n / rows);
+      cvt_rows_bf16_kernel<<<blocks, threads, 0, st>>>(stage_, reinterpret_cast<bf16*>(s.dst) + s.dst_off_elems, rows, K, 0, 0);
+      break;
+    }
+    case WeightSlot::BF16_GEGLU_ROWS: {
+      const int rows = int(s.shape[0]); const int K = int(n / rows);
+      cvt_rows_bf16_kernel<<<blocks, threads, 0, st>>>(stage_, reinterpret_cast<bf16*>(s.dst), rows, K, 1, rows / 2);
+      break;
+    }
+    case WeightSlot::F32_GEGLU_VEC:
+      perm_geglu_vec_kernel<<<(int(n) + 255) / 256, 256, 0, st>>>(stage_, reinterpret_cast<float*>(s.dst), int(n), int(n) / 2);
+      break;
+    case WeightSlot::BF16_CONV3:
+      cvt_conv3_bf16_kernel<<<blocks, threads, 0, st>>>(stage_, reinterpret_cast<bf16*>(s.dst), int(s.shape[0]), int(s.shape[1]));
+      break;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));   // stage_ is reused by the next tensor
+  s.loaded = true;
+  return 0;
+}
+
+int Engine::finalize_weights(std::string* missing) {
+  int n = 0;
+  for (auto& kv : slots_)
+    if (!kv.second.loaded) { if (missing && n < 8) *missing += kv.first + " "; ++n; }
+  if (n) { err_ = "missing weights: " + (missing ? *missing : std::string("?")); return -n; }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM descriptors
+static int pick_bn(int M, int N) {
+  auto cost = [&](int bn) {
+    const long tiles = long((M + 127) / 128) * ((N + bn - 1) / bn);
+    return double((tiles + 147) / 148) * bn;
+  };
+  return cost(256) < cost(160) ? 256 : 160;
+}
+
+struct ConvGeom { int S, H, W, C; int stride; };   // H,W = OUTPUT dims; C = input channels
+
+static bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode, const ConvGeom* cg, const bf16* Wt, int M, int N,
+                      int Ktot, const GemmEpilogue& ep, std::string& err) {
+  memset(&g, 0, sizeof g);
+  bn = pick_bn(M, N);
+  g.M = M; g.N = N; g.a_mode = a_mode; g.ep = ep;
+  g.num_kb = (Ktot + 63) / 64;
+  bool ok = true;
+  if (a_mode == A_LINEAR) {
+    uint64_t dims[2] = {uint64_t(Ktot), uint64_t(M)}; uint64_t str[1] = {uint64_t(lda) * 2}; uint32_t box[2] = {64, 128};
+    ok = make_tmap_bf16(&g.tmA, A, 2, dims, str, box);
+  } else {
+    const int W = cg->W, H = cg->H, C = cg->C;
+    if (W > 128 || 128 % W != 0 || C % 64 != 0) { err = "conv geometry unsupported (need W | 128, Cin % 64 == 0)"; return false; }
+    const int BH = std::min(H, 128 / W);
+    const int BS = 128 / (W * BH);
+    if (H % BH != 0) { err = "conv geometry unsupported (H)"; return false; }
+    g.conv_W = W; g.conv_H = H; g.conv_cin = C; g.cin_blocks = C / 64;
+    if (a_mode == A_CONV3X3) {
+      uint64_t dims[4] = {uint64_t(C), uint64_t(W), uint64_t(H), uint64_t(cg->S)};
+      uint64_t str[3] = {uint64_t(C) * 2, uint64_t(W) * C * 2, uint64_t(H) * W * C * 2};
+      uint32_t box[4] = {64, uint32_t(W), uint32_t(BH), uint32_t(BS)};
+      ok = make_tmap_bf16(&g.tmA, A, 4, dims, str, box);
+    } else {
+      const int Win = 2 * W, Hin = 2 * H;
+      uint64_t dims[5] = {uint64_t(2 * C), uint64_t(W), 2, uint64_t(H), uint64_t(cg->S)};
+      uint64_t str[4] = {uint64_t(2 * C) * 2, uint64_t(Win) * C * 2, uint64_t(2) * Win * C * 2, uint64_t(Hin) * Win * C * 2};
+      uint32_t box[5] = {64, uint32_t(W), 1, uint32_t(BH), uint32_t(BS)};
+      ok = make_tmap_bf16(&g.tmA, A, 5, dims, str, box);
+    }
+  }
+  if (!ok) { err = "tensor map (A) encode failed"; return false; }
+  uint64_t dimsB[2] = {uint64_t(Ktot), uint64_t(N)}; uint64_t strB[1] = {uint64_t(Ktot) * 2}; uint32_t boxB[2] = {64, uint32_t(bn)};
+  if (!make_tmap_bf16(&g.tmB, Wt, 2, dimsB, strB, boxB)) { err = "tensor map (B) encode failed"; return false; }
+  return true;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
+  return g_num_sms;
+}
+
+cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<160>::SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::SMEM_BYTES);
+    attr_set = true;
+  }
+  const int tiles = ((g.M + 127) / 128) * ((g.N + bn - 1) / bn);
+  const int grid = std::min(tiles, num_sms());
+  if (bn == 256) gemm_bf16_tcgen05_kernel<256><<<grid, 192, GemmCfg<256>::SMEM_BYTES, st>>>(g);
+  else gemm_bf16_tcgen05_kernel<160><<<grid, 192, GemmCfg<160>::SMEM_BYTES, st>>>(g);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ attention descriptors
+static bool make_attn_maps(AttnParams& a, const bf16* q, int ldq, int Nq, int Sq, const bf16* k, const bf16* v, int ldkv, int Nkv,
+                           int Skv, int H, int d, int bkv, std::string& err) {
+  auto mk = [&](CUtensorMap* m, const bf16* base, int ld, int N, int S, int rows) {
+    uint64_t dims[4] = {uint64_t(d), uint64_t(H), uint64_t(N), uint64_t(S)};
+    uint64_t str[3] = {uint64_t(d) * 2, uint64_t(ld) * 2, uint64_t(N) * ld * 2};
+    uint32_t box[4] = {64, 1, uint32_t(rows), 1};
+    return make_tmap_bf16(m, base, 4, dims, str, box);
+  };
+  if (d % 8 != 0 || d > 192) { err = "head dim must be a multiple of 8 and <= 192"; return false; }
+  if (!mk(&a.tmQ, q, ldq, Nq, Sq, 128) || !mk(&a.tmK, k, ldkv, Nkv, Skv, bkv) || !mk(&a.tmV, v, ldkv, Nkv, Skv, bkv)) {
+    err = "tensor map (attention) encode failed";
+    return false;
+  }
+  return true;
+}
+
+template <int DCH, int BKV>
+static cudaError_t launch_self_t(const AttnParams& a, int S, cudaStream_t st) {
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(self_attn_kernel<DCH, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SelfAttnCfg<DCH, BKV>::SMEM_BYTES); set = true; }
+  dim3 grid((a.Nq + 127) / 128, a.H, S);
+  self_attn_kernel<DCH, BKV><<<grid, 192, SelfAttnCfg<DCH, BKV>::SMEM_BYTES, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_self_attn(const AttnParams& a, int dch, int S, cudaStream_t st) {
+  if (dch == 1) return launch_self_t<1, 128>(a, S, st);
+  if (dch == 2) return launch_self_t<2, 128>(a, S, st);
+  return launch_self_t<3, 64>(a, S, st);
+}
+template <int DCH>
+static cudaError_t launch_cross_t(const AttnParams& a, int units, cudaStream_t st) {
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(cross_attn_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, CrossAttnCfg<DCH>::SMEM_BYTES); set = true; }
+  dim3 grid((a.Nq + 127) / 128, a.H, units);
+  cross_attn_kernel<DCH><<<grid, 192, CrossAttnCfg<DCH>::SMEM_BYTES, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_cross_attn(const AttnParams& a, int dch, int units, cudaStream_t st) {
+  if (dch == 1) return launch_cross_t<1>(a, units, st);
+  if (dch == 2) return launch_cross_t<2>(a, units, st);
+  return launch_cross_t<3>(a, units, st);
+}
+static int dch_for(int d) { return d <= 64 ? 1 : (d <= 128 ? 2 : 3); }
+static int bkv_for(int d) { return d <= 128 ? 128 : 64; }
+
+// ------------------------------------------------------------------------------------------------ contexts / timesteps
+int Engine::set_contexts(const float* ctx, int n_ctx, cudaStream_t st) {
+  if (n_ctx > maxCtx_) { err_ = "too many contexts"; return -1; }
+  const size_t n = size_t(n_ctx) * cfg_.ctx_len * cfg_.ctx_dim;
+  if (n > stage_elems_) { err_ = "context batch exceeds staging buffer"; return -1; }
+  CK(cudaMemcpyAsync(stage_, ctx, n * sizeof(float), cudaMemcpyDefault, st));
+  cast_bf16_kernel<<<int(std::min<size_t>((n / 4 + 255) / 256, 2048)), 256, 0, st>>>(stage_, ctx_bf16_, n / 4);
+  CK(cudaGetLastError());
+  const int M = n_ctx * cfg_.ctx_len;
+  for (auto& t : tfs_) {
+    GemmParams g; int bn;
+    GemmEpilogue ep; memset(&ep, 0, sizeof ep);
+    ep.out_bf16 = t.kv_cache; ep.ldob = 2 * t.C; ep.rows_per_group = 1;
+    if (!make_gemm(g, bn, ctx_bf16_, cfg_.ctx_dim, A_LINEAR, nullptr, t.w_kv2, M, 2 * t.C, cfg_.ctx_dim, ep, err_)) return -1;
+    CK(launch_gemm(g, bn, st));
+  }
+  return 0;
+}
+
+int Engine::set_timesteps(const float* ts, int n, cudaStream_t st) {
+  if (n > maxT_) { err_ = "too many timesteps"; return -1; }
+  const int temb = cfg_.boc[0] * 4;
+  CK(cudaMemcpyAsync(ts_dev_, ts, n * sizeof(float), cudaMemcpyDefault, st));
+  float* a1 = temb_act_; float* a2 = temb_act_ + size_t(maxT_) * temb;
+  const int wpb = 8;
+  small_linear_kernel<<<(temb + wpb - 1) / wpb, wpb * 32, 0, st>>>(ts_dev_, 1, t_w1_, t_b1_, a1, temb, n, temb, cfg_.boc[0], 2, 1);
+  small_linear_kernel<<<(temb + wpb - 1) / wpb, wpb * 32, 0, st>>>(a1, temb, t_w2_, t_b2_, a2, temb, n, temb, temb, 0, 0);
+  small_linear_kernel<<<(tproj_total_ + wpb - 1) / wpb, wpb * 32, 0, st>>>(a2, temb, tproj_w_, tproj_b_, temb_table_, tproj_total_, n,
+                                                                           tproj_total_, temb, 1, 0);
+  CK(cudaGetLastError());
+  nT_ = n;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ plan builder
+struct Arena {
+  struct Blk { size_t off, size; bool free; };
+  std::vector<Blk> blks;
+  size_t peak = 0;
+  Arena() { blks.push_back({0, size_t(1) << 62, true}); }
+  size_t alloc(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    for (size_t i = 0; i < blks.size(); ++i)
+      if (blks[i].free && blks[i].size >= bytes) {
+        const size_t off = blks[i].off;
+        if (blks[i].size > bytes) {
+          Blk rest{off + bytes, blks[i].size - bytes, true};
+          blks[i].size = bytes;
+          blks.insert(blks.begin() + i + 1, rest);
+        }
+        blks[i].free = false;
+        peak = std::max(peak, off + bytes);
+        return off;
+      }
+    return size_t(-1);
+  }
+  void release(size_t off) {
+    for (size_t i = 0; i < blks.size(); ++i)
+      if (blks[i].off == off && !blks[i].free) {
+        blks[i].free = true;
+        if (i + 1 < blks.size() && blks[i + 1].free) { blks[i].size += blks[i + 1].size; blks.erase(blks.begin() + i + 1); }
+        if (i > 0 && blks[i - 1].free) { blks[i - 1].size += blks[i].size; blks.erase(blks.begin() + i); }
+        return;
+      }
+  }
+};
+
+struct PlanBuilder {
+  Engine& E;
+  Plan* plan;         // null in the sizing pass
+  int S;
+  Arena ar;
+  bool failed = false;
+  double flops = 0;
+  float* x_in = nullptr;    // patched per call
+  float* eps_out = nullptr;
+
+  PlanBuilder(Engine& e, Plan* p, int s) : E(e), plan(p), S(s) {}
+  template <typename T> T* A(size_t n) {
+    const size_t off = ar.alloc(n * sizeof(T));
+    return reinterpret_cast<T*>(E.arena_ + off);     // arena_ may be null in the sizing pass (pointer arithmetic only)
+  }
+  template <typename T> void F(T* p) { ar.release(size_t(reinterpret_cast<uint8_t*>(p) - E.arena_)); }
+  void push(const Op& op) { if (plan) plan->ops.push_back(op); }
+
+  void gemm(const char* tag, const bf16* Ain, int lda, int mode, const ConvGeom* cg, const bf16* Wt, int M, int N, int K, GemmEpilogue ep) {
+    flops += 2.0 * M * N * K;
+    if (!plan) return;
+    Op op{}; op.kind = OP_GEMM; op.tag = tag;
+    if (ep.rows_per_group == 0) ep.rows_per_group = 1;
+    if (!make_gemm(op.gemm, op.gemm_bn, Ain, lda, mode, cg, Wt, M, N, K, ep, E.err_)) { failed = true; return; }
+    push(op);
+  }
+  void gn(const float* x1, int C1, const float* x2, int C2, int HW, const float* g, const float* b, float eps, int silu, bf16* out, bf16* raw) {
+    const int chunk = std::max(16, HW / 64);
+    const int nch = (HW + chunk - 1) / chunk;
+    float2* partial = A<float2>(size_t(S) * nch * E.cfg_.groups);
+    Op s{}; s.kind = OP_GN_STATS; s.f_in = x1; s.f_in2 = x2; s.C1 = C1; s.C2 = C2; s.HW = HW; s.chunk = chunk; s.nchunks = nch;
+    s.partial = partial; s.tag = "gn_stats";
+    push(s);
+    Op a = s; a.kind = OP_GN_APPLY; a.gamma = g; a.beta = b; a.eps = eps; a.silu = silu; a.h_out = out; a.h_out2 = raw; a.tag = "gn_apply";
+    push(a);
+    F(partial);
+  }
+  void ln(const float* x, const float* g, const float* b, bf16* out, int rows, int C) {
+    Op o{}; o.kind = OP_LN; o.f_in = x; o.gamma = g; o.beta = b; o.h_out = out; o.rows = rows; o.C1 = C; o.eps = 1e-5f; o.tag = "layernorm";
+    push(o);
+  }
+
+  // ResnetBlock2D (oracle/sd_unet.py ResnetBlock2D): returns a new fp32 [S*HW][cout] buffer
+  float* resblock(const ResW& w, const float* x1, int C1, const float* x2, int C2, int Hh, int Ww) {
+    const int HW = Hh * Ww, M = S * HW, cin = C1 + C2, cout = w.cout;
+    ConvGeom cg{S, Hh, Ww, cin, 1};
+    bf16* a1 = A<bf16>(size_t(M) * cin);
+    bf16* raw = w.wsc ? A<bf16>(size_t(M) * cin) : nullptr;
+    gn(x1, C1, x2, C2, HW, w.n1g, w.n1b, 1e-5f, 1, a1, raw);
+    float* h1 = A<float>(size_t(M) * cout);
+    GemmEpilogue e1; memset(&e1, 0, sizeof e1);
+    e1.bias = w.b1; e1.rowvec = E.temb_rows_ + w.temb_off; e1.ldrv = E.tproj_total_; e1.rows_per_group = HW; e1.out_f32 = h1; e1.ldo = cout;
+    gemm("res.conv1", a1, cin, A_CONV3X3, &cg, w.w1, M, cout, 9 * cin, e1);
+    F(a1);
+    bf16* a2 = A<bf16>(size_t(M) * cout);
+    gn(h1, cout, nullptr, 0, HW, w.n2g, w.n2b, 1e-5f, 1, a2, nullptr);
+    F(h1);
+    const float* resid = x1;
+    float* sc = nullptr;
+    if (w.wsc) {
+      sc = A<float>(size_t(M) * cout);
+      GemmEpilogue es; memset(&es, 0, sizeof es);
+      es.bias = w.bsc; es.out_f32 = sc; es.ldo = cout;
+      gemm("res.shortcut", raw, cin, A_LINEAR, nullptr, w.wsc, M, cout, cin, es);
+      F(raw);
+      resid = sc;
+    }
+    float* out = A<float>(size_t(M) * cout);
+    ConvGeom cg2{S, Hh, Ww, cout, 1};
+    GemmEpilogue e2; memset(&e2, 0, sizeof e2);
+    e2.bias = w.b2; e2.residual = resid; e2.ldr = cout; e2.out_f32 = out; e2.ldo = cout;
+    gemm("res.conv2", a2, cout, A_CONV3X3, &cg2, w.w2, M, cout, 9 * cout, e2);
+    F(a2);
+    if (sc) F(sc);
+    return out;
+  }
+
+  // Transformer2DModel with one BasicTransformerBlock: returns a new fp32 buffer
+  float* transformer(int ti, const float* x, int Hh, int Ww) {
+    const TfW& w = E.tfs_[ti];
+    const int C = w.C, HW = Hh * Ww, M = S * HW, H = E.cfg_.heads, d = C / H;
+    bf16* a = A<bf16>(size_t(M) * C);
+    gn(x, C, nullptr, 0, HW, w.gng, w.gnb, 1e-6f, 0, a, nullptr);
+    float* t = A<float>(size_t(M) * C);
+    GemmEpilogue e; memset(&e, 0, sizeof e);
+    e.bias = w.b_in; e.out_f32 = t; e.ldo = C;
+    gemm("tf.proj_in", a, C, A_LINEAR, nullptr, w.w_in, M, C, C, e);
+    // ---- self-attention
+    ln(t, w.ln1g, w.ln1b, a, M, C);
+    bf16* qkv = A<bf16>(size_t(M) * 3 * C);
+    memset(&e, 0, sizeof e); e.out_bf16 = qkv; e.ldob = 3 * C;
+    gemm("tf.qkv", a, C, A_LINEAR, nullptr, w.w_qkv, M, 3 * C, C, e);
+    bf16* att = A<bf16>(size_t(M) * C);
+    flops += 4.0 * S * double(HW) * HW * C;
+    if (plan) {
+      Op o{}; o.kind = OP_SELF_ATTN; o.tag = "self_attn"; o.tf_index = ti; o.dch = dch_for(d); o.bkv = bkv_for(d);
+      AttnParams& p = o.attn;
+      if (!make_attn_maps(p, qkv, 3 * C, HW, S, qkv + C, qkv + 2 * C, 3 * C, HW, S, H, d, o.bkv, E.err_)) failed = true;
+      p.H = H; p.d = d; p.Nq = HW; p.Nkv = HW; p.scale_log2 = float(1.4426950408889634 / std::sqrt(double(d)));
+      p.out = att; p.ldo = C;
+      push(o);
+    }
+    F(qkv);
+    memset(&e, 0, sizeof e); e.bias = w.b_o1; e.residual = t; e.ldr = C; e.out_f32 = t; e.ldo = C;
+    gemm("tf.attn1.out", att, C, A_LINEAR, nullptr, w.w_o1, M, C, C, e);
+    // ---- cross-attention
+    ln(t, w.ln2g, w.ln2b, a, M, C);
+    bf16* qc = A<bf16>(size_t(M) * C);
+    memset(&e, 0, sizeof e); e.out_bf16 = qc; e.ldob = C;
+    gemm("tf.q2", a, C, A_LINEAR, nullptr, w.w_q2, M, C, C, e);
+    flops += 4.0 * S * double(HW) * E.cfg_.ctx_len * C;
+    if (plan) {
+      Op o{}; o.kind = OP_CROSS_ATTN; o.tag = "cross_attn"; o.tf_index = ti; o.dch = dch_for(d);
+      o.blend_layer = -1;
+      if (HW == 256 && E.cfg_.sample == 64) {   // LocalBlend layers: 16x16 maps of the down/up path
+        int idx = 0;
+        for (int j = 0; j < ti; ++j) if (E.tf_tokens_[j] == 256) ++idx;
+        // the mid block never has 256 tokens for sample 64 (8x8), so every 256-token layer counts
+        o.blend_layer = idx;
+      }
+      AttnParams& p = o.attn;
+      if (!make_attn_maps(p, qc, C, HW, S, w.kv_cache, w.kv_cache + C, 2 * C, E.cfg_.ctx_len, E.maxCtx_, H, d, 80, E.err_)) failed = true;
+      p.H = H; p.d = d; p.Nq = HW; p.Nkv = E.cfg_.ctx_len; p.scale_log2 = float(1.4426950408889634 / std::sqrt(double(d)));
+      p.out = att; p.ldo = C;
+      push(o);
+    }
+    F(qc);
+    memset(&e, 0, sizeof e); e.bias = w.b_o2; e.residual = t; e.ldr = C; e.out_f32 = t; e.ldo = C;
+    gemm("tf.attn2.out", att, C, A_LINEAR, nullptr, w.w_o2, M, C, C, e);
+    F(att);
+    // ---- GEGLU feed-forward
+    ln(t, w.ln3g, w.ln3b, a, M, C);
+    bf16* ff = A<bf16>(size_t(M) * 4 * C);
+    memset(&e, 0, sizeof e); e.bias = w.b_ff1; e.out_bf16 = ff; e.ldob = 4 * C; e.geglu = 1;
+    gemm("tf.ff1_geglu", a, C, A_LINEAR, nullptr, w.w_ff1, M, 8 * C, C, e);
+    memset(&e, 0, sizeof e); e.bias = w.b_ff2; e.residual = t; e.ldr = C; e.out_bf16 = a; e.ldob = C;
+    gemm("tf.ff2", ff, 4 * C, A_LINEAR, nullptr, w.w_ff2, M, C, 4 * C, e);
+    F(ff);
+    F(t);
+    float* out = A<float>(size_t(M) * C);
+    memset(&e, 0, sizeof e); e.bias = w.b_out; e.residual = x; e.ldr = C; e.out_f32 = out; e.ldo = C;
+    gemm("tf.proj_out", a, C, A_LINEAR, nullptr, w.w_out, M, C, C, e);
+    F(a);
+    return out;
+  }
+
+  void build() {
+    const UNetCfg& c = E.cfg_;
+    int Hh = c.sample, Ww = c.sample;
+    x_in = A<float>(size_t(S) * c.in_ch * Hh * Ww);
+    eps_out = A<float>(size_t(S) * c.out_ch * Hh * Ww);
+    std::vector<std::pair<float*, int>> skips;
+    float* x = A<float>(size_t(S) * Hh * Ww * c.boc[0]);
+    { Op o{}; o.kind = OP_CONV_IN; o.f_in = x_in; o.f_out = x; o.H = Hh; o.W = Ww; o.C1 = c.boc[0]; o.tag = "conv_in"; push(o); }
+    skips.push_back({x, c.boc[0]});
+    int ri = 0, ti = 0, C = c.boc[0];
+    for (int i = 0; i < 4; ++i) {
+      for (int l = 0; l < c.layers; ++l) {
+        float* y = resblock(E.res_[ri++], x, C, nullptr, 0, Hh, Ww);
+        C = c.boc[i];
+        if (i < 3) { float* z = transformer(ti++, y, Hh, Ww); F(y); y = z; }
+        x = y;
+        skips.push_back({x, C});
+      }
+      if (i < 3) {
+        const int M0 = S * Hh * Ww;
+        bf16* xb = A<bf16>(size_t(M0) * C);
+        { Op o{}; o.kind = OP_CAST; o.f_in = x; o.h_out = xb; o.count = size_t(M0) * C / 4; o.tag = "cast_bf16"; push(o); }
+        Hh /= 2; Ww /= 2;
+        float* y = A<float>(size_t(S) * Hh * Ww * C);
+        ConvGeom cg{S, Hh, Ww, C, 2};
+        GemmEpilogue e; memset(&e, 0, sizeof e); e.bias = E.down_b_[i]; e.out_f32 = y; e.ldo = C;
+        gemm("downsample", xb, C, A_CONV3X3S2, &cg, E.down_w_[i], S * Hh * Ww, C, 9 * C, e);
+        F(xb);
+        x = y;
+        skips.push_back({x, C});
+      }
+    }
+    // mid
+    { float* y = resblock(E.res_[ri++], x, C, nullptr, 0, Hh, Ww); float* z = transformer(ti++, y, Hh, Ww); F(y);
+      float* u = resblock(E.res_[ri++], z, C, nullptr, 0, Hh, Ww); F(z); x = u; }
+    bool x_owned = true;
+    for (int i = 0; i < 4; ++i) {
+      const int oc = c.boc[3 - i];
+      for (int l = 0; l < c.layers + 1; ++l) {
+        auto sk = skips.back(); skips.pop_back();
+        float* y = resblock(E.res_[ri++], x, C, sk.first, sk.second, Hh, Ww);
+        if (x_owned) F(x);
+        F(sk.first);
+        C = oc;
+        if (i > 0) { float* z = transformer(ti++, y, Hh, Ww); F(y); y = z; }
+        x = y; x_owned = true;
+      }
+      if (i < 3) {
+        bf16* up = A<bf16>(size_t(S) * 4 * Hh * Ww * C);
+        { Op o{}; o.kind = OP_UPSAMPLE; o.f_in = x; o.h_out = up; o.H = Hh; o.W = Ww; o.C1 = C; o.tag = "upsample2x"; push(o); }
+        F(x);
+        Hh *= 2; Ww *= 2;
+        float* y = A<float>(size_t(S) * Hh * Ww * C);
+        ConvGeom cg{S, Hh, Ww, C, 1};
+        GemmEpilogue e; memset(&e, 0, sizeof e); e.bias = E.up_b_[i]; e.out_f32 = y; e.ldo = C;
+        gemm("upsample.conv", up, C, A_CONV3X3, &cg, E.up_w_[i], S * Hh * Ww, C, 9 * C, e);
+        F(up);
+        x = y;
+      }
+    }
+    bf16* fin = A<bf16>(size_t(S) * Hh * Ww * C);
+    gn(x, C, nullptr, 0, Hh * Ww, E.norm_out_g_, E.norm_out_b_, 1e-5f, 1, fin, nullptr);
+    { Op o{}; o.kind = OP_CONV_OUT; o.h_in = fin; o.f_out = eps_out; o.H = Hh; o.W = Ww; o.C1 = C; o.tag = "conv_out"; push(o); }
+    flops += 2.0 * S * Hh * Ww * 36.0 * c.boc[0] * 2;
+  }
+};
+
+Plan* Engine::get_plan(int S) {
+  auto it = plans_.find(S);
+  if (it != plans_.end()) return it->second.get();
+  if (S > maxS_) { err_ = "batch exceeds max_samples"; return nullptr; }
+  if (!arena_) {   // sizing pass at the maximum batch
+    PlanBuilder sz(*this, nullptr, maxS_);
+    sz.build();
+    arena_bytes_ = sz.ar.peak + (size_t(1) << 20);
+    flops_per_sample_ = sz.flops / maxS_;
+    if (cudaMalloc(&arena_, arena_bytes_) != cudaSuccess) { err_ = "arena cudaMalloc failed"; arena_ = nullptr; return nullptr; }
+  }
+  std::unique_ptr<Plan> p(new Plan());
+  p->S = S;
+  PlanBuilder b(*this, p.get(), S);
+  b.build();
+  if (b.failed || b.ar.peak > arena_bytes_) { if (err_.empty()) err_ = "plan build failed"; return nullptr; }
+  Plan* raw = p.get();
+  plans_[S] = std::move(p);
+  return raw;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+long Engine::forward(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st) {
+  Plan* plan = get_plan(S);
+  if (!plan) return -1;
+  const UNetCfg& c = cfg_;
+  long launches = 0;
+  // per-call time-embedding rows
+  {
+    dim3 grid(std::max(1, tproj_total_ / 4 / 256), S);
+    gather_rows_kernel<<<grid, 256, 0, st>>>(temb_table_, cc.time_idx, temb_rows_, tproj_total_ / 4);
+    ++launches;
+  }
+  const size_t lat = size_t(c.in_ch) * c.sample * c.sample;
+  for (Op& op : plan->ops) {
+    switch (op.kind) {
+      case OP_CONV_IN: {
+        CK(cudaMemcpyAsync(const_cast<float*>(op.f_in), x, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        const size_t sm = (36 * size_t(op.C1) + 12 * (op.W + 2)) * sizeof(float);
+        static bool set = false;
+        if (!set) { cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); set = true; }
+        conv_in_kernel<<<dim3(op.H, S), 256, sm, st>>>(op.f_in, conv_in_w_, conv_in_b_, op.f_out, op.H, op.W, op.C1);
+        break;
+      }
+      case OP_GN_STATS: {
+        GNStatsParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, op.chunk, op.partial};
+        const int half = (op.C1 + op.C2) / 2;
+        const int threads = std::min(640, ((half + 31) / 32) * 32);
+        gn_stats_kernel<<<dim3(op.nchunks, S), threads, 0, st>>>(p);
+        break;
+      }
+      case OP_GN_APPLY: {
+        const int C = op.C1 + op.C2;
+        const int chunk = 16;
+        GNApplyParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, chunk, op.nchunks, op.partial, op.gamma, op.beta, op.eps, op.silu, op.h_out, op.h_out2};
+        gn_apply_kernel<<<dim3((op.HW + chunk - 1) / chunk, S), 256, 2 * C * sizeof(float), st>>>(p);
+        break;
+      }
+      case OP_GEMM:
+        CK(launch_gemm(op.gemm, op.gemm_bn, st));
+        break;
+      case OP_LN:
+        layernorm_kernel<32><<<(op.rows + 7) / 8, 256, 0, st>>>(op.f_in, op.gamma, op.beta, op.h_out, op.rows, op.C1, op.eps);
+        break;
+      case OP_SELF_ATTN: {
+        AttnParams a = op.attn;
+        if (cc.self_mask & (1u << op.tf_index)) { a.q_idx = cc.self_q; a.k_idx = cc.self_k; a.v_idx = cc.self_v; }
+        CK(launch_self_attn(a, op.dch, S, st));
+        break;
+      }
+      case OP_CROSS_ATTN: {
+        AttnParams a = op.attn;
+        a.unit_s0 = cc.unit_s0; a.unit_s1 = cc.unit_s1; a.unit_img = cc.unit_img; a.ctx_idx = cc.ctx_idx;
+        a.mapper = cc.mapper; a.c_base = cc.c_base; a.c_tar = cc.c_tar; a.replace_m = cc.replace_m; a.is_replace = cc.is_replace;
+        a.blend_alpha = cc.blend_alpha; a.n_blend_layers = n_blend_layers_;
+        a.blend_layer = op.blend_layer;
+        a.blend_acc = (op.blend_layer >= 0) ? cc.blend_acc : nullptr;
+        CK(launch_cross_attn(a, op.dch, cc.n_units, st));
+        break;
+      }
+      case OP_UPSAMPLE: {
+        const size_t total = size_t(S) * 4 * op.H * op.W * (op.C1 / 4);
+        upsample2x_bf16_kernel<<<int(std::min<size_t>((total + 255) / 256, 8192)), 256, 0, st>>>(op.f_in, op.h_out, S, op.H, op.W, op.C1);
+        break;
+      }
+      case OP_CAST:
+        cast_bf16_kernel<<<int(std::min<size_t>((op.count + 255) / 256, 8192)), 256, 0, st>>>(op.f_in, op.h_out, op.count);
+        break;
+      case OP_CONV_OUT: {
+        static bool set = false;
+        if (!set) { cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); set = true; }
+        const size_t npix = size_t(S) * op.H * op.W;
+        conv_out_kernel<<<int(std::min<size_t>((npix + 7) / 8, 4096)), 256, 36 * size_t(op.C1) * sizeof(float), st>>>(
+            op.h_in, conv_out_w_, conv_out_b_, op.f_out, S, op.H, op.W, op.C1);
+        CK(cudaMemcpyAsync(eps, op.f_out, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        break;
+      }
+    }
+    ++launches;
+  }
+  CK(cudaGetLastError());
+  return launches;
+}
+
+}  // namespace hedit

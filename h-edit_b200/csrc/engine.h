@@ -1,0 +1,148 @@
+// UNet engine: owns device weights (bf16 GEMM operands, fp32 norms/biases), a static activation arena, and one
+// launch plan per batch size (every tensor map is encoded once at plan-build time).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "gemm.cuh"
+
+namespace hedit {
+
+typedef __nv_bfloat16 bf16;
+
+struct UNetCfg {
+  int in_ch = 4, out_ch = 4, sample = 64;
+  int boc[4] = {320, 640, 1280, 1280};
+  int layers = 2, heads = 8, ctx_dim = 768, groups = 32;
+  int ctx_len = 77;
+};
+
+struct ResW {
+  int cin = 0, cout = 0, temb_off = 0;
+  float *n1g = 0, *n1b = 0, *n2g = 0, *n2b = 0, *b1 = 0, *b2 = 0, *bsc = 0;
+  bf16 *w1 = 0, *w2 = 0, *wsc = 0;
+};
+struct TfW {
+  int C = 0, cross_index = 0;
+  float *gng = 0, *gnb = 0, *b_in = 0, *b_out = 0, *ln1g = 0, *ln1b = 0, *ln2g = 0, *ln2b = 0, *ln3g = 0, *ln3b = 0;
+  float *b_o1 = 0, *b_o2 = 0, *b_ff1 = 0, *b_ff2 = 0;
+  bf16 *w_in = 0, *w_out = 0, *w_qkv = 0, *w_o1 = 0, *w_q2 = 0, *w_kv2 = 0, *w_o2 = 0, *w_ff1 = 0, *w_ff2 = 0;
+  bf16* kv_cache = 0;      // [max_ctx][77][2C]
+};
+
+// How one named reference tensor is converted into the engine's layout.
+struct WeightSlot {
+  enum Kind { F32_COPY, BF16_ROWS, BF16_CONV3, BF16_GEGLU_ROWS, F32_GEGLU_VEC } kind;
+  void* dst = nullptr;
+  size_t dst_off_elems = 0;     // element offset inside dst (row-concatenated tensors)
+  std::vector<int64_t> shape;   // expected source shape
+  bool loaded = false;
+};
+
+enum OpKind { OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_GEMM, OP_LN, OP_SELF_ATTN, OP_CROSS_ATTN, OP_UPSAMPLE, OP_CAST, OP_CONV_OUT };
+
+struct Op {
+  OpKind kind;
+  // generic payloads (only the ones relevant to `kind` are used)
+  GemmParams gemm; int gemm_bn = 0;
+  AttnParams attn; int dch = 0, bkv = 0, tf_index = 0, blend_layer = -1;
+  const float* f_in = nullptr; const float* f_in2 = nullptr; float* f_out = nullptr;
+  const bf16* h_in = nullptr; bf16* h_out = nullptr; bf16* h_out2 = nullptr;
+  const float* gamma = nullptr; const float* beta = nullptr; const float* w = nullptr; const float* b = nullptr;
+  float2* partial = nullptr;
+  int C1 = 0, C2 = 0, HW = 0, H = 0, W = 0, rows = 0, chunk = 0, nchunks = 0, silu = 0;
+  float eps = 0.f;
+  size_t count = 0;
+  const char* tag = "";
+};
+
+// Per-call attention control (device arrays prepared by the edit loop).
+struct CallCtrl {
+  const int* ctx_idx = nullptr;        // [S] index into the text K/V cache
+  const int* time_idx = nullptr;       // [S] row of the timestep-embedding table
+  // self-attention injection (applied on transformer blocks whose bit is set in self_mask)
+  uint32_t self_mask = 0;
+  const int *self_q = nullptr, *self_k = nullptr, *self_v = nullptr;
+  // cross-attention work units + P2P edit tables for the current step
+  const int *unit_s0 = nullptr, *unit_s1 = nullptr, *unit_img = nullptr;
+  int n_units = 0;
+  const int* mapper = nullptr; const float* c_base = nullptr; const float* c_tar = nullptr;
+  const float* replace_m = nullptr; const int* is_replace = nullptr;
+  float* blend_acc = nullptr; const float* blend_alpha = nullptr;
+};
+
+struct Plan {
+  int S = 0;
+  std::vector<Op> ops;
+  size_t launches = 0;
+};
+
+class Engine {
+ public:
+  Engine(const UNetCfg& cfg, int max_samples, int max_ctx);
+  ~Engine();
+  bool ok() const { return err_.empty(); }
+  const std::string& error() const { return err_; }
+
+  int load_tensor(const char* name, const float* src, const int64_t* dims, int ndim, cudaStream_t st);
+  int finalize_weights(std::string* missing);
+
+  // text contexts -> cached K/V for the 16 cross-attention layers; ctx fp32 [n_ctx][77][ctx_dim] (host or device)
+  int set_contexts(const float* ctx, int n_ctx, cudaStream_t st);
+  // timestep-embedding table for a list of timesteps (host array)
+  int set_timesteps(const float* ts, int n, cudaStream_t st);
+
+  // x [S][4][h][w] fp32 NCHW (device) -> eps [S][4][h][w] (device).  Returns kernels launched, <0 on error.
+  long forward(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st);
+
+  const UNetCfg& cfg() const { return cfg_; }
+  int max_samples() const { return maxS_; }
+  int n_blend_layers() const { return n_blend_layers_; }
+  int n_tf() const { return int(tfs_.size()); }
+  int tf_tokens(int i) const { return tf_tokens_[i]; }
+  int latent_elems() const { return cfg_.in_ch * cfg_.sample * cfg_.sample; }
+  double flops_per_sample() const { return flops_per_sample_; }
+  void* scratch_alloc(size_t bytes);     // persistent device allocations owned by the engine
+
+  std::string err_;
+
+ private:
+  friend struct PlanBuilder;
+  Plan* get_plan(int S);
+  void reg(const std::string& name, WeightSlot::Kind k, void* dst, size_t off, std::vector<int64_t> shape);
+  template <typename T> T* dalloc(size_t n);
+
+  UNetCfg cfg_;
+  int maxS_, maxCtx_;
+  std::map<std::string, WeightSlot> slots_;
+  std::vector<void*> owned_;
+  // weights
+  float *conv_in_w_ = 0, *conv_in_b_ = 0, *conv_out_w_ = 0, *conv_out_b_ = 0, *norm_out_g_ = 0, *norm_out_b_ = 0;
+  float *t_w1_ = 0, *t_b1_ = 0, *t_w2_ = 0, *t_b2_ = 0, *tproj_w_ = 0, *tproj_b_ = 0;
+  int tproj_total_ = 0;
+  std::vector<ResW> res_;       // in forward order
+  std::vector<TfW> tfs_;        // in forward order (== controller layer order / 2)
+  std::vector<int> tf_tokens_;
+  std::vector<bf16*> down_w_, up_w_;
+  std::vector<float*> down_b_, up_b_;
+  int n_blend_layers_ = 0;
+  double flops_per_sample_ = 0;
+  // runtime buffers
+  uint8_t* arena_ = 0; size_t arena_bytes_ = 0;
+  float* temb_act_ = 0;         // [maxT][temb_dim]
+  float* temb_table_ = 0;       // [maxT][tproj_total]
+  float* temb_rows_ = 0;        // [maxS][tproj_total] gathered per call
+  float* ts_dev_ = 0;
+  int maxT_ = 128, nT_ = 0;
+  bf16* ctx_bf16_ = 0;          // [max_ctx*77][ctx_dim]
+  float* stage_ = 0; size_t stage_elems_ = 0;   // fp32 staging for weight upload
+  std::map<int, std::unique_ptr<Plan>> plans_;
+};
+
+}  // namespace hedit

@@ -1,0 +1,130 @@
+"""Python handle on the native UNet engine + batched edit loop (C ABI in include/hedit_b200.h).
+PyTorch is used only for device memory and streams; all compute happens in libhedit_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .p2p import EditPlan
+
+
+def unet_config_of(unet) -> dict:
+    """Geometry of a diffusers-style (or oracle) SD-1.x UNet object."""
+    cfg = getattr(unet, "cfg", None) or getattr(unet, "config", None)
+    get = (lambda k, d=None: getattr(cfg, k, d)) if not isinstance(cfg, dict) else (lambda k, d=None: cfg.get(k, d))
+    heads = get("attention_head_dim", 8)
+    return dict(in_channels=get("in_channels", 4), out_channels=get("out_channels", 4), sample_size=get("sample_size", 64),
+                block_out_channels=tuple(get("block_out_channels", (320, 640, 1280, 1280))), layers_per_block=get("layers_per_block", 2),
+                heads=heads if isinstance(heads, int) else heads[0], cross_attention_dim=get("cross_attention_dim", 768),
+                norm_groups=get("norm_num_groups", 32), ctx_len=77)
+
+
+class UNetEngine:
+    def __init__(self, config: dict, max_samples: int, max_contexts: Optional[int] = None, device: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("hedit_b200: no CUDA device visible; the B200 path has no CPU fallback")
+        c = _lib.UNetConfigC()
+        c.in_channels, c.out_channels, c.sample_size = config["in_channels"], config["out_channels"], config["sample_size"]
+        for i, v in enumerate(config["block_out_channels"]):
+            c.block_out_channels[i] = v
+        c.layers_per_block, c.heads = config["layers_per_block"], config["heads"]
+        c.cross_attention_dim, c.norm_groups, c.ctx_len = config["cross_attention_dim"], config["norm_groups"], config["ctx_len"]
+        self.config = dict(config)
+        self.device = device
+        self.max_samples = max_samples
+        self.max_contexts = max_contexts or max(max_samples, 4)
+        self.handle = self.lib.hedit_engine_create(C.byref(c), max_samples, self.max_contexts, device)
+        if not self.handle:
+            raise RuntimeError("hedit_b200: engine creation failed: " + _lib.last_error())
+        self.latent_shape = (config["in_channels"], config["sample_size"], config["sample_size"])
+        self.last_stats: Dict[str, int] = {}
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.hedit_engine_destroy(h)
+
+    # ---- weights
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        for name, t in sd.items():
+            if not torch.is_floating_point(t):
+                continue
+            t = t.detach().to(torch.float32).contiguous()
+            dims = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(self.lib.hedit_engine_load_tensor(self.handle, name.encode(), t.data_ptr(), dims, t.dim()), f"load {name}")
+        _lib.check(self.lib.hedit_engine_finalize(self.handle), "finalize weights")
+
+    @classmethod
+    def from_unet(cls, unet, max_samples: int, max_contexts: Optional[int] = None, device: int = 0) -> "UNetEngine":
+        eng = cls(unet_config_of(unet), max_samples, max_contexts, device)
+        eng.load_state_dict(unet.state_dict())
+        return eng
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- plain UNet call (use_controller=False)
+    def forward(self, x: torch.Tensor, timesteps, ctx: torch.Tensor) -> torch.Tensor:
+        dev = torch.device("cuda", self.device)
+        x = x.to(dev, torch.float32).contiguous()
+        S = x.shape[0]
+        ts = np.ascontiguousarray(np.broadcast_to(np.asarray(timesteps, dtype=np.float32).reshape(-1), (S,)))
+        ctx = ctx.to(torch.float32).contiguous()
+        eps = torch.empty_like(x)
+        n = _lib.check(self.lib.hedit_unet_forward(self.handle, x.data_ptr(), ts.ctypes.data, ctx.data_ptr(), S, eps.data_ptr(), self._stream()),
+                       "unet forward")
+        self.last_stats = {"kernel_launches": n, "sample_forwards": S}
+        return eps
+
+    # ---- the bridge-sampling loop
+    def edit(self, xT: torch.Tensor, zs: torch.Tensor, ctx: torch.Tensor, timesteps: Sequence[int], coef: np.ndarray,
+             cfg_scales: Sequence[float], plan: Optional[EditPlan], weight_reconstruction: float = 0.1, optimization_steps: int = 1,
+             explicit_form: bool = False, schedule: int = 1, trace: bool = False):
+        """xT (B,C,h,w), zs (B,steps,C,h,w), ctx (1+2B,77,D): all on the SAME side (all host or all on this device).
+        Returns (edited, recon[, trace]) on that side."""
+        B, steps = xT.shape[0], zs.shape[1]
+        on_host = not xT.is_cuda
+        assert zs.is_cuda == xT.is_cuda, "xT and zs must live on the same side"
+        xT = xT.to(torch.float32).contiguous()
+        zs = zs.to(torch.float32).contiguous()
+        ctx = ctx.to(torch.float32).contiguous()
+        assert ctx.shape[0] == 1 + 2 * B and zs.shape[0] == B and len(timesteps) == steps + 1 and coef.shape == (steps, 6)
+        mk = (lambda *s: torch.empty(*s, dtype=torch.float32, pin_memory=True)) if on_host else \
+            (lambda *s: torch.empty(*s, dtype=torch.float32, device=xT.device))
+        edited, recon = mk(*xT.shape), mk(*xT.shape)
+        tr = mk(steps, B, 2, *xT.shape[1:]) if trace else None
+        ts = np.ascontiguousarray(np.asarray(timesteps, dtype=np.float32))
+        coef = np.ascontiguousarray(coef, dtype=np.float32)
+        a = _lib.EditArgsC()
+        a.B, a.steps, a.opt_steps, a.explicit_form, a.schedule, a.buffers_on_host = B, steps, optimization_steps, int(explicit_form), schedule, int(on_host)
+        a.xT, a.zs, a.ctx, a.timesteps, a.coef = xT.data_ptr(), zs.data_ptr(), ctx.data_ptr(), ts.ctypes.data, coef.ctypes.data
+        a.w_src, a.w_src_edit, a.w_tar = [float(v) for v in cfg_scales]
+        a.weight_reconstruction = float(weight_reconstruction)
+        keep = [ts, coef, xT, zs, ctx]
+        if plan is not None:
+            a.use_p2p = 1
+            arrs = dict(mapper=plan.mapper, is_replace=plan.is_replace, c_base=plan.c_base, c_tar=plan.c_tar,
+                        has_blend=plan.has_blend, blend_alpha=plan.blend_alpha)
+            for k, v in arrs.items():
+                v = np.ascontiguousarray(v)
+                keep.append(v)
+                setattr(a, k, v.ctypes.data)
+            if plan.replace_m is not None:
+                rm = np.ascontiguousarray(plan.replace_m)
+                keep.append(rm)
+                a.replace_m = rm.ctypes.data
+            if not plan.has_blend.any():
+                a.has_blend = None
+            a.self_lo, a.self_hi = plan.self_window
+            a.self_max_tokens = 32 * 32
+            a.start_blend, a.blend_th = plan.start_blend, plan.blend_th
+        a.edited, a.recon = edited.data_ptr(), recon.data_ptr()
+        a.trace = tr.data_ptr() if tr is not None else None
+        _lib.check(self.lib.hedit_edit_p2p(self.handle, C.byref(a), self._stream()), "edit")
+        self.last_stats = {"sample_forwards": int(a.n_sample_forwards), "kernel_launches": int(a.n_kernel_launches)}
+        return (edited, recon, tr) if trace else (edited, recon)

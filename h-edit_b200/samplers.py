@@ -1,0 +1,85 @@
+"""Drop-in sampler callables: same names and argument meaning as the reference's
+text-guided/inversion/p2p_h_edit.py (h_Edit_p2p_implicit :529, h_Edit_p2p_explicit :380), backed by the native
+batched loop.  `model` is the reference's duck-typed StableDiffusionPipeline (unet, scheduler, tokenizer,
+text_encoder, device)."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Union
+
+import torch
+
+from .engine import UNetEngine
+from .p2p import compile_edit_plan
+from .schedule import step_tables
+
+
+def encode_text(model, prompts: Union[str, List[str]]) -> torch.Tensor:
+    """text-guided/inversion/inversion_utils.py:13-36 (tokenise to max_length, run the text encoder)."""
+    tok = model.tokenizer(prompts, padding="max_length", max_length=model.tokenizer.model_max_length, truncation=True,
+                          return_tensors="pt")
+    with torch.no_grad():
+        return model.text_encoder(tok.input_ids.to(model.device))[0]
+
+
+def get_engine(model, max_samples: int = 5, device: int = 0) -> UNetEngine:
+    """One persistent engine per pipeline object (replaces the per-image deepcopy at main_p2p.py:119)."""
+    eng = getattr(model, "_hedit_b200_engine", None)
+    if eng is None or eng.max_samples < max_samples:
+        eng = UNetEngine.from_unet(model.unet, max_samples=max_samples, max_contexts=max(8, 1 + 2 * (max_samples // 5 + 1)), device=device)
+        model._hedit_b200_engine = eng
+    return eng
+
+
+def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Sequence[Sequence[str]], cfg_scales, controllers,
+                     eta=1.0, weight_reconstruction=0.075, optimization_steps=1, after_skip_steps=None, is_ddim_inversion=False,
+                     explicit_form=False, schedule=1, engine: Optional[UNetEngine] = None, trace=False):
+    """B independent edits in one native call.  xT (B,C,h,w); zs (B,steps,C,h,w); prompt_pairs[b] = [src, tar];
+    controllers[b] = P2P controller of image b (ours or the reference's) or None for all (P2P off)."""
+    B = xT.shape[0]
+    steps = after_skip_steps if after_skip_steps is not None else model.scheduler.num_inference_steps
+    eng = engine or get_engine(model, max_samples=5 * B)
+    ctx = [encode_text(model, [""])]
+    for src, tar in prompt_pairs:
+        ctx.append(encode_text(model, [src, tar]))
+    ctx = torch.cat(ctx).float()
+    ctx = ctx.cpu() if not xT.is_cuda else ctx.to(xT.device)
+    ts, coef = step_tables(model.scheduler, steps, eta, is_ddim_inversion)
+    plan = None
+    if controllers is not None and all(c is not None for c in controllers):
+        plan = compile_edit_plan(controllers, steps)
+    out = eng.edit(xT, zs[:, :steps], ctx, ts, coef, cfg_scales, plan, weight_reconstruction, optimization_steps, explicit_form, schedule, trace)
+    if plan is not None:
+        for c in controllers:       # keep the controller's observable counters consistent with the reference
+            c.cur_step = getattr(c, "cur_step", 0) + steps
+            if getattr(c, "local_blend", None) is not None:
+                c.local_blend.counter += steps
+    return out
+
+
+def _single(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstruction, optimization_steps, after_skip_steps,
+            is_ddim_inversion, explicit_form):
+    assert len(prompts) >= 2, "only support prompt editing"
+    dev = xT.device
+    x = xT.reshape(1, *xT.shape[-3:])
+    steps = after_skip_steps
+    z = zs[:steps].reshape(1, steps, *xT.shape[-3:])
+    # hand a real P2P controller to the fused path; a bare AttentionStore (no-P2P modes) carries no edit tables
+    ctrl = [controller] if (controller is not None and hasattr(controller, "cross_replace_alpha")) else None
+    use_cuda = torch.device(dev).type == "cuda"
+    x, z = (x.cuda(), z.cuda()) if use_cuda else (x.cpu(), z.cpu())
+    edited, recon = h_edit_p2p_batch(model, x, z, [prompts[:2]], cfg_scales, ctrl, eta, weight_reconstruction, optimization_steps, steps,
+                                     is_ddim_inversion, explicit_form)
+    return edited.to(dev), recon.to(dev)
+
+
+def h_Edit_p2p_implicit(model, xT, eta=1.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None,
+                        weight_reconstruction=0.075, optimization_steps=1, after_skip_steps=35, is_ddim_inversion=True):
+    """Reference signature (p2p_h_edit.py:529).  Returns (edited, reconstructed), each (1,C,h,w)."""
+    return _single(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstruction, optimization_steps, after_skip_steps,
+                   is_ddim_inversion, False)
+
+
+def h_Edit_p2p_explicit(model, xT, eta=1.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None,
+                        is_ddim_inversion=True, after_skip_steps=35):
+    """Reference signature (p2p_h_edit.py:380)."""
+    return _single(model, xT, eta, prompts, cfg_scales, zs, controller, 0.0, 1, after_skip_steps, is_ddim_inversion, True)

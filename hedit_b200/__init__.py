@@ -1,0 +1,9 @@
+"""Import alias: the package directory is `h-edit_b200/` (not a valid Python identifier); `import hedit_b200`
+resolves to it."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "h-edit_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+del _f

@@ -1,0 +1,121 @@
+/*
+ * hedit_b200 -- C ABI of the B200-native h-Edit hot path (reverse-time bridge sampling loop).
+ *
+ * The reference (nktoan/h-edit) has no FFI: its boundary is Python duck typing.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference root); INTEGRATION.md shows the ctypes binding
+ * a reference maintainer would add.  All pointers are plain device or host addresses (cudaMemcpyDefault semantics
+ * where noted); no torch types cross this boundary.  Every function returns 0 / a non-negative count on success
+ * and a negative code on failure, with the reason available from hedit_last_error().
+ */
+#ifndef HEDIT_B200_H
+#define HEDIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hedit_engine hedit_engine;
+
+/* SD-1.x UNet geometry (diffusers UNet2DConditionModel config the reference loads at
+ * text-guided/main_p2p.py:106; restated in oracle/sd_unet.py). */
+typedef struct hedit_unet_config {
+  int32_t in_channels, out_channels, sample_size;
+  int32_t block_out_channels[4];
+  int32_t layers_per_block, heads, cross_attention_dim, norm_groups, ctx_len;
+} hedit_unet_config;
+
+/* Per-step scalars of reverse_step / compute_full_coeff (text-guided/inversion/inversion_utils.py:58-126,168-195
+ * and the coeff line text-guided/inversion/p2p_h_edit.py:664-665), precomputed by the host. */
+typedef struct hedit_step_coef {
+  float sqrt_1m_at, sqrt_at, sqrt_ap, dir, noise, coeff;
+} hedit_step_coef;
+
+/* One batched edit = B independent images, each with prompts [src, tar].
+ * Replaces the loop-level callables h_Edit_p2p_implicit / h_Edit_p2p_explicit
+ * (text-guided/inversion/p2p_h_edit.py:529,380) including the P2P controller hook surface
+ * (text-guided/p2p/ptp_utils.py:31-123, p2p/ptp_classes.py:17-283) compiled into per-step tables. */
+typedef struct hedit_edit_args {
+  int32_t B;                 /* images */
+  int32_t steps;             /* after_skip_steps (number of timesteps executed) */
+  int32_t opt_steps;         /* optimization_steps K (implicit form) */
+  int32_t explicit_form;     /* 0: h_Edit_p2p_implicit, 1: h_Edit_p2p_explicit */
+  int32_t schedule;          /* 0: the reference's UNet call pattern (9 sample-forwards / step at K=1);
+                                1: exact-reuse merged pattern (7 / step): source-branch outputs of call C are reused
+                                   as the next step's call-A source inputs, calls B and C share one launch */
+  int32_t buffers_on_host;   /* 1: xT, zs, ctx, edited, recon, trace are host pointers (copies are part of the call) */
+  const float* xT;           /* [B][C][h][w] */
+  const float* zs;           /* [B][steps][C][h][w]; zs[b][idx] as in the reference (idx = steps-1-i at step i) */
+  const float* ctx;          /* [1+2B][ctx_len][cross_dim]: row 0 = "", then (src_b, tar_b) pairs (encode_text) */
+  const float* timesteps;    /* [steps+1]: t_0 .. t_{steps-1}, then the final previous timestep (0) */
+  const hedit_step_coef* coef; /* [steps] (host) */
+  float w_src, w_src_edit, w_tar;   /* cfg_scales */
+  float weight_reconstruction;
+  /* ---- Prompt-to-Prompt tables (host pointers); use_p2p = 0 runs every UNet call with use_controller=False */
+  int32_t use_p2p;
+  const int32_t* mapper;     /* [B][80]  AttentionRefine.mapper (clamped to [0,77)) */
+  const int32_t* is_replace; /* [B]      1: AttentionReplace matrix form */
+  const float* replace_m;    /* [B][77][80] or NULL */
+  const float* c_base;       /* [steps+1][B][80]  coefficient on the mapped source probability at controller step s */
+  const float* c_tar;        /* [steps+1][B][80]  coefficient on the target's own probability */
+  int32_t self_lo, self_hi;  /* AttentionControlEdit.num_self_replace */
+  int32_t self_max_tokens;   /* 32*32 (ptp_classes.py:196) */
+  const int32_t* has_blend;  /* [B] or NULL */
+  const float* blend_alpha;  /* [B][2][80]  LocalBlend.alpha_layers */
+  int32_t start_blend;       /* LocalBlend.start_blend */
+  float blend_th;            /* LocalBlend.th */
+  /* ---- outputs */
+  float* edited;             /* [B][C][h][w] */
+  float* recon;              /* [B][C][h][w] */
+  float* trace;              /* [steps][B][2][C][h][w] or NULL: xt after every timestep */
+  int64_t n_sample_forwards; /* out */
+  int64_t n_kernel_launches; /* out */
+} hedit_edit_args;
+
+const char* hedit_last_error(void);
+int hedit_device_count(void);
+
+/* engine lifetime: replaces copy.deepcopy(pipeline).to(device) per image (text-guided/main_p2p.py:119) with
+ * persistent device weights */
+hedit_engine* hedit_engine_create(const hedit_unet_config* cfg, int max_samples, int max_contexts, int device);
+void hedit_engine_destroy(hedit_engine* e);
+/* state-dict ingestion by diffusers parameter name (fp32, host or device pointer) */
+int hedit_engine_load_tensor(hedit_engine* e, const char* name, const float* data, const int64_t* dims, int ndim);
+int hedit_engine_finalize(hedit_engine* e);
+double hedit_engine_flops_per_sample(hedit_engine* e);
+
+/* model.unet(sample, t, encoder_hidden_states=ctx, cross_attention_kwargs={'use_controller': False}).sample
+ * (text-guided/inversion/p2p_h_edit.py:613).  x/eps: [S][C][h][w] device fp32; timesteps: [S] host; ctx:
+ * [S][ctx_len][cross_dim] host or device.  stream: cudaStream_t or NULL. */
+int hedit_unet_forward(hedit_engine* e, const float* x, const float* timesteps, const float* ctx, int S, float* eps, void* stream);
+
+/* the whole bridge-sampling loop for a batch of images */
+int hedit_edit_p2p(hedit_engine* e, hedit_edit_args* args, void* stream);
+
+/* ---- single operators, exposed for parity tests (device pointers) ------------------------------------------- */
+/* D[M][N] = A[M][K] W[N][K]^T (+bias) (+residual) -> fp32 and/or bf16; A, W bf16 */
+int hedit_op_linear(const void* A_bf16, const void* W_bf16, const float* bias, const float* residual, float* out_f32, void* out_bf16,
+                    int M, int N, int K, void* stream);
+/* 3x3 conv, pad 1, stride 1 or 2, NHWC bf16 in [S][Hin][Win][C], weights bf16 [Cout][3][3][C] -> fp32 NHWC */
+int hedit_op_conv3x3(const void* x_bf16, const void* w_bf16, const float* bias, float* out_f32, int S, int Hin, int Win, int C, int Cout,
+                     int stride, void* stream);
+/* softmax(Q K^T/sqrt(d)) V per (sample, head); q/k/v bf16 [S][N][H*d] with row strides ldq/ldkv; idx arrays may be NULL */
+int hedit_op_self_attention(const void* q, const void* k, const void* v, int ldq, int ldkv, int S, int Nq, int Nkv, int H, int d,
+                            const int32_t* q_idx, const int32_t* k_idx, const int32_t* v_idx, void* out_bf16, void* stream);
+/* N x 77 cross attention with the fused Prompt-to-Prompt edit (replaces P2PCrossAttnProcessor.__call__ +
+ * AttentionControlEdit.forward for is_cross=True: text-guided/p2p/ptp_utils.py:38-123, p2p/ptp_classes.py:202-283).
+ * q bf16 [S][Nq][H*d]; kv bf16 [n_ctx][77][2*H*d] (K | V); work units = single samples (s1 = -1) or (source, target) pairs. */
+int hedit_op_cross_attention_p2p(const void* q, const void* kv, int S, int n_ctx, int Nq, int H, int d, int n_units, const int32_t* unit_s0,
+                                 const int32_t* unit_s1, const int32_t* unit_img, const int32_t* ctx_idx, const int32_t* mapper,
+                                 const float* c_base, const float* c_tar, const float* replace_m, const int32_t* is_replace,
+                                 float* blend_acc, const float* blend_alpha, int blend_layer, int n_blend_layers, void* out_bf16, void* stream);
+/* GroupNorm(32 groups)(+SiLU): fp32 NHWC [S][HW][C] -> bf16 */
+int hedit_op_group_norm(const float* x, const float* gamma, const float* beta, void* out_bf16, int S, int HW, int C, int groups, float eps,
+                        int silu, void* stream);
+int hedit_op_layer_norm(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows, int C, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEDIT_B200_H */

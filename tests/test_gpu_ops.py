@@ -1,0 +1,177 @@
+"""-m gpu: operator-level parity of the hand-written sm_100a kernels (through the C ABI) against plain PyTorch fp32
+references of the same op evaluated on the SAME bf16-rounded operands.  Tolerances are stated per test: operands
+are bf16 (exactly representable in fp32), accumulation is fp32, so differences come from summation order
+(~1e-6 relative) plus, where the kernel writes bf16, one output rounding (2^-9 relative)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import P, bf, lib, rel_err, sync_check  # noqa: E402
+
+DEV = "cuda"
+
+
+def _seed(s=0):
+    torch.manual_seed(s)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 160, 64), (256, 320, 320), (4096, 960, 320), (1000, 1280, 1280), (77 * 3, 2560, 768),
+                                   (64, 64, 64), (4096 * 2, 320, 2880), (130, 48, 200)])
+def test_linear(M, N, K):
+    _seed()
+    A, W = bf(torch.randn(M, K, device=DEV)), bf(torch.randn(N, K, device=DEV) / math.sqrt(K))
+    bias, res = torch.randn(N, device=DEV), torch.randn(M, N, device=DEV)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    outb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    sync_check(lib().hedit_op_linear(P(A), P(W), P(bias), P(res), P(out), P(outb), M, N, K, None), "linear")
+    ref = A.float() @ W.float().t() + bias + res
+    r, m = rel_err(out, ref)
+    assert r < 2e-5, (r, m)          # fp32 accumulate, order-of-summation only
+    rb, _ = rel_err(outb, ref)
+    assert rb < 4e-3, rb             # + one bf16 rounding of the output
+
+
+@pytest.mark.parametrize("S,H,W,C,Cout,stride", [(2, 64, 64, 64, 64, 1), (1, 64, 64, 320, 320, 1), (3, 32, 32, 128, 256, 1),
+                                                 (5, 8, 8, 192, 160, 1), (4, 16, 16, 640, 320, 1), (2, 64, 64, 64, 128, 2),
+                                                 (3, 32, 32, 128, 128, 2), (5, 16, 16, 256, 256, 2), (9, 4, 4, 64, 64, 1), (2, 64, 64, 960, 320, 1)])
+def test_conv3x3(S, H, W, C, Cout, stride):
+    _seed(1)
+    x = bf(torch.randn(S, H, W, C, device=DEV))
+    w = bf(torch.randn(Cout, C, 3, 3, device=DEV) / math.sqrt(9 * C))
+    bias = torch.randn(Cout, device=DEV)
+    w_k = w.permute(0, 2, 3, 1).contiguous()          # [Cout][3][3][C]
+    Ho, Wo = H // stride, W // stride
+    out = torch.full((S, Ho, Wo, Cout), float("nan"), device=DEV)
+    sync_check(lib().hedit_op_conv3x3(P(x), P(w_k), P(bias), P(out), S, H, W, C, Cout, stride, None), "conv")
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=stride, padding=1).permute(0, 2, 3, 1)
+    r, m = rel_err(out, ref)
+    assert r < 2e-5, (r, m)
+
+
+def _attn_ref(q, k, v, H, d):
+    S, Nq, _ = q.shape
+    qh = q.float().reshape(S, Nq, H, d).permute(0, 2, 1, 3)
+    kh = k.float().reshape(S, -1, H, d).permute(0, 2, 1, 3)
+    vh = v.float().reshape(S, -1, H, d).permute(0, 2, 1, 3)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * d ** -0.5, dim=-1)
+    return (p @ vh).permute(0, 2, 1, 3).reshape(S, Nq, H * d)
+
+
+@pytest.mark.parametrize("S,N,H,d", [(2, 256, 8, 40), (1, 4096, 8, 40), (2, 1024, 8, 80), (3, 256, 8, 160), (2, 64, 8, 160),
+                                     (2, 16, 8, 8), (2, 1024, 4, 16), (1, 256, 8, 32), (2, 200, 2, 24)])
+def test_self_attention(S, N, H, d):
+    _seed(2)
+    C = H * d
+    qkv = bf(torch.randn(S, N, 3 * C, device=DEV) * 1.5)
+    out = torch.zeros(S, N, C, device=DEV, dtype=torch.bfloat16)
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    sync_check(lib().hedit_op_self_attention(P(q), P(k), P(v), 3 * C, 3 * C, S, N, N, H, d, None, None, None, P(out), None), "self attn")
+    ref = _attn_ref(q, k, v, H, d)
+    r, m = rel_err(out, ref)
+    # P is rounded to bf16 before P.V (same policy as the bf16 GEMM operands) and the output is bf16
+    assert r < 1e-2, (r, m)
+
+
+def test_self_attention_injection():
+    """P2P self-replace as a pointer swap: target sample reads the source sample's Q and K, keeps its own V."""
+    _seed(3)
+    S, N, H, d = 4, 256, 8, 40
+    C = H * d
+    qkv = bf(torch.randn(S, N, 3 * C, device=DEV))
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    idx = torch.tensor([0, 1, 2, 2], dtype=torch.int32, device=DEV)
+    out = torch.zeros(S, N, C, device=DEV, dtype=torch.bfloat16)
+    sync_check(lib().hedit_op_self_attention(P(q), P(k), P(v), 3 * C, 3 * C, S, N, N, H, d, P(idx), P(idx), None, P(out), None), "self attn idx")
+    li = idx.long()
+    ref = _attn_ref(q[li], k[li], v, H, d)
+    r, m = rel_err(out, ref)
+    assert r < 1e-2, (r, m)
+
+
+@pytest.mark.parametrize("N,H,d,replace", [(256, 8, 160, False), (4096, 8, 40, False), (1024, 8, 80, True), (64, 8, 160, False), (256, 8, 8, True)])
+def test_cross_attention_p2p(N, H, d, replace):
+    """Fused softmax -> P2P cross edit -> P.V against a torch restatement of ptp_classes.py:202-283 on the same operands."""
+    _seed(4)
+    C = H * d
+    S, n_ctx = 5, 3                       # samples: 0,1 plain (ctx 0), 2 = source (ctx 1), 3 = target (ctx 2), 4 plain (ctx 1)
+    q = bf(torch.randn(S, N, C, device=DEV))
+    kv = bf(torch.randn(n_ctx, 77, 2 * C, device=DEV))
+    ctx_idx = torch.tensor([0, 0, 1, 2, 1], dtype=torch.int32, device=DEV)
+    us0 = torch.tensor([0, 1, 2, 4], dtype=torch.int32, device=DEV)
+    us1 = torch.tensor([-1, -1, 3, -1], dtype=torch.int32, device=DEV)
+    uimg = torch.zeros(4, dtype=torch.int32, device=DEV)
+    g = torch.Generator().manual_seed(5)
+    mapper = torch.randint(0, 77, (1, 80), generator=g).int()
+    ra = (torch.rand(77, generator=g) > 0.3).float()
+    eq = torch.ones(77); eq[5] = 2.0
+    aw = (torch.rand(77, generator=g) > 0.2).float()
+    M = torch.rand(77, 77, generator=g) * (torch.rand(77, 77, generator=g) > 0.9).float()
+    if replace:
+        cb, ct = eq * aw, 1 - aw
+    else:
+        cb, ct = ra * eq * aw, (1 - ra) * eq * aw + (1 - aw)
+    pad = lambda t: torch.cat([t, torch.zeros(3)]).reshape(1, 80).to(DEV)
+    rm = torch.zeros(1, 77, 80); rm[0, :, :77] = M
+    blend_alpha = torch.zeros(1, 2, 80); blend_alpha[0, 0, 3] = 1; blend_alpha[0, 1, 4] = 1
+    nbl = 2
+    acc = torch.zeros(1, 2, nbl, H, N, device=DEV)
+    out = torch.zeros(S, N, C, device=DEV, dtype=torch.bfloat16)
+    isr = torch.tensor([1 if replace else 0], dtype=torch.int32, device=DEV)
+    d_map, d_cb, d_ct, d_rm, d_ba = mapper.to(DEV), pad(cb), pad(ct), rm.to(DEV), blend_alpha.to(DEV)     # keep alive across the launch
+    sync_check(lib().hedit_op_cross_attention_p2p(P(q), P(kv), S, n_ctx, N, H, d, 4, P(us0), P(us1), P(uimg), P(ctx_idx), P(d_map),
+                                                  P(d_cb), P(d_ct), P(d_rm), P(isr), P(acc), P(d_ba), 1, nbl, P(out), None),
+               "cross attn")
+    # reference
+    k, v = kv[..., :C], kv[..., C:]
+    li = ctx_idx.long()
+    qh = q.float().reshape(S, N, H, d).permute(0, 2, 1, 3)
+    kh = k[li].float().reshape(S, 77, H, d).permute(0, 2, 1, 3)
+    vh = v[li].float().reshape(S, 77, H, d).permute(0, 2, 1, 3)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * d ** -0.5, dim=-1)      # (S,H,N,77)
+    base, tar = p[2], p[3]
+    mp = mapper[0, :77].long().to(DEV)
+    if replace:
+        mapped = torch.einsum("hpw,wn->hpn", base, M.to(DEV)) * eq.to(DEV)
+    else:
+        mapped = (base[:, :, mp] * ra.to(DEV) + tar * (1 - ra.to(DEV))) * eq.to(DEV)
+    new = mapped * aw.to(DEV) + (1 - aw.to(DEV)) * tar
+    p = p.clone(); p[3] = new
+    ref = (p @ vh).permute(0, 2, 1, 3).reshape(S, N, C)
+    r, m = rel_err(out, ref)
+    assert r < 1e-2, (r, m)
+    ref_acc = torch.stack([(p[2] * blend_alpha[0, 0, :77].to(DEV)).sum(-1), (p[3] * blend_alpha[0, 1, :77].to(DEV)).sum(-1)])   # (2,H,N)
+    r2, m2 = rel_err(acc[0, :, 1], ref_acc)
+    assert r2 < 1e-4, (r2, m2)       # fp32 probabilities (ex2.approx), never rounded to bf16
+    assert acc[0, :, 0].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("S,HW,C,silu", [(2, 4096, 320, 1), (3, 256, 1280, 1), (2, 1024, 960, 0), (5, 64, 2560, 1), (2, 16, 64, 1)])
+def test_group_norm(S, HW, C, silu):
+    _seed(6)
+    x = torch.randn(S, HW, C, device=DEV) * 2 + 0.5
+    g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
+    out = torch.zeros(S, HW, C, device=DEV, dtype=torch.bfloat16)
+    sync_check(lib().hedit_op_group_norm(P(x), P(g), P(b), P(out), S, HW, C, 32, 1e-5, silu, None), "gn")
+    ref = F.group_norm(x.permute(0, 2, 1), 32, g, b, 1e-5).permute(0, 2, 1)
+    if silu:
+        ref = F.silu(ref)
+    r, m = rel_err(out, ref)
+    assert r < 4e-3, (r, m)          # one bf16 output rounding
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 1280), (77, 64), (256, 640)])
+def test_layer_norm(rows, C):
+    _seed(7)
+    x = torch.randn(rows, C, device=DEV) * 3 + 1
+    g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
+    out = torch.zeros(rows, C, device=DEV, dtype=torch.bfloat16)
+    sync_check(lib().hedit_op_layer_norm(P(x), P(g), P(b), P(out), rows, C, 1e-5, None), "ln")
+    ref = F.layer_norm(x, (C,), g, b, 1e-5)
+    r, m = rel_err(out, ref)
+    assert r < 4e-3, (r, m)
