@@ -46,6 +46,10 @@ SYMBOLS = {
     "hedit_engine_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
     "hedit_engine_finalize": (_I, [_P]),
     "hedit_engine_flops_per_sample": (C.c_double, [_P]),
+    "hedit_operand_dtype": (C.c_char_p, []),
+    "hedit_engine_tensor_count": (_I, [_P]),
+    "hedit_engine_tensor_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_int64)]),
+    "hedit_engine_profile_forward": (_I, [_P, _I, _I, C.c_char_p, _I]),
     "hedit_unet_forward": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "hedit_edit_p2p": (_I, [_P, C.POINTER(EditArgsC), _P]),
     "hedit_op_linear": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
@@ -75,6 +79,11 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def operand_torch_dtype():
+    import torch
+    return torch.float16 if load().hedit_operand_dtype() == b"fp16" else torch.bfloat16
 
 
 def last_error() -> str:

@@ -28,7 +28,7 @@ struct AttnParams {
   const int* q_idx;               // per sample: which sample's Q / K / V to read (null = own)
   const int* k_idx;
   const int* v_idx;
-  __nv_bfloat16* out;             // [S*Nq][ldo], head h at columns h*d
+  op_t* out;             // [S*Nq][ldo], head h at columns h*d
   int ldo;
   // ---- cross-attention only
   const int* unit_s0;             // per work unit: first sample
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(192) self_attn_kernel(const __grid_constant__ 
             l += e[i];
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+          for (int i = 0; i < 16; ++i) pk[i] = pack_op2(e[2 * i], e[2 * i + 1]);
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = 0u;
@@ -251,16 +251,16 @@ __global__ void __launch_bounds__(192) self_attn_kernel(const __grid_constant__ 
       tmem_ld16(tO + lane_sel + c, o);
       tmem_ld_wait();
       if (row < p.Nq) {
-        __nv_bfloat16* dst = p.out + (size_t(s) * p.Nq + row) * p.ldo + h * p.d + c;
+        op_t* dst = p.out + (size_t(s) * p.Nq + row) * p.ldo + h * p.d + c;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (c + g * 8 < p.d) {
             const int b = g * 8;
             *reinterpret_cast<uint4*>(dst + b) = make_uint4(
-                pack_bf16x2(__uint_as_float(o[b]) * inv, __uint_as_float(o[b + 1]) * inv),
-                pack_bf16x2(__uint_as_float(o[b + 2]) * inv, __uint_as_float(o[b + 3]) * inv),
-                pack_bf16x2(__uint_as_float(o[b + 4]) * inv, __uint_as_float(o[b + 5]) * inv),
-                pack_bf16x2(__uint_as_float(o[b + 6]) * inv, __uint_as_float(o[b + 7]) * inv));
+                pack_op2(__uint_as_float(o[b]) * inv, __uint_as_float(o[b + 1]) * inv),
+                pack_op2(__uint_as_float(o[b + 2]) * inv, __uint_as_float(o[b + 3]) * inv),
+                pack_op2(__uint_as_float(o[b + 4]) * inv, __uint_as_float(o[b + 5]) * inv),
+                pack_op2(__uint_as_float(o[b + 6]) * inv, __uint_as_float(o[b + 7]) * inv));
           }
         }
       }
@@ -431,8 +431,8 @@ __global__ void __launch_bounds__(192) cross_attn_kernel(const __grid_constant__
 #pragma unroll
         for (int u = 0; u < 2; ++u)
           *reinterpret_cast<uint4*>(tile + sw128_off(r, u0 + u)) =
-              make_uint4(pack_bf16x2(pr[8 * u], pr[8 * u + 1]), pack_bf16x2(pr[8 * u + 2], pr[8 * u + 3]),
-                         pack_bf16x2(pr[8 * u + 4], pr[8 * u + 5]), pack_bf16x2(pr[8 * u + 6], pr[8 * u + 7]));
+              make_uint4(pack_op2(pr[8 * u], pr[8 * u + 1]), pack_op2(pr[8 * u + 2], pr[8 * u + 3]),
+                         pack_op2(pr[8 * u + 4], pr[8 * u + 5]), pack_op2(pr[8 * u + 6], pr[8 * u + 7]));
       }
       if (do_blend && nph == 2) {
         float* acc = p.blend_acc + (((size_t(img) * 2 + ph) * p.n_blend_layers + p.blend_layer) * p.H + h) * p.Nq + row;
@@ -451,16 +451,16 @@ __global__ void __launch_bounds__(192) cross_attn_kernel(const __grid_constant__
         tmem_ld16(tO + lane_sel + c, o);
         tmem_ld_wait();
         if (row < p.Nq) {
-          __nv_bfloat16* dst = p.out + (size_t(s) * p.Nq + row) * p.ldo + h * p.d + c;
+          op_t* dst = p.out + (size_t(s) * p.Nq + row) * p.ldo + h * p.d + c;
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             if (c + g * 8 < p.d) {
               const int b = g * 8;
               *reinterpret_cast<uint4*>(dst + b) = make_uint4(
-                  pack_bf16x2(__uint_as_float(o[b]), __uint_as_float(o[b + 1])),
-                  pack_bf16x2(__uint_as_float(o[b + 2]), __uint_as_float(o[b + 3])),
-                  pack_bf16x2(__uint_as_float(o[b + 4]), __uint_as_float(o[b + 5])),
-                  pack_bf16x2(__uint_as_float(o[b + 6]), __uint_as_float(o[b + 7])));
+                  pack_op2(__uint_as_float(o[b]), __uint_as_float(o[b + 1])),
+                  pack_op2(__uint_as_float(o[b + 2]), __uint_as_float(o[b + 3])),
+                  pack_op2(__uint_as_float(o[b + 4]), __uint_as_float(o[b + 5])),
+                  pack_op2(__uint_as_float(o[b + 6]), __uint_as_float(o[b + 7])));
             }
           }
         }

@@ -1,7 +1,9 @@
 // extern "C" boundary (include/hedit_b200.h).  Plain pointers and sizes only.
 #include <cstring>
 #include <mutex>
+#include <map>
 #include <string>
+#include <vector>
 
 #include "../../include/hedit_b200.h"
 #include "elementwise.cuh"
@@ -90,6 +92,55 @@ int hedit_engine_finalize(hedit_engine* h) {
 
 double hedit_engine_flops_per_sample(hedit_engine* h) { return h ? h->E->flops_per_sample() : 0.0; }
 
+const char* hedit_operand_dtype(void) { return HEDIT_OPERAND_NAME; }
+
+int hedit_engine_tensor_count(hedit_engine* h) { return h ? h->E->tensor_count() : fail("null engine"); }
+
+int hedit_engine_tensor_info(hedit_engine* h, int index, char* name_buf, int name_len, int64_t* dims4) {
+  if (!h) return fail("null engine");
+  std::string name; std::vector<int64_t> shape;
+  if (!h->E->tensor_info(index, name, shape)) return fail("tensor index out of range");
+  if (int(name.size()) + 1 > name_len || shape.size() > 4) return fail("tensor_info buffer too small");
+  memcpy(name_buf, name.c_str(), name.size() + 1);
+  for (size_t i = 0; i < shape.size(); ++i) dims4[i] = shape[i];
+  return int(shape.size());
+}
+
+int hedit_engine_profile_forward(hedit_engine* h, int S, int reps, char* out, int out_len) {
+  if (!h) return fail("null engine");
+  cudaSetDevice(h->device);
+  Engine& E = *h->E;
+  if (S > h->cap) return fail("S exceeds max_samples");
+  const size_t lat = size_t(E.latent_elems());
+  float *x = nullptr, *eps = nullptr, *ctx = nullptr;
+  const size_t ctx_n = size_t(77) * E.cfg().ctx_dim;
+  if (cudaMalloc(&x, S * lat * sizeof(float)) != cudaSuccess || cudaMalloc(&eps, S * lat * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&ctx, ctx_n * sizeof(float)) != cudaSuccess)
+    return fail("cudaMalloc");
+  cudaMemset(x, 0, S * lat * sizeof(float)); cudaMemset(ctx, 0, ctx_n * sizeof(float));
+  const float t = 501.f;
+  std::vector<int> zeros(S, 0), ident(S), minus1(S, -1);
+  for (int s = 0; s < S; ++s) ident[s] = s;
+  if (E.set_timesteps(&t, 1, 0) || E.set_contexts(ctx, 1, 0)) return fail(E.error());
+  cudaMemcpy(h->d_tidx, zeros.data(), S * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_ctx_idx, zeros.data(), S * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_unit0, ident.data(), S * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_unit1, minus1.data(), S * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_uimg, zeros.data(), S * sizeof(int), cudaMemcpyHostToDevice);
+  CallCtrl cc;
+  cc.ctx_idx = h->d_ctx_idx; cc.time_idx = h->d_tidx; cc.unit_s0 = h->d_unit0; cc.unit_s1 = h->d_unit1; cc.unit_img = h->d_uimg; cc.n_units = S;
+  std::map<std::string, std::pair<double, long>> acc;
+  if (E.forward(x, eps, S, cc, 0) < 0) return fail(E.error());     // warm-up
+  for (int r = 0; r < reps; ++r)
+    if (E.forward_profiled(x, eps, S, cc, 0, acc) < 0) return fail(E.error());
+  cudaFree(x); cudaFree(eps); cudaFree(ctx);
+  std::string js;
+  for (auto& kv : acc) js += kv.first + ":" + std::to_string(kv.second.first / reps) + ":" + std::to_string(kv.second.second / reps) + ";";
+  if (int(js.size()) + 1 > out_len) return fail("profile buffer too small");
+  memcpy(out, js.c_str(), js.size() + 1);
+  return 0;
+}
+
 int hedit_unet_forward(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int S, float* eps, void* stream) {
   if (!h) return fail("null engine");
   cudaSetDevice(h->device);
@@ -147,7 +198,7 @@ int hedit_op_linear(const void* A, const void* W, const float* bias, const float
   uint64_t db[2] = {uint64_t(K), uint64_t(N)}, sb[1] = {uint64_t(K) * 2}; uint32_t bb[2] = {64, uint32_t(bn)};
   if (!make_tmap_bf16(&g.tmA, A, 2, da, sa, ba) || !make_tmap_bf16(&g.tmB, W, 2, db, sb, bb)) return fail("tensor map encode failed");
   g.ep.bias = bias; g.ep.residual = residual; g.ep.ldr = N; g.ep.out_f32 = out_f32; g.ep.ldo = N;
-  g.ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); g.ep.ldob = N; g.ep.rows_per_group = 1;
+  g.ep.out_bf16 = reinterpret_cast<op_t*>(out_bf16); g.ep.ldob = N; g.ep.rows_per_group = 1;
   cudaError_t e = launch_gemm(g, bn, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "linear launch");
   return 0;
@@ -201,7 +252,7 @@ int hedit_op_self_attention(const void* q, const void* k, const void* v, int ldq
   const int dch = d <= 64 ? 1 : (d <= 128 ? 2 : 3), bkv = d <= 128 ? 128 : 64;
   if (!attn_maps(a, q, ldq, Nq, S, k, v, ldkv, Nkv, S, H, d, bkv)) return fail("tensor map encode failed");
   a.H = H; a.d = d; a.Nq = Nq; a.Nkv = Nkv; a.scale_log2 = float(1.4426950408889634 / sqrt(double(d)));
-  a.q_idx = q_idx; a.k_idx = k_idx; a.v_idx = v_idx; a.out = reinterpret_cast<__nv_bfloat16*>(out); a.ldo = H * d;
+  a.q_idx = q_idx; a.k_idx = k_idx; a.v_idx = v_idx; a.out = reinterpret_cast<op_t*>(out); a.ldo = H * d;
   cudaError_t e = launch_self_attn(a, dch, S, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "self attention launch");
   return 0;
@@ -215,10 +266,10 @@ int hedit_op_cross_attention_p2p(const void* q, const void* kv, int S, int n_ctx
   AttnParams a; memset(&a, 0, sizeof a);
   const int C = H * d;
   const int dch = d <= 64 ? 1 : (d <= 128 ? 2 : 3);
-  const __nv_bfloat16* kvp = reinterpret_cast<const __nv_bfloat16*>(kv);
+  const op_t* kvp = reinterpret_cast<const op_t*>(kv);
   if (!attn_maps(a, q, C, Nq, S, kvp, kvp + C, 2 * C, 77, n_ctx, H, d, 80)) return fail("tensor map encode failed");
   a.H = H; a.d = d; a.Nq = Nq; a.Nkv = 77; a.scale_log2 = float(1.4426950408889634 / sqrt(double(d)));
-  a.out = reinterpret_cast<__nv_bfloat16*>(out); a.ldo = C;
+  a.out = reinterpret_cast<op_t*>(out); a.ldo = C;
   a.unit_s0 = unit_s0; a.unit_s1 = unit_s1; a.unit_img = unit_img; a.ctx_idx = ctx_idx; a.mapper = mapper; a.c_base = c_base; a.c_tar = c_tar;
   a.replace_m = replace_m; a.is_replace = is_replace; a.blend_acc = blend_acc; a.blend_alpha = blend_alpha; a.blend_layer = blend_layer;
   a.n_blend_layers = n_blend_layers;
@@ -236,7 +287,7 @@ int hedit_op_group_norm(const float* x, const float* gamma, const float* beta, v
   if (cudaMalloc(&partial, size_t(S) * nch * groups * sizeof(float2)) != cudaSuccess) return fail("cudaMalloc");
   GNStatsParams sp{x, nullptr, C, 0, HW, groups, chunk, partial};
   gn_stats_kernel<<<dim3(nch, S), std::min(640, ((C / 2 + 31) / 32) * 32), 0, st>>>(sp);
-  GNApplyParams ap{x, nullptr, C, 0, HW, groups, 16, nch, partial, gamma, beta, eps, silu, reinterpret_cast<__nv_bfloat16*>(out), nullptr};
+  GNApplyParams ap{x, nullptr, C, 0, HW, groups, 16, nch, partial, gamma, beta, eps, silu, reinterpret_cast<op_t*>(out), nullptr};
   gn_apply_kernel<<<dim3((HW + 15) / 16, S), 256, 2 * C * sizeof(float), st>>>(ap);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(partial);
@@ -246,7 +297,7 @@ int hedit_op_group_norm(const float* x, const float* gamma, const float* beta, v
 
 int hedit_op_layer_norm(const float* x, const float* gamma, const float* beta, void* out, int rows, int C, float eps, void* stream) {
   if (C % 64 || C > 2048) return fail("layer norm needs C % 64 == 0 and C <= 2048");
-  layernorm_kernel<32><<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), rows, C, eps);
+  layernorm_kernel<32><<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, gamma, beta, reinterpret_cast<op_t*>(out), rows, C, eps);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "layer norm launch");
   return 0;

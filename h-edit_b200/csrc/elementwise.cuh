@@ -50,8 +50,8 @@ struct GNApplyParams {
   const float2* partial;
   const float* gamma; const float* beta;
   float eps; int silu;
-  __nv_bfloat16* out;      // [S][HW][C]
-  __nv_bfloat16* raw_out;  // [S][HW][C] or null
+  op_t* out;      // [S][HW][C]
+  op_t* raw_out;  // [S][HW][C] or null
 };
 
 static __global__ void gn_apply_kernel(const GNApplyParams p) {
@@ -93,8 +93,8 @@ static __global__ void gn_apply_kernel(const GNApplyParams p) {
     float y2 = t.z * sa[c + 2] + sb[c + 2], y3 = t.w * sa[c + 3] + sb[c + 3];
     if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
     const size_t o = (size_t(s) * p.HW + px) * C + c;
-    *reinterpret_cast<uint2*>(p.out + o) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-    if (p.raw_out) *reinterpret_cast<uint2*>(p.raw_out + o) = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+    *reinterpret_cast<uint2*>(p.out + o) = make_uint2(pack_op2(y0, y1), pack_op2(y2, y3));
+    if (p.raw_out) *reinterpret_cast<uint2*>(p.raw_out + o) = make_uint2(pack_op2(t.x, t.y), pack_op2(t.z, t.w));
   }
 }
 
@@ -102,7 +102,7 @@ static __global__ void gn_apply_kernel(const GNApplyParams p) {
 // One warp per token row (C <= 2048, C % 64 == 0): row held in registers, two-pass mean / variance, bf16 out.
 template <int MAXV>   // MAXV float2 per lane
 static __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 __nv_bfloat16* __restrict__ out, int rows, int C, float eps) {
+                                 op_t* __restrict__ out, int rows, int C, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -123,27 +123,27 @@ static __global__ void layernorm_kernel(const float* __restrict__ x, const float
 #pragma unroll
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / C + eps);
-  __nv_bfloat16* orow = out + size_t(row) * C;
+  op_t* orow = out + size_t(row) * C;
 #pragma unroll
   for (int k = 0; k < MAXV; ++k)
     if (k < nv) {
       const int c = 2 * (lane + 32 * k);
       const float2 g = *reinterpret_cast<const float2*>(gamma + c);
       const float2 b = *reinterpret_cast<const float2*>(beta + c);
-      *reinterpret_cast<uint32_t*>(orow + c) = pack_bf16x2((v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y);
+      *reinterpret_cast<uint32_t*>(orow + c) = pack_op2((v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ casts / resampling
-static __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n4) {
+static __global__ void cast_bf16_kernel(const float* __restrict__ x, op_t* __restrict__ y, size_t n4) {
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
     const float4 t = reinterpret_cast<const float4*>(x)[i];
-    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_op2(t.x, t.y), pack_op2(t.z, t.w));
   }
 }
 
 // nearest 2x upsample, fp32 NHWC -> bf16 NHWC (operand of the following 3x3 conv)
-static __global__ void upsample2x_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int S, int H, int W, int C) {
+static __global__ void upsample2x_bf16_kernel(const float* __restrict__ x, op_t* __restrict__ y, int S, int H, int W, int C) {
   const int quads = C >> 2;
   const size_t total = size_t(S) * (2 * H) * (2 * W) * quads;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
@@ -153,7 +153,7 @@ static __global__ void upsample2x_bf16_kernel(const float* __restrict__ x, __nv_
     const int oy = int(r % (2 * H));
     const int s = int(r / (2 * H));
     const float4 t = *reinterpret_cast<const float4*>(x + ((size_t(s) * H + (oy >> 1)) * W + (ox >> 1)) * C + 4 * cq);
-    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_op2(t.x, t.y), pack_op2(t.z, t.w));
   }
 }
 
@@ -188,7 +188,7 @@ static __global__ void conv_in_kernel(const float* __restrict__ x, const float* 
 
 // conv_out: 3x3, C0 -> 4 channels; input bf16 NHWC (already GroupNorm+SiLU'd), output fp32 NCHW (the latent layout of the
 // reference).  One warp per output pixel; weights [4][C0][3][3] fp32 re-laid as [tap][C0][4] in shared memory.
-static __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+static __global__ void conv_out_kernel(const op_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                 float* __restrict__ y, int S, int H, int W, int C0) {
   extern __shared__ float sm[];          // [9][C0][4]
   for (int i = threadIdx.x; i < 36 * C0; i += blockDim.x) {
@@ -204,10 +204,10 @@ static __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, cons
     for (int tap = 0; tap < 9; ++tap) {
       const int yy = yo + tap / 3 - 1, xx = xo + tap % 3 - 1;
       if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const __nv_bfloat16* xr = x + ((size_t(s) * H + yy) * W + xx) * C0;
+      const op_t* xr = x + ((size_t(s) * H + yy) * W + xx) * C0;
       for (int c = 2 * lane; c < C0; c += 64) {
-        const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(xr + c);
-        const float x0 = __low2float(t), x1 = __high2float(t);
+        const float2 t = op2_to_float2(*reinterpret_cast<const uint32_t*>(xr + c));
+        const float x0 = t.x, x1 = t.y;
         const float4 w0 = *reinterpret_cast<const float4*>(&sm[(tap * C0 + c) * 4]);
         const float4 w1 = *reinterpret_cast<const float4*>(&sm[(tap * C0 + c + 1) * 4]);
         a0 = fmaf(x0, w0.x, fmaf(x1, w1.x, a0)); a1 = fmaf(x0, w0.y, fmaf(x1, w1.y, a1));

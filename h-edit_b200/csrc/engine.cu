@@ -33,7 +33,7 @@ __global__ void cvt_rows_bf16_kernel(const float* __restrict__ src, bf16* __rest
       const int ch = r >> 5, j = r & 31;
       sr = (j < 16) ? (ch * 16 + j) : (half_rows + ch * 16 + (j - 16));
     }
-    dst[i] = __float2bfloat16(src[size_t(sr) * K + k]);
+    dst[i] = to_op(src[size_t(sr) * K + k]);
   }
 }
 __global__ void perm_geglu_vec_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int half_rows) {
@@ -49,7 +49,7 @@ __global__ void cvt_conv3_bf16_kernel(const float* __restrict__ src, bf16* __res
     const int ci = int(i % I);
     const int tap = int((i / I) % 9);
     const int o = int(i / (size_t(I) * 9));
-    dst[i] = __float2bfloat16(src[(size_t(o) * I + ci) * 9 + tap]);
+    dst[i] = to_op(src[(size_t(o) * I + ci) * 9 + tap]);
   }
 }
 
@@ -684,86 +684,121 @@ Plan* Engine::get_plan(int S) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl& cc, cudaStream_t st) {
+  const UNetCfg& c = cfg_;
+  const size_t lat = size_t(c.in_ch) * c.sample * c.sample;
+  switch (op.kind) {
+    case OP_CONV_IN: {
+      CK(cudaMemcpyAsync(const_cast<float*>(op.f_in), x, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      const size_t sm = (36 * size_t(op.C1) + 12 * (op.W + 2)) * sizeof(float);
+      static bool set = false;
+      if (!set) { cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); set = true; }
+      conv_in_kernel<<<dim3(op.H, S), 256, sm, st>>>(op.f_in, conv_in_w_, conv_in_b_, op.f_out, op.H, op.W, op.C1);
+      break;
+    }
+    case OP_GN_STATS: {
+      GNStatsParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, op.chunk, op.partial};
+      const int half = (op.C1 + op.C2) / 2;
+      const int threads = std::min(640, ((half + 31) / 32) * 32);
+      gn_stats_kernel<<<dim3(op.nchunks, S), threads, 0, st>>>(p);
+      break;
+    }
+    case OP_GN_APPLY: {
+      const int C = op.C1 + op.C2;
+      const int chunk = 16;
+      GNApplyParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, chunk, op.nchunks, op.partial, op.gamma, op.beta, op.eps, op.silu, op.h_out, op.h_out2};
+      gn_apply_kernel<<<dim3((op.HW + chunk - 1) / chunk, S), 256, 2 * C * sizeof(float), st>>>(p);
+      break;
+    }
+    case OP_GEMM:
+      CK(launch_gemm(op.gemm, op.gemm_bn, st));
+      break;
+    case OP_LN:
+      layernorm_kernel<32><<<(op.rows + 7) / 8, 256, 0, st>>>(op.f_in, op.gamma, op.beta, op.h_out, op.rows, op.C1, op.eps);
+      break;
+    case OP_SELF_ATTN: {
+      AttnParams a = op.attn;
+      if (cc.self_mask & (1u << op.tf_index)) { a.q_idx = cc.self_q; a.k_idx = cc.self_k; a.v_idx = cc.self_v; }
+      CK(launch_self_attn(a, op.dch, S, st));
+      break;
+    }
+    case OP_CROSS_ATTN: {
+      AttnParams a = op.attn;
+      a.unit_s0 = cc.unit_s0; a.unit_s1 = cc.unit_s1; a.unit_img = cc.unit_img; a.ctx_idx = cc.ctx_idx;
+      a.mapper = cc.mapper; a.c_base = cc.c_base; a.c_tar = cc.c_tar; a.replace_m = cc.replace_m; a.is_replace = cc.is_replace;
+      a.blend_alpha = cc.blend_alpha; a.n_blend_layers = n_blend_layers_;
+      a.blend_layer = op.blend_layer;
+      a.blend_acc = (op.blend_layer >= 0) ? cc.blend_acc : nullptr;
+      CK(launch_cross_attn(a, op.dch, cc.n_units, st));
+      break;
+    }
+    case OP_UPSAMPLE: {
+      const size_t total = size_t(S) * 4 * op.H * op.W * (op.C1 / 4);
+      upsample2x_bf16_kernel<<<int(std::min<size_t>((total + 255) / 256, 8192)), 256, 0, st>>>(op.f_in, op.h_out, S, op.H, op.W, op.C1);
+      break;
+    }
+    case OP_CAST:
+      cast_bf16_kernel<<<int(std::min<size_t>((op.count + 255) / 256, 8192)), 256, 0, st>>>(op.f_in, op.h_out, op.count);
+      break;
+    case OP_CONV_OUT: {
+      static bool set = false;
+      if (!set) { cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); set = true; }
+      const size_t npix = size_t(S) * op.H * op.W;
+      conv_out_kernel<<<int(std::min<size_t>((npix + 7) / 8, 4096)), 256, 36 * size_t(op.C1) * sizeof(float), st>>>(
+          op.h_in, conv_out_w_, conv_out_b_, op.f_out, S, op.H, op.W, op.C1);
+      CK(cudaMemcpyAsync(eps, op.f_out, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      break;
+    }
+  }
+  return 1;
+}
+
 long Engine::forward(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st) {
   Plan* plan = get_plan(S);
   if (!plan) return -1;
-  const UNetCfg& c = cfg_;
   long launches = 0;
-  // per-call time-embedding rows
-  {
+  {   // per-call time-embedding rows
     dim3 grid(std::max(1, tproj_total_ / 4 / 256), S);
     gather_rows_kernel<<<grid, 256, 0, st>>>(temb_table_, cc.time_idx, temb_rows_, tproj_total_ / 4);
     ++launches;
   }
-  const size_t lat = size_t(c.in_ch) * c.sample * c.sample;
   for (Op& op : plan->ops) {
-    switch (op.kind) {
-      case OP_CONV_IN: {
-        CK(cudaMemcpyAsync(const_cast<float*>(op.f_in), x, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        const size_t sm = (36 * size_t(op.C1) + 12 * (op.W + 2)) * sizeof(float);
-        static bool set = false;
-        if (!set) { cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); set = true; }
-        conv_in_kernel<<<dim3(op.H, S), 256, sm, st>>>(op.f_in, conv_in_w_, conv_in_b_, op.f_out, op.H, op.W, op.C1);
-        break;
-      }
-      case OP_GN_STATS: {
-        GNStatsParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, op.chunk, op.partial};
-        const int half = (op.C1 + op.C2) / 2;
-        const int threads = std::min(640, ((half + 31) / 32) * 32);
-        gn_stats_kernel<<<dim3(op.nchunks, S), threads, 0, st>>>(p);
-        break;
-      }
-      case OP_GN_APPLY: {
-        const int C = op.C1 + op.C2;
-        const int chunk = 16;
-        GNApplyParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, chunk, op.nchunks, op.partial, op.gamma, op.beta, op.eps, op.silu, op.h_out, op.h_out2};
-        gn_apply_kernel<<<dim3((op.HW + chunk - 1) / chunk, S), 256, 2 * C * sizeof(float), st>>>(p);
-        break;
-      }
-      case OP_GEMM:
-        CK(launch_gemm(op.gemm, op.gemm_bn, st));
-        break;
-      case OP_LN:
-        layernorm_kernel<32><<<(op.rows + 7) / 8, 256, 0, st>>>(op.f_in, op.gamma, op.beta, op.h_out, op.rows, op.C1, op.eps);
-        break;
-      case OP_SELF_ATTN: {
-        AttnParams a = op.attn;
-        if (cc.self_mask & (1u << op.tf_index)) { a.q_idx = cc.self_q; a.k_idx = cc.self_k; a.v_idx = cc.self_v; }
-        CK(launch_self_attn(a, op.dch, S, st));
-        break;
-      }
-      case OP_CROSS_ATTN: {
-        AttnParams a = op.attn;
-        a.unit_s0 = cc.unit_s0; a.unit_s1 = cc.unit_s1; a.unit_img = cc.unit_img; a.ctx_idx = cc.ctx_idx;
-        a.mapper = cc.mapper; a.c_base = cc.c_base; a.c_tar = cc.c_tar; a.replace_m = cc.replace_m; a.is_replace = cc.is_replace;
-        a.blend_alpha = cc.blend_alpha; a.n_blend_layers = n_blend_layers_;
-        a.blend_layer = op.blend_layer;
-        a.blend_acc = (op.blend_layer >= 0) ? cc.blend_acc : nullptr;
-        CK(launch_cross_attn(a, op.dch, cc.n_units, st));
-        break;
-      }
-      case OP_UPSAMPLE: {
-        const size_t total = size_t(S) * 4 * op.H * op.W * (op.C1 / 4);
-        upsample2x_bf16_kernel<<<int(std::min<size_t>((total + 255) / 256, 8192)), 256, 0, st>>>(op.f_in, op.h_out, S, op.H, op.W, op.C1);
-        break;
-      }
-      case OP_CAST:
-        cast_bf16_kernel<<<int(std::min<size_t>((op.count + 255) / 256, 8192)), 256, 0, st>>>(op.f_in, op.h_out, op.count);
-        break;
-      case OP_CONV_OUT: {
-        static bool set = false;
-        if (!set) { cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); set = true; }
-        const size_t npix = size_t(S) * op.H * op.W;
-        conv_out_kernel<<<int(std::min<size_t>((npix + 7) / 8, 4096)), 256, 36 * size_t(op.C1) * sizeof(float), st>>>(
-            op.h_in, conv_out_w_, conv_out_b_, op.f_out, S, op.H, op.W, op.C1);
-        CK(cudaMemcpyAsync(eps, op.f_out, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        break;
-      }
-    }
+    if (launch_op(op, S, x, eps, cc, st) < 0) return -1;
     ++launches;
   }
   CK(cudaGetLastError());
   return launches;
+}
+
+long Engine::forward_profiled(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st, std::map<std::string, std::pair<double, long>>& acc) {
+  Plan* plan = get_plan(S);
+  if (!plan) return -1;
+  dim3 grid(std::max(1, tproj_total_ / 4 / 256), S);
+  gather_rows_kernel<<<grid, 256, 0, st>>>(temb_table_, cc.time_idx, temb_rows_, tproj_total_ / 4);
+  std::vector<cudaEvent_t> ev(plan->ops.size() + 1);
+  for (auto& e : ev) cudaEventCreate(&e);
+  cudaEventRecord(ev[0], st);
+  for (size_t i = 0; i < plan->ops.size(); ++i) {
+    if (launch_op(plan->ops[i], S, x, eps, cc, st) < 0) return -1;
+    cudaEventRecord(ev[i + 1], st);
+  }
+  CK(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < plan->ops.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+    auto& a = acc[plan->ops[i].tag];
+    a.first += ms; a.second += 1;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return long(plan->ops.size()) + 1;
+}
+
+bool Engine::tensor_info(int i, std::string& name, std::vector<int64_t>& shape) const {
+  if (i < 0 || i >= int(slots_.size())) return false;
+  auto it = slots_.begin();
+  std::advance(it, i);
+  name = it->first; shape = it->second.shape;
+  return true;
 }
 
 }  // namespace hedit

@@ -14,7 +14,7 @@
 
 namespace hedit {
 
-typedef __nv_bfloat16 bf16;
+typedef op_t bf16;   // historical alias: "the 16-bit operand type"
 
 struct UNetCfg {
   int in_ch = 4, out_ch = 4, sample = 64;
@@ -100,6 +100,10 @@ class Engine {
 
   // x [S][4][h][w] fp32 NCHW (device) -> eps [S][4][h][w] (device).  Returns kernels launched, <0 on error.
   long forward(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st);
+  // Same launches with a CUDA-event pair around every op; accumulates milliseconds per op tag (diagnostics / bench roofline).
+  long forward_profiled(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st, std::map<std::string, std::pair<double, long>>& acc);
+  int tensor_count() const { return int(slots_.size()); }
+  bool tensor_info(int i, std::string& name, std::vector<int64_t>& shape) const;
 
   const UNetCfg& cfg() const { return cfg_; }
   int max_samples() const { return maxS_; }
@@ -115,6 +119,7 @@ class Engine {
  private:
   friend struct PlanBuilder;
   Plan* get_plan(int S);
+  long launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl& cc, cudaStream_t st);
   void reg(const std::string& name, WeightSlot::Kind k, void* dst, size_t off, std::vector<int64_t> shape);
   template <typename T> T* dalloc(size_t n);
 

@@ -22,7 +22,7 @@ struct GemmEpilogue {
   const float* rowvec;      // [groups][ldrv] or null; group = row / rows_per_group (time-embedding add)
   const float* residual;    // [M][ldr] fp32 or null
   float* out_f32;           // [M][ldo] or null
-  __nv_bfloat16* out_bf16;  // [M][ldob] or null
+  op_t* out_bf16;  // [M][ldob] or null
   int rows_per_group, ldrv, ldr, ldo, ldob;
   int geglu;                // 1: every 32-col chunk = 16 value | 16 gate -> bf16 out has N/2 columns
 };
@@ -184,11 +184,11 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tcgen05_kernel(const __grid_
           }
           if (e.geglu) {
             // chunk = 16 value columns followed by their 16 gate columns -> 16 outputs
-            __nv_bfloat16* o = e.out_bf16 + size_t(row) * e.ldob + (col >> 1);
+            op_t* o = e.out_bf16 + size_t(row) * e.ldob + (col >> 1);
             uint32_t pk[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2)
-              pk[j >> 1] = pack_bf16x2(v[j] * gelu_erf_f(v[16 + j]), v[j + 1] * gelu_erf_f(v[17 + j]));
+              pk[j >> 1] = pack_op2(v[j] * gelu_erf_f(v[16 + j]), v[j + 1] * gelu_erf_f(v[17 + j]));
             *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             continue;
@@ -207,11 +207,11 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tcgen05_kernel(const __grid_
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
           if (e.out_bf16) {
-            __nv_bfloat16* o = e.out_bf16 + size_t(row) * e.ldob + col;
+            op_t* o = e.out_bf16 + size_t(row) * e.ldob + col;
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
-              *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                                                            pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+              *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_op2(v[j], v[j + 1]), pack_op2(v[j + 2], v[j + 3]),
+                                                            pack_op2(v[j + 4], v[j + 5]), pack_op2(v[j + 6], v[j + 7]));
           }
         } else {
           // ragged tail (N not a multiple of 32): scalar, no geglu
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tcgen05_kernel(const __grid_
             if (rv) x += rv[col + j];
             if (e.residual) x += e.residual[size_t(row) * e.ldr + col + j];
             if (e.out_f32) e.out_f32[size_t(row) * e.ldo + col + j] = x;
-            if (e.out_bf16) e.out_bf16[size_t(row) * e.ldob + col + j] = __float2bfloat16(x);
+            if (e.out_bf16) e.out_bf16[size_t(row) * e.ldob + col + j] = to_op(x);
           }
         }
       }

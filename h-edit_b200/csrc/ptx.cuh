@@ -3,10 +3,27 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace hedit {
+
+// 16-bit tensor-core operand type.  Default fp16 (11-bit significand): same tcgen05 kind::f16 throughput as bf16
+// with 8x smaller operand rounding error, which is what bounds parity against the reference's fp32 UNet.  Range is
+// not an issue for SD-1.x (normalised activations, fp32 residual stream and accumulators).  -DHEDIT_OPERAND_BF16
+// switches every kernel to bf16 operands.
+#ifdef HEDIT_OPERAND_BF16
+typedef __nv_bfloat16 op_t;
+#define HEDIT_UMMA_FMT 1u
+#define HEDIT_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define HEDIT_OPERAND_NAME "bf16"
+#else
+typedef __half op_t;
+#define HEDIT_UMMA_FMT 0u
+#define HEDIT_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define HEDIT_OPERAND_NAME "fp16"
+#endif
 
 #define HEDIT_DEVICE __device__ __forceinline__
 
@@ -168,18 +185,36 @@ HEDIT_DEVICE uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_
 }
 HEDIT_DEVICE uint64_t umma_desc_kmajor_sw128(uint32_t saddr) { return umma_smem_desc(saddr, 16, 1024); }
 
-// Instruction descriptor (kind::f16): fp32 accumulate, bf16 A/B.
-//   [4,6) c_format=1(F32)  [7,10) a_format=1(BF16)  [10,13) b_format=1(BF16)
+// Instruction descriptor (kind::f16): fp32 accumulate, 16-bit A/B.
+//   [4,6) c_format=1(F32)  [7,10) a_format (0=F16, 1=BF16)  [10,13) b_format
 //   [15] a_major (0=K,1=MN) [16] b_major            [17,23) N>>3          [24,29) M>>4
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
+  return (1u << 4) | (HEDIT_UMMA_FMT << 7) | (HEDIT_UMMA_FMT << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
          (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- misc math / packing
-HEDIT_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
+HEDIT_DEVICE uint32_t pack_op2(float lo, float hi) {
+#ifdef HEDIT_OPERAND_BF16
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+#else
+  __half2 v = __floats2half2_rn(lo, hi);
+#endif
   return *reinterpret_cast<uint32_t*>(&v);
+}
+HEDIT_DEVICE op_t to_op(float x) {
+#ifdef HEDIT_OPERAND_BF16
+  return __float2bfloat16(x);
+#else
+  return __float2half_rn(x);
+#endif
+}
+HEDIT_DEVICE float2 op2_to_float2(uint32_t u) {
+#ifdef HEDIT_OPERAND_BF16
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+#else
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+#endif
 }
 HEDIT_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 HEDIT_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include "ptx.cuh"
+
 namespace hedit {
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -23,7 +25,7 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-// bf16 tensor, `rank` dims (dim 0 innermost, contiguous).  strides_bytes[i] is the byte stride of dim i+1
+// 16-bit operand tensor (op_t), `rank` dims (dim 0 innermost, contiguous).  strides_bytes[i] is the byte stride of dim i+1
 // (rank-1 entries).  128-byte swizzle; out-of-bounds elements read as zero.
 inline bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box) {
@@ -33,7 +35,7 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const u
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = enc(out, HEDIT_TMAP_DTYPE, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

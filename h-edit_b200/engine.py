@@ -65,6 +65,46 @@ class UNetEngine:
         eng.load_state_dict(unet.state_dict())
         return eng
 
+    def tensor_specs(self):
+        """[(diffusers parameter name, shape)] the engine expects."""
+        out = []
+        buf = C.create_string_buffer(256)
+        dims = (C.c_int64 * 4)()
+        for i in range(self.lib.hedit_engine_tensor_count(self.handle)):
+            nd = _lib.check(self.lib.hedit_engine_tensor_info(self.handle, i, buf, 256, dims), "tensor_info")
+            out.append((buf.value.decode(), tuple(int(dims[k]) for k in range(nd))))
+        return out
+
+    def load_random_weights(self, seed: int = 0) -> None:
+        """Synthetic random-init weights generated on the device (benchmarks: no pretrained weights exist offline).
+        Variance-preserving scale; norm gammas near 1."""
+        g = torch.Generator(device=f"cuda:{self.device}").manual_seed(seed)
+        dev = torch.device("cuda", self.device)
+        for name, shape in self.tensor_specs():
+            if len(shape) >= 2:
+                fan_in = 1
+                for d in shape[1:]:
+                    fan_in *= d
+                t = (torch.rand(shape, generator=g, device=dev) * 2 - 1) * (3.0 / fan_in) ** 0.5
+            elif name.endswith("weight"):
+                t = 0.8 + 0.4 * torch.rand(shape, generator=g, device=dev)
+            else:
+                t = (torch.rand(shape, generator=g, device=dev) * 2 - 1) * 0.1
+            dims = (C.c_int64 * len(shape))(*shape)
+            _lib.check(self.lib.hedit_engine_load_tensor(self.handle, name.encode(), t.data_ptr(), dims, len(shape)), f"load {name}")
+        _lib.check(self.lib.hedit_engine_finalize(self.handle), "finalize weights")
+
+    def profile_forward(self, S: int, reps: int = 3):
+        """{op tag: (ms per forward, launches per forward)} measured with CUDA events around every kernel."""
+        buf = C.create_string_buffer(8192)
+        _lib.check(self.lib.hedit_engine_profile_forward(self.handle, S, reps, buf, 8192), "profile")
+        out = {}
+        for rec in buf.value.decode().split(";"):
+            if rec:
+                tag, ms, n = rec.split(":")
+                out[tag] = (float(ms), int(n))
+        return out
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

@@ -43,3 +43,26 @@ def step_tables(scheduler, after_skip_steps: int, eta, is_ddim_inversion: bool) 
         coeff = full - sig[t] * (a[tt] / a[t])
         coef[i] = [float((1 - a_t) ** 0.5), float(a_t ** 0.5), float(a_p ** 0.5), float(direction), float(noise), float(coeff)]
     return ts + [0], coef
+
+
+class DDIMTables:
+    """Minimal DDIM scheduler state for callers that have no diffusers scheduler object (benchmarks, tests):
+    scaled-linear betas 0.00085..0.012 over 1000 train steps, set_alpha_to_one=False, "leading" timestep spacing
+    with steps_offset (1 for the SD hub config used when eta > 0, 0 for the eta = 0 scheduler built at
+    text-guided/main_p2p.py:139-146)."""
+
+    class _Cfg:
+        pass
+
+    def __init__(self, num_inference_steps: int, steps_offset: int = 1, num_train_timesteps: int = 1000,
+                 beta_start: float = 0.00085, beta_end: float = 0.012):
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        self.alphas = 1.0 - betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.final_alpha_cumprod = self.alphas_cumprod[0]
+        self.config = DDIMTables._Cfg()
+        self.config.num_train_timesteps = num_train_timesteps
+        self.config.steps_offset = steps_offset
+        self.num_inference_steps = num_inference_steps
+        ratio = num_train_timesteps // num_inference_steps
+        self.timesteps = (torch.arange(0, num_inference_steps) * ratio).round().flip(0).to(torch.int64) + steps_offset

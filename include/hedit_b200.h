@@ -84,6 +84,13 @@ void hedit_engine_destroy(hedit_engine* e);
 int hedit_engine_load_tensor(hedit_engine* e, const char* name, const float* data, const int64_t* dims, int ndim);
 int hedit_engine_finalize(hedit_engine* e);
 double hedit_engine_flops_per_sample(hedit_engine* e);
+/* "fp16" (default) or "bf16": the 16-bit tensor-core operand type this build uses for activations/weights */
+const char* hedit_operand_dtype(void);
+/* enumerate the state-dict tensors the engine expects (diffusers parameter names): returns ndim, fills dims4 */
+int hedit_engine_tensor_count(hedit_engine* e);
+int hedit_engine_tensor_info(hedit_engine* e, int index, char* name_buf, int name_len, int64_t* dims4);
+/* diagnostics: one UNet forward of S samples with CUDA events around every kernel; writes "tag:ms:launches;" records */
+int hedit_engine_profile_forward(hedit_engine* e, int S, int reps, char* out, int out_len);
 
 /* model.unet(sample, t, encoder_hidden_states=ctx, cross_attention_kwargs={'use_controller': False}).sample
  * (text-guided/inversion/p2p_h_edit.py:613).  x/eps: [S][C][h][w] device fp32; timesteps: [S] host; ctx:
@@ -94,26 +101,26 @@ int hedit_unet_forward(hedit_engine* e, const float* x, const float* timesteps, 
 int hedit_edit_p2p(hedit_engine* e, hedit_edit_args* args, void* stream);
 
 /* ---- single operators, exposed for parity tests (device pointers) ------------------------------------------- */
-/* D[M][N] = A[M][K] W[N][K]^T (+bias) (+residual) -> fp32 and/or bf16; A, W bf16 */
-int hedit_op_linear(const void* A_bf16, const void* W_bf16, const float* bias, const float* residual, float* out_f32, void* out_bf16,
+/* D[M][N] = A[M][K] W[N][K]^T (+bias) (+residual) -> fp32 and/or 16-bit; A, W in the operand dtype (hedit_operand_dtype) */
+int hedit_op_linear(const void* A_h16, const void* W_h16, const float* bias, const float* residual, float* out_f32, void* out_h16,
                     int M, int N, int K, void* stream);
-/* 3x3 conv, pad 1, stride 1 or 2, NHWC bf16 in [S][Hin][Win][C], weights bf16 [Cout][3][3][C] -> fp32 NHWC */
-int hedit_op_conv3x3(const void* x_bf16, const void* w_bf16, const float* bias, float* out_f32, int S, int Hin, int Win, int C, int Cout,
+/* 3x3 conv, pad 1, stride 1 or 2, NHWC 16-bit in [S][Hin][Win][C], weights 16-bit [Cout][3][3][C] -> fp32 NHWC */
+int hedit_op_conv3x3(const void* x_h16, const void* w_h16, const float* bias, float* out_f32, int S, int Hin, int Win, int C, int Cout,
                      int stride, void* stream);
-/* softmax(Q K^T/sqrt(d)) V per (sample, head); q/k/v bf16 [S][N][H*d] with row strides ldq/ldkv; idx arrays may be NULL */
+/* softmax(Q K^T/sqrt(d)) V per (sample, head); q/k/v 16-bit [S][N][H*d] with row strides ldq/ldkv; idx arrays may be NULL */
 int hedit_op_self_attention(const void* q, const void* k, const void* v, int ldq, int ldkv, int S, int Nq, int Nkv, int H, int d,
-                            const int32_t* q_idx, const int32_t* k_idx, const int32_t* v_idx, void* out_bf16, void* stream);
+                            const int32_t* q_idx, const int32_t* k_idx, const int32_t* v_idx, void* out_h16, void* stream);
 /* N x 77 cross attention with the fused Prompt-to-Prompt edit (replaces P2PCrossAttnProcessor.__call__ +
  * AttentionControlEdit.forward for is_cross=True: text-guided/p2p/ptp_utils.py:38-123, p2p/ptp_classes.py:202-283).
- * q bf16 [S][Nq][H*d]; kv bf16 [n_ctx][77][2*H*d] (K | V); work units = single samples (s1 = -1) or (source, target) pairs. */
+ * q 16-bit [S][Nq][H*d]; kv 16-bit [n_ctx][77][2*H*d] (K | V); work units = single samples (s1 = -1) or (source, target) pairs. */
 int hedit_op_cross_attention_p2p(const void* q, const void* kv, int S, int n_ctx, int Nq, int H, int d, int n_units, const int32_t* unit_s0,
                                  const int32_t* unit_s1, const int32_t* unit_img, const int32_t* ctx_idx, const int32_t* mapper,
                                  const float* c_base, const float* c_tar, const float* replace_m, const int32_t* is_replace,
-                                 float* blend_acc, const float* blend_alpha, int blend_layer, int n_blend_layers, void* out_bf16, void* stream);
-/* GroupNorm(32 groups)(+SiLU): fp32 NHWC [S][HW][C] -> bf16 */
-int hedit_op_group_norm(const float* x, const float* gamma, const float* beta, void* out_bf16, int S, int HW, int C, int groups, float eps,
+                                 float* blend_acc, const float* blend_alpha, int blend_layer, int n_blend_layers, void* out_h16, void* stream);
+/* GroupNorm(32 groups)(+SiLU): fp32 NHWC [S][HW][C] -> 16-bit operand dtype */
+int hedit_op_group_norm(const float* x, const float* gamma, const float* beta, void* out_h16, int S, int HW, int C, int groups, float eps,
                         int silu, void* stream);
-int hedit_op_layer_norm(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows, int C, float eps, void* stream);
+int hedit_op_layer_norm(const float* x, const float* gamma, const float* beta, void* out_h16, int rows, int C, float eps, void* stream);
 
 #ifdef __cplusplus
 }

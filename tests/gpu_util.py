@@ -15,7 +15,12 @@ def lib():
 
 
 def bf(t):
-    return t.to(torch.bfloat16).contiguous()
+    """Round to the library's 16-bit operand dtype (fp16 by default, bf16 with -DHEDIT_OPERAND_BF16)."""
+    return t.to(_lib.operand_torch_dtype()).contiguous()
+
+
+def opdtype():
+    return _lib.operand_torch_dtype()
 
 
 def sync_check(rc, what):

@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-from gpu_util import P, bf, lib, rel_err, sync_check  # noqa: E402
+from gpu_util import P, bf, lib, opdtype, rel_err, sync_check  # noqa: E402
 
 DEV = "cuda"
 
@@ -28,7 +28,7 @@ def test_linear(M, N, K):
     A, W = bf(torch.randn(M, K, device=DEV)), bf(torch.randn(N, K, device=DEV) / math.sqrt(K))
     bias, res = torch.randn(N, device=DEV), torch.randn(M, N, device=DEV)
     out = torch.full((M, N), float("nan"), device=DEV)
-    outb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    outb = torch.zeros(M, N, device=DEV, dtype=opdtype())
     sync_check(lib().hedit_op_linear(P(A), P(W), P(bias), P(res), P(out), P(outb), M, N, K, None), "linear")
     ref = A.float() @ W.float().t() + bias + res
     r, m = rel_err(out, ref)
@@ -69,7 +69,7 @@ def test_self_attention(S, N, H, d):
     _seed(2)
     C = H * d
     qkv = bf(torch.randn(S, N, 3 * C, device=DEV) * 1.5)
-    out = torch.zeros(S, N, C, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(S, N, C, device=DEV, dtype=opdtype())
     q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
     sync_check(lib().hedit_op_self_attention(P(q), P(k), P(v), 3 * C, 3 * C, S, N, N, H, d, None, None, None, P(out), None), "self attn")
     ref = _attn_ref(q, k, v, H, d)
@@ -86,7 +86,7 @@ def test_self_attention_injection():
     qkv = bf(torch.randn(S, N, 3 * C, device=DEV))
     q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
     idx = torch.tensor([0, 1, 2, 2], dtype=torch.int32, device=DEV)
-    out = torch.zeros(S, N, C, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(S, N, C, device=DEV, dtype=opdtype())
     sync_check(lib().hedit_op_self_attention(P(q), P(k), P(v), 3 * C, 3 * C, S, N, N, H, d, P(idx), P(idx), None, P(out), None), "self attn idx")
     li = idx.long()
     ref = _attn_ref(q[li], k[li], v, H, d)
@@ -121,7 +121,7 @@ def test_cross_attention_p2p(N, H, d, replace):
     blend_alpha = torch.zeros(1, 2, 80); blend_alpha[0, 0, 3] = 1; blend_alpha[0, 1, 4] = 1
     nbl = 2
     acc = torch.zeros(1, 2, nbl, H, N, device=DEV)
-    out = torch.zeros(S, N, C, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(S, N, C, device=DEV, dtype=opdtype())
     isr = torch.tensor([1 if replace else 0], dtype=torch.int32, device=DEV)
     d_map, d_cb, d_ct, d_rm, d_ba = mapper.to(DEV), pad(cb), pad(ct), rm.to(DEV), blend_alpha.to(DEV)     # keep alive across the launch
     sync_check(lib().hedit_op_cross_attention_p2p(P(q), P(kv), S, n_ctx, N, H, d, 4, P(us0), P(us1), P(uimg), P(ctx_idx), P(d_map),
@@ -156,7 +156,7 @@ def test_group_norm(S, HW, C, silu):
     _seed(6)
     x = torch.randn(S, HW, C, device=DEV) * 2 + 0.5
     g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
-    out = torch.zeros(S, HW, C, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(S, HW, C, device=DEV, dtype=opdtype())
     sync_check(lib().hedit_op_group_norm(P(x), P(g), P(b), P(out), S, HW, C, 32, 1e-5, silu, None), "gn")
     ref = F.group_norm(x.permute(0, 2, 1), 32, g, b, 1e-5).permute(0, 2, 1)
     if silu:
@@ -170,7 +170,7 @@ def test_layer_norm(rows, C):
     _seed(7)
     x = torch.randn(rows, C, device=DEV) * 3 + 1
     g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
-    out = torch.zeros(rows, C, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(rows, C, device=DEV, dtype=opdtype())
     sync_check(lib().hedit_op_layer_norm(P(x), P(g), P(b), P(out), rows, C, 1e-5, None), "ln")
     ref = F.layer_norm(x, (C,), g, b, 1e-5)
     r, m = rel_err(out, ref)

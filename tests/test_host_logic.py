@@ -1,0 +1,119 @@
+"""CPU: host-side logic of the product package (no GPU, no compute calls into the library)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import hedit_b200
+from hedit_b200 import _lib, p2p
+from oracle import h_edit as oh
+from oracle import p2p as op
+from oracle.pipeline import DDIMSchedulerTables, ToyTokenizer
+from refload import load_reference, reference_available
+from test_oracle_pin import PAIRS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hedit_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(hedit_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/hedit_b200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == declared, "ctypes table and header disagree"
+
+
+def test_engine_creation_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        hedit_b200.UNetEngine(dict(in_channels=4, out_channels=4, sample_size=64, block_out_channels=(64, 128, 256, 256),
+                                   layers_per_block=2, heads=8, cross_attention_dim=64, norm_groups=32, ctx_len=77), max_samples=2)
+
+
+@pytest.mark.parametrize("T,skip,eta,ddim", [(50, 0, 1.0, False), (10, 0, 1.0, False), (50, 15, 1.0, False), (20, 0, 1.0, True), (10, 2, 0.6, False)])
+def test_step_tables_match_oracle_scheduler_algebra(T, skip, eta, ddim):
+    """schedule.step_tables reproduces reverse_step / compute_full_coeff (oracle restatement of inversion_utils.py)."""
+    sched = DDIMSchedulerTables(steps_offset=0 if ddim else 1)
+    sched.set_timesteps(T)
+    S = T - skip
+    ts, coef = hedit_b200.step_tables(sched, S, eta, ddim)
+    op_ts = [int(t) for t in sched.timesteps[-S:]]
+    assert ts == op_ts + [0]
+    g = torch.Generator().manual_seed(0)
+    for i, t in enumerate(op_ts):
+        x, eps, z = (torch.randn(2, 4, 8, 8, generator=g) for _ in range(3))
+        ref = oh.reverse_step(sched, eps, t, x, eta, z, ddim)
+        k = coef[i]
+        x0 = (x - k[0] * eps) / k[1]
+        mine = (k[2] * x0 + k[3] * eps) + k[4] * z
+        assert (mine - ref).abs().max().item() < 2e-5
+        tt = ts[i + 1]
+        ab = sched.alphas_cumprod
+        c_ref = oh.full_coeff(sched, t, tt, eta, ddim) - (1 - ab[t]) ** 0.5 * (ab[tt] ** 0.5 / ab[t] ** 0.5)
+        assert abs(float(c_ref) - float(k[5])) < 1e-6
+
+
+@pytest.mark.parametrize("prompts,bw_src,bw_tar", PAIRS)
+@pytest.mark.parametrize("is_replace", [False, True])
+def test_product_controller_tables_match_oracle(prompts, bw_src, bw_tar, is_replace):
+    tok = ToyTokenizer()
+    if is_replace and len(prompts[0].split(" ")) != len(prompts[1].split(" ")):
+        pytest.skip("replace controller needs equal word counts")
+    T = 10
+    eqp = {"words": (bw_tar,), "values": (2.0,)}
+    c = hedit_b200.make_controller(prompts, is_replace, 0.4, 0.35, blend_word=((bw_src,), (bw_tar,)), equilizer_params=eqp, num_steps=T, tokenizer=tok)
+    s = op.make_edit_spec(prompts, is_replace, 0.4, 0.35, ((bw_src,), (bw_tar,)), eqp, T, tok)
+    assert torch.equal(c.cross_replace_alpha.reshape(T + 1, 77), s.alpha_words)
+    assert tuple(c.num_self_replace) == tuple(s.self_window)
+    assert torch.equal(c.equalizer.reshape(77), s.equalizer)
+    assert torch.equal(c.local_blend.alpha_layers.reshape(2, 77), s.blend_alpha)
+    if is_replace:
+        assert torch.equal(c.mapper[0], s.replace_matrix)
+    else:
+        assert torch.equal(c.mapper[0], s.mapper) and torch.equal(c.alphas.reshape(77), s.refine_alpha)
+    # compiled plan == the oracle's edit formula evaluated on random probabilities
+    plan = hedit_b200.compile_edit_plan([c], T)
+    g = torch.Generator().manual_seed(1)
+    base, tar = torch.rand(3, 5, 77, generator=g), torch.rand(3, 5, 77, generator=g)
+    for step in (0, 3, 4, 9):
+        aw = s.alpha_words[step]
+        want = op._mapped_base(s, base, tar) * aw + (1 - aw) * tar
+        cb, ct = torch.from_numpy(plan.c_base[step, 0, :77]), torch.from_numpy(plan.c_tar[step, 0, :77])
+        if is_replace:
+            mapped = torch.einsum("hpw,wn->hpn", base, torch.from_numpy(plan.replace_m[0, :, :77]))
+        else:
+            mapped = base[:, :, torch.from_numpy(plan.mapper[0, :77]).long()]
+        got = mapped * cb + tar * ct
+        assert (got - want).abs().max().item() < 1e-6
+    assert plan.has_blend.tolist() == [1] and plan.start_blend == s.start_blend
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_compile_edit_plan_accepts_reference_controller_objects():
+    ref = load_reference()
+    tok = ToyTokenizer()
+    prompts = PAIRS[0][0]
+    T = 8
+    kw = dict(cross_replace_steps=0.4, self_replace_steps=0.35, blend_word=(("lizard",), ("lizard",)),
+              equilizer_params={"words": ("lizard",), "values": (2.0,)}, num_steps=T, tokenizer=tok)
+    c_ref = ref.ptp_controller_utils.make_controller(prompts=prompts, is_replace_controller=False, device="cpu", **kw)
+    c_own = hedit_b200.make_controller(prompts, False, **kw)
+    a, b = hedit_b200.compile_edit_plan([c_ref], T), hedit_b200.compile_edit_plan([c_own], T)
+    for f in ("mapper", "is_replace", "c_base", "c_tar", "has_blend", "blend_alpha"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert a.self_window == b.self_window and a.start_blend == b.start_blend and a.blend_th == b.blend_th
+
+
+def test_batched_plan_stacks_images():
+    tok = ToyTokenizer()
+    ctrls = [hedit_b200.make_controller(p, False, 0.4, 0.35, blend_word=((s,), (t,)) if i % 2 == 0 else None,
+                                        equilizer_params=None, num_steps=6, tokenizer=tok) for i, (p, s, t) in enumerate(PAIRS)]
+    plan = hedit_b200.compile_edit_plan(ctrls, 6)
+    assert plan.mapper.shape == (4, 80) and plan.c_base.shape == (7, 4, 80) and plan.has_blend.tolist() == [1, 0, 1, 0]
+    with pytest.raises(ValueError):
+        hedit_b200.compile_edit_plan(ctrls, 7)

@@ -1,0 +1,94 @@
+"""CPU: pins the oracle.  (1) against the committed golden fixtures produced by the UNMODIFIED reference loop
+(tools/make_golden.py) -- runs anywhere; (2) live against the reference's own set-up classes when /root/reference
+is present (build container only)."""
+import pytest
+import torch
+
+from oracle import p2p as op
+from oracle.pipeline import OraclePipeline, ToyTokenizer
+from oracle_run import load_golden, run_oracle_on_golden
+from refload import load_reference, reference_available
+
+PAIRS = [
+    (["a green lizard is sitting on a branch", "a brown lizard is sitting on a branch"], "lizard", "lizard"),
+    (["a cat sitting next to a mirror", "a silver cat sculpture sitting next to a mirror"], "cat", "cat"),
+    (["a photo of a house on a hill", "a photo of a castle on a hill in winter"], "house", "castle"),
+    (["two birds on a wire", "two parrots on a wire"], "birds", "parrots"),
+]
+
+
+@pytest.mark.parametrize("name", ["small32_refine", "small32_replace_mos2"])
+def test_oracle_matches_reference_golden(name):
+    g = load_golden(name)
+    ed, rc, tr, spec = run_oracle_on_golden(g)
+    # same torch build, same op order as the reference loop -> bit-exact here; allow round-off across torch builds
+    assert (ed - g["edited"]).abs().max().item() <= 1e-4
+    assert (rc - g["recon"]).abs().max().item() <= 1e-4
+    assert (tr - g["trace"]).abs().max().item() <= 1e-4
+    # intrinsic known answer: the reconstruction row returns the inverted latent
+    assert (rc - g["w0"]).abs().max().item() < 1e-3
+    tb = g["tables"]
+    assert torch.equal(tb["alpha_words"], spec.alpha_words) and tuple(tb["self_window"]) == tuple(spec.self_window)
+    for k in ("mapper", "refine_alpha", "replace_matrix", "equalizer", "blend_alpha"):
+        if k in tb:
+            assert torch.equal(tb[k], getattr(spec, k)), k
+
+
+@pytest.mark.slow
+def test_oracle_matches_reference_golden_blend64():
+    g = load_golden("tiny_replace_mos2")
+    ed, rc, tr, _ = run_oracle_on_golden(g)
+    assert (ed - g["edited"]).abs().max().item() <= 1e-4 and (tr - g["trace"]).abs().max().item() <= 1e-4
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("prompts,bw_src,bw_tar", PAIRS)
+@pytest.mark.parametrize("is_replace", [False, True])
+def test_setup_tables_match_reference_classes(prompts, bw_src, bw_tar, is_replace):
+    ref = load_reference()
+    tok = ToyTokenizer()
+    if is_replace and len(prompts[0].split(" ")) != len(prompts[1].split(" ")):
+        pytest.skip("replace controller needs equal word counts")
+    T = 12
+    kw = dict(cross_replace_steps=0.4, self_replace_steps=0.35, blend_word=((bw_src,), (bw_tar,)),
+              equilizer_params={"words": (bw_tar,), "values": (2.0,)}, num_steps=T, tokenizer=tok)
+    c = ref.ptp_controller_utils.make_controller(prompts=prompts, is_replace_controller=is_replace, device="cpu", **kw)
+    s = op.make_edit_spec(prompts, is_replace, kw["cross_replace_steps"], kw["self_replace_steps"], kw["blend_word"],
+                          kw["equilizer_params"], T, tok)
+    assert torch.equal(c.cross_replace_alpha.reshape(T + 1, 77), s.alpha_words)
+    assert tuple(c.num_self_replace) == tuple(s.self_window)
+    assert torch.equal(c.equalizer.reshape(77), s.equalizer)
+    assert torch.equal(c.local_blend.alpha_layers.reshape(2, 77), s.blend_alpha) and c.local_blend.start_blend == s.start_blend
+    inner = c.prev_controller
+    if is_replace:
+        assert torch.equal(inner.mapper[0], s.replace_matrix)
+    else:
+        assert torch.equal(inner.mapper[0], s.mapper) and torch.equal(inner.alphas.reshape(77), s.refine_alpha)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_hook_matches_reference_controller():
+    """One attention-layer call of the oracle hook vs the reference controller object on the same probabilities
+    (edit region, in-place semantics, stored views, step counter)."""
+    ref = load_reference()
+    tok = ToyTokenizer()
+    prompts = PAIRS[1][0]
+    T = 6
+    c = ref.ptp_controller_utils.make_controller(prompts=prompts, is_replace_controller=False, cross_replace_steps=0.4, self_replace_steps=0.5,
+                                                 blend_word=None, equilizer_params={"words": ("silver",), "values": (2.0,)}, num_steps=T,
+                                                 tokenizer=tok, device="cpu")
+    c.num_att_layers = 2
+    s = op.make_edit_spec(prompts, False, 0.4, 0.5, None, {"words": ("silver",), "values": (2.0,)}, T, tok)
+    st = op.P2PState(num_att_layers=2)
+    g = torch.Generator().manual_seed(3)
+    for step in range(T):
+        for is_cross, M in ((False, 64), (True, 77)):
+            p = torch.softmax(torch.randn(32, 64, M, generator=g), -1)
+            a, b = p.clone(), p.clone()
+            c(a, is_cross, "down", True)
+            op.p2p_hook(st, s, b, is_cross, "down", True)
+            assert torch.equal(a, b), (step, is_cross)
+        assert c.cur_step == st.cur_step == step + 1
+    for k in c.attention_store:
+        for x, y in zip(c.attention_store[k], st.attention_store[k]):
+            assert torch.equal(x, y)

@@ -17,3 +17,9 @@ for t in tiny_refine_blend tiny_reference_schedule tiny_replace_mos2 tiny_noblen
 done
 cat gpurun_out/summary.txt
 grep -h -E "passed|failed|error" gpurun_out/*.log | tail -40
+if [ -n "$HEDIT_BENCH" ]; then
+  timeout 900 python bench.py --steps 1 --warmup 1 --profile --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err
+  echo "bench rc=$?" >> gpurun_out/summary.txt
+  tail -c 3000 gpurun_out/bench_quick.json
+  tail -5 gpurun_out/bench_quick.err
+fi

@@ -33,6 +33,9 @@ CASES = {
     "tiny_replace_mos2": (UNetConfig.tiny(sample_size=64), 6, 2, True, True),
     "tiny_refine_noblend": (UNetConfig.tiny(sample_size=64), 6, 1, False, False),
     "sd15_config1": (UNetConfig.sd15(), 10, 1, False, True),
+    # fast fixtures for the CPU (-m "not gpu") suite: 32x32 latent (LocalBlend needs 64x64, so it is off here)
+    "small32_refine": (UNetConfig.tiny(sample_size=32), 4, 1, False, False),
+    "small32_replace_mos2": (UNetConfig.tiny(sample_size=32), 3, 2, True, False),
 }
 
 
@@ -77,7 +80,7 @@ def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
                      weights="oracle.sd_unet.seeded_init_(seed=0)", w0="randn(seed 0)*0.18215*5",
                      generator="tools/make_golden.py", seconds=dict(inversion=t_inv, edit=t_edit),
                      torch=torch.__version__, threads=torch.get_num_threads()),
-        "w0": w0, "zs": zs[:T].clone(), "xT": wts[T].clone(), "xts": wts.clone(),
+        "w0": w0, "zs": zs[:T].clone(), "xT": wts[T].clone(),
         "ctx_uncond": enc(model, [""]), "ctx_src": enc(model, [PROMPTS[0]]), "ctx_tar": enc(model, [PROMPTS[1]]),
         "edited": edited.detach().clone(), "recon": recon.detach().clone(),
         "trace": torch.stack(trace),
@@ -102,7 +105,7 @@ def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "all"])
+    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "all"])
     args = ap.parse_args()
     ref = load_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
