@@ -3,7 +3,12 @@
 Tolerance policy (DESIGN.md "Precision"): GEMM/conv/attention operands are bf16 (relative rounding 2^-9 = 0.2 %),
 accumulation, normalisation statistics, softmax, residual stream and scheduler algebra are fp32.  The oracle is pure
 fp32, so the expected discrepancy of one UNet call is a few 1e-3 relative (measured and asserted below); over the
-chained loop it compounds, and the loop-level bound is stated per test."""
+chained loop it compounds, and the loop-level bound is stated per test.
+
+Measured on B200 (fp16 operands, round 1): one tiny UNet call 1.3e-3; loops (relative L2 over the latent): reconstruction row
+0.8-1.7e-2, edited row 0.5-1.0e-2 (per-pixel max-abs of the reconstruction row <= 0.07 on latents of magnitude ~1).  The bounds
+asserted below are ~2.5x those measurements.  With -DHEDIT_OPERAND_BF16 the same numbers are ~8x larger (6-12e-2)."""
+TOL_LOOP = 4e-2
 import os
 
 import pytest
@@ -47,7 +52,7 @@ def test_unet_forward_tiny(tiny64):
     model.unet.cpu()
     r, m = rel_err(eps, ref)
     print("tiny unet forward rel", r, "max", m, "launches", eng.last_stats)
-    assert r < 1.5e-2, (r, m)
+    assert r < 4e-3, (r, m)     # measured 1.3e-3 on B200 with fp16 operands (1.0e-2 with bf16)
 
 
 def _run_golden(name, eng_cache={}, schedule=1, tol=None):
@@ -88,24 +93,24 @@ def _run_golden(name, eng_cache={}, schedule=1, tol=None):
 def test_edit_loop_tiny_refine_blend():
     r_ed, r_rc, r_w0, st = _run_golden("tiny_refine_blend")
     assert st["sample_forwards"] == 10 * 7
-    assert r_rc < 3e-2 and r_w0 < 3e-2      # reconstruction row: intrinsic known answer (returns the inverted latent)
-    assert r_ed < 1.5e-1                     # edit row passes through thresholded LocalBlend masks and hard P2P windows
+    assert r_rc < TOL_LOOP and r_w0 < TOL_LOOP      # reconstruction row: intrinsic known answer (returns the inverted latent)
+    assert r_ed < TOL_LOOP                           # edit row passes through thresholded LocalBlend masks and hard P2P windows
 
 
 def test_edit_loop_tiny_reference_schedule():
     r_ed, r_rc, r_w0, st = _run_golden("tiny_refine_blend", schedule=0)
     assert st["sample_forwards"] == 10 * 9
-    assert r_rc < 3e-2 and r_ed < 1.5e-1
+    assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
 
 
 def test_edit_loop_tiny_replace_mos2():
     r_ed, r_rc, r_w0, st = _run_golden("tiny_replace_mos2")
-    assert r_rc < 3e-2 and r_ed < 1.5e-1
+    assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
 
 
 def test_edit_loop_tiny_noblend():
     r_ed, r_rc, r_w0, st = _run_golden("tiny_refine_noblend")
-    assert r_rc < 3e-2 and r_ed < 8e-2
+    assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "sd15_config1.pt")), reason="full-size golden missing")
@@ -113,4 +118,4 @@ def test_edit_loop_sd15_config1():
     """BASELINE.json configs[0]: full SD-1.5 geometry, 1 image, 10 DDIM steps, implicit h-Edit-R + P2P (Refine+Reweight+LocalBlend),
     against outputs of the UNMODIFIED reference loop (tools/make_golden.py)."""
     r_ed, r_rc, r_w0, st = _run_golden("sd15_config1")
-    assert r_rc < 3e-2 and r_ed < 1.5e-1
+    assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
