@@ -47,7 +47,7 @@ struct AttnParams {
 
 HEDIT_DEVICE float ex2f(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
@@ -269,6 +269,254 @@ __global__ void __launch_bounds__(192) self_attn_kernel(const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------------- v2
+// Main self-attention kernel (all SD-1.x head dims, Nq >= 256, Nkv % BKV == 0).  One CTA owns TWO 128-row query tiles of
+// one (sample, head): two softmax warpgroups ping-pong against a single MMA warp, so the tensor core computes
+// S_B / P_A.V while warpgroup A does its exponentials and vice versa, and each K/V block fetched by TMA serves both
+// tiles.  S_t(j+1) is issued as soon as warpgroup t has copied S_t(j) to registers (s_free), so the score MMA is off
+// the critical path; P.V(j) completion (pv_done) gates only the reuse of the P tile and the lazy O rescale.
+// TMEM columns: S_t at t*BKV, O_t at 2*BKV + t*DCH*64.
+template <int DCH>
+struct SelfAttn2Cfg {
+  static constexpr int BKV = (DCH == 1) ? 128 : 64;
+  static constexpr int KSTAGES = (DCH == 3) ? 2 : 3;
+  static constexpr int PCH = BKV / 64;
+  static constexpr uint32_t QT_BYTES = DCH * 128 * 128;          // one Q tile
+  static constexpr uint32_t KV_BYTES = DCH * BKV * 128;          // one K (or V) block
+  static constexpr uint32_t PT_BYTES = PCH * 128 * 128;          // one P tile
+  static constexpr uint32_t SMEM_BYTES = 2 * QT_BYTES + 2 * KSTAGES * KV_BYTES + 2 * PT_BYTES + 256;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr uint32_t O_COL0 = 2 * BKV, O_STRIDE = DCH * 64;
+  static constexpr int THREADS = 320;
+  static_assert(O_COL0 + 2 * O_STRIDE <= 512, "TMEM budget");
+};
+
+template <int DCH>
+static __global__ void __launch_bounds__(320, 1) self_attn2_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = SelfAttn2Cfg<DCH>;
+  constexpr int BKV = Cfg::BKV, KSTAGES = Cfg::KSTAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;                               // [2 tiles][DCH][128 rows][128 B]
+  uint8_t* sK = sQ + 2 * Cfg::QT_BYTES;             // [KSTAGES][DCH][BKV rows][128 B]
+  uint8_t* sV = sK + KSTAGES * Cfg::KV_BYTES;
+  uint8_t* sP = sV + KSTAGES * Cfg::KV_BYTES;       // [2 tiles][PCH][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::PT_BYTES);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* k_full = bars + 1;              // KSTAGES
+  uint64_t* v_full = k_full + KSTAGES;
+  uint64_t* kv_empty = v_full + KSTAGES;
+  uint64_t* s_full = kv_empty + KSTAGES;    // 2
+  uint64_t* p_full = s_full + 2;            // 2 (4 arrivals each)
+  uint64_t* pv_done = p_full + 2;           // 2: P.V of block j has completed (P smem reusable, O stable)
+  uint64_t* s_free = pv_done + 2;           // 2 (4 arrivals each): S tile has been copied to registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, s = blockIdx.z;
+  const int sq = p.q_idx ? p.q_idx[s] : s;
+  const int sk = p.k_idx ? p.k_idx[s] : s;
+  const int sv = p.v_idx ? p.v_idx[s] : s;
+  const int nblk = p.Nkv / BKV;
+  const int DK = (p.d + 15) & ~15;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&s_free[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 8) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 9) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * Cfg::QT_BYTES);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + t * Cfg::QT_BYTES + c * 16384, &p.tmQ, q_full, c * 64, h, q0 + t * 128, sq);
+      int st = 0; uint32_t ph = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sK + st * Cfg::KV_BYTES + c * BKV * 128, &p.tmK, &k_full[st], c * 64, h, j * BKV, sk);
+        mbar_expect_tx(&v_full[st], Cfg::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sV + st * Cfg::KV_BYTES + c * BKV * 128, &p.tmV, &v_full[st], c * 64, h, j * BKV, sv);
+        if (++st == KSTAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------ MMA issuer: the whole warp runs the (uniform) control flow,
+    // one elected lane issues tcgen05.mma / commit, so descriptors live in uniform registers.
+    const uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
+    const uint32_t idesc_o = umma_idesc_bf16(128, DK, 0, 1);
+    const int ks = DK >> 4;
+    const uint32_t q_lo = umma_desc_lo_kmajor(smem_u32(sQ));
+    const uint32_t p_lo = umma_desc_lo_kmajor(smem_u32(sP));
+    const uint32_t k_lo = umma_desc_lo_kmajor(smem_u32(sK));
+    const uint32_t v_lo = umma_desc_lo(smem_u32(sV), BKV * 128);
+    auto issue_s = [&](int tile, int st) {          // S_tile = Q_tile K_st^T   (<= 4*DCH K-steps of 16)
+      const uint32_t qa = q_lo + tile * (Cfg::QT_BYTES >> 4), kb = k_lo + st * (Cfg::KV_BYTES >> 4);
+      const uint32_t d = tmem_base + tile * BKV;
+#pragma unroll
+      for (int k = 0; k < 4 * DCH; ++k)
+        if (k < ks)
+          umma_f16_ss(d, umma_desc_make(qa + (k >> 2) * (16384 >> 4) + 2 * (k & 3)),
+                      umma_desc_make(kb + (k >> 2) * ((BKV * 128) >> 4) + 2 * (k & 3)), idesc_s, k != 0);
+      umma_commit(&s_full[tile]);
+    };
+    auto issue_pv = [&](int tile, int st, bool accumulate) {   // O_tile += P_tile V_st   (BKV/16 K-steps of 16 kv rows)
+      const uint32_t pa = p_lo + tile * (Cfg::PT_BYTES >> 4), vb = v_lo + st * (Cfg::KV_BYTES >> 4);
+      const uint32_t d = tmem_base + Cfg::O_COL0 + tile * Cfg::O_STRIDE;
+#pragma unroll
+      for (int k = 0; k < BKV / 16; ++k)
+        umma_f16_ss(d, umma_desc_make(pa + (k >> 2) * (16384 >> 4) + 2 * (k & 3)), umma_desc_make(vb + k * (2048 >> 4)), idesc_o,
+                    (accumulate || k != 0) ? 1u : 0u);
+      umma_commit(&pv_done[tile]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) { issue_s(0, 0); issue_s(1, 0); }
+    __syncwarp();
+    int st = 0; uint32_t ph = 0;
+    for (int j = 0; j < nblk; ++j) {
+      int st1 = st + 1; uint32_t ph1 = ph;
+      if (st1 == KSTAGES) { st1 = 0; ph1 ^= 1; }
+      const bool more = (j + 1 < nblk);
+      if (more) mbar_wait(&k_full[st1], ph1);
+      mbar_wait(&v_full[st], ph);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (more) {
+          mbar_wait(&s_free[t], j & 1);
+          tc_fence_after();
+          if (elect_one()) issue_s(t, st1);
+          __syncwarp();
+        }
+        mbar_wait(&p_full[t], j & 1);
+        tc_fence_after();
+        if (elect_one()) issue_pv(t, st, j != 0);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&kv_empty[st]);
+      __syncwarp();
+      st = st1; ph = ph1;
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warpgroups (warps 0-3: tile A, 4-7: tile B)
+    const int tile = warp >> 2;
+    const int r = threadIdx.x & 127;
+    const uint32_t lane_sel = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + tile * BKV + lane_sel;
+    const uint32_t tO = tmem_base + Cfg::O_COL0 + tile * Cfg::O_STRIDE + lane_sel;
+    uint8_t* sPt = sP + tile * Cfg::PT_BYTES;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[tile], j & 1);
+      tc_fence_after();
+      uint32_t v[BKV];                               // launch guarantees Nkv % BKV == 0: no column masking
+#pragma unroll
+      for (int c = 0; c < BKV; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[tile]);      // the MMA warp may overwrite S with the next block's scores
+      float bmax;
+      {
+        float mx[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mx[k] = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < BKV; i += 8)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) mx[k] = fmaxf(mx[k], __uint_as_float(v[i + k]));
+        bmax = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      }
+      bmax *= p.scale_log2;
+      float alpha = 1.f;
+      bool bump = false;
+      if (j == 0) {
+        m_used = bmax;
+      } else if (bmax > m_used + 8.f) {
+        alpha = ex2f(m_used - bmax);
+        m_used = bmax;
+        l *= alpha;
+        bump = true;
+      }
+      if (j > 0) { mbar_wait(&pv_done[tile], (j - 1) & 1); tc_fence_after(); }   // previous P.V done: P smem free, O stable
+      if (__any_sync(0xffffffffu, bump)) {
+#pragma unroll 1
+        for (int c = 0; c < DK; c += 16) {
+          uint32_t o[16];
+          tmem_ld16(tO + c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tO + c, o);
+        }
+        tmem_st_wait();
+      }
+      const float neg_m = -m_used;
+      float ls[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ls[k] = 0.f;
+#pragma unroll
+      for (int c = 0; c < BKV; c += 8) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          e[i] = ex2f(fmaf(__uint_as_float(v[c + i]), p.scale_log2, neg_m));
+          ls[i] += e[i];                              // 8 independent accumulation chains
+        }
+        *reinterpret_cast<uint4*>(sPt + (c >> 6) * 16384 + sw128_off(r, (c & 63) >> 3)) =
+            make_uint4(pack_op2(e[0], e[1]), pack_op2(e[2], e[3]), pack_op2(e[4], e[5]), pack_op2(e[6], e[7]));
+      }
+      l += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[tile]);
+    }
+    mbar_wait(&pv_done[tile], (nblk - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int row = q0 + tile * 128 + r;
+#pragma unroll 1
+    for (int c = 0; c < DK; c += 16) {
+      uint32_t o[16];
+      tmem_ld16(tO + c, o);
+      tmem_ld_wait();
+      if (row < p.Nq) {
+        op_t* dst = p.out + (size_t(s) * p.Nq + row) * p.ldo + h * p.d + c;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c + g * 8 < p.d) {
+            const int b = g * 8;
+            *reinterpret_cast<uint4*>(dst + b) = make_uint4(
+                pack_op2(__uint_as_float(o[b]) * inv, __uint_as_float(o[b + 1]) * inv),
+                pack_op2(__uint_as_float(o[b + 2]) * inv, __uint_as_float(o[b + 3]) * inv),
+                pack_op2(__uint_as_float(o[b + 4]) * inv, __uint_as_float(o[b + 5]) * inv),
+                pack_op2(__uint_as_float(o[b + 6]) * inv, __uint_as_float(o[b + 7]) * inv));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ======================================================================================================= cross

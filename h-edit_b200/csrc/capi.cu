@@ -15,6 +15,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st);
 cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st);
 cudaError_t launch_self_attn(const AttnParams& a, int dch, int S, cudaStream_t st);
 cudaError_t launch_cross_attn(const AttnParams& a, int dch, int units, cudaStream_t st);
+int self_attn_bkv(int d, int Nq, int Nkv);
 }  // namespace hedit
 
 using namespace hedit;
@@ -249,7 +250,7 @@ int hedit_op_self_attention(const void* q, const void* k, const void* v, int ldq
                             const int32_t* q_idx, const int32_t* k_idx, const int32_t* v_idx, void* out, void* stream) {
   if (d % 8 || d > 192) return fail("head dim must be a multiple of 8 and <= 192");
   AttnParams a; memset(&a, 0, sizeof a);
-  const int dch = d <= 64 ? 1 : (d <= 128 ? 2 : 3), bkv = d <= 128 ? 128 : 64;
+  const int dch = d <= 64 ? 1 : (d <= 128 ? 2 : 3), bkv = self_attn_bkv(d, Nq, Nkv);
   if (!attn_maps(a, q, ldq, Nq, S, k, v, ldkv, Nkv, S, H, d, bkv)) return fail("tensor map encode failed");
   a.H = H; a.d = d; a.Nq = Nq; a.Nkv = Nkv; a.scale_log2 = float(1.4426950408889634 / sqrt(double(d)));
   a.q_idx = q_idx; a.k_idx = k_idx; a.v_idx = v_idx; a.out = reinterpret_cast<op_t*>(out); a.ldo = H * d;
@@ -286,7 +287,7 @@ int hedit_op_group_norm(const float* x, const float* gamma, const float* beta, v
   float2* partial = nullptr;
   if (cudaMalloc(&partial, size_t(S) * nch * groups * sizeof(float2)) != cudaSuccess) return fail("cudaMalloc");
   GNStatsParams sp{x, nullptr, C, 0, HW, groups, chunk, partial};
-  gn_stats_kernel<<<dim3(nch, S), std::min(640, ((C / 2 + 31) / 32) * 32), 0, st>>>(sp);
+  gn_stats_kernel<<<dim3(nch, S), std::min(640, ((C / 4 + 31) / 32) * 32), 0, st>>>(sp);
   GNApplyParams ap{x, nullptr, C, 0, HW, groups, 16, nch, partial, gamma, beta, eps, silu, reinterpret_cast<op_t*>(out), nullptr};
   gn_apply_kernel<<<dim3((HW + 15) / 16, S), 256, 2 * C * sizeof(float), st>>>(ap);
   cudaError_t e = cudaStreamSynchronize(st);
@@ -297,7 +298,7 @@ int hedit_op_group_norm(const float* x, const float* gamma, const float* beta, v
 
 int hedit_op_layer_norm(const float* x, const float* gamma, const float* beta, void* out, int rows, int C, float eps, void* stream) {
   if (C % 64 || C > 2048) return fail("layer norm needs C % 64 == 0 and C <= 2048");
-  layernorm_kernel<32><<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, gamma, beta, reinterpret_cast<op_t*>(out), rows, C, eps);
+  launch_layernorm(x, gamma, beta, reinterpret_cast<op_t*>(out), rows, C, eps, reinterpret_cast<cudaStream_t>(stream));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "layer norm launch");
   return 0;

@@ -16,26 +16,36 @@ struct GNStatsParams {
 
 static __global__ void gn_stats_kernel(const GNStatsParams p) {
   __shared__ float ssum[32], ssq[32];
-  const int C = p.C1 + p.C2, half = C >> 1, cpg = C / p.groups;
+  const int C = p.C1 + p.C2, quads = C >> 2, cpg = C / p.groups;
   const int s = blockIdx.y, ch = blockIdx.x, nch = gridDim.x;
   if (threadIdx.x < 32) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
   __syncthreads();
   const int p0 = ch * p.chunk, p1 = min(p.HW, p0 + p.chunk);
-  for (int v = threadIdx.x; v < half; v += blockDim.x) {
-    const int c = 2 * v;
-    const float* base; int ld, cc;
-    if (c < p.C1) { base = p.x1 + size_t(s) * p.HW * p.C1; ld = p.C1; cc = c; }
-    else { base = p.x2 + size_t(s) * p.HW * p.C2; ld = p.C2; cc = c - p.C1; }
-    float a = 0.f, b = 0.f;
-#pragma unroll 4
-    for (int px = p0; px < p1; ++px) {
-      const float2 t = *reinterpret_cast<const float2*>(base + size_t(px) * ld + cc);
-      a += t.x + t.y;
-      b += t.x * t.x + t.y * t.y;
+  for (int v = threadIdx.x; v < quads; v += blockDim.x) {
+    const int c = 4 * v;
+    const float* base; int ld;
+    if (c < p.C1) { base = p.x1 + size_t(s) * p.HW * p.C1 + c; ld = p.C1; }
+    else { base = p.x2 + size_t(s) * p.HW * p.C2 + (c - p.C1); ld = p.C2; }
+    float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;      // channel pairs (c,c+1) and (c+2,c+3): a pair never straddles a group
+    int px = p0;
+    for (; px + 8 <= p1; px += 8) {
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = *reinterpret_cast<const float4*>(base + size_t(px + u) * ld);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a0 += t[u].x + t[u].y; b0 += t[u].x * t[u].x + t[u].y * t[u].y;
+        a1 += t[u].z + t[u].w; b1 += t[u].z * t[u].z + t[u].w * t[u].w;
+      }
     }
-    const int g = c / cpg;
-    atomicAdd(&ssum[g], a);
-    atomicAdd(&ssq[g], b);
+    for (; px < p1; ++px) {
+      const float4 t = *reinterpret_cast<const float4*>(base + size_t(px) * ld);
+      a0 += t.x + t.y; b0 += t.x * t.x + t.y * t.y;
+      a1 += t.z + t.w; b1 += t.z * t.z + t.w * t.w;
+    }
+    const int g0 = c / cpg, g1 = (c + 2) / cpg;
+    if (g0 == g1) { atomicAdd(&ssum[g0], a0 + a1); atomicAdd(&ssq[g0], b0 + b1); }
+    else { atomicAdd(&ssum[g0], a0); atomicAdd(&ssq[g0], b0); atomicAdd(&ssum[g1], a1); atomicAdd(&ssq[g1], b1); }
   }
   __syncthreads();
   if (threadIdx.x < p.groups)
@@ -60,18 +70,28 @@ static __global__ void gn_apply_kernel(const GNApplyParams p) {
   const int C = p.C1 + p.C2, cpg = C / p.groups;
   const int s = blockIdx.y;
   float* sa = sm; float* sb = sm + C;
-  if (threadIdx.x < p.groups) {
-    double su = 0.0, sq = 0.0;
-    for (int k = 0; k < p.nstat_chunks; ++k) {
-      const float2 t = p.partial[(size_t(s) * p.nstat_chunks + k) * p.groups + threadIdx.x];
-      su += t.x; sq += t.y;
+  {   // finalise the statistics: 8 threads per group sum the chunk partials, then one thread per group combines in double
+    __shared__ float2 part[8][32];
+    const int g = threadIdx.x & 31, sl = threadIdx.x >> 5;      // blockDim.x == 256
+    float su = 0.f, sq = 0.f;
+    if (g < p.groups)
+      for (int k = sl; k < p.nstat_chunks; k += 8) {
+        const float2 t = p.partial[(size_t(s) * p.nstat_chunks + k) * p.groups + g];
+        su += t.x; sq += t.y;
+      }
+    part[sl][g] = make_float2(su, sq);
+    __syncthreads();
+    if (threadIdx.x < p.groups) {
+      double dsu = 0.0, dsq = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { dsu += part[k][threadIdx.x].x; dsq += part[k][threadIdx.x].y; }
+      const double n = double(p.HW) * cpg;
+      const double mean = dsu / n;
+      double var = dsq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      smean[threadIdx.x] = float(mean);
+      srstd[threadIdx.x] = float(1.0 / sqrt(var + double(p.eps)));
     }
-    const double n = double(p.HW) * cpg;
-    const double mean = su / n;
-    double var = sq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    smean[threadIdx.x] = float(mean);
-    srstd[threadIdx.x] = float(1.0 / sqrt(var + double(p.eps)));
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -100,19 +120,23 @@ static __global__ void gn_apply_kernel(const GNApplyParams p) {
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // One warp per token row (C <= 2048, C % 64 == 0): row held in registers, two-pass mean / variance, bf16 out.
-template <int MAXV>   // MAXV float2 per lane
+template <int NV>   // float2 per lane; NV > 0: exactly C/64, NV == 0: runtime count (<= 32)
 static __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  op_t* __restrict__ out, int rows, int C, float eps) {
+  constexpr int MAXV = NV > 0 ? NV : 32;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const int nv = C >> 6;       // float2 per lane
+  const int nv = NV > 0 ? NV : (C >> 6);
   const float* xr = x + size_t(row) * C;
   float2 v[MAXV];
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < MAXV; ++k)
-    if (k < nv) { v[k] = *reinterpret_cast<const float2*>(xr + 2 * (lane + 32 * k)); s += v[k].x + v[k].y; }
+    if (k < nv) v[k] = *reinterpret_cast<const float2*>(xr + 2 * (lane + 32 * k));
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k)
+    if (k < nv) s += v[k].x + v[k].y;
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / C;
@@ -132,6 +156,16 @@ static __global__ void layernorm_kernel(const float* __restrict__ x, const float
       const float2 b = *reinterpret_cast<const float2*>(beta + c);
       *reinterpret_cast<uint32_t*>(orow + c) = pack_op2((v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y);
     }
+}
+
+static inline void launch_layernorm(const float* x, const float* g, const float* b, op_t* out, int rows, int C, float eps, cudaStream_t st) {
+  const int grid = (rows + 7) / 8;
+  switch (C) {
+    case 320: layernorm_kernel<5><<<grid, 256, 0, st>>>(x, g, b, out, rows, C, eps); break;
+    case 640: layernorm_kernel<10><<<grid, 256, 0, st>>>(x, g, b, out, rows, C, eps); break;
+    case 1280: layernorm_kernel<20><<<grid, 256, 0, st>>>(x, g, b, out, rows, C, eps); break;
+    default: layernorm_kernel<0><<<grid, 256, 0, st>>>(x, g, b, out, rows, C, eps); break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ casts / resampling

@@ -331,8 +331,8 @@ cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st) {
   }
   const int tiles = ((g.M + 127) / 128) * ((g.N + bn - 1) / bn);
   const int grid = std::min(tiles, num_sms());
-  if (bn == 256) gemm_bf16_tcgen05_kernel<256><<<grid, 192, GemmCfg<256>::SMEM_BYTES, st>>>(g);
-  else gemm_bf16_tcgen05_kernel<160><<<grid, 192, GemmCfg<160>::SMEM_BYTES, st>>>(g);
+  if (bn == 256) gemm_bf16_tcgen05_kernel<256><<<grid, 320, GemmCfg<256>::SMEM_BYTES, st>>>(g);
+  else gemm_bf16_tcgen05_kernel<160><<<grid, 320, GemmCfg<160>::SMEM_BYTES, st>>>(g);
   return cudaGetLastError();
 }
 
@@ -361,7 +361,21 @@ static cudaError_t launch_self_t(const AttnParams& a, int S, cudaStream_t st) {
   self_attn_kernel<DCH, BKV><<<grid, 192, SelfAttnCfg<DCH, BKV>::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
+template <int DCH>
+static cudaError_t launch_self2_t(const AttnParams& a, int S, cudaStream_t st) {
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(self_attn2_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SelfAttn2Cfg<DCH>::SMEM_BYTES); set = true; }
+  dim3 grid((a.Nq + 255) / 256, a.H, S);
+  self_attn2_kernel<DCH><<<grid, SelfAttn2Cfg<DCH>::THREADS, SelfAttn2Cfg<DCH>::SMEM_BYTES, st>>>(a);
+  return cudaGetLastError();
+}
 cudaError_t launch_self_attn(const AttnParams& a, int dch, int S, cudaStream_t st) {
+  const int bkv2 = (dch == 1) ? 128 : 64;
+  if (a.Nq >= 256 && a.Nkv % bkv2 == 0) {      // two query tiles per CTA, ping-pong softmax warpgroups
+    if (dch == 1) return launch_self2_t<1>(a, S, st);
+    if (dch == 2) return launch_self2_t<2>(a, S, st);
+    return launch_self2_t<3>(a, S, st);
+  }
   if (dch == 1) return launch_self_t<1, 128>(a, S, st);
   if (dch == 2) return launch_self_t<2, 128>(a, S, st);
   return launch_self_t<3, 64>(a, S, st);
@@ -380,7 +394,12 @@ cudaError_t launch_cross_attn(const AttnParams& a, int dch, int units, cudaStrea
   return launch_cross_t<3>(a, units, st);
 }
 static int dch_for(int d) { return d <= 64 ? 1 : (d <= 128 ? 2 : 3); }
-static int bkv_for(int d) { return d <= 128 ? 128 : 64; }
+// K/V rows per TMA box: must match the kernel variant launch_self_attn() picks for the same (d, Nq, Nkv)
+int self_attn_bkv(int d, int Nq, int Nkv) {
+  const int bkv2 = (d <= 64) ? 128 : 64;
+  if (Nq >= 256 && Nkv % bkv2 == 0) return bkv2;
+  return d <= 128 ? 128 : 64;
+}
 
 // ------------------------------------------------------------------------------------------------ contexts / timesteps
 int Engine::set_contexts(const float* ctx, int n_ctx, cudaStream_t st) {
@@ -544,7 +563,7 @@ struct PlanBuilder {
     bf16* att = A<bf16>(size_t(M) * C);
     flops += 4.0 * S * double(HW) * HW * C;
     if (plan) {
-      Op o{}; o.kind = OP_SELF_ATTN; o.tag = "self_attn"; o.tf_index = ti; o.dch = dch_for(d); o.bkv = bkv_for(d);
+      Op o{}; o.kind = OP_SELF_ATTN; o.tag = "self_attn"; o.tf_index = ti; o.dch = dch_for(d); o.bkv = self_attn_bkv(d, HW, HW);
       AttnParams& p = o.attn;
       if (!make_attn_maps(p, qkv, 3 * C, HW, S, qkv + C, qkv + 2 * C, 3 * C, HW, S, H, d, o.bkv, E.err_)) failed = true;
       p.H = H; p.d = d; p.Nq = HW; p.Nkv = HW; p.scale_log2 = float(1.4426950408889634 / std::sqrt(double(d)));
@@ -698,14 +717,14 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
     }
     case OP_GN_STATS: {
       GNStatsParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, op.chunk, op.partial};
-      const int half = (op.C1 + op.C2) / 2;
-      const int threads = std::min(640, ((half + 31) / 32) * 32);
+      const int quads = (op.C1 + op.C2) / 4;
+      const int threads = std::min(640, ((quads + 31) / 32) * 32);
       gn_stats_kernel<<<dim3(op.nchunks, S), threads, 0, st>>>(p);
       break;
     }
     case OP_GN_APPLY: {
       const int C = op.C1 + op.C2;
-      const int chunk = 16;
+      const int chunk = op.HW >= 4096 ? 64 : (op.HW >= 1024 ? 32 : 16);
       GNApplyParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, chunk, op.nchunks, op.partial, op.gamma, op.beta, op.eps, op.silu, op.h_out, op.h_out2};
       gn_apply_kernel<<<dim3((op.HW + chunk - 1) / chunk, S), 256, 2 * C * sizeof(float), st>>>(p);
       break;
@@ -714,7 +733,7 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
       CK(launch_gemm(op.gemm, op.gemm_bn, st));
       break;
     case OP_LN:
-      layernorm_kernel<32><<<(op.rows + 7) / 8, 256, 0, st>>>(op.f_in, op.gamma, op.beta, op.h_out, op.rows, op.C1, op.eps);
+      launch_layernorm(op.f_in, op.gamma, op.beta, op.h_out, op.rows, op.C1, op.eps, st);
       break;
     case OP_SELF_ATTN: {
       AttnParams a = op.attn;

@@ -4,7 +4,7 @@
 //
 // A and W are bf16, K-major, fetched by TMA (128-byte swizzle) into a multi-stage shared-memory ring; the fp32
 // accumulator lives in TMEM (two buffers, so the epilogue of tile i overlaps the main loop of tile i+1).
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (single elected thread) + TMEM owner, 2..5 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (single elected thread) + TMEM owner, 2..9 = epilogue.
 //
 // A-operand addressing modes (all NHWC bf16 activations, no im2col buffer is ever materialised):
 //   A_LINEAR   : 2-D map [M][K]                                   (linear layers, 1x1 convs)
@@ -34,19 +34,36 @@ struct GemmParams {
   GemmEpilogue ep;
 };
 
+// Coalesced write-back of one 32x32 chunk from the per-warp staging tile: lane = (row-in-group-of-4, quad); 8 iterations
+// cover the 32 rows.  All feature switches are compile-time so the loop body is ~12 instructions per float4.
+template <bool BIAS, bool RV, bool RES, bool F32, bool H16>
+HEDIT_DEVICE void epi_store_rows(const float4* stg, int rq, int rr, const float4& bb, const float4& rvv, const float4 (&rs)[8],
+                                 float* o32, size_t ldo4, op_t* o16, size_t ldob4) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + rr;
+    float4 a = stg[r * 8 + (rq ^ (r & 7))];
+    if (BIAS) { a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w; }
+    if (RV) { a.x += rvv.x; a.y += rvv.y; a.z += rvv.z; a.w += rvv.w; }
+    if (RES) { a.x += rs[i].x; a.y += rs[i].y; a.z += rs[i].z; a.w += rs[i].w; }
+    if (F32) *reinterpret_cast<float4*>(o32 + i * ldo4) = a;
+    if (H16) *reinterpret_cast<uint2*>(o16 + i * ldob4) = make_uint2(pack_op2(a.x, a.y), pack_op2(a.z, a.w));
+  }
+}
+
 template <int BN>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
-  static constexpr int STAGES = (BN > 160) ? 4 : 6;
+  static constexpr int STAGES = (BN > 160) ? 4 : 5;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/;
-  static constexpr int THREADS = 192;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
+  static constexpr int THREADS = 320;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -68,7 +85,7 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tcgen05_kernel(const __grid_
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -78,27 +95,28 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tcgen05_kernel(const __grid_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) << 7;
-        const int n0 = (tile % n_tiles) * BN;
-        int s0 = 0, y0 = 0;
-        if (p.a_mode != A_LINEAR) {
-          const int hw = p.conv_H * p.conv_W;
-          s0 = m0 / hw;
-          y0 = (m0 % hw) / p.conv_W;
-        }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ------------------------------------------------------------------ TMA producer (whole warp runs the loop so the
+    // addressing stays in uniform registers; one elected lane issues the copies)
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) << 7;
+      const int n0 = (tile % n_tiles) * BN;
+      int s0 = 0, y0 = 0;
+      if (p.a_mode != A_LINEAR) {
+        const int hw = p.conv_H * p.conv_W;
+        s0 = m0 / hw;
+        y0 = (m0 % hw) / p.conv_W;
+      }
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (p.a_mode == A_LINEAR) {
             tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * 64, m0);
           } else {
-            const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
             const int ky = tap / 3, kx = tap - ky * 3;
             if (p.a_mode == A_CONV3X3) {
               tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * 64, kx - 1, y0 + ky - 1, s0);
@@ -109,65 +127,102 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tcgen05_kernel(const __grid_
             }
           }
           tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (p.a_mode != A_LINEAR && ++cb == p.cin_blocks) { cb = 0; ++tap; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      int stage = 0; uint32_t phase = 0; int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t da = umma_desc_kmajor_sw128(sa);
-          const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)   // 4 x (K=16) per 64-wide stage; +32 B per step inside the swizzle atom
-            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        if (elect_one()) {
+          const uint32_t la = umma_desc_lo_kmajor(smem_base + stage * Cfg::STAGE_BYTES);
+          const uint32_t lb = umma_desc_lo_kmajor(smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES);
+          umma_f16_ss(d_tmem, umma_desc_make(la), umma_desc_make(lb), idesc, kb != 0);
+          umma_f16_ss(d_tmem, umma_desc_make(la + 2), umma_desc_make(lb + 2), idesc, 1);
+          umma_f16_ss(d_tmem, umma_desc_make(la + 4), umma_desc_make(lb + 4), idesc, 1);
+          umma_f16_ss(d_tmem, umma_desc_make(la + 6), umma_desc_make(lb + 6), idesc, 1);
           umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tfull_bar[acc]);
+      __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
+    // ------------------------------------------------------------------ epilogue: 8 warps; warp w owns TMEM lane quarter
+    // (w & 3) and every second 32-column chunk.  Accumulators are read row-per-thread (TMEM lane == row), transposed
+    // through a per-warp XOR-swizzled 32x32 fp32 staging tile, and written back with 8 lanes per row so that every
+    // global load/store instruction touches 4 fully used 128-byte lines (the row-per-thread pattern touches 32).
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const GemmEpilogue& e = p.ep;
+    float4* stg = reinterpret_cast<float4*>(smem + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * 256;   // [32 rows][8 quads]
+    const int rq = lane & 7, rr = lane >> 3;           // read-back role (non-GEGLU): quad, row-in-group-of-4
+    const int gq = lane & 3, gr = lane >> 2;           // read-back role (GEGLU, 16 outputs): quad, row-in-group-of-8
+    // feature combination of this launch -> specialised write-back loop (0 = generic path)
+    const bool has_b = e.bias != nullptr, has_rv = e.rowvec != nullptr, has_res = e.residual != nullptr;
+    const bool has32 = e.out_f32 != nullptr, has16 = e.out_bf16 != nullptr;
+    int mode = 0;
+    if (!e.geglu) {
+      if (has_b && !has_rv && !has_res && has32 && !has16) mode = 1;
+      else if (has_b && !has_rv && has_res && has32 && !has16) mode = 2;
+      else if (has_b && has_rv && !has_res && has32 && !has16 && (e.rows_per_group & 31) == 0) mode = 3;
+      else if (!has_b && !has_rv && !has_res && !has32 && has16) mode = 4;
+      else if (has_b && !has_rv && has_res && !has32 && has16) mode = 5;
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / n_tiles) << 7;
       const int n0 = (tile % n_tiles) * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int rbase = m0 + quarter * 32;
+      const bool rows_full = (rbase + 32 <= p.M);
+      const uint32_t t_row = tmem_base + acc * 256 + (uint32_t(quarter * 32) << 16);
+      const size_t row0 = size_t(rbase + rr);
+      float4 rs[8];
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), rvv = bb;
+      auto prefetch = [&](int col) {       // operands of the write-back that do not depend on the accumulator
+        if (mode != 0 && rows_full && col + 32 <= p.N) {
+          const int cq = col + 4 * rq;
+          if (has_b) bb = *reinterpret_cast<const float4*>(e.bias + cq);
+          if (mode == 3) rvv = *reinterpret_cast<const float4*>(e.rowvec + size_t(rbase / e.rows_per_group) * e.ldrv + cq);
+          if (has_res) {
+            const float* rp = e.residual + row0 * e.ldr + cq;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rs[i] = *reinterpret_cast<const float4*>(rp + size_t(4 * i) * e.ldr);
+          }
+        }
+      };
+      prefetch(n0 + half * 32);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t t_row = tmem_base + acc * 256 + (uint32_t(quarter * 32) << 16);
-      const float* rv = (e.rowvec && row_ok) ? e.rowvec + size_t(row / e.rows_per_group) * e.ldrv : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
         const int col = n0 + c0;
         if (col >= p.N) break;                      // warp-uniform
         uint32_t raw[32];
         tmem_ld32(t_row + c0, raw);
         tmem_ld_wait();
-        if (!row_ok) continue;
-        float v[32];
+        if (e.geglu) {
+          // chunk = 16 value columns followed by their 16 gate columns -> 16 outputs (bias applied before the gate)
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        const bool full = (col + 32 <= p.N);
-        if (full) {
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
           if (e.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -175,55 +230,61 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tcgen05_kernel(const __grid_
               v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
             }
           }
-          if (rv) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(rv + col + j);
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
+          for (int q = 0; q < 4; ++q)
+            stg[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q] * gelu_fast_f(v[16 + 4 * q]), v[4 * q + 1] * gelu_fast_f(v[17 + 4 * q]),
+                                                           v[4 * q + 2] * gelu_fast_f(v[18 + 4 * q]), v[4 * q + 3] * gelu_fast_f(v[19 + 4 * q]));
+          __syncwarp();
+          op_t* go = e.out_bf16 + size_t(rbase + gr) * e.ldob + (col >> 1) + 4 * gq;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + gr;
+            const float4 a = stg[r * 8 + (gq ^ (r & 7))];
+            if (rbase + r < p.M) *reinterpret_cast<uint2*>(go + size_t(8 * i) * e.ldob) = make_uint2(pack_op2(a.x, a.y), pack_op2(a.z, a.w));
           }
-          if (e.geglu) {
-            // chunk = 16 value columns followed by their 16 gate columns -> 16 outputs
-            op_t* o = e.out_bf16 + size_t(row) * e.ldob + (col >> 1);
-            uint32_t pk[8];
+          __syncwarp();
+          continue;
+        }
 #pragma unroll
-            for (int j = 0; j < 16; j += 2)
-              pk[j >> 1] = pack_op2(v[j] * gelu_erf_f(v[16 + j]), v[j + 1] * gelu_erf_f(v[17 + j]));
-            *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            continue;
-          }
-          if (e.residual) {
-            const float* r = e.residual + size_t(row) * e.ldr + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(r + j);
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if (e.out_f32) {
-            float* o = e.out_f32 + size_t(row) * e.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-          if (e.out_bf16) {
-            op_t* o = e.out_bf16 + size_t(row) * e.ldob + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_op2(v[j], v[j + 1]), pack_op2(v[j + 2], v[j + 3]),
-                                                            pack_op2(v[j + 4], v[j + 5]), pack_op2(v[j + 6], v[j + 7]));
+        for (int q = 0; q < 8; ++q)
+          stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
+                                                         __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
+        __syncwarp();
+        const int cq = col + 4 * rq;
+        if (mode != 0 && rows_full && col + 32 <= p.N) {
+          float* o32 = has32 ? e.out_f32 + row0 * e.ldo + cq : nullptr;
+          op_t* o16 = has16 ? e.out_bf16 + row0 * e.ldob + cq : nullptr;
+          const size_t l32 = size_t(4) * e.ldo, l16 = size_t(4) * e.ldob;
+          switch (mode) {
+            case 1: epi_store_rows<true, false, false, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16); break;
+            case 2: epi_store_rows<true, false, true, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16); break;
+            case 3: epi_store_rows<true, true, false, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16); break;
+            case 4: epi_store_rows<false, false, false, false, true>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16); break;
+            default: epi_store_rows<true, false, true, false, true>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16); break;
           }
         } else {
-          // ragged tail (N not a multiple of 32): scalar, no geglu
-          for (int j = 0; j < 32 && col + j < p.N; ++j) {
-            float x = v[j];
-            if (e.bias) x += e.bias[col + j];
-            if (rv) x += rv[col + j];
-            if (e.residual) x += e.residual[size_t(row) * e.ldr + col + j];
-            if (e.out_f32) e.out_f32[size_t(row) * e.ldo + col + j] = x;
-            if (e.out_bf16) e.out_bf16[size_t(row) * e.ldob + col + j] = to_op(x);
+          // generic path: partial tiles, ragged N, unusual feature combinations
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + rr, row = rbase + r;
+            const float4 a4 = stg[r * 8 + (rq ^ (r & 7))];
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+              const int cc = cq + k;
+              if (row < p.M && cc < p.N) {
+                float x = av[k];
+                if (e.bias) x += e.bias[cc];
+                if (e.rowvec) x += e.rowvec[size_t(row / e.rows_per_group) * e.ldrv + cc];
+                if (e.residual) x += e.residual[size_t(row) * e.ldr + cc];
+                if (e.out_f32) e.out_f32[size_t(row) * e.ldo + cc] = x;
+                if (e.out_bf16) e.out_bf16[size_t(row) * e.ldob + cc] = to_op(x);
+              }
+            }
           }
         }
+        __syncwarp();
+        prefetch(col + 64);                        // next chunk of this warp
       }
       tc_fence_before();
       __syncwarp();

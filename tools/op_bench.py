@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Micro-benchmarks of single operators through the C ABI (CUDA events, device-resident inputs).  Used for tuning and
+as the target of `ncu` captures.  python tools/op_bench.py [attn|linear|conv|all] [--iters N]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from gpu_util import P, bf, lib  # noqa: E402
+
+DEV = "cuda"
+
+
+def timeit(fn, iters):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_attn(iters):
+    for (S, N, H, d) in [(8, 4096, 8, 40), (8, 1024, 8, 80), (8, 256, 8, 160)]:
+        C = H * d
+        qkv = bf(torch.randn(S, N, 3 * C, device=DEV))
+        out = torch.zeros(S, N, C, device=DEV, dtype=qkv.dtype)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        fn = lambda: lib().hedit_op_self_attention(P(q), P(k), P(v), 3 * C, 3 * C, S, N, N, H, d, None, None, None, P(out), None)
+        ms = timeit(fn, iters)
+        fl = 4.0 * S * H * N * N * d
+        print(f"self_attn S={S} N={N} H={H} d={d}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  ({S * H * (N / 128) ** 2 / 148 :.0f} 128x128 blocks/SM, "
+              f"{ms * 1e-3 * 1.9e9 / (S * H * (N / 128) ** 2 / 148):.0f} cyc/block @1.9GHz)")
+
+
+def bench_linear(iters):
+    for (M, N, K, res, f32) in [(163840, 960, 320, False, False), (163840, 320, 320, True, True), (40960, 1920, 640, False, False),
+                                (40960, 640, 2560, True, True), (163840, 320, 1280, True, True), (10240, 1280, 1280, True, True)]:
+        A, W = bf(torch.randn(M, K, device=DEV)), bf(torch.randn(N, K, device=DEV) * K ** -0.5)
+        bias = torch.randn(N, device=DEV) if f32 or res else None      # fp16-out projections (q/k/v) carry no bias
+        r = torch.randn(M, N, device=DEV) if res else None
+        o32 = torch.empty(M, N, device=DEV) if f32 else None
+        o16 = None if f32 else torch.empty(M, N, device=DEV, dtype=A.dtype)
+        fn = lambda: lib().hedit_op_linear(P(A), P(W), P(bias), P(r), P(o32), P(o16), M, N, K, None)
+        ms = timeit(fn, iters)
+        print(f"linear M={M} N={N} K={K} res={res} f32out={f32}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+
+
+def bench_conv(iters):
+    for (S, H, C, Co, st) in [(16, 64, 320, 320, 1), (16, 32, 640, 640, 1), (16, 16, 1280, 1280, 1), (16, 8, 2560, 1280, 1), (16, 64, 960, 320, 1)]:
+        x = bf(torch.randn(S, H, H, C, device=DEV))
+        w = bf(torch.randn(Co, 3, 3, C, device=DEV) * (9 * C) ** -0.5)
+        bias = torch.randn(Co, device=DEV)
+        out = torch.empty(S, H // st, H // st, Co, device=DEV)
+        fn = lambda: lib().hedit_op_conv3x3(P(x), P(w), P(bias), P(out), S, H, H, C, Co, st, None)
+        ms = timeit(fn, iters)
+        print(f"conv3x3 S={S} {H}x{H} C={C}->{Co}: {ms:.3f} ms  {2.0 * S * (H // st) ** 2 * Co * 9 * C / ms / 1e9:.1f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="?", default="all")
+    ap.add_argument("--iters", type=int, default=10)
+    a = ap.parse_args()
+    torch.manual_seed(0)
+    if a.what in ("attn", "all"):
+        bench_attn(a.iters)
+    if a.what in ("linear", "all"):
+        bench_linear(a.iters)
+    if a.what in ("conv", "all"):
+        bench_conv(a.iters)
