@@ -289,7 +289,7 @@ int hedit_op_group_norm(const float* x, const float* gamma, const float* beta, v
   GNStatsParams sp{x, nullptr, C, 0, HW, groups, chunk, partial};
   gn_stats_kernel<<<dim3(nch, S), std::min(640, ((C / 4 + 31) / 32) * 32), 0, st>>>(sp);
   GNApplyParams ap{x, nullptr, C, 0, HW, groups, 16, nch, partial, gamma, beta, eps, silu, reinterpret_cast<op_t*>(out), nullptr};
-  gn_apply_kernel<<<dim3((HW + 15) / 16, S), 256, 2 * C * sizeof(float), st>>>(ap);
+  gn_apply_kernel<<<dim3((HW + 15) / 16, S), std::max(256, std::min(640, ((C / 4 + 31) / 32) * 32)), 0, st>>>(ap);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(partial);
   if (e != cudaSuccess) return cuda_fail(e, "group norm");

@@ -65,21 +65,21 @@ struct GNApplyParams {
 };
 
 static __global__ void gn_apply_kernel(const GNApplyParams p) {
-  extern __shared__ float sm[];       // a[C], b[C]
   __shared__ float smean[32], srstd[32];
-  const int C = p.C1 + p.C2, cpg = C / p.groups;
+  const int C = p.C1 + p.C2, cpg = C / p.groups, quads = C >> 2;
   const int s = blockIdx.y;
-  float* sa = sm; float* sb = sm + C;
   {   // finalise the statistics: 8 threads per group sum the chunk partials, then one thread per group combines in double
     __shared__ float2 part[8][32];
-    const int g = threadIdx.x & 31, sl = threadIdx.x >> 5;      // blockDim.x == 256
-    float su = 0.f, sq = 0.f;
-    if (g < p.groups)
-      for (int k = sl; k < p.nstat_chunks; k += 8) {
-        const float2 t = p.partial[(size_t(s) * p.nstat_chunks + k) * p.groups + g];
-        su += t.x; sq += t.y;
-      }
-    part[sl][g] = make_float2(su, sq);
+    const int g = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    if (sl < 8) {
+      float su = 0.f, sq = 0.f;
+      if (g < p.groups)
+        for (int k = sl; k < p.nstat_chunks; k += 8) {
+          const float2 t = p.partial[(size_t(s) * p.nstat_chunks + k) * p.groups + g];
+          su += t.x; sq += t.y;
+        }
+      part[sl][g] = make_float2(su, sq);
+    }
     __syncthreads();
     if (threadIdx.x < p.groups) {
       double dsu = 0.0, dsq = 0.0;
@@ -94,27 +94,37 @@ static __global__ void gn_apply_kernel(const GNApplyParams p) {
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float a = srstd[g] * p.gamma[c];
-    sa[c] = a;
-    sb[c] = p.beta[c] - smean[g] * a;
-  }
-  __syncthreads();
+  // thread <-> fixed channel quad: affine coefficients live in registers, pixels are streamed (coalesced across threads)
   const int p0 = blockIdx.x * p.chunk, p1 = min(p.HW, p0 + p.chunk);
-  const int quads = C >> 2;
-  const int total = (p1 - p0) * quads;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int px = p0 + i / quads, c = (i % quads) << 2;
-    float4 t;
-    if (c < p.C1) t = *reinterpret_cast<const float4*>(p.x1 + (size_t(s) * p.HW + px) * p.C1 + c);
-    else t = *reinterpret_cast<const float4*>(p.x2 + (size_t(s) * p.HW + px) * p.C2 + (c - p.C1));
-    float y0 = t.x * sa[c] + sb[c], y1 = t.y * sa[c + 1] + sb[c + 1];
-    float y2 = t.z * sa[c + 2] + sb[c + 2], y3 = t.w * sa[c + 3] + sb[c + 3];
-    if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-    const size_t o = (size_t(s) * p.HW + px) * C + c;
-    *reinterpret_cast<uint2*>(p.out + o) = make_uint2(pack_op2(y0, y1), pack_op2(y2, y3));
-    if (p.raw_out) *reinterpret_cast<uint2*>(p.raw_out + o) = make_uint2(pack_op2(t.x, t.y), pack_op2(t.z, t.w));
+  for (int v = threadIdx.x; v < quads; v += blockDim.x) {
+    const int c = 4 * v;
+    float ca[4], cb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = (c + k) / cpg;
+      ca[k] = srstd[g] * p.gamma[c + k];
+      cb[k] = p.beta[c + k] - smean[g] * ca[k];
+    }
+    const float* base; int ld;
+    if (c < p.C1) { base = p.x1 + size_t(s) * p.HW * p.C1 + c; ld = p.C1; }
+    else { base = p.x2 + size_t(s) * p.HW * p.C2 + (c - p.C1); ld = p.C2; }
+    op_t* o = p.out + size_t(s) * p.HW * C + c;
+    op_t* ro = p.raw_out ? p.raw_out + size_t(s) * p.HW * C + c : nullptr;
+    for (int px = p0; px < p1; px += 4) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (px + u < p1) t[u] = *reinterpret_cast<const float4*>(base + size_t(px + u) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (px + u < p1) {
+          float y0 = fmaf(t[u].x, ca[0], cb[0]), y1 = fmaf(t[u].y, ca[1], cb[1]);
+          float y2 = fmaf(t[u].z, ca[2], cb[2]), y3 = fmaf(t[u].w, ca[3], cb[3]);
+          if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+          *reinterpret_cast<uint2*>(o + size_t(px + u) * C) = make_uint2(pack_op2(y0, y1), pack_op2(y2, y3));
+          if (ro) *reinterpret_cast<uint2*>(ro + size_t(px + u) * C) = make_uint2(pack_op2(t[u].x, t[u].y), pack_op2(t[u].z, t[u].w));
+        }
+    }
   }
 }
 
@@ -192,31 +202,33 @@ static __global__ void upsample2x_bf16_kernel(const float* __restrict__ x, op_t*
 }
 
 // ------------------------------------------------------------------------------------------------ conv_in / conv_out
-// conv_in: 3x3, Cin=4 (NCHW fp32 latent) -> C0 channels (NHWC fp32).  fp32 CUDA-core math (47 MMAC / sample).
-// grid (H, S); weights [C0][4][3][3] fp32.
+// conv_in: 3x3, Cin=4 (NCHW fp32 latent) -> C0 channels (NHWC fp32).  fp32 CUDA-core math (47 MMAC / sample, exact).
+// grid (ceil(H/RB), S): each CTA stages the [36][C0] weights once and produces RB output rows.
+constexpr int kConvInRows = 8;
 static __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                float* __restrict__ y, int H, int W, int C0) {
   extern __shared__ float sm[];
   float* sw = sm;                       // [36][C0] (transposed for conflict-free reads)
-  float* sx = sm + 36 * C0;             // [4][3][W+2]
-  const int yrow = blockIdx.x, s = blockIdx.y;
+  float* sx = sm + 36 * C0;             // [4][RB+2][W+2]
+  const int y0 = blockIdx.x * kConvInRows, s = blockIdx.y;
+  const int rows = min(kConvInRows, H - y0), PW = W + 2, PR = kConvInRows + 2;
   for (int i = threadIdx.x; i < 36 * C0; i += blockDim.x) { const int co = i / 36, k = i % 36; sw[k * C0 + co] = w[i]; }
-  for (int i = threadIdx.x; i < 12 * (W + 2); i += blockDim.x) {
-    const int xx = i % (W + 2) - 1, r = (i / (W + 2)) % 3, ci = i / (3 * (W + 2));
-    const int yy = yrow + r - 1;
+  for (int i = threadIdx.x; i < 4 * PR * PW; i += blockDim.x) {
+    const int xx = i % PW - 1, r = (i / PW) % PR, ci = i / (PR * PW);
+    const int yy = y0 + r - 1;
     sx[i] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? x[((size_t(s) * 4 + ci) * H + yy) * W + xx] : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < W * C0; i += blockDim.x) {
-    const int co = i % C0, xo = i / C0;
+  for (int i = threadIdx.x; i < rows * W * C0; i += blockDim.x) {
+    const int co = i % C0, xo = (i / C0) % W, r = i / (C0 * W);
     float acc = bias[co];
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int dr = 0; dr < 3; ++dr)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) acc = fmaf(sx[(ci * 3 + r) * (W + 2) + xo + k], sw[(ci * 9 + r * 3 + k) * C0 + co], acc);
-    y[((size_t(s) * H + yrow) * W + xo) * C0 + co] = acc;
+        for (int k = 0; k < 3; ++k) acc = fmaf(sx[(ci * PR + r + dr) * PW + xo + k], sw[(ci * 9 + dr * 3 + k) * C0 + co], acc);
+    y[((size_t(s) * H + y0 + r) * W + xo) * C0 + co] = acc;
   }
 }
 

@@ -196,10 +196,10 @@ Engine::Engine(const UNetCfg& cfg, int max_samples, int max_ctx) : cfg_(cfg), ma
     reg("up_blocks." + std::to_string(i) + ".upsamplers.0.conv.bias", WeightSlot::F32_COPY, bu, 0, {cu});
   }
   norm_out_g_ = dalloc<float>(cfg.boc[0]); norm_out_b_ = dalloc<float>(cfg.boc[0]);
-  conv_out_w_ = dalloc<float>(size_t(cfg.out_ch) * cfg.boc[0] * 9); conv_out_b_ = dalloc<float>(cfg.out_ch);
+  conv_out_w_ = dalloc<bf16>(size_t(cfg.out_ch) * cfg.boc[0] * 9); conv_out_b_ = dalloc<float>(cfg.out_ch);
   reg("conv_norm_out.weight", WeightSlot::F32_COPY, norm_out_g_, 0, {cfg.boc[0]});
   reg("conv_norm_out.bias", WeightSlot::F32_COPY, norm_out_b_, 0, {cfg.boc[0]});
-  reg("conv_out.weight", WeightSlot::F32_COPY, conv_out_w_, 0, {cfg.out_ch, cfg.boc[0], 3, 3});
+  reg("conv_out.weight", WeightSlot::BF16_CONV3, conv_out_w_, 0, {cfg.out_ch, cfg.boc[0], 3, 3});
   reg("conv_out.bias", WeightSlot::F32_COPY, conv_out_b_, 0, {cfg.out_ch});
 
   temb_act_ = dalloc<float>(size_t(maxT_) * temb * 2);
@@ -676,8 +676,13 @@ struct PlanBuilder {
     }
     bf16* fin = A<bf16>(size_t(S) * Hh * Ww * C);
     gn(x, C, nullptr, 0, Hh * Ww, E.norm_out_g_, E.norm_out_b_, 1e-5f, 1, fin, nullptr);
-    { Op o{}; o.kind = OP_CONV_OUT; o.h_in = fin; o.f_out = eps_out; o.H = Hh; o.W = Ww; o.C1 = C; o.tag = "conv_out"; push(o); }
-    flops += 2.0 * S * Hh * Ww * 36.0 * c.boc[0] * 2;
+    {   // conv_out (C0 -> 4) on the tensor-core conv path; the epilogue writes the NCHW latent layout directly
+      ConvGeom cg{S, Hh, Ww, C, 1};
+      GemmEpilogue e{}; e.bias = E.conv_out_b_; e.out_f32 = eps_out; e.ldo = c.out_ch; e.nchw_hw = Hh * Ww;
+      gemm("conv_out", fin, C, A_CONV3X3, &cg, E.conv_out_w_, S * Hh * Ww, c.out_ch, 9 * C, e);
+      Op o{}; o.kind = OP_CONV_OUT; o.f_out = eps_out; o.tag = "copy_out"; push(o);
+    }
+    flops += 2.0 * S * Hh * Ww * 36.0 * c.boc[0];
   }
 };
 
@@ -709,10 +714,10 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
   switch (op.kind) {
     case OP_CONV_IN: {
       CK(cudaMemcpyAsync(const_cast<float*>(op.f_in), x, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      const size_t sm = (36 * size_t(op.C1) + 12 * (op.W + 2)) * sizeof(float);
+      const size_t sm = (36 * size_t(op.C1) + 4 * (kConvInRows + 2) * (op.W + 2)) * sizeof(float);
       static bool set = false;
-      if (!set) { cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); set = true; }
-      conv_in_kernel<<<dim3(op.H, S), 256, sm, st>>>(op.f_in, conv_in_w_, conv_in_b_, op.f_out, op.H, op.W, op.C1);
+      if (!set) { cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
+      conv_in_kernel<<<dim3((op.H + kConvInRows - 1) / kConvInRows, S), 512, sm, st>>>(op.f_in, conv_in_w_, conv_in_b_, op.f_out, op.H, op.W, op.C1);
       break;
     }
     case OP_GN_STATS: {
@@ -724,9 +729,10 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
     }
     case OP_GN_APPLY: {
       const int C = op.C1 + op.C2;
-      const int chunk = op.HW >= 4096 ? 64 : (op.HW >= 1024 ? 32 : 16);
+      const int chunk = op.HW >= 4096 ? 32 : 16;
+      const int threads = std::max(256, std::min(640, ((C / 4 + 31) / 32) * 32));
       GNApplyParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, chunk, op.nchunks, op.partial, op.gamma, op.beta, op.eps, op.silu, op.h_out, op.h_out2};
-      gn_apply_kernel<<<dim3((op.HW + chunk - 1) / chunk, S), 256, 2 * C * sizeof(float), st>>>(p);
+      gn_apply_kernel<<<dim3((op.HW + chunk - 1) / chunk, S), threads, 0, st>>>(p);
       break;
     }
     case OP_GEMM:
@@ -759,15 +765,9 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
     case OP_CAST:
       cast_bf16_kernel<<<int(std::min<size_t>((op.count + 255) / 256, 8192)), 256, 0, st>>>(op.f_in, op.h_out, op.count);
       break;
-    case OP_CONV_OUT: {
-      static bool set = false;
-      if (!set) { cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); set = true; }
-      const size_t npix = size_t(S) * op.H * op.W;
-      conv_out_kernel<<<int(std::min<size_t>((npix + 7) / 8, 4096)), 256, 36 * size_t(op.C1) * sizeof(float), st>>>(
-          op.h_in, conv_out_w_, conv_out_b_, op.f_out, S, op.H, op.W, op.C1);
+    case OP_CONV_OUT:
       CK(cudaMemcpyAsync(eps, op.f_out, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
       break;
-    }
   }
   return 1;
 }

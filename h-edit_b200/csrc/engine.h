@@ -128,7 +128,8 @@ class Engine {
   std::map<std::string, WeightSlot> slots_;
   std::vector<void*> owned_;
   // weights
-  float *conv_in_w_ = 0, *conv_in_b_ = 0, *conv_out_w_ = 0, *conv_out_b_ = 0, *norm_out_g_ = 0, *norm_out_b_ = 0;
+  float *conv_in_w_ = 0, *conv_in_b_ = 0, *conv_out_b_ = 0, *norm_out_g_ = 0, *norm_out_b_ = 0;
+  bf16* conv_out_w_ = 0;
   float *t_w1_ = 0, *t_b1_ = 0, *t_w2_ = 0, *t_b2_ = 0, *tproj_w_ = 0, *tproj_b_ = 0;
   int tproj_total_ = 0;
   std::vector<ResW> res_;       // in forward order

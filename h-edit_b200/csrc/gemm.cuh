@@ -25,6 +25,7 @@ struct GemmEpilogue {
   op_t* out_bf16;  // [M][ldob] or null
   int rows_per_group, ldrv, ldr, ldo, ldob;
   int geglu;                // 1: every 32-col chunk = 16 value | 16 gate -> bf16 out has N/2 columns
+  int nchw_hw;              // >0: write out_f32 as [row / hw][N][row % hw] (NCHW latent layout; small-N generic path only)
 };
 
 struct GemmParams {
@@ -277,7 +278,10 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
                 if (e.bias) x += e.bias[cc];
                 if (e.rowvec) x += e.rowvec[size_t(row / e.rows_per_group) * e.ldrv + cc];
                 if (e.residual) x += e.residual[size_t(row) * e.ldr + cc];
-                if (e.out_f32) e.out_f32[size_t(row) * e.ldo + cc] = x;
+                if (e.out_f32) {
+                  if (e.nchw_hw) e.out_f32[(size_t(row / e.nchw_hw) * p.N + cc) * e.nchw_hw + (row % e.nchw_hw)] = x;
+                  else e.out_f32[size_t(row) * e.ldo + cc] = x;
+                }
                 if (e.out_bf16) e.out_bf16[size_t(row) * e.ldob + cc] = to_op(x);
               }
             }
