@@ -24,13 +24,14 @@ class StepCoefC(C.Structure):
 class EditArgsC(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("steps", C.c_int32), ("opt_steps", C.c_int32), ("explicit_form", C.c_int32),
-        ("schedule", C.c_int32), ("buffers_on_host", C.c_int32),
+        ("schedule", C.c_int32), ("buffers_on_host", C.c_int32), ("variant", C.c_int32),
         ("xT", C.c_void_p), ("zs", C.c_void_p), ("ctx", C.c_void_p), ("timesteps", C.c_void_p), ("coef", C.c_void_p),
         ("w_src", C.c_float), ("w_src_edit", C.c_float), ("w_tar", C.c_float), ("weight_reconstruction", C.c_float),
         ("use_p2p", C.c_int32),
         ("mapper", C.c_void_p), ("is_replace", C.c_void_p), ("replace_m", C.c_void_p), ("c_base", C.c_void_p), ("c_tar", C.c_void_p),
         ("self_lo", C.c_int32), ("self_hi", C.c_int32), ("self_max_tokens", C.c_int32),
         ("has_blend", C.c_void_p), ("blend_alpha", C.c_void_p), ("start_blend", C.c_int32), ("blend_th", C.c_float),
+        ("masa_start_step", C.c_int32), ("masa_start_layer", C.c_int32), ("mos_pull", C.c_int32),
         ("edited", C.c_void_p), ("recon", C.c_void_p), ("trace", C.c_void_p),
         ("n_sample_forwards", C.c_int64), ("n_kernel_launches", C.c_int64),
     ]

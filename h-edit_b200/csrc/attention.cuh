@@ -43,6 +43,7 @@ struct AttnParams {
   float* blend_acc;               // [img][2][n_blend_layers][H][Nq] fp32 accumulators or null
   const float* blend_alpha;       // [img][2][80]
   int blend_layer, n_blend_layers;
+  int tiles_per_cta;              // cross_attn2_kernel: query tiles handled by one CTA
 };
 
 HEDIT_DEVICE float ex2f(float x) {
@@ -717,6 +718,278 @@ __global__ void __launch_bounds__(192) cross_attn_kernel(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(o_read);
     }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------------- cross v2
+// Pipelined cross-attention for head dims <= 128: one CTA owns (work unit, head) and a run of query tiles.  The text
+// K/V of both phases (source, target) are loaded ONCE; "items" (tile, phase) stream through double-buffered Q smem and
+// S/O TMEM so that the TMA load and score MMA of item i+2 and the P.V MMA / output of item i-1 overlap the softmax of
+// item i.  Same P2P edit / LocalBlend accumulation as cross_attn_kernel.
+template <int DCH>
+struct CrossAttn2Cfg {
+  static constexpr int BKV = 80;
+  static constexpr int NQ = (DCH == 1) ? 2 : 1;                   // Q smem buffers (shared-memory budget)
+  static constexpr uint32_t Q_BYTES = DCH * 128 * 128;            // one Q tile
+  static constexpr uint32_t KV_BYTES = DCH * BKV * 128;           // K (or V) of one context
+  static constexpr uint32_t P_BYTES = 2 * 128 * 128;
+  static constexpr uint32_t PB_BYTES = BKV * 128 * 4;             // fp32 probabilities [col][row]: source (PB) and target scratch (PT)
+  static constexpr uint32_t SMEM_BYTES = NQ * Q_BYTES + 4 * KV_BYTES + P_BYTES + 2 * PB_BYTES + 256 + 1024;   // + barriers + edit tables
+  static constexpr uint32_t TMEM_COLS = 512;                      // S[2] at 0,128 ; O[2] at 256, 384
+  static_assert(DCH <= 2, "cross v2 supports head dims <= 128");
+};
+
+template <int DCH>
+static __global__ void __launch_bounds__(192, 1) cross_attn2_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = CrossAttn2Cfg<DCH>;
+  constexpr int BKV = Cfg::BKV, NQ = Cfg::NQ;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;                                   // [NQ][DCH][128][128 B]
+  uint8_t* sKV = sQ + NQ * Cfg::Q_BYTES;                // [phase][K|V][DCH][80][128 B]
+  uint8_t* sP = sKV + 4 * Cfg::KV_BYTES;
+  float* sPB = reinterpret_cast<float*>(sP + Cfg::P_BYTES);
+  float* sPT = sPB + BKV * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPT) + Cfg::PB_BYTES);
+  uint64_t* kv_full = bars;            // 1
+  uint64_t* q_full = bars + 1;         // 2
+  uint64_t* q_empty = bars + 3;        // 2
+  uint64_t* s_full = bars + 5;         // 2
+  uint64_t* s_free = bars + 7;         // 2 (4 arrivals)
+  uint64_t* pv_done = bars + 9;        // 2
+  uint64_t* o_free = bars + 11;        // 2 (4 arrivals)
+  uint64_t* p_full = bars + 13;        // 1 (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  int* sMap = reinterpret_cast<int*>(bars + 32);          // [80] edit tables of this image, staged once per CTA
+  float* sCb = reinterpret_cast<float*>(sMap + 80);
+  float* sCt = sCb + 80;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, unit = blockIdx.z;
+  const int s0 = p.unit_s0[unit], s1 = p.unit_s1[unit];
+  const int nph = (s1 >= 0) ? 2 : 1;
+  const int img = p.unit_img[unit];
+  const int DK = (p.d + 15) & ~15;
+  const int ntiles = (p.Nq + 127) >> 7;
+  const int t0 = blockIdx.x * p.tiles_per_cta;
+  const int nt = min(p.tiles_per_cta, ntiles - t0);
+  const int n_items = nt * nph;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
+    mbar_init(kv_full, 1); mbar_init(p_full, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
+      mbar_init(&pv_done[i], 1); mbar_init(&o_free[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (nph == 2 && threadIdx.x < BKV) {
+    sMap[threadIdx.x] = p.mapper[img * BKV + threadIdx.x];
+    sCb[threadIdx.x] = p.c_base[img * BKV + threadIdx.x];
+    sCt[threadIdx.x] = p.c_tar[img * BKV + threadIdx.x];
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, nph * 2 * Cfg::KV_BYTES);
+      for (int ph = 0; ph < nph; ++ph) {
+        const int ctx = p.ctx_idx[ph ? s1 : s0];
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) {
+          tma_load_4d(sKV + (ph * 2 + 0) * Cfg::KV_BYTES + c * BKV * 128, &p.tmK, kv_full, c * 64, h, 0, ctx);
+          tma_load_4d(sKV + (ph * 2 + 1) * Cfg::KV_BYTES + c * BKV * 128, &p.tmV, kv_full, c * 64, h, 0, ctx);
+        }
+      }
+      for (int i = 0; i < n_items; ++i) {
+        const int qb = i % NQ, tile = t0 + i / nph, ph = i % nph;
+        mbar_wait(&q_empty[qb], ((i / NQ) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qb], Cfg::Q_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + qb * Cfg::Q_BYTES + c * 16384, &p.tmQ, &q_full[qb], c * 64, h, tile * 128, ph ? s1 : s0);
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform control flow)
+    const uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
+    const uint32_t idesc_o = umma_idesc_bf16(128, DK, 0, 1);
+    const int ks = DK >> 4;
+    const uint32_t q_lo = umma_desc_lo_kmajor(smem_u32(sQ));
+    const uint32_t p_lo = umma_desc_lo_kmajor(smem_u32(sP));
+    const uint32_t k_lo = umma_desc_lo_kmajor(smem_u32(sKV));
+    const uint32_t v_lo = umma_desc_lo(smem_u32(sKV) + Cfg::KV_BYTES, BKV * 128);
+    auto issue_s = [&](int i) {        // S[i&1] = Q_i K_ph^T ; frees the Q buffer when done
+      const int b = i & 1, qb = i % NQ, ph = i % nph;
+      const uint32_t qa = q_lo + qb * (Cfg::Q_BYTES >> 4), kb = k_lo + ph * ((2 * Cfg::KV_BYTES) >> 4);
+#pragma unroll
+      for (int k = 0; k < 4 * DCH; ++k)
+        if (k < ks)
+          umma_f16_ss(tmem_base + b * 128, umma_desc_make(qa + (k >> 2) * (16384 >> 4) + 2 * (k & 3)),
+                      umma_desc_make(kb + (k >> 2) * ((BKV * 128) >> 4) + 2 * (k & 3)), idesc_s, k != 0);
+      umma_commit(&s_full[b]);
+      umma_commit(&q_empty[qb]);
+    };
+    auto issue_pv = [&](int i) {
+      const int b = i & 1, ph = i % nph;
+      const uint32_t vb = v_lo + ph * ((2 * Cfg::KV_BYTES) >> 4);
+#pragma unroll
+      for (int k = 0; k < BKV / 16; ++k)
+        umma_f16_ss(tmem_base + 256 + b * 128, umma_desc_make(p_lo + (k >> 2) * (16384 >> 4) + 2 * (k & 3)), umma_desc_make(vb + k * (2048 >> 4)),
+                    idesc_o, k != 0);
+      umma_commit(&pv_done[b]);
+    };
+    auto try_issue_s = [&](int i) {    // S_i needs Q_i in smem and S[i&1] drained by the softmax of item i-2
+      mbar_wait(&q_full[i % NQ], (i / NQ) & 1);
+      if (i >= 2) mbar_wait(&s_free[i & 1], ((i - 2) >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) issue_s(i);
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    try_issue_s(0);
+    if (n_items > 1) try_issue_s(1);
+    for (int i = 0; i < n_items; ++i) {
+      const int b = i & 1;
+      mbar_wait(p_full, i & 1);
+      mbar_wait(&o_free[b], ((i >> 1) & 1) ^ 1);          // output of item i-2 has been read out of O[b]
+      tc_fence_after();
+      if (elect_one()) issue_pv(i);
+      __syncwarp();
+      if (i + 2 < n_items) try_issue_s(i + 2);
+    }
+  } else {
+    // ------------------------------------------------------------ softmax / edit / output (warps 0..3)
+    const int r = threadIdx.x;
+    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    const int NKV = p.Nkv;                            // 77
+    auto write_out = [&](int i) {                      // O of item i -> global
+      const int b = i & 1, tile = t0 + i / nph, ph = i % nph;
+      const int row = tile * 128 + r, s = ph ? s1 : s0;
+      mbar_wait(&pv_done[b], (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < DK; c += 16) {
+        uint32_t o[16];
+        tmem_ld16(tmem_base + 256 + b * 128 + lane_sel + c, o);
+        tmem_ld_wait();
+        if (row < p.Nq) {
+          op_t* dst = p.out + (size_t(s) * p.Nq + row) * p.ldo + h * p.d + c;
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            if (c + g * 8 < p.d) {
+              const int q = g * 8;
+              *reinterpret_cast<uint4*>(dst + q) = make_uint4(
+                  pack_op2(__uint_as_float(o[q]), __uint_as_float(o[q + 1])), pack_op2(__uint_as_float(o[q + 2]), __uint_as_float(o[q + 3])),
+                  pack_op2(__uint_as_float(o[q + 4]), __uint_as_float(o[q + 5])), pack_op2(__uint_as_float(o[q + 6]), __uint_as_float(o[q + 7])));
+            }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[b]);
+    };
+    const bool rep = p.is_replace && p.is_replace[img];
+    for (int i = 0; i < n_items; ++i) {
+      const int b = i & 1, tile = t0 + i / nph, ph = i % nph;
+      const int row = tile * 128 + r;
+      mbar_wait(&s_full[b], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV; c += 16) tmem_ld16(tmem_base + b * 128 + lane_sel + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[b]);
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < BKV; ++j)
+        if (j < NKV) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(v[j]));
+      const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < BKV; ++j) {
+        const float e = (j < NKV) ? ex2f(fmaf(__uint_as_float(v[j]), p.scale_log2, -m)) : 0.f;
+        v[j] = __float_as_uint(e);
+        ls[j & 3] += e;
+      }
+      const float inv = 1.f / ((ls[0] + ls[1]) + (ls[2] + ls[3]));
+      const bool edit = (ph == 1);
+      const bool stash = (nph == 2 && ph == 0);
+      if (i > 0) { mbar_wait(&pv_done[(i - 1) & 1], ((i - 1) >> 1) & 1); tc_fence_after(); }     // P tile free again
+      float* dstf = edit ? sPT : sPB;
+      if (!edit) {
+        // plain softmax: probabilities -> P tile (and, for the source of a P2P pair, fp32 copy for the target's edit)
+#pragma unroll
+        for (int c = 0; c < BKV; c += 8) {
+          float pr[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pr[k] = __uint_as_float(v[c + k]) * inv;
+          *reinterpret_cast<uint4*>(sP + (c >> 6) * 16384 + sw128_off(r, (c & 63) >> 3)) =
+              make_uint4(pack_op2(pr[0], pr[1]), pack_op2(pr[2], pr[3]), pack_op2(pr[4], pr[5]), pack_op2(pr[6], pr[7]));
+          if (stash) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dstf[(c + k) * 128 + r] = pr[k];
+          }
+        }
+      } else {
+        // P2P target: stage own probabilities, then a ROLLED edit loop (keeps the kernel small enough for the I-cache)
+#pragma unroll
+        for (int j = 0; j < BKV; ++j) dstf[j * 128 + r] = __uint_as_float(v[j]) * inv;
+        const int* mp = sMap;
+        const float* cb = sCb;
+        const float* ct = sCt;
+#pragma unroll 1
+        for (int c = 0; c < BKV; c += 8) {
+          float pr[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int jc = c + k;
+            float x = 0.f;
+            if (jc < NKV) {
+              float base;
+              if (rep) {
+                const float* M = p.replace_m + size_t(img) * 77 * BKV + jc;
+                base = 0.f;
+#pragma unroll 1
+                for (int w = 0; w < 77; ++w) base = fmaf(sPB[w * 128 + r], M[w * BKV], base);
+              } else {
+                base = sPB[mp[jc] * 128 + r];
+              }
+              x = base * cb[jc] + sPT[jc * 128 + r] * ct[jc];
+            }
+            pr[k] = x;
+            sPT[jc * 128 + r] = x;                    // edited probabilities (for the LocalBlend accumulation below)
+          }
+          *reinterpret_cast<uint4*>(sP + (c >> 6) * 16384 + sw128_off(r, (c & 63) >> 3)) =
+              make_uint4(pack_op2(pr[0], pr[1]), pack_op2(pr[2], pr[3]), pack_op2(pr[4], pr[5]), pack_op2(pr[6], pr[7]));
+        }
+      }
+      if (p.blend_acc != nullptr && nph == 2 && row < p.Nq) {
+        const float* bal = p.blend_alpha + (size_t(img) * 2 + ph) * BKV;
+        float bsum = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < NKV; ++j) bsum = fmaf(bal[j], dstf[j * 128 + r], bsum);
+        float* acc = p.blend_acc + (((size_t(img) * 2 + ph) * p.n_blend_layers + p.blend_layer) * p.H + h) * p.Nq + row;
+        *acc += bsum;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (i > 0) write_out(i - 1);
+    }
+    if (n_items > 0) write_out(n_items - 1);
   }
   tc_fence_before();
   __syncthreads();

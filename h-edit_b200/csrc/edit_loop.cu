@@ -43,11 +43,11 @@ __global__ void gather_latents_kernel(const float* __restrict__ pool, const int*
 struct CallDesc {
   int S = 0;
   int pool_off = 0;                 // first sample of this call inside the eps pool
-  std::vector<int> lat, ctx, us0, us1, uimg, sq;
-  int *d_lat = 0, *d_ctx = 0, *d_us0 = 0, *d_us1 = 0, *d_uimg = 0, *d_sq = 0;
+  std::vector<int> lat, ctx, us0, us1, uimg, sq, sk;
+  int *d_lat = 0, *d_ctx = 0, *d_us0 = 0, *d_us1 = 0, *d_uimg = 0, *d_sq = 0, *d_sk = 0;
   int n_units = 0;
-  bool p2p = false;
-  void add(int l, int c) { lat.push_back(l); ctx.push_back(c); sq.push_back(S); ++S; }
+  bool p2p = false;      // attention control active in this launch (P2P edit / MasaCtrl)
+  void add(int l, int c) { lat.push_back(l); ctx.push_back(c); sq.push_back(S); sk.push_back(S); ++S; }
   void unit(int a, int b, int img) { us0.push_back(a); us1.push_back(b); uimg.push_back(img); ++n_units; }
 };
 
@@ -71,7 +71,8 @@ static int upload_ints(Engine& E, TempPool& tp, const std::vector<int>& v, int**
 }
 static int finish_call(Engine& E, TempPool& tp, CallDesc& c, cudaStream_t st) {
   if (upload_ints(E, tp, c.lat, &c.d_lat, st) || upload_ints(E, tp, c.ctx, &c.d_ctx, st) || upload_ints(E, tp, c.us0, &c.d_us0, st) ||
-      upload_ints(E, tp, c.us1, &c.d_us1, st) || upload_ints(E, tp, c.uimg, &c.d_uimg, st) || upload_ints(E, tp, c.sq, &c.d_sq, st))
+      upload_ints(E, tp, c.us1, &c.d_us1, st) || upload_ints(E, tp, c.uimg, &c.d_uimg, st) || upload_ints(E, tp, c.sq, &c.d_sq, st) ||
+      upload_ints(E, tp, c.sk, &c.d_sk, st))
     return -1;
   return 0;
 }
@@ -87,7 +88,9 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   const UNetCfg& c = E.cfg();
   const int B = a.B, T = a.steps, K = a.explicit_form ? 1 : std::max(1, a.opt_steps);
   const int n = E.latent_elems();
-  const bool p2p = a.use_p2p != 0;
+  const bool masa = a.masa_start_layer >= 0;
+  const bool p2p = a.use_p2p != 0 && a.variant == 0 && !masa;
+  const bool ctrl = p2p || masa;          // launches C / BC / E run with attention control
   const bool blend = p2p && a.has_blend != nullptr && a.blend_alpha != nullptr && E.n_blend_layers() > 0 && c.sample == 64;
   const cudaMemcpyKind kIn = a.buffers_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const cudaMemcpyKind kOut = a.buffers_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
@@ -102,13 +105,39 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   auto XO = [&](int b) { return 4 * B + b; };
   std::vector<int> iuA(2 * B), icA(2 * B), iuA0(2 * B), icA0(2 * B), iu(B), ics(B), ict(B);
   int pool = 0;
-  if (a.explicit_form) {
-    CallDesc e; e.p2p = p2p; e.pool_off = 0;
+  if (a.variant == 1) {
+    // h_Edit_R_* : only the edit row is denoised; no attention control
+    CallDesc A; A.pool_off = 0;
+    for (int b = 0; b < B; ++b) {
+      const int s = A.S;
+      A.add(XT(b, 1), 0); A.add(XT(b, 1), 1 + 2 * b);
+      if (a.explicit_form) A.add(XT(b, 1), 2 + 2 * b);
+      for (int j = s; j < A.S; ++j) A.unit(j, -1, b);
+      iuA[2 * b] = iuA[2 * b + 1] = iuA0[2 * b] = iuA0[2 * b + 1] = s;
+      icA[2 * b] = icA[2 * b + 1] = icA0[2 * b] = icA0[2 * b + 1] = s + 1;
+      if (a.explicit_form) { iu[b] = s; ics[b] = s + 1; ict[b] = s + 2; }
+    }
+    calls.push_back(A);
+    pool = A.S;
+    if (!a.explicit_form) {
+      CallDesc C; C.pool_off = pool;
+      for (int b = 0; b < B; ++b) {
+        const int s = C.S;
+        C.add(XO(b), 0); C.add(XO(b), 1 + 2 * b); C.add(XO(b), 2 + 2 * b);
+        for (int j = 0; j < 3; ++j) C.unit(s + j, -1, b);
+        iu[b] = C.pool_off + s; ics[b] = C.pool_off + s + 1; ict[b] = C.pool_off + s + 2;
+      }
+      pool += C.S;
+      calls.push_back(C);
+    }
+  } else if (a.explicit_form) {
+    CallDesc e; e.p2p = ctrl; e.pool_off = 0;
     for (int b = 0; b < B; ++b) {
       const int s = e.S;
       e.add(XT(b, 0), 0); e.add(XT(b, 1), 0); e.add(XT(b, 0), 1 + 2 * b); e.add(XT(b, 1), 1 + 2 * b); e.add(XT(b, 1), 2 + 2 * b);
       e.unit(s, -1, b); e.unit(s + 1, -1, b); e.unit(s + 3, -1, b);
       if (p2p) { e.unit(s + 2, s + 4, b); e.sq[s + 4] = s + 2; } else { e.unit(s + 2, -1, b); e.unit(s + 4, -1, b); }
+      e.sk[s + 1] = s; e.sk[s + 4] = s + 2;
       iuA[2 * b] = iuA0[2 * b] = s; iuA[2 * b + 1] = iuA0[2 * b + 1] = s + 1;
       icA[2 * b] = icA0[2 * b] = s + 2; icA[2 * b + 1] = icA0[2 * b + 1] = s + 3;
       iu[b] = s + 1; ics[b] = s + 3; ict[b] = s + 4;
@@ -116,7 +145,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     calls.push_back(e);
     pool = e.S;
   } else if (a.schedule == 0) {
-    CallDesc A, Bc, C; C.p2p = p2p;
+    CallDesc A, Bc, C; C.p2p = ctrl;
     A.pool_off = 0;
     for (int b = 0; b < B; ++b) {
       const int s = A.S;
@@ -133,12 +162,13 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
       C.add(XP(b, 0), 0); C.add(XO(b), 0); C.add(XP(b, 0), 1 + 2 * b); C.add(XO(b), 2 + 2 * b);
       C.unit(s, -1, b); C.unit(s + 1, -1, b);
       if (p2p) { C.unit(s + 2, s + 3, b); C.sq[s + 3] = s + 2; } else { C.unit(s + 2, -1, b); C.unit(s + 3, -1, b); }
+      C.sk[s + 1] = s; C.sk[s + 3] = s + 2;
       iu[b] = C.pool_off + s + 1; ict[b] = C.pool_off + s + 3;
     }
     pool = A.S + Bc.S + C.S;
     calls.push_back(A); calls.push_back(Bc); calls.push_back(C);
   } else {
-    CallDesc A, BC; BC.p2p = p2p;
+    CallDesc A, BC; BC.p2p = ctrl;
     A.pool_off = 0;
     for (int b = 0; b < B; ++b) {
       const int s = A.S;
@@ -153,6 +183,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
       BC.add(XP(b, 0), 0); BC.add(XO(b), 0); BC.add(XP(b, 0), 1 + 2 * b); BC.add(XO(b), 2 + 2 * b); BC.add(XO(b), 1 + 2 * b);
       BC.unit(s, -1, b); BC.unit(s + 1, -1, b); BC.unit(s + 4, -1, b);
       if (p2p) { BC.unit(s + 2, s + 3, b); BC.sq[s + 3] = s + 2; } else { BC.unit(s + 2, -1, b); BC.unit(s + 3, -1, b); }
+      BC.sk[s + 1] = s; BC.sk[s + 3] = s + 2;
       iuA[2 * b] = BC.pool_off + s; icA[2 * b] = BC.pool_off + s + 2;              // reused next step for the orig row
       iu[b] = BC.pool_off + s + 1; ict[b] = BC.pool_off + s + 3; ics[b] = BC.pool_off + s + 4;
     }
@@ -219,6 +250,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   long long fwd = 0;
   float* xt = L.lat; float* xprev = L.lat + size_t(2) * B * n; float* xopt = L.lat + size_t(4) * B * n;
 
+  int masa_step = 0;      // MasaCtrl's editor counts every controlled launch (masactrl_utils.py:15-23)
   auto run_call = [&](CallDesc& cd, int tindex, int ctrl_step, bool save) -> int {
     dim3 g(std::max(1, n / 4 / 256), cd.S);
     gather_latents_kernel<<<g, 256, 0, st>>>(L.lat, cd.d_lat, L.xin, n / 4);
@@ -226,16 +258,21 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     CallCtrl cc;
     cc.ctx_idx = cd.d_ctx; cc.time_idx = L.tidx + size_t(tindex) * maxS;
     cc.unit_s0 = cd.d_us0; cc.unit_s1 = cd.d_us1; cc.unit_img = cd.d_uimg; cc.n_units = cd.n_units;
-    if (cd.p2p) {
+    if (cd.p2p && p2p) {
       if (a.self_lo <= ctrl_step && ctrl_step < a.self_hi) { cc.self_mask = mask_small; cc.self_q = cd.d_sq; cc.self_k = cd.d_sq; cc.self_v = nullptr; }
       cc.mapper = L.mapper; cc.is_replace = L.is_replace; cc.replace_m = L.replace_m;
       cc.c_base = L.c_base + size_t(ctrl_step) * B * 80; cc.c_tar = L.c_tar + size_t(ctrl_step) * B * 80;
       if (blend && save) { cc.blend_acc = L.blend_acc; cc.blend_alpha = L.blend_alpha; }
+    } else if (cd.p2p && masa && masa_step >= a.masa_start_step) {
+      uint32_t m = 0;
+      for (int l = std::max(0, a.masa_start_layer); l < E.n_tf(); ++l) m |= 1u << l;
+      cc.self_mask = m; cc.self_q = nullptr; cc.self_k = cd.d_sk; cc.self_v = cd.d_sk;
     }
     const long r = E.forward(L.xin, L.eps + size_t(cd.pool_off) * n, cd.S, cc, st);
     if (r < 0) return -1;
     launches += r;
     fwd += cd.S;
+    if (cd.p2p && masa) ++masa_step;
     return 0;
   };
 
@@ -258,17 +295,18 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     for (int k = 0; k < K; ++k) {
       const bool save = (k == K - 1);
       if (!a.explicit_form) {
-        if (a.schedule == 0) { if (run_call(calls[1], i + 1, i, false)) return -1; if (run_call(calls[2], i + 1, i, save)) return -1; }
+        if (a.variant == 0 && a.schedule == 0) { if (run_call(calls[1], i + 1, i, false)) return -1; if (run_call(calls[2], i + 1, i, save)) return -1; }
         else if (run_call(calls[1], i + 1, i, save)) return -1;
       }
       CorrParams cp;
       cp.eps = L.eps; cp.iu = L.iu; cp.ics = L.ics; cp.ict = L.ict; cp.w_src_edit = a.w_src_edit; cp.w_tar = a.w_tar;
       cp.corr = L.corr; cp.x_opt = xopt; cp.x_stride = n; cp.x_base = xprev + n; cp.xb_stride = size_t(2) * n;
-      cp.partial = (k > 0) ? L.partial : nullptr; cp.n = n;
+      const bool pull = (k > 0) && a.mos_pull != 0;
+      cp.partial = pull ? L.partial : nullptr; cp.n = n;
       hstep_corr_kernel<<<dim3(nparts, B), 256, 0, st>>>(cp);
       UpdateParams up;
       up.x_opt = xopt; up.x_stride = n; up.x_base = xprev + n; up.xb_stride = size_t(2) * n; up.corr = L.corr;
-      up.partial = (k > 0) ? L.partial : nullptr; up.nparts = nparts; up.coeff = hc.coeff; up.w_rec = a.weight_reconstruction; up.n = n;
+      up.partial = pull ? L.partial : nullptr; up.nparts = nparts; up.coeff = hc.coeff; up.w_rec = a.weight_reconstruction; up.n = n;
       hstep_update_kernel<<<dim3(nparts, B), 256, 0, st>>>(up);
       launches += 2;
     }

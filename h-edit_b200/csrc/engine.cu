@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "elementwise.cuh"
@@ -388,9 +389,28 @@ static cudaError_t launch_cross_t(const AttnParams& a, int units, cudaStream_t s
   cross_attn_kernel<DCH><<<grid, 192, CrossAttnCfg<DCH>::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
+template <int DCH>
+static cudaError_t launch_cross2_t(AttnParams a, int units, cudaStream_t st) {
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(cross_attn2_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, CrossAttn2Cfg<DCH>::SMEM_BYTES); set = true; }
+  const int ntiles = (a.Nq + 127) / 128;
+  // enough CTAs for ~2 waves, but long enough runs of tiles per CTA to amortise the K/V load and the pipeline fill
+  int groups = 1;
+  while (groups < ntiles && groups * a.H * units < 2 * 148 && ntiles / (groups * 2) >= 2) groups *= 2;
+  a.tiles_per_cta = (ntiles + groups - 1) / groups;
+  dim3 grid((ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta, a.H, units);
+  cross_attn2_kernel<DCH><<<grid, 192, CrossAttn2Cfg<DCH>::SMEM_BYTES, st>>>(a);
+  return cudaGetLastError();
+}
 cudaError_t launch_cross_attn(const AttnParams& a, int dch, int units, cudaStream_t st) {
-  if (dch == 1) return launch_cross_t<1>(a, units, st);
-  if (dch == 2) return launch_cross_t<2>(a, units, st);
+  static const bool force_v1 = getenv("HEDIT_CROSS_V1") != nullptr;      // tuning switch: single-tile kernel
+  if (force_v1) {
+    if (dch == 1) return launch_cross_t<1>(a, units, st);
+    if (dch == 2) return launch_cross_t<2>(a, units, st);
+    return launch_cross_t<3>(a, units, st);
+  }
+  if (dch == 1) return launch_cross2_t<1>(a, units, st);
+  if (dch == 2) return launch_cross2_t<2>(a, units, st);
   return launch_cross_t<3>(a, units, st);
 }
 static int dch_for(int d) { return d <= 64 ? 1 : (d <= 128 ? 2 : 3); }

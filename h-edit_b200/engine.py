@@ -124,8 +124,9 @@ class UNetEngine:
     # ---- the bridge-sampling loop
     def edit(self, xT: torch.Tensor, zs: torch.Tensor, ctx: torch.Tensor, timesteps: Sequence[int], coef: np.ndarray,
              cfg_scales: Sequence[float], plan: Optional[EditPlan], weight_reconstruction: float = 0.1, optimization_steps: int = 1,
-             explicit_form: bool = False, schedule: int = 1, trace: bool = False):
+             explicit_form: bool = False, schedule: int = 1, trace: bool = False, variant: int = 0, masactrl=None, mos_pull: bool = True):
         """xT (B,C,h,w), zs (B,steps,C,h,w), ctx (1+2B,77,D): all on the SAME side (all host or all on this device).
+        variant 1 = h_Edit_R_* (no attention control); masactrl = (start_step, start_layer) enables mutual self-attention.
         Returns (edited, recon[, trace]) on that side."""
         B, steps = xT.shape[0], zs.shape[1]
         on_host = not xT.is_cuda
@@ -145,6 +146,9 @@ class UNetEngine:
         a.xT, a.zs, a.ctx, a.timesteps, a.coef = xT.data_ptr(), zs.data_ptr(), ctx.data_ptr(), ts.ctypes.data, coef.ctypes.data
         a.w_src, a.w_src_edit, a.w_tar = [float(v) for v in cfg_scales]
         a.weight_reconstruction = float(weight_reconstruction)
+        a.variant = int(variant)
+        a.mos_pull = int(mos_pull)
+        a.masa_start_step, a.masa_start_layer = (int(masactrl[0]), int(masactrl[1])) if masactrl is not None else (0, -1)
         keep = [ts, coef, xT, zs, ctx]
         if plan is not None:
             a.use_p2p = 1

@@ -32,7 +32,8 @@ def get_engine(model, max_samples: int = 5, device: int = 0) -> UNetEngine:
 
 def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Sequence[Sequence[str]], cfg_scales, controllers,
                      eta=1.0, weight_reconstruction=0.075, optimization_steps=1, after_skip_steps=None, is_ddim_inversion=False,
-                     explicit_form=False, schedule=1, engine: Optional[UNetEngine] = None, trace=False):
+                     explicit_form=False, schedule=1, engine: Optional[UNetEngine] = None, trace=False, variant=0, masactrl=None,
+                     mos_pull=True):
     """B independent edits in one native call.  xT (B,C,h,w); zs (B,steps,C,h,w); prompt_pairs[b] = [src, tar];
     controllers[b] = P2P controller of image b (ours or the reference's) or None for all (P2P off)."""
     B = xT.shape[0]
@@ -47,7 +48,8 @@ def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Se
     plan = None
     if controllers is not None and all(c is not None for c in controllers):
         plan = compile_edit_plan(controllers, steps)
-    out = eng.edit(xT, zs[:, :steps], ctx, ts, coef, cfg_scales, plan, weight_reconstruction, optimization_steps, explicit_form, schedule, trace)
+    out = eng.edit(xT, zs[:, :steps], ctx, ts, coef, cfg_scales, plan, weight_reconstruction, optimization_steps, explicit_form, schedule, trace,
+                   variant=variant, masactrl=masactrl, mos_pull=mos_pull)
     if plan is not None:
         for c in controllers:       # keep the controller's observable counters consistent with the reference
             c.cur_step = getattr(c, "cur_step", 0) + steps
@@ -57,7 +59,7 @@ def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Se
 
 
 def _single(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstruction, optimization_steps, after_skip_steps,
-            is_ddim_inversion, explicit_form):
+            is_ddim_inversion, explicit_form, variant=0, masactrl=None, mos_pull=True):
     assert len(prompts) >= 2, "only support prompt editing"
     dev = xT.device
     x = xT.reshape(1, *xT.shape[-3:])
@@ -68,7 +70,7 @@ def _single(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstr
     use_cuda = torch.device(dev).type == "cuda"
     x, z = (x.cuda(), z.cuda()) if use_cuda else (x.cpu(), z.cpu())
     edited, recon = h_edit_p2p_batch(model, x, z, [prompts[:2]], cfg_scales, ctrl, eta, weight_reconstruction, optimization_steps, steps,
-                                     is_ddim_inversion, explicit_form)
+                                     is_ddim_inversion, explicit_form, variant=variant, masactrl=masactrl, mos_pull=mos_pull)
     return edited.to(dev), recon.to(dev)
 
 
@@ -83,3 +85,50 @@ def h_Edit_p2p_explicit(model, xT, eta=1.0, prompts="", cfg_scales=None, prog_ba
                         is_ddim_inversion=True, after_skip_steps=35):
     """Reference signature (p2p_h_edit.py:380)."""
     return _single(model, xT, eta, prompts, cfg_scales, zs, controller, 0.0, 1, after_skip_steps, is_ddim_inversion, True)
+
+
+def h_Edit_R_implicit(model, xT, eta=1.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None,
+                      weight_reconstruction=0.1, optimization_steps=1, after_skip_steps=35, is_ddim_inversion=False):
+    """Reference signature (p2p_h_edit.py:162): h-Edit-R, implicit form, no P2P.  skip == 0 only (the reference's extra
+    pre-step for skipped schedules, :239-267, is not implemented)."""
+    assert not is_ddim_inversion, "only DDPM sampling (reference assert, p2p_h_edit.py:196)"
+    assert after_skip_steps == model.scheduler.num_inference_steps, "h_Edit_R_implicit: skip > 0 is not supported on the fused path"
+    return _single(model, xT, eta, prompts, cfg_scales, zs, None, weight_reconstruction, optimization_steps, after_skip_steps,
+                   is_ddim_inversion, False, variant=1)
+
+
+def h_Edit_R_explicit(model, xT, eta=1.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None,
+                      is_ddim_inversion=False, after_skip_steps=35):
+    """Reference signature (p2p_h_edit.py:21): h-Edit-R, explicit form, no P2P."""
+    return _single(model, xT, eta, prompts, cfg_scales, zs, None, 0.0, 1, after_skip_steps, is_ddim_inversion, True, variant=1)
+
+
+class MutualSelfAttentionControl:
+    """Holds MasaCtrl's schedule (masactrl/masactrl.py:11-36): mutual self-attention from `start_step` on, in transformer
+    blocks >= `start_layer` (of 16).  The control itself runs inside self_attn_kernel as a K/V source-sample swap."""
+
+    def __init__(self, start_step=4, start_layer=10, layer_idx=None, step_idx=None, total_steps=50, model_type="SD"):
+        if layer_idx is not None or step_idx is not None:
+            raise NotImplementedError("explicit layer_idx / step_idx lists are not supported on the fused path")
+        self.start_step, self.start_layer, self.total_steps = start_step, start_layer, total_steps
+        self.cur_step = 0
+        self.cur_att_layer = 0
+        self.num_att_layers = -1
+
+
+def regiter_attention_editor_diffusers(model, editor) -> None:
+    """Same (misspelt) name as the reference's registration hook (masactrl/masactrl_utils.py:35): records the editor on the
+    pipeline object; no per-layer monkey-patching is needed."""
+    model._hedit_masactrl_editor = editor
+    editor.num_att_layers = 32
+
+
+def h_Edit_masactrl_implicit(model, xT, eta=1.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, optimization_steps=1,
+                             after_skip_steps=35, is_ddim_inversion=True):
+    """Reference signature (masactrl_h_edit.py:14)."""
+    ed = getattr(model, "_hedit_masactrl_editor", None)
+    assert ed is not None, "call regiter_attention_editor_diffusers(model, MutualSelfAttentionControl(...)) first"
+    out = _single(model, xT, eta, prompts, cfg_scales, zs, None, 0.0, optimization_steps, after_skip_steps, is_ddim_inversion, False,
+                  masactrl=(ed.start_step - ed.cur_step, ed.start_layer), mos_pull=False)
+    ed.cur_step += after_skip_steps * optimization_steps
+    return out

@@ -45,6 +45,9 @@ typedef struct hedit_edit_args {
                                 1: exact-reuse merged pattern (7 / step): source-branch outputs of call C are reused
                                    as the next step's call-A source inputs, calls B and C share one launch */
   int32_t buffers_on_host;   /* 1: xT, zs, ctx, edited, recon, trace are host pointers (copies are part of the call) */
+  int32_t variant;           /* 0: P2P-family samplers (orig and edit rows both denoised: h_Edit_p2p_*, h_Edit_masactrl_implicit);
+                                1: h_Edit_R_implicit / h_Edit_R_explicit (p2p_h_edit.py:162,21): no attention control, both rows are
+                                   stepped with the edit row's source-guided noise prediction */
   const float* xT;           /* [B][C][h][w] */
   const float* zs;           /* [B][steps][C][h][w]; zs[b][idx] as in the reference (idx = steps-1-i at step i) */
   const float* ctx;          /* [1+2B][ctx_len][cross_dim]: row 0 = "", then (src_b, tar_b) pairs (encode_text) */
@@ -65,6 +68,10 @@ typedef struct hedit_edit_args {
   const float* blend_alpha;  /* [B][2][80]  LocalBlend.alpha_layers */
   int32_t start_blend;       /* LocalBlend.start_blend */
   float blend_th;            /* LocalBlend.th */
+  /* ---- MasaCtrl mutual self-attention (masactrl/masactrl.py:53-69): from controller step >= masa_start_step, in transformer
+   * blocks >= masa_start_layer, the edit samples attend to the K/V of their source samples.  masa_start_layer < 0: off */
+  int32_t masa_start_step, masa_start_layer;
+  int32_t mos_pull;          /* 1: apply the L1 reconstruction pull on MOS iterations k>0 (p2p_h_edit.py:670-686); 0: masactrl_h_edit.py */
   /* ---- outputs */
   float* edited;             /* [B][C][h][w] */
   float* recon;              /* [B][C][h][w] */

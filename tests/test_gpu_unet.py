@@ -119,3 +119,53 @@ def test_edit_loop_sd15_config1():
     against outputs of the UNMODIFIED reference loop (tools/make_golden.py)."""
     r_ed, r_rc, r_w0, st = _run_golden("sd15_config1")
     assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# other reference samplers on the same hot path (SURVEY 8a rows 2 and 10), each against a golden produced by the
+# unmodified reference function (tools/make_golden.py --config variants)
+def _run_variant(name, eng_cache={}):
+    _fp32()
+    g = load_golden(name)
+    meta = g["meta"]
+    cfg = cfg_from_meta(meta)
+    if "m" not in eng_cache:
+        model = OraclePipeline(cfg, seed=0)
+        eng_cache["m"] = (model, UNetEngine.from_unet(model.unet, max_samples=5, max_contexts=4))
+    model, eng = eng_cache["m"]
+    T, K, mode = meta["T"], meta["K"], meta["mode"]
+    model.scheduler.set_timesteps(T)
+    ts, coef = hedit_b200.step_tables(model.scheduler, T, meta["eta"], False)
+    ctx = torch.cat([g["ctx_uncond"], g["ctx_src"], g["ctx_tar"]]).cuda()
+    xT = g["xT"].reshape(1, *g["xT"].shape[-3:]).cuda()
+    zs = g["zs"].reshape(1, *g["zs"].shape).cuda()
+    cfgs = meta["cfg_scales"]
+    if mode == "p2p_explicit":
+        bw = meta["blend_words"]
+        ctrl = hedit_b200.make_controller(meta["prompts"], False, meta["xa"], meta["sa"], blend_word=((bw[0],), (bw[1],)),
+                                          equilizer_params={"words": (bw[1],), "values": (2.0,)}, num_steps=T, tokenizer=model.tokenizer)
+        plan = hedit_b200.compile_edit_plan([ctrl], T)
+        ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, plan, 0.0, 1, explicit_form=True)
+        want_fwd = 5 * T
+    elif mode == "R_implicit":
+        ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, meta["weight_reconstruction"], K, variant=1)
+        want_fwd = (2 + 3 * K) * T
+    elif mode == "R_explicit":
+        ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, 1, explicit_form=True, variant=1)
+        want_fwd = 3 * T
+    elif mode == "masactrl":
+        ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, K, masactrl=(meta["masa_start_step"], meta["masa_start_layer"]), mos_pull=False)
+        want_fwd = (2 + 5 * K) * T
+    r_ed, m_ed = rel_err(ed.cpu(), g["edited"])
+    r_rc, m_rc = rel_err(rc.cpu(), g["recon"])
+    print(f"{name}: edited rel {r_ed:.3e} max {m_ed:.3e} | recon rel {r_rc:.3e} max {m_rc:.3e} | {eng.last_stats}")
+    assert eng.last_stats["sample_forwards"] == want_fwd
+    assert r_ed < TOL_LOOP and r_rc < TOL_LOOP
+    return r_ed, r_rc
+
+
+@pytest.mark.parametrize("name", ["tiny_p2p_explicit", "tiny_R_implicit_mos2", "tiny_R_explicit", "tiny_masactrl_mos2"])
+def test_sampler_variants(name):
+    if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", name + ".pt")):
+        pytest.skip("golden missing")
+    _run_variant(name)

@@ -27,6 +27,14 @@ from refload import load_reference  # noqa: E402
 PROMPTS = ["a green lizard is sitting on a branch", "a brown lizard is sitting on a branch"]
 BLEND = ("lizard", "lizard")
 
+# sampler variants beyond the north-star implicit+P2P loop: name -> (unet cfg, T, K, mode)
+VARIANTS = {
+    "tiny_p2p_explicit": (UNetConfig.tiny(sample_size=64), 6, 1, "p2p_explicit"),
+    "tiny_R_implicit_mos2": (UNetConfig.tiny(sample_size=64), 5, 2, "R_implicit"),
+    "tiny_R_explicit": (UNetConfig.tiny(sample_size=64), 6, 1, "R_explicit"),
+    "tiny_masactrl_mos2": (UNetConfig.tiny(sample_size=64), 5, 2, "masactrl"),
+}
+
 CASES = {
     # name: (unet cfg, T, K, is_replace, blend)
     "tiny_refine_blend": (UNetConfig.tiny(sample_size=64), 10, 1, False, True),
@@ -103,14 +111,75 @@ def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
     return out
 
 
+def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
+    """Other reference samplers on the same set-up: h_Edit_p2p_explicit (p2p_h_edit.py:380), h_Edit_R_implicit/explicit (:162,:21),
+    h_Edit_masactrl_implicit (masactrl_h_edit.py:14)."""
+    import importlib
+    torch.set_num_threads(os.cpu_count())
+    model = OraclePipeline(cfg, seed=0)
+    model.scheduler.set_timesteps(T)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    w0 = torch.randn(1, cfg.in_channels, cfg.sample_size, cfg.sample_size, generator=g) * 0.18215 * 5
+    prompts = list(PROMPTS)
+    if mode == "masactrl":
+        prompts[0] = ""                      # main_masactrl.py:180
+    torch.manual_seed(0)
+    _, zs, wts, _ = ref.ddpm_inversion.inversion_forward_process_ddpm(
+        model, w0, etas=1.0, prog_bar=False, prompt=prompts[0], cfg_scale_src=1.0, num_inference_steps=T)
+    meta_extra = {}
+    kw = dict(xT=wts[T], eta=1.0, prompts=prompts, cfg_scales=[1.0, 5.0, 7.5], prog_bar=False, zs=zs[:T], after_skip_steps=T,
+              is_ddim_inversion=False)
+    if mode == "p2p_explicit":
+        controller = ref.ptp_controller_utils.make_controller(
+            prompts=prompts, is_replace_controller=False, cross_replace_steps=xa, self_replace_steps=sa,
+            blend_word=((BLEND[0],), (BLEND[1],)), equilizer_params={"words": (BLEND[1],), "values": (2.0,)}, num_steps=T,
+            tokenizer=model.tokenizer, device=model.device)
+        ref.ptp_utils.register_attention_control(model, controller)
+        edited, recon = ref.p2p_h_edit.h_Edit_p2p_explicit(model, controller=controller, **kw)
+    elif mode == "R_implicit":
+        edited, recon = ref.p2p_h_edit.h_Edit_R_implicit(model, controller=None, weight_reconstruction=0.1, optimization_steps=K, **kw)
+    elif mode == "R_explicit":
+        edited, recon = ref.p2p_h_edit.h_Edit_R_explicit(model, controller=None, **kw)
+    elif mode == "masactrl":
+        masa_pkg = importlib.import_module("masactrl")
+        sys.modules.setdefault("masa_ctrl", masa_pkg)                       # reference typo: masactrl.py:8 imports `masa_ctrl`
+        sys.modules.setdefault("masa_ctrl.masactrl_utils", importlib.import_module("masactrl.masactrl_utils"))
+        masa = importlib.import_module("masactrl.masactrl")
+        mh = importlib.import_module("inversion.masactrl_h_edit")
+        start_step, start_layer = 2, 10
+        editor = masa.MutualSelfAttentionControl(start_step, start_layer, total_steps=T * K)
+        importlib.import_module("masactrl.masactrl_utils").regiter_attention_editor_diffusers(model, editor)
+        edited, recon = mh.h_Edit_masactrl_implicit(model, optimization_steps=K, **kw)
+        meta_extra = dict(masa_start_step=start_step, masa_start_layer=start_layer)
+    else:
+        raise ValueError(mode)
+    enc = ref.inversion_utils.encode_text
+    return {
+        "meta": dict(name=name, mode=mode, T=T, K=K, xa=xa, sa=sa, prompts=prompts, blend_words=BLEND, cfg_scales=[1.0, 5.0, 7.5], eta=1.0,
+                     weight_reconstruction=0.1, is_replace=False, blend=(mode == "p2p_explicit"),
+                     unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
+                               cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
+                     weights="oracle.sd_unet.seeded_init_(seed=0)", generator="tools/make_golden.py", torch=torch.__version__, **meta_extra),
+        "w0": w0, "zs": zs[:T].clone(), "xT": wts[T].clone(),
+        "ctx_uncond": enc(model, [""]), "ctx_src": enc(model, [prompts[0]]), "ctx_tar": enc(model, [prompts[1]]),
+        "edited": edited.detach().clone(), "recon": recon.detach().clone(),
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "all"])
+    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "variants", "all"])
     args = ap.parse_args()
     ref = load_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    if args.config in ("variants", "all"):
+        for name, (cfg, T, K, mode) in VARIANTS.items():
+            out = run_variant(ref, name, cfg, T, K, mode)
+            path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
+            torch.save(out, path)
+            print(name, "->", path, "|edited| %.4f" % out["edited"].abs().mean().item(), flush=True)
     for name, (cfg, T, K, rep, blend) in CASES.items():
-        if args.config != "all" and not name.startswith(args.config):
+        if args.config == "variants" or (args.config != "all" and not name.startswith(args.config)):
             continue
         out = run_case(ref, name, cfg, T, K, rep, blend)
         path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")

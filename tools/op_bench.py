@@ -64,6 +64,34 @@ def bench_conv(iters):
         print(f"conv3x3 S={S} {H}x{H} C={C}->{Co}: {ms:.3f} ms  {2.0 * S * (H // st) ** 2 * Co * 9 * C / ms / 1e9:.1f} TFLOP/s")
 
 
+def bench_cross(iters):
+    for (S, N, H, d, pairs) in [(40, 4096, 8, 40, False), (40, 4096, 8, 40, True), (40, 1024, 8, 80, True)]:
+        C = H * d
+        n_ctx = 17
+        q = bf(torch.randn(S, N, C, device=DEV))
+        kv = bf(torch.randn(n_ctx, 77, 2 * C, device=DEV))
+        ctx_idx = torch.randint(0, n_ctx, (S,), dtype=torch.int32, device=DEV)
+        if pairs:      # per image: 3 singles + one (source, target) pair
+            us0, us1, uimg = [], [], []
+            for b in range(S // 5):
+                s = 5 * b
+                us0 += [s, s + 1, s + 4, s + 2]; us1 += [-1, -1, -1, s + 3]; uimg += [b] * 4
+        else:
+            us0, us1, uimg = list(range(S)), [-1] * S, [0] * S
+        t = lambda v, dt=torch.int32: torch.tensor(v, dtype=dt, device=DEV)
+        us0, us1, uimg = t(us0), t(us1), t(uimg)
+        nimg = S // 5
+        mapper = torch.randint(0, 77, (nimg, 80), dtype=torch.int32, device=DEV)
+        cb, ct = torch.rand(nimg, 80, device=DEV), torch.rand(nimg, 80, device=DEV)
+        isr = torch.zeros(nimg, dtype=torch.int32, device=DEV)
+        out = torch.zeros(S, N, C, device=DEV, dtype=q.dtype)
+        fn = lambda: lib().hedit_op_cross_attention_p2p(P(q), P(kv), S, n_ctx, N, H, d, len(us0), P(us0), P(us1), P(uimg), P(ctx_idx), P(mapper),
+                                                        P(cb), P(ct), None, P(isr), None, None, -1, 0, P(out), None)
+        ms = timeit(fn, iters)
+        items = S * H * (N // 128)
+        print(f"cross_attn S={S} N={N} H={H} d={d} pairs={pairs}: {ms:.3f} ms  ({items} tile-phases, {ms * 1e-3 * 1.9e9 * 148 / items:.0f} SM-cycles/tile-phase)")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -76,3 +104,5 @@ if __name__ == "__main__":
         bench_linear(a.iters)
     if a.what in ("conv", "all"):
         bench_conv(a.iters)
+    if a.what in ("cross", "all"):
+        bench_cross(a.iters)
