@@ -32,6 +32,7 @@ class EditArgsC(C.Structure):
         ("self_lo", C.c_int32), ("self_hi", C.c_int32), ("self_max_tokens", C.c_int32),
         ("has_blend", C.c_void_p), ("blend_alpha", C.c_void_p), ("start_blend", C.c_int32), ("blend_th", C.c_float),
         ("masa_start_step", C.c_int32), ("masa_start_layer", C.c_int32), ("mos_pull", C.c_int32),
+        ("xt_is_pair", C.c_int32), ("ctrl_step0", C.c_int32), ("blend_state", C.c_void_p),
         ("edited", C.c_void_p), ("recon", C.c_void_p), ("trace", C.c_void_p),
         ("n_sample_forwards", C.c_int64), ("n_kernel_launches", C.c_int64),
     ]
@@ -47,11 +48,13 @@ SYMBOLS = {
     "hedit_engine_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
     "hedit_engine_finalize": (_I, [_P]),
     "hedit_engine_flops_per_sample": (C.c_double, [_P]),
+    "hedit_engine_blend_state_elems": (_I, [_P, _I]),
     "hedit_operand_dtype": (C.c_char_p, []),
     "hedit_engine_tensor_count": (_I, [_P]),
     "hedit_engine_tensor_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_int64)]),
     "hedit_engine_profile_forward": (_I, [_P, _I, _I, C.c_char_p, _I]),
     "hedit_unet_forward": (_I, [_P, _P, _P, _P, _I, _P, _P]),
+    "hedit_unet_forward_indexed": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _P]),
     "hedit_edit_p2p": (_I, [_P, C.POINTER(EditArgsC), _P]),
     "hedit_op_linear": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "hedit_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

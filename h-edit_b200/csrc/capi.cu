@@ -93,6 +93,11 @@ int hedit_engine_finalize(hedit_engine* h) {
 
 double hedit_engine_flops_per_sample(hedit_engine* h) { return h ? h->E->flops_per_sample() : 0.0; }
 
+int hedit_engine_blend_state_elems(hedit_engine* h, int B) {
+  if (!h) return fail("null engine");
+  return B * 2 * h->E->n_blend_layers() * h->E->cfg().heads * 256;
+}
+
 const char* hedit_operand_dtype(void) { return HEDIT_OPERAND_NAME; }
 
 int hedit_engine_tensor_count(hedit_engine* h) { return h ? h->E->tensor_count() : fail("null engine"); }
@@ -142,24 +147,27 @@ int hedit_engine_profile_forward(hedit_engine* h, int S, int reps, char* out, in
   return 0;
 }
 
-int hedit_unet_forward(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int S, float* eps, void* stream) {
+int hedit_unet_forward_indexed(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int n_ctx, const int32_t* ctx_idx,
+                               int S, float* eps, void* stream) {
   if (!h) return fail("null engine");
   cudaSetDevice(h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   Engine& E = *h->E;
   if (S > h->cap) return fail("S exceeds max_samples");
   // distinct timesteps -> table rows
-  std::vector<float> uniq; std::vector<int> tidx(S), ident(S), minus1(S, -1), zeros(S, 0);
+  std::vector<float> uniq; std::vector<int> tidx(S), ident(S), minus1(S, -1), zeros(S, 0), cidx(S);
   for (int s = 0; s < S; ++s) {
     int j = -1;
     for (size_t k = 0; k < uniq.size(); ++k) if (uniq[k] == timesteps[s]) j = int(k);
     if (j < 0) { uniq.push_back(timesteps[s]); j = int(uniq.size()) - 1; }
     tidx[s] = j; ident[s] = s;
+    cidx[s] = ctx_idx ? ctx_idx[s] : s;
+    if (cidx[s] < 0 || cidx[s] >= n_ctx) return fail("ctx_idx out of range");
   }
   if (E.set_timesteps(uniq.data(), int(uniq.size()), st)) return fail(E.error());
-  if (E.set_contexts(ctx, S, st)) return fail(E.error());
+  if (E.set_contexts(ctx, n_ctx, st)) return fail(E.error());
   cudaMemcpyAsync(h->d_tidx, tidx.data(), S * sizeof(int), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(h->d_ctx_idx, ident.data(), S * sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(h->d_ctx_idx, cidx.data(), S * sizeof(int), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(h->d_unit0, ident.data(), S * sizeof(int), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(h->d_unit1, minus1.data(), S * sizeof(int), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(h->d_uimg, zeros.data(), S * sizeof(int), cudaMemcpyHostToDevice, st);
@@ -171,6 +179,10 @@ int hedit_unet_forward(hedit_engine* h, const float* x, const float* timesteps, 
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(e, "unet forward");
   return int(r);
+}
+
+int hedit_unet_forward(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int S, float* eps, void* stream) {
+  return hedit_unet_forward_indexed(h, x, timesteps, ctx, S, nullptr, S, eps, stream);
 }
 
 int hedit_edit_p2p(hedit_engine* h, hedit_edit_args* args, void* stream) {

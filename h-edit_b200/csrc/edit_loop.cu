@@ -95,6 +95,10 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   const cudaMemcpyKind kIn = a.buffers_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const cudaMemcpyKind kOut = a.buffers_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (B < 1 || T < 1) { E.err_ = "bad batch/steps"; return -1; }
+  if (a.xt_is_pair && !a.explicit_form && a.variant == 0 && a.schedule != 0) {
+    E.err_ = "xt_is_pair (single-step use) needs schedule 0: the exact-reuse schedule carries UNet outputs across timesteps";
+    return -1;
+  }
   TempPool tp;
 
   // ---- call descriptors.  latent pool slots: xt[b][row] = 2b+row ; xprev[b][row] = 2B+2b+row ; xopt[b] = 4B+b
@@ -229,19 +233,26 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
       L.has_blend = reinterpret_cast<int*>(tp.get(size_t(B) * sizeof(int)));
       L.blend_alpha = fa(size_t(B) * 2 * 80);
       const size_t accn = size_t(B) * 2 * E.n_blend_layers() * c.heads * 256;
-      L.blend_acc = fa(accn);
       CKE(cudaMemcpyAsync(L.has_blend, a.has_blend, size_t(B) * sizeof(int), cudaMemcpyHostToDevice, st));
       CKE(cudaMemcpyAsync(L.blend_alpha, a.blend_alpha, size_t(B) * 2 * 80 * sizeof(float), cudaMemcpyHostToDevice, st));
-      CKE(cudaMemsetAsync(L.blend_acc, 0, accn * sizeof(float), st));
+      if (a.blend_state) {
+        L.blend_acc = a.blend_state;               // caller-owned, carried across single-step calls
+      } else {
+        L.blend_acc = fa(accn);
+        CKE(cudaMemsetAsync(L.blend_acc, 0, accn * sizeof(float), st));
+      }
     }
   }
   // ---- inputs
   if (E.set_contexts(a.ctx, 1 + 2 * B, st)) return -1;
   if (E.set_timesteps(a.timesteps, T + 1, st)) return -1;
   CKE(cudaMemcpyAsync(L.zs, a.zs, size_t(B) * T * n * sizeof(float), kIn, st));
-  // xt rows 0 and 1 <- xT
-  CKE(cudaMemcpy2DAsync(L.lat, size_t(2) * n * sizeof(float), a.xT, size_t(n) * sizeof(float), size_t(n) * sizeof(float), B, kIn, st));
-  CKE(cudaMemcpy2DAsync(L.lat + n, size_t(2) * n * sizeof(float), a.xT, size_t(n) * sizeof(float), size_t(n) * sizeof(float), B, kIn, st));
+  if (a.xt_is_pair) {
+    CKE(cudaMemcpyAsync(L.lat, a.xT, size_t(2) * B * n * sizeof(float), kIn, st));
+  } else {   // xt rows 0 and 1 <- xT
+    CKE(cudaMemcpy2DAsync(L.lat, size_t(2) * n * sizeof(float), a.xT, size_t(n) * sizeof(float), size_t(n) * sizeof(float), B, kIn, st));
+    CKE(cudaMemcpy2DAsync(L.lat + n, size_t(2) * n * sizeof(float), a.xT, size_t(n) * sizeof(float), size_t(n) * sizeof(float), B, kIn, st));
+  }
 
   uint32_t mask_small = 0;    // transformer blocks whose token count allows self-attention replacement
   for (int i = 0; i < E.n_tf(); ++i) if (E.tf_tokens(i) <= a.self_max_tokens) mask_small |= 1u << i;
@@ -259,11 +270,11 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     cc.ctx_idx = cd.d_ctx; cc.time_idx = L.tidx + size_t(tindex) * maxS;
     cc.unit_s0 = cd.d_us0; cc.unit_s1 = cd.d_us1; cc.unit_img = cd.d_uimg; cc.n_units = cd.n_units;
     if (cd.p2p && p2p) {
-      if (a.self_lo <= ctrl_step && ctrl_step < a.self_hi) { cc.self_mask = mask_small; cc.self_q = cd.d_sq; cc.self_k = cd.d_sq; cc.self_v = nullptr; }
+      if (a.self_lo <= a.ctrl_step0 + ctrl_step && a.ctrl_step0 + ctrl_step < a.self_hi) { cc.self_mask = mask_small; cc.self_q = cd.d_sq; cc.self_k = cd.d_sq; cc.self_v = nullptr; }
       cc.mapper = L.mapper; cc.is_replace = L.is_replace; cc.replace_m = L.replace_m;
       cc.c_base = L.c_base + size_t(ctrl_step) * B * 80; cc.c_tar = L.c_tar + size_t(ctrl_step) * B * 80;
       if (blend && save) { cc.blend_acc = L.blend_acc; cc.blend_alpha = L.blend_alpha; }
-    } else if (cd.p2p && masa && masa_step >= a.masa_start_step) {
+    } else if (cd.p2p && masa && a.ctrl_step0 + masa_step >= a.masa_start_step) {
       uint32_t m = 0;
       for (int l = std::max(0, a.masa_start_layer); l < E.n_tf(); ++l) m |= 1u << l;
       cc.self_mask = m; cc.self_q = nullptr; cc.self_k = cd.d_sk; cc.self_v = cd.d_sk;
@@ -313,7 +324,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     // xt <- [x_orig_{t-1}, x_opt]
     CKE(cudaMemcpy2DAsync(xt, size_t(2) * n * sizeof(float), xprev, size_t(2) * n * sizeof(float), size_t(n) * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
     CKE(cudaMemcpy2DAsync(xt + n, size_t(2) * n * sizeof(float), xopt, size_t(n) * sizeof(float), size_t(n) * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
-    if (blend && (i + 1) > a.start_blend) {
+    if (blend && (a.ctrl_step0 + i + 1) > a.start_blend) {
       BlendParams bp;
       bp.acc = L.blend_acc; bp.has_blend = L.has_blend; bp.L = E.n_blend_layers(); bp.H = c.heads; bp.th = a.blend_th;
       bp.xt = xt; bp.C = c.in_ch; bp.hh = c.sample; bp.ww = c.sample;

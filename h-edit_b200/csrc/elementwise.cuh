@@ -15,11 +15,11 @@ struct GNStatsParams {
 };
 
 static __global__ void gn_stats_kernel(const GNStatsParams p) {
-  __shared__ float ssum[32], ssq[32];
+  // Deterministic: every thread parks the sums of its two channel pairs in shared memory and one thread per group adds
+  // them in channel order (no atomics), so the whole UNet is run-to-run bit-reproducible.
+  __shared__ float2 tsum[2][640];                      // [pair-in-quad][quad]  (C <= 2560)
   const int C = p.C1 + p.C2, quads = C >> 2, cpg = C / p.groups;
   const int s = blockIdx.y, ch = blockIdx.x, nch = gridDim.x;
-  if (threadIdx.x < 32) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
-  __syncthreads();
   const int p0 = ch * p.chunk, p1 = min(p.HW, p0 + p.chunk);
   for (int v = threadIdx.x; v < quads; v += blockDim.x) {
     const int c = 4 * v;
@@ -43,13 +43,19 @@ static __global__ void gn_stats_kernel(const GNStatsParams p) {
       a0 += t.x + t.y; b0 += t.x * t.x + t.y * t.y;
       a1 += t.z + t.w; b1 += t.z * t.z + t.w * t.w;
     }
-    const int g0 = c / cpg, g1 = (c + 2) / cpg;
-    if (g0 == g1) { atomicAdd(&ssum[g0], a0 + a1); atomicAdd(&ssq[g0], b0 + b1); }
-    else { atomicAdd(&ssum[g0], a0); atomicAdd(&ssq[g0], b0); atomicAdd(&ssum[g1], a1); atomicAdd(&ssq[g1], b1); }
+    tsum[0][v] = make_float2(a0, b0);
+    tsum[1][v] = make_float2(a1, b1);
   }
   __syncthreads();
-  if (threadIdx.x < p.groups)
-    p.partial[(size_t(s) * nch + ch) * p.groups + threadIdx.x] = make_float2(ssum[threadIdx.x], ssq[threadIdx.x]);
+  if (threadIdx.x < p.groups) {
+    const int g = threadIdx.x;
+    float su = 0.f, sq = 0.f;
+    for (int pr = g * (cpg >> 1); pr < (g + 1) * (cpg >> 1); ++pr) {      // channel pairs of this group, in order
+      const float2 t = tsum[pr & 1][pr >> 1];
+      su += t.x; sq += t.y;
+    }
+    p.partial[(size_t(s) * nch + ch) * p.groups + g] = make_float2(su, sq);
+  }
 }
 
 // Pass 2: finalise statistics (double combine), then y = [silu](x * a_c + b_c) -> bf16, optionally also the raw

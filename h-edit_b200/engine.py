@@ -105,30 +105,53 @@ class UNetEngine:
                 out[tag] = (float(ms), int(n))
         return out
 
+    def new_blend_state(self, B: int) -> torch.Tensor:
+        """Zeroed LocalBlend accumulator for single-step use (hedit_edit_args.blend_state)."""
+        n = self.lib.hedit_engine_blend_state_elems(self.handle, B)
+        return torch.zeros(max(n, 1), dtype=torch.float32, device=torch.device("cuda", self.device))
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- plain UNet call (use_controller=False)
-    def forward(self, x: torch.Tensor, timesteps, ctx: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, timesteps, ctx: torch.Tensor, ctx_index=None) -> torch.Tensor:
+        """eps = unet(x, t, ctx).  ctx is (S,77,D), or (n_ctx,77,D) with ctx_index[S] selecting a context per sample.
+        Batches larger than max_samples are processed in chunks."""
         dev = torch.device("cuda", self.device)
         x = x.to(dev, torch.float32).contiguous()
         S = x.shape[0]
         ts = np.ascontiguousarray(np.broadcast_to(np.asarray(timesteps, dtype=np.float32).reshape(-1), (S,)))
         ctx = ctx.to(torch.float32).contiguous()
         eps = torch.empty_like(x)
-        n = _lib.check(self.lib.hedit_unet_forward(self.handle, x.data_ptr(), ts.ctypes.data, ctx.data_ptr(), S, eps.data_ptr(), self._stream()),
-                       "unet forward")
-        self.last_stats = {"kernel_launches": n, "sample_forwards": S}
+        if ctx_index is None:
+            assert ctx.shape[0] == S
+            idx = np.arange(S, dtype=np.int32)
+        else:
+            idx = np.ascontiguousarray(np.asarray(ctx_index, dtype=np.int32))
+        launches = 0
+        for lo in range(0, S, self.max_samples):
+            hi = min(S, lo + self.max_samples)
+            if ctx_index is None:
+                c, ci = ctx[lo:hi].contiguous(), np.arange(hi - lo, dtype=np.int32)
+            else:
+                c, ci = ctx, np.ascontiguousarray(idx[lo:hi])
+            assert c.shape[0] <= self.max_contexts, "more contexts than the engine was created for"
+            tsc = np.ascontiguousarray(ts[lo:hi])
+            launches += _lib.check(self.lib.hedit_unet_forward_indexed(self.handle, x[lo:hi].data_ptr(), tsc.ctypes.data, c.data_ptr(), c.shape[0],
+                                                                       ci.ctypes.data, hi - lo, eps[lo:hi].data_ptr(), self._stream()), "unet forward")
+        self.last_stats = {"kernel_launches": launches, "sample_forwards": S}
         return eps
 
     # ---- the bridge-sampling loop
     def edit(self, xT: torch.Tensor, zs: torch.Tensor, ctx: torch.Tensor, timesteps: Sequence[int], coef: np.ndarray,
              cfg_scales: Sequence[float], plan: Optional[EditPlan], weight_reconstruction: float = 0.1, optimization_steps: int = 1,
-             explicit_form: bool = False, schedule: int = 1, trace: bool = False, variant: int = 0, masactrl=None, mos_pull: bool = True):
+             explicit_form: bool = False, schedule: int = 1, trace: bool = False, variant: int = 0, masactrl=None, mos_pull: bool = True,
+             xt_is_pair: bool = False, ctrl_step0: int = 0, blend_state: Optional[torch.Tensor] = None):
         """xT (B,C,h,w), zs (B,steps,C,h,w), ctx (1+2B,77,D): all on the SAME side (all host or all on this device).
         variant 1 = h_Edit_R_* (no attention control); masactrl = (start_step, start_layer) enables mutual self-attention.
         Returns (edited, recon[, trace]) on that side."""
         B, steps = xT.shape[0], zs.shape[1]
+        out_shape = (B,) + tuple(xT.shape[-3:])
         on_host = not xT.is_cuda
         assert zs.is_cuda == xT.is_cuda, "xT and zs must live on the same side"
         xT = xT.to(torch.float32).contiguous()
@@ -137,8 +160,8 @@ class UNetEngine:
         assert ctx.shape[0] == 1 + 2 * B and zs.shape[0] == B and len(timesteps) == steps + 1 and coef.shape == (steps, 6)
         mk = (lambda *s: torch.empty(*s, dtype=torch.float32, pin_memory=True)) if on_host else \
             (lambda *s: torch.empty(*s, dtype=torch.float32, device=xT.device))
-        edited, recon = mk(*xT.shape), mk(*xT.shape)
-        tr = mk(steps, B, 2, *xT.shape[1:]) if trace else None
+        edited, recon = mk(*out_shape), mk(*out_shape)
+        tr = mk(steps, B, 2, *out_shape[1:]) if trace else None
         ts = np.ascontiguousarray(np.asarray(timesteps, dtype=np.float32))
         coef = np.ascontiguousarray(coef, dtype=np.float32)
         a = _lib.EditArgsC()
@@ -149,6 +172,8 @@ class UNetEngine:
         a.variant = int(variant)
         a.mos_pull = int(mos_pull)
         a.masa_start_step, a.masa_start_layer = (int(masactrl[0]), int(masactrl[1])) if masactrl is not None else (0, -1)
+        a.xt_is_pair, a.ctrl_step0 = int(xt_is_pair), int(ctrl_step0)
+        a.blend_state = blend_state.data_ptr() if blend_state is not None else None
         keep = [ts, coef, xT, zs, ctx]
         if plan is not None:
             a.use_p2p = 1

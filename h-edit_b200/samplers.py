@@ -132,3 +132,44 @@ def h_Edit_masactrl_implicit(model, xT, eta=1.0, prompts="", cfg_scales=None, pr
                   masactrl=(ed.start_step - ed.cur_step, ed.start_layer), mos_pull=False)
     ed.cur_step += after_skip_steps * optimization_steps
     return out
+
+
+class HEditStepper:
+    """Per-timestep interface to the same native loop (`h_edit_step`): the body of the reference's `for i, t in enumerate(op)`
+    (p2p_h_edit.py:598-699) as one call, with the controller state (P2P step counter, LocalBlend word maps) carried here.
+    Uses the reference's UNet call pattern (schedule 0), since the exact-reuse schedule carries UNet outputs across steps."""
+
+    def __init__(self, model, prompt_pairs, cfg_scales, controllers=None, eta=1.0, weight_reconstruction=0.075, optimization_steps=1,
+                 after_skip_steps=None, is_ddim_inversion=False, explicit_form=False, engine: Optional[UNetEngine] = None):
+        self.model = model
+        self.B = len(prompt_pairs)
+        self.steps = after_skip_steps if after_skip_steps is not None else model.scheduler.num_inference_steps
+        self.eng = engine or get_engine(model, max_samples=5 * self.B)
+        dev = torch.device("cuda", self.eng.device)
+        ctx = [encode_text(model, [""])] + [encode_text(model, list(pp)) for pp in prompt_pairs]
+        self.ctx = torch.cat(ctx).float().to(dev)
+        self.ts, self.coef = step_tables(model.scheduler, self.steps, eta, is_ddim_inversion)
+        self.plan = compile_edit_plan(controllers, self.steps) if controllers is not None else None
+        self.cfg_scales, self.w_rec, self.K, self.explicit = cfg_scales, weight_reconstruction, optimization_steps, explicit_form
+        self.blend_state = self.eng.new_blend_state(self.B) if self.plan is not None and self.plan.has_blend.any() else None
+        self.i = 0
+
+    def step(self, xt: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+        """xt (B,2,C,h,w) = rows (x_orig, x_edit) at the current timestep; z (B,C,h,w) = zs[:, idx] of this step.
+        Returns xt at the previous timestep."""
+        import dataclasses
+        i = self.i
+        plan = None
+        if self.plan is not None:
+            plan = dataclasses.replace(self.plan, steps=1, c_base=self.plan.c_base[i:i + 2], c_tar=self.plan.c_tar[i:i + 2])
+        dev = self.ctx.device
+        ed, rc = self.eng.edit(xt.to(dev).contiguous(), z.to(dev)[:, None].contiguous(), self.ctx, self.ts[i:i + 2], self.coef[i:i + 1],
+                               self.cfg_scales, plan, self.w_rec, self.K, self.explicit, schedule=0, xt_is_pair=True, ctrl_step0=i,
+                               blend_state=self.blend_state)
+        self.i += 1
+        return torch.stack([rc, ed], dim=1)
+
+
+def h_edit_step(stepper: HEditStepper, xt: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    """One reverse-time bridge step [x_orig_t, x_edit_t] -> [x_orig_{t-1}, x_edit_{t-1}] (incl. P2P injection and LocalBlend)."""
+    return stepper.step(xt, z)

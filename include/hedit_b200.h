@@ -72,6 +72,11 @@ typedef struct hedit_edit_args {
    * blocks >= masa_start_layer, the edit samples attend to the K/V of their source samples.  masa_start_layer < 0: off */
   int32_t masa_start_step, masa_start_layer;
   int32_t mos_pull;          /* 1: apply the L1 reconstruction pull on MOS iterations k>0 (p2p_h_edit.py:670-686); 0: masactrl_h_edit.py */
+  /* ---- single-step use (h_edit_step): run `steps` timesteps of a longer schedule and carry the controller state outside */
+  int32_t xt_is_pair;        /* 1: xT is [B][2][C][h][w] = (x_orig, x_edit) rows of an edit in progress (requires schedule 0) */
+  int32_t ctrl_step0;        /* controller step (AttentionControl.cur_step / LocalBlend.counter) before the first executed timestep;
+                                c_base / c_tar row 0 corresponds to controller step ctrl_step0 */
+  float* blend_state;        /* device [B][2][n_blend_layers][heads][256] accumulated word maps carried across calls, or NULL */
   /* ---- outputs */
   float* edited;             /* [B][C][h][w] */
   float* recon;              /* [B][C][h][w] */
@@ -91,6 +96,8 @@ void hedit_engine_destroy(hedit_engine* e);
 int hedit_engine_load_tensor(hedit_engine* e, const char* name, const float* data, const int64_t* dims, int ndim);
 int hedit_engine_finalize(hedit_engine* e);
 double hedit_engine_flops_per_sample(hedit_engine* e);
+/* number of floats of hedit_edit_args.blend_state for a batch of B images */
+int hedit_engine_blend_state_elems(hedit_engine* e, int B);
 /* "fp16" (default) or "bf16": the 16-bit tensor-core operand type this build uses for activations/weights */
 const char* hedit_operand_dtype(void);
 /* enumerate the state-dict tensors the engine expects (diffusers parameter names): returns ndim, fills dims4 */
@@ -103,6 +110,10 @@ int hedit_engine_profile_forward(hedit_engine* e, int S, int reps, char* out, in
  * (text-guided/inversion/p2p_h_edit.py:613).  x/eps: [S][C][h][w] device fp32; timesteps: [S] host; ctx:
  * [S][ctx_len][cross_dim] host or device.  stream: cudaStream_t or NULL. */
 int hedit_unet_forward(hedit_engine* e, const float* x, const float* timesteps, const float* ctx, int S, float* eps, void* stream);
+/* same, with n_ctx distinct contexts shared by the samples through ctx_idx[S] (host): the inversion callables
+ * (text-guided/inversion/ddpm_inversion.py:130-132, ddim_inversion.py:31-52) evaluate many timesteps against two prompts */
+int hedit_unet_forward_indexed(hedit_engine* e, const float* x, const float* timesteps, const float* ctx, int n_ctx, const int32_t* ctx_idx,
+                               int S, float* eps, void* stream);
 
 /* the whole bridge-sampling loop for a batch of images */
 int hedit_edit_p2p(hedit_engine* e, hedit_edit_args* args, void* stream);

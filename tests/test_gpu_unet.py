@@ -169,3 +169,71 @@ def test_sampler_variants(name):
     if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", name + ".pt")):
         pytest.skip("golden missing")
     _run_variant(name)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# inversion callables on the native engine
+def test_ddpm_inversion_matches_reference_golden():
+    """inversion_forward_process_ddpm: same global-RNG draws as the reference (torch.manual_seed(0)), all 2T noise predictions in
+    one batched launch; zs / x_T against the tensors the reference produced for tiny_refine_noblend."""
+    _fp32()
+    g = load_golden("tiny_refine_noblend")
+    meta = g["meta"]
+    model = OraclePipeline(cfg_from_meta(meta), seed=0)
+    model.scheduler.set_timesteps(meta["T"])
+    torch.manual_seed(0)
+    xt, zs, xts, _ = hedit_b200.inversion_forward_process_ddpm(model, g["w0"], etas=1.0, prog_bar=False, prompt=meta["prompts"][0],
+                                                                 cfg_scale_src=1.0, num_inference_steps=meta["T"])
+    r_x, _ = rel_err(xts[meta["T"]], g["xT"])
+    r_z, m_z = rel_err(zs, g["zs"])
+    print(f"ddpm inversion: xT rel {r_x:.3e} | zs rel {r_z:.3e} max {m_z:.3e}")
+    assert r_x < 1e-6            # x_T is a pure function of w0 and the RNG stream
+    assert r_z < 2e-2            # z = (x_{t-1} - mu(eps))/sigma amplifies the UNet's operand rounding by 1/sigma
+
+
+def test_ddim_inversion_matches_reference_golden():
+    import os as _os
+    if not _os.path.exists(_os.path.join(_os.path.dirname(__file__), "golden", "tiny_ddim_inversion.pt")):
+        pytest.skip("golden missing")
+    _fp32()
+    g = load_golden("tiny_ddim_inversion")
+    meta = g["meta"]
+    model = OraclePipeline(cfg_from_meta(meta), seed=0, steps_offset=0)
+    model.scheduler.set_timesteps(meta["T"])
+    latent, zs, latents = hedit_b200.ddim_inversion(model, g["w0"], meta["prompt"], meta["cfg_scale"])
+    r_l, _ = rel_err(torch.cat(latents), g["latents"])
+    r_z, m_z = rel_err(zs, g["zs"])
+    print(f"ddim inversion: latents rel {r_l:.3e} | zs abs-max err {m_z:.3e} (|zs| max {g['zs'].abs().max().item():.3e})")
+    assert r_l < TOL_LOOP
+    assert m_z < 2e-2 * max(1.0, g["latents"].abs().max().item())      # zs are round-off residuals of the deterministic trajectory
+
+
+def test_h_edit_step_equals_loop():
+    """Stepping the edit one timestep at a time (h_edit_step, controller state carried by HEditStepper) reproduces the
+    whole-loop call with the same UNet call pattern."""
+    _fp32()
+    g = load_golden("tiny_refine_blend")
+    meta = g["meta"]
+    model = OraclePipeline(cfg_from_meta(meta), seed=0)
+    T = meta["T"]
+    model.scheduler.set_timesteps(T)
+    eng = UNetEngine.from_unet(model.unet, max_samples=5, max_contexts=4)
+    bw = meta["blend_words"]
+    mk = lambda: hedit_b200.make_controller(meta["prompts"], False, meta["xa"], meta["sa"], blend_word=((bw[0],), (bw[1],)),
+                                            equilizer_params={"words": (bw[1],), "values": (2.0,)}, num_steps=T, tokenizer=model.tokenizer)
+    xT = g["xT"].reshape(1, *g["xT"].shape[-3:]).cuda()
+    zs = g["zs"].reshape(1, *g["zs"].shape).cuda()
+    ed_loop, rc_loop = hedit_b200.h_edit_p2p_batch(model, xT, zs, [meta["prompts"]], meta["cfg_scales"], [mk()], eta=1.0,
+                                                   weight_reconstruction=0.1, after_skip_steps=T, schedule=0, engine=eng)
+    st = hedit_b200.HEditStepper(model, [meta["prompts"]], meta["cfg_scales"], [mk()], eta=1.0, weight_reconstruction=0.1,
+                                 after_skip_steps=T, engine=eng)
+    xt = torch.stack([xT, xT], dim=1)
+    for i in range(T):
+        xt = hedit_b200.h_edit_step(st, xt, zs[:, T - 1 - i])
+    r_ed, m_ed = rel_err(xt[:, 1], ed_loop)
+    r_rc, m_rc = rel_err(xt[:, 0], rc_loop)
+    print(f"h_edit_step vs loop: edited rel {r_ed:.3e} max {m_ed:.3e} | recon rel {r_rc:.3e} max {m_rc:.3e}")
+    # identical kernels, identical inputs, no atomics anywhere in the path -> bit-identical
+    assert m_ed == 0.0 and m_rc == 0.0
+    r_g, _ = rel_err(xt[:, 1].cpu(), g["edited"])
+    assert r_g < TOL_LOOP

@@ -166,12 +166,32 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
     }
 
 
+def run_ddim_inversion(ref, name="tiny_ddim_inversion", T=6):
+    """Reference ddim_inversion (inversion/ddim_inversion.py:55) with the eta = 0 scheduler (steps_offset 0, main_p2p.py:139-141)."""
+    import importlib
+    cfg = UNetConfig.tiny(sample_size=64)
+    model = OraclePipeline(cfg, seed=0, steps_offset=0)
+    model.scheduler.set_timesteps(T)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    w0 = torch.randn(1, cfg.in_channels, cfg.sample_size, cfg.sample_size, generator=g) * 0.18215 * 5
+    di = importlib.import_module("inversion.ddim_inversion")
+    latent, zs, latents = di.ddim_inversion(model, w0, PROMPTS[0], 1.0)
+    return {"meta": dict(name=name, T=T, prompt=PROMPTS[0], cfg_scale=1.0, steps_offset=0,
+                         unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
+                                   cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim)),
+            "w0": w0, "latent": latent.clone(), "zs": zs.clone(), "latents": torch.cat(latents).clone()}
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "variants", "all"])
+    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "variants", "inversion", "all"])
     args = ap.parse_args()
     ref = load_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    if args.config in ("inversion", "all"):
+        out = run_ddim_inversion(ref)
+        torch.save(out, os.path.join(ROOT, "tests", "golden", "tiny_ddim_inversion.pt"))
+        print("tiny_ddim_inversion |zs|", out["zs"].abs().mean().item(), flush=True)
     if args.config in ("variants", "all"):
         for name, (cfg, T, K, mode) in VARIANTS.items():
             out = run_variant(ref, name, cfg, T, K, mode)
@@ -179,7 +199,7 @@ def main():
             torch.save(out, path)
             print(name, "->", path, "|edited| %.4f" % out["edited"].abs().mean().item(), flush=True)
     for name, (cfg, T, K, rep, blend) in CASES.items():
-        if args.config == "variants" or (args.config != "all" and not name.startswith(args.config)):
+        if args.config in ("variants", "inversion") or (args.config != "all" and not name.startswith(args.config)):
             continue
         out = run_case(ref, name, cfg, T, K, rep, blend)
         path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
