@@ -279,45 +279,49 @@ __global__ void __launch_bounds__(192) self_attn_kernel(const __grid_constant__ 
 // tiles.  S_t(j+1) is issued as soon as warpgroup t has copied S_t(j) to registers (s_free), so the score MMA is off
 // the critical path; P.V(j) completion (pv_done) gates only the reuse of the P tile and the lazy O rescale.
 // TMEM columns: S_t at t*BKV, O_t at 2*BKV + t*DCH*64.
-template <int DCH>
+template <int DCH, int NT_, int BKV_>
 struct SelfAttn2Cfg {
-  static constexpr int BKV = (DCH == 1) ? 128 : 64;
+  static constexpr int NT = NT_;                                 // query tiles (= softmax warpgroups) per CTA
+  static constexpr int BKV = BKV_;
   static constexpr int KSTAGES = (DCH == 3) ? 2 : 3;
   static constexpr int PCH = BKV / 64;
   static constexpr uint32_t QT_BYTES = DCH * 128 * 128;          // one Q tile
   static constexpr uint32_t KV_BYTES = DCH * BKV * 128;          // one K (or V) block
   static constexpr uint32_t PT_BYTES = PCH * 128 * 128;          // one P tile
-  static constexpr uint32_t SMEM_BYTES = 2 * QT_BYTES + 2 * KSTAGES * KV_BYTES + 2 * PT_BYTES + 256;
-  static constexpr uint32_t TMEM_COLS = 512;
-  static constexpr uint32_t O_COL0 = 2 * BKV, O_STRIDE = DCH * 64;
-  static constexpr int THREADS = 320;
-  static_assert(O_COL0 + 2 * O_STRIDE <= 512, "TMEM budget");
+  static constexpr uint32_t SMEM_BYTES = NT * QT_BYTES + 2 * KSTAGES * KV_BYTES + NT * PT_BYTES + 512;
+  static constexpr uint32_t O_COL0 = NT * BKV, O_STRIDE = DCH * 64;
+  static constexpr uint32_t TMEM_COLS = (O_COL0 + NT * O_STRIDE <= 256) ? 256 : 512;
+  static constexpr int MIN_CTAS = (TMEM_COLS == 256 && NT * QT_BYTES + 2 * KSTAGES * KV_BYTES + NT * PT_BYTES + 512 <= 114 * 1024) ? 2 : 1;
+  static constexpr int THREADS = 128 * NT + 64;
+  static_assert(O_COL0 + NT * O_STRIDE <= 512, "TMEM budget");
 };
 
-template <int DCH>
-static __global__ void __launch_bounds__(320, 1) self_attn2_kernel(const __grid_constant__ AttnParams p) {
-  using Cfg = SelfAttn2Cfg<DCH>;
-  constexpr int BKV = Cfg::BKV, KSTAGES = Cfg::KSTAGES;
+template <int DCH, int NT_, int BKV_>
+static __global__ void __launch_bounds__(SelfAttn2Cfg<DCH, NT_, BKV_>::THREADS, SelfAttn2Cfg<DCH, NT_, BKV_>::MIN_CTAS)
+self_attn2_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = SelfAttn2Cfg<DCH, NT_, BKV_>;
+  constexpr int BKV = Cfg::BKV, KSTAGES = Cfg::KSTAGES, NT = Cfg::NT;
+  constexpr int MMA_WARP = 4 * NT, TMA_WARP = 4 * NT + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sQ = smem;                               // [2 tiles][DCH][128 rows][128 B]
-  uint8_t* sK = sQ + 2 * Cfg::QT_BYTES;             // [KSTAGES][DCH][BKV rows][128 B]
+  uint8_t* sQ = smem;                               // [NT tiles][DCH][128 rows][128 B]
+  uint8_t* sK = sQ + NT * Cfg::QT_BYTES;             // [KSTAGES][DCH][BKV rows][128 B]
   uint8_t* sV = sK + KSTAGES * Cfg::KV_BYTES;
-  uint8_t* sP = sV + KSTAGES * Cfg::KV_BYTES;       // [2 tiles][PCH][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::PT_BYTES);
+  uint8_t* sP = sV + KSTAGES * Cfg::KV_BYTES;       // [NT tiles][PCH][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NT * Cfg::PT_BYTES);
   uint64_t* q_full = bars;                  // 1
   uint64_t* k_full = bars + 1;              // KSTAGES
   uint64_t* v_full = k_full + KSTAGES;
   uint64_t* kv_empty = v_full + KSTAGES;
-  uint64_t* s_full = kv_empty + KSTAGES;    // 2
-  uint64_t* p_full = s_full + 2;            // 2 (4 arrivals each)
-  uint64_t* pv_done = p_full + 2;           // 2: P.V of block j has completed (P smem reusable, O stable)
-  uint64_t* s_free = pv_done + 2;           // 2 (4 arrivals each): S tile has been copied to registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  uint64_t* s_full = kv_empty + KSTAGES;    // NT
+  uint64_t* p_full = s_full + NT;           // NT (4 arrivals each)
+  uint64_t* pv_done = p_full + NT;          // NT: P.V of block j has completed (P smem reusable, O stable)
+  uint64_t* s_free = pv_done + NT;          // NT (4 arrivals each): S tile has been copied to registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + NT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, h = blockIdx.y, s = blockIdx.z;
+  const int q0 = blockIdx.x * (128 * NT), h = blockIdx.y, s = blockIdx.z;
   const int sq = p.q_idx ? p.q_idx[s] : s;
   const int sk = p.k_idx ? p.k_idx[s] : s;
   const int sv = p.v_idx ? p.v_idx[s] : s;
@@ -328,21 +332,21 @@ static __global__ void __launch_bounds__(320, 1) self_attn2_kernel(const __grid_
     tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
     for (int i = 0; i < KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&s_free[i], 4); }
+    for (int i = 0; i < NT; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&s_free[i], 4); }
     fence_mbar_init();
   }
-  if (warp == 8) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 9) {
+  if (warp == TMA_WARP) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * Cfg::QT_BYTES);
+      mbar_expect_tx(q_full, NT * Cfg::QT_BYTES);
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
+      for (int t = 0; t < NT; ++t)
 #pragma unroll
         for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + t * Cfg::QT_BYTES + c * 16384, &p.tmQ, q_full, c * 64, h, q0 + t * 128, sq);
       int st = 0; uint32_t ph = 0;
@@ -357,7 +361,7 @@ static __global__ void __launch_bounds__(320, 1) self_attn2_kernel(const __grid_
         if (++st == KSTAGES) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------ MMA issuer: the whole warp runs the (uniform) control flow,
     // one elected lane issues tcgen05.mma / commit, so descriptors live in uniform registers.
     const uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
@@ -389,8 +393,14 @@ static __global__ void __launch_bounds__(320, 1) self_attn2_kernel(const __grid_
     mbar_wait(q_full, 0);
     mbar_wait(&k_full[0], 0);
     tc_fence_after();
-    if (elect_one()) { issue_s(0, 0); issue_s(1, 0); }
+    if (elect_one()) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) issue_s(t, 0);
+    }
     __syncwarp();
+    // Fixed round-robin over the query tiles with blocking (hardware-suspended) waits.  An event-driven polling variant
+    // (mbarrier.test_wait over all tiles) was measured 20 % slower: the MMA warp's reaction latency matters more than
+    // head-of-line blocking.
     int st = 0; uint32_t ph = 0;
     for (int j = 0; j < nblk; ++j) {
       int st1 = st + 1; uint32_t ph1 = ph;
@@ -399,14 +409,14 @@ static __global__ void __launch_bounds__(320, 1) self_attn2_kernel(const __grid_
       if (more) mbar_wait(&k_full[st1], ph1);
       mbar_wait(&v_full[st], ph);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (more) {
+      for (int t = 0; t < NT; ++t) {
+        if (more) {                                   // S_t(j+1) as soon as warpgroup t has pulled S_t(j) into registers
           mbar_wait(&s_free[t], j & 1);
           tc_fence_after();
           if (elect_one()) issue_s(t, st1);
           __syncwarp();
         }
-        mbar_wait(&p_full[t], j & 1);
+        mbar_wait(&p_full[t], j & 1);                 // P_t(j).V(j) once the probabilities are in shared memory
         tc_fence_after();
         if (elect_one()) issue_pv(t, st, j != 0);
         __syncwarp();
@@ -416,7 +426,7 @@ static __global__ void __launch_bounds__(320, 1) self_attn2_kernel(const __grid_
       st = st1; ph = ph1;
     }
   } else {
-    // ------------------------------------------------------------ softmax warpgroups (warps 0-3: tile A, 4-7: tile B)
+    // ------------------------------------------------------------ softmax warpgroups (warps 4t..4t+3 own query tile t)
     const int tile = warp >> 2;
     const int r = threadIdx.x & 127;
     const uint32_t lane_sel = uint32_t((warp & 3) * 32) << 16;
@@ -517,7 +527,7 @@ static __global__ void __launch_bounds__(320, 1) self_attn2_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+  if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ======================================================================================================= cross

@@ -362,20 +362,30 @@ static cudaError_t launch_self_t(const AttnParams& a, int S, cudaStream_t st) {
   self_attn_kernel<DCH, BKV><<<grid, 192, SelfAttnCfg<DCH, BKV>::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
-template <int DCH>
+template <int DCH, int NT, int BKV>
 static cudaError_t launch_self2_t(const AttnParams& a, int S, cudaStream_t st) {
+  using Cfg = SelfAttn2Cfg<DCH, NT, BKV>;
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(self_attn2_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SelfAttn2Cfg<DCH>::SMEM_BYTES); set = true; }
-  dim3 grid((a.Nq + 255) / 256, a.H, S);
-  self_attn2_kernel<DCH><<<grid, SelfAttn2Cfg<DCH>::THREADS, SelfAttn2Cfg<DCH>::SMEM_BYTES, st>>>(a);
+  if (!set) { cudaFuncSetAttribute(self_attn2_kernel<DCH, NT, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
+  constexpr int rows = 128 * NT;
+  dim3 grid((a.Nq + rows - 1) / rows, a.H, S);
+  self_attn2_kernel<DCH, NT, BKV><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
+// tuning switch HEDIT_ATTN_CFG for head dims <= 64 (measured on B200, N=4096, d=40, cycles per 128x128 block):
+//   1 (default) = 2 tiles x 64-column blocks, 2 CTAs/SM: 1543;  0 = 2 tiles x 128-column blocks, 1 CTA/SM: 1645;
+//   2 = 4 tiles x 64-column blocks, 1 CTA/SM: 2220
+static int attn_cfg() { static const int v = getenv("HEDIT_ATTN_CFG") ? atoi(getenv("HEDIT_ATTN_CFG")) : 1; return v; }
 cudaError_t launch_self_attn(const AttnParams& a, int dch, int S, cudaStream_t st) {
-  const int bkv2 = (dch == 1) ? 128 : 64;
-  if (a.Nq >= 256 && a.Nkv % bkv2 == 0) {      // two query tiles per CTA, ping-pong softmax warpgroups
-    if (dch == 1) return launch_self2_t<1>(a, S, st);
-    if (dch == 2) return launch_self2_t<2>(a, S, st);
-    return launch_self2_t<3>(a, S, st);
+  const int bkv2 = (dch == 1 && attn_cfg() == 0) ? 128 : 64;
+  if (a.Nq >= 256 && a.Nkv % bkv2 == 0) {      // several query tiles per CTA
+    if (dch == 1) {
+      if (attn_cfg() == 1) return launch_self2_t<1, 2, 64>(a, S, st);
+      if (attn_cfg() == 2) return launch_self2_t<1, 4, 64>(a, S, st);
+      return launch_self2_t<1, 2, 128>(a, S, st);
+    }
+    if (dch == 2) return launch_self2_t<2, 2, 64>(a, S, st);
+    return launch_self2_t<3, 2, 64>(a, S, st);
   }
   if (dch == 1) return launch_self_t<1, 128>(a, S, st);
   if (dch == 2) return launch_self_t<2, 128>(a, S, st);
@@ -414,9 +424,10 @@ cudaError_t launch_cross_attn(const AttnParams& a, int dch, int units, cudaStrea
   return launch_cross_t<3>(a, units, st);
 }
 static int dch_for(int d) { return d <= 64 ? 1 : (d <= 128 ? 2 : 3); }
+static int attn_cfg();
 // K/V rows per TMA box: must match the kernel variant launch_self_attn() picks for the same (d, Nq, Nkv)
 int self_attn_bkv(int d, int Nq, int Nkv) {
-  const int bkv2 = (d <= 64) ? 128 : 64;
+  const int bkv2 = (d <= 64 && attn_cfg() == 0) ? 128 : 64;
   if (Nq >= 256 && Nkv % bkv2 == 0) return bkv2;
   return d <= 128 ? 128 : 64;
 }

@@ -63,6 +63,18 @@ HEDIT_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (for event-driven issue loops)
+HEDIT_DEVICE bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded spin: a protocol bug traps (the launch reports an error) instead of hanging the GPU box.
 HEDIT_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
