@@ -198,7 +198,14 @@ int hedit_edit_p2p(hedit_engine* h, hedit_edit_args* args, void* stream) {
 
 // ------------------------------------------------------------------------------------------------ single operators
 static int pick_bn_op(int M, int N) {
-  auto cost = [&](int bn) { const long tiles = long((M + 127) / 128) * ((N + bn - 1) / bn); return double((tiles + 147) / 148) * bn; };
+  static const int force = getenv("HEDIT_GEMM_BN") ? atoi(getenv("HEDIT_GEMM_BN")) : 0;     // tuning switch
+  if (force == 160 || force == 256) return force;
+  // Measured on B200: one 128 x BN x 16 MMA step costs ~ BN/2 + 90 cycles (operand fetch + TMA refill share the SM's shared-
+  // memory bandwidth), so wide tiles win unless they add a wave or mostly-empty columns.
+  auto cost = [&](int bn) {
+    const long tiles = long((M + 127) / 128) * ((N + bn - 1) / bn);
+    return double((tiles + 147) / 148) * (bn / 2 + 90);
+  };
   return cost(256) < cost(160) ? 256 : 160;
 }
 
@@ -208,7 +215,7 @@ int hedit_op_linear(const void* A, const void* W, const float* bias, const float
   const int bn = pick_bn_op(M, N);
   g.M = M; g.N = N; g.num_kb = (K + 63) / 64; g.a_mode = A_LINEAR;
   uint64_t da[2] = {uint64_t(K), uint64_t(M)}, sa[1] = {uint64_t(K) * 2}; uint32_t ba[2] = {64, 128};
-  uint64_t db[2] = {uint64_t(K), uint64_t(N)}, sb[1] = {uint64_t(K) * 2}; uint32_t bb[2] = {64, uint32_t(bn)};
+  uint64_t db[2] = {uint64_t(K), uint64_t(N)}, sb[1] = {uint64_t(K) * 2}; uint32_t bb[2] = {64, uint32_t(bn / 2)};
   if (!make_tmap_bf16(&g.tmA, A, 2, da, sa, ba) || !make_tmap_bf16(&g.tmB, W, 2, db, sb, bb)) return fail("tensor map encode failed");
   g.ep.bias = bias; g.ep.residual = residual; g.ep.ldr = N; g.ep.out_f32 = out_f32; g.ep.ldo = N;
   g.ep.out_bf16 = reinterpret_cast<op_t*>(out_bf16); g.ep.ldob = N; g.ep.rows_per_group = 1;
@@ -239,7 +246,7 @@ int hedit_op_conv3x3(const void* x, const void* w, const float* bias, float* out
     uint32_t b[5] = {64, uint32_t(Wd), 1, uint32_t(BH), uint32_t(BS)};
     ok = make_tmap_bf16(&g.tmA, x, 5, d, s, b);
   }
-  uint64_t db[2] = {uint64_t(9 * C), uint64_t(Cout)}, sb[1] = {uint64_t(9 * C) * 2}; uint32_t bb[2] = {64, uint32_t(bn)};
+  uint64_t db[2] = {uint64_t(9 * C), uint64_t(Cout)}, sb[1] = {uint64_t(9 * C) * 2}; uint32_t bb[2] = {64, uint32_t(bn / 2)};
   if (!ok || !make_tmap_bf16(&g.tmB, w, 2, db, sb, bb)) return fail("tensor map encode failed");
   g.ep.bias = bias; g.ep.out_f32 = out; g.ep.ldo = Cout; g.ep.rows_per_group = 1;
   cudaError_t e = launch_gemm(g, bn, reinterpret_cast<cudaStream_t>(stream));
@@ -301,7 +308,7 @@ int hedit_op_group_norm(const float* x, const float* gamma, const float* beta, v
   GNStatsParams sp{x, nullptr, C, 0, HW, groups, chunk, partial};
   gn_stats_kernel<<<dim3(nch, S), std::min(640, ((C / 4 + 31) / 32) * 32), 0, st>>>(sp);
   GNApplyParams ap{x, nullptr, C, 0, HW, groups, 16, nch, partial, gamma, beta, eps, silu, reinterpret_cast<op_t*>(out), nullptr};
-  gn_apply_kernel<<<dim3((HW + 15) / 16, S), std::max(256, std::min(640, ((C / 4 + 31) / 32) * 32)), 0, st>>>(ap);
+  gn_apply_kernel<<<dim3((HW + 15) / 16, S), std::max(256, (C / 4) * std::max(1, (256 + C / 4 - 1) / (C / 4))), 0, st>>>(ap);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(partial);
   if (e != cudaSuccess) return cuda_fail(e, "group norm");

@@ -100,9 +100,12 @@ static __global__ void gn_apply_kernel(const GNApplyParams p) {
     }
   }
   __syncthreads();
-  // thread <-> fixed channel quad: affine coefficients live in registers, pixels are streamed (coalesced across threads)
+  // thread <-> (fixed channel quad, pixel sub-lane): affine coefficients live in registers, pixels are streamed with all
+  // threads busy for every channel count (blockDim = quads * nsub, nsub pixel sub-lanes)
   const int p0 = blockIdx.x * p.chunk, p1 = min(p.HW, p0 + p.chunk);
-  for (int v = threadIdx.x; v < quads; v += blockDim.x) {
+  const int nsub = max(1, int(blockDim.x) / quads);
+  const int v = threadIdx.x % quads, sub = threadIdx.x / quads;
+  if (sub < nsub) {
     const int c = 4 * v;
     float ca[4], cb[4];
 #pragma unroll
@@ -116,19 +119,20 @@ static __global__ void gn_apply_kernel(const GNApplyParams p) {
     else { base = p.x2 + size_t(s) * p.HW * p.C2 + (c - p.C1); ld = p.C2; }
     op_t* o = p.out + size_t(s) * p.HW * C + c;
     op_t* ro = p.raw_out ? p.raw_out + size_t(s) * p.HW * C + c : nullptr;
-    for (int px = p0; px < p1; px += 4) {
+    for (int px = p0 + sub; px < p1; px += 4 * nsub) {
       float4 t[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (px + u < p1) t[u] = *reinterpret_cast<const float4*>(base + size_t(px + u) * ld);
+        if (px + u * nsub < p1) t[u] = *reinterpret_cast<const float4*>(base + size_t(px + u * nsub) * ld);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (px + u < p1) {
+        if (px + u * nsub < p1) {
+          const int q = px + u * nsub;
           float y0 = fmaf(t[u].x, ca[0], cb[0]), y1 = fmaf(t[u].y, ca[1], cb[1]);
           float y2 = fmaf(t[u].z, ca[2], cb[2]), y3 = fmaf(t[u].w, ca[3], cb[3]);
           if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-          *reinterpret_cast<uint2*>(o + size_t(px + u) * C) = make_uint2(pack_op2(y0, y1), pack_op2(y2, y3));
-          if (ro) *reinterpret_cast<uint2*>(ro + size_t(px + u) * C) = make_uint2(pack_op2(t[u].x, t[u].y), pack_op2(t[u].z, t[u].w));
+          *reinterpret_cast<uint2*>(o + size_t(q) * C) = make_uint2(pack_op2(y0, y1), pack_op2(y2, y3));
+          if (ro) *reinterpret_cast<uint2*>(ro + size_t(q) * C) = make_uint2(pack_op2(t[u].x, t[u].y), pack_op2(t[u].z, t[u].w));
         }
     }
   }
@@ -209,12 +213,13 @@ static __global__ void upsample2x_bf16_kernel(const float* __restrict__ x, op_t*
 
 // ------------------------------------------------------------------------------------------------ conv_in / conv_out
 // conv_in: 3x3, Cin=4 (NCHW fp32 latent) -> C0 channels (NHWC fp32).  fp32 CUDA-core math (47 MMAC / sample, exact).
-// grid (ceil(H/RB), S): each CTA stages the [36][C0] weights once and produces RB output rows.
-constexpr int kConvInRows = 8;
+// grid (H / RB, S).  Each thread owns 4 consecutive output channels (weights as float4) and 4 consecutive pixels, so one
+// weight load + a 6-wide sliding input window feed 48 FMAs (the naive mapping is shared-memory-load bound).
+constexpr int kConvInRows = 4;
 static __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                float* __restrict__ y, int H, int W, int C0) {
   extern __shared__ float sm[];
-  float* sw = sm;                       // [36][C0] (transposed for conflict-free reads)
+  float* sw = sm;                       // [36][C0] (tap-major: consecutive threads read consecutive float4)
   float* sx = sm + 36 * C0;             // [4][RB+2][W+2]
   const int y0 = blockIdx.x * kConvInRows, s = blockIdx.y;
   const int rows = min(kConvInRows, H - y0), PW = W + 2, PR = kConvInRows + 2;
@@ -225,16 +230,31 @@ static __global__ void conv_in_kernel(const float* __restrict__ x, const float* 
     sx[i] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? x[((size_t(s) * 4 + ci) * H + yy) * W + xx] : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < rows * W * C0; i += blockDim.x) {
-    const int co = i % C0, xo = (i / C0) % W, r = i / (C0 * W);
-    float acc = bias[co];
+  const int cq = C0 >> 2, xq = (W + 3) >> 2;
+  for (int i = threadIdx.x; i < rows * xq * cq; i += blockDim.x) {
+    const int c4 = (i % cq) << 2, xo = ((i / cq) % xq) << 2, r = i / (cq * xq);
+    const float4 bq = *reinterpret_cast<const float4*>(bias + c4);
+    float4 acc[4] = {bq, bq, bq, bq};
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci)
 #pragma unroll
-      for (int dr = 0; dr < 3; ++dr)
+      for (int dr = 0; dr < 3; ++dr) {
+        float in[6];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) acc = fmaf(sx[(ci * PR + r + dr) * PW + xo + k], sw[(ci * 9 + dr * 3 + k) * C0 + co], acc);
-    y[((size_t(s) * H + y0 + r) * W + xo) * C0 + co] = acc;
+        for (int k = 0; k < 6; ++k) in[k] = sx[(ci * PR + r + dr) * PW + min(xo + k, PW - 1)];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4 wq = *reinterpret_cast<const float4*>(sw + (ci * 9 + dr * 3 + k) * C0 + c4);
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            acc[px].x = fmaf(in[px + k], wq.x, acc[px].x); acc[px].y = fmaf(in[px + k], wq.y, acc[px].y);
+            acc[px].z = fmaf(in[px + k], wq.z, acc[px].z); acc[px].w = fmaf(in[px + k], wq.w, acc[px].w);
+          }
+        }
+      }
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+      if (xo + px < W) *reinterpret_cast<float4*>(y + ((size_t(s) * H + y0 + r) * W + xo + px) * C0 + c4) = acc[px];
   }
 }
 

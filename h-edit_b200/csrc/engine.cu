@@ -272,9 +272,13 @@ int Engine::finalize_weights(std::string* missing) {
 
 // ------------------------------------------------------------------------------------------------ GEMM descriptors
 static int pick_bn(int M, int N) {
+  static const int force = getenv("HEDIT_GEMM_BN") ? atoi(getenv("HEDIT_GEMM_BN")) : 0;     // tuning switch
+  if (force == 160 || force == 256) return force;
+  // Measured on B200: one 128 x BN x 16 MMA step costs ~ BN/2 + 90 cycles (operand fetch + TMA refill share the SM's shared-
+  // memory bandwidth), so wide tiles win unless they add a wave or mostly-empty columns.
   auto cost = [&](int bn) {
     const long tiles = long((M + 127) / 128) * ((N + bn - 1) / bn);
-    return double((tiles + 147) / 148) * bn;
+    return double((tiles + 147) / 148) * (bn / 2 + 90);
   };
   return cost(256) < cost(160) ? 256 : 160;
 }
@@ -312,7 +316,7 @@ static bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode
     }
   }
   if (!ok) { err = "tensor map (A) encode failed"; return false; }
-  uint64_t dimsB[2] = {uint64_t(Ktot), uint64_t(N)}; uint64_t strB[1] = {uint64_t(Ktot) * 2}; uint32_t boxB[2] = {64, uint32_t(bn)};
+  uint64_t dimsB[2] = {uint64_t(Ktot), uint64_t(N)}; uint64_t strB[1] = {uint64_t(Ktot) * 2}; uint32_t boxB[2] = {64, uint32_t(bn / 2)};
   if (!make_tmap_bf16(&g.tmB, Wt, 2, dimsB, strB, boxB)) { err = "tensor map (B) encode failed"; return false; }
   return true;
 }
@@ -323,18 +327,33 @@ static int num_sms() {
   return g_num_sms;
 }
 
-cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st) {
+// tuning switch HEDIT_GEMM_CLUSTER=1 enables the cta_group::2 (CTA pair) variant
+// (default off: measured equal to the single-CTA kernel on B200 for every UNet shape -- the kernel is not bound by W traffic)
+static bool gemm_cluster() { static const bool v = getenv("HEDIT_GEMM_CLUSTER") && atoi(getenv("HEDIT_GEMM_CLUSTER")) != 0; return v; }
+
+template <int BN, bool CL>
+static cudaError_t launch_gemm_t(const GemmParams& g, cudaStream_t st) {
   static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<160>::SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::SMEM_BYTES);
-    attr_set = true;
+  if (!attr_set) { cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, CL>::SMEM_BYTES); attr_set = true; }
+  const int m_tiles = (g.M + 127) / 128, n_tiles = (g.N + BN - 1) / BN;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = GemmCfg<BN, CL>::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (CL) {
+    const int pairs = ((m_tiles + 1) / 2) * n_tiles;
+    cfg.gridDim = dim3(2 * std::min(pairs, num_sms() / 2));
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(std::min(m_tiles * n_tiles, num_sms()));
   }
-  const int tiles = ((g.M + 127) / 128) * ((g.N + bn - 1) / bn);
-  const int grid = std::min(tiles, num_sms());
-  if (bn == 256) gemm_bf16_tcgen05_kernel<256><<<grid, 320, GemmCfg<256>::SMEM_BYTES, st>>>(g);
-  else gemm_bf16_tcgen05_kernel<160><<<grid, 320, GemmCfg<160>::SMEM_BYTES, st>>>(g);
-  return cudaGetLastError();
+  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CL>, g);
+}
+
+cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st) {
+  const bool cl = gemm_cluster() && g.M > 128;
+  if (bn == 256) return cl ? launch_gemm_t<256, true>(g, st) : launch_gemm_t<256, false>(g, st);
+  return cl ? launch_gemm_t<160, true>(g, st) : launch_gemm_t<160, false>(g, st);
 }
 
 // ------------------------------------------------------------------------------------------------ attention descriptors
@@ -748,7 +767,7 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
       const size_t sm = (36 * size_t(op.C1) + 4 * (kConvInRows + 2) * (op.W + 2)) * sizeof(float);
       static bool set = false;
       if (!set) { cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
-      conv_in_kernel<<<dim3((op.H + kConvInRows - 1) / kConvInRows, S), 512, sm, st>>>(op.f_in, conv_in_w_, conv_in_b_, op.f_out, op.H, op.W, op.C1);
+      conv_in_kernel<<<dim3((op.H + kConvInRows - 1) / kConvInRows, S), 256, sm, st>>>(op.f_in, conv_in_w_, conv_in_b_, op.f_out, op.H, op.W, op.C1);
       break;
     }
     case OP_GN_STATS: {
@@ -761,7 +780,8 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
     case OP_GN_APPLY: {
       const int C = op.C1 + op.C2;
       const int chunk = op.HW >= 4096 ? 32 : 16;
-      const int threads = std::max(256, std::min(640, ((C / 4 + 31) / 32) * 32));
+      const int quads_ = C / 4;
+      const int threads = std::max(256, quads_ * std::max(1, (256 + quads_ - 1) / quads_));      // quads * nsub (<= 640)
       GNApplyParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, chunk, op.nchunks, op.partial, op.gamma, op.beta, op.eps, op.silu, op.h_out, op.h_out2};
       gn_apply_kernel<<<dim3((op.HW + chunk - 1) / chunk, S), threads, 0, st>>>(p);
       break;

@@ -52,20 +52,26 @@ HEDIT_DEVICE void epi_store_rows(const float4* stg, int rq, int rr, const float4
   }
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
-  static constexpr int STAGES = (BN > 160) ? 4 : 5;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
-  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;     // PAIR: each CTA stages half of the W tile
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = PAIR ? (BN > 160 ? 6 : 7) : (BN > 160 ? 4 : 5);
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
   static constexpr int THREADS = 320;
 };
 
-template <int BN>
+// PAIR = true: cta_group::2.  Two CTAs of one cluster (an SM pair) own two consecutive M tiles of the same N tile and issue
+// ONE 256 x BN x 16 tcgen05.mma per K step from the leader: each SM reads its own A tile and only HALF of the W tile from
+// its shared memory (the tensor cores exchange the halves), which halves the W shared-memory traffic that bounds the
+// single-CTA kernel (SS-mode operand reads + TMA writes ~ 2 x 115 B/clk/SM at 128x160 tiles vs 128 B/clk/SM available).
+// Protocol: both CTAs' TMA loads complete on the LEADER's full barrier; the leader's MMA commits multicast to both CTAs'
+// empty / accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
+template <int BN, bool CLUSTER>
 __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CLUSTER>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -80,18 +86,27 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
   const int lane = threadIdx.x & 31;
   const int m_tiles = (p.M + 127) >> 7;
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  // work items: single tiles, or (CLUSTER) pairs of M tiles; `rank` selects this CTA's M tile inside a pair
+  const uint32_t rank = CLUSTER ? cluster_ctarank() : 0u;
+  const int num_tiles = CLUSTER ? ((m_tiles + 1) >> 1) * n_tiles : m_tiles * n_tiles;
+  const int tile0 = CLUSTER ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int tstep = CLUSTER ? int(gridDim.x >> 1) : int(gridDim.x);
+  auto tile_m0 = [&](int tile) { return CLUSTER ? (((tile / n_tiles) * 2 + int(rank)) << 7) : ((tile / n_tiles) << 7); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CLUSTER ? 16 : 8); }
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) {
+    if (CLUSTER) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();        // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -99,8 +114,8 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
     // ------------------------------------------------------------------ TMA producer (whole warp runs the loop so the
     // addressing stays in uniform registers; one elected lane issues the copies)
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) << 7;
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
+      const int m0 = tile_m0(tile);
       const int n0 = (tile % n_tiles) * BN;
       int s0 = 0, y0 = 0;
       if (p.a_mode != A_LINEAR) {
@@ -114,20 +129,26 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
         if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          if (p.a_mode == A_LINEAR) {
-            tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * 64, m0);
+          const int ky = tap / 3, kx = tap - ky * 3;
+          const int px = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
+          const int py = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
+          if (CLUSTER) {
+            // both CTAs' bytes are reported to the leader's barrier (the leader's MMA consumes both halves)
+            const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            if (p.a_mode == A_LINEAR) tma_load_2d_2sm(sa, &p.tmA, lfull, kb * 64, m0);
+            else if (p.a_mode == A_CONV3X3) tma_load_4d_2sm(sa, &p.tmA, lfull, cb * 64, kx - 1, y0 + ky - 1, s0);
+            else tma_load_5d_2sm(sa, &p.tmA, lfull, px * p.conv_cin + cb * 64, dx, py, y0 + dy, s0);
+            tma_load_2d_2sm(sb, &p.tmB, lfull, kb * 64, n0 + int(rank) * (BN / 2));
           } else {
-            const int ky = tap / 3, kx = tap - ky * 3;
-            if (p.a_mode == A_CONV3X3) {
-              tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * 64, kx - 1, y0 + ky - 1, s0);
-            } else {
-              const int px = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
-              const int py = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
-              tma_load_5d(sa, &p.tmA, &full_bar[stage], px * p.conv_cin + cb * 64, dx, py, y0 + dy, s0);
-            }
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (p.a_mode == A_LINEAR) tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * 64, m0);
+            else if (p.a_mode == A_CONV3X3) tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * 64, kx - 1, y0 + ky - 1, s0);
+            else tma_load_5d(sa, &p.tmA, &full_bar[stage], px * p.conv_cin + cb * 64, dx, py, y0 + dy, s0);
+            // the W map's box is BN/2 rows (shared with the pair variant): two loads
+            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
+            tma_load_2d(sb + (BN / 2) * 128, &p.tmB, &full_bar[stage], kb * 64, n0 + BN / 2);
           }
-          tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
         }
         __syncwarp();
         if (p.a_mode != A_LINEAR && ++cb == p.cin_blocks) { cb = 0; ++tap; }
@@ -135,33 +156,53 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-    const uint32_t smem_base = smem_u32(smem);
-    int stage = 0; uint32_t phase = 0; int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * 256;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues);
+    // in PAIR mode only the leader CTA issues (cta_group::2 instructions drive both SMs' tensor cores)
+    if (!CLUSTER || rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(CLUSTER ? 256 : 128, BN, 0, 0);
+      const uint32_t a_lo0 = umma_desc_lo_kmajor(smem_u32(smem));
+      const uint32_t b_lo0 = umma_desc_lo_kmajor(smem_u32(smem) + Cfg::A_BYTES);
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      // The issue thread is the critical resource at 128x160 tiles (4 MMAs = 320 tensor cycles per K block): probe the NEXT
+      // stage's barrier (non-blocking) before issuing the current stage's MMAs so its latency hides behind them.
+      bool ready = mbar_test(&full_bar[0], 0);
+      for (int tile = tile0; tile < num_tiles; tile += tstep, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t la = umma_desc_lo_kmajor(smem_base + stage * Cfg::STAGE_BYTES);
-          const uint32_t lb = umma_desc_lo_kmajor(smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES);
-          umma_f16_ss(d_tmem, umma_desc_make(la), umma_desc_make(lb), idesc, kb != 0);
-          umma_f16_ss(d_tmem, umma_desc_make(la + 2), umma_desc_make(lb + 2), idesc, 1);
-          umma_f16_ss(d_tmem, umma_desc_make(la + 4), umma_desc_make(lb + 4), idesc, 1);
-          umma_f16_ss(d_tmem, umma_desc_make(la + 6), umma_desc_make(lb + 6), idesc, 1);
-          umma_commit(&empty_bar[stage]);
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        const bool last_tile = (tile + tstep >= num_tiles);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (!ready) mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          int nstage = stage + 1; uint32_t nphase = phase;
+          if (nstage == STAGES) { nstage = 0; nphase ^= 1; }
+          const bool more = !(last_tile && kb + 1 == p.num_kb);
+          ready = more ? mbar_test(&full_bar[nstage], nphase) : false;
+          if (elect_one()) {
+            const uint32_t la = a_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
+            const uint32_t lb = b_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
+            if (CLUSTER) {
+              umma_f16_ss_2sm(d_tmem, umma_desc_make(la), umma_desc_make(lb), idesc, kb != 0);
+              umma_f16_ss_2sm(d_tmem, umma_desc_make(la + 2), umma_desc_make(lb + 2), idesc, 1);
+              umma_f16_ss_2sm(d_tmem, umma_desc_make(la + 4), umma_desc_make(lb + 4), idesc, 1);
+              umma_f16_ss_2sm(d_tmem, umma_desc_make(la + 6), umma_desc_make(lb + 6), idesc, 1);
+              umma_commit_2sm(&empty_bar[stage], 3);
+            } else {
+              umma_f16_ss(d_tmem, umma_desc_make(la), umma_desc_make(lb), idesc, kb != 0);
+              umma_f16_ss(d_tmem, umma_desc_make(la + 2), umma_desc_make(lb + 2), idesc, 1);
+              umma_f16_ss(d_tmem, umma_desc_make(la + 4), umma_desc_make(lb + 4), idesc, 1);
+              umma_f16_ss(d_tmem, umma_desc_make(la + 6), umma_desc_make(lb + 6), idesc, 1);
+              umma_commit(&empty_bar[stage]);
+            }
+          }
+          __syncwarp();
+          stage = nstage; phase = nphase;
         }
+        if (elect_one()) { if (CLUSTER) umma_commit_2sm(&tfull_bar[acc], 3); else umma_commit(&tfull_bar[acc]); }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(&tfull_bar[acc]);
-      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 8 warps; warp w owns TMEM lane quarter
@@ -186,8 +227,8 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
       else if (has_b && !has_rv && has_res && !has32 && has16) mode = 5;
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / n_tiles) << 7;
+    for (int tile = tile0; tile < num_tiles; tile += tstep, ++it) {
+      const int m0 = tile_m0(tile);
       const int n0 = (tile % n_tiles) * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -292,13 +333,20 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CLUSTER) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));     // the leader's MMA waits for both CTAs
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (CLUSTER) cluster_sync_all();        // no CTA exits while its peer may still multicast into it / arrive on its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    if (CLUSTER) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 }  // namespace hedit
