@@ -90,11 +90,16 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   const int n = E.latent_elems();
   const bool masa = a.masa_start_layer >= 0;
   const bool p2p = a.use_p2p != 0 && a.variant == 0 && !masa;
-  const bool ctrl = p2p || masa;          // launches C / BC / E run with attention control
+  const bool pnp = a.pnp != 0;
+  const bool ctrl = p2p || masa || pnp;   // launches C / BC / E run with attention control
   const bool blend = p2p && a.has_blend != nullptr && a.blend_alpha != nullptr && E.n_blend_layers() > 0 && c.sample == 64;
   const cudaMemcpyKind kIn = a.buffers_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const cudaMemcpyKind kOut = a.buffers_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (B < 1 || T < 1) { E.err_ = "bad batch/steps"; return -1; }
+  if (pnp && (a.explicit_form || a.variant != 0 || a.use_p2p || masa || !a.pnp_qk_on || !a.pnp_feat_on || a.xt_is_pair)) {
+    E.err_ = "Plug-and-Play runs the implicit form only (pnp_h_edit.py:33), without P2P / MasaCtrl, and needs both per-step flag arrays";
+    return -1;
+  }
   if (a.xt_is_pair && !a.explicit_form && a.variant == 0 && a.schedule != 0) {
     E.err_ = "xt_is_pair (single-step use) needs schedule 0: the exact-reuse schedule carries UNet outputs across timesteps";
     return -1;
@@ -134,6 +139,33 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
       pool += C.S;
       calls.push_back(C);
     }
+  } else if (pnp) {
+    // h_Edit_PnP_implicit (pnp_h_edit.py:104-160).  Reference pattern per step: A (4) at t, then at tt [x_opt,src], [x_opt,null] and
+    // the injected pair ([xo',src],[x_opt,tar]) = 8 sample-forwards.  schedule 1 reuses the pair's untouched source sample
+    // [xo',src] as the next step's [xo,src] (injection only ever writes the target sample): 7 per step.
+    CallDesc A, BC; BC.p2p = true;
+    A.pool_off = 0;
+    for (int b = 0; b < B; ++b) {
+      const int s = A.S;
+      A.add(XT(b, 0), 0); A.add(XT(b, 1), 0); A.add(XT(b, 1), 1 + 2 * b);
+      if (a.schedule == 0) A.add(XT(b, 0), 1 + 2 * b);
+      for (int j = s; j < A.S; ++j) A.unit(j, -1, b);
+      iuA[2 * b] = iuA0[2 * b] = s; iuA[2 * b + 1] = iuA0[2 * b + 1] = s + 1;
+      icA[2 * b + 1] = icA0[2 * b + 1] = s + 2;
+      icA0[2 * b] = (a.schedule == 0) ? s + 3 : s + 2;       // step 0: xo == xe
+      icA[2 * b] = s + 3;                                     // schedule 1: patched below to the pair's source sample
+    }
+    BC.pool_off = A.S;
+    for (int b = 0; b < B; ++b) {
+      const int s = BC.S;
+      BC.add(XP(b, 0), 1 + 2 * b); BC.add(XO(b), 2 + 2 * b); BC.add(XO(b), 1 + 2 * b); BC.add(XO(b), 0);
+      for (int j = 0; j < 4; ++j) BC.unit(s + j, -1, b);
+      BC.sq[s + 1] = s;                                       // target <- source (q, k and the resnet features)
+      if (a.schedule != 0) icA[2 * b] = BC.pool_off + s;
+      ict[b] = BC.pool_off + s + 1; ics[b] = BC.pool_off + s + 2; iu[b] = BC.pool_off + s + 3;
+    }
+    pool = A.S + BC.S;
+    calls.push_back(A); calls.push_back(BC);
   } else if (a.explicit_form) {
     CallDesc e; e.p2p = ctrl; e.pool_off = 0;
     for (int b = 0; b < B; ++b) {
@@ -274,6 +306,9 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
       cc.mapper = L.mapper; cc.is_replace = L.is_replace; cc.replace_m = L.replace_m;
       cc.c_base = L.c_base + size_t(ctrl_step) * B * 80; cc.c_tar = L.c_tar + size_t(ctrl_step) * B * 80;
       if (blend && save) { cc.blend_acc = L.blend_acc; cc.blend_alpha = L.blend_alpha; }
+    } else if (cd.p2p && pnp) {
+      if (a.pnp_qk_on[ctrl_step]) { cc.self_mask = a.pnp_self_mask; cc.self_q = cd.d_sq; cc.self_k = cd.d_sq; cc.self_v = nullptr; }
+      if (a.pnp_feat_on[ctrl_step]) cc.feat_src = cd.d_sq;
     } else if (cd.p2p && masa && a.ctrl_step0 + masa_step >= a.masa_start_step) {
       uint32_t m = 0;
       for (int l = std::max(0, a.masa_start_layer); l < E.n_tf(); ++l) m |= 1u << l;
@@ -306,7 +341,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     for (int k = 0; k < K; ++k) {
       const bool save = (k == K - 1);
       if (!a.explicit_form) {
-        if (a.variant == 0 && a.schedule == 0) { if (run_call(calls[1], i + 1, i, false)) return -1; if (run_call(calls[2], i + 1, i, save)) return -1; }
+        if (a.variant == 0 && a.schedule == 0 && !pnp) { if (run_call(calls[1], i + 1, i, false)) return -1; if (run_call(calls[2], i + 1, i, save)) return -1; }
         else if (run_call(calls[1], i + 1, i, save)) return -1;
       }
       CorrParams cp;

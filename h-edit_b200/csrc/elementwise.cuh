@@ -196,6 +196,17 @@ static __global__ void cast_bf16_kernel(const float* __restrict__ x, op_t* __res
   }
 }
 
+// Plug-and-Play feature injection (reference: text-guided/plug_n_play/pnp_utils.py:138-146): sample s takes the activation of sample
+// src[s] (rows whose src[s] == s are left alone).  Applied to conv2's INPUT, which makes conv2's output of the two samples identical,
+// exactly what the reference's copy of conv2's output produces.  n16 = 16-byte words per sample.
+static __global__ void copy_samples_kernel(op_t* __restrict__ buf, const int* __restrict__ src, size_t n16) {
+  const int s = blockIdx.y, f = src[s];
+  if (f == s || f < 0) return;
+  const uint4* from = reinterpret_cast<const uint4*>(buf) + size_t(f) * n16;
+  uint4* to = reinterpret_cast<uint4*>(buf) + size_t(s) * n16;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n16; i += size_t(gridDim.x) * blockDim.x) to[i] = from[i];
+}
+
 // nearest 2x upsample, fp32 NHWC -> bf16 NHWC (operand of the following 3x3 conv)
 static __global__ void upsample2x_bf16_kernel(const float* __restrict__ x, op_t* __restrict__ y, int S, int H, int W, int C) {
   const int quads = C >> 2;

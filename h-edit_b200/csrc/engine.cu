@@ -561,7 +561,7 @@ struct PlanBuilder {
   }
 
   // ResnetBlock2D (oracle/sd_unet.py ResnetBlock2D): returns a new fp32 [S*HW][cout] buffer
-  float* resblock(const ResW& w, const float* x1, int C1, const float* x2, int C2, int Hh, int Ww) {
+  float* resblock(const ResW& w, const float* x1, int C1, const float* x2, int C2, int Hh, int Ww, bool pnp_site = false) {
     const int HW = Hh * Ww, M = S * HW, cin = C1 + C2, cout = w.cout;
     ConvGeom cg{S, Hh, Ww, cin, 1};
     bf16* a1 = A<bf16>(size_t(M) * cin);
@@ -575,6 +575,7 @@ struct PlanBuilder {
     bf16* a2 = A<bf16>(size_t(M) * cout);
     gn(h1, cout, nullptr, 0, HW, w.n2g, w.n2b, 1e-5f, 1, a2, nullptr);
     F(h1);
+    if (pnp_site) { Op o{}; o.kind = OP_FEAT_COPY; o.h_out = a2; o.count = size_t(HW) * cout * sizeof(bf16) / 16; o.tag = "pnp_feat_copy"; push(o); }
     const float* resid = x1;
     float* sc = nullptr;
     if (w.wsc) {
@@ -704,7 +705,7 @@ struct PlanBuilder {
       const int oc = c.boc[3 - i];
       for (int l = 0; l < c.layers + 1; ++l) {
         auto sk = skips.back(); skips.pop_back();
-        float* y = resblock(E.res_[ri++], x, C, sk.first, sk.second, Hh, Ww);
+        float* y = resblock(E.res_[ri++], x, C, sk.first, sk.second, Hh, Ww, /*pnp_site=*/i == 1 && l == 1);
         if (x_owned) F(x);
         F(sk.first);
         C = oc;
@@ -819,6 +820,10 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
     case OP_CONV_OUT:
       CK(cudaMemcpyAsync(eps, op.f_out, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
       break;
+    case OP_FEAT_COPY:
+      if (!cc.feat_src) return 0;
+      copy_samples_kernel<<<dim3(unsigned(std::min<size_t>((op.count + 255) / 256, 64)), S), 256, 0, st>>>(op.h_out, cc.feat_src, op.count);
+      break;
   }
   return 1;
 }
@@ -833,8 +838,9 @@ long Engine::forward(const float* x, float* eps, int S, const CallCtrl& cc, cuda
     ++launches;
   }
   for (Op& op : plan->ops) {
-    if (launch_op(op, S, x, eps, cc, st) < 0) return -1;
-    ++launches;
+    const long r = launch_op(op, S, x, eps, cc, st);
+    if (r < 0) return -1;
+    launches += r;
   }
   CK(cudaGetLastError());
   return launches;

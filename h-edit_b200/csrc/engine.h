@@ -45,7 +45,7 @@ struct WeightSlot {
   bool loaded = false;
 };
 
-enum OpKind { OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_GEMM, OP_LN, OP_SELF_ATTN, OP_CROSS_ATTN, OP_UPSAMPLE, OP_CAST, OP_CONV_OUT };
+enum OpKind { OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_GEMM, OP_LN, OP_SELF_ATTN, OP_CROSS_ATTN, OP_UPSAMPLE, OP_CAST, OP_CONV_OUT, OP_FEAT_COPY };
 
 struct Op {
   OpKind kind;
@@ -69,6 +69,8 @@ struct CallCtrl {
   // self-attention injection (applied on transformer blocks whose bit is set in self_mask)
   uint32_t self_mask = 0;
   const int *self_q = nullptr, *self_k = nullptr, *self_v = nullptr;
+  // Plug-and-Play feature injection at up_blocks[1].resnets[1] (pnp_utils.py:138-146): [S] source sample per sample, or null
+  const int* feat_src = nullptr;
   // cross-attention work units + P2P edit tables for the current step
   const int *unit_s0 = nullptr, *unit_s1 = nullptr, *unit_img = nullptr;
   int n_units = 0;

@@ -146,9 +146,10 @@ class UNetEngine:
     def edit(self, xT: torch.Tensor, zs: torch.Tensor, ctx: torch.Tensor, timesteps: Sequence[int], coef: np.ndarray,
              cfg_scales: Sequence[float], plan: Optional[EditPlan], weight_reconstruction: float = 0.1, optimization_steps: int = 1,
              explicit_form: bool = False, schedule: int = 1, trace: bool = False, variant: int = 0, masactrl=None, mos_pull: bool = True,
-             xt_is_pair: bool = False, ctrl_step0: int = 0, blend_state: Optional[torch.Tensor] = None):
+             xt_is_pair: bool = False, ctrl_step0: int = 0, blend_state: Optional[torch.Tensor] = None, pnp=None):
         """xT (B,C,h,w), zs (B,steps,C,h,w), ctx (1+2B,77,D): all on the SAME side (all host or all on this device).
-        variant 1 = h_Edit_R_* (no attention control); masactrl = (start_step, start_layer) enables mutual self-attention.
+        variant 1 = h_Edit_R_* (no attention control); masactrl = (start_step, start_layer) enables mutual self-attention;
+        pnp = (self_mask, qk_on[steps], feat_on[steps]) runs h_Edit_PnP_implicit (Plug-and-Play q/k and feature injection).
         Returns (edited, recon[, trace]) on that side."""
         B, steps = xT.shape[0], zs.shape[1]
         out_shape = (B,) + tuple(xT.shape[-3:])
@@ -175,6 +176,11 @@ class UNetEngine:
         a.xt_is_pair, a.ctrl_step0 = int(xt_is_pair), int(ctrl_step0)
         a.blend_state = blend_state.data_ptr() if blend_state is not None else None
         keep = [ts, coef, xT, zs, ctx]
+        if pnp is not None:
+            qk_on, feat_on = (np.ascontiguousarray(np.asarray(v, dtype=np.int32)) for v in pnp[1:])
+            assert qk_on.shape == (steps,) and feat_on.shape == (steps,)
+            keep += [qk_on, feat_on]
+            a.pnp, a.pnp_self_mask, a.pnp_qk_on, a.pnp_feat_on = 1, int(pnp[0]), qk_on.ctypes.data, feat_on.ctypes.data
         if plan is not None:
             a.use_p2p = 1
             arrs = dict(mapper=plan.mapper, is_replace=plan.is_replace, c_base=plan.c_base, c_tar=plan.c_tar,

@@ -33,7 +33,7 @@ def get_engine(model, max_samples: int = 5, device: int = 0) -> UNetEngine:
 def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Sequence[Sequence[str]], cfg_scales, controllers,
                      eta=1.0, weight_reconstruction=0.075, optimization_steps=1, after_skip_steps=None, is_ddim_inversion=False,
                      explicit_form=False, schedule=1, engine: Optional[UNetEngine] = None, trace=False, variant=0, masactrl=None,
-                     mos_pull=True):
+                     mos_pull=True, pnp=None):
     """B independent edits in one native call.  xT (B,C,h,w); zs (B,steps,C,h,w); prompt_pairs[b] = [src, tar];
     controllers[b] = P2P controller of image b (ours or the reference's) or None for all (P2P off)."""
     B = xT.shape[0]
@@ -49,7 +49,7 @@ def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Se
     if controllers is not None and all(c is not None for c in controllers):
         plan = compile_edit_plan(controllers, steps)
     out = eng.edit(xT, zs[:, :steps], ctx, ts, coef, cfg_scales, plan, weight_reconstruction, optimization_steps, explicit_form, schedule, trace,
-                   variant=variant, masactrl=masactrl, mos_pull=mos_pull)
+                   variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp)
     if plan is not None:
         for c in controllers:       # keep the controller's observable counters consistent with the reference
             c.cur_step = getattr(c, "cur_step", 0) + steps
@@ -59,7 +59,7 @@ def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Se
 
 
 def _single(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstruction, optimization_steps, after_skip_steps,
-            is_ddim_inversion, explicit_form, variant=0, masactrl=None, mos_pull=True):
+            is_ddim_inversion, explicit_form, variant=0, masactrl=None, mos_pull=True, pnp=None):
     assert len(prompts) >= 2, "only support prompt editing"
     dev = xT.device
     x = xT.reshape(1, *xT.shape[-3:])
@@ -70,7 +70,7 @@ def _single(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstr
     use_cuda = torch.device(dev).type == "cuda"
     x, z = (x.cuda(), z.cuda()) if use_cuda else (x.cpu(), z.cpu())
     edited, recon = h_edit_p2p_batch(model, x, z, [prompts[:2]], cfg_scales, ctrl, eta, weight_reconstruction, optimization_steps, steps,
-                                     is_ddim_inversion, explicit_form, variant=variant, masactrl=masactrl, mos_pull=mos_pull)
+                                     is_ddim_inversion, explicit_form, variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp)
     return edited.to(dev), recon.to(dev)
 
 
@@ -132,6 +132,65 @@ def h_Edit_masactrl_implicit(model, xT, eta=1.0, prompts="", cfg_scales=None, pr
                   masactrl=(ed.start_step - ed.cur_step, ed.start_layer), mos_pull=False)
     ed.cur_step += after_skip_steps * optimization_steps
     return out
+
+
+# ---- Plug-and-Play (text-guided/plug_n_play/pnp_utils.py, inversion/pnp_h_edit.py) ---------------------------------------
+PNP_ATTN_BLOCKS = {1: [1, 2], 2: [0, 1, 2], 3: [0, 1, 2]}     # pnp_utils.py:88: decoder self-attention layers 4-11
+
+
+def register_time(model, t) -> None:
+    """pnp_utils.py:12 / pnp_h_edit.py:10.  The fused loop derives the injection flags of every step from the schedules recorded by
+    the two register_* functions below, so this only keeps the attribute observable."""
+    model._hedit_pnp_t = t
+
+
+def register_attention_control_efficient(model, injection_schedule) -> None:
+    """Same name as pnp_utils.py:29: records the timesteps at which the target's self-attention q and k are replaced by the source's
+    in `PNP_ATTN_BLOCKS` (the swap itself is a source-sample index inside self_attn_kernel)."""
+    model._hedit_pnp_qk = None if injection_schedule is None else {int(t) for t in injection_schedule}
+
+
+def register_conv_control_efficient(model, injection_schedule) -> None:
+    """Same name as pnp_utils.py:97: records the timesteps at which the target takes the source's conv2 output in
+    up_blocks[1].resnets[1]."""
+    model._hedit_pnp_conv = None if injection_schedule is None else {int(t) for t in injection_schedule}
+
+
+def pnp_self_mask(layers_per_block: int = 2) -> int:
+    """Bit mask over transformer blocks in forward order of the layers of `PNP_ATTN_BLOCKS`."""
+    L, m = layers_per_block, 0
+    for res, blocks in PNP_ATTN_BLOCKS.items():
+        for b in blocks:
+            m |= 1 << (3 * L + 1 + (res - 1) * (L + 1) + b)
+    return m
+
+
+def pnp_step_flags(model, after_skip_steps: int):
+    """(qk_on, feat_on) per executed timestep: the injected pair call of step i runs at tt = op[i+1] (0 after the last step) and the
+    patched forwards test `self.t in injection_schedule or self.t == 1000` (pnp_utils.py:51-52,138)."""
+    op = [int(t) for t in model.scheduler.timesteps[-after_skip_steps:]]
+    tts = op[1:] + [0]
+    on = lambda sched: [int(sched is not None and (tt in sched or tt == 1000)) for tt in tts]
+    return on(getattr(model, "_hedit_pnp_qk", None)), on(getattr(model, "_hedit_pnp_conv", None))
+
+
+def h_Edit_PnP_implicit(model, xT, eta=0, prompts="", cfg_scales=None, prog_bar=False, zs=None, optimization_steps=1, after_skip_steps=35,
+                        is_ddim_inversion=True, schedule=1):
+    """Reference signature (pnp_h_edit.py:33); `schedule` = 0 reproduces the reference's 8 UNet sample-forwards per step, 1 (default)
+    the exact-reuse 7."""
+    qk_on, feat_on = pnp_step_flags(model, after_skip_steps)
+    L = getattr(getattr(model.unet, "cfg", None), "layers_per_block", 2)
+    B = 1
+    eng = get_engine(model, max_samples=5 * B)
+    dev = xT.device
+    x = xT.reshape(1, *xT.shape[-3:])
+    z = zs[:after_skip_steps].reshape(1, after_skip_steps, *xT.shape[-3:])
+    use_cuda = torch.device(dev).type == "cuda"
+    x, z = (x.cuda(), z.cuda()) if use_cuda else (x.cpu(), z.cpu())
+    edited, recon = h_edit_p2p_batch(model, x, z, [prompts[:2]], cfg_scales, None, eta, 0.0, optimization_steps, after_skip_steps,
+                                     is_ddim_inversion, False, schedule=schedule, engine=eng, mos_pull=False,
+                                     pnp=(pnp_self_mask(L), qk_on, feat_on))
+    return edited.to(dev), recon.to(dev)
 
 
 class HEditStepper:

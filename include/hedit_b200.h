@@ -72,6 +72,15 @@ typedef struct hedit_edit_args {
    * blocks >= masa_start_layer, the edit samples attend to the K/V of their source samples.  masa_start_layer < 0: off */
   int32_t masa_start_step, masa_start_layer;
   int32_t mos_pull;          /* 1: apply the L1 reconstruction pull on MOS iterations k>0 (p2p_h_edit.py:670-686); 0: masactrl_h_edit.py */
+  /* ---- Plug-and-Play (text-guided/plug_n_play/pnp_utils.py:29-164 driven by inversion/pnp_h_edit.py:33): pnp = 1 runs
+   * h_Edit_PnP_implicit.  The attention-controlled call of a step is the pair ([x_orig,src],[x_opt,tar]) at the previous timestep tt;
+   * when pnp_qk_on[i] != 0 (tt in the qk injection schedule) the target takes the source's self-attention q and k in the transformer
+   * blocks of pnp_self_mask (bit = block index in forward order), and when pnp_feat_on[i] != 0 it takes the source's conv2 output at
+   * up_blocks[1].resnets[1].  Requires explicit_form = 0, variant = 0, use_p2p = 0. */
+  int32_t pnp;
+  uint32_t pnp_self_mask;
+  const int32_t* pnp_qk_on;   /* host [steps] */
+  const int32_t* pnp_feat_on; /* host [steps] */
   /* ---- single-step use (h_edit_step): run `steps` timesteps of a longer schedule and carry the controller state outside */
   int32_t xt_is_pair;        /* 1: xT is [B][2][C][h][w] = (x_orig, x_edit) rows of an edit in progress (requires schedule 0) */
   int32_t ctrl_step0;        /* controller step (AttentionControl.cur_step / LocalBlend.counter) before the first executed timestep;
