@@ -6,7 +6,7 @@ samplers.py (reference-compatible h_Edit_* callables)."""
 from .p2p import (EditController, LocalBlend, compile_edit_plan, get_equalizer, get_refinement_mapper,  # noqa: F401
                   get_replacement_mapper, get_time_words_attention_alpha, get_word_inds, make_controller,
                   register_attention_control)
-from .schedule import DDIMTables, step_tables  # noqa: F401
+from .schedule import DDIMTables, skip_pre_coeff, step_tables  # noqa: F401
 from .tokenizer import WordTokenizer  # noqa: F401
 from .engine import UNetEngine, unet_config_of  # noqa: F401
 from .samplers import (HEditStepper, h_edit_step, MutualSelfAttentionControl, encode_text, get_engine, h_Edit_masactrl_implicit, h_Edit_p2p_explicit,  # noqa: F401

@@ -33,6 +33,7 @@ class EditArgsC(C.Structure):
         ("has_blend", C.c_void_p), ("blend_alpha", C.c_void_p), ("start_blend", C.c_int32), ("blend_th", C.c_float),
         ("masa_start_step", C.c_int32), ("masa_start_layer", C.c_int32), ("mos_pull", C.c_int32),
         ("pnp", C.c_int32), ("pnp_self_mask", C.c_uint32), ("pnp_qk_on", C.c_void_p), ("pnp_feat_on", C.c_void_p),
+        ("pre_step", C.c_int32), ("pre_coeff", C.c_float),
         ("xt_is_pair", C.c_int32), ("ctrl_step0", C.c_int32), ("blend_state", C.c_void_p),
         ("edited", C.c_void_p), ("recon", C.c_void_p), ("trace", C.c_void_p),
         ("n_sample_forwards", C.c_int64), ("n_kernel_launches", C.c_int64),

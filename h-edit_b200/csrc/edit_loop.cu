@@ -322,6 +322,23 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     return 0;
   };
 
+  if (a.pre_step) {
+    // h_Edit_R_implicit after skipped steps (p2p_h_edit.py:239-267): one editing move of the edit row at the first timestep
+    if (a.variant != 1 || a.explicit_form) { E.err_ = "pre_step belongs to h_Edit_R_implicit (variant 1, implicit form)"; return -1; }
+    CKE(cudaMemcpy2DAsync(xopt, size_t(n) * sizeof(float), xt + n, size_t(2) * n * sizeof(float), size_t(n) * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+    if (run_call(calls[1], 0, 0, false)) return -1;
+    CorrParams cp;
+    cp.eps = L.eps; cp.iu = L.iu; cp.ics = L.ics; cp.ict = L.ict; cp.w_src_edit = a.w_src_edit; cp.w_tar = a.w_tar;
+    cp.corr = L.corr; cp.x_opt = xopt; cp.x_stride = n; cp.x_base = xopt; cp.xb_stride = n; cp.partial = nullptr; cp.n = n;
+    hstep_corr_kernel<<<dim3(nparts, B), 256, 0, st>>>(cp);
+    UpdateParams up;
+    up.x_opt = xopt; up.x_stride = n; up.x_base = xopt; up.xb_stride = n; up.corr = L.corr;
+    up.partial = nullptr; up.nparts = nparts; up.coeff = a.pre_coeff; up.w_rec = 0.f; up.n = n;
+    hstep_update_kernel<<<dim3(nparts, B), 256, 0, st>>>(up);
+    launches += 2;
+    CKE(cudaMemcpy2DAsync(xt + n, size_t(2) * n * sizeof(float), xopt, size_t(n) * sizeof(float), size_t(n) * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+  }
+
   for (int i = 0; i < T; ++i) {
     const int idx = T - 1 - i;                     // zs index (p2p_h_edit.py:599)
     const hedit_step_coef& hc = a.coef[i];

@@ -26,6 +26,8 @@ struct GemmEpilogue {
   int rows_per_group, ldrv, ldr, ldo, ldob;
   int geglu;                // 1: every 32-col chunk = 16 value | 16 gate -> bf16 out has N/2 columns
   int nchw_hw;              // >0: write out_f32 as [row / hw][N][row % hw] (NCHW latent layout; small-N generic path only)
+  float2* colstats;         // [ceil(M/32)][N] or null: (sum, sum of squares) of the fp32 output over each block of 32 rows, per
+                            // column -- the GroupNorm statistics of the NEXT layer, produced while the tile is still in registers
 };
 
 struct GemmParams {
@@ -37,9 +39,26 @@ struct GemmParams {
 
 // Coalesced write-back of one 32x32 chunk from the per-warp staging tile: lane = (row-in-group-of-4, quad); 8 iterations
 // cover the 32 rows.  All feature switches are compile-time so the loop body is ~12 instructions per float4.
+// Column statistics of one 32x32 chunk: every lane holds partial sums of its 4 columns over 8 rows; the 4 lanes that share a
+// column quad (lane bits 3,4) are combined in a fixed order and lane rr == 0 writes (sum, sumsq) x 4 columns.
+HEDIT_DEVICE void epi_store_colstats(float4 su, float4 sq, int rr, float2* dst) {
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    su.x += __shfl_xor_sync(0xffffffffu, su.x, o); su.y += __shfl_xor_sync(0xffffffffu, su.y, o);
+    su.z += __shfl_xor_sync(0xffffffffu, su.z, o); su.w += __shfl_xor_sync(0xffffffffu, su.w, o);
+    sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
+    sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
+  }
+  if (rr == 0) {
+    reinterpret_cast<float4*>(dst)[0] = make_float4(su.x, sq.x, su.y, sq.y);
+    reinterpret_cast<float4*>(dst)[1] = make_float4(su.z, sq.z, su.w, sq.w);
+  }
+}
+
 template <bool BIAS, bool RV, bool RES, bool F32, bool H16>
 HEDIT_DEVICE void epi_store_rows(const float4* stg, int rq, int rr, const float4& bb, const float4& rvv, const float4 (&rs)[8],
-                                 float* o32, size_t ldo4, op_t* o16, size_t ldob4) {
+                                 float* o32, size_t ldo4, op_t* o16, size_t ldob4, float2* cst) {
+  float4 su = make_float4(0.f, 0.f, 0.f, 0.f), sq = su;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = 4 * i + rr;
@@ -49,7 +68,12 @@ HEDIT_DEVICE void epi_store_rows(const float4* stg, int rq, int rr, const float4
     if (RES) { a.x += rs[i].x; a.y += rs[i].y; a.z += rs[i].z; a.w += rs[i].w; }
     if (F32) *reinterpret_cast<float4*>(o32 + i * ldo4) = a;
     if (H16) *reinterpret_cast<uint2*>(o16 + i * ldob4) = make_uint2(pack_op2(a.x, a.y), pack_op2(a.z, a.w));
+    if (F32) {   // (only fp32 outputs feed a GroupNorm)
+      su.x += a.x; su.y += a.y; su.z += a.z; su.w += a.w;
+      sq.x = fmaf(a.x, a.x, sq.x); sq.y = fmaf(a.y, a.y, sq.y); sq.z = fmaf(a.z, a.z, sq.z); sq.w = fmaf(a.w, a.w, sq.w);
+    }
   }
+  if (F32 && cst) epi_store_colstats(su, sq, rr, cst);      // cst is warp-uniform
 }
 
 template <int BN, bool PAIR>
@@ -297,21 +321,23 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
           float* o32 = has32 ? e.out_f32 + row0 * e.ldo + cq : nullptr;
           op_t* o16 = has16 ? e.out_bf16 + row0 * e.ldob + cq : nullptr;
           const size_t l32 = size_t(4) * e.ldo, l16 = size_t(4) * e.ldob;
+          float2* cst = e.colstats ? e.colstats + size_t(rbase >> 5) * p.N + cq : nullptr;
           switch (mode) {
-            case 1: epi_store_rows<true, false, false, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16); break;
-            case 2: epi_store_rows<true, false, true, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16); break;
-            case 3: epi_store_rows<true, true, false, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16); break;
-            case 4: epi_store_rows<false, false, false, false, true>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16); break;
-            default: epi_store_rows<true, false, true, false, true>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16); break;
+            case 1: epi_store_rows<true, false, false, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
+            case 2: epi_store_rows<true, false, true, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
+            case 3: epi_store_rows<true, true, false, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
+            case 4: epi_store_rows<false, false, false, false, true>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
+            default: epi_store_rows<true, false, true, false, true>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
           }
         } else {
           // generic path: partial tiles, ragged N, unusual feature combinations
+          float gsu[4] = {0.f, 0.f, 0.f, 0.f}, gsq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
           for (int i = 0; i < 8; ++i) {
             const int r = 4 * i + rr, row = rbase + r;
             const float4 a4 = stg[r * 8 + (rq ^ (r & 7))];
             const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll 1
+#pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int cc = cq + k;
               if (row < p.M && cc < p.N) {
@@ -319,6 +345,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
                 if (e.bias) x += e.bias[cc];
                 if (e.rowvec) x += e.rowvec[size_t(row / e.rows_per_group) * e.ldrv + cc];
                 if (e.residual) x += e.residual[size_t(row) * e.ldr + cc];
+                gsu[k] += x; gsq[k] = fmaf(x, x, gsq[k]);
                 if (e.out_f32) {
                   if (e.nchw_hw) e.out_f32[(size_t(row / e.nchw_hw) * p.N + cc) * e.nchw_hw + (row % e.nchw_hw)] = x;
                   else e.out_f32[size_t(row) * e.ldo + cc] = x;
@@ -327,6 +354,9 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
               }
             }
           }
+          if (e.colstats && rbase < p.M && col + 32 <= p.N)      // (colstats is only requested for N % 32 == 0)
+            epi_store_colstats(make_float4(gsu[0], gsu[1], gsu[2], gsu[3]), make_float4(gsq[0], gsq[1], gsq[2], gsq[3]), rr,
+                               e.colstats + size_t(rbase >> 5) * p.N + cq);
         }
         __syncwarp();
         prefetch(col + 64);                        // next chunk of this warp

@@ -146,7 +146,7 @@ class UNetEngine:
     def edit(self, xT: torch.Tensor, zs: torch.Tensor, ctx: torch.Tensor, timesteps: Sequence[int], coef: np.ndarray,
              cfg_scales: Sequence[float], plan: Optional[EditPlan], weight_reconstruction: float = 0.1, optimization_steps: int = 1,
              explicit_form: bool = False, schedule: int = 1, trace: bool = False, variant: int = 0, masactrl=None, mos_pull: bool = True,
-             xt_is_pair: bool = False, ctrl_step0: int = 0, blend_state: Optional[torch.Tensor] = None, pnp=None):
+             xt_is_pair: bool = False, ctrl_step0: int = 0, blend_state: Optional[torch.Tensor] = None, pnp=None, pre_coeff=None):
         """xT (B,C,h,w), zs (B,steps,C,h,w), ctx (1+2B,77,D): all on the SAME side (all host or all on this device).
         variant 1 = h_Edit_R_* (no attention control); masactrl = (start_step, start_layer) enables mutual self-attention;
         pnp = (self_mask, qk_on[steps], feat_on[steps]) runs h_Edit_PnP_implicit (Plug-and-Play q/k and feature injection).
@@ -176,6 +176,8 @@ class UNetEngine:
         a.xt_is_pair, a.ctrl_step0 = int(xt_is_pair), int(ctrl_step0)
         a.blend_state = blend_state.data_ptr() if blend_state is not None else None
         keep = [ts, coef, xT, zs, ctx]
+        if pre_coeff is not None:      # h_Edit_R_implicit on a skipped schedule
+            a.pre_step, a.pre_coeff = 1, float(pre_coeff)
         if pnp is not None:
             qk_on, feat_on = (np.ascontiguousarray(np.asarray(v, dtype=np.int32)) for v in pnp[1:])
             assert qk_on.shape == (steps,) and feat_on.shape == (steps,)

@@ -10,7 +10,7 @@ import torch
 
 from .engine import UNetEngine
 from .p2p import compile_edit_plan
-from .schedule import step_tables
+from .schedule import skip_pre_coeff, step_tables
 
 
 def encode_text(model, prompts: Union[str, List[str]]) -> torch.Tensor:
@@ -33,7 +33,7 @@ def get_engine(model, max_samples: int = 5, device: int = 0) -> UNetEngine:
 def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Sequence[Sequence[str]], cfg_scales, controllers,
                      eta=1.0, weight_reconstruction=0.075, optimization_steps=1, after_skip_steps=None, is_ddim_inversion=False,
                      explicit_form=False, schedule=1, engine: Optional[UNetEngine] = None, trace=False, variant=0, masactrl=None,
-                     mos_pull=True, pnp=None):
+                     mos_pull=True, pnp=None, pre_coeff=None):
     """B independent edits in one native call.  xT (B,C,h,w); zs (B,steps,C,h,w); prompt_pairs[b] = [src, tar];
     controllers[b] = P2P controller of image b (ours or the reference's) or None for all (P2P off)."""
     B = xT.shape[0]
@@ -49,7 +49,7 @@ def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Se
     if controllers is not None and all(c is not None for c in controllers):
         plan = compile_edit_plan(controllers, steps)
     out = eng.edit(xT, zs[:, :steps], ctx, ts, coef, cfg_scales, plan, weight_reconstruction, optimization_steps, explicit_form, schedule, trace,
-                   variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp)
+                   variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp, pre_coeff=pre_coeff)
     if plan is not None:
         for c in controllers:       # keep the controller's observable counters consistent with the reference
             c.cur_step = getattr(c, "cur_step", 0) + steps
@@ -59,7 +59,7 @@ def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Se
 
 
 def _single(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstruction, optimization_steps, after_skip_steps,
-            is_ddim_inversion, explicit_form, variant=0, masactrl=None, mos_pull=True, pnp=None):
+            is_ddim_inversion, explicit_form, variant=0, masactrl=None, mos_pull=True, pnp=None, pre_coeff=None):
     assert len(prompts) >= 2, "only support prompt editing"
     dev = xT.device
     x = xT.reshape(1, *xT.shape[-3:])
@@ -70,7 +70,7 @@ def _single(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstr
     use_cuda = torch.device(dev).type == "cuda"
     x, z = (x.cuda(), z.cuda()) if use_cuda else (x.cpu(), z.cpu())
     edited, recon = h_edit_p2p_batch(model, x, z, [prompts[:2]], cfg_scales, ctrl, eta, weight_reconstruction, optimization_steps, steps,
-                                     is_ddim_inversion, explicit_form, variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp)
+                                     is_ddim_inversion, explicit_form, variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp, pre_coeff=pre_coeff)
     return edited.to(dev), recon.to(dev)
 
 
@@ -89,12 +89,11 @@ def h_Edit_p2p_explicit(model, xT, eta=1.0, prompts="", cfg_scales=None, prog_ba
 
 def h_Edit_R_implicit(model, xT, eta=1.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None,
                       weight_reconstruction=0.1, optimization_steps=1, after_skip_steps=35, is_ddim_inversion=False):
-    """Reference signature (p2p_h_edit.py:162): h-Edit-R, implicit form, no P2P.  skip == 0 only (the reference's extra
-    pre-step for skipped schedules, :239-267, is not implemented)."""
+    """Reference signature (p2p_h_edit.py:162): h-Edit-R, implicit form, no P2P; on a skipped schedule the edit row is first moved
+    once at the first executed timestep (:239-267)."""
     assert not is_ddim_inversion, "only DDPM sampling (reference assert, p2p_h_edit.py:196)"
-    assert after_skip_steps == model.scheduler.num_inference_steps, "h_Edit_R_implicit: skip > 0 is not supported on the fused path"
     return _single(model, xT, eta, prompts, cfg_scales, zs, None, weight_reconstruction, optimization_steps, after_skip_steps,
-                   is_ddim_inversion, False, variant=1)
+                   is_ddim_inversion, False, variant=1, pre_coeff=skip_pre_coeff(model.scheduler, after_skip_steps, eta, is_ddim_inversion))
 
 
 def h_Edit_R_explicit(model, xT, eta=1.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None,

@@ -45,6 +45,21 @@ def step_tables(scheduler, after_skip_steps: int, eta, is_ddim_inversion: bool) 
     return ts + [0], coef
 
 
+def skip_pre_coeff(scheduler, after_skip_steps: int, eta, is_ddim_inversion: bool = False):
+    """Coefficient of the extra editing move `h_Edit_R_implicit` makes at the first timestep after skipped steps
+    (text-guided/inversion/p2p_h_edit.py:214-218,262-263), or None when nothing was skipped."""
+    T = scheduler.num_inference_steps
+    if after_skip_steps == T:
+        return None
+    etas = [eta] * T if isinstance(eta, (int, float)) else list(eta)
+    ac = scheduler.alphas_cumprod.detach().float().cpu()
+    sig, a = (1 - ac) ** 0.5, ac ** 0.5
+    ta, t = int(scheduler.timesteps[-(after_skip_steps + 1)]), int(scheduler.timesteps[-after_skip_steps])
+    e = etas[after_skip_steps - 1]                       # idx of step i = 0 (p2p_h_edit.py:234)
+    omega = 0 if is_ddim_inversion else e * (sig[t] / (sig[ta] * a[t])) * ((ac[t] - ac[ta]) ** 0.5)
+    return float((1 - ac[t] - omega ** 2) ** 0.5 - sig[ta] * (a[t] / a[ta]))
+
+
 class DDIMTables:
     """Minimal DDIM scheduler state for callers that have no diffusers scheduler object (benchmarks, tests):
     scaled-linear betas 0.00085..0.012 over 1000 train steps, set_alpha_to_one=False, "leading" timestep spacing

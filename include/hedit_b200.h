@@ -81,6 +81,12 @@ typedef struct hedit_edit_args {
   uint32_t pnp_self_mask;
   const int32_t* pnp_qk_on;   /* host [steps] */
   const int32_t* pnp_feat_on; /* host [steps] */
+  /* ---- h_Edit_R_implicit on a skipped schedule (p2p_h_edit.py:214-267): pre_step = 1 first moves the edit row at the first
+   * executed timestep by pre_coeff * (eps_tar - eps_src_edit) evaluated at that timestep (3 extra sample-forwards per image);
+   * pre_coeff = compute_full_coeff(time_ahead, t) - sqrt(1-abar[time_ahead]) * sqrt(abar[t]) / sqrt(abar[time_ahead]).
+   * Requires variant = 1, explicit_form = 0. */
+  int32_t pre_step;
+  float pre_coeff;
   /* ---- single-step use (h_edit_step): run `steps` timesteps of a longer schedule and carry the controller state outside */
   int32_t xt_is_pair;        /* 1: xT is [B][2][C][h][w] = (x_orig, x_edit) rows of an edit in progress (requires schedule 0) */
   int32_t ctrl_step0;        /* controller step (AttentionControl.cur_step / LocalBlend.counter) before the first executed timestep;

@@ -97,6 +97,13 @@ class ResnetBlock2D(nn.Module):
         self.norm2 = nn.GroupNorm(groups, cout, eps=eps)
         self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+        # parameter-free attributes of diffusers' ResnetBlock2D that the Plug-and-Play patched forward reads
+        # (text-guided/plug_n_play/pnp_utils.py:99-160); SD-1.x values
+        self.nonlinearity = nn.SiLU()
+        self.dropout = nn.Dropout(0.0)
+        self.upsample = self.downsample = None
+        self.time_embedding_norm = "default"
+        self.output_scale_factor = 1.0
 
     def forward(self, x, temb):
         h = self.conv1(F.silu(self.norm1(x)))

@@ -150,12 +150,39 @@ def _run_variant(name, eng_cache={}):
     elif mode == "R_implicit":
         ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, meta["weight_reconstruction"], K, variant=1)
         want_fwd = (2 + 3 * K) * T
+    elif mode == "R_implicit_skip":
+        S = meta["after_skip_steps"]
+        ts, coef = hedit_b200.step_tables(model.scheduler, S, meta["eta"], False)
+        pre = hedit_b200.skip_pre_coeff(model.scheduler, S, meta["eta"], False)
+        assert pre is not None and hedit_b200.skip_pre_coeff(model.scheduler, T, meta["eta"], False) is None
+        ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, meta["weight_reconstruction"], K, variant=1, pre_coeff=pre)
+        want_fwd = (2 + 3 * K) * S + 3
     elif mode == "R_explicit":
         ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, 1, explicit_form=True, variant=1)
         want_fwd = 3 * T
     elif mode == "masactrl":
         ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, K, masactrl=(meta["masa_start_step"], meta["masa_start_layer"]), mos_pull=False)
         want_fwd = (2 + 5 * K) * T
+    elif mode == "pnp":
+        # same registration calls as main_plugnplay.py:196-197, on the schedules the golden was generated with
+        hedit_b200.register_attention_control_efficient(model, meta["pnp_qk_timesteps"])
+        hedit_b200.register_conv_control_efficient(model, meta["pnp_conv_timesteps"])
+        qk_on, feat_on = hedit_b200.pnp_step_flags(model, T)
+        assert 0 < sum(qk_on) < sum(feat_on) < T
+        pnp = (hedit_b200.pnp_self_mask(2), qk_on, feat_on)
+        ed0, rc0 = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, K, schedule=0, mos_pull=False, pnp=pnp)
+        assert eng.last_stats["sample_forwards"] == (4 + 4 * K) * T
+        r0, _ = rel_err(ed0.cpu(), g["edited"])
+        assert r0 < TOL_LOOP
+        ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, K, schedule=1, mos_pull=False, pnp=pnp)
+        want_fwd = (3 + 4 * K) * T
+        # the exact-reuse schedule changes no arithmetic
+        assert (ed - ed0).abs().max().item() == 0.0 and (rc - rc0).abs().max().item() == 0.0
+        # the injection matters: with it switched off the edit differs from the golden by far more than the tolerance
+        off = (0, [0] * T, [0] * T)
+        ed_off, _ = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, K, schedule=1, mos_pull=False, pnp=off)
+        assert rel_err(ed_off.cpu(), g["edited"])[0] > 5 * TOL_LOOP
+        ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, K, schedule=1, mos_pull=False, pnp=pnp)
     r_ed, m_ed = rel_err(ed.cpu(), g["edited"])
     r_rc, m_rc = rel_err(rc.cpu(), g["recon"])
     print(f"{name}: edited rel {r_ed:.3e} max {m_ed:.3e} | recon rel {r_rc:.3e} max {m_rc:.3e} | {eng.last_stats}")
@@ -164,7 +191,7 @@ def _run_variant(name, eng_cache={}):
     return r_ed, r_rc
 
 
-@pytest.mark.parametrize("name", ["tiny_p2p_explicit", "tiny_R_implicit_mos2", "tiny_R_explicit", "tiny_masactrl_mos2"])
+@pytest.mark.parametrize("name", ["tiny_p2p_explicit", "tiny_R_implicit_mos2", "tiny_R_explicit", "tiny_masactrl_mos2", "tiny_pnp", "tiny_R_implicit_skip2"])
 def test_sampler_variants(name):
     if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", name + ".pt")):
         pytest.skip("golden missing")

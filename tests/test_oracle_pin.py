@@ -34,6 +34,22 @@ def test_oracle_matches_reference_golden(name):
             assert torch.equal(tb[k], getattr(spec, k)), k
 
 
+def test_oracle_pnp_matches_reference_golden():
+    """oracle/pnp.py against the outputs of the unmodified reference h_Edit_PnP_implicit + pnp_utils registration (MOS K=2)."""
+    from oracle import pnp as opnp
+    from oracle_run import cfg_from_meta
+    g = load_golden("small32_pnp_mos2")
+    meta = g["meta"]
+    model = OraclePipeline(cfg_from_meta(meta), seed=0)
+    model.scheduler.set_timesteps(meta["T"])
+    st = opnp.PnPState(set(meta["pnp_qk_timesteps"]), set(meta["pnp_conv_timesteps"]))
+    opnp.install_oracle_pnp(model.unet, st)
+    ed, rc = opnp.h_edit_pnp_implicit(model.unet, model.scheduler, g["ctx_uncond"], g["ctx_src"], g["ctx_tar"], g["xT"], g["zs"], st,
+                                      meta["cfg_scales"], eta=meta["eta"], optimization_steps=meta["K"], after_skip_steps=meta["T"])
+    assert (ed - g["edited"]).abs().max().item() <= 1e-4 and (rc - g["recon"]).abs().max().item() <= 1e-4
+    assert (rc - g["w0"]).abs().max().item() < 1e-3          # intrinsic known answer: the reconstruction row returns the inverted latent
+
+
 @pytest.mark.slow
 def test_oracle_matches_reference_golden_blend64():
     g = load_golden("tiny_replace_mos2")

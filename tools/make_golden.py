@@ -33,6 +33,9 @@ VARIANTS = {
     "tiny_R_implicit_mos2": (UNetConfig.tiny(sample_size=64), 5, 2, "R_implicit"),
     "tiny_R_explicit": (UNetConfig.tiny(sample_size=64), 6, 1, "R_explicit"),
     "tiny_masactrl_mos2": (UNetConfig.tiny(sample_size=64), 5, 2, "masactrl"),
+    "tiny_R_implicit_skip2": (UNetConfig.tiny(sample_size=64), 6, 1, "R_implicit_skip"),
+    "tiny_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "pnp"),
+    "small32_pnp_mos2": (UNetConfig.tiny(sample_size=32), 4, 2, "pnp"),
 }
 
 CASES = {
@@ -138,6 +141,12 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
         edited, recon = ref.p2p_h_edit.h_Edit_p2p_explicit(model, controller=controller, **kw)
     elif mode == "R_implicit":
         edited, recon = ref.p2p_h_edit.h_Edit_R_implicit(model, controller=None, weight_reconstruction=0.1, optimization_steps=K, **kw)
+    elif mode == "R_implicit_skip":
+        # main_p2p.py:220-236 with --skip 2: start from wts[T-2], use the first T-2 noise maps
+        S = T - 2
+        kw.update(xT=wts[S], zs=zs[:S], after_skip_steps=S)
+        edited, recon = ref.p2p_h_edit.h_Edit_R_implicit(model, controller=None, weight_reconstruction=0.1, optimization_steps=K, **kw)
+        meta_extra = dict(after_skip_steps=S)
     elif mode == "R_explicit":
         edited, recon = ref.p2p_h_edit.h_Edit_R_explicit(model, controller=None, **kw)
     elif mode == "masactrl":
@@ -151,6 +160,17 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
         importlib.import_module("masactrl.masactrl_utils").regiter_attention_editor_diffusers(model, editor)
         edited, recon = mh.h_Edit_masactrl_implicit(model, optimization_steps=K, **kw)
         meta_extra = dict(masa_start_step=start_step, masa_start_layer=start_layer)
+    elif mode == "pnp":
+        # main_plugnplay.py:186-208 (h_edit_R_pnp), with the injection fractions raised so that short schedules have both
+        # injected and un-injected steps
+        pu = importlib.import_module("plug_n_play.pnp_utils")
+        ph = importlib.import_module("inversion.pnp_h_edit")
+        f_t, attn_t = int(T * 0.8), int(T * 0.5)
+        qk_ts, conv_ts = model.scheduler.timesteps[:attn_t], model.scheduler.timesteps[:f_t]
+        pu.register_attention_control_efficient(model, qk_ts)
+        pu.register_conv_control_efficient(model, conv_ts)
+        edited, recon = ph.h_Edit_PnP_implicit(model, optimization_steps=K, **kw)
+        meta_extra = dict(pnp_qk_timesteps=[int(t) for t in qk_ts], pnp_conv_timesteps=[int(t) for t in conv_ts])
     else:
         raise ValueError(mode)
     enc = ref.inversion_utils.encode_text
@@ -160,7 +180,7 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
                      unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
                                cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
                      weights="oracle.sd_unet.seeded_init_(seed=0)", generator="tools/make_golden.py", torch=torch.__version__, **meta_extra),
-        "w0": w0, "zs": zs[:T].clone(), "xT": wts[T].clone(),
+        "w0": w0, "zs": kw["zs"].clone(), "xT": kw["xT"].clone(),
         "ctx_uncond": enc(model, [""]), "ctx_src": enc(model, [prompts[0]]), "ctx_tar": enc(model, [prompts[1]]),
         "edited": edited.detach().clone(), "recon": recon.detach().clone(),
     }
@@ -184,7 +204,7 @@ def run_ddim_inversion(ref, name="tiny_ddim_inversion", T=6):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "variants", "inversion", "all"])
+    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "variants", "inversion", "pnp", "all"])
     args = ap.parse_args()
     ref = load_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
@@ -192,14 +212,18 @@ def main():
         out = run_ddim_inversion(ref)
         torch.save(out, os.path.join(ROOT, "tests", "golden", "tiny_ddim_inversion.pt"))
         print("tiny_ddim_inversion |zs|", out["zs"].abs().mean().item(), flush=True)
-    if args.config in ("variants", "all"):
+    if args.config in ("variants", "all", "pnp"):
         for name, (cfg, T, K, mode) in VARIANTS.items():
+            if args.config == "pnp" and mode not in ("pnp", "R_implicit_skip"):
+                continue
+            if args.config == "pnp" and os.path.exists(os.path.join(ROOT, "tests", "golden", f"{name}.pt")):
+                continue
             out = run_variant(ref, name, cfg, T, K, mode)
             path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
             torch.save(out, path)
             print(name, "->", path, "|edited| %.4f" % out["edited"].abs().mean().item(), flush=True)
     for name, (cfg, T, K, rep, blend) in CASES.items():
-        if args.config in ("variants", "inversion") or (args.config != "all" and not name.startswith(args.config)):
+        if args.config in ("variants", "inversion", "pnp") or (args.config != "all" and not name.startswith(args.config)):
             continue
         out = run_case(ref, name, cfg, T, K, rep, blend)
         path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
