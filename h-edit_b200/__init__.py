@@ -6,13 +6,14 @@ samplers.py (reference-compatible h_Edit_* callables)."""
 from .p2p import (EditController, LocalBlend, compile_edit_plan, get_equalizer, get_refinement_mapper,  # noqa: F401
                   get_replacement_mapper, get_time_words_attention_alpha, get_word_inds, make_controller,
                   register_attention_control)
-from .schedule import DDIMTables, skip_pre_coeff, step_tables  # noqa: F401
+from .schedule import DDIMTables, skip_pre_coeff, step_tables, x0_tables  # noqa: F401
 from .tokenizer import WordTokenizer  # noqa: F401
 from .engine import UNetEngine, unet_config_of  # noqa: F401
 from .samplers import (HEditStepper, h_edit_step, MutualSelfAttentionControl, encode_text, get_engine, h_Edit_masactrl_implicit, h_Edit_p2p_explicit,  # noqa: F401
                        h_Edit_p2p_implicit, h_Edit_R_explicit, h_Edit_R_implicit, h_edit_p2p_batch, regiter_attention_editor_diffusers,
                        h_Edit_PnP_implicit, pnp_self_mask, pnp_step_flags, register_attention_control_efficient, register_conv_control_efficient, register_time)
 
+from . import style  # noqa: F401,E402
 from .inversion import ddim_inversion, inversion_forward_process_ddpm, sample_xts_from_x0  # noqa: F401,E402
 
 __all__ = ["inversion_forward_process_ddpm", "ddim_inversion", "UNetEngine", "unet_config_of", "make_controller", "register_attention_control", "compile_edit_plan",

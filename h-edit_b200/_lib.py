@@ -21,6 +21,9 @@ class StepCoefC(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("sqrt_1m_at", "sqrt_at", "sqrt_ap", "dir", "noise", "coeff")]
 
 
+GUIDANCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int)
+
+
 class EditArgsC(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("steps", C.c_int32), ("opt_steps", C.c_int32), ("explicit_form", C.c_int32),
@@ -34,6 +37,8 @@ class EditArgsC(C.Structure):
         ("masa_start_step", C.c_int32), ("masa_start_layer", C.c_int32), ("mos_pull", C.c_int32),
         ("pnp", C.c_int32), ("pnp_self_mask", C.c_uint32), ("pnp_qk_on", C.c_void_p), ("pnp_feat_on", C.c_void_p),
         ("pre_step", C.c_int32), ("pre_coeff", C.c_float),
+        ("guidance", C.c_void_p), ("guidance_user", C.c_void_p), ("guidance_weight", C.c_float), ("x0_coef", C.c_void_p),
+        ("guid_x0", C.c_void_p), ("guid_grad", C.c_void_p),
         ("xt_is_pair", C.c_int32), ("ctrl_step0", C.c_int32), ("blend_state", C.c_void_p),
         ("edited", C.c_void_p), ("recon", C.c_void_p), ("trace", C.c_void_p),
         ("n_sample_forwards", C.c_int64), ("n_kernel_launches", C.c_int64),

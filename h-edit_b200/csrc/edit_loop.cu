@@ -100,6 +100,10 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     E.err_ = "Plug-and-Play runs the implicit form only (pnp_h_edit.py:33), without P2P / MasaCtrl, and needs both per-step flag arrays";
     return -1;
   }
+  if (a.guidance && (a.explicit_form || !a.x0_coef || !a.guid_x0 || !a.guid_grad)) {
+    E.err_ = "reward guidance runs in the implicit form and needs x0_coef, guid_x0 and guid_grad";
+    return -1;
+  }
   if (a.xt_is_pair && !a.explicit_form && a.variant == 0 && a.schedule != 0) {
     E.err_ = "xt_is_pair (single-step use) needs schedule 0: the exact-reuse schedule carries UNet outputs across timesteps";
     return -1;
@@ -372,6 +376,24 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
       up.partial = pull ? L.partial : nullptr; up.nparts = nparts; up.coeff = hc.coeff; up.w_rec = a.weight_reconstruction; up.n = n;
       hstep_update_kernel<<<dim3(nparts, B), 256, 0, st>>>(up);
       launches += 2;
+      if (a.guidance) {
+        // reward-guided Langevin move on the Tweedie prediction of the just-updated x_opt (h_edit.py:150-172); eps_tar is the
+        // target-guided noise of THIS iteration's UNet call (evaluated before the text move), as in the reference
+        const float s1m = a.x0_coef[2 * i], sa = a.x0_coef[2 * i + 1];
+        X0PredParams xp;
+        xp.eps = L.eps; xp.iu = L.iu; xp.ict = L.ict; xp.w_tar = a.w_tar; xp.sqrt_1m_att = s1m; xp.sqrt_att = sa;
+        xp.x_opt = xopt; xp.x_stride = n; xp.x0 = a.guid_x0; xp.n = n;
+        hstep_x0pred_kernel<<<dim3(nparts, B), 256, 0, st>>>(xp);
+        if (a.guidance(a.guidance_user, i, k) != 0) { E.err_ = "guidance callback failed"; return -1; }
+        GuidNormParams gn;
+        gn.corr = L.corr; gn.grad_x0 = a.guid_grad; gn.inv_sqrt_att = 1.f / sa; gn.partial = L.partial; gn.n = n;
+        hstep_guid_norm_kernel<<<dim3(nparts, B), 256, 0, st>>>(gn);
+        GuidUpdateParams gu;
+        gu.x_opt = xopt; gu.x_stride = n; gu.grad_x0 = a.guid_grad; gu.inv_sqrt_att = 1.f / sa; gu.weight = a.guidance_weight;
+        gu.partial = L.partial; gu.nparts = nparts; gu.n = n;
+        hstep_guid_update_kernel<<<dim3(nparts, B), 256, 0, st>>>(gu);
+        launches += 3;
+      }
     }
     // xt <- [x_orig_{t-1}, x_opt]
     CKE(cudaMemcpy2DAsync(xt, size_t(2) * n * sizeof(float), xprev, size_t(2) * n * sizeof(float), size_t(n) * sizeof(float), B, cudaMemcpyDeviceToDevice, st));

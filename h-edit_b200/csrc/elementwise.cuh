@@ -58,6 +58,41 @@ static __global__ void gn_stats_kernel(const GNStatsParams p) {
   }
 }
 
+// Fused-statistics path: the producing GEMM's epilogue already wrote (sum, sumsq) per 32-row block per column (gemm.cuh colstats);
+// this kernel folds them into (mean, rstd) per (sample, group).  grid (groups, S), 128 threads; fixed summation order.
+struct GNFinalizeParams {
+  const float2* cs1; const float2* cs2;   // [S*HW/32][C1], [S*HW/32][C2] (cs2 null when C2 == 0)
+  int C1, C2, HW, groups;
+  float eps;
+  float2* stats;                          // [S][groups] (mean, rstd)
+};
+
+static __global__ void gn_finalize_kernel(const GNFinalizeParams p) {
+  __shared__ double ssu[128], ssq[128];
+  const int C = p.C1 + p.C2, cpg = C / p.groups;
+  const int g = blockIdx.x, s = blockIdx.y, nrb = p.HW >> 5;
+  const int c0 = g * cpg;
+  float su = 0.f, sq = 0.f;
+  for (int i = threadIdx.x; i < nrb * cpg; i += blockDim.x) {
+    const int rb = i / cpg, c = c0 + (i - rb * cpg);
+    const float2 t = (c < p.C1) ? p.cs1[(size_t(s) * nrb + rb) * p.C1 + c] : p.cs2[(size_t(s) * nrb + rb) * p.C2 + (c - p.C1)];
+    su += t.x; sq += t.y;
+  }
+  ssu[threadIdx.x] = su; ssq[threadIdx.x] = sq;
+  __syncthreads();
+  for (int o = 64; o; o >>= 1) {
+    if (threadIdx.x < o) { ssu[threadIdx.x] += ssu[threadIdx.x + o]; ssq[threadIdx.x] += ssq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = double(p.HW) * cpg;
+    const double mean = ssu[0] / n;
+    double var = ssq[0] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    p.stats[size_t(s) * p.groups + g] = make_float2(float(mean), float(1.0 / sqrt(var + double(p.eps))));
+  }
+}
+
 // Pass 2: finalise statistics (double combine), then y = [silu](x * a_c + b_c) -> bf16, optionally also the raw
 // bf16 copy of x (operand of the 1x1 shortcut conv).
 struct GNApplyParams {
@@ -68,13 +103,16 @@ struct GNApplyParams {
   float eps; int silu;
   op_t* out;      // [S][HW][C]
   op_t* raw_out;  // [S][HW][C] or null
+  const float2* stats;   // [S][groups] (mean, rstd) from gn_finalize_kernel, or null (then `partial` is finalised here)
 };
 
 static __global__ void gn_apply_kernel(const GNApplyParams p) {
   __shared__ float smean[32], srstd[32];
   const int C = p.C1 + p.C2, cpg = C / p.groups, quads = C >> 2;
   const int s = blockIdx.y;
-  {   // finalise the statistics: 8 threads per group sum the chunk partials, then one thread per group combines in double
+  if (p.stats) {
+    if (threadIdx.x < p.groups) { const float2 t = p.stats[size_t(s) * p.groups + threadIdx.x]; smean[threadIdx.x] = t.x; srstd[threadIdx.x] = t.y; }
+  } else {   // finalise the statistics: 8 threads per group sum the chunk partials, then one thread per group combines in double
     __shared__ float2 part[8][32];
     const int g = threadIdx.x & 31, sl = threadIdx.x >> 5;
     if (sl < 8) {

@@ -533,8 +533,22 @@ struct PlanBuilder {
     const size_t off = ar.alloc(n * sizeof(T));
     return reinterpret_cast<T*>(E.arena_ + off);     // arena_ may be null in the sizing pass (pointer arithmetic only)
   }
-  template <typename T> void F(T* p) { ar.release(size_t(reinterpret_cast<uint8_t*>(p) - E.arena_)); }
+  template <typename T> void F(T* p) {
+    ar.release(size_t(reinterpret_cast<uint8_t*>(p) - E.arena_));
+    auto it = colstats_of.find(reinterpret_cast<const void*>(p));
+    if (it != colstats_of.end()) { ar.release(size_t(reinterpret_cast<uint8_t*>(it->second) - E.arena_)); colstats_of.erase(it); }
+  }
   void push(const Op& op) { if (plan) plan->ops.push_back(op); }
+  // GroupNorm statistics fused into the producer: fp32 tensors whose every 32-row block lies inside one sample get a
+  // [M/32][N] (sum, sumsq) side buffer written by the GEMM epilogue; it lives exactly as long as the tensor.
+  std::map<const void*, float2*> colstats_of;
+  float2* want_colstats(const float* out, int M, int N, int HW) {
+    static const bool off = getenv("HEDIT_GN_FUSED") && atoi(getenv("HEDIT_GN_FUSED")) == 0;      // tuning switch: separate gn_stats pass
+    if (off || (HW & 31) || (N & 31)) return nullptr;
+    float2* cs = A<float2>(size_t((M + 31) / 32) * N);
+    colstats_of[out] = cs;
+    return cs;
+  }
 
   void gemm(const char* tag, const bf16* Ain, int lda, int mode, const ConvGeom* cg, const bf16* Wt, int M, int N, int K, GemmEpilogue ep) {
     flops += 2.0 * M * N * K;
@@ -545,6 +559,18 @@ struct PlanBuilder {
     push(op);
   }
   void gn(const float* x1, int C1, const float* x2, int C2, int HW, const float* g, const float* b, float eps, int silu, bf16* out, bf16* raw) {
+    auto c1 = colstats_of.find(x1), c2 = colstats_of.find(x2);
+    if (c1 != colstats_of.end() && (x2 == nullptr || c2 != colstats_of.end())) {
+      float2* stats = A<float2>(size_t(S) * E.cfg_.groups);
+      Op f{}; f.kind = OP_GN_FINALIZE; f.cs1 = c1->second; f.cs2 = x2 ? c2->second : nullptr; f.C1 = C1; f.C2 = C2; f.HW = HW; f.eps = eps;
+      f.stats = stats; f.tag = "gn_finalize";
+      push(f);
+      Op a{}; a.kind = OP_GN_APPLY; a.f_in = x1; a.f_in2 = x2; a.C1 = C1; a.C2 = C2; a.HW = HW; a.gamma = g; a.beta = b; a.eps = eps; a.silu = silu;
+      a.h_out = out; a.h_out2 = raw; a.stats = stats; a.tag = "gn_apply";
+      push(a);
+      F(stats);
+      return;
+    }
     const int chunk = std::max(16, HW / 64);
     const int nch = (HW + chunk - 1) / chunk;
     float2* partial = A<float2>(size_t(S) * nch * E.cfg_.groups);
@@ -570,6 +596,7 @@ struct PlanBuilder {
     float* h1 = A<float>(size_t(M) * cout);
     GemmEpilogue e1; memset(&e1, 0, sizeof e1);
     e1.bias = w.b1; e1.rowvec = E.temb_rows_ + w.temb_off; e1.ldrv = E.tproj_total_; e1.rows_per_group = HW; e1.out_f32 = h1; e1.ldo = cout;
+    e1.colstats = want_colstats(h1, M, cout, HW);
     gemm("res.conv1", a1, cin, A_CONV3X3, &cg, w.w1, M, cout, 9 * cin, e1);
     F(a1);
     bf16* a2 = A<bf16>(size_t(M) * cout);
@@ -590,6 +617,7 @@ struct PlanBuilder {
     ConvGeom cg2{S, Hh, Ww, cout, 1};
     GemmEpilogue e2; memset(&e2, 0, sizeof e2);
     e2.bias = w.b2; e2.residual = resid; e2.ldr = cout; e2.out_f32 = out; e2.ldo = cout;
+    e2.colstats = want_colstats(out, M, cout, HW);
     gemm("res.conv2", a2, cout, A_CONV3X3, &cg2, w.w2, M, cout, 9 * cout, e2);
     F(a2);
     if (sc) F(sc);
@@ -660,6 +688,7 @@ struct PlanBuilder {
     F(t);
     float* out = A<float>(size_t(M) * C);
     memset(&e, 0, sizeof e); e.bias = w.b_out; e.residual = x; e.ldr = C; e.out_f32 = out; e.ldo = C;
+    e.colstats = want_colstats(out, M, C, HW);
     gemm("tf.proj_out", a, C, A_LINEAR, nullptr, w.w_out, M, C, C, e);
     F(a);
     return out;
@@ -691,6 +720,7 @@ struct PlanBuilder {
         float* y = A<float>(size_t(S) * Hh * Ww * C);
         ConvGeom cg{S, Hh, Ww, C, 2};
         GemmEpilogue e; memset(&e, 0, sizeof e); e.bias = E.down_b_[i]; e.out_f32 = y; e.ldo = C;
+        e.colstats = want_colstats(y, S * Hh * Ww, C, Hh * Ww);
         gemm("downsample", xb, C, A_CONV3X3S2, &cg, E.down_w_[i], S * Hh * Ww, C, 9 * C, e);
         F(xb);
         x = y;
@@ -720,6 +750,7 @@ struct PlanBuilder {
         float* y = A<float>(size_t(S) * Hh * Ww * C);
         ConvGeom cg{S, Hh, Ww, C, 1};
         GemmEpilogue e; memset(&e, 0, sizeof e); e.bias = E.up_b_[i]; e.out_f32 = y; e.ldo = C;
+        e.colstats = want_colstats(y, S * Hh * Ww, C, Hh * Ww);
         gemm("upsample.conv", up, C, A_CONV3X3, &cg, E.up_w_[i], S * Hh * Ww, C, 9 * C, e);
         F(up);
         x = y;
@@ -778,12 +809,17 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
       gn_stats_kernel<<<dim3(op.nchunks, S), threads, 0, st>>>(p);
       break;
     }
+    case OP_GN_FINALIZE: {
+      GNFinalizeParams p{op.cs1, op.cs2, op.C1, op.C2, op.HW, c.groups, op.eps, op.stats};
+      gn_finalize_kernel<<<dim3(c.groups, S), 128, 0, st>>>(p);
+      break;
+    }
     case OP_GN_APPLY: {
       const int C = op.C1 + op.C2;
       const int chunk = op.HW >= 4096 ? 32 : 16;
       const int quads_ = C / 4;
       const int threads = std::max(256, quads_ * std::max(1, (256 + quads_ - 1) / quads_));      // quads * nsub (<= 640)
-      GNApplyParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, chunk, op.nchunks, op.partial, op.gamma, op.beta, op.eps, op.silu, op.h_out, op.h_out2};
+      GNApplyParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, chunk, op.nchunks, op.partial, op.gamma, op.beta, op.eps, op.silu, op.h_out, op.h_out2, op.stats};
       gn_apply_kernel<<<dim3((op.HW + chunk - 1) / chunk, S), threads, 0, st>>>(p);
       break;
     }

@@ -45,7 +45,7 @@ struct WeightSlot {
   bool loaded = false;
 };
 
-enum OpKind { OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_GEMM, OP_LN, OP_SELF_ATTN, OP_CROSS_ATTN, OP_UPSAMPLE, OP_CAST, OP_CONV_OUT, OP_FEAT_COPY };
+enum OpKind { OP_CONV_IN, OP_GN_STATS, OP_GN_FINALIZE, OP_GN_APPLY, OP_GEMM, OP_LN, OP_SELF_ATTN, OP_CROSS_ATTN, OP_UPSAMPLE, OP_CAST, OP_CONV_OUT, OP_FEAT_COPY };
 
 struct Op {
   OpKind kind;
@@ -56,6 +56,7 @@ struct Op {
   const bf16* h_in = nullptr; bf16* h_out = nullptr; bf16* h_out2 = nullptr;
   const float* gamma = nullptr; const float* beta = nullptr; const float* w = nullptr; const float* b = nullptr;
   float2* partial = nullptr;
+  const float2 *cs1 = nullptr, *cs2 = nullptr; float2* stats = nullptr;     // fused GroupNorm statistics (gemm colstats -> gn_finalize)
   int C1 = 0, C2 = 0, HW = 0, H = 0, W = 0, rows = 0, chunk = 0, nchunks = 0, silu = 0;
   float eps = 0.f;
   size_t count = 0;

@@ -137,6 +137,75 @@ static __global__ void hstep_update_kernel(const UpdateParams p) {
   }
 }
 
+// ---- reward-guided (Langevin) move of the style path (text-guided-n-style/inversion/h_edit.py:150-172) ----------------------
+// x0 = (x_opt - sqrt(1-abar_tt) eps_tar) / sqrt(abar_tt)   (reverse_step_pred_x0, inversion_utils.py:128-140), eps_tar = u + w_tar (c_tar - u)
+struct X0PredParams {
+  const float* eps; const int* iu; const int* ict;
+  float w_tar, sqrt_1m_att, sqrt_att;
+  const float* x_opt; size_t x_stride;
+  float* x0;              // [B][n]
+  int n;
+};
+
+static __global__ void hstep_x0pred_kernel(const X0PredParams p) {
+  const int b = blockIdx.y;
+  const float* u = p.eps + size_t(p.iu[b]) * p.n;
+  const float* ct = p.eps + size_t(p.ict[b]) * p.n;
+  const float* x = p.x_opt + size_t(b) * p.x_stride;
+  float* o = p.x0 + size_t(b) * p.n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+    const float uu = u[i];
+    const float e_tar = uu + p.w_tar * (ct[i] - uu);
+    o[i] = (x[i] - p.sqrt_1m_att * e_tar) / p.sqrt_att;
+  }
+}
+
+// per-image partial sums of corr^2 and of (dL/dx)^2, dL/dx = grad_x0 / sqrt(abar_tt): the two RMS values of rho (h_edit.py:166-167)
+struct GuidNormParams {
+  const float* corr; const float* grad_x0;   // [B][n]
+  float inv_sqrt_att;
+  float2* partial;        // [B][gridDim.x]
+  int n;
+};
+
+static __global__ void hstep_guid_norm_kernel(const GuidNormParams p) {
+  const int b = blockIdx.y;
+  float sc = 0.f, sg = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+    const float c = p.corr[size_t(b) * p.n + i], g = p.grad_x0[size_t(b) * p.n + i] * p.inv_sqrt_att;
+    sc = fmaf(c, c, sc); sg = fmaf(g, g, sg);
+  }
+  __shared__ float s1[32], s2[32];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { sc += __shfl_xor_sync(0xffffffffu, sc, o); sg += __shfl_xor_sync(0xffffffffu, sg, o); }
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = sc; s2[threadIdx.x >> 5] = sg; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { a += s1[w]; c += s2[w]; }
+    p.partial[size_t(b) * gridDim.x + blockIdx.x] = make_float2(a, c);
+  }
+}
+
+// x_opt <- x_opt - rho * dL/dx,   rho = rms(corr) / rms(dL/dx) * weight  (per image; h_edit.py:166-169)
+struct GuidUpdateParams {
+  float* x_opt; size_t x_stride;
+  const float* grad_x0; float inv_sqrt_att, weight;
+  const float2* partial; int nparts;
+  int n;
+};
+
+static __global__ void hstep_guid_update_kernel(const GuidUpdateParams p) {
+  const int b = blockIdx.y;
+  float a = 0.f, c = 0.f;
+  for (int k = 0; k < p.nparts; ++k) { const float2 t = p.partial[size_t(b) * p.nparts + k]; a += t.x; c += t.y; }
+  const float inv_n = 1.f / float(p.n);
+  const float rho = sqrtf(a * inv_n) / sqrtf(c * inv_n) * p.weight;
+  float* x = p.x_opt + size_t(b) * p.x_stride;
+  const float* g = p.grad_x0 + size_t(b) * p.n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) x[i] -= rho * (g[i] * p.inv_sqrt_att);
+}
+
 // LocalBlend (ptp_classes.py:44-72): one CTA per image.  acc holds, per (src|tar, layer, head, pixel), the running sum
 // over steps of sum_j blend_alpha_j * prob_j for the 16x16 cross-attention layers.
 struct BlendParams {

@@ -146,10 +146,11 @@ class UNetEngine:
     def edit(self, xT: torch.Tensor, zs: torch.Tensor, ctx: torch.Tensor, timesteps: Sequence[int], coef: np.ndarray,
              cfg_scales: Sequence[float], plan: Optional[EditPlan], weight_reconstruction: float = 0.1, optimization_steps: int = 1,
              explicit_form: bool = False, schedule: int = 1, trace: bool = False, variant: int = 0, masactrl=None, mos_pull: bool = True,
-             xt_is_pair: bool = False, ctrl_step0: int = 0, blend_state: Optional[torch.Tensor] = None, pnp=None, pre_coeff=None):
+             xt_is_pair: bool = False, ctrl_step0: int = 0, blend_state: Optional[torch.Tensor] = None, pnp=None, pre_coeff=None, guidance=None):
         """xT (B,C,h,w), zs (B,steps,C,h,w), ctx (1+2B,77,D): all on the SAME side (all host or all on this device).
         variant 1 = h_Edit_R_* (no attention control); masactrl = (start_step, start_layer) enables mutual self-attention;
-        pnp = (self_mask, qk_on[steps], feat_on[steps]) runs h_Edit_PnP_implicit (Plug-and-Play q/k and feature injection).
+        pnp = (self_mask, qk_on[steps], feat_on[steps]) runs h_Edit_PnP_implicit (Plug-and-Play q/k and feature injection);
+        guidance = (fn, weight, x0_coef[steps,2]) adds the reward-guided Langevin move: fn(x0 (B,C,h,w) cuda tensor) -> dLoss/dx0.
         Returns (edited, recon[, trace]) on that side."""
         B, steps = xT.shape[0], zs.shape[1]
         out_shape = (B,) + tuple(xT.shape[-3:])
@@ -176,6 +177,29 @@ class UNetEngine:
         a.xt_is_pair, a.ctrl_step0 = int(xt_is_pair), int(ctrl_step0)
         a.blend_state = blend_state.data_ptr() if blend_state is not None else None
         keep = [ts, coef, xT, zs, ctx]
+        cb_error = []
+        if guidance is not None:
+            fn, weight, x0_coef = guidance
+            dev = torch.device("cuda", self.device)
+            x0_buf = torch.empty(out_shape, dtype=torch.float32, device=dev)
+            grad_buf = torch.zeros(out_shape, dtype=torch.float32, device=dev)
+            x0_coef = np.ascontiguousarray(x0_coef, dtype=np.float32)
+            assert x0_coef.shape == (steps, 2)
+
+            def _cb(_user, step, opt_step):
+                try:       # runs on the launching stream (torch's current stream): x0_buf is ready in stream order
+                    g = fn(x0_buf)
+                    grad_buf.copy_(g.reshape(out_shape).to(torch.float32))
+                    return 0
+                except Exception as exc:       # surfaced after the native call returns
+                    cb_error.append(exc)
+                    return -1
+
+            cfn = _lib.GUIDANCE_FN(_cb)
+            keep += [cfn, x0_buf, grad_buf, x0_coef]
+            a.guidance = C.cast(cfn, C.c_void_p)
+            a.guidance_weight, a.x0_coef = float(weight), x0_coef.ctypes.data
+            a.guid_x0, a.guid_grad = x0_buf.data_ptr(), grad_buf.data_ptr()
         if pre_coeff is not None:      # h_Edit_R_implicit on a skipped schedule
             a.pre_step, a.pre_coeff = 1, float(pre_coeff)
         if pnp is not None:
@@ -202,6 +226,9 @@ class UNetEngine:
             a.start_blend, a.blend_th = plan.start_blend, plan.blend_th
         a.edited, a.recon = edited.data_ptr(), recon.data_ptr()
         a.trace = tr.data_ptr() if tr is not None else None
-        _lib.check(self.lib.hedit_edit_p2p(self.handle, C.byref(a), self._stream()), "edit")
+        rc = self.lib.hedit_edit_p2p(self.handle, C.byref(a), self._stream())
+        if cb_error:
+            raise cb_error[0]
+        _lib.check(rc, "edit")
         self.last_stats = {"sample_forwards": int(a.n_sample_forwards), "kernel_launches": int(a.n_kernel_launches)}
         return (edited, recon, tr) if trace else (edited, recon)

@@ -33,7 +33,7 @@ def get_engine(model, max_samples: int = 5, device: int = 0) -> UNetEngine:
 def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Sequence[Sequence[str]], cfg_scales, controllers,
                      eta=1.0, weight_reconstruction=0.075, optimization_steps=1, after_skip_steps=None, is_ddim_inversion=False,
                      explicit_form=False, schedule=1, engine: Optional[UNetEngine] = None, trace=False, variant=0, masactrl=None,
-                     mos_pull=True, pnp=None, pre_coeff=None):
+                     mos_pull=True, pnp=None, pre_coeff=None, guidance=None):
     """B independent edits in one native call.  xT (B,C,h,w); zs (B,steps,C,h,w); prompt_pairs[b] = [src, tar];
     controllers[b] = P2P controller of image b (ours or the reference's) or None for all (P2P off)."""
     B = xT.shape[0]
@@ -49,7 +49,7 @@ def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Se
     if controllers is not None and all(c is not None for c in controllers):
         plan = compile_edit_plan(controllers, steps)
     out = eng.edit(xT, zs[:, :steps], ctx, ts, coef, cfg_scales, plan, weight_reconstruction, optimization_steps, explicit_form, schedule, trace,
-                   variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp, pre_coeff=pre_coeff)
+                   variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp, pre_coeff=pre_coeff, guidance=guidance)
     if plan is not None:
         for c in controllers:       # keep the controller's observable counters consistent with the reference
             c.cur_step = getattr(c, "cur_step", 0) + steps

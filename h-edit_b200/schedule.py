@@ -45,6 +45,15 @@ def step_tables(scheduler, after_skip_steps: int, eta, is_ddim_inversion: bool) 
     return ts + [0], coef
 
 
+def x0_tables(scheduler, after_skip_steps: int) -> np.ndarray:
+    """(sqrt(1 - abar_tt), sqrt(abar_tt)) of every executed step's PREVIOUS timestep tt: the scalars of `reverse_step_pred_x0`
+    (text-guided-n-style/inversion/inversion_utils.py:128-140) as called at text-guided-n-style/inversion/h_edit.py:155."""
+    ac = scheduler.alphas_cumprod.detach().float().cpu()
+    ts = [int(t) for t in scheduler.timesteps[-after_skip_steps:]]
+    tts = ts[1:] + [0]
+    return np.asarray([[float((1 - ac[tt]) ** 0.5), float(ac[tt] ** 0.5)] for tt in tts], dtype=np.float32)
+
+
 def skip_pre_coeff(scheduler, after_skip_steps: int, eta, is_ddim_inversion: bool = False):
     """Coefficient of the extra editing move `h_Edit_R_implicit` makes at the first timestep after skipped steps
     (text-guided/inversion/p2p_h_edit.py:214-218,262-263), or None when nothing was skipped."""

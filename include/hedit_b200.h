@@ -32,6 +32,11 @@ typedef struct hedit_step_coef {
   float sqrt_1m_at, sqrt_at, sqrt_ap, dir, noise, coeff;
 } hedit_step_coef;
 
+/* Reward-model hook of the guided samplers (text-guided-n-style/inversion/h_edit.py:150-172): called once per (timestep, MOS
+ * iteration) on the launching stream with x0 = the Tweedie prediction [B][C][h][w] already written to guid_x0 (device); must
+ * enqueue, on the same stream, work that leaves dLoss/dx0 [B][C][h][w] in guid_grad (device).  Returns 0 on success. */
+typedef int (*hedit_guidance_fn)(void* user, int step, int opt_step);
+
 /* One batched edit = B independent images, each with prompts [src, tar].
  * Replaces the loop-level callables h_Edit_p2p_implicit / h_Edit_p2p_explicit
  * (text-guided/inversion/p2p_h_edit.py:529,380) including the P2P controller hook surface
@@ -87,6 +92,15 @@ typedef struct hedit_edit_args {
    * Requires variant = 1, explicit_form = 0. */
   int32_t pre_step;
   float pre_coeff;
+  /* ---- reward guidance: after the text-guided move of every MOS iteration, x_opt <- x_opt - rho * dLoss/dx with
+   * dLoss/dx = guid_grad / sqrt(abar_tt), rho = rms(corr) / rms(dLoss/dx) * guidance_weight per image (h_edit.py:150-172).
+   * guidance = NULL: off.  x0_coef[steps][2] (host) = (sqrt(1 - abar_tt), sqrt(abar_tt)) of every step's previous timestep. */
+  hedit_guidance_fn guidance;
+  void* guidance_user;
+  float guidance_weight;
+  const float* x0_coef;
+  float* guid_x0;            /* device [B][C][h][w] */
+  float* guid_grad;          /* device [B][C][h][w] */
   /* ---- single-step use (h_edit_step): run `steps` timesteps of a longer schedule and carry the controller state outside */
   int32_t xt_is_pair;        /* 1: xT is [B][2][C][h][w] = (x_orig, x_edit) rows of an edit in progress (requires schedule 0) */
   int32_t ctrl_step0;        /* controller step (AttentionControl.cur_step / LocalBlend.counter) before the first executed timestep;

@@ -108,3 +108,35 @@ def test_hook_matches_reference_controller():
     for k in c.attention_store:
         for x, y in zip(c.attention_store[k], st.attention_store[k]):
             assert torch.equal(x, y)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_clip_gram_restatement_matches_reference_classes():
+    """oracle/clip_visual.py vs the reference's own CLIP class + CLIPEncoder.get_gram_matrix_residual (base_clip.py:55) on the same seeded
+    weights.  Runs in a subprocess: the style tree has its own `inversion` / `p2p` packages that would shadow the text-guided ones."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, importlib, torch
+sys.path[:0] = [%r, %r, "/root/reference/text-guided-n-style"]
+from oracle.clip_visual import tiny_style_encoder
+bc = importlib.import_module("clip_guidance.base_clip")
+cm = importlib.import_module("clip_guidance.clip.model")
+import torchvision
+tiny = tiny_style_encoder()
+enc = bc.CLIPEncoder.__new__(bc.CLIPEncoder); torch.nn.Module.__init__(enc)
+enc.clip_model = cm.CLIP(embed_dim=32, image_resolution=224, vision_layers=3, vision_width=64, vision_patch_size=16, context_length=8,
+                         vocab_size=64, transformer_width=64, transformer_heads=1, transformer_layers=1)
+enc.clip_model.visual.load_state_dict(tiny.visual.state_dict())
+enc.preprocess = torchvision.transforms.Normalize((0.48145466*2-1, 0.4578275*2-1, 0.40821073*2-1), (0.26862954*2, 0.26130258*2, 0.27577711*2))
+enc.ref = tiny.ref
+img = torch.randn(1, 3, 96, 96, generator=torch.Generator().manual_seed(5)).clamp(-1, 1)
+a, b = enc.get_gram_matrix_residual(img), tiny.get_gram_matrix_residual(img)
+err = ((a - b).norm() / a.norm()).item()
+print("GRAM_REL_ERR", err)
+assert err < 1e-5, err
+""" % (root, os.path.join(root, "tests", "refshim"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "GRAM_REL_ERR" in r.stdout, r.stderr[-2000:]

@@ -202,10 +202,84 @@ def run_ddim_inversion(ref, name="tiny_ddim_inversion", T=6):
             "w0": w0, "latent": latent.clone(), "zs": zs.clone(), "latents": torch.cat(latents).clone()}
 
 
+def run_style(name="tiny_style_mos2", T=4, K=2, weight=0.5):
+    """The UNMODIFIED style sampler (text-guided-n-style/inversion/h_edit.py:14 `h_Edit_p2p_implicit(model, image_encoder, ...)`) with the
+    reference's own `CLIPEncoder.get_gram_matrix_residual` (clip_guidance/base_clip.py:55) on a small seeded CLIP ViT and the oracle's
+    small VAE decoder.  Must run in its own process: the style tree has its own `inversion` / `p2p` packages."""
+    import importlib
+    style_root = "/root/reference/text-guided-n-style"
+    for p in (os.path.join(ROOT, "tests", "refshim"), style_root):
+        sys.path.insert(0, p)
+    from oracle.clip_visual import tiny_style_encoder
+    from oracle.vae import AutoencoderKLDecoder, VAEConfig
+    he = importlib.import_module("inversion.h_edit")
+    inv = importlib.import_module("inversion.ddpm_inversion")
+    iu = importlib.import_module("inversion.inversion_utils")
+    pcu = importlib.import_module("p2p.ptp_controller_utils")
+    ptu = importlib.import_module("p2p.ptp_utils")
+    bc = importlib.import_module("clip_guidance.base_clip")
+    clip_model = importlib.import_module("clip_guidance.clip.model")
+    import torchvision
+
+    torch.set_num_threads(os.cpu_count())
+    cfg = UNetConfig.tiny(sample_size=64)
+    model = OraclePipeline(cfg, seed=0)
+    model.vae = AutoencoderKLDecoder(VAEConfig.tiny())
+    model.scheduler.set_timesteps(T)
+    tiny = tiny_style_encoder()
+    # the reference's CLIPEncoder, constructed without its weight download (base_clip.py:31-52), carrying the same seeded weights
+    enc = bc.CLIPEncoder.__new__(bc.CLIPEncoder)
+    torch.nn.Module.__init__(enc)
+    enc.clip_model = clip_model.CLIP(embed_dim=32, image_resolution=224, vision_layers=3, vision_width=64, vision_patch_size=16, context_length=8,
+                                     vocab_size=64, transformer_width=64, transformer_heads=1, transformer_layers=1)
+    enc.clip_model.visual.load_state_dict(tiny.visual.state_dict())
+    enc.preprocess = torchvision.transforms.Normalize((0.48145466 * 2 - 1, 0.4578275 * 2 - 1, 0.40821073 * 2 - 1),
+                                                      (0.26862954 * 2, 0.26130258 * 2, 0.27577711 * 2))
+    enc.ref = tiny.ref
+    for q in enc.parameters():
+        q.requires_grad_(False)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    w0 = torch.randn(1, cfg.in_channels, cfg.sample_size, cfg.sample_size, generator=g) * 0.18215 * 5
+    torch.manual_seed(0)
+    _, zs, wts, _ = inv.inversion_forward_process_ddpm(model, w0, etas=1.0, prog_bar=False, prompt=PROMPTS[0], cfg_scale_src=1.0,
+                                                       num_inference_steps=T)
+    # main_edit.py:179-195: blend words are forced off for the style path; Refine controller
+    controller = pcu.make_controller(prompts=PROMPTS, is_replace_controller=False, cross_replace_steps=0.4, self_replace_steps=0.35,
+                                     blend_word=None, equilizer_params=None, num_steps=T, tokenizer=model.tokenizer, device=model.device)
+    ptu.register_attention_control(model, controller)
+    edited, recon = he.h_Edit_p2p_implicit(model, enc, xT=wts[T], eta=1.0, prompts=PROMPTS, cfg_scales=[1.0, 5.0, 7.5], prog_bar=False,
+                                           zs=zs[:T], controller=controller, weight_edit_clip=weight, optimization_steps=K,
+                                           after_skip_steps=T, is_ddim_inversion=False)
+    # the same run without the reward (image_encoder=None) shows how much of the edit the style term accounts for
+    controller2 = pcu.make_controller(prompts=PROMPTS, is_replace_controller=False, cross_replace_steps=0.4, self_replace_steps=0.35,
+                                      blend_word=None, equilizer_params=None, num_steps=T, tokenizer=model.tokenizer, device=model.device)
+    ptu.register_attention_control(model, controller2)
+    edited_ns, _ = he.h_Edit_p2p_implicit(model, None, xT=wts[T], eta=1.0, prompts=PROMPTS, cfg_scales=[1.0, 5.0, 7.5], prog_bar=False,
+                                          zs=zs[:T], controller=controller2, weight_edit_clip=weight, optimization_steps=K,
+                                          after_skip_steps=T, is_ddim_inversion=False)
+    enc_t = iu.encode_text
+    out = {"meta": dict(name=name, mode="style", T=T, K=K, xa=0.4, sa=0.35, prompts=PROMPTS, cfg_scales=[1.0, 5.0, 7.5], eta=1.0,
+                        weight_edit_clip=weight, is_replace=False, blend=False,
+                        unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
+                                  cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
+                        vae="oracle.vae.AutoencoderKLDecoder(VAEConfig.tiny(), seed 7)", clip="oracle.clip_visual.tiny_style_encoder(seed 11)",
+                        generator="tools/make_golden.py --config style", torch=torch.__version__),
+           "w0": w0, "zs": zs[:T].clone(), "xT": wts[T].clone(),
+           "ctx_uncond": enc_t(model, [""]), "ctx_src": enc_t(model, [PROMPTS[0]]), "ctx_tar": enc_t(model, [PROMPTS[1]]),
+           "edited": edited.detach().clone(), "recon": recon.detach().clone(), "edited_no_style": edited_ns.detach().clone()}
+    path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
+    torch.save(out, path)
+    print(name, "->", path, "|edited| %.4f" % out["edited"].abs().mean().item(),
+          "| style term moved the edit by %.4f (rel)" % ((edited - edited_ns).norm() / edited_ns.norm()).item(), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "variants", "inversion", "pnp", "all"])
+    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "variants", "inversion", "pnp", "style", "all"])
     args = ap.parse_args()
+    if args.config == "style":
+        run_style()
+        return
     ref = load_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     if args.config in ("inversion", "all"):
