@@ -17,6 +17,11 @@ class UNetConfigC(C.Structure):
                 ("cross_attention_dim", C.c_int32), ("norm_groups", C.c_int32), ("ctx_len", C.c_int32)]
 
 
+class VaeConfigC(C.Structure):
+    _fields_ = [("latent_channels", C.c_int32), ("out_channels", C.c_int32), ("block_out_channels", C.c_int32 * 4),
+                ("layers_per_block", C.c_int32), ("norm_groups", C.c_int32)]
+
+
 class StepCoefC(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("sqrt_1m_at", "sqrt_at", "sqrt_ap", "dir", "noise", "coeff")]
 
@@ -63,6 +68,15 @@ SYMBOLS = {
     "hedit_unet_forward": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "hedit_unet_forward_indexed": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _P]),
     "hedit_edit_p2p": (_I, [_P, C.POINTER(EditArgsC), _P]),
+    "hedit_vae_create": (_P, [C.POINTER(VaeConfigC), _I]),
+    "hedit_vae_destroy": (None, [_P]),
+    "hedit_vae_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
+    "hedit_vae_finalize": (_I, [_P]),
+    "hedit_vae_tensor_count": (_I, [_P]),
+    "hedit_vae_tensor_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_int64)]),
+    "hedit_vae_decode": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "hedit_vae_decode_backward": (_I, [_P, _P, _P, _P]),
+    "hedit_vae_last_flops": (C.c_double, [_P]),
     "hedit_op_linear": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "hedit_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "hedit_op_self_attention": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

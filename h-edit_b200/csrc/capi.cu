@@ -9,6 +9,7 @@
 #include "elementwise.cuh"
 #include "engine.h"
 #include "tmap.h"
+#include "vae.h"
 
 namespace hedit {
 int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st);
@@ -29,6 +30,11 @@ struct hedit_engine {
   int device;
   int *d_ctx_idx = nullptr, *d_tidx = nullptr, *d_unit0 = nullptr, *d_unit1 = nullptr, *d_uimg = nullptr;
   int cap = 0;
+};
+
+struct hedit_vae {
+  VaeDecoder* D;
+  int device;
 };
 
 extern "C" {
@@ -184,6 +190,70 @@ int hedit_unet_forward_indexed(hedit_engine* h, const float* x, const float* tim
 int hedit_unet_forward(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int S, float* eps, void* stream) {
   return hedit_unet_forward_indexed(h, x, timesteps, ctx, S, nullptr, S, eps, stream);
 }
+
+// ------------------------------------------------------------------------------------------------ VAE decoder
+hedit_vae* hedit_vae_create(const hedit_vae_config* cfg, int device) {
+  if (!cfg) { fail("null config"); return nullptr; }
+  if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only"); return nullptr; }
+  VaeCfg c;
+  c.latent_ch = cfg->latent_channels; c.out_ch = cfg->out_channels; c.layers = cfg->layers_per_block; c.groups = cfg->norm_groups;
+  for (int i = 0; i < 4; ++i) c.boc[i] = cfg->block_out_channels[i];
+  if (c.latent_ch != 4 || c.out_ch > 4 || c.groups > 32) { fail("unsupported VAE config (need 4 latent channels, <= 4 output channels, <= 32 groups)"); return nullptr; }
+  for (int i = 0; i < 4; ++i)
+    if (c.boc[i] % 64 != 0 || c.boc[i] > 2048 || c.boc[i] % c.groups != 0) { fail("VAE block_out_channels must be multiples of 64 (and of the group count), <= 2048"); return nullptr; }
+  hedit_vae* v = new hedit_vae();
+  v->device = device;
+  v->D = new VaeDecoder(c);
+  if (!v->D->ok()) { fail(v->D->error()); delete v->D; delete v; return nullptr; }
+  return v;
+}
+void hedit_vae_destroy(hedit_vae* v) {
+  if (!v) return;
+  cudaSetDevice(v->device);
+  delete v->D;
+  delete v;
+}
+int hedit_vae_load_tensor(hedit_vae* v, const char* name, const float* data, const int64_t* dims, int ndim) {
+  if (!v) return fail("null vae");
+  cudaSetDevice(v->device);
+  const int r = v->D->load_tensor(name, data, dims, ndim, 0);
+  if (r) return fail(v->D->error(), r);
+  return 0;
+}
+int hedit_vae_finalize(hedit_vae* v) {
+  if (!v) return fail("null vae");
+  std::string missing;
+  if (v->D->finalize(&missing)) return fail(v->D->error());
+  return 0;
+}
+int hedit_vae_tensor_count(hedit_vae* v) { return v ? v->D->tensor_count() : fail("null vae"); }
+int hedit_vae_tensor_info(hedit_vae* v, int index, char* name_buf, int name_len, int64_t* dims4) {
+  if (!v) return fail("null vae");
+  std::string name; std::vector<int64_t> shape;
+  if (!v->D->tensor_info(index, name, shape)) return fail("tensor index out of range");
+  if (int(name.size()) + 1 > name_len || shape.size() > 4) return fail("tensor_info buffer too small");
+  memcpy(name_buf, name.c_str(), name.size() + 1);
+  for (size_t i = 0; i < shape.size(); ++i) dims4[i] = shape[i];
+  return int(shape.size());
+}
+int hedit_vae_decode(hedit_vae* v, const float* z, float* img, int B, int h, int w, void* stream) {
+  if (!v) return fail("null vae");
+  cudaSetDevice(v->device);
+  if (v->D->decode(z, img, B, h, w, reinterpret_cast<cudaStream_t>(stream))) return fail(v->D->error());
+  return int(v->D->launches());
+}
+int hedit_vae_decode_backward(hedit_vae* v, const float* dimg, float* dz, void* stream) {
+  if (!v) return fail("null vae");
+  cudaSetDevice(v->device);
+  if (v->D->backward(dimg, dz, reinterpret_cast<cudaStream_t>(stream))) return fail(v->D->error());
+  return int(v->D->launches());
+}
+double hedit_vae_last_flops(hedit_vae* v) { return v ? v->D->flops() : 0.0; }
 
 int hedit_edit_p2p(hedit_engine* h, hedit_edit_args* args, void* stream) {
   if (!h || !args) return fail("null engine/args");

@@ -283,10 +283,8 @@ static int pick_bn(int M, int N) {
   return cost(256) < cost(160) ? 256 : 160;
 }
 
-struct ConvGeom { int S, H, W, C; int stride; };   // H,W = OUTPUT dims; C = input channels
-
-static bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode, const ConvGeom* cg, const bf16* Wt, int M, int N,
-                      int Ktot, const GemmEpilogue& ep, std::string& err) {
+bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode, const ConvGeom* cg, const bf16* Wt, int M, int N,
+               int Ktot, const GemmEpilogue& ep, std::string& err, int ldw) {
   memset(&g, 0, sizeof g);
   bn = pick_bn(M, N);
   g.M = M; g.N = N; g.a_mode = a_mode; g.ep = ep;
@@ -297,15 +295,19 @@ static bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode
     ok = make_tmap_bf16(&g.tmA, A, 2, dims, str, box);
   } else {
     const int W = cg->W, H = cg->H, C = cg->C;
-    if (W > 128 || 128 % W != 0 || C % 64 != 0) { err = "conv geometry unsupported (need W | 128, Cin % 64 == 0)"; return false; }
-    const int BH = std::min(H, 128 / W);
-    const int BS = 128 / (W * BH);
+    const bool wide = W > 128;          // one 128-row tile = part of an image row (stride-1 convs only)
+    if ((wide ? (W % 128 != 0 || a_mode != A_CONV3X3) : 128 % W != 0) || C % 64 != 0) {
+      err = "conv geometry unsupported (need W | 128 or 128 | W, Cin % 64 == 0)";
+      return false;
+    }
+    const int BH = wide ? 1 : std::min(H, 128 / W);
+    const int BS = wide ? 1 : 128 / (W * BH);
     if (H % BH != 0) { err = "conv geometry unsupported (H)"; return false; }
     g.conv_W = W; g.conv_H = H; g.conv_cin = C; g.cin_blocks = C / 64;
     if (a_mode == A_CONV3X3) {
       uint64_t dims[4] = {uint64_t(C), uint64_t(W), uint64_t(H), uint64_t(cg->S)};
       uint64_t str[3] = {uint64_t(C) * 2, uint64_t(W) * C * 2, uint64_t(H) * W * C * 2};
-      uint32_t box[4] = {64, uint32_t(W), uint32_t(BH), uint32_t(BS)};
+      uint32_t box[4] = {64, uint32_t(std::min(W, 128)), uint32_t(BH), uint32_t(BS)};
       ok = make_tmap_bf16(&g.tmA, A, 4, dims, str, box);
     } else {
       const int Win = 2 * W, Hin = 2 * H;
@@ -316,7 +318,7 @@ static bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode
     }
   }
   if (!ok) { err = "tensor map (A) encode failed"; return false; }
-  uint64_t dimsB[2] = {uint64_t(Ktot), uint64_t(N)}; uint64_t strB[1] = {uint64_t(Ktot) * 2}; uint32_t boxB[2] = {64, uint32_t(bn / 2)};
+  uint64_t dimsB[2] = {uint64_t(Ktot), uint64_t(N)}; uint64_t strB[1] = {uint64_t(ldw > 0 ? ldw : Ktot) * 2}; uint32_t boxB[2] = {64, uint32_t(bn / 2)};
   if (!make_tmap_bf16(&g.tmB, Wt, 2, dimsB, strB, boxB)) { err = "tensor map (B) encode failed"; return false; }
   return true;
 }

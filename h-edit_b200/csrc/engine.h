@@ -16,6 +16,12 @@ namespace hedit {
 
 typedef op_t bf16;   // historical alias: "the 16-bit operand type"
 
+struct ConvGeom { int S, H, W, C; int stride; };   // H,W = OUTPUT dims; C = input channels
+// D[M][N] = A W^T launch description (TMA maps encoded here).  ldw = row stride of W in elements (0: dense [N][Ktot]).
+bool make_gemm(GemmParams& g, int& bn, const op_t* A, int lda, int a_mode, const ConvGeom* cg, const op_t* Wt, int M, int N, int Ktot,
+               const GemmEpilogue& ep, std::string& err, int ldw = 0);
+cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st);
+
 struct UNetCfg {
   int in_ch = 4, out_ch = 4, sample = 64;
   int boc[4] = {320, 640, 1280, 1280};

@@ -141,11 +141,12 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
     for (int tile = tile0; tile < num_tiles; tile += tstep) {
       const int m0 = tile_m0(tile);
       const int n0 = (tile % n_tiles) * BN;
-      int s0 = 0, y0 = 0;
+      int s0 = 0, y0 = 0, x0 = 0;
       if (p.a_mode != A_LINEAR) {
         const int hw = p.conv_H * p.conv_W;
         s0 = m0 / hw;
         y0 = (m0 % hw) / p.conv_W;
+        x0 = (m0 % hw) % p.conv_W;       // non-zero only for images wider than one 128-row tile (VAE decoder, W = 256 / 512)
       }
       int tap = 0, cb = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -161,13 +162,13 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
             const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             if (p.a_mode == A_LINEAR) tma_load_2d_2sm(sa, &p.tmA, lfull, kb * 64, m0);
-            else if (p.a_mode == A_CONV3X3) tma_load_4d_2sm(sa, &p.tmA, lfull, cb * 64, kx - 1, y0 + ky - 1, s0);
+            else if (p.a_mode == A_CONV3X3) tma_load_4d_2sm(sa, &p.tmA, lfull, cb * 64, x0 + kx - 1, y0 + ky - 1, s0);
             else tma_load_5d_2sm(sa, &p.tmA, lfull, px * p.conv_cin + cb * 64, dx, py, y0 + dy, s0);
             tma_load_2d_2sm(sb, &p.tmB, lfull, kb * 64, n0 + int(rank) * (BN / 2));
           } else {
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             if (p.a_mode == A_LINEAR) tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * 64, m0);
-            else if (p.a_mode == A_CONV3X3) tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * 64, kx - 1, y0 + ky - 1, s0);
+            else if (p.a_mode == A_CONV3X3) tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * 64, x0 + kx - 1, y0 + ky - 1, s0);
             else tma_load_5d(sa, &p.tmA, &full_bar[stage], px * p.conv_cin + cb * 64, dx, py, y0 + dy, s0);
             // the W map's box is BN/2 rows (shared with the pair variant): two loads
             tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
@@ -249,6 +250,9 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
       else if (has_b && has_rv && !has_res && has32 && !has16 && (e.rows_per_group & 31) == 0) mode = 3;
       else if (!has_b && !has_rv && !has_res && !has32 && has16) mode = 4;
       else if (has_b && !has_rv && has_res && !has32 && has16) mode = 5;
+      else if (!has_b && !has_rv && !has_res && has32 && !has16) mode = 6;
+      else if (has_b && !has_rv && !has_res && !has32 && has16) mode = 7;
+      else if (!has_b && !has_rv && has_res && has32 && !has16) mode = 8;
     }
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tstep, ++it) {
@@ -327,7 +331,10 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
             case 2: epi_store_rows<true, false, true, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
             case 3: epi_store_rows<true, true, false, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
             case 4: epi_store_rows<false, false, false, false, true>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
-            default: epi_store_rows<true, false, true, false, true>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
+            case 5: epi_store_rows<true, false, true, false, true>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
+            case 6: epi_store_rows<false, false, false, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
+            case 7: epi_store_rows<true, false, false, false, true>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
+            default: epi_store_rows<false, false, true, true, false>(stg, rq, rr, bb, rvv, rs, o32, l32, o16, l16, cst); break;
           }
         } else {
           // generic path: partial tiles, ragged N, unusual feature combinations

@@ -292,6 +292,13 @@ HEDIT_DEVICE op_t to_op(float x) {
   return __float2half_rn(x);
 #endif
 }
+HEDIT_DEVICE float op_to_float(op_t x) {
+#ifdef HEDIT_OPERAND_BF16
+  return __bfloat162float(x);
+#else
+  return __half2float(x);
+#endif
+}
 HEDIT_DEVICE float2 op2_to_float2(uint32_t u) {
 #ifdef HEDIT_OPERAND_BF16
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));

@@ -147,6 +147,30 @@ int hedit_unet_forward_indexed(hedit_engine* e, const float* x, const float* tim
 /* the whole bridge-sampling loop for a batch of images */
 int hedit_edit_p2p(hedit_engine* e, hedit_edit_args* args, void* stream);
 
+/* ---- VAE decoder: `model.vae.decode(z).sample` (diffusers AutoencoderKL decode direction; text-guided/main_p2p.py:262-275) and the
+ * gradient of a scalar loss on the decoded image with respect to z, which the reference's style path obtains with torch.autograd
+ * through that decode (text-guided-n-style/inversion/h_edit.py:158-164).  Weights are ingested by diffusers parameter name
+ * ("post_quant_conv.weight", "decoder.conv_in.weight", ...), fp32, host or device pointer. */
+typedef struct hedit_vae hedit_vae;
+typedef struct hedit_vae_config {
+  int32_t latent_channels, out_channels;
+  int32_t block_out_channels[4];
+  int32_t layers_per_block, norm_groups;
+} hedit_vae_config;
+hedit_vae* hedit_vae_create(const hedit_vae_config* cfg, int device);
+void hedit_vae_destroy(hedit_vae* v);
+int hedit_vae_load_tensor(hedit_vae* v, const char* name, const float* data, const int64_t* dims, int ndim);
+int hedit_vae_finalize(hedit_vae* v);
+int hedit_vae_tensor_count(hedit_vae* v);
+int hedit_vae_tensor_info(hedit_vae* v, int index, char* name_buf, int name_len, int64_t* dims4);
+/* z [B][latent][h][w] (device fp32, already divided by the scaling factor 0.18215) -> img [B][out][8h][8w] (device fp32).
+ * Returns the number of kernels launched; keeps the activations decode_backward needs until the next decode. */
+int hedit_vae_decode(hedit_vae* v, const float* z, float* img, int B, int h, int w, void* stream);
+/* dimg [B][out][8h][8w] = dLoss/dimg of the last decode -> dz [B][latent][h][w] = dLoss/dz (device fp32) */
+int hedit_vae_decode_backward(hedit_vae* v, const float* dimg, float* dz, void* stream);
+/* floating-point operations of the last decode (+ backward) call, for roofline accounting */
+double hedit_vae_last_flops(hedit_vae* v);
+
 /* ---- single operators, exposed for parity tests (device pointers) ------------------------------------------- */
 /* D[M][N] = A[M][K] W[N][K]^T (+bias) (+residual) -> fp32 and/or 16-bit; A, W in the operand dtype (hedit_operand_dtype) */
 int hedit_op_linear(const void* A_h16, const void* W_h16, const float* bias, const float* residual, float* out_f32, void* out_h16,

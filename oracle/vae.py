@@ -30,8 +30,8 @@ class VAEConfig:
 
     @staticmethod
     def tiny() -> "VAEConfig":
-        """Same topology (3 upsamplers = 8x), narrow: CPU fixtures."""
-        return VAEConfig(block_out_channels=(32, 32, 64, 64))
+        """Same topology (3 upsamplers = 8x), narrow (channel counts stay multiples of 64, the native conv's TMA box): fixtures."""
+        return VAEConfig(block_out_channels=(64, 64, 128, 128))
 
 
 class _Sample:
