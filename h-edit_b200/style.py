@@ -3,9 +3,9 @@
 The text-guided part of every step (two classifier-free-guided UNet calls with P2P injection, h-term move) runs in the native
 batched loop; after each implicit-loop iteration the loop hands the Tweedie prediction x0 to a reward hook and applies the
 Langevin move x <- x - rho * dLoss/dx with fused element kernels (csrc/hstep.cuh: hstep_x0pred / guid_norm / guid_update).
-The reward gradient itself is evaluated through the reference's reward-model protocol: `model.vae.decode(z).sample`
-and `image_encoder.get_gram_matrix_residual(img)` are caller-supplied torch modules differentiated with torch.autograd on the
-same CUDA stream.  (A hand-written VAE-decoder / CLIP forward+backward is the next step for this path; see DESIGN.md.)"""
+The VAE decode of x0 and its backward (the bulk of a Langevin step) run on the native decoder engine (csrc/vae.cu, built from
+`model.vae`'s weights); the small CLIP branch of the reward, `image_encoder.get_gram_matrix_residual(img)`, is the caller's torch
+module (the reference's reward-model protocol) differentiated by torch.autograd on the same CUDA stream."""
 from __future__ import annotations
 
 from typing import Callable, Optional, Sequence
@@ -37,21 +37,64 @@ def clip_gram_guidance(model, image_encoder, autocast: bool = True) -> Callable[
     return fn
 
 
+def get_vae_engine(model, device: int = 0):
+    """One persistent native decoder per pipeline object, built from `model.vae`'s state dict."""
+    from .vae import VaeDecoderEngine
+    eng = getattr(model, "_hedit_b200_vae", None)
+    if eng is None:
+        eng = VaeDecoderEngine.from_vae(model.vae, device=device)
+        model._hedit_b200_vae = eng
+    return eng
+
+
+def clip_gram_guidance_native(vae_engine, image_encoder, vae_batch: int = 2) -> Callable[[torch.Tensor], torch.Tensor]:
+    """Same reward gradient as `clip_gram_guidance`, with the VAE decode and its backward on the native kernels
+    (csrc/vae.cu: ~2.5 TFLOP forward + ~2.5 TFLOP backward per image at 512x512, the dominant cost of a Langevin step); only the
+    small CLIP branch (bicubic resize, 3 ViT blocks, Gram residual norm; ~0.03 TFLOP) is differentiated by torch.autograd.
+    The decoder computes in fp32 with 16-bit tensor-core operands, which is at least the precision of the reference's
+    `autocast("cuda")` decode (h_edit.py:158)."""
+
+    def fn(x0: torch.Tensor) -> torch.Tensor:
+        out = torch.empty_like(x0)
+        for lo in range(0, x0.shape[0], vae_batch):
+            hi = min(x0.shape[0], lo + vae_batch)
+            img = vae_engine.decode_tensor(x0[lo:hi] * (1 / VAE_SCALE))
+            with torch.enable_grad():
+                im = img.detach().requires_grad_(True)
+                total = None
+                for b in range(hi - lo):
+                    loss = torch.linalg.norm(image_encoder.get_gram_matrix_residual(im[b:b + 1]))
+                    total = loss if total is None else total + loss
+                dimg = torch.autograd.grad(outputs=total, inputs=im)[0]
+            out[lo:hi] = vae_engine.backward(dimg) * (1 / VAE_SCALE)
+        return out
+
+    return fn
+
+
 def h_edit_style_batch(model, image_encoder, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Sequence[Sequence[str]], cfg_scales,
                        controllers, eta=1.0, weight_edit_clip=0.55, optimization_steps=1, after_skip_steps=None, is_ddim_inversion=False,
-                       schedule=1, engine=None, autocast=True, guidance_fn: Optional[Callable] = None):
-    """B independent text+style edits in one native call (xT (B,C,h,w) and zs (B,steps,C,h,w) on the GPU)."""
+                       schedule=1, engine=None, autocast=True, guidance_fn: Optional[Callable] = None, native_vae: bool = True):
+    """B independent text+style edits in one native call (xT (B,C,h,w) and zs (B,steps,C,h,w) on the GPU).
+    native_vae = True (default): the VAE decode inside the guidance loop and its backward run on the native decoder engine;
+    False: the whole reward branch is differentiated by torch.autograd through `model.vae` (compat path)."""
     steps = after_skip_steps if after_skip_steps is not None else model.scheduler.num_inference_steps
     guidance = None
     if image_encoder or guidance_fn is not None:
-        fn = guidance_fn if guidance_fn is not None else clip_gram_guidance(model, image_encoder, autocast)
+        if guidance_fn is not None:
+            fn = guidance_fn
+        elif native_vae:
+            fn = clip_gram_guidance_native(get_vae_engine(model, xT.device.index or 0), image_encoder)
+        else:
+            fn = clip_gram_guidance(model, image_encoder, autocast)
         guidance = (fn, weight_edit_clip, x0_tables(model.scheduler, steps))
     return h_edit_p2p_batch(model, xT, zs, prompt_pairs, cfg_scales, controllers, eta, 0.0, optimization_steps, steps, is_ddim_inversion,
                             False, schedule=schedule, engine=engine, mos_pull=False, guidance=guidance)
 
 
 def h_Edit_p2p_implicit(model, image_encoder, xT, eta=1.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None,
-                        weight_edit_clip=0.55, optimization_steps=1, after_skip_steps=100, is_ddim_inversion=False, autocast=True):
+                        weight_edit_clip=0.55, optimization_steps=1, after_skip_steps=100, is_ddim_inversion=False, autocast=True,
+                        native_vae=True):
     """Reference signature (text-guided-n-style/inversion/h_edit.py:14).  Returns (edited, reconstructed), each (1,C,h,w)."""
     assert len(prompts) >= 2, "only support prompt editing"
     dev = xT.device
@@ -59,5 +102,5 @@ def h_Edit_p2p_implicit(model, image_encoder, xT, eta=1.0, prompts="", cfg_scale
     z = zs[:after_skip_steps].reshape(1, after_skip_steps, *xT.shape[-3:]).cuda()
     ctrl = [controller] if (controller is not None and hasattr(controller, "cross_replace_alpha")) else None
     edited, recon = h_edit_style_batch(model, image_encoder, x, z, [prompts[:2]], cfg_scales, ctrl, eta, weight_edit_clip, optimization_steps,
-                                       after_skip_steps, is_ddim_inversion, autocast=autocast)
+                                       after_skip_steps, is_ddim_inversion, autocast=autocast, native_vae=native_vae)
     return edited.to(dev), recon.to(dev)

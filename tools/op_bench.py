@@ -92,6 +92,24 @@ def bench_cross(iters):
         print(f"cross_attn S={S} N={N} H={H} d={d} pairs={pairs}: {ms:.3f} ms  ({items} tile-phases, {ms * 1e-3 * 1.9e9 * 148 / items:.0f} SM-cycles/tile-phase)")
 
 
+def bench_vae(iters):
+    """SD-1.x VAE decoder geometry, 64x64 latent -> 512x512 image: decode and decode+backward (random-init weights)."""
+    import hedit_b200
+    eng = hedit_b200.VaeDecoderEngine(dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2, norm_groups=32))
+    eng.load_random_weights(0)
+    for B in (1, 4):
+        z = torch.randn(B, 4, 64, 64, device=DEV) * 5
+        img = eng.decode_tensor(z)
+        f_fwd = eng.last_stats["flops"]
+        dimg = torch.randn_like(img)
+        eng.backward(dimg)
+        f_all = eng.last_stats["flops"]
+        ms_f = timeit(lambda: eng.decode_tensor(z), iters)
+        ms_fb = timeit(lambda: (eng.decode_tensor(z), eng.backward(dimg)), iters)
+        print(f"vae B={B}: decode {ms_f:.2f} ms ({f_fwd / ms_f / 1e9:.0f} TFLOP/s, {f_fwd / B / 1e12:.3f} TFLOP/image) | decode+backward {ms_fb:.2f} ms "
+              f"({f_all / ms_fb / 1e9:.0f} TFLOP/s) | backward alone ~{ms_fb - ms_f:.2f} ms ({(f_all - f_fwd) / max(ms_fb - ms_f, 1e-6) / 1e9:.0f} TFLOP/s)")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -106,3 +124,5 @@ if __name__ == "__main__":
         bench_conv(a.iters)
     if a.what in ("cross", "all"):
         bench_cross(a.iters)
+    if a.what in ("vae", "all"):
+        bench_vae(a.iters)
