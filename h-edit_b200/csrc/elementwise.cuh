@@ -59,7 +59,8 @@ static __global__ void gn_stats_kernel(const GNStatsParams p) {
 }
 
 // Fused-statistics path: the producing GEMM's epilogue already wrote (sum, sumsq) per 32-row block per column (gemm.cuh colstats);
-// this kernel folds them into (mean, rstd) per (sample, group).  grid (groups, S), 128 threads; fixed summation order.
+// this kernel folds them into (mean, rstd) per (sample, group).  grid (groups, S), a power-of-two block (128..512 threads); fixed
+// summation order.
 struct GNFinalizeParams {
   const float2* cs1; const float2* cs2;   // [S*HW/32][C1], [S*HW/32][C2] (cs2 null when C2 == 0)
   int C1, C2, HW, groups;
@@ -68,19 +69,30 @@ struct GNFinalizeParams {
 };
 
 static __global__ void gn_finalize_kernel(const GNFinalizeParams p) {
-  __shared__ double ssu[128], ssq[128];
+  __shared__ double ssu[512], ssq[512];
   const int C = p.C1 + p.C2, cpg = C / p.groups;
   const int g = blockIdx.x, s = blockIdx.y, nrb = p.HW >> 5;
   const int c0 = g * cpg;
-  float su = 0.f, sq = 0.f;
-  for (int i = threadIdx.x; i < nrb * cpg; i += blockDim.x) {
-    const int rb = i / cpg, c = c0 + (i - rb * cpg);
-    const float2 t = (c < p.C1) ? p.cs1[(size_t(s) * nrb + rb) * p.C1 + c] : p.cs2[(size_t(s) * nrb + rb) * p.C2 + (c - p.C1)];
-    su += t.x; sq += t.y;
+  // thread <-> (channel of the group, row-block lane): a thread walks row blocks of ONE channel, so consecutive threads read
+  // consecutive channels (coalesced over the group's cpg columns) and the index arithmetic stays out of the loop
+  const int lanes = max(1, int(blockDim.x) / cpg);
+  const int cl = threadIdx.x % cpg, rl = threadIdx.x / cpg;
+  float su0 = 0.f, sq0 = 0.f, su1 = 0.f, sq1 = 0.f;
+  if (rl < lanes) {
+    const int c = c0 + cl;
+    const float2* base; int ld;
+    if (c < p.C1) { base = p.cs1 + size_t(s) * nrb * p.C1 + c; ld = p.C1; }
+    else { base = p.cs2 + size_t(s) * nrb * p.C2 + (c - p.C1); ld = p.C2; }
+    int rb = rl;
+    for (; rb + lanes < nrb; rb += 2 * lanes) {
+      const float2 t0 = base[size_t(rb) * ld], t1 = base[size_t(rb + lanes) * ld];
+      su0 += t0.x; sq0 += t0.y; su1 += t1.x; sq1 += t1.y;
+    }
+    if (rb < nrb) { const float2 t0 = base[size_t(rb) * ld]; su0 += t0.x; sq0 += t0.y; }
   }
-  ssu[threadIdx.x] = su; ssq[threadIdx.x] = sq;
+  ssu[threadIdx.x] = double(su0) + double(su1); ssq[threadIdx.x] = double(sq0) + double(sq1);
   __syncthreads();
-  for (int o = 64; o; o >>= 1) {
+  for (int o = blockDim.x >> 1; o; o >>= 1) {
     if (threadIdx.x < o) { ssu[threadIdx.x] += ssu[threadIdx.x + o]; ssq[threadIdx.x] += ssq[threadIdx.x + o]; }
     __syncthreads();
   }

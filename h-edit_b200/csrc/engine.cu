@@ -813,7 +813,7 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
     }
     case OP_GN_FINALIZE: {
       GNFinalizeParams p{op.cs1, op.cs2, op.C1, op.C2, op.HW, c.groups, op.eps, op.stats};
-      gn_finalize_kernel<<<dim3(c.groups, S), 128, 0, st>>>(p);
+      gn_finalize_kernel<<<dim3(c.groups, S), (op.HW >= 16384 ? 512 : 128), 0, st>>>(p);
       break;
     }
     case OP_GN_APPLY: {

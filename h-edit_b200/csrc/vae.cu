@@ -199,7 +199,7 @@ int VaeDecoder::gn_fwd(const float* x, const float2* cs, int S, int HW, int C, c
   if (dry_) return 0;
   if (cs) {
     GNFinalizeParams p{cs, nullptr, C, 0, HW, cfg_.groups, 1e-6f, stats};
-    gn_finalize_kernel<<<dim3(cfg_.groups, S), 128, 0, st_>>>(p);
+    gn_finalize_kernel<<<dim3(cfg_.groups, S), (HW >= 16384 ? 512 : 128), 0, st_>>>(p);
   } else {
     const int chunk = std::max(16, HW / 256);
     GNStatsParams sp{x, nullptr, C, 0, HW, cfg_.groups, chunk, partial};
@@ -225,7 +225,7 @@ int VaeDecoder::gn_bwd(const float* g, const GNSave& sv, const float* add, float
   if (dry_) return 0;
   GNBwdParams p{g, sv.x, sv.C, sv.HW, cfg_.groups, chunk, nch, sv.stats, sv.gamma, sv.beta, sv.silu, partial, red, add, dx, dx16};
   const int quads = sv.C / 4;
-  gn_bwd_stats_kernel<<<dim3(nch, sv.S), std::min(512, ((quads + 31) / 32) * 32), 0, st_>>>(p);
+  gn_bwd_stats_kernel<<<dim3(nch, sv.S), std::min(512, std::max(256, quads * std::max(1, (256 + quads - 1) / quads))), 0, st_>>>(p);
   gn_bwd_reduce_kernel<<<dim3(cfg_.groups, sv.S), 128, 0, st_>>>(partial, red, nch, cfg_.groups, float(1.0 / (double(sv.HW) * (sv.C / cfg_.groups))));
   GNBwdParams q = p; q.chunk = sv.HW >= 4096 ? 32 : 16;
   const int threads = std::max(256, quads * std::max(1, (256 + quads - 1) / quads));

@@ -116,41 +116,49 @@ HEDIT_DEVICE float silu_grad_f(float y) {
   return s * fmaf(y, 1.0f - s, 1.0f);
 }
 
-// grid (nchunks, S); thread <-> channel quad (C <= 2048); fixed-order reductions (no atomics)
+// grid (nchunks, S); blockDim = quads * nsub: thread <-> (channel quad, pixel sub-lane); fixed-order reductions (no atomics)
 static __global__ void gn_bwd_stats_kernel(const GNBwdParams p) {
-  __shared__ float2 csum[2048];
+  __shared__ float2 csum[2048];            // [nsub][C]  (blockDim.x * 4 entries)
   __shared__ float sa[32], sb[32];
   const int quads = p.C >> 2, cpg = p.C / p.groups;
   const int s = blockIdx.y, ch = blockIdx.x;
   const int p0 = ch * p.chunk, p1 = min(p.HW, p0 + p.chunk);
+  const int nsub = max(1, int(blockDim.x) / quads);
   if (threadIdx.x < p.groups) { const float2 t = p.stats[size_t(s) * p.groups + threadIdx.x]; sa[threadIdx.x] = t.x; sb[threadIdx.x] = t.y; }
   __syncthreads();
-  for (int v = threadIdx.x; v < quads; v += blockDim.x) {
+  const int v = threadIdx.x % quads, sub = threadIdx.x / quads;
+  if (sub < nsub) {
     const int c = 4 * v;
     float mean[4], rstd[4], ga[4], be[4], a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 4; ++k) { const int g = (c + k) / cpg; mean[k] = sa[g]; rstd[k] = sb[g]; ga[k] = p.gamma[c + k]; be[k] = p.beta[c + k]; }
     const float* gp = p.g + size_t(s) * p.HW * p.C + c;
     const float* xp = p.x + size_t(s) * p.HW * p.C + c;
-    for (int px = p0; px < p1; ++px) {
+    for (int px = p0 + sub; px < p1; px += 2 * nsub) {
+      const bool two = px + nsub < p1;
       const float4 g4 = *reinterpret_cast<const float4*>(gp + size_t(px) * p.C);
       const float4 x4 = *reinterpret_cast<const float4*>(xp + size_t(px) * p.C);
-      const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+      float4 g5 = make_float4(0.f, 0.f, 0.f, 0.f), x5 = g5;
+      if (two) { g5 = *reinterpret_cast<const float4*>(gp + size_t(px + nsub) * p.C); x5 = *reinterpret_cast<const float4*>(xp + size_t(px + nsub) * p.C); }
+      const float gv[8] = {g4.x, g4.y, g4.z, g4.w, g5.x, g5.y, g5.z, g5.w}, xv[8] = {x4.x, x4.y, x4.z, x4.w, x5.x, x5.y, x5.z, x5.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float xh = (xv[k] - mean[k]) * rstd[k];
-        float d = gv[k] * ga[k];
-        if (p.silu) d *= silu_grad_f(fmaf(xh, ga[k], be[k]));
-        a[k] += d; b[k] = fmaf(d, xh, b[k]);
+      for (int k = 0; k < 8; ++k) {
+        if (k >= 4 && !two) break;
+        const int kk = k & 3;
+        const float xh = (xv[k] - mean[kk]) * rstd[kk];
+        float d = gv[k] * ga[kk];
+        if (p.silu) d *= silu_grad_f(fmaf(xh, ga[kk], be[kk]));
+        a[kk] += d; b[kk] = fmaf(d, xh, b[kk]);
       }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) csum[c + k] = make_float2(a[k], b[k]);
+    for (int k = 0; k < 4; ++k) csum[sub * p.C + c + k] = make_float2(a[k], b[k]);
   }
   __syncthreads();
   if (threadIdx.x < p.groups) {
     float su = 0.f, sq = 0.f;
-    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { su += csum[c].x; sq += csum[c].y; }
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c)
+      for (int u = 0; u < nsub; ++u) { su += csum[u * p.C + c].x; sq += csum[u * p.C + c].y; }
     p.partial[(size_t(s) * p.nchunks + ch) * p.groups + threadIdx.x] = make_float2(su, sq);
   }
 }
