@@ -22,12 +22,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TFLOP_PER_SAMPLE_FORWARD = 0.8033            # SD-1.x UNet, 64x64 latent, 77 ctx tokens
+GEMM_TFLOP_PER_SAMPLE_FORWARD = 2 * (200.16 + 138.42) * 1e-3      # conv3x3 + linear/1x1 GMAC of one sample-forward
 PROMPT_PAIRS = [
     (["a green lizard is sitting on a branch", "a brown lizard is sitting on a branch"], ("lizard", "lizard")),
     (["a cat sitting next to a mirror", "a silver cat sculpture sitting next to a mirror"], ("cat", "cat")),
     (["a photo of a house on a hill", "a photo of a castle on a hill in winter"], ("house", "castle")),
     (["two birds on a wire", "two parrots on a wire"], ("birds", "parrots")),
 ]
+
+
+def ncu_traffic(kernel_prefix):
+    """dram read+write bytes per launch of the dominant kernel from the committed `ncu --set full` capture (tools/ncu_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "ncu_full_summary.json")
+    if not os.path.exists(p):
+        return None
+    for name, d in json.load(open(p)).items():
+        if kernel_prefix in name and "conv" in d.get("file", ""):
+            return d["dram_read_bytes"] + d["dram_write_bytes"]
+    return None
 
 
 def measured_peaks():
@@ -165,18 +177,19 @@ def run_gpu(args, rank, world, local_rank):
     xT_d, zs_d, ctx_d = xT_h.to(dev), zs_h.to(dev), ctx_h.to(dev)
     cfgs = [1.0, 5.0, 7.5]
 
-    def step(host):
+    def step(host, schedule=None):
+        schedule = args.schedule if schedule is None else schedule
         if host:
-            ed, rc = eng.edit(xT_h, zs_h, ctx_h, ts, coef, cfgs, plan, 0.1, 1, False, args.schedule)
+            ed, rc = eng.edit(xT_h, zs_h, ctx_h, ts, coef, cfgs, plan, 0.1, 1, False, schedule)
             ed_dev = ed.to(dev, non_blocking=True) if world > 1 else ed
         else:
-            ed, rc = eng.edit(xT_d, zs_d, ctx_d, ts, coef, cfgs, plan, 0.1, 1, False, args.schedule)
+            ed, rc = eng.edit(xT_d, zs_d, ctx_d, ts, coef, cfgs, plan, 0.1, 1, False, schedule)
             ed_dev = ed
         if world > 1:
             gather_results(ed_dev, B * world)      # the only collective: final result gather over NCCL
         return eng.last_stats
 
-    def timed(host, n):
+    def timed(host, n, schedule=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -184,7 +197,7 @@ def run_gpu(args, rank, world, local_rank):
         e0.record()
         fwd = launches = 0
         for _ in range(n):
-            st = step(host)
+            st = step(host, schedule)
             fwd += st["sample_forwards"]; launches += st["kernel_launches"]
         e1.record()
         torch.cuda.synchronize()
@@ -208,9 +221,26 @@ def run_gpu(args, rank, world, local_rank):
     achieved_tf = fwd * TFLOP_PER_SAMPLE_FORWARD / (ms / 1e3)          # this rank's UNet work / max-over-ranks time
     h2d = (xT_h.numel() + zs_h.numel() + ctx_h.numel()) * 4 + plan.c_base.nbytes + plan.c_tar.nbytes + plan.mapper.nbytes + plan.blend_alpha.nbytes
     d2h = 2 * xT_h.numel() * 4
-    prof = None
-    if args.profile and rank == 0:
-        prof = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(eng.profile_forward(5 * B, 2).items(), key=lambda kv: -kv[1][0])}
+    # opt-in schedule 2 (cfg_src == 1: u + 1*(c-u) == c, 5 UNet sample-forwards per step), reported next to the headline
+    skip = None
+    if args.schedule == 1:
+        ms2, fwd2, _ = timed(False, 1, schedule=2)
+        skip = {"value": B * world / (ms2 / 1e3), "unit": "images/s", "sample_forwards_per_image": fwd2 / B,
+                "note": "schedule 2: same edit up to one fp32 rounding per element of the source-guided noise; not the headline"}
+    # live per-kernel timing (CUDA events around every launch of one UNet forward of 5B samples) -> the dominant kernel's roofline
+    prof = gemm = None
+    if rank == 0:
+        pf = eng.profile_forward(5 * B, 2)
+        prof = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(pf.items(), key=lambda kv: -kv[1][0])}
+        gemm_tags = [k for k in pf if k.startswith(("res.", "tf.", "upsample.conv", "downsample", "conv_out"))]
+        gemm_ms = sum(pf[k][0] for k in gemm_tags)
+        gemm_n = sum(pf[k][1] for k in gemm_tags)
+        total_ms = sum(v[0] for v in pf.values())
+        gemm_tf = 5 * B * GEMM_TFLOP_PER_SAMPLE_FORWARD / (gemm_ms / 1e3)
+        gemm = {"kernel": "gemm_bf16_tcgen05_kernel (implicit-GEMM conv3x3 + linear launches)", "launches_per_forward": gemm_n,
+                "avg_launch_us": 1e3 * gemm_ms / gemm_n, "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
+                "share_of_forward": gemm_ms / total_ms,
+                "algorithmic": "2*M*N*K per launch; 338.58 GMAC per UNet sample-forward over all GEMM launches (SURVEY 8d)"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -225,18 +255,23 @@ def run_gpu(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": "implicit h-Edit-R + P2P (Refine+Reweight+LocalBlend), SD-1.5 UNet geometry random-init, 64x64 latent (512^2), 50 DDIM steps, batch 8/GPU",
                        "global_batch": B * world, "timesteps": T, "optimization_steps": 1,
-                       "schedule": "exact-reuse (7 UNet sample-forwards/step)" if args.schedule == 1 else "reference (9 UNet sample-forwards/step)",
+                       "schedule": {0: "reference (9 UNet sample-forwards/step)", 1: "exact-reuse (7 UNet sample-forwards/step)",
+                                    2: "exact-reuse + skip-uncond at cfg_src=1 (5 UNet sample-forwards/step)"}[args.schedule],
                        "sample_forwards_per_image": fwd / (B * args.steps),
                        "l2": "working set per step (1.7 GB fp16 weights + GBs of activations) >> 126 MB L2; no explicit flush needed"},
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
-                         "peak_source": peak_src,
-                         "note": "achieved = executed UNet sample-forwards x 0.8033 TFLOP / device time of the timed region (per GPU)"},
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                         "traffic": ncu_traffic("gemm_bf16_tcgen05_kernel"), "peak_source": peak_src, "dominant_kernel": gemm,
+                         "note": "achieved = executed UNet sample-forwards x 0.8033 TFLOP / device time of the timed region (per GPU), i.e. the whole "
+                                 "step incl. attention, norms and the h-step kernels; dominant_kernel = the GEMM/conv kernel alone, timed live with CUDA "
+                                 "events around each of its launches; traffic = dram read+write bytes of one conv launch (S=16, 64x64, 320->320: "
+                                 "algorithmic 42 MB in + 84 MB out, L2-absorbed writes) from the committed ncu --set full capture (profiles/)"},
+            "skip_uncond_schedule": skip,
             "cpu_baseline": cpu,
         }
-        if prof:
+        if prof and args.profile:
             line["kernel_breakdown_ms_per_forward"] = prof
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -251,7 +286,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="images per GPU")
     ap.add_argument("--timesteps", type=int, default=50)
-    ap.add_argument("--schedule", type=int, default=1, choices=[0, 1])
+    ap.add_argument("--schedule", type=int, default=1, choices=[0, 1, 2])
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -48,7 +48,9 @@ typedef struct hedit_edit_args {
   int32_t explicit_form;     /* 0: h_Edit_p2p_implicit, 1: h_Edit_p2p_explicit */
   int32_t schedule;          /* 0: the reference's UNet call pattern (9 sample-forwards / step at K=1);
                                 1: exact-reuse merged pattern (7 / step): source-branch outputs of call C are reused
-                                   as the next step's call-A source inputs, calls B and C share one launch */
+                                   as the next step's call-A source inputs, calls B and C share one launch;
+                                2: (opt-in, requires w_src == 1) additionally drops the unconditional forwards that only feed
+                                   u + 1 * (c - u) == c (5 / step); equal to schedule 1 up to one fp32 rounding per element */
   int32_t buffers_on_host;   /* 1: xT, zs, ctx, edited, recon, trace are host pointers (copies are part of the call) */
   int32_t variant;           /* 0: P2P-family samplers (orig and edit rows both denoised: h_Edit_p2p_*, h_Edit_masactrl_implicit);
                                 1: h_Edit_R_implicit / h_Edit_R_explicit (p2p_h_edit.py:162,21): no attention control, both rows are

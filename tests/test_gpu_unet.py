@@ -103,6 +103,16 @@ def test_edit_loop_tiny_reference_schedule():
     assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
 
 
+def test_edit_loop_tiny_skip_uncond_schedule():
+    """schedule 2 (opt-in for cfg_src == 1): u + 1 * (c - u) == c, so 5 UNet sample-forwards per step instead of 7."""
+    r_ed, r_rc, r_w0, st = _run_golden("tiny_refine_blend", schedule=2)
+    assert st["sample_forwards"] == 10 * 5
+    assert r_rc < TOL_LOOP and r_w0 < TOL_LOOP and r_ed < TOL_LOOP
+    r_ed, r_rc, _, st = _run_golden("tiny_replace_mos2", schedule=2)
+    assert st["sample_forwards"] == 6 * (1 + 4 * 2)
+    assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
+
+
 def test_edit_loop_tiny_replace_mos2():
     r_ed, r_rc, r_w0, st = _run_golden("tiny_replace_mos2")
     assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
