@@ -22,6 +22,10 @@ class VaeConfigC(C.Structure):
                 ("layers_per_block", C.c_int32), ("norm_groups", C.c_int32)]
 
 
+class ClipConfigC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("resolution", "patch", "width", "heads", "layers")]
+
+
 class StepCoefC(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("sqrt_1m_at", "sqrt_at", "sqrt_ap", "dir", "noise", "coeff")]
 
@@ -77,6 +81,13 @@ SYMBOLS = {
     "hedit_vae_decode": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "hedit_vae_decode_backward": (_I, [_P, _P, _P, _P]),
     "hedit_vae_last_flops": (C.c_double, [_P]),
+    "hedit_clip_create": (_P, [C.POINTER(ClipConfigC), _I]),
+    "hedit_clip_destroy": (None, [_P]),
+    "hedit_clip_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
+    "hedit_clip_finalize": (_I, [_P]),
+    "hedit_clip_set_reference": (_I, [_P, _P, _P]),
+    "hedit_clip_gram_loss": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "hedit_clip_gram_backward": (_I, [_P, _P, _P]),
     "hedit_op_linear": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "hedit_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "hedit_op_self_attention": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -10,6 +10,7 @@
 #include "engine.h"
 #include "tmap.h"
 #include "vae.h"
+#include "clip.h"
 
 namespace hedit {
 int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st);
@@ -30,6 +31,11 @@ struct hedit_engine {
   int device;
   int *d_ctx_idx = nullptr, *d_tidx = nullptr, *d_unit0 = nullptr, *d_unit1 = nullptr, *d_uimg = nullptr;
   int cap = 0;
+};
+
+struct hedit_clip {
+  ClipGram* C;
+  int device;
 };
 
 struct hedit_vae {
@@ -254,6 +260,67 @@ int hedit_vae_decode_backward(hedit_vae* v, const float* dimg, float* dz, void* 
   return int(v->D->launches());
 }
 double hedit_vae_last_flops(hedit_vae* v) { return v ? v->D->flops() : 0.0; }
+
+// ------------------------------------------------------------------------------------------------ CLIP-Gram style reward
+hedit_clip* hedit_clip_create(const hedit_clip_config* cfg, int device) {
+  if (!cfg) { fail("null config"); return nullptr; }
+  if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only"); return nullptr; }
+  ClipCfg c;
+  c.resolution = cfg->resolution; c.patch = cfg->patch; c.width = cfg->width; c.heads = cfg->heads; c.layers = cfg->layers;
+  const int G = c.patch > 0 ? c.resolution / c.patch : 0;
+  if (c.patch < 1 || c.resolution % c.patch || c.heads < 1 || c.width != 64 * c.heads || G * G + 1 > 256 || c.layers < 1 || c.width % 64 ||
+      (3 * c.patch * c.patch) % 8) {
+    fail("unsupported CLIP config (need a ViT with head dim 64, <= 256 tokens, width % 64 == 0)");
+    return nullptr;
+  }
+  hedit_clip* h = new hedit_clip();
+  h->device = device;
+  h->C = new ClipGram(c);
+  if (!h->C->ok()) { fail(h->C->error()); delete h->C; delete h; return nullptr; }
+  return h;
+}
+void hedit_clip_destroy(hedit_clip* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  delete c->C;
+  delete c;
+}
+int hedit_clip_load_tensor(hedit_clip* c, const char* name, const float* data, const int64_t* dims, int ndim) {
+  if (!c) return fail("null clip");
+  cudaSetDevice(c->device);
+  const int r = c->C->load_tensor(name, data, dims, ndim, 0);
+  if (r < 0) return fail(c->C->error(), r);
+  return r;
+}
+int hedit_clip_finalize(hedit_clip* c) {
+  if (!c) return fail("null clip");
+  std::string missing;
+  if (c->C->finalize(&missing)) return fail(c->C->error());
+  return 0;
+}
+int hedit_clip_set_reference(hedit_clip* c, const float* ref, void* stream) {
+  if (!c) return fail("null clip");
+  cudaSetDevice(c->device);
+  if (c->C->set_reference(ref, reinterpret_cast<cudaStream_t>(stream))) return fail(c->C->error());
+  return 0;
+}
+int hedit_clip_gram_loss(hedit_clip* c, const float* img, int B, int H, int W, float* loss, void* stream) {
+  if (!c) return fail("null clip");
+  cudaSetDevice(c->device);
+  if (c->C->forward(img, B, H, W, loss, reinterpret_cast<cudaStream_t>(stream))) return fail(c->C->error());
+  return int(c->C->launches());
+}
+int hedit_clip_gram_backward(hedit_clip* c, float* dimg, void* stream) {
+  if (!c) return fail("null clip");
+  cudaSetDevice(c->device);
+  if (c->C->backward(dimg, reinterpret_cast<cudaStream_t>(stream))) return fail(c->C->error());
+  return int(c->C->launches());
+}
 
 int hedit_edit_p2p(hedit_engine* h, hedit_edit_args* args, void* stream) {
   if (!h || !args) return fail("null engine/args");

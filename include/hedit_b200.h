@@ -173,6 +173,27 @@ int hedit_vae_decode_backward(hedit_vae* v, const float* dimg, float* dz, void* 
 /* floating-point operations of the last decode (+ backward) call, for roofline accounting */
 double hedit_vae_last_flops(hedit_vae* v);
 
+/* ---- CLIP-Gram style reward: `torch.linalg.norm(image_encoder.get_gram_matrix_residual(img))` and its gradient with respect to
+ * img (text-guided-n-style/clip_guidance/base_clip.py:55-66 over clip/model.py:339-359; differentiated by torch.autograd at
+ * text-guided-n-style/inversion/h_edit.py:161-164).  Weights = state dict of the CLIP image tower (`clip_model.visual`: "conv1.weight",
+ * "class_embedding", "positional_embedding", "ln_pre.*", "transformer.resblocks.{i}.*" for i < layers), fp32.  ViT variants with head
+ * dim 64 and at most 256 tokens (ViT-B/16 at 224 px: 197). */
+typedef struct hedit_clip hedit_clip;
+typedef struct hedit_clip_config {
+  int32_t resolution, patch, width, heads, layers;   /* layers = blocks evaluated: features[2] -> 3 */
+} hedit_clip_config;
+hedit_clip* hedit_clip_create(const hedit_clip_config* cfg, int device);
+void hedit_clip_destroy(hedit_clip* c);
+/* returns 1 (ignored) for tensors this path does not use (later blocks, ln_post, proj) */
+int hedit_clip_load_tensor(hedit_clip* c, const char* name, const float* data, const int64_t* dims, int ndim);
+int hedit_clip_finalize(hedit_clip* c);
+/* ref [1][3][resolution][resolution]: the CLIP-normalised style image (CLIPEncoder.ref, base_clip.py:43-52), device fp32 */
+int hedit_clip_set_reference(hedit_clip* c, const float* ref, void* stream);
+/* img [B][3][H][W] in [-1,1] (device fp32) -> loss[B] (device fp32); keeps the activations gram_backward needs */
+int hedit_clip_gram_loss(hedit_clip* c, const float* img, int B, int H, int W, float* loss, void* stream);
+/* dimg [B][3][H][W] = d loss[b] / d img[b] of the last gram_loss call */
+int hedit_clip_gram_backward(hedit_clip* c, float* dimg, void* stream);
+
 /* ---- single operators, exposed for parity tests (device pointers) ------------------------------------------- */
 /* D[M][N] = A[M][K] W[N][K]^T (+bias) (+residual) -> fp32 and/or 16-bit; A, W in the operand dtype (hedit_operand_dtype) */
 int hedit_op_linear(const void* A_h16, const void* W_h16, const float* bias, const float* residual, float* out_f32, void* out_h16,

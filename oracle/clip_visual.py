@@ -67,6 +67,13 @@ class VisionTransformer(nn.Module):
         return feats
 
 
+class _ClipModelView:
+    """`.clip_model.visual` access path of the reference's CLIPEncoder (base_clip.py:33)."""
+
+    def __init__(self, visual):
+        self.visual = visual
+
+
 class GramStyleEncoder(nn.Module):
     """`image_encoder` of the style sampler: get_gram_matrix_residual(img in [-1,1], NCHW) -> (D,D) (base_clip.py:55-66)."""
 
@@ -76,6 +83,7 @@ class GramStyleEncoder(nn.Module):
     def __init__(self, visual: VisionTransformer, ref: torch.Tensor):
         super().__init__()
         self.visual = visual
+        self.clip_model = _ClipModelView(visual)
         self.register_buffer("ref", ref)                                   # (1,3,224,224), already CLIP-normalised (:43-52)
         self.register_buffer("mean", torch.tensor(self.MEAN).reshape(1, 3, 1, 1))
         self.register_buffer("std", torch.tensor(self.STD).reshape(1, 3, 1, 1))

@@ -32,8 +32,8 @@ def _setup():
     return g, meta, model, enc
 
 
-@pytest.mark.parametrize("native_vae", [True, False])
-def test_style_sampler_matches_reference_golden(native_vae):
+@pytest.mark.parametrize("native_vae,native_clip", [(True, True), (True, False), (False, False)])
+def test_style_sampler_matches_reference_golden(native_vae, native_clip):
     g, meta, model, enc = _setup()
     T, K = meta["T"], meta["K"]
     ctrl = hedit_b200.make_controller(meta["prompts"], False, meta["xa"], meta["sa"], blend_word=None, equilizer_params=None, num_steps=T,
@@ -42,11 +42,11 @@ def test_style_sampler_matches_reference_golden(native_vae):
     ed, rc = hedit_b200.style.h_Edit_p2p_implicit(model, enc, xT=g["xT"].cuda(), eta=meta["eta"], prompts=meta["prompts"],
                                                   cfg_scales=meta["cfg_scales"], zs=g["zs"].cuda(), controller=ctrl,
                                                   weight_edit_clip=meta["weight_edit_clip"], optimization_steps=K, after_skip_steps=T,
-                                                  is_ddim_inversion=False, autocast=False, native_vae=native_vae)
+                                                  is_ddim_inversion=False, autocast=False, native_vae=native_vae, native_clip=native_clip)
     r_ed, m_ed = rel_err(ed.cpu(), g["edited"])
     r_rc, m_rc = rel_err(rc.cpu(), g["recon"])
     r_ns, _ = rel_err(ed.cpu(), g["edited_no_style"])
-    print(f"style (native VAE {native_vae}): edited rel {r_ed:.3e} max {m_ed:.3e} | recon rel {r_rc:.3e} | distance to the no-style edit {r_ns:.3e}")
+    print(f"style (native VAE {native_vae}, native CLIP {native_clip}): edited rel {r_ed:.3e} max {m_ed:.3e} | recon rel {r_rc:.3e} | distance to the no-style edit {r_ns:.3e}")
     assert r_ed < TOL_STYLE and r_rc < TOL_STYLE
     assert r_ns > 5 * TOL_STYLE            # the reward term is a large part of the result, so the check above is meaningful
     # without an image encoder the sampler reduces to the text-guided loop (h_edit.py:157 `if image_encoder:`)
