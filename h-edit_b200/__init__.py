@@ -16,6 +16,8 @@ from .samplers import (HEditStepper, h_edit_step, MutualSelfAttentionControl, en
 from . import style  # noqa: F401,E402
 from .vae import VaeDecoderEngine, vae_config_of  # noqa: F401,E402
 from .clip_gram import ClipGramEngine  # noqa: F401,E402
+from . import face  # noqa: F401,E402
+from .face import FaceUNetEngine  # noqa: F401,E402
 from .inversion import ddim_inversion, inversion_forward_process_ddpm, sample_xts_from_x0  # noqa: F401,E402
 
 __all__ = ["inversion_forward_process_ddpm", "ddim_inversion", "UNetEngine", "unet_config_of", "make_controller", "register_attention_control", "compile_edit_plan",

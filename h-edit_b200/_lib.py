@@ -26,6 +26,25 @@ class ClipConfigC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("resolution", "patch", "width", "heads", "layers")]
 
 
+class FaceConfigC(C.Structure):
+    _fields_ = [("ch", C.c_int32), ("n_levels", C.c_int32), ("ch_mult", C.c_int32 * 8), ("num_res_blocks", C.c_int32), ("attn_resolution", C.c_int32),
+                ("image_size", C.c_int32), ("in_channels", C.c_int32), ("out_ch", C.c_int32)]
+
+
+class FaceStepCoefC(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("t", "tm1", "sqrt_1m_at", "sqrt_at", "sqrt_1m_atm1", "sqrt_atm1", "c2", "noise")]
+
+
+REWARD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int)
+
+
+class FaceArgsC(C.Structure):
+    _fields_ = [("B", C.c_int32), ("steps", C.c_int32), ("opt_steps", C.c_int32), ("xT", C.c_void_p), ("zs", C.c_void_p), ("coef", C.c_void_p),
+                ("weight", C.c_float), ("mask", C.c_void_p), ("use_id", C.c_int32), ("use_lpips", C.c_int32), ("reward", C.c_void_p),
+                ("reward_user", C.c_void_p), ("reward_x0", C.c_void_p), ("reward_grad", C.c_void_p), ("edited", C.c_void_p),
+                ("n_sample_forwards", C.c_int64), ("n_kernel_launches", C.c_int64)]
+
+
 class StepCoefC(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("sqrt_1m_at", "sqrt_at", "sqrt_ap", "dir", "noise", "coeff")]
 
@@ -88,6 +107,14 @@ SYMBOLS = {
     "hedit_clip_set_reference": (_I, [_P, _P, _P]),
     "hedit_clip_gram_loss": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "hedit_clip_gram_backward": (_I, [_P, _P, _P]),
+    "hedit_face_create": (_P, [C.POINTER(FaceConfigC), _I]),
+    "hedit_face_destroy": (None, [_P]),
+    "hedit_face_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
+    "hedit_face_finalize": (_I, [_P]),
+    "hedit_face_tensor_count": (_I, [_P]),
+    "hedit_face_tensor_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_int64)]),
+    "hedit_face_unet_forward": (_I, [_P, _P, _P, _I, _P, _P]),
+    "hedit_face_edit": (_I, [_P, C.POINTER(FaceArgsC), _P]),
     "hedit_op_linear": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "hedit_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "hedit_op_self_attention": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -11,9 +11,11 @@
 #include "tmap.h"
 #include "vae.h"
 #include "clip.h"
+#include "face.h"
 
 namespace hedit {
 int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st);
+int run_face_edit(FaceUNet& U, hedit_face_args& a, cudaStream_t st);
 cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st);
 cudaError_t launch_self_attn(const AttnParams& a, int dch, int S, cudaStream_t st);
 cudaError_t launch_cross_attn(const AttnParams& a, int dch, int units, cudaStream_t st);
@@ -31,6 +33,11 @@ struct hedit_engine {
   int device;
   int *d_ctx_idx = nullptr, *d_tidx = nullptr, *d_unit0 = nullptr, *d_unit1 = nullptr, *d_uimg = nullptr;
   int cap = 0;
+};
+
+struct hedit_face {
+  FaceUNet* U;
+  int device;
 };
 
 struct hedit_clip {
@@ -260,6 +267,73 @@ int hedit_vae_decode_backward(hedit_vae* v, const float* dimg, float* dz, void* 
   return int(v->D->launches());
 }
 double hedit_vae_last_flops(hedit_vae* v) { return v ? v->D->flops() : 0.0; }
+
+// ------------------------------------------------------------------------------------------------ face swapping
+hedit_face* hedit_face_create(const hedit_face_config* cfg, int device) {
+  if (!cfg) { fail("null config"); return nullptr; }
+  if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only"); return nullptr; }
+  FaceCfg c;
+  c.ch = cfg->ch; c.nlevels = cfg->n_levels; c.nres = cfg->num_res_blocks; c.attn_res = cfg->attn_resolution; c.resolution = cfg->image_size;
+  c.in_ch = cfg->in_channels; c.out_ch = cfg->out_ch;
+  if (c.nlevels < 1 || c.nlevels > 8 || c.ch % 64 || c.in_ch > 4 || c.out_ch > 4 || c.nres < 1) { fail("unsupported face UNet config"); return nullptr; }
+  for (int i = 0; i < 8; ++i) c.mult[i] = i < c.nlevels ? cfg->ch_mult[i] : 0;
+  const int low = c.resolution >> (c.nlevels - 1);
+  if ((c.resolution > 128 ? c.resolution % 128 : 128 % c.resolution) || low < 1 || (low << (c.nlevels - 1)) != c.resolution || (low * low) % 32) {
+    fail("face UNet image size must divide 128 or be a multiple of it, and the coarsest level must keep >= 32 pixels");
+    return nullptr;
+  }
+  hedit_face* h = new hedit_face();
+  h->device = device;
+  h->U = new FaceUNet(c);
+  if (!h->U->ok()) { fail(h->U->error()); delete h->U; delete h; return nullptr; }
+  return h;
+}
+void hedit_face_destroy(hedit_face* f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  delete f->U;
+  delete f;
+}
+int hedit_face_load_tensor(hedit_face* f, const char* name, const float* data, const int64_t* dims, int ndim) {
+  if (!f) return fail("null face engine");
+  cudaSetDevice(f->device);
+  const int r = f->U->load_tensor(name, data, dims, ndim, 0);
+  if (r) return fail(f->U->error(), r);
+  return 0;
+}
+int hedit_face_finalize(hedit_face* f) {
+  if (!f) return fail("null face engine");
+  std::string missing;
+  if (f->U->finalize(&missing)) return fail(f->U->error());
+  return 0;
+}
+int hedit_face_tensor_count(hedit_face* f) { return f ? f->U->tensor_count() : fail("null face engine"); }
+int hedit_face_tensor_info(hedit_face* f, int index, char* name_buf, int name_len, int64_t* dims4) {
+  if (!f) return fail("null face engine");
+  std::string name; std::vector<int64_t> shape;
+  if (!f->U->tensor_info(index, name, shape)) return fail("tensor index out of range");
+  if (int(name.size()) + 1 > name_len || shape.size() > 4) return fail("tensor_info buffer too small");
+  memcpy(name_buf, name.c_str(), name.size() + 1);
+  for (size_t i = 0; i < shape.size(); ++i) dims4[i] = shape[i];
+  return int(shape.size());
+}
+int hedit_face_unet_forward(hedit_face* f, const float* x, const float* t, int S, float* eps, void* stream) {
+  if (!f) return fail("null face engine");
+  cudaSetDevice(f->device);
+  if (f->U->forward(x, t, eps, S, reinterpret_cast<cudaStream_t>(stream))) return fail(f->U->error());
+  return int(f->U->launches());
+}
+int hedit_face_edit(hedit_face* f, hedit_face_args* args, void* stream) {
+  if (!f || !args) return fail("null face engine / args");
+  cudaSetDevice(f->device);
+  if (run_face_edit(*f->U, *args, reinterpret_cast<cudaStream_t>(stream))) return fail(f->U->error().empty() ? "face edit failed" : f->U->error());
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ CLIP-Gram style reward
 hedit_clip* hedit_clip_create(const hedit_clip_config* cfg, int device) {

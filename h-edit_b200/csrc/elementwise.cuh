@@ -361,7 +361,8 @@ static __global__ void conv_out_kernel(const op_t* __restrict__ x, const float* 
 
 // ------------------------------------------------------------------------------------------------ small linear (time MLP)
 // out[r][n] = act_out( sum_k act_in(in[r][k]) * W[n][k] + b[n] ), rows <= 64.  One warp per output feature n.
-// in_mode: 0 = as is, 1 = SiLU, 2 = sinusoidal timestep embedding of in[r][0] (flip_sin_to_cos, freq shift 0; K = dim).
+// in_mode: 0 = as is, 1 = SiLU, 2 = sinusoidal timestep embedding of in[r][0] (flip_sin_to_cos, freq shift 0; K = dim),
+//          3 = DDPM sinusoidal embedding [sin | cos] with frequencies exp(-ln(1e4) f / (K/2 - 1)) (face-swapping/diffusion/diffusion.py:6-24).
 static __global__ void small_linear_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ W, const float* __restrict__ b,
                                     float* __restrict__ out, int ld_out, int rows, int N, int K, int in_mode, int out_silu) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -377,6 +378,11 @@ static __global__ void small_linear_kernel(const float* __restrict__ in, int ld_
         const int f = (k < half) ? k : k - half;
         const float ang = in[r * ld_in] * expf(-9.210340371976184f * float(f) / float(half));
         a = (k < half) ? cosf(ang) : sinf(ang);
+      } else if (in_mode == 3) {
+        const int half = K >> 1;
+        const int f = (k < half) ? k : k - half;
+        const float ang = in[r * ld_in] * expf(-9.210340371976184f * float(f) / float(half - 1));
+        a = (k < half) ? sinf(ang) : cosf(ang);
       } else {
         a = in[size_t(r) * ld_in + k];
         if (in_mode == 1) a = silu_f(a);

@@ -303,7 +303,7 @@ bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode, const
     const int BH = wide ? 1 : std::min(H, 128 / W);
     const int BS = wide ? 1 : 128 / (W * BH);
     if (H % BH != 0) { err = "conv geometry unsupported (H)"; return false; }
-    g.conv_W = W; g.conv_H = H; g.conv_cin = C; g.cin_blocks = C / 64;
+    g.conv_W = W; g.conv_H = H; g.conv_cin = C; g.cin_blocks = C / 64; g.conv_pad01 = cg->pad01;
     if (a_mode == A_CONV3X3) {
       uint64_t dims[4] = {uint64_t(C), uint64_t(W), uint64_t(H), uint64_t(cg->S)};
       uint64_t str[3] = {uint64_t(C) * 2, uint64_t(W) * C * 2, uint64_t(H) * W * C * 2};

@@ -16,7 +16,7 @@ namespace hedit {
 
 typedef op_t bf16;   // historical alias: "the 16-bit operand type"
 
-struct ConvGeom { int S, H, W, C; int stride; };   // H,W = OUTPUT dims; C = input channels
+struct ConvGeom { int S, H, W, C; int stride; int pad01; };   // H,W = OUTPUT dims; C = input channels; pad01: stride-2 convs padded (0,1,0,1)
 // D[M][N] = A W^T launch description (TMA maps encoded here).  ldw = row stride of W in elements (0: dense [N][Ktot]).
 bool make_gemm(GemmParams& g, int& bn, const op_t* A, int lda, int a_mode, const ConvGeom* cg, const op_t* Wt, int M, int N, int Ktot,
                const GemmEpilogue& ep, std::string& err, int ldw = 0);

@@ -34,6 +34,7 @@ struct GemmParams {
   CUtensorMap tmA, tmB;
   int M, N, num_kb;
   int a_mode, conv_W, conv_H, conv_cin, cin_blocks;
+  int conv_pad01;           // A_CONV3X3S2 only: 0 = padding 1 on every side (SD downsampler); 1 = padding (0,1,0,1) (DDPM downsampler)
   GemmEpilogue ep;
 };
 
@@ -155,8 +156,9 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           const int ky = tap / 3, kx = tap - ky * 3;
-          const int px = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
-          const int py = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
+          // stride 2: input x = 2X + kx - pad_left -> (parity, coarse offset) in the space-to-depth view
+          const int px = p.conv_pad01 ? (kx == 1 ? 1 : 0) : (kx == 1 ? 0 : 1), dx = p.conv_pad01 ? (kx == 2 ? 1 : 0) : (kx == 0 ? -1 : 0);
+          const int py = p.conv_pad01 ? (ky == 1 ? 1 : 0) : (ky == 1 ? 0 : 1), dy = p.conv_pad01 ? (ky == 2 ? 1 : 0) : (ky == 0 ? -1 : 0);
           if (CLUSTER) {
             // both CTAs' bytes are reported to the leader's barrier (the leader's MMA consumes both halves)
             const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);

@@ -1,0 +1,55 @@
+// Shared executor pieces of the convolutional engines that run outside the UNet's static plan (VAE decoder, face-swapping DDPM UNet):
+// a bump arena with a sizing ("dry") pass, GEMM / implicit-GEMM conv launch helpers and the GroupNorm forward with statistics taken
+// from the producing GEMM's epilogue.
+#pragma once
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <string>
+
+#include "engine.h"
+
+namespace hedit {
+
+class NetExec {
+ public:
+  std::string err_;
+  long launches() const { return launches_; }
+  double flops() const { return flops_; }
+  size_t arena_bytes() const { return arena_bytes_; }
+
+ protected:
+  ~NetExec() { if (arena_) cudaFree(arena_); }
+  template <typename T> T* A(size_t n) {
+    const size_t bytes = (n * sizeof(T) + 1023) & ~size_t(1023);
+    const size_t off = top_;
+    top_ += bytes;
+    peak_ = std::max(peak_, top_);
+    return reinterpret_cast<T*>(arena_ + off);      // arena_ is null in the sizing pass: offsets only, nothing is launched
+  }
+  // (re)allocate the arena so that `need` bytes fit
+  int reserve(size_t need, const char* what);
+  int gemm(const op_t* Ain, int lda, int mode, const ConvGeom* cg, const op_t* Wt, int M, int N, int K, const GemmEpilogue& ep, int ldw = 0);
+  // 3x3 conv, stride 1 pad 1, or stride 2 (H, W = OUTPUT dims) with padding 1 / (0,1,0,1)
+  int conv3(const op_t* x, const op_t* w, int S, int H, int W, int cin, int cout, GemmEpilogue ep, int stride = 1, int pad01 = 0);
+  float2* colstats_for(int M, int N, int HW);
+  // GroupNorm(+SiLU) of the channel concatenation [x1 | x2] (x2 may be null) -> 16-bit operand (+ raw 16-bit copy); statistics from
+  // the producers' colstats when both are present, else a separate statistics pass.  *stats_out = (mean, rstd) per (sample, group).
+  int gn_fwd(const float* x1, const float2* cs1, int C1, const float* x2, const float2* cs2, int C2, int S, int HW, const float* g,
+             const float* b, float eps, int silu, op_t* out, op_t* raw, float2** stats_out);
+
+  // GroupNorm -> fused q|k|v projection -> single-head attention over N tokens (scores and P.V on the GEMM, probabilities
+  // materialised per sample) -> output projection + residual.  Optional outputs feed a backward pass.
+  int attn1h_fwd(const float* x, const float2* cs_x, int S, int N, int C, const float* gng, const float* gnb, float eps, const op_t* w_qkv,
+                 const float* b_qkv, const op_t* w_o, const float* b_o, float** out, float2** cs_out, float2** gn_stats_out = nullptr,
+                 const op_t** qkv_out = nullptr, const op_t** P_out = nullptr);
+
+  int groups_ = 32;
+  uint8_t* arena_ = nullptr;
+  size_t arena_bytes_ = 0, top_ = 0, peak_ = 0;
+  bool dry_ = false;
+  cudaStream_t st_ = 0;
+  long launches_ = 0;
+  double flops_ = 0;
+};
+
+}  // namespace hedit

@@ -67,6 +67,7 @@ void VaeDecoder::reg_res(const std::string& name, int cin, int cout, ResW& r) {
 }
 
 VaeDecoder::VaeDecoder(const VaeCfg& cfg) : cfg_(cfg) {
+  groups_ = cfg.groups;
   const int L = cfg.latent_ch, C3 = cfg.boc[3], C0 = cfg.boc[0];
   pq_w_ = walloc<float>(L * L); pq_b_ = walloc<float>(L);
   reg("post_quant_conv.weight", {L, L, 1, 1}, {{Slot::F32, pq_w_, 0, 0}});
@@ -113,7 +114,6 @@ VaeDecoder::VaeDecoder(const VaeCfg& cfg) : cfg_(cfg) {
 
 VaeDecoder::~VaeDecoder() {
   for (void* p : owned_) cudaFree(p);
-  if (arena_) cudaFree(arena_);
 }
 
 int VaeDecoder::load_tensor(const char* name, const float* src, const int64_t* dims, int ndim, cudaStream_t st) {
@@ -159,63 +159,6 @@ bool VaeDecoder::tensor_info(int i, std::string& name, std::vector<int64_t>& sha
   return true;
 }
 
-// ------------------------------------------------------------------------------------------------ executor helpers
-template <typename T>
-T* VaeDecoder::A(size_t n) {
-  const size_t bytes = (n * sizeof(T) + 1023) & ~size_t(1023);
-  const size_t off = top_;
-  top_ += bytes;
-  peak_ = std::max(peak_, top_);
-  return reinterpret_cast<T*>(arena_ + off);      // arena_ is null in the sizing pass: offsets only, nothing is launched
-}
-
-int VaeDecoder::gemm(const op_t* Ain, int lda, int mode, const ConvGeom* cg, const op_t* Wt, int M, int N, int K, const GemmEpilogue& ep, int ldw) {
-  flops_ += 2.0 * M * N * K;
-  if (dry_) return 0;
-  GemmParams g; int bn;
-  GemmEpilogue e = ep;
-  if (e.rows_per_group == 0) e.rows_per_group = 1;
-  if (!make_gemm(g, bn, Ain, lda, mode, cg, Wt, M, N, K, e, err_, ldw)) return -1;
-  VCK(launch_gemm(g, bn, st_));
-  ++launches_;
-  return 0;
-}
-
-// conv3x3 (pad 1) of a 16-bit NHWC activation; M = S*H*W rows
-int VaeDecoder::conv3(const op_t* x, const op_t* w, int S, int H, int W, int cin, int cout, GemmEpilogue ep) {
-  ConvGeom cg{S, H, W, cin, 1};
-  return gemm(x, cin, A_CONV3X3, &cg, w, S * H * W, cout, 9 * cin, ep);
-}
-
-float2* VaeDecoder::colstats_for(int M, int N, int HW) { return ((HW & 31) || (N & 31)) ? nullptr : A<float2>(size_t((M + 31) / 32) * N); }
-
-// GroupNorm(+SiLU) forward: statistics from the producer's colstats when available, else a separate statistics pass
-int VaeDecoder::gn_fwd(const float* x, const float2* cs, int S, int HW, int C, const float* g, const float* b, int silu, op_t* out, op_t* raw,
-                       float2** stats_out) {
-  float2* stats = A<float2>(size_t(S) * cfg_.groups);
-  if (stats_out) *stats_out = stats;
-  float2* partial = nullptr; int nch = 0;
-  if (!cs) { const int chunk = std::max(16, HW / 256); nch = (HW + chunk - 1) / chunk; partial = A<float2>(size_t(S) * nch * cfg_.groups); }
-  if (dry_) return 0;
-  if (cs) {
-    GNFinalizeParams p{cs, nullptr, C, 0, HW, cfg_.groups, 1e-6f, stats};
-    gn_finalize_kernel<<<dim3(cfg_.groups, S), (HW >= 16384 ? 512 : 128), 0, st_>>>(p);
-  } else {
-    const int chunk = std::max(16, HW / 256);
-    GNStatsParams sp{x, nullptr, C, 0, HW, cfg_.groups, chunk, partial};
-    gn_stats_kernel<<<dim3(nch, S), std::min(640, ((C / 4 + 31) / 32) * 32), 0, st_>>>(sp);
-    gn_partial_finalize_kernel<<<dim3(cfg_.groups, S), 128, 0, st_>>>(partial, stats, nch, cfg_.groups, 1.0 / (double(HW) * (C / cfg_.groups)), 1e-6f);
-    ++launches_;
-  }
-  const int chunk = HW >= 4096 ? 32 : 16, quads = C / 4;
-  const int threads = std::max(256, quads * std::max(1, (256 + quads - 1) / quads));
-  GNApplyParams ap{x, nullptr, C, 0, HW, cfg_.groups, chunk, 0, nullptr, g, b, 1e-6f, silu, out, raw, stats};
-  gn_apply_kernel<<<dim3((HW + chunk - 1) / chunk, S), threads, 0, st_>>>(ap);
-  launches_ += 2;
-  VCK(cudaGetLastError());
-  return 0;
-}
-
 // GroupNorm(+SiLU) backward: g = dL/d(out) fp32 -> dx (+ add) as fp32 and/or 16-bit
 int VaeDecoder::gn_bwd(const float* g, const GNSave& sv, const float* add, float* dx, op_t* dx16) {
   const int chunk = sv.HW >= 65536 ? 128 : (sv.HW >= 4096 ? 64 : 16);
@@ -241,14 +184,14 @@ int VaeDecoder::res_fwd(const ResW& w, ResSave& sv, const float* x, const float2
   op_t* a1 = A<op_t>(size_t(M) * w.cin);
   op_t* raw = w.wsc ? A<op_t>(size_t(M) * w.cin) : nullptr;
   sv.n1 = GNSave{x, nullptr, S, HW, w.cin, w.n1g, w.n1b, 1};
-  if (gn_fwd(x, cs_x, S, HW, w.cin, w.n1g, w.n1b, 1, a1, raw, &sv.n1.stats)) return -1;
+  if (gn_fwd1(x, cs_x, S, HW, w.cin, w.n1g, w.n1b, 1, a1, raw, &sv.n1.stats)) return -1;
   float* h1 = A<float>(size_t(M) * w.cout);
   GemmEpilogue e1; memset(&e1, 0, sizeof e1);
   e1.bias = w.c1.bias; e1.out_f32 = h1; e1.ldo = w.cout; e1.colstats = colstats_for(M, w.cout, HW);
   if (conv3(a1, w.c1.fwd, S, H, W, w.cin, w.cout, e1)) return -1;
   op_t* a2 = A<op_t>(size_t(M) * w.cout);
   sv.n2 = GNSave{h1, nullptr, S, HW, w.cout, w.n2g, w.n2b, 1};
-  if (gn_fwd(h1, e1.colstats, S, HW, w.cout, w.n2g, w.n2b, 1, a2, nullptr, &sv.n2.stats)) return -1;
+  if (gn_fwd1(h1, e1.colstats, S, HW, w.cout, w.n2g, w.n2b, 1, a2, nullptr, &sv.n2.stats)) return -1;
   const float* resid = x;
   if (w.wsc) {
     float* sc = A<float>(size_t(M) * w.cout);
@@ -295,37 +238,10 @@ int VaeDecoder::res_bwd(const ResW& w, const ResSave& sv, const float* dout, con
 // ------------------------------------------------------------------------------------------------ mid-block attention (1 head of dim C)
 int VaeDecoder::attn_fwd(const float* x, const float2* cs_x, int S, int N, float** out, float2** cs_out) {
   const AttnW& w = attn_;
-  const int C = w.C, M = S * N;
   AttnSave& sv = attn_sv_;
-  op_t* y = A<op_t>(size_t(M) * C);
-  sv.gn = GNSave{x, nullptr, S, N, C, w.gng, w.gnb, 0};
-  if (gn_fwd(x, cs_x, S, N, C, w.gng, w.gnb, 0, y, nullptr, &sv.gn.stats)) return -1;
-  op_t* qkv = A<op_t>(size_t(M) * 3 * C);
-  GemmEpilogue e; memset(&e, 0, sizeof e);
-  e.bias = w.b_qkv; e.out_bf16 = qkv; e.ldob = 3 * C;
-  if (gemm(y, C, A_LINEAR, nullptr, w.w_qkv, M, 3 * C, C, e)) return -1;
-  float* Sc = A<float>(size_t(N) * N);                       // scores of one sample (reused)
-  op_t* P = A<op_t>(size_t(S) * N * N);                      // probabilities of every sample (kept for the backward)
-  op_t* vt = A<op_t>(size_t(S) * C * N);
-  op_t* o = A<op_t>(size_t(M) * C);
-  if (!dry_) {
-    transpose_h16_kernel<<<dim3((C + 31) / 32, (N + 31) / 32, S), dim3(32, 8), 0, st_>>>(qkv + 2 * C, size_t(N) * 3 * C, 3 * C, vt, size_t(C) * N, N, N, C);
-    ++launches_;
-  }
-  const float scale = 1.0f / std::sqrt(float(C));
-  for (int s = 0; s < S; ++s) {
-    const op_t* q = qkv + size_t(s) * N * 3 * C;
-    memset(&e, 0, sizeof e); e.out_f32 = Sc; e.ldo = N;
-    if (gemm(q, 3 * C, A_LINEAR, nullptr, q + C, N, N, C, e, 3 * C)) return -1;
-    if (!dry_) { attn_softmax_rows_kernel<<<dim3(N, 1), 256, 0, st_>>>(Sc, P + size_t(s) * N * N, N, scale * 1.4426950408889634f); ++launches_; }
-    memset(&e, 0, sizeof e); e.out_bf16 = o + size_t(s) * N * C; e.ldob = C;
-    if (gemm(P + size_t(s) * N * N, N, A_LINEAR, nullptr, vt + size_t(s) * C * N, N, C, N, e)) return -1;
-  }
-  float* res = A<float>(size_t(M) * C);
-  memset(&e, 0, sizeof e); e.bias = w.b_o; e.residual = x; e.ldr = C; e.out_f32 = res; e.ldo = C; e.colstats = colstats_for(M, C, N);
-  if (gemm(o, C, A_LINEAR, nullptr, w.w_o, M, C, C, e)) return -1;
-  sv.qkv = qkv; sv.P = P; sv.S = S; sv.N = N;
-  *out = res; *cs_out = e.colstats;
+  sv.gn = GNSave{x, nullptr, S, N, w.C, w.gng, w.gnb, 0};
+  if (attn1h_fwd(x, cs_x, S, N, w.C, w.gng, w.gnb, 1e-6f, w.w_qkv, w.b_qkv, w.w_o, w.b_o, out, cs_out, &sv.gn.stats, &sv.qkv, &sv.P)) return -1;
+  sv.S = S; sv.N = N;
   return 0;
 }
 
@@ -429,7 +345,7 @@ int VaeDecoder::run_forward(const float* z, float* img, int B, int h, int w) {
   }
   op_t* fin = A<op_t>(size_t(B) * H * W * C);
   out_sv_ = GNSave{x, nullptr, B, H * W, C, no_g_, no_b_, 1};
-  if (gn_fwd(x, cs, B, H * W, C, no_g_, no_b_, 1, fin, nullptr, &out_sv_.stats)) return -1;
+  if (gn_fwd1(x, cs, B, H * W, C, no_g_, no_b_, 1, fin, nullptr, &out_sv_.stats)) return -1;
   GemmEpilogue e; memset(&e, 0, sizeof e);
   e.bias = cout_b_; e.out_f32 = img; e.ldo = c.out_ch; e.nchw_hw = H * W;
   if (conv3(fin, cout_w_, B, H, W, C, c.out_ch, e)) return -1;
@@ -505,14 +421,7 @@ int VaeDecoder::ensure_arena(int B, int h, int w) {
   if (!r) r = run_backward(nullptr, nullptr);
   dry_ = false; arena_ = arena_saved_;
   if (r) return -1;
-  const size_t need = peak_ + (size_t(1) << 20);
-  if (need > arena_bytes_) {
-    if (arena_) cudaFree(arena_);
-    arena_ = nullptr; arena_bytes_ = 0;
-    if (cudaMalloc(&arena_, need) != cudaSuccess) { err_ = "VAE arena cudaMalloc failed (" + std::to_string(need >> 20) + " MiB)"; return -1; }
-    arena_bytes_ = need;
-  }
-  return 0;
+  return reserve(peak_ + (size_t(1) << 20), "VAE");
 }
 
 int VaeDecoder::decode(const float* z, float* img, int B, int h, int w, cudaStream_t st) {

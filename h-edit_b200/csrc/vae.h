@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "netexec.h"
 
 namespace hedit {
 
@@ -15,7 +16,7 @@ struct VaeCfg {
   int layers = 2, groups = 32;
 };
 
-class VaeDecoder {
+class VaeDecoder : public NetExec {
  public:
   explicit VaeDecoder(const VaeCfg& cfg);
   ~VaeDecoder();
@@ -30,10 +31,6 @@ class VaeDecoder {
   int decode(const float* z, float* img, int B, int h, int w, cudaStream_t st);
   // dimg [B][out_ch][8h][8w] -> dz [B][latent_ch][h][w] for the last decode()
   int backward(const float* dimg, float* dz, cudaStream_t st);
-  long launches() const { return launches_; }
-  double flops() const { return flops_; }
-  size_t arena_bytes() const { return arena_bytes_; }
-  std::string err_;
 
  private:
   struct Slot {
@@ -56,14 +53,12 @@ class VaeDecoder {
   struct AttnSave { GNSave gn; const op_t* qkv = nullptr; const op_t* P = nullptr; int S = 0, N = 0; };
 
   template <typename T> T* walloc(size_t n);
-  template <typename T> T* A(size_t n);
   void reg(const std::string& name, std::vector<int64_t> shape, std::vector<Slot::Dst> dsts);
   void reg_conv3(const std::string& name, int O, int I, Conv3W& w);
   void reg_res(const std::string& name, int cin, int cout, ResW& r);
-  int gemm(const op_t* Ain, int lda, int mode, const ConvGeom* cg, const op_t* Wt, int M, int N, int K, const GemmEpilogue& ep, int ldw = 0);
-  int conv3(const op_t* x, const op_t* w, int S, int H, int W, int cin, int cout, GemmEpilogue ep);
-  float2* colstats_for(int M, int N, int HW);
-  int gn_fwd(const float* x, const float2* cs, int S, int HW, int C, const float* g, const float* b, int silu, op_t* out, op_t* raw, float2** stats_out);
+  int gn_fwd1(const float* x, const float2* cs, int S, int HW, int C, const float* g, const float* b, int silu, op_t* out, op_t* raw, float2** stats_out) {
+    return gn_fwd(x, cs, C, nullptr, nullptr, 0, S, HW, g, b, 1e-6f, silu, out, raw, stats_out);
+  }
   int gn_bwd(const float* g, const GNSave& sv, const float* add, float* dx, op_t* dx16);
   int res_fwd(const ResW& w, ResSave& sv, const float* x, const float2* cs_x, int S, int H, int W, float** out, float2** cs_out);
   int res_bwd(const ResW& w, const ResSave& sv, const float* dout, const op_t* dout16, float** dx, op_t** dx16);
@@ -83,10 +78,8 @@ class VaeDecoder {
   std::vector<ResW> up_res_[4];
   Conv3W up_conv_[3];
   // run state
-  uint8_t* arena_ = nullptr; uint8_t* arena_saved_ = nullptr; size_t arena_bytes_ = 0, top_ = 0, peak_ = 0, fwd_top_ = 0;
-  bool dry_ = false, have_tape_ = false;
-  cudaStream_t st_ = 0;
-  long launches_ = 0; double flops_ = 0;
+  uint8_t* arena_saved_ = nullptr; size_t fwd_top_ = 0;
+  bool have_tape_ = false;
   ResSave mid_sv_[2]; AttnSave attn_sv_; std::vector<ResSave> up_sv_[4]; GNSave out_sv_{};
   int outH_ = 0, outW_ = 0, outC_ = 0, tapeB_ = 0, lat_h_ = 0, lat_w_ = 0;
 };

@@ -194,6 +194,48 @@ int hedit_clip_gram_loss(hedit_clip* c, const float* img, int B, int H, int W, f
 /* dimg [B][3][H][W] = d loss[b] / d img[b] of the last gram_loss call */
 int hedit_clip_gram_backward(hedit_clip* c, float* dimg, void* stream);
 
+/* ---- face swapping: the pixel-space DDPM denoiser `model(x, t)` (face-swapping/diffusion/diffusion.py:193-341; weights by the
+ * reference's parameter names: "temb.dense.0.weight", "conv_in.weight", "down.0.block.0.norm1.weight", ...) and the reward-guided
+ * sampler `h_Edit_R` (face-swapping/inversion/h_edit_R.py:7-137). */
+typedef struct hedit_face hedit_face;
+typedef struct hedit_face_config {
+  int32_t ch, n_levels, ch_mult[8], num_res_blocks, attn_resolution, image_size, in_channels, out_ch;
+} hedit_face_config;
+hedit_face* hedit_face_create(const hedit_face_config* cfg, int device);
+void hedit_face_destroy(hedit_face* f);
+int hedit_face_load_tensor(hedit_face* f, const char* name, const float* data, const int64_t* dims, int ndim);
+int hedit_face_finalize(hedit_face* f);
+int hedit_face_tensor_count(hedit_face* f);
+int hedit_face_tensor_info(hedit_face* f, int index, char* name_buf, int name_len, int64_t* dims4);
+/* eps = model(x, t): x, eps [S][3][R][R] device fp32; t [S] host.  Returns kernels launched. */
+int hedit_face_unet_forward(hedit_face* f, const float* x, const float* t, int S, float* eps, void* stream);
+
+/* reward hook of h_Edit_R: which = 0 -> idloss.get_cosine_loss, 1 -> lpipsloss.get_lpips_loss (arcface/arcface_model.py:62,91).
+ * Called on the launching stream with the Tweedie prediction x0 [B][3][R][R] in reward_x0 (device); must leave d loss / d x0 (per
+ * image) in reward_grad (device), enqueued on the same stream.  Returns 0 on success. */
+typedef int (*hedit_reward_fn)(void* user, int which, int step, int opt_step);
+typedef struct hedit_face_step_coef {
+  float t, tm1;                 /* timestep and previous timestep (0 after the last step) */
+  float sqrt_1m_at, sqrt_at;    /* of alpha_bar[t] */
+  float sqrt_1m_atm1, sqrt_atm1;/* of alpha_bar[tm1] */
+  float c2, noise;              /* c2 = sqrt(1-abar[tm1]) * sqrt(1 - 0.5^2);  noise = etas[idx] * sqrt(1-abar[tm1]) * 0.5  (h_edit_R.py:82-86) */
+} hedit_face_step_coef;
+typedef struct hedit_face_args {
+  int32_t B, steps, opt_steps;
+  const float* xT;              /* device [B][3][R][R] */
+  const float* zs;              /* device [B][steps][3][R][R]; zs[b][idx], idx = steps-1-i at step i */
+  const hedit_face_step_coef* coef;   /* host [steps] */
+  float weight;                 /* weight_edit_face: rho = sqrt(abar[tm1]) * weight (h_edit_R.py:106) */
+  const float* mask;            /* device [B][3][R][R] soft face mask or NULL (h_edit_R.py:113-116; applies to the ID move only) */
+  int32_t use_id, use_lpips;
+  hedit_reward_fn reward; void* reward_user;
+  float* reward_x0;             /* device [B][3][R][R] */
+  float* reward_grad;           /* device [B][3][R][R] */
+  float* edited;                /* device [B][3][R][R] out */
+  int64_t n_sample_forwards, n_kernel_launches;   /* out */
+} hedit_face_args;
+int hedit_face_edit(hedit_face* f, hedit_face_args* args, void* stream);
+
 /* ---- single operators, exposed for parity tests (device pointers) ------------------------------------------- */
 /* D[M][N] = A[M][K] W[N][K]^T (+bias) (+residual) -> fp32 and/or 16-bit; A, W in the operand dtype (hedit_operand_dtype) */
 int hedit_op_linear(const void* A_h16, const void* W_h16, const float* bias, const float* residual, float* out_f32, void* out_h16,

@@ -273,12 +273,61 @@ def run_style(name="tiny_style_mos2", T=4, K=2, weight=0.5):
           "| style term moved the edit by %.4f (rel)" % ((edited - edited_ns).norm() / edited_ns.norm()).item(), flush=True)
 
 
+def run_face(name="tiny_face_k2", T=5, K=2, weight=50.0):
+    """The UNMODIFIED face-swapping sampler (face-swapping/inversion/h_edit_R.py:7 `h_Edit_R`) and inversion
+    (inversion/sde_inversion.py:54) on the reference's own `Model` class (diffusion/diffusion.py:193) in a small configuration carrying
+    the oracle's seeded weights, with seeded stand-ins for the ArcFace / LPIPS reward models (their weights do not exist offline).
+    Must run in its own process (the face tree has its own `inversion` package)."""
+    import importlib
+    import numpy as np
+    sys.path.insert(0, "/root/reference/face-swapping")
+    from oracle.face_unet import FaceUNet, FaceUNetConfig, TinyIDLoss, TinyLPIPSLoss
+    ref_model = importlib.import_module("diffusion.diffusion")
+    du = importlib.import_module("diffusion.diffusion_utils")
+    inv = importlib.import_module("inversion.sde_inversion")
+    he = importlib.import_module("inversion.h_edit_R")
+    torch.set_num_threads(os.cpu_count())
+    cfg = FaceUNetConfig.tiny()
+    oracle_model = FaceUNet(cfg)
+    model = ref_model.Model(cfg.as_reference_dict())
+    model.load_state_dict(oracle_model.state_dict())
+    model.eval()
+    betas = torch.from_numpy(du.get_beta_schedule(beta_schedule="linear", beta_start=0.0001, beta_end=0.02, num_diffusion_timesteps=1000)).float()
+    skip = 1000 // T
+    seq = (np.arange(0, 1000, skip) + 1)[::-1]                        # main_edit.py:140-142
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x0 = torch.tanh(torch.randn(1, 3, cfg.image_size, cfg.image_size, generator=g))
+    ref_img = torch.tanh(torch.randn(1, 3, cfg.image_size, cfg.image_size, generator=g))
+    idloss, lpipsloss = TinyIDLoss(ref_img), TinyLPIPSLoss(x0.clone())
+    with torch.no_grad():
+        _, zs, xts, _ = inv.inversion_forward_process_sde(model, x0, betas, seq, etas=1.0, num_inference_steps=T, device="cpu")
+    edited = he.h_Edit_R(model, lpipsloss, idloss, xts[T].clone(), betas, seq, eta=1.0, zs=zs[:T], weight_edit_face=weight, optimization_steps=K,
+                         after_skip_steps=T, num_inference_steps=T, soft_face_mask=None)
+    recon = he.h_Edit_R(model, None, None, xts[T].clone(), betas, seq, eta=1.0, zs=zs[:T], weight_edit_face=weight, optimization_steps=K,
+                        after_skip_steps=T, num_inference_steps=T, soft_face_mask=None)
+    out = {"meta": dict(name=name, mode="face", T=T, K=K, weight_edit_face=weight, seq=[int(v) for v in seq],
+                        unet=dict(ch=cfg.ch, ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks, attn_resolutions=list(cfg.attn_resolutions),
+                                  image_size=cfg.image_size),
+                        rewards="oracle.face_unet.TinyIDLoss(seed 21) / TinyLPIPSLoss(seed 22)", generator="tools/make_golden.py --config face",
+                        torch=torch.__version__),
+           "x0": x0, "ref_img": ref_img, "zs": zs[:T].clone(), "xT": xts[T].clone(), "betas": betas,
+           "edited": edited.detach().clone(), "no_reward": recon.detach().clone()}
+    path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
+    torch.save(out, path)
+    print(name, "->", path, "|edited| %.4f" % out["edited"].abs().mean().item(),
+          "| rewards moved the result by %.4f (rel) | no-reward run returns x0 to %.2e" %
+          (((edited - recon).norm() / recon.norm()).item(), (recon - x0).abs().max().item()), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "variants", "inversion", "pnp", "style", "all"])
+    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
     args = ap.parse_args()
     if args.config == "style":
         run_style()
+        return
+    if args.config == "face":
+        run_face()
         return
     ref = load_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
