@@ -10,7 +10,7 @@ import hedit_b200
 from hedit_b200 import _lib, p2p
 from oracle import h_edit as oh
 from oracle import p2p as op
-from oracle.pipeline import DDIMSchedulerTables, ToyTokenizer
+from oracle.pipeline import DDIMSchedulerTables, OraclePipeline, ToyTokenizer
 from refload import load_reference, reference_available
 from test_oracle_pin import PAIRS
 
@@ -117,3 +117,66 @@ def test_batched_plan_stacks_images():
     assert plan.mapper.shape == (4, 80) and plan.c_base.shape == (7, 4, 80) and plan.has_blend.tolist() == [1, 0, 1, 0]
     with pytest.raises(ValueError):
         hedit_b200.compile_edit_plan(ctrls, 7)
+
+
+# ---- host-side tables of the samplers added after the north-star loop --------------------------------------------------------------
+def test_other_engines_fail_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        hedit_b200.VaeDecoderEngine(dict(latent_channels=4, out_channels=3, block_out_channels=(64, 64, 128, 128), layers_per_block=2, norm_groups=32))
+    with pytest.raises(RuntimeError):
+        hedit_b200.ClipGramEngine(224, 16, 64, 1)
+    with pytest.raises(RuntimeError):
+        hedit_b200.FaceUNetEngine(dict(ch=64, ch_mult=(1, 2, 2), num_res_blocks=2, attn_resolution=16, image_size=64, in_channels=3, out_ch=3))
+
+
+def test_pnp_flags_and_layer_mask():
+    """Plug-and-Play: the injected pair call of step i runs at tt = op[i+1] (0 after the last step) and the patched forwards test
+    `t in schedule` (plug_n_play/pnp_utils.py:51,138); layers = decoder self-attention blocks 4-11 (pnp_utils.py:88)."""
+    model = OraclePipeline(build_unet=False)
+    T = 10
+    model.scheduler.set_timesteps(T)
+    ts = [int(t) for t in model.scheduler.timesteps]
+    hedit_b200.register_attention_control_efficient(model, ts[:4])
+    hedit_b200.register_conv_control_efficient(model, ts[:7])
+    qk, ft = hedit_b200.pnp_step_flags(model, T)
+    assert qk == [1, 1, 1, 0, 0, 0, 0, 0, 0, 0] and ft == [1, 1, 1, 1, 1, 1, 0, 0, 0, 0]
+    qk, ft = hedit_b200.pnp_step_flags(model, T - 3)            # skipped schedule: op = timesteps[-7:]
+    assert qk == [0] * 7 and ft == [1, 1, 1, 0, 0, 0, 0]
+    assert hedit_b200.pnp_self_mask(2) == 0xFF00
+    hedit_b200.register_attention_control_efficient(model, None)
+    assert hedit_b200.pnp_step_flags(model, T)[0] == [0] * T
+
+
+def test_skip_pre_coeff_and_x0_tables_follow_the_reference_formulas():
+    model = OraclePipeline(build_unet=False)
+    T, S = 20, 14
+    model.scheduler.set_timesteps(T)
+    sched = model.scheduler
+    assert hedit_b200.skip_pre_coeff(sched, T, 1.0) is None
+    ta, t = int(sched.timesteps[-(S + 1)]), int(sched.timesteps[-S])
+    want = oh.full_coeff(sched, ta, t, 1.0, False) - (1 - sched.alphas_cumprod[ta]) ** 0.5 * (sched.alphas_cumprod[t] ** 0.5 / sched.alphas_cumprod[ta] ** 0.5)
+    assert abs(hedit_b200.skip_pre_coeff(sched, S, 1.0) - float(want)) < 1e-7
+    x0c = hedit_b200.x0_tables(sched, S)
+    tts = [int(v) for v in sched.timesteps[-S:]][1:] + [0]
+    for (a, b), tt in zip(x0c, tts):
+        assert abs(a - float((1 - sched.alphas_cumprod[tt]) ** 0.5)) < 1e-7 and abs(b - float(sched.alphas_cumprod[tt] ** 0.5)) < 1e-7
+
+
+def test_face_step_tables_follow_the_reference_formulas():
+    """face-swapping/inversion/h_edit_R.py:68-88,106 with the beta schedule of main_edit.py:130-142."""
+    import numpy as np
+    T = 10
+    betas = torch.linspace(0.0001, 0.02, 1000, dtype=torch.float64).float()
+    seq = (np.arange(0, 1000, 1000 // T) + 1)[::-1]
+    tab = hedit_b200.face.face_step_tables(betas, seq, T, T - 2, eta=1.0)
+    ab = (1 - betas).cumprod(0)
+    op = [int(v) for v in seq[-(T - 2):]]
+    assert tab.shape == (T - 2, 8)
+    for i, t in enumerate(op):
+        tm1 = op[i + 1] if i + 1 < len(op) else 0
+        c1 = (1 - ab[tm1]).sqrt() * 0.5
+        c2 = (1 - ab[tm1]).sqrt() * ((1 - 0.25) ** 0.5)
+        want = [t, tm1, (1 - ab[t]) ** 0.5, ab[t] ** 0.5, (1 - ab[tm1]) ** 0.5, ab[tm1].sqrt(), c2, 1.0 * c1]
+        assert np.allclose(tab[i], np.asarray([float(v) for v in want], dtype=np.float32), rtol=1e-6, atol=0)

@@ -140,3 +140,31 @@ assert err < 1e-5, err
 """ % (root, os.path.join(root, "tests", "refshim"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "GRAM_REL_ERR" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_face_unet_restatement_matches_reference_class():
+    """oracle/face_unet.py vs the reference's own `Model` (face-swapping/diffusion/diffusion.py:193) on the same seeded weights, and the face
+    golden's intrinsic known answer (the no-reward run of h_Edit_R returns the inverted image).  Subprocess: own `inversion` package."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, importlib, torch
+sys.path[:0] = [%r, "/root/reference/face-swapping"]
+from oracle.face_unet import FaceUNet, FaceUNetConfig
+cfg = FaceUNetConfig.tiny()
+m = FaceUNet(cfg)
+ref = importlib.import_module("diffusion.diffusion").Model(cfg.as_reference_dict())
+ref.load_state_dict(m.state_dict())
+x = torch.randn(2, 3, cfg.image_size, cfg.image_size, generator=torch.Generator().manual_seed(1)); t = torch.tensor([981.0, 11.0])
+with torch.no_grad():
+    err = ((m(x, t) - ref(x, t)).norm() / ref(x, t).norm()).item()
+print("FACE_REL_ERR", err)
+assert err < 1e-5, err
+""" % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "FACE_REL_ERR" in r.stdout, r.stderr[-2000:]
+    g = load_golden("tiny_face_k2")
+    assert (g["no_reward"] - g["x0"]).abs().max().item() < 1e-4
