@@ -114,6 +114,7 @@ SYMBOLS = {
     "hedit_face_tensor_count": (_I, [_P]),
     "hedit_face_tensor_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_int64)]),
     "hedit_face_unet_forward": (_I, [_P, _P, _P, _I, _P, _P]),
+    "hedit_face_last_flops": (C.c_double, [_P]),
     "hedit_face_edit": (_I, [_P, C.POINTER(FaceArgsC), _P]),
     "hedit_op_linear": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "hedit_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -328,6 +328,7 @@ int hedit_face_unet_forward(hedit_face* f, const float* x, const float* t, int S
   if (f->U->forward(x, t, eps, S, reinterpret_cast<cudaStream_t>(stream))) return fail(f->U->error());
   return int(f->U->launches());
 }
+double hedit_face_last_flops(hedit_face* f) { return f ? f->U->flops() : 0.0; }
 int hedit_face_edit(hedit_face* f, hedit_face_args* args, void* stream) {
   if (!f || !args) return fail("null face engine / args");
   cudaSetDevice(f->device);

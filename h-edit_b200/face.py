@@ -94,7 +94,7 @@ class FaceUNetEngine:
         tt = np.ascontiguousarray(np.broadcast_to(np.asarray(torch.as_tensor(t).detach().cpu().numpy() if torch.is_tensor(t) else t, dtype=np.float32).reshape(-1), (S,)))
         eps = torch.empty_like(x)
         n = _lib.check(self.lib.hedit_face_unet_forward(self.handle, x.data_ptr(), tt.ctypes.data, S, eps.data_ptr(), self._stream()), "face unet forward")
-        self.last_stats = {"kernel_launches": n, "sample_forwards": S}
+        self.last_stats = {"kernel_launches": n, "sample_forwards": S, "flops": self.lib.hedit_face_last_flops(self.handle)}
         return eps
 
     __call__ = forward

@@ -209,6 +209,8 @@ int hedit_face_tensor_count(hedit_face* f);
 int hedit_face_tensor_info(hedit_face* f, int index, char* name_buf, int name_len, int64_t* dims4);
 /* eps = model(x, t): x, eps [S][3][R][R] device fp32; t [S] host.  Returns kernels launched. */
 int hedit_face_unet_forward(hedit_face* f, const float* x, const float* t, int S, float* eps, void* stream);
+/* floating-point operations (GEMM / conv) of the last denoiser call, for roofline accounting */
+double hedit_face_last_flops(hedit_face* f);
 
 /* reward hook of h_Edit_R: which = 0 -> idloss.get_cosine_loss, 1 -> lpipsloss.get_lpips_loss (arcface/arcface_model.py:62,91).
  * Called on the launching stream with the Tweedie prediction x0 [B][3][R][R] in reward_x0 (device); must leave d loss / d x0 (per

@@ -110,6 +110,19 @@ def bench_vae(iters):
               f"({f_all / ms_fb / 1e9:.0f} TFLOP/s) | backward alone ~{ms_fb - ms_f:.2f} ms ({(f_all - f_fwd) / max(ms_fb - ms_f, 1e-6) / 1e9:.0f} TFLOP/s)")
 
 
+def bench_face(iters):
+    """CelebA-HQ DDPM UNet geometry (ch 128 x (1,1,2,2,4,4), 256x256), random-init weights: one denoiser call."""
+    import hedit_b200
+    eng = hedit_b200.FaceUNetEngine(dict(ch=128, ch_mult=(1, 1, 2, 2, 4, 4), num_res_blocks=2, attn_resolution=16, image_size=256, in_channels=3, out_ch=3))
+    eng.load_random_weights(0)
+    for S in (1, 8):
+        x = torch.randn(S, 3, 256, 256, device=DEV)
+        eng(x, 500.0)
+        fl = eng.last_stats["flops"]
+        ms = timeit(lambda: eng(x, 500.0), iters)
+        print(f"face unet S={S}: {ms:.2f} ms  {fl / ms / 1e9:.0f} TFLOP/s  ({fl / S / 1e12:.3f} TFLOP/sample, {eng.last_stats['kernel_launches']} launches)")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -126,3 +139,5 @@ if __name__ == "__main__":
         bench_cross(a.iters)
     if a.what in ("vae", "all"):
         bench_vae(a.iters)
+    if a.what in ("face", "all"):
+        bench_face(a.iters)
