@@ -52,6 +52,33 @@ HEDIT_DEVICE float ex2f(float x) {
   return y;
 }
 
+// exp2 of 8 scaled scores: x = v * scale - m.  POLY of the 8 values (0, 2 or 4) are evaluated on the FMA pipe instead of the MUFU
+// (Cody-Waite range reduction with the 1.5*2^23 rounding constant + a degree-3 minimax polynomial of 2^f on [-0.5, 0.5], relative error
+// 7.5e-5, well below the 16-bit rounding of P), using the packed fp32x2 instructions of sm_100 -- the self-attention softmax is bound
+// by the 16/clk/SM exponent unit, not by issue slots.  Returns the 8 values as 4 float2 (for packed row-sum adds).
+template <int POLY>
+HEDIT_DEVICE void exp2_block8(const uint32_t* v, float scale, float neg_m, float2 (&e)[4]) {
+  const float2 sc = make_float2(scale, scale), nm = make_float2(neg_m, neg_m);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), sc, nm);
+    const bool poly = (POLY == 4) ? (k & 1) : (POLY == 2 ? (k == 3) : false);
+    if (!poly) {
+      e[k] = make_float2(ex2f(x.x), ex2f(x.y));
+    } else {
+      const float2 xc = make_float2(fmaxf(x.x, -125.f), fmaxf(x.y, -125.f));
+      const float2 t = __fadd2_rn(xc, make_float2(12582912.f, 12582912.f));            // low mantissa bits = round(x)
+      const float2 j = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+      const float2 f = __ffma2_rn(j, make_float2(-1.f, -1.f), xc);                        // in [-0.5, 0.5]
+      float2 q = __ffma2_rn(f, make_float2(0.0551716648f, 0.0551716648f), make_float2(0.2426111251f, 0.2426111251f));
+      q = __ffma2_rn(q, f, make_float2(0.6932609677f, 0.6932609677f));
+      q = __ffma2_rn(q, f, make_float2(0.9999280572f, 0.9999280572f));
+      e[k] = make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                         __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+    }
+  }
+}
+
 // byte offset of (row, 16-byte unit u) inside a [rows][64 bf16] 128B-swizzled tile
 HEDIT_DEVICE uint32_t sw128_off(int row, int unit) { return uint32_t(row) * 128u + uint32_t((unit ^ (row & 7)) << 4); }
 
@@ -296,7 +323,7 @@ struct SelfAttn2Cfg {
   static_assert(O_COL0 + NT * O_STRIDE <= 512, "TMEM budget");
 };
 
-template <int DCH, int NT_, int BKV_>
+template <int DCH, int NT_, int BKV_, int POLY = 0>
 static __global__ void __launch_bounds__(SelfAttn2Cfg<DCH, NT_, BKV_>::THREADS, SelfAttn2Cfg<DCH, NT_, BKV_>::MIN_CTAS)
 self_attn2_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = SelfAttn2Cfg<DCH, NT_, BKV_>;
@@ -480,21 +507,19 @@ self_attn2_kernel(const __grid_constant__ AttnParams p) {
         tmem_st_wait();
       }
       const float neg_m = -m_used;
-      float ls[8];
+      float2 ls[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) ls[k] = 0.f;
+      for (int k = 0; k < 4; ++k) ls[k] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < BKV; c += 8) {
-        float e[8];
+        float2 e[4];
+        exp2_block8<POLY>(&v[c], p.scale_log2, neg_m, e);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          e[i] = ex2f(fmaf(__uint_as_float(v[c + i]), p.scale_log2, neg_m));
-          ls[i] += e[i];                              // 8 independent accumulation chains
-        }
+        for (int k = 0; k < 4; ++k) ls[k] = __fadd2_rn(ls[k], e[k]);      // 8 independent accumulation chains, packed adds
         *reinterpret_cast<uint4*>(sPt + (c >> 6) * 16384 + sw128_off(r, (c & 63) >> 3)) =
-            make_uint4(pack_op2(e[0], e[1]), pack_op2(e[2], e[3]), pack_op2(e[4], e[5]), pack_op2(e[6], e[7]));
+            make_uint4(pack_op2(e[0].x, e[0].y), pack_op2(e[1].x, e[1].y), pack_op2(e[2].x, e[2].y), pack_op2(e[3].x, e[3].y));
       }
-      l += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+      l += ((ls[0].x + ls[0].y) + (ls[1].x + ls[1].y)) + ((ls[2].x + ls[2].y) + (ls[3].x + ls[3].y));
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();

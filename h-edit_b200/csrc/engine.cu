@@ -383,16 +383,18 @@ static cudaError_t launch_self_t(const AttnParams& a, int S, cudaStream_t st) {
   self_attn_kernel<DCH, BKV><<<grid, 192, SelfAttnCfg<DCH, BKV>::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
-template <int DCH, int NT, int BKV>
+template <int DCH, int NT, int BKV, int POLY = 0>
 static cudaError_t launch_self2_t(const AttnParams& a, int S, cudaStream_t st) {
   using Cfg = SelfAttn2Cfg<DCH, NT, BKV>;
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(self_attn2_kernel<DCH, NT, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
+  if (!set) { cudaFuncSetAttribute(self_attn2_kernel<DCH, NT, BKV, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
   constexpr int rows = 128 * NT;
   dim3 grid((a.Nq + rows - 1) / rows, a.H, S);
-  self_attn2_kernel<DCH, NT, BKV><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  self_attn2_kernel<DCH, NT, BKV, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
+// tuning switch HEDIT_ATTN_POLY: how many of every 8 softmax exponentials run on the FMA pipe instead of the MUFU (0, 2 or 4)
+static int attn_poly() { static const int v = getenv("HEDIT_ATTN_POLY") ? atoi(getenv("HEDIT_ATTN_POLY")) : 0; return v; }
 // tuning switch HEDIT_ATTN_CFG for head dims <= 64 (measured on B200, N=4096, d=40, cycles per 128x128 block):
 //   1 (default) = 2 tiles x 64-column blocks, 2 CTAs/SM: 1543;  0 = 2 tiles x 128-column blocks, 1 CTA/SM: 1645;
 //   2 = 4 tiles x 64-column blocks, 1 CTA/SM: 2220
@@ -401,7 +403,11 @@ cudaError_t launch_self_attn(const AttnParams& a, int dch, int S, cudaStream_t s
   const int bkv2 = (dch == 1 && attn_cfg() == 0) ? 128 : 64;
   if (a.Nq >= 256 && a.Nkv % bkv2 == 0) {      // several query tiles per CTA
     if (dch == 1) {
-      if (attn_cfg() == 1) return launch_self2_t<1, 2, 64>(a, S, st);
+      if (attn_cfg() == 1) {
+        if (attn_poly() == 4) return launch_self2_t<1, 2, 64, 4>(a, S, st);
+        if (attn_poly() == 2) return launch_self2_t<1, 2, 64, 2>(a, S, st);
+        return launch_self2_t<1, 2, 64>(a, S, st);
+      }
       if (attn_cfg() == 2) return launch_self2_t<1, 4, 64>(a, S, st);
       return launch_self2_t<1, 2, 128>(a, S, st);
     }
