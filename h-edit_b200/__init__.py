@@ -14,7 +14,7 @@ from .samplers import (HEditStepper, h_edit_step, MutualSelfAttentionControl, en
                        h_Edit_PnP_implicit, pnp_self_mask, pnp_step_flags, register_attention_control_efficient, register_conv_control_efficient, register_time)
 
 from . import style  # noqa: F401,E402
-from .vae import VaeDecoderEngine, vae_config_of  # noqa: F401,E402
+from .vae import VaeDecoderEngine, VaeEncoderEngine, vae_config_of  # noqa: F401,E402
 from .clip_gram import ClipGramEngine  # noqa: F401,E402
 from . import face  # noqa: F401,E402
 from .face import FaceUNetEngine  # noqa: F401,E402

@@ -107,6 +107,11 @@ SYMBOLS = {
     "hedit_clip_set_reference": (_I, [_P, _P, _P]),
     "hedit_clip_gram_loss": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "hedit_clip_gram_backward": (_I, [_P, _P, _P]),
+    "hedit_vae_enc_create": (_P, [C.POINTER(VaeConfigC), _I]),
+    "hedit_vae_enc_destroy": (None, [_P]),
+    "hedit_vae_enc_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
+    "hedit_vae_enc_finalize": (_I, [_P]),
+    "hedit_vae_encode": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "hedit_face_create": (_P, [C.POINTER(FaceConfigC), _I]),
     "hedit_face_destroy": (None, [_P]),
     "hedit_face_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),

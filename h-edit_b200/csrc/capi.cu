@@ -10,6 +10,7 @@
 #include "engine.h"
 #include "tmap.h"
 #include "vae.h"
+#include "vae_enc.h"
 #include "clip.h"
 #include "face.h"
 
@@ -42,6 +43,11 @@ struct hedit_face {
 
 struct hedit_clip {
   ClipGram* C;
+  int device;
+};
+
+struct hedit_vae_enc {
+  VaeEncoder* E;
   int device;
 };
 
@@ -267,6 +273,52 @@ int hedit_vae_decode_backward(hedit_vae* v, const float* dimg, float* dz, void* 
   return int(v->D->launches());
 }
 double hedit_vae_last_flops(hedit_vae* v) { return v ? v->D->flops() : 0.0; }
+
+hedit_vae_enc* hedit_vae_enc_create(const hedit_vae_config* cfg, int device) {
+  if (!cfg) { fail("null config"); return nullptr; }
+  if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only"); return nullptr; }
+  VaeCfg c;
+  c.latent_ch = cfg->latent_channels; c.out_ch = cfg->out_channels; c.layers = cfg->layers_per_block; c.groups = cfg->norm_groups;
+  for (int i = 0; i < 4; ++i) c.boc[i] = cfg->block_out_channels[i];
+  if (c.latent_ch != 4 || c.out_ch > 4 || c.groups > 32) { fail("unsupported VAE config"); return nullptr; }
+  for (int i = 0; i < 4; ++i)
+    if (c.boc[i] % 64 != 0 || c.boc[i] > 2048 || c.boc[i] % c.groups != 0) { fail("VAE block_out_channels must be multiples of 64 (and of the group count), <= 2048"); return nullptr; }
+  hedit_vae_enc* v = new hedit_vae_enc();
+  v->device = device;
+  v->E = new VaeEncoder(c);
+  if (!v->E->ok()) { fail(v->E->error()); delete v->E; delete v; return nullptr; }
+  return v;
+}
+void hedit_vae_enc_destroy(hedit_vae_enc* v) {
+  if (!v) return;
+  cudaSetDevice(v->device);
+  delete v->E;
+  delete v;
+}
+int hedit_vae_enc_load_tensor(hedit_vae_enc* v, const char* name, const float* data, const int64_t* dims, int ndim) {
+  if (!v) return fail("null vae encoder");
+  cudaSetDevice(v->device);
+  const int r = v->E->load_tensor(name, data, dims, ndim, 0);
+  if (r) return fail(v->E->error(), r);
+  return 0;
+}
+int hedit_vae_enc_finalize(hedit_vae_enc* v) {
+  if (!v) return fail("null vae encoder");
+  std::string missing;
+  if (v->E->finalize(&missing)) return fail(v->E->error());
+  return 0;
+}
+int hedit_vae_encode(hedit_vae_enc* v, const float* img, float* moments, int B, int H, int W, void* stream) {
+  if (!v) return fail("null vae encoder");
+  cudaSetDevice(v->device);
+  if (v->E->encode(img, moments, B, H, W, reinterpret_cast<cudaStream_t>(stream))) return fail(v->E->error());
+  return int(v->E->launches());
+}
 
 // ------------------------------------------------------------------------------------------------ face swapping
 hedit_face* hedit_face_create(const hedit_face_config* cfg, int device) {

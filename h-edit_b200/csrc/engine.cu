@@ -295,8 +295,8 @@ bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode, const
     ok = make_tmap_bf16(&g.tmA, A, 2, dims, str, box);
   } else {
     const int W = cg->W, H = cg->H, C = cg->C;
-    const bool wide = W > 128;          // one 128-row tile = part of an image row (stride-1 convs only)
-    if ((wide ? (W % 128 != 0 || a_mode != A_CONV3X3) : 128 % W != 0) || C % 64 != 0) {
+    const bool wide = W > 128;          // one 128-row tile = part of an image row
+    if ((wide ? W % 128 != 0 : 128 % W != 0) || C % 64 != 0) {
       err = "conv geometry unsupported (need W | 128 or 128 | W, Cin % 64 == 0)";
       return false;
     }
@@ -313,7 +313,7 @@ bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode, const
       const int Win = 2 * W, Hin = 2 * H;
       uint64_t dims[5] = {uint64_t(2 * C), uint64_t(W), 2, uint64_t(H), uint64_t(cg->S)};
       uint64_t str[4] = {uint64_t(2 * C) * 2, uint64_t(Win) * C * 2, uint64_t(2) * Win * C * 2, uint64_t(Hin) * Win * C * 2};
-      uint32_t box[5] = {64, uint32_t(W), 1, uint32_t(BH), uint32_t(BS)};
+      uint32_t box[5] = {64, uint32_t(std::min(W, 128)), 1, uint32_t(BH), uint32_t(BS)};
       ok = make_tmap_bf16(&g.tmA, A, 5, dims, str, box);
     }
   }

@@ -165,13 +165,13 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             if (p.a_mode == A_LINEAR) tma_load_2d_2sm(sa, &p.tmA, lfull, kb * 64, m0);
             else if (p.a_mode == A_CONV3X3) tma_load_4d_2sm(sa, &p.tmA, lfull, cb * 64, x0 + kx - 1, y0 + ky - 1, s0);
-            else tma_load_5d_2sm(sa, &p.tmA, lfull, px * p.conv_cin + cb * 64, dx, py, y0 + dy, s0);
+            else tma_load_5d_2sm(sa, &p.tmA, lfull, px * p.conv_cin + cb * 64, x0 + dx, py, y0 + dy, s0);
             tma_load_2d_2sm(sb, &p.tmB, lfull, kb * 64, n0 + int(rank) * (BN / 2));
           } else {
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             if (p.a_mode == A_LINEAR) tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * 64, m0);
             else if (p.a_mode == A_CONV3X3) tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * 64, x0 + kx - 1, y0 + ky - 1, s0);
-            else tma_load_5d(sa, &p.tmA, &full_bar[stage], px * p.conv_cin + cb * 64, dx, py, y0 + dy, s0);
+            else tma_load_5d(sa, &p.tmA, &full_bar[stage], px * p.conv_cin + cb * 64, x0 + dx, py, y0 + dy, s0);
             // the W map's box is BN/2 rows (shared with the pair variant): two loads
             tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
             tma_load_2d(sb + (BN / 2) * 128, &p.tmB, &full_bar[stage], kb * 64, n0 + BN / 2);

@@ -115,3 +115,60 @@ class VaeDecoderEngine:
         n = _lib.check(self.lib.hedit_vae_decode_backward(self.handle, g.data_ptr(), dz.data_ptr(), self._stream()), "vae decode backward")
         self.last_stats = {"kernel_launches": n, "flops": self.lib.hedit_vae_last_flops(self.handle)}
         return dz * scale
+
+
+class _Gaussian:
+    def __init__(self, moments):
+        self.mean, self.logvar = moments.chunk(2, dim=1)
+
+    def mode(self):
+        return self.mean
+
+
+class _EncOut:
+    def __init__(self, moments):
+        self.latent_dist = _Gaussian(moments)
+
+
+class VaeEncoderEngine:
+    """`model.vae.encode(x).latent_dist.mode()` (text-guided/main_p2p.py:154-159) on the native encoder."""
+
+    def __init__(self, config: dict, device: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("hedit_b200: no CUDA device visible; the B200 path has no CPU fallback")
+        c = _lib.VaeConfigC()
+        c.latent_channels, c.out_channels = config["latent_channels"], config["out_channels"]
+        for i, v in enumerate(config["block_out_channels"]):
+            c.block_out_channels[i] = v
+        c.layers_per_block, c.norm_groups = config["layers_per_block"], config["norm_groups"]
+        self.config, self.device = dict(config), device
+        self.handle = self.lib.hedit_vae_enc_create(C.byref(c), device)
+        if not self.handle:
+            raise RuntimeError("hedit_b200: VAE encoder creation failed: " + _lib.last_error())
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.hedit_vae_enc_destroy(h)
+
+    @classmethod
+    def from_vae(cls, vae, device: int = 0) -> "VaeEncoderEngine":
+        eng = cls(vae_config_of(vae), device)
+        for name, t in vae.state_dict().items():
+            if not torch.is_floating_point(t) or not name.startswith(("encoder.", "quant_conv.")):
+                continue
+            t = t.detach().to(torch.float32).contiguous()
+            dims = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(eng.lib.hedit_vae_enc_load_tensor(eng.handle, name.encode(), t.data_ptr(), dims, t.dim()), f"load {name}")
+        _lib.check(eng.lib.hedit_vae_enc_finalize(eng.handle), "finalize VAE encoder weights")
+        return eng
+
+    def encode(self, x: torch.Tensor) -> _EncOut:
+        dev = torch.device("cuda", self.device)
+        x = x.detach().to(dev, torch.float32).contiguous()
+        B, _, H, W = x.shape
+        mom = torch.empty(B, 2 * self.config["latent_channels"], H // 8, W // 8, dtype=torch.float32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.hedit_vae_encode(self.handle, x.data_ptr(), mom.data_ptr(), B, H, W, stream), "vae encode")
+        return _EncOut(mom)

@@ -173,6 +173,15 @@ int hedit_vae_decode_backward(hedit_vae* v, const float* dimg, float* dz, void* 
 /* floating-point operations of the last decode (+ backward) call, for roofline accounting */
 double hedit_vae_last_flops(hedit_vae* v);
 
+/* VAE encoder: `model.vae.encode(x).latent_dist` (text-guided/main_p2p.py:154-159); weights "encoder.*" and "quant_conv.*" */
+typedef struct hedit_vae_enc hedit_vae_enc;
+hedit_vae_enc* hedit_vae_enc_create(const hedit_vae_config* cfg, int device);
+void hedit_vae_enc_destroy(hedit_vae_enc* v);
+int hedit_vae_enc_load_tensor(hedit_vae_enc* v, const char* name, const float* data, const int64_t* dims, int ndim);
+int hedit_vae_enc_finalize(hedit_vae_enc* v);
+/* img [B][3][H][W] (device fp32, in [-1,1]) -> moments [B][2*latent][H/8][W/8] = (mean | logvar) (device fp32); latent_dist.mode() = mean */
+int hedit_vae_encode(hedit_vae_enc* v, const float* img, float* moments, int B, int H, int W, void* stream);
+
 /* ---- CLIP-Gram style reward: `torch.linalg.norm(image_encoder.get_gram_matrix_residual(img))` and its gradient with respect to
  * img (text-guided-n-style/clip_guidance/base_clip.py:55-66 over clip/model.py:339-359; differentiated by torch.autograd at
  * text-guided-n-style/inversion/h_edit.py:161-164).  Weights = state dict of the CLIP image tower (`clip_model.visual`: "conv1.weight",

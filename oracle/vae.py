@@ -127,6 +127,82 @@ class Decoder(nn.Module):
         return self.conv_out(F.silu(self.conv_norm_out(x)))
 
 
+class _Downsampler(nn.Module):
+    """diffusers Downsample2D(padding=0): zero-pad (0,1,0,1) then a stride-2 3x3 conv."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (0, 1, 0, 1)))
+
+
+class _DownBlock(nn.Module):
+    def __init__(self, cin, cout, n, groups, add_down):
+        super().__init__()
+        self.resnets = nn.ModuleList([VaeResnet(cin if i == 0 else cout, cout, groups) for i in range(n)])
+        self.downsamplers = nn.ModuleList([_Downsampler(cout)]) if add_down else None
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        return x if self.downsamplers is None else self.downsamplers[0](x)
+
+
+class Encoder(nn.Module):
+    """diffusers-0.18 `Encoder` (AutoencoderKL encode direction, SD-1.x): conv_in, 4 DownEncoderBlock2D, the same mid block as the
+    decoder, GroupNorm + SiLU + conv_out to 2 x latent channels (mean | logvar)."""
+
+    def __init__(self, cfg: VAEConfig):
+        super().__init__()
+        boc, g = cfg.block_out_channels, cfg.norm_num_groups
+        self.conv_in = nn.Conv2d(cfg.out_channels, boc[0], 3, padding=1)
+        self.down_blocks = nn.ModuleList()
+        prev = boc[0]
+        for i, c in enumerate(boc):
+            self.down_blocks.append(_DownBlock(prev, c, cfg.layers_per_block, g, add_down=i != len(boc) - 1))
+            prev = c
+        self.mid_block = _Mid(boc[-1], g)
+        self.conv_norm_out = nn.GroupNorm(g, boc[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(boc[-1], 2 * cfg.latent_channels, 3, padding=1)
+
+    def forward(self, x):
+        x = self.conv_in(x)
+        for b in self.down_blocks:
+            x = b(x)
+        return self.conv_out(F.silu(self.conv_norm_out(self.mid_block(x))))
+
+
+class _Gaussian:
+    def __init__(self, moments):
+        self.mean, self.logvar = moments.chunk(2, dim=1)
+
+    def mode(self):
+        return self.mean
+
+
+class _EncOut:
+    def __init__(self, moments):
+        self.latent_dist = _Gaussian(moments)
+
+
+class AutoencoderKLEncoder(nn.Module):
+    """`model.vae` for the encode direction: `.encode(x).latent_dist.mode()` / `.mean` (text-guided/main_p2p.py:154-159)."""
+
+    def __init__(self, cfg: VAEConfig = VAEConfig(), seed: int = 8):
+        super().__init__()
+        self.cfg = cfg
+        self.encoder = Encoder(cfg)
+        self.quant_conv = nn.Conv2d(2 * cfg.latent_channels, 2 * cfg.latent_channels, 1)
+        seeded_init_(self, seed)
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    def encode(self, x):
+        return _EncOut(self.quant_conv(self.encoder(x)))
+
+
 class AutoencoderKLDecoder(nn.Module):
     """`model.vae` for the decode direction: `.decode(z).sample`."""
 

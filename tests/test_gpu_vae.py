@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from oracle.vae import AutoencoderKLDecoder, VAEConfig  # noqa: E402
+from oracle.vae import AutoencoderKLDecoder, AutoencoderKLEncoder, VAEConfig  # noqa: E402
 
 import hedit_b200  # noqa: E402
 from gpu_util import rel_err  # noqa: E402
@@ -66,3 +66,22 @@ def test_vae_full_size_geometry():
     assert r < TOL_FWD
     gz = eng.backward(torch.ones_like(out))
     assert torch.isfinite(gz).all() and gz.abs().max().item() > 0
+
+
+@pytest.mark.parametrize("cfg,B,px", [(VAEConfig.tiny(), 2, 256), (VAEConfig(), 1, 512)])
+def test_vae_encode_matches_torch(cfg, B, px):
+    """`vae.encode(x).latent_dist.mode()` (main_p2p.py:154-159): wide-image convs and the (0,1,0,1)-padded stride-2 downsamplers."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    vae = AutoencoderKLEncoder(cfg).cuda()
+    eng = hedit_b200.VaeEncoderEngine.from_vae(vae)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.tanh(torch.randn(B, 3, px, px, generator=g)).cuda()
+    with torch.no_grad():
+        ref = vae.encode(x).latent_dist
+    out = eng.encode(x).latent_dist
+    r, m = rel_err(out.mode(), ref.mode())
+    r2, _ = rel_err(out.logvar, ref.logvar)
+    print(f"vae encode {px}px boc={cfg.block_out_channels}: mean rel {r:.3e} max {m:.3e} | logvar rel {r2:.3e}")
+    assert out.mode().shape == (B, 4, px // 8, px // 8)
+    assert r < TOL_FWD and r2 < TOL_FWD
