@@ -3,7 +3,7 @@
 CPU restatement of the reference's Plug-and-Play attention/feature injection
 (/root/reference/text-guided/plug_n_play/pnp_utils.py) for the oracle SD-1.x UNet, and of the sampler that drives it
 (/root/reference/text-guided/inversion/pnp_h_edit.py:33-160).  Pinned against the unmodified reference functions by
-tests/golden/*pnp*.pt (tools/make_golden.py) in tests/test_oracle_pin.py.
+tests/golden/*pnp*.pt (tests/make_golden.py) in tests/test_oracle_pin.py.
 """
 from __future__ import annotations
 

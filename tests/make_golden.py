@@ -6,8 +6,8 @@ on the oracle's seeded random-init SD-1.x UNet restatement (no pretrained weight
 Runs only in the build container (the GPU box has no /root/reference); the resulting tensors are committed so
 that tests on the GPU box can compare the CUDA path and the oracle port against the reference's own outputs.
 
-    python tools/make_golden.py --config tiny      # seconds
-    python tools/make_golden.py --config sd15      # BASELINE.json configs[0]: full SD-1.5 UNet, T=10, ~10 min CPU
+    python tests/make_golden.py --config tiny      # seconds
+    python tests/make_golden.py --config sd15      # BASELINE.json configs[0]: full SD-1.5 UNet, T=10, ~10 min CPU
 """
 import argparse
 import os
@@ -89,7 +89,7 @@ def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
                      unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
                                cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
                      weights="oracle.sd_unet.seeded_init_(seed=0)", w0="randn(seed 0)*0.18215*5",
-                     generator="tools/make_golden.py", seconds=dict(inversion=t_inv, edit=t_edit),
+                     generator="tests/make_golden.py", seconds=dict(inversion=t_inv, edit=t_edit),
                      torch=torch.__version__, threads=torch.get_num_threads()),
         "w0": w0, "zs": zs[:T].clone(), "xT": wts[T].clone(),
         "ctx_uncond": enc(model, [""]), "ctx_src": enc(model, [PROMPTS[0]]), "ctx_tar": enc(model, [PROMPTS[1]]),
@@ -179,7 +179,7 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
                      weight_reconstruction=0.1, is_replace=False, blend=(mode == "p2p_explicit"),
                      unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
                                cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
-                     weights="oracle.sd_unet.seeded_init_(seed=0)", generator="tools/make_golden.py", torch=torch.__version__, **meta_extra),
+                     weights="oracle.sd_unet.seeded_init_(seed=0)", generator="tests/make_golden.py", torch=torch.__version__, **meta_extra),
         "w0": w0, "zs": kw["zs"].clone(), "xT": kw["xT"].clone(),
         "ctx_uncond": enc(model, [""]), "ctx_src": enc(model, [prompts[0]]), "ctx_tar": enc(model, [prompts[1]]),
         "edited": edited.detach().clone(), "recon": recon.detach().clone(),
@@ -263,7 +263,7 @@ def run_style(name="tiny_style_mos2", T=4, K=2, weight=0.5):
                         unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
                                   cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
                         vae="oracle.vae.AutoencoderKLDecoder(VAEConfig.tiny(), seed 7)", clip="oracle.clip_visual.tiny_style_encoder(seed 11)",
-                        generator="tools/make_golden.py --config style", torch=torch.__version__),
+                        generator="tests/make_golden.py --config style", torch=torch.__version__),
            "w0": w0, "zs": zs[:T].clone(), "xT": wts[T].clone(),
            "ctx_uncond": enc_t(model, [""]), "ctx_src": enc_t(model, [PROMPTS[0]]), "ctx_tar": enc_t(model, [PROMPTS[1]]),
            "edited": edited.detach().clone(), "recon": recon.detach().clone(), "edited_no_style": edited_ns.detach().clone()}
@@ -308,7 +308,7 @@ def run_face(name="tiny_face_k2", T=5, K=2, weight=50.0):
     out = {"meta": dict(name=name, mode="face", T=T, K=K, weight_edit_face=weight, seq=[int(v) for v in seq],
                         unet=dict(ch=cfg.ch, ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks, attn_resolutions=list(cfg.attn_resolutions),
                                   image_size=cfg.image_size),
-                        rewards="oracle.face_unet.TinyIDLoss(seed 21) / TinyLPIPSLoss(seed 22)", generator="tools/make_golden.py --config face",
+                        rewards="oracle.face_unet.TinyIDLoss(seed 21) / TinyLPIPSLoss(seed 22)", generator="tests/make_golden.py --config face",
                         torch=torch.__version__),
            "x0": x0, "ref_img": ref_img, "zs": zs[:T].clone(), "xT": xts[T].clone(), "betas": betas,
            "edited": edited.detach().clone(), "no_reward": recon.detach().clone()}

@@ -1,6 +1,6 @@
 """Loads the UNMODIFIED reference sampler modules from /root/reference/text-guided (this container only; the GPU
 box has no /root/reference) behind the import shims in tests/refshim.  Used by tests/test_oracle_pin.py and
-tools/make_golden.py to pin the oracle."""
+tests/make_golden.py to pin the oracle."""
 import os
 import sys
 

@@ -1,6 +1,6 @@
 """GPU: face-swapping path -- the native pixel-space DDPM UNet against the oracle restatement of the reference's
 `Model` (pinned to the reference class on CPU), and the native `h_Edit_R` loop against outputs of the UNMODIFIED reference sampler
-(tools/make_golden.py --config face)."""
+(tests/make_golden.py --config face)."""
 import os
 import sys
 

@@ -1,5 +1,5 @@
 """GPU: combined text-guided + style editing -- the native loop with the reward hook against the outputs of the
-UNMODIFIED reference sampler text-guided-n-style/inversion/h_edit.py:14 (tools/make_golden.py --config style)."""
+UNMODIFIED reference sampler text-guided-n-style/inversion/h_edit.py:14 (tests/make_golden.py --config style)."""
 import os
 import sys
 

@@ -126,14 +126,14 @@ def test_edit_loop_tiny_noblend():
 @pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "sd15_config1.pt")), reason="full-size golden missing")
 def test_edit_loop_sd15_config1():
     """BASELINE.json configs[0]: full SD-1.5 geometry, 1 image, 10 DDIM steps, implicit h-Edit-R + P2P (Refine+Reweight+LocalBlend),
-    against outputs of the UNMODIFIED reference loop (tools/make_golden.py)."""
+    against outputs of the UNMODIFIED reference loop (tests/make_golden.py)."""
     r_ed, r_rc, r_w0, st = _run_golden("sd15_config1")
     assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # other reference samplers on the same hot path (SURVEY 8a rows 2 and 10), each against a golden produced by the
-# unmodified reference function (tools/make_golden.py --config variants)
+# unmodified reference function (tests/make_golden.py --config variants)
 def _run_variant(name, eng_cache={}):
     _fp32()
     g = load_golden(name)

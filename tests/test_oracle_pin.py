@@ -1,5 +1,5 @@
 """CPU: pins the oracle.  (1) against the committed golden fixtures produced by the UNMODIFIED reference loop
-(tools/make_golden.py) -- runs anywhere; (2) live against the reference's own set-up classes when /root/reference
+(tests/make_golden.py) -- runs anywhere; (2) live against the reference's own set-up classes when /root/reference
 is present (build container only)."""
 import pytest
 import torch
