@@ -133,6 +133,19 @@ def h_Edit_masactrl_implicit(model, xT, eta=1.0, prompts="", cfg_scales=None, pr
     return out
 
 
+def h_Edit_masactrl_explicit(model, xT, eta=1.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, after_skip_steps=35,
+                             is_ddim_inversion=True):
+    """Explicit-form h-Edit with MasaCtrl (BASELINE.json configs[2]).  The reference ships NO function of this form (only
+    `h_Edit_masactrl_implicit`); this composes the update of `h_Edit_p2p_explicit` (p2p_h_edit.py:480-514) with the MasaCtrl editor
+    active in its attention-controlled call, as SURVEY 8d describes.  One 5-sample UNet launch per step."""
+    ed = getattr(model, "_hedit_masactrl_editor", None)
+    assert ed is not None, "call regiter_attention_editor_diffusers(model, MutualSelfAttentionControl(...)) first"
+    out = _single(model, xT, eta, prompts, cfg_scales, zs, None, 0.0, 1, after_skip_steps, is_ddim_inversion, True,
+                  masactrl=(ed.start_step - ed.cur_step, ed.start_layer), mos_pull=False)
+    ed.cur_step += after_skip_steps
+    return out
+
+
 # ---- Plug-and-Play (text-guided/plug_n_play/pnp_utils.py, inversion/pnp_h_edit.py) ---------------------------------------
 PNP_ATTN_BLOCKS = {1: [1, 2], 2: [0, 1, 2], 3: [0, 1, 2]}     # pnp_utils.py:88: decoder self-attention layers 4-11
 

@@ -274,3 +274,26 @@ def test_h_edit_step_equals_loop():
     assert m_ed == 0.0 and m_rc == 0.0
     r_g, _ = rel_err(xt[:, 1].cpu(), g["edited"])
     assert r_g < TOL_LOOP
+
+
+def test_masactrl_explicit_composition():
+    """BASELINE configs[2] names an explicit-form MasaCtrl sampler that the reference does not ship; the composed variant must reduce to
+    the explicit no-control update when the editor never becomes active, and differ from it when it is."""
+    _fp32()
+    g = load_golden("tiny_masactrl_mos2")
+    meta = g["meta"]
+    model = OraclePipeline(cfg_from_meta(meta), seed=0)
+    T = meta["T"]
+    model.scheduler.set_timesteps(T)
+    kw = dict(xT=g["xT"].cuda(), eta=1.0, prompts=meta["prompts"], cfg_scales=meta["cfg_scales"], zs=g["zs"].cuda(), after_skip_steps=T,
+              is_ddim_inversion=False)
+    hedit_b200.regiter_attention_editor_diffusers(model, hedit_b200.MutualSelfAttentionControl(meta["masa_start_step"], meta["masa_start_layer"], total_steps=T))
+    ed_on, rc_on = hedit_b200.h_Edit_masactrl_explicit(model, **kw)
+    eng = hedit_b200.get_engine(model)
+    assert eng.last_stats["sample_forwards"] == 5 * T
+    hedit_b200.regiter_attention_editor_diffusers(model, hedit_b200.MutualSelfAttentionControl(T + 5, meta["masa_start_layer"], total_steps=T))
+    ed_off, rc_off = hedit_b200.h_Edit_masactrl_explicit(model, **kw)
+    ed_ref, rc_ref = hedit_b200.h_Edit_p2p_explicit(model, controller=None, **kw)
+    assert (ed_off - ed_ref).abs().max().item() == 0.0 and (rc_off - rc_ref).abs().max().item() == 0.0
+    assert torch.isfinite(ed_on).all() and rel_err(ed_on, ed_off)[0] > 1e-2
+    assert rel_err(rc_on, rc_off)[0] < 1e-6          # the reconstruction row never reads the edit row
