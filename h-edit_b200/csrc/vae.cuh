@@ -112,7 +112,7 @@ struct GNBwdParams {
 };
 
 HEDIT_DEVICE float silu_grad_f(float y) {
-  const float s = 1.0f / (1.0f + __expf(-y));
+  const float s = __fdividef(1.0f, 1.0f + __expf(-y));
   return s * fmaf(y, 1.0f - s, 1.0f);
 }
 
