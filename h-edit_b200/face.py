@@ -198,3 +198,51 @@ def h_Edit_R(model, lpipsloss, idloss, xT, betas, seq, eta=1.0, zs=None, weight_
                    id_grad=_reward_grad(idloss.get_cosine_loss if idloss else None),
                    lpips_grad=_reward_grad(lpipsloss.get_lpips_loss if lpipsloss else None), mask=soft_face_mask)
     return out.to(dev)
+
+
+@torch.no_grad()
+def sample_xts_from_x0_sde(model, x0, betas, seq, num_inference_steps=100):
+    """Reference signature (face-swapping/inversion/sde_inversion.py:4): independent draws x_t ~ q(x_t | x_0), seeded 42 like the reference."""
+    torch.manual_seed(42)
+    torch.cuda.manual_seed(42)
+    ab = (1.0 - betas).cumprod(dim=0)
+    pos = {int(v): k for k, v in enumerate(seq)}
+    shape = (num_inference_steps + 1,) + tuple(x0.shape[1:])
+    xts = torch.zeros(shape, device=x0.device)
+    noise_added = torch.zeros(shape, device=x0.device)
+    xts[0] = x0[0]
+    for t in reversed(list(seq)):
+        idx = num_inference_steps - pos[int(t)]
+        noise = torch.randn_like(x0)
+        xts[idx] = (x0 * (ab[int(t)] ** 0.5) + noise * ((1 - ab[int(t)]) ** 0.5))[0]
+        noise_added[idx] = noise[0]
+    return xts, noise_added
+
+
+@torch.no_grad()
+def inversion_forward_process_sde(model, x0, betas, seq, etas=1.0, num_inference_steps=100, device=None):
+    """Reference signature (face-swapping/inversion/sde_inversion.py:54); returns (xt, zs, xts, noise_added).  Given the independently
+    sampled x_t's the T noise predictions do not depend on each other, so they are ONE batched denoiser call on the native engine instead
+    of T calls of batch 1."""
+    assert not (etas is None or (isinstance(etas, (int, float)) and etas == 0)), "eta must be > 0 (reference assert, sde_inversion.py:127)"
+    T = num_inference_steps
+    etas = [etas] * T if isinstance(etas, (int, float)) else list(etas)
+    ts = [int(t) for t in seq]
+    xts, noise_added = sample_xts_from_x0_sde(model, x0, betas, seq, num_inference_steps=T)
+    eng = get_face_engine(model, x0.device.index or 0 if x0.device.type == "cuda" else 0)
+    dev = torch.device("cuda", eng.device)
+    ab = (1.0 - betas.to(dev)).cumprod(dim=0)
+    x_in = torch.stack([xts[T - k] for k in range(T)]).to(dev)              # step k (timestep ts[k]) starts from xts[T - k]
+    eps = torch.cat([eng(x_in[lo:lo + 16], ts[lo:lo + 16]) for lo in range(0, T, 16)])
+    zs = torch.zeros((T,) + tuple(x0.shape[1:]), device=x0.device)
+    for k, t in enumerate(ts):
+        idx = T - k - 1
+        tm1 = ts[k + 1] if k < T - 1 else 0
+        x0_hat = (x_in[k] - (1 - ab[t]) ** 0.5 * eps[k]) / ab[t] ** 0.5
+        c1 = (1 - ab[tm1]).sqrt() * 0.5
+        c2 = (1 - ab[tm1]).sqrt() * ((1 - 0.5 ** 2) ** 0.5)
+        mu = ab[tm1].sqrt() * x0_hat + c2 * eps[k]
+        z = (xts[idx].to(dev) - mu) / (etas[idx] * c1)
+        zs[idx] = z.to(x0.device)
+        xts[idx] = (mu + (etas[idx] * c1) * z).to(x0.device)
+    return xts[1][None], zs, xts, noise_added

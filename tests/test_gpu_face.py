@@ -80,3 +80,21 @@ def test_face_h_edit_R_matches_reference_golden():
     print(f"face h_Edit_R: edited rel {r_ed:.3e} max {m_ed:.3e} | no-reward rel {r_nr:.3e} (returns x0 to {r_x0:.3e}) | distance edited<->no-reward {r_far:.3e}")
     assert r_ed < TOL_LOOP and r_nr < TOL_LOOP and r_x0 < TOL_LOOP
     assert r_far > 5 * TOL_LOOP
+
+
+def test_face_sde_inversion_matches_reference_golden():
+    """inversion_forward_process_sde (sde_inversion.py:54) on the native denoiser: same seed-42 draws as the reference, all T noise
+    predictions in one batched call; z_t against the tensors the reference produced for the face golden."""
+    _fp32()
+    g = load_golden("tiny_face_k2")
+    meta = g["meta"]
+    u = meta["unet"]
+    cfg = FaceUNetConfig(ch=u["ch"], ch_mult=tuple(u["ch_mult"]), num_res_blocks=u["num_res_blocks"], attn_resolutions=tuple(u["attn_resolutions"]),
+                         image_size=u["image_size"])
+    model = FaceUNet(cfg)          # CPU module: only its weights are used
+    T = meta["T"]
+    _, zs, xts, _ = hedit_b200.face.inversion_forward_process_sde(model, g["x0"], g["betas"], meta["seq"], etas=1.0, num_inference_steps=T)
+    r_x, _ = rel_err(xts[T], g["xT"])
+    r_z, m_z = rel_err(zs, g["zs"])
+    print(f"face sde inversion: xT rel {r_x:.3e} | zs rel {r_z:.3e} max {m_z:.3e}")
+    assert r_x < 1e-6 and r_z < 2e-2
