@@ -303,9 +303,11 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
             }
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            stg[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q] * gelu_fast_f(v[16 + 4 * q]), v[4 * q + 1] * gelu_fast_f(v[17 + 4 * q]),
-                                                           v[4 * q + 2] * gelu_fast_f(v[18 + 4 * q]), v[4 * q + 3] * gelu_fast_f(v[19 + 4 * q]));
+          for (int q = 0; q < 4; ++q) {
+            const float2 g0 = gelu_fast_f2(make_float2(v[16 + 4 * q], v[17 + 4 * q])), g1 = gelu_fast_f2(make_float2(v[18 + 4 * q], v[19 + 4 * q]));
+            const float2 o0 = __fmul2_rn(make_float2(v[4 * q], v[4 * q + 1]), g0), o1 = __fmul2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), g1);
+            stg[lane * 8 + (q ^ (lane & 7))] = make_float4(o0.x, o0.y, o1.x, o1.y);
+          }
           __syncwarp();
           op_t* go = e.out_bf16 + size_t(rbase + gr) * e.ldob + (col >> 1) + 4 * gq;
 #pragma unroll
