@@ -16,6 +16,7 @@ from .samplers import (HEditStepper, h_edit_step, MutualSelfAttentionControl, en
 from . import style  # noqa: F401,E402
 from .vae import VaeDecoderEngine, VaeEncoderEngine, vae_config_of  # noqa: F401,E402
 from .clip_gram import ClipGramEngine  # noqa: F401,E402
+from .text_encoder import TextEncoderEngine  # noqa: F401,E402
 from . import face  # noqa: F401,E402
 from .face import FaceUNetEngine  # noqa: F401,E402
 from .inversion import ddim_inversion, inversion_forward_process_ddpm, sample_xts_from_x0  # noqa: F401,E402

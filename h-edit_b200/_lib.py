@@ -22,6 +22,10 @@ class VaeConfigC(C.Structure):
                 ("layers_per_block", C.c_int32), ("norm_groups", C.c_int32)]
 
 
+class TextConfigC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("vocab", "width", "heads", "layers", "ffn", "tokens")]
+
+
 class ClipConfigC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("resolution", "patch", "width", "heads", "layers")]
 
@@ -100,6 +104,11 @@ SYMBOLS = {
     "hedit_vae_decode": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "hedit_vae_decode_backward": (_I, [_P, _P, _P, _P]),
     "hedit_vae_last_flops": (C.c_double, [_P]),
+    "hedit_text_create": (_P, [C.POINTER(TextConfigC), _I]),
+    "hedit_text_destroy": (None, [_P]),
+    "hedit_text_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
+    "hedit_text_finalize": (_I, [_P]),
+    "hedit_text_encode": (_I, [_P, _P, _I, _P, _P]),
     "hedit_clip_create": (_P, [C.POINTER(ClipConfigC), _I]),
     "hedit_clip_destroy": (None, [_P]),
     "hedit_clip_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),

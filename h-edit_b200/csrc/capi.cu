@@ -12,6 +12,7 @@
 #include "vae.h"
 #include "vae_enc.h"
 #include "clip.h"
+#include "clip_text.h"
 #include "face.h"
 
 namespace hedit {
@@ -38,6 +39,11 @@ struct hedit_engine {
 
 struct hedit_face {
   FaceUNet* U;
+  int device;
+};
+
+struct hedit_text {
+  ClipText* T;
   int device;
 };
 
@@ -318,6 +324,53 @@ int hedit_vae_encode(hedit_vae_enc* v, const float* img, float* moments, int B, 
   cudaSetDevice(v->device);
   if (v->E->encode(img, moments, B, H, W, reinterpret_cast<cudaStream_t>(stream))) return fail(v->E->error());
   return int(v->E->launches());
+}
+
+// ------------------------------------------------------------------------------------------------ CLIP text tower
+hedit_text* hedit_text_create(const hedit_text_config* cfg, int device) {
+  if (!cfg) { fail("null config"); return nullptr; }
+  if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only"); return nullptr; }
+  TextCfg c;
+  c.vocab = cfg->vocab; c.width = cfg->width; c.heads = cfg->heads; c.layers = cfg->layers; c.ffn = cfg->ffn; c.tokens = cfg->tokens;
+  if (c.heads < 1 || c.width != 64 * c.heads || c.tokens < 1 || c.tokens > 256 || c.layers < 1 || c.ffn % 64 || c.vocab < 1) {
+    fail("unsupported CLIP text config (need head dim 64, <= 256 tokens, ffn % 64 == 0)");
+    return nullptr;
+  }
+  hedit_text* h = new hedit_text();
+  h->device = device;
+  h->T = new ClipText(c);
+  if (!h->T->ok()) { fail(h->T->error()); delete h->T; delete h; return nullptr; }
+  return h;
+}
+void hedit_text_destroy(hedit_text* t) {
+  if (!t) return;
+  cudaSetDevice(t->device);
+  delete t->T;
+  delete t;
+}
+int hedit_text_load_tensor(hedit_text* t, const char* name, const float* data, const int64_t* dims, int ndim) {
+  if (!t) return fail("null text encoder");
+  cudaSetDevice(t->device);
+  const int r = t->T->load_tensor(name, data, dims, ndim, 0);
+  if (r < 0) return fail(t->T->error(), r);
+  return r;
+}
+int hedit_text_finalize(hedit_text* t) {
+  if (!t) return fail("null text encoder");
+  std::string missing;
+  if (t->T->finalize(&missing)) return fail(t->T->error());
+  return 0;
+}
+int hedit_text_encode(hedit_text* t, const int32_t* ids, int B, float* out, void* stream) {
+  if (!t) return fail("null text encoder");
+  cudaSetDevice(t->device);
+  if (t->T->forward(ids, B, out, reinterpret_cast<cudaStream_t>(stream))) return fail(t->T->error());
+  return int(t->T->launches());
 }
 
 // ------------------------------------------------------------------------------------------------ face swapping

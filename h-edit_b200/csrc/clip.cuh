@@ -56,6 +56,14 @@ static __global__ void unpatchify_kernel(const float* __restrict__ gp, float* __
     gimg[i] = post * gp[((size_t(b) * G + gy) * G + gx) * K + (c * P + py) * P + px];
   }
 }
+// token + position embedding: x[b][t][:] = tok[ids[b][t]][:] + pos[t][:]   (CLIP text tower)
+static __global__ void embed_tokens_kernel(const int* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                                           float* __restrict__ x, int T, int W, int vocab) {
+  const int r = blockIdx.x, t = r % T;
+  int id = ids[r];
+  id = min(max(id, 0), vocab - 1);
+  for (int c = threadIdx.x; c < W; c += blockDim.x) x[size_t(r) * W + c] = tok[size_t(id) * W + c] + pos[size_t(t) * W + c];
+}
 // class-token rows: x[b][0][:] = class_embedding + positional_embedding[0]
 static __global__ void class_token_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos, int T, int W) {
   const int b = blockIdx.x;
@@ -148,7 +156,8 @@ HEDIT_DEVICE void att_load_rows(op_t* dst, const op_t* src, int N, int ld_src) {
   }
 }
 
-static __global__ void att_small_fwd_kernel(const op_t* __restrict__ qkv, float* __restrict__ P, op_t* __restrict__ out, int N, int H, float scale) {
+static __global__ void att_small_fwd_kernel(const op_t* __restrict__ qkv, float* __restrict__ P, op_t* __restrict__ out, int N, int H, float scale,
+                                            int causal = 0) {
   extern __shared__ __align__(16) uint8_t att_sm[];
   op_t* sK = reinterpret_cast<op_t*>(att_sm);
   op_t* sV = sK + kAttMaxN * kAttLd;
@@ -170,7 +179,7 @@ static __global__ void att_small_fwd_kernel(const op_t* __restrict__ qkv, float*
     for (int u = 0; u < kAttMaxN / 32; ++u) {
       const int j = lane + 32 * u;
       float a = -INFINITY;
-      if (j < N) {
+      if (j < N && !(causal && j > row)) {
         a = 0.f;
         for (int c = 0; c < kAttD; c += 2) {
           const float2 kk = op2_to_float2(*reinterpret_cast<const uint32_t*>(sK + j * kAttLd + c));
@@ -184,7 +193,7 @@ static __global__ void att_small_fwd_kernel(const op_t* __restrict__ qkv, float*
     for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float l = 0.f;
 #pragma unroll
-    for (int u = 0; u < kAttMaxN / 32; ++u) { sc[u] = (lane + 32 * u < N) ? __expf(sc[u] - mx) : 0.f; l += sc[u]; }
+    for (int u = 0; u < kAttMaxN / 32; ++u) { sc[u] = (sc[u] > -INFINITY) ? __expf(sc[u] - mx) : 0.f; l += sc[u]; }
 #pragma unroll
     for (int o = 16; o; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
     const float inv = 1.f / l;
@@ -192,7 +201,7 @@ static __global__ void att_small_fwd_kernel(const op_t* __restrict__ qkv, float*
 #pragma unroll
     for (int u = 0; u < kAttMaxN / 32; ++u) {
       const int j = lane + 32 * u;
-      if (j < N) { const float p = sc[u] * inv; prow[j] = p; sP[warp * kAttMaxN + j] = p; }
+      if (j < N) { const float p = sc[u] * inv; if (P) prow[j] = p; sP[warp * kAttMaxN + j] = p; }
     }
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;

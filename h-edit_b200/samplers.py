@@ -13,10 +13,29 @@ from .p2p import compile_edit_plan
 from .schedule import skip_pre_coeff, step_tables
 
 
+def get_text_engine(model, device: int = 0):
+    """Native CLIP text tower built once from `model.text_encoder` when that is a transformers CLIPTextModel with quick_gelu (SD-1.x);
+    None otherwise (any other text-encoder object is simply called, as the reference does)."""
+    if hasattr(model, "_hedit_b200_text"):
+        return model._hedit_b200_text
+    eng = None
+    te = getattr(model, "text_encoder", None)
+    cfg = getattr(te, "config", None)
+    if te is not None and hasattr(te, "text_model") and getattr(cfg, "hidden_act", None) == "quick_gelu" and torch.cuda.is_available() and \
+            cfg.hidden_size == 64 * cfg.num_attention_heads:
+        from .text_encoder import TextEncoderEngine
+        eng = TextEncoderEngine.from_text_encoder(te, device=device)
+    model._hedit_b200_text = eng
+    return eng
+
+
 def encode_text(model, prompts: Union[str, List[str]]) -> torch.Tensor:
     """text-guided/inversion/inversion_utils.py:13-36 (tokenise to max_length, run the text encoder)."""
     tok = model.tokenizer(prompts, padding="max_length", max_length=model.tokenizer.model_max_length, truncation=True,
                           return_tensors="pt")
+    eng = get_text_engine(model)
+    if eng is not None:
+        return eng(tok.input_ids)[0]
     with torch.no_grad():
         return model.text_encoder(tok.input_ids.to(model.device))[0]
 

@@ -203,6 +203,17 @@ int hedit_clip_gram_loss(hedit_clip* c, const float* img, int B, int H, int W, f
 /* dimg [B][3][H][W] = d loss[b] / d img[b] of the last gram_loss call */
 int hedit_clip_gram_backward(hedit_clip* c, float* dimg, void* stream);
 
+/* ---- CLIP text tower: `model.text_encoder(ids)[0]` as called by encode_text (text-guided/inversion/inversion_utils.py:13-36).
+ * Weights by transformers' CLIPTextModel parameter names ("text_model.embeddings.token_embedding.weight", ...); head dim must be 64. */
+typedef struct hedit_text hedit_text;
+typedef struct hedit_text_config { int32_t vocab, width, heads, layers, ffn, tokens; } hedit_text_config;
+hedit_text* hedit_text_create(const hedit_text_config* cfg, int device);
+void hedit_text_destroy(hedit_text* t);
+int hedit_text_load_tensor(hedit_text* t, const char* name, const float* data, const int64_t* dims, int ndim);
+int hedit_text_finalize(hedit_text* t);
+/* ids [B][tokens] int32 (host) -> last_hidden_state [B][tokens][width] (device fp32) */
+int hedit_text_encode(hedit_text* t, const int32_t* ids, int B, float* out, void* stream);
+
 /* ---- face swapping: the pixel-space DDPM denoiser `model(x, t)` (face-swapping/diffusion/diffusion.py:193-341; weights by the
  * reference's parameter names: "temb.dense.0.weight", "conv_in.weight", "down.0.block.0.norm1.weight", ...) and the reward-guided
  * sampler `h_Edit_R` (face-swapping/inversion/h_edit_R.py:7-137). */
