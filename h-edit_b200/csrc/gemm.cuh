@@ -281,8 +281,45 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
         }
       };
       prefetch(n0 + half * 32);
+      // GEGLU: the bias of all columns this warp will touch in this tile (up to 4 chunks x 32), one float4 per lane, fetched while the
+      // accumulator is still being computed; the chunks below read it with shuffles instead of 8 exposed global loads per chunk
+      float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e.geglu && e.bias) {
+        const int gc = n0 + half * 32 + 64 * (lane >> 3) + 4 * (lane & 7);
+        if (gc + 4 <= p.N && half * 32 + 64 * (lane >> 3) < BN) gb = *reinterpret_cast<const float4*>(e.bias + gc);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      // 16-bit outputs without bias / residual (q|k|v, q, text k|v projections): 64 columns per iteration, converted to 16 bits BEFORE the
+      // staging transpose (so the 4 KB tile holds 32 rows x 64 columns) and written back as full 128-byte lines -- half the latency-bound
+      // iterations and half the store instructions of the 32-column path.
+      const bool wide16 = (BN == 256) && mode == 4 && rows_full && ((p.N - n0) >= BN || ((p.N - n0) & 63) == 0);
+      if (wide16) {
+        op_t* stg16 = reinterpret_cast<op_t*>(stg);
+        const int wu = lane & 7, wr = lane >> 3;
+#pragma unroll 1
+        for (int c0 = half * 64; c0 < BN; c0 += 128) {
+          const int col = n0 + c0;
+          if (col + 64 > p.N) break;                  // warp-uniform
+          uint32_t raw[64];
+          tmem_ld32(t_row + c0, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+          tmem_ld32(t_row + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<uint4*>(stg16 + lane * 64 + ((u ^ (lane & 7)) << 3)) =
+                make_uint4(pack_op2(__uint_as_float(raw[8 * u]), __uint_as_float(raw[8 * u + 1])), pack_op2(__uint_as_float(raw[8 * u + 2]), __uint_as_float(raw[8 * u + 3])),
+                           pack_op2(__uint_as_float(raw[8 * u + 4]), __uint_as_float(raw[8 * u + 5])), pack_op2(__uint_as_float(raw[8 * u + 6]), __uint_as_float(raw[8 * u + 7])));
+          __syncwarp();
+          op_t* o16 = e.out_bf16 + size_t(rbase + wr) * e.ldob + col + 8 * wu;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + wr;
+            *reinterpret_cast<uint4*>(o16 + size_t(4 * i) * e.ldob) = *reinterpret_cast<const uint4*>(stg16 + r * 64 + ((wu ^ (r & 7)) << 3));
+          }
+          __syncwarp();
+        }
+      } else
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BN; c0 += 64) {
         const int col = n0 + c0;
@@ -296,10 +333,11 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
           if (e.bias) {
+            const int src0 = ((c0 - half * 32) >> 6) << 3;        // lanes holding this chunk's 8 float4
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(e.bias + col + j);
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] += __shfl_sync(0xffffffffu, gb.x, src0 + j); v[4 * j + 1] += __shfl_sync(0xffffffffu, gb.y, src0 + j);
+              v[4 * j + 2] += __shfl_sync(0xffffffffu, gb.z, src0 + j); v[4 * j + 3] += __shfl_sync(0xffffffffu, gb.w, src0 + j);
             }
           }
 #pragma unroll
