@@ -266,21 +266,24 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
       const bool rows_full = (rbase + 32 <= p.M);
       const uint32_t t_row = tmem_base + acc * 256 + (uint32_t(quarter * 32) << 16);
       const size_t row0 = size_t(rbase + rr);
-      float4 rs[8];
-      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), rvv = bb;
-      auto prefetch = [&](int col) {       // operands of the write-back that do not depend on the accumulator
+      // Operands of the write-back that do not depend on the accumulator (bias, time-embedding row, residual) are double-buffered: the
+      // set of chunk c+1 is requested BEFORE the write-back of chunk c, so its global-load latency hides behind that write-back and the
+      // next chunk's TMEM read (the epilogue of the small-K layers is latency-bound, not bandwidth-bound).
+      float4 rs[8], rsN[8];
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), rvv = bb, bbN = bb, rvvN = bb;
+      auto prefetch = [&](int col, float4& b_, float4& rv_, float4 (&r_)[8]) {
         if (mode != 0 && rows_full && col + 32 <= p.N) {
           const int cq = col + 4 * rq;
-          if (has_b) bb = *reinterpret_cast<const float4*>(e.bias + cq);
-          if (mode == 3) rvv = *reinterpret_cast<const float4*>(e.rowvec + size_t(rbase / e.rows_per_group) * e.ldrv + cq);
+          if (has_b) b_ = *reinterpret_cast<const float4*>(e.bias + cq);
+          if (mode == 3) rv_ = *reinterpret_cast<const float4*>(e.rowvec + size_t(rbase / e.rows_per_group) * e.ldrv + cq);
           if (has_res) {
             const float* rp = e.residual + row0 * e.ldr + cq;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rs[i] = *reinterpret_cast<const float4*>(rp + size_t(4 * i) * e.ldr);
+            for (int i = 0; i < 8; ++i) r_[i] = *reinterpret_cast<const float4*>(rp + size_t(4 * i) * e.ldr);
           }
         }
       };
-      prefetch(n0 + half * 32);
+      prefetch(n0 + half * 32, bb, rvv, rs);
       // GEGLU: the bias of all columns this warp will touch in this tile (up to 4 chunks x 32), one float4 per lane, fetched while the
       // accumulator is still being computed; the chunks below read it with shuffles instead of 8 exposed global loads per chunk
       float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -362,6 +365,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
           stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
                                                          __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
         __syncwarp();
+        if (c0 + 64 < BN) prefetch(col + 64, bbN, rvvN, rsN);      // next chunk of this warp (warp-uniform condition)
         const int cq = col + 4 * rq;
         if (mode != 0 && rows_full && col + 32 <= p.N) {
           float* o32 = has32 ? e.out_f32 + row0 * e.ldo + cq : nullptr;
@@ -408,7 +412,9 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
                                e.colstats + size_t(rbase >> 5) * p.N + cq);
         }
         __syncwarp();
-        prefetch(col + 64);                        // next chunk of this warp
+        bb = bbN; rvv = rvvN;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rs[i] = rsN[i];
       }
       tc_fence_before();
       __syncwarp();
