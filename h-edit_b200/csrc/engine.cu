@@ -824,7 +824,8 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
     }
     case OP_GN_APPLY: {
       const int C = op.C1 + op.C2;
-      const int chunk = op.HW >= 4096 ? 32 : 16;
+      static const int gn_chunk = getenv("HEDIT_GN_CHUNK") ? atoi(getenv("HEDIT_GN_CHUNK")) : 0;      // tuning switch
+      const int chunk = gn_chunk > 0 ? gn_chunk : (op.HW >= 4096 ? 32 : 16);
       const int quads_ = C / 4;
       const int threads = std::max(256, quads_ * std::max(1, (256 + quads_ - 1) / quads_));      // quads * nsub (<= 640)
       GNApplyParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, chunk, op.nchunks, op.partial, op.gamma, op.beta, op.eps, op.silu, op.h_out, op.h_out2, op.stats};
