@@ -16,7 +16,7 @@ namespace hedit {
 
 typedef op_t bf16;   // historical alias: "the 16-bit operand type"
 
-struct ConvGeom { int S, H, W, C; int stride; int pad01; };   // H,W = OUTPUT dims; C = input channels; pad01: stride-2 convs padded (0,1,0,1)
+struct ConvGeom { int S, H, W, C; int stride; int pad01; int ox, oy; };   // H,W = OUTPUT dims; C = input channels; pad01: stride-2 convs padded (0,1,0,1); ox, oy: first-tap offsets of A_CONV2X2
 // D[M][N] = A W^T launch description (TMA maps encoded here).  ldw = row stride of W in elements (0: dense [N][Ktot]).
 bool make_gemm(GemmParams& g, int& bn, const op_t* A, int lda, int a_mode, const ConvGeom* cg, const op_t* Wt, int M, int N, int Ktot,
                const GemmEpilogue& ep, std::string& err, int ldw = 0);
@@ -46,6 +46,7 @@ struct TfW {
 struct WeightSlot {
   enum Kind { F32_COPY, BF16_ROWS, BF16_CONV3, BF16_GEGLU_ROWS, F32_GEGLU_VEC } kind;
   void* dst = nullptr;
+  void* dst_up = nullptr;       // BF16_CONV3 of an upsampler: additionally the 4 pre-summed 2x2 phase kernels [4][O][2][2][I] (fused upsample conv)
   size_t dst_off_elems = 0;     // element offset inside dst (row-concatenated tensors)
   std::vector<int64_t> shape;   // expected source shape
   bool loaded = false;
@@ -144,7 +145,7 @@ class Engine {
   std::vector<ResW> res_;       // in forward order
   std::vector<TfW> tfs_;        // in forward order (== controller layer order / 2)
   std::vector<int> tf_tokens_;
-  std::vector<bf16*> down_w_, up_w_;
+  std::vector<bf16*> down_w_, up_w_, up_wp_;
   std::vector<float*> down_b_, up_b_;
   int n_blend_layers_ = 0;
   double flops_per_sample_ = 0;

@@ -10,12 +10,15 @@
 //   A_LINEAR   : 2-D map [M][K]                                   (linear layers, 1x1 convs)
 //   A_CONV3X3  : 4-D map (C, W, H, S); tap (ky,kx) = box shifted by (kx-1, ky-1); TMA zero-fills the padding
 //   A_CONV3X3S2: 5-D map (2C, W/2, 2, H/2, S) over the same memory = space-to-depth view for stride 2, pad 1
+//   A_CONV2X2  : 4-D map like A_CONV3X3, 4 taps (a,b) = box shifted by (b + conv_ox, a + conv_oy): one output phase of
+//                "nearest 2x upsample -> 3x3 conv" evaluated on the COARSE input with pre-summed weights (2.25x fewer flops);
+//                the epilogue scatters row (s,y,x) to the fine pixel (2y+py, 2x+px) (GemmEpilogue::up_*)
 #pragma once
 #include "ptx.cuh"
 
 namespace hedit {
 
-enum { A_LINEAR = 0, A_CONV3X3 = 1, A_CONV3X3S2 = 2 };
+enum { A_LINEAR = 0, A_CONV3X3 = 1, A_CONV3X3S2 = 2, A_CONV2X2 = 3 };
 
 struct GemmEpilogue {
   const float* bias;        // [N] or null
@@ -26,6 +29,8 @@ struct GemmEpilogue {
   int rows_per_group, ldrv, ldr, ldo, ldob;
   int geglu;                // 1: every 32-col chunk = 16 value | 16 gate -> bf16 out has N/2 columns
   int nchw_hw;              // >0: write out_f32 as [row / hw][N][row % hw] (NCHW latent layout; small-N generic path only)
+  int up_W, up_H, up_py, up_px;   // up_W > 0: GEMM row (s,y,x) of a coarse up_H x up_W grid is written to fine row (s, 2y+up_py, 2x+up_px)
+                            // (out_f32 + bias only); its colstats block goes to [s][phase][block] so that the 4 phases tile the sample
   float2* colstats;         // [ceil(M/32)][N] or null: (sum, sum of squares) of the fp32 output over each block of 32 rows, per
                             // column -- the GroupNorm statistics of the NEXT layer, produced while the tile is still in registers
 };
@@ -34,6 +39,7 @@ struct GemmParams {
   CUtensorMap tmA, tmB;
   int M, N, num_kb;
   int a_mode, conv_W, conv_H, conv_cin, cin_blocks;
+  int conv_ox, conv_oy;     // A_CONV2X2 only: first tap offset per axis (-1 for output phase 0, 0 for phase 1)
   int conv_pad01;           // A_CONV3X3S2 only: 0 = padding 1 on every side (SD downsampler); 1 = padding (0,1,0,1) (DDPM downsampler)
   GemmEpilogue ep;
 };
@@ -155,7 +161,10 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
         if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          const int ky = tap / 3, kx = tap - ky * 3;
+          const int kw = (p.a_mode == A_CONV2X2) ? 2 : 3;
+          const int ky = tap / kw, kx = tap - ky * kw;
+          // box shift of this tap: 3x3 -> (kx-1, ky-1); one phase of the fused upsample conv -> (kx + ox, ky + oy)
+          const int sx = (p.a_mode == A_CONV2X2) ? kx + p.conv_ox : kx - 1, sy = (p.a_mode == A_CONV2X2) ? ky + p.conv_oy : ky - 1;
           // stride 2: input x = 2X + kx - pad_left -> (parity, coarse offset) in the space-to-depth view
           const int px = p.conv_pad01 ? (kx == 1 ? 1 : 0) : (kx == 1 ? 0 : 1), dx = p.conv_pad01 ? (kx == 2 ? 1 : 0) : (kx == 0 ? -1 : 0);
           const int py = p.conv_pad01 ? (ky == 1 ? 1 : 0) : (ky == 1 ? 0 : 1), dy = p.conv_pad01 ? (ky == 2 ? 1 : 0) : (ky == 0 ? -1 : 0);
@@ -164,13 +173,13 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
             const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             if (p.a_mode == A_LINEAR) tma_load_2d_2sm(sa, &p.tmA, lfull, kb * 64, m0);
-            else if (p.a_mode == A_CONV3X3) tma_load_4d_2sm(sa, &p.tmA, lfull, cb * 64, x0 + kx - 1, y0 + ky - 1, s0);
+            else if (p.a_mode == A_CONV3X3 || p.a_mode == A_CONV2X2) tma_load_4d_2sm(sa, &p.tmA, lfull, cb * 64, x0 + sx, y0 + sy, s0);
             else tma_load_5d_2sm(sa, &p.tmA, lfull, px * p.conv_cin + cb * 64, x0 + dx, py, y0 + dy, s0);
             tma_load_2d_2sm(sb, &p.tmB, lfull, kb * 64, n0 + int(rank) * (BN / 2));
           } else {
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             if (p.a_mode == A_LINEAR) tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * 64, m0);
-            else if (p.a_mode == A_CONV3X3) tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * 64, x0 + kx - 1, y0 + ky - 1, s0);
+            else if (p.a_mode == A_CONV3X3 || p.a_mode == A_CONV2X2) tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * 64, x0 + sx, y0 + sy, s0);
             else tma_load_5d(sa, &p.tmA, &full_bar[stage], px * p.conv_cin + cb * 64, x0 + dx, py, y0 + dy, s0);
             // the W map's box is BN/2 rows (shared with the pair variant): two loads
             tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
@@ -365,6 +374,33 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
           stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
                                                          __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
         __syncwarp();
+        if (e.up_W > 0) {
+          // fused-upsample phase: bias + fp32 store to the fine-grid row of every coarse pixel, column statistics per (sample, phase)
+          const int cq = col + 4 * rq, hw = e.up_W * e.up_H;
+          float4 su = make_float4(0.f, 0.f, 0.f, 0.f), sq = su;
+          const bool cols_ok = (cq + 4 <= p.N);
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e.bias && cols_ok) b4 = *reinterpret_cast<const float4*>(e.bias + cq);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + rr, m = rbase + r;
+            float4 a = stg[r * 8 + (rq ^ (r & 7))];
+            a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+            if (m < p.M && cols_ok) {
+              const int sm_ = m / hw, rem = m - sm_ * hw, y = rem / e.up_W, x = rem - y * e.up_W;
+              const size_t frow = (size_t(sm_) * 2 * e.up_H + 2 * y + e.up_py) * (2 * e.up_W) + 2 * x + e.up_px;
+              *reinterpret_cast<float4*>(e.out_f32 + frow * e.ldo + cq) = a;
+              su.x += a.x; su.y += a.y; su.z += a.z; su.w += a.w;
+              sq.x = fmaf(a.x, a.x, sq.x); sq.y = fmaf(a.y, a.y, sq.y); sq.z = fmaf(a.z, a.z, sq.z); sq.w = fmaf(a.w, a.w, sq.w);
+            }
+          }
+          if (e.colstats && rbase < p.M && col + 32 <= p.N) {
+            const int nbc = hw >> 5, blk = rbase >> 5, sb = blk / nbc;
+            epi_store_colstats(su, sq, rr, e.colstats + size_t(blk + sb * 3 * nbc + (e.up_py * 2 + e.up_px) * nbc) * p.N + cq);
+          }
+          __syncwarp();
+          continue;
+        }
         if (c0 + 64 < BN) prefetch(col + 64, bbN, rvvN, rsN);      // next chunk of this warp (warp-uniform condition)
         const int cq = col + 4 * rq;
         if (mode != 0 && rows_full && col + 32 <= p.N) {
