@@ -54,24 +54,6 @@ __global__ void cvt_conv3_bf16_kernel(const float* __restrict__ src, bf16* __res
   }
 }
 
-// upsampler conv [O][I][3][3] fp32 -> the four phase kernels of "nearest 2x upsample -> 3x3 conv" on the coarse grid:
-// dst[p = py*2+px][o][a][b][i] = sum over the 3x3 taps (ky,kx) that land on coarse offset (a,b) for output phase (py,px):
-// phase 0: a=0 <- {k=0}, a=1 <- {k=1,2};  phase 1: a=0 <- {k=0,1}, a=1 <- {k=2}   (first-tap offset = phase - 1)
-__global__ void cvt_upconv_phases_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I) {
-  const size_t total = size_t(4) * O * 4 * I;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int ci = int(i % I), b = int((i / I) % 2), a = int((i / (size_t(I) * 2)) % 2), o = int((i / (size_t(I) * 4)) % O), p = int(i / (size_t(I) * 4 * O));
-    const int py = p >> 1, px = p & 1;
-    const int ky0 = (py == 0) ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), ky1 = (py == 0) ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
-    const int kx0 = (px == 0) ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kx1 = (px == 0) ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
-    const float* w = src + (size_t(o) * I + ci) * 9;
-    float acc = 0.f;
-    for (int ky = ky0; ky <= ky1; ++ky)
-      for (int kx = kx0; kx <= kx1; ++kx) acc += w[ky * 3 + kx];
-    dst[i] = to_op(acc);
-  }
-}
-
 template <typename T>
 T* Engine::dalloc(size_t n) {
   void* p = nullptr;

@@ -107,7 +107,14 @@ FaceUNet::FaceUNet(const FaceCfg& cfg) : cfg_(cfg) {
       cur = ch * cfg.mult[i];
       if (res == cfg.attn_res) { up_[i].attn.emplace_back(); reg_attn("up." + std::to_string(i) + ".attn." + std::to_string(j), cur, up_[i].attn.back()); }
     }
-    if (i != 0) { up_[i].has_resample = true; reg_conv3("up." + std::to_string(i) + ".upsample.conv", cur, cur, up_[i].resample); res *= 2; }
+    if (i != 0) {
+      up_[i].has_resample = true;
+      const std::string nm = "up." + std::to_string(i) + ".upsample.conv";
+      reg_conv3(nm, cur, cur, up_[i].resample);
+      up_[i].up_phases = walloc<op_t>(size_t(4) * cur * 4 * cur);
+      slots_[nm + ".weight"].dsts.push_back({Slot::CONV_UP_PHASES, up_[i].up_phases, 0, 0});
+      res *= 2;
+    }
   }
   no_g_ = walloc<float>(cur); no_b_ = walloc<float>(cur);
   reg("norm_out.weight", {cur}, {{Slot::F32, no_g_, 0, 0}}); reg("norm_out.bias", {cur}, {{Slot::F32, no_b_, 0, 0}});
@@ -158,6 +165,7 @@ int FaceUNet::load_tensor(const char* name, const float* src, const int64_t* dim
         case Slot::F32: FCK(cudaMemcpyAsync(d.dst, stage_, n * sizeof(float), cudaMemcpyDeviceToDevice, st)); break;
         case Slot::CONV_FWD: vae_cvt_weight_kernel<<<blocks, 256, 0, st>>>(stage_, reinterpret_cast<op_t*>(d.dst), O, I, 0, 0, 0); break;
         case Slot::ROWS: vae_cvt_weight_kernel<<<blocks, 256, 0, st>>>(stage_, reinterpret_cast<op_t*>(d.dst), O, I, 2, d.ld, d.off); break;
+        case Slot::CONV_UP_PHASES: cvt_upconv_phases_kernel<<<blocks, 256, 0, st>>>(stage_, reinterpret_cast<op_t*>(d.dst), O, I); break;
       }
     }
   }
@@ -271,18 +279,10 @@ int FaceUNet::run(const float* x, float* eps, int S) {
       if (!up_[i].attn.empty()) { if (attn_fwd(up_[i].attn[j], h, S, H * H, &g)) return -1; h = g; }
     }
     if (up_[i].has_resample) {
-      op_t* up = A<op_t>(size_t(S) * 4 * H * H * h.C);
-      if (!dry_) {
-        const size_t total = size_t(S) * 4 * H * H * (h.C / 4);
-        upsample2x_bf16_kernel<<<int(std::min<size_t>((total + 255) / 256, 16384)), 256, 0, st_>>>(h.x, up, S, H, H, h.C);
-        ++launches_;
-      }
+      float* y; float2* csy;
+      if (upconv_fused(h.x, up_[i].up_phases, up_[i].resample.b, S, H, H, h.C, &y, &csy)) return -1;
       H *= 2;
-      float* y = A<float>(size_t(S) * H * H * h.C);
-      GemmEpilogue e; memset(&e, 0, sizeof e);
-      e.bias = up_[i].resample.b; e.out_f32 = y; e.ldo = h.C; e.colstats = colstats_for(S * H * H, h.C, H * H);
-      if (conv3(up, up_[i].resample.w, S, H, H, h.C, h.C, e)) return -1;
-      h = Act{y, e.colstats, h.C};
+      h = Act{y, csy, h.C};
     }
   }
   op_t* fin = A<op_t>(size_t(S) * H * H * h.C);

@@ -29,7 +29,7 @@ class FaceUNet : public NetExec {
 
  private:
   struct Slot {
-    enum Kind { F32, CONV_FWD, ROWS };
+    enum Kind { F32, CONV_FWD, ROWS, CONV_UP_PHASES };
     struct Dst { Kind kind; void* dst; int ld; int off; };
     std::vector<int64_t> shape;
     std::vector<Dst> dsts;
@@ -38,7 +38,7 @@ class FaceUNet : public NetExec {
   struct Conv3W { op_t* w = nullptr; float* b = nullptr; int O = 0, I = 0; };
   struct ResW { int cin = 0, cout = 0, temb_off = 0; float *n1g = 0, *n1b = 0, *n2g = 0, *n2b = 0, *bsc = 0; Conv3W c1, c2; op_t* wsc = 0; };
   struct AttnW { int C = 0; float *gng = 0, *gnb = 0, *b_qkv = 0, *b_o = 0; op_t *w_qkv = 0, *w_o = 0; };
-  struct Level { std::vector<ResW> res; std::vector<AttnW> attn; Conv3W resample; bool has_resample = false; };
+  struct Level { std::vector<ResW> res; std::vector<AttnW> attn; Conv3W resample; op_t* up_phases = nullptr; bool has_resample = false; };
   struct Act { float* x; float2* cs; int C; };
 
   template <typename T> T* walloc(size_t n);

@@ -77,6 +77,23 @@ int NetExec::gn_fwd(const float* x1, const float2* cs1, int C1, const float* x2,
   return 0;
 }
 
+int NetExec::upconv_fused(const float* x, const op_t* w_phases, const float* bias, int S, int H, int W, int C, float** out, float2** cs_out) {
+  const int M0 = S * H * W;
+  op_t* xb = A<op_t>(size_t(M0) * C);
+  if (!dry_) { vae_cast_kernel<<<4096, 256, 0, st_>>>(x, xb, size_t(M0) * C / 4); ++launches_; }
+  float* y = A<float>(size_t(4) * M0 * C);
+  float2* cs = colstats_for(4 * M0, C, 4 * H * W);
+  for (int ph = 0; ph < 4; ++ph) {
+    ConvGeom cg{S, H, W, C, 1, 0, (ph & 1) - 1, (ph >> 1) - 1};
+    GemmEpilogue e; memset(&e, 0, sizeof e);
+    e.bias = bias; e.out_f32 = y; e.ldo = C; e.colstats = cs;
+    e.up_W = W; e.up_H = H; e.up_py = ph >> 1; e.up_px = ph & 1;
+    if (gemm(xb, C, A_CONV2X2, &cg, w_phases + size_t(ph) * C * 4 * C, M0, C, 4 * C, e)) return -1;
+  }
+  *out = y; *cs_out = cs;
+  return 0;
+}
+
 int NetExec::attn1h_fwd(const float* x, const float2* cs_x, int S, int N, int C, const float* gng, const float* gnb, float eps, const op_t* w_qkv,
                         const float* b_qkv, const op_t* w_o, const float* b_o, float** out, float2** cs_out, float2** gn_stats_out,
                         const op_t** qkv_out, const op_t** P_out) {

@@ -43,6 +43,10 @@ class NetExec {
                  const float* b_qkv, const op_t* w_o, const float* b_o, float** out, float2** cs_out, float2** gn_stats_out = nullptr,
                  const op_t** qkv_out = nullptr, const op_t** P_out = nullptr);
 
+  // nearest-2x upsample -> 3x3 conv (bias) as four 2x2 phase convs on the coarse grid (weights from cvt_upconv_phases_kernel):
+  // x fp32 [S][H][W][C] -> *out fp32 [S][2H][2W][C] with column statistics in *cs_out
+  int upconv_fused(const float* x, const op_t* w_phases, const float* bias, int S, int H, int W, int C, float** out, float2** cs_out);
+
   int groups_ = 32;
   uint8_t* arena_ = nullptr;
   size_t arena_bytes_ = 0, top_ = 0, peak_ = 0;

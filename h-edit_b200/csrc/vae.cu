@@ -99,7 +99,12 @@ VaeDecoder::VaeDecoder(const VaeCfg& cfg) : cfg_(cfg) {
       up_res_[i].emplace_back();
       reg_res("decoder.up_blocks." + std::to_string(i) + ".resnets." + std::to_string(l), l == 0 ? prev : c, c, up_res_[i].back());
     }
-    if (i < 3) reg_conv3("decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv", c, c, up_conv_[i]);
+    if (i < 3) {
+      const std::string nm = "decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv";
+      reg_conv3(nm, c, c, up_conv_[i]);
+      up_phases_[i] = walloc<op_t>(size_t(4) * c * 4 * c);
+      slots_[nm + ".weight"].dsts.push_back({Slot::CONV_UP_PHASES, up_phases_[i], 0, 0});
+    }
     prev = c;
   }
   no_g_ = walloc<float>(C0); no_b_ = walloc<float>(C0);
@@ -135,6 +140,7 @@ int VaeDecoder::load_tensor(const char* name, const float* src, const int64_t* d
       case Slot::ROWS: vae_cvt_weight_kernel<<<blocks, 256, 0, st>>>(stage_, reinterpret_cast<op_t*>(d.dst), O, I, 2, d.ld, d.off); break;
       case Slot::ROWS_T: vae_cvt_weight_kernel<<<blocks, 256, 0, st>>>(stage_, reinterpret_cast<op_t*>(d.dst), O, I, 3, d.ld, d.off); break;
       case Slot::CONVOUT_DGRAD: vae_cvt_convout_dgrad_kernel<<<blocks, 256, 0, st>>>(stage_, reinterpret_cast<float*>(d.dst), O, I); break;
+      case Slot::CONV_UP_PHASES: cvt_upconv_phases_kernel<<<blocks, 256, 0, st>>>(stage_, reinterpret_cast<op_t*>(d.dst), O, I); break;
     }
   }
   VCK(cudaGetLastError());
@@ -329,18 +335,10 @@ int VaeDecoder::run_forward(const float* z, float* img, int B, int h, int w) {
     }
     C = c.boc[3 - i];
     if (i < 3) {
-      op_t* up = A<op_t>(size_t(B) * 4 * H * W * C);
-      if (!dry_) {
-        const size_t total = size_t(B) * 4 * H * W * (C / 4);
-        upsample2x_bf16_kernel<<<int(std::min<size_t>((total + 255) / 256, 16384)), 256, 0, st_>>>(x, up, B, H, W, C);
-        ++launches_;
-      }
+      float* o; float2* cso;
+      if (upconv_fused(x, up_phases_[i], up_conv_[i].bias, B, H, W, C, &o, &cso)) return -1;
       H *= 2; W *= 2;
-      float* o = A<float>(size_t(B) * H * W * C);
-      GemmEpilogue e; memset(&e, 0, sizeof e);
-      e.bias = up_conv_[i].bias; e.out_f32 = o; e.ldo = C; e.colstats = colstats_for(B * H * W, C, H * W);
-      if (conv3(up, up_conv_[i].fwd, B, H, W, C, C, e)) return -1;
-      x = o; cs = e.colstats;
+      x = o; cs = cso;
     }
   }
   op_t* fin = A<op_t>(size_t(B) * H * W * C);

@@ -34,7 +34,7 @@ class VaeDecoder : public NetExec {
 
  private:
   struct Slot {
-    enum Kind { F32, CONV_FWD, CONV_DGRAD, ROWS, ROWS_T, CONVOUT_DGRAD };
+    enum Kind { F32, CONV_FWD, CONV_DGRAD, ROWS, ROWS_T, CONVOUT_DGRAD, CONV_UP_PHASES };
     struct Dst { Kind kind; void* dst; int ld; int off; };
     std::vector<int64_t> shape;
     std::vector<Dst> dsts;
@@ -77,6 +77,7 @@ class VaeDecoder : public NetExec {
   AttnW attn_;
   std::vector<ResW> up_res_[4];
   Conv3W up_conv_[3];
+  op_t* up_phases_[3] = {nullptr, nullptr, nullptr};     // fused upsample conv: [4][C][2][2][C]
   // run state
   uint8_t* arena_saved_ = nullptr; size_t fwd_top_ = 0;
   bool have_tape_ = false;
