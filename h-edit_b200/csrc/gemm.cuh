@@ -14,6 +14,8 @@
 //                "nearest 2x upsample -> 3x3 conv" evaluated on the COARSE input with pre-summed weights (2.25x fewer flops);
 //                the epilogue scatters row (s,y,x) to the fine pixel (2y+py, 2x+px) (GemmEpilogue::up_*)
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace hedit {
@@ -155,41 +157,54 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
         y0 = (m0 % hw) / p.conv_W;
         x0 = (m0 % hw) % p.conv_W;       // non-zero only for images wider than one 128-row tile (VAE decoder, W = 256 / 512)
       }
-      int tap = 0, cb = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (elect_one()) {
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          const int kw = (p.a_mode == A_CONV2X2) ? 2 : 3;
-          const int ky = tap / kw, kx = tap - ky * kw;
-          // box shift of this tap: 3x3 -> (kx-1, ky-1); one phase of the fused upsample conv -> (kx + ox, ky + oy)
-          const int sx = (p.a_mode == A_CONV2X2) ? kx + p.conv_ox : kx - 1, sy = (p.a_mode == A_CONV2X2) ? ky + p.conv_oy : ky - 1;
-          // stride 2: input x = 2X + kx - pad_left -> (parity, coarse offset) in the space-to-depth view
-          const int px = p.conv_pad01 ? (kx == 1 ? 1 : 0) : (kx == 1 ? 0 : 1), dx = p.conv_pad01 ? (kx == 2 ? 1 : 0) : (kx == 0 ? -1 : 0);
-          const int py = p.conv_pad01 ? (ky == 1 ? 1 : 0) : (ky == 1 ? 0 : 1), dy = p.conv_pad01 ? (ky == 2 ? 1 : 0) : (ky == 0 ? -1 : 0);
-          if (CLUSTER) {
-            // both CTAs' bytes are reported to the leader's barrier (the leader's MMA consumes both halves)
-            const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            if (p.a_mode == A_LINEAR) tma_load_2d_2sm(sa, &p.tmA, lfull, kb * 64, m0);
-            else if (p.a_mode == A_CONV3X3 || p.a_mode == A_CONV2X2) tma_load_4d_2sm(sa, &p.tmA, lfull, cb * 64, x0 + sx, y0 + sy, s0);
-            else tma_load_5d_2sm(sa, &p.tmA, lfull, px * p.conv_cin + cb * 64, x0 + dx, py, y0 + dy, s0);
-            tma_load_2d_2sm(sb, &p.tmB, lfull, kb * 64, n0 + int(rank) * (BN / 2));
-          } else {
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            if (p.a_mode == A_LINEAR) tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * 64, m0);
-            else if (p.a_mode == A_CONV3X3 || p.a_mode == A_CONV2X2) tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * 64, x0 + sx, y0 + sy, s0);
-            else tma_load_5d(sa, &p.tmA, &full_bar[stage], px * p.conv_cin + cb * 64, x0 + dx, py, y0 + dy, s0);
-            // the W map's box is BN/2 rows (shared with the pair variant): two loads
-            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
-            tma_load_2d(sb + (BN / 2) * 128, &p.tmB, &full_bar[stage], kb * 64, n0 + BN / 2);
+      // The producer's issue rate is on the critical path of the conv GEMMs, so the K loop is specialised per addressing mode at compile
+      // time (constant tap arithmetic, no mode tests inside the loop).
+      auto k_loop = [&](auto mode_c) {
+        constexpr int MODE = decltype(mode_c)::value;
+        constexpr int KW = (MODE == A_CONV2X2) ? 2 : 3;
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            const int ky = tap / KW, kx = tap - ky * KW;
+            int c1 = 0, c2 = 0, c3 = 0, c4 = 0;          // TMA coordinates of the A box beyond the channel coordinate
+            if (MODE == A_CONV3X3) { c1 = x0 + kx - 1; c2 = y0 + ky - 1; c3 = s0; }
+            else if (MODE == A_CONV2X2) { c1 = x0 + kx + p.conv_ox; c2 = y0 + ky + p.conv_oy; c3 = s0; }
+            else if (MODE == A_CONV3X3S2) {
+              // stride 2: input x = 2X + kx - pad_left -> (parity, coarse offset) in the space-to-depth view
+              const int px = p.conv_pad01 ? (kx == 1 ? 1 : 0) : (kx == 1 ? 0 : 1), dx = p.conv_pad01 ? (kx == 2 ? 1 : 0) : (kx == 0 ? -1 : 0);
+              const int py = p.conv_pad01 ? (ky == 1 ? 1 : 0) : (ky == 1 ? 0 : 1), dy = p.conv_pad01 ? (ky == 2 ? 1 : 0) : (ky == 0 ? -1 : 0);
+              c1 = x0 + dx; c2 = py; c3 = y0 + dy; c4 = px * p.conv_cin;
+            }
+            if (CLUSTER) {
+              // both CTAs' bytes are reported to the leader's barrier (the leader's MMA consumes both halves)
+              const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              if (MODE == A_LINEAR) tma_load_2d_2sm(sa, &p.tmA, lfull, kb * 64, m0);
+              else if (MODE == A_CONV3X3S2) tma_load_5d_2sm(sa, &p.tmA, lfull, c4 + cb * 64, c1, c2, c3, s0);
+              else tma_load_4d_2sm(sa, &p.tmA, lfull, cb * 64, c1, c2, c3);
+              tma_load_2d_2sm(sb, &p.tmB, lfull, kb * 64, n0 + int(rank) * (BN / 2));
+            } else {
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              if (MODE == A_LINEAR) tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * 64, m0);
+              else if (MODE == A_CONV3X3S2) tma_load_5d(sa, &p.tmA, &full_bar[stage], c4 + cb * 64, c1, c2, c3, s0);
+              else tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * 64, c1, c2, c3);
+              // the W map's box is BN/2 rows (shared with the pair variant): two loads
+              tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
+              tma_load_2d(sb + (BN / 2) * 128, &p.tmB, &full_bar[stage], kb * 64, n0 + BN / 2);
+            }
           }
+          __syncwarp();
+          if (MODE != A_LINEAR && ++cb == p.cin_blocks) { cb = 0; ++tap; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (p.a_mode != A_LINEAR && ++cb == p.cin_blocks) { cb = 0; ++tap; }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
+      };
+      if (p.a_mode == A_CONV3X3) k_loop(std::integral_constant<int, A_CONV3X3>{});
+      else if (p.a_mode == A_LINEAR) k_loop(std::integral_constant<int, A_LINEAR>{});
+      else if (p.a_mode == A_CONV2X2) k_loop(std::integral_constant<int, A_CONV2X2>{});
+      else k_loop(std::integral_constant<int, A_CONV3X3S2>{});
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues);
