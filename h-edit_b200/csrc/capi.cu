@@ -532,7 +532,8 @@ int hedit_op_linear(const void* A, const void* W, const float* bias, const float
   const int bn = pick_bn_op(M, N);
   g.M = M; g.N = N; g.num_kb = (K + 63) / 64; g.a_mode = A_LINEAR;
   uint64_t da[2] = {uint64_t(K), uint64_t(M)}, sa[1] = {uint64_t(K) * 2}; uint32_t ba[2] = {64, 128};
-  uint64_t db[2] = {uint64_t(K), uint64_t(N)}, sb[1] = {uint64_t(K) * 2}; uint32_t bb[2] = {64, uint32_t(bn / 2)};
+  uint64_t db[2] = {uint64_t(K), uint64_t(N)}, sb[1] = {uint64_t(K) * 2}; uint32_t bb[2] = {64, uint32_t(gemm_cluster() ? bn / 2 : bn)};
+  g.b_full_box = gemm_cluster() ? 0 : 1;
   if (!make_tmap_bf16(&g.tmA, A, 2, da, sa, ba) || !make_tmap_bf16(&g.tmB, W, 2, db, sb, bb)) return fail("tensor map encode failed");
   g.ep.bias = bias; g.ep.residual = residual; g.ep.ldr = N; g.ep.out_f32 = out_f32; g.ep.ldo = N;
   g.ep.out_bf16 = reinterpret_cast<op_t*>(out_bf16); g.ep.ldob = N; g.ep.rows_per_group = 1;
@@ -563,7 +564,8 @@ int hedit_op_conv3x3(const void* x, const void* w, const float* bias, float* out
     uint32_t b[5] = {64, uint32_t(Wd), 1, uint32_t(BH), uint32_t(BS)};
     ok = make_tmap_bf16(&g.tmA, x, 5, d, s, b);
   }
-  uint64_t db[2] = {uint64_t(9 * C), uint64_t(Cout)}, sb[1] = {uint64_t(9 * C) * 2}; uint32_t bb[2] = {64, uint32_t(bn / 2)};
+  uint64_t db[2] = {uint64_t(9 * C), uint64_t(Cout)}, sb[1] = {uint64_t(9 * C) * 2}; uint32_t bb[2] = {64, uint32_t(gemm_cluster() ? bn / 2 : bn)};
+  g.b_full_box = gemm_cluster() ? 0 : 1;
   if (!ok || !make_tmap_bf16(&g.tmB, w, 2, db, sb, bb)) return fail("tensor map encode failed");
   g.ep.bias = bias; g.ep.out_f32 = out; g.ep.ldo = Cout; g.ep.rows_per_group = 1;
   cudaError_t e = launch_gemm(g, bn, reinterpret_cast<cudaStream_t>(stream));

@@ -321,7 +321,8 @@ bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode, const
     }
   }
   if (!ok) { err = "tensor map (A) encode failed"; return false; }
-  uint64_t dimsB[2] = {uint64_t(Ktot), uint64_t(N)}; uint64_t strB[1] = {uint64_t(ldw > 0 ? ldw : Ktot) * 2}; uint32_t boxB[2] = {64, uint32_t(bn / 2)};
+  uint64_t dimsB[2] = {uint64_t(Ktot), uint64_t(N)}; uint64_t strB[1] = {uint64_t(ldw > 0 ? ldw : Ktot) * 2}; uint32_t boxB[2] = {64, uint32_t(gemm_cluster() ? bn / 2 : bn)};
+  g.b_full_box = gemm_cluster() ? 0 : 1;
   if (!make_tmap_bf16(&g.tmB, Wt, 2, dimsB, strB, boxB)) { err = "tensor map (B) encode failed"; return false; }
   return true;
 }
@@ -334,7 +335,7 @@ static int num_sms() {
 
 // tuning switch HEDIT_GEMM_CLUSTER=1 enables the cta_group::2 (CTA pair) variant
 // (default off: measured equal to the single-CTA kernel on B200 for every UNet shape -- the kernel is not bound by W traffic)
-static bool gemm_cluster() { static const bool v = getenv("HEDIT_GEMM_CLUSTER") && atoi(getenv("HEDIT_GEMM_CLUSTER")) != 0; return v; }
+bool gemm_cluster() { static const bool v = getenv("HEDIT_GEMM_CLUSTER") && atoi(getenv("HEDIT_GEMM_CLUSTER")) != 0; return v; }
 
 template <int BN, bool CL>
 static cudaError_t launch_gemm_t(const GemmParams& g, cudaStream_t st) {

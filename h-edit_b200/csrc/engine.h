@@ -21,6 +21,7 @@ struct ConvGeom { int S, H, W, C; int stride; int pad01; int ox, oy; };   // H,W
 bool make_gemm(GemmParams& g, int& bn, const op_t* A, int lda, int a_mode, const ConvGeom* cg, const op_t* Wt, int M, int N, int Ktot,
                const GemmEpilogue& ep, std::string& err, int ldw = 0);
 cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st);
+bool gemm_cluster();      // HEDIT_GEMM_CLUSTER=1: cta_group::2 pair variant (W boxes of BN/2 rows)
 
 struct UNetCfg {
   int in_ch = 4, out_ch = 4, sample = 64;

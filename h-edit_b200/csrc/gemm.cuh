@@ -42,6 +42,7 @@ struct GemmParams {
   int M, N, num_kb;
   int a_mode, conv_W, conv_H, conv_cin, cin_blocks;
   int conv_ox, conv_oy;     // A_CONV2X2 only: first tap offset per axis (-1 for output phase 0, 0 for phase 1)
+  int b_full_box;           // 1: tmB's box covers all BN rows (single-CTA launches: one W load per K block instead of two)
   int conv_pad01;           // A_CONV3X3S2 only: 0 = padding 1 on every side (SD downsampler); 1 = padding (0,1,0,1) (DDPM downsampler)
   GemmEpilogue ep;
 };
@@ -191,9 +192,12 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
               if (MODE == A_LINEAR) tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * 64, m0);
               else if (MODE == A_CONV3X3S2) tma_load_5d(sa, &p.tmA, &full_bar[stage], c4 + cb * 64, c1, c2, c3, s0);
               else tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * 64, c1, c2, c3);
-              // the W map's box is BN/2 rows (shared with the pair variant): two loads
-              tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
-              tma_load_2d(sb + (BN / 2) * 128, &p.tmB, &full_bar[stage], kb * 64, n0 + BN / 2);
+              if (p.b_full_box) {
+                tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
+              } else {       // the W map's box is BN/2 rows (shared with the pair variant): two loads
+                tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
+                tma_load_2d(sb + (BN / 2) * 128, &p.tmB, &full_bar[stage], kb * 64, n0 + BN / 2);
+              }
             }
           }
           __syncwarp();
