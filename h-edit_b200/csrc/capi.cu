@@ -170,8 +170,33 @@ int hedit_engine_profile_forward(hedit_engine* h, int S, int reps, char* out, in
   if (E.forward(x, eps, S, cc, 0) < 0) return fail(E.error());     // warm-up
   for (int r = 0; r < reps; ++r)
     if (E.forward_profiled(x, eps, S, cc, 0, acc) < 0) return fail(E.error());
+  // the whole forward, launched kernel by kernel vs replayed from a CUDA graph ("@" records; how much of it is launch gaps)
+  double ms_imm = 0, ms_graph = 0;
+  {
+    cudaStream_t st; cudaStreamCreate(&st);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms = 0;
+    E.forward(x, eps, S, cc, st);
+    cudaEventRecord(e0, st);
+    for (int r = 0; r < reps; ++r) E.forward(x, eps, S, cc, st);
+    cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1); ms_imm = ms / reps;
+    cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      E.forward(x, eps, S, cc, st);
+      if (cudaStreamEndCapture(st, &g) == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
+        cudaGraphLaunch(ge, st);
+        cudaEventRecord(e0, st);
+        for (int r = 0; r < reps; ++r) cudaGraphLaunch(ge, st);
+        cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1); ms_graph = ms / reps;
+      }
+    }
+    cudaGetLastError();
+    if (ge) cudaGraphExecDestroy(ge);
+    if (g) cudaGraphDestroy(g);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
+  }
   cudaFree(x); cudaFree(eps); cudaFree(ctx);
-  std::string js;
+  std::string js = "@immediate:" + std::to_string(ms_imm) + ":0;@graph:" + std::to_string(ms_graph) + ":0;";
   for (auto& kv : acc) js += kv.first + ":" + std::to_string(kv.second.first / reps) + ":" + std::to_string(kv.second.second / reps) + ";";
   if (int(js.size()) + 1 > out_len) return fail("profile buffer too small");
   memcpy(out, js.c_str(), js.size() + 1);

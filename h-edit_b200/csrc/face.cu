@@ -297,11 +297,16 @@ int FaceUNet::forward(const float* x, const float* t_host, float* eps, int S, cu
   if (S < 1) { err_ = "bad batch"; return -1; }
   const int tch = 4 * cfg_.ch;
   if (S > max_S_) {
+    drop_graphs();                       // they address the old time-embedding buffers
     ts_dev_ = walloc<float>(S); temb_a_ = walloc<float>(size_t(S) * tch); temb_b_ = walloc<float>(size_t(S) * tch);
     temb_rows_ = walloc<float>(size_t(S) * tproj_total_);
     if (!ts_dev_ || !temb_a_ || !temb_b_ || !temb_rows_) return -1;
     max_S_ = S;
   }
+  // the time steps are the only host input: copied outside the (replayable) launch sequence
+  FCK(cudaMemcpyAsync(ts_dev_, t_host, S * sizeof(float), cudaMemcpyHostToDevice, st));
+  const GraphKey key{reinterpret_cast<uintptr_t>(x), reinterpret_cast<uintptr_t>(eps), uintptr_t(S), 0};
+  if (replay(key, st)) return 0;
   // sizing pass, then the real one
   uint8_t* saved = arena_;
   dry_ = true; top_ = 0; peak_ = 0; arena_ = nullptr;
@@ -309,16 +314,17 @@ int FaceUNet::forward(const float* x, const float* t_host, float* eps, int S, cu
   dry_ = false; arena_ = saved;
   if (r) return -1;
   if (reserve(peak_ + (size_t(1) << 20), "face UNet")) return -1;
-  st_ = st; top_ = 0; launches_ = 0; flops_ = 0;
-  FCK(cudaMemcpyAsync(ts_dev_, t_host, S * sizeof(float), cudaMemcpyHostToDevice, st));
-  const int wpb = 8;
-  small_linear_kernel<<<(tch + wpb - 1) / wpb, wpb * 32, 0, st>>>(ts_dev_, 1, t_w1_, t_b1_, temb_a_, tch, S, tch, cfg_.ch, 3, 1);
-  small_linear_kernel<<<(tch + wpb - 1) / wpb, wpb * 32, 0, st>>>(temb_a_, tch, t_w2_, t_b2_, temb_b_, tch, S, tch, tch, 0, 0);
-  small_linear_kernel<<<(tproj_total_ + wpb - 1) / wpb, wpb * 32, 0, st>>>(temb_b_, tch, tproj_w_, tproj_b_, temb_rows_, tproj_total_, S, tproj_total_, tch, 1, 0);
-  launches_ += 3;
-  if (run(x, eps, S)) return -1;
-  FCK(cudaGetLastError());
-  return 0;
+  return run_or_capture(key, st, [&]() -> int {
+    top_ = 0; launches_ = 0; flops_ = 0;
+    const int wpb = 8;
+    small_linear_kernel<<<(tch + wpb - 1) / wpb, wpb * 32, 0, st_>>>(ts_dev_, 1, t_w1_, t_b1_, temb_a_, tch, S, tch, cfg_.ch, 3, 1);
+    small_linear_kernel<<<(tch + wpb - 1) / wpb, wpb * 32, 0, st_>>>(temb_a_, tch, t_w2_, t_b2_, temb_b_, tch, S, tch, tch, 0, 0);
+    small_linear_kernel<<<(tproj_total_ + wpb - 1) / wpb, wpb * 32, 0, st_>>>(temb_b_, tch, tproj_w_, tproj_b_, temb_rows_, tproj_total_, S, tproj_total_, tch, 1, 0);
+    launches_ += 3;
+    if (run(x, eps, S)) return -1;
+    FCK(cudaGetLastError());
+    return 0;
+  });
 }
 
 }  // namespace hedit

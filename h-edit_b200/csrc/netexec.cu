@@ -2,6 +2,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "elementwise.cuh"
@@ -21,8 +22,66 @@ namespace hedit {
     }                                                                                              \
   } while (0)
 
+NetExec::~NetExec() {
+  drop_graphs();
+  if (cap_stream_) cudaStreamDestroy(cap_stream_);
+  if (arena_) cudaFree(arena_);
+}
+
+void NetExec::drop_graphs() {
+  for (auto& g : graphs_) if (g.exec) cudaGraphExecDestroy(g.exec);
+  graphs_.clear();
+}
+
+static bool net_graphs_on() { static const bool v = !(getenv("HEDIT_NET_GRAPH") && atoi(getenv("HEDIT_NET_GRAPH")) == 0); return v; }
+
+bool NetExec::replay(const GraphKey& key, cudaStream_t st) {
+  for (auto& g : graphs_)
+    if (g.key == key && g.exec) {
+      if (cudaGraphLaunch(g.exec, st) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.bad = true; return false; }
+      launches_ = g.launches; flops_ = g.flops;
+      return true;
+    }
+  return false;
+}
+
+int NetExec::run_or_capture(const GraphKey& key, cudaStream_t st, const std::function<int()>& body) {
+  GraphEntry* ent = nullptr;
+  for (auto& g : graphs_) if (g.key == key) ent = &g;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (st) cudaStreamIsCapturing(st, &cs);                      // the caller is itself capturing: just add our launches to its graph
+  cudaGetLastError();
+  if (!net_graphs_on() || cs != cudaStreamCaptureStatusNone || (ent && ent->bad)) { st_ = st; return body(); }
+  if (!ent) {                                                  // first sighting: remember the key, launch directly
+    if (graphs_.size() >= 16) drop_graphs();
+    graphs_.push_back(GraphEntry{key, nullptr, 0, 0.0, false});
+    st_ = st;
+    return body();
+  }
+  if (!cap_stream_ && cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ent->bad = true; st_ = st; return body(); }
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); ent->bad = true; st_ = st; return body(); }
+  st_ = cap_stream_;
+  const int r = body();
+  st_ = st;
+  const cudaError_t ec = cudaStreamEndCapture(cap_stream_, &graph);
+  if (r) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return r; }
+  if (ec != cudaSuccess || !graph || cudaGraphInstantiate(&ent->exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    ent->exec = nullptr; ent->bad = true;
+    launches_ = 0; flops_ = 0;
+    return body();
+  }
+  cudaGraphDestroy(graph);
+  ent->launches = launches_; ent->flops = flops_;
+  NCK(cudaGraphLaunch(ent->exec, st));
+  return 0;
+}
+
 int NetExec::reserve(size_t need, const char* what) {
   if (need <= arena_bytes_) return 0;
+  drop_graphs();
   if (arena_) cudaFree(arena_);
   arena_ = nullptr; arena_bytes_ = 0;
   if (cudaMalloc(&arena_, need) != cudaSuccess) { err_ = std::string(what) + " arena cudaMalloc failed (" + std::to_string(need >> 20) + " MiB)"; return -1; }

@@ -4,7 +4,10 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <array>
+#include <functional>
 #include <string>
+#include <vector>
 
 #include "engine.h"
 
@@ -18,7 +21,7 @@ class NetExec {
   size_t arena_bytes() const { return arena_bytes_; }
 
  protected:
-  ~NetExec() { if (arena_) cudaFree(arena_); }
+  ~NetExec();
   template <typename T> T* A(size_t n) {
     const size_t bytes = (n * sizeof(T) + 1023) & ~size_t(1023);
     const size_t off = top_;
@@ -47,6 +50,15 @@ class NetExec {
   // x fp32 [S][H][W][C] -> *out fp32 [S][2H][2W][C] with column statistics in *cs_out
   int upconv_fused(const float* x, const op_t* w_phases, const float* bias, int S, int H, int W, int C, float** out, float2** cs_out);
 
+  // CUDA-graph replay of a whole pass.  `body` must be a fixed sequence of launches on st_ determined by `key` (buffer addresses,
+  // batch) and by device-resident data only.  A key's first call launches directly; its second call is captured (on a private
+  // stream: the caller's may be the legacy default stream) and instantiated; later calls are one cudaGraphLaunch on `st`.
+  // HEDIT_NET_GRAPH=0 always launches directly.  Graphs are dropped when the arena or any buffer they address is reallocated.
+  using GraphKey = std::array<uintptr_t, 4>;
+  bool replay(const GraphKey& key, cudaStream_t st);                 // true: a stored graph was launched
+  int run_or_capture(const GraphKey& key, cudaStream_t st, const std::function<int()>& body);
+  void drop_graphs();
+
   int groups_ = 32;
   uint8_t* arena_ = nullptr;
   size_t arena_bytes_ = 0, top_ = 0, peak_ = 0;
@@ -54,6 +66,11 @@ class NetExec {
   cudaStream_t st_ = 0;
   long launches_ = 0;
   double flops_ = 0;
+
+ private:
+  struct GraphEntry { GraphKey key; cudaGraphExec_t exec; long launches; double flops; bool bad; };
+  std::vector<GraphEntry> graphs_;
+  cudaStream_t cap_stream_ = nullptr;
 };
 
 }  // namespace hedit

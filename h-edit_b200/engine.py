@@ -98,11 +98,14 @@ class UNetEngine:
         """{op tag: (ms per forward, launches per forward)} measured with CUDA events around every kernel."""
         buf = C.create_string_buffer(8192)
         _lib.check(self.lib.hedit_engine_profile_forward(self.handle, S, reps, buf, 8192), "profile")
-        out = {}
+        out, self.last_profile_whole = {}, {}
         for rec in buf.value.decode().split(";"):
             if rec:
                 tag, ms, n = rec.split(":")
-                out[tag] = (float(ms), int(n))
+                if tag.startswith("@"):          # whole forward: launched kernel by kernel / replayed from a CUDA graph
+                    self.last_profile_whole[tag[1:]] = float(ms)
+                else:
+                    out[tag] = (float(ms), int(n))
         return out
 
     def new_blend_state(self, B: int) -> torch.Tensor:

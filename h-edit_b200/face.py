@@ -86,13 +86,15 @@ class FaceUNetEngine:
             _lib.check(self.lib.hedit_face_load_tensor(self.handle, name.encode(), t.data_ptr(), dims, len(shape)), f"load {name}")
         _lib.check(self.lib.hedit_face_finalize(self.handle), "finalize face UNet weights")
 
-    def forward(self, x: torch.Tensor, t) -> torch.Tensor:
-        """eps = model(x, t) (diffusion.py:301): x (S,3,R,R); t scalar or (S,)."""
+    def forward(self, x: torch.Tensor, t, out: torch.Tensor = None) -> torch.Tensor:
+        """eps = model(x, t) (diffusion.py:301): x (S,3,R,R); t scalar or (S,).  Calls that repeat the same (x, out) buffers and batch
+        are replayed from a CUDA graph from the third call on (netexec.h); results are bit-identical to the direct launches."""
         dev = torch.device("cuda", self.device)
         x = x.detach().to(dev, torch.float32).contiguous()
         S = x.shape[0]
         tt = np.ascontiguousarray(np.broadcast_to(np.asarray(torch.as_tensor(t).detach().cpu().numpy() if torch.is_tensor(t) else t, dtype=np.float32).reshape(-1), (S,)))
-        eps = torch.empty_like(x)
+        eps = torch.empty_like(x) if out is None else out
+        assert eps.is_contiguous() and eps.shape == x.shape and eps.dtype == torch.float32 and eps.device == x.device
         n = _lib.check(self.lib.hedit_face_unet_forward(self.handle, x.data_ptr(), tt.ctypes.data, S, eps.data_ptr(), self._stream()), "face unet forward")
         self.last_stats = {"kernel_launches": n, "sample_forwards": S, "flops": self.lib.hedit_face_last_flops(self.handle)}
         return eps

@@ -41,6 +41,28 @@ def test_face_unet_forward_matches_torch(cfg, S):
     assert r < TOL_UNET
 
 
+def test_face_unet_graph_replay_is_bit_identical():
+    """Same (x, out) buffers: 1st call launches directly, 2nd is captured, 3rd+ are CUDA-graph replays (netexec.h); a changed time step
+    and changed input VALUES must flow through the replay, and all three ways must agree bitwise with direct launches on new buffers."""
+    cfg = FaceUNetConfig.tiny()
+    eng = hedit_b200.FaceUNetEngine.from_model(FaceUNet(cfg).cuda())
+    g = torch.Generator(device="cpu").manual_seed(6)
+    xa = torch.randn(2, 3, cfg.image_size, cfg.image_size, generator=g).cuda()
+    xb = torch.randn(2, 3, cfg.image_size, cfg.image_size, generator=g).cuda()
+    x, out = xa.clone(), torch.empty_like(xa)
+    outs = [eng(x, 500.0, out=out).clone() for _ in range(4)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    x.copy_(xb)
+    replayed = eng(x, torch.tensor([37.0, 912.0]), out=out).clone()          # replay with new values and time steps
+    direct = eng(xb.clone(), torch.tensor([37.0, 912.0]))                    # new buffers -> direct launches
+    assert torch.equal(replayed, direct)
+    assert not torch.equal(replayed, outs[0])
+    big = eng(torch.cat([xa, xb, xa]), 500.0)                                # larger batch: arena regrows, graphs are dropped
+    assert torch.equal(big[:2], outs[0])
+    assert torch.equal(eng(x, torch.tensor([37.0, 912.0]), out=out), direct)
+
+
 def test_face_unet_full_geometry_runs():
     """CelebA-HQ geometry (ch 128, mult (1,1,2,2,4,4), 256x256, attention at 16x16), random-init: forward against torch."""
     _fp32()

@@ -121,6 +121,14 @@ def bench_face(iters):
         fl = eng.last_stats["flops"]
         ms = timeit(lambda: eng(x, 500.0), iters)
         print(f"face unet S={S}: {ms:.2f} ms  {fl / ms / 1e9:.0f} TFLOP/s  ({fl / S / 1e12:.3f} TFLOP/sample, {eng.last_stats['kernel_launches']} launches)")
+        try:                     # the same launches replayed from a CUDA graph: how much of the time is launch gaps
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                eng(x, 500.0)
+            msg = timeit(g.replay, iters)
+            print(f"   graph replay: {msg:.2f} ms  {fl / msg / 1e9:.0f} TFLOP/s")
+        except Exception as ex:
+            print("   graph capture failed:", ex)
 
 
 if __name__ == "__main__":
