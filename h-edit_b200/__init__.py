@@ -19,6 +19,8 @@ from .clip_gram import ClipGramEngine  # noqa: F401,E402
 from .text_encoder import TextEncoderEngine  # noqa: F401,E402
 from . import face  # noqa: F401,E402
 from .face import FaceUNetEngine  # noqa: F401,E402
+from . import compat  # noqa: F401,E402
+from .compat import CompatUNet, controller_kind, h_edit_p2p_implicit_compat, register_attention_control_compat  # noqa: F401,E402
 from .inversion import ddim_inversion, inversion_forward_process_ddpm, sample_xts_from_x0  # noqa: F401,E402
 
 __all__ = ["inversion_forward_process_ddpm", "ddim_inversion", "UNetEngine", "unet_config_of", "make_controller", "register_attention_control", "compile_edit_plan",

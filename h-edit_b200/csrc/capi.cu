@@ -203,8 +203,8 @@ int hedit_engine_profile_forward(hedit_engine* h, int S, int reps, char* out, in
   return 0;
 }
 
-int hedit_unet_forward_indexed(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int n_ctx, const int32_t* ctx_idx,
-                               int S, float* eps, void* stream) {
+static int unet_forward_impl(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int n_ctx, const int32_t* ctx_idx,
+                             int S, float* eps, void* stream, hedit_attn_probs_fn probs_cb, void* probs_user) {
   if (!h) return fail("null engine");
   cudaSetDevice(h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -230,11 +230,23 @@ int hedit_unet_forward_indexed(hedit_engine* h, const float* x, const float* tim
   cudaStreamSynchronize(st);     // host vectors go out of scope
   CallCtrl cc;
   cc.ctx_idx = h->d_ctx_idx; cc.time_idx = h->d_tidx; cc.unit_s0 = h->d_unit0; cc.unit_s1 = h->d_unit1; cc.unit_img = h->d_uimg; cc.n_units = S;
+  cc.probs_cb = probs_cb; cc.probs_user = probs_user;
   const long r = E.forward(x, eps, S, cc, st);
   if (r < 0) return fail(E.error());
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(e, "unet forward");
   return int(r);
+}
+
+int hedit_unet_forward_indexed(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int n_ctx, const int32_t* ctx_idx,
+                               int S, float* eps, void* stream) {
+  return unet_forward_impl(h, x, timesteps, ctx, n_ctx, ctx_idx, S, eps, stream, nullptr, nullptr);
+}
+
+int hedit_unet_forward_compat(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int S, float* eps,
+                              hedit_attn_probs_fn probs_hook, void* user, void* stream) {
+  if (!probs_hook) return fail("hedit_unet_forward_compat needs a probabilities hook");
+  return unet_forward_impl(h, x, timesteps, ctx, S, nullptr, S, eps, stream, probs_hook, user);
 }
 
 int hedit_unet_forward(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int S, float* eps, void* stream) {

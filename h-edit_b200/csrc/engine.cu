@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "compat_attn.cuh"
 #include "elementwise.cuh"
 #include "tmap.h"
 
@@ -183,6 +184,7 @@ Engine::Engine(const UNetCfg& cfg, int max_samples, int max_ctx) : cfg_(cfg), ma
     reg(B + ".ff.net.2.bias", WeightSlot::F32_COPY, w.b_ff2, 0, {C});
     tfs_.push_back(w);
     tf_tokens_.push_back(t.tokens);
+    tf_place_.push_back(t.name.rfind("down_blocks", 0) == 0 ? 0 : t.name.rfind("mid_block", 0) == 0 ? 1 : 2);
   }
   for (int i = 0; i < 3; ++i) {
     const int c = cfg.boc[i];
@@ -223,6 +225,7 @@ Engine::Engine(const UNetCfg& cfg, int max_samples, int max_ctx) : cfg_(cfg), ma
 Engine::~Engine() {
   for (void* p : owned_) cudaFree(p);
   if (arena_) cudaFree(arena_);
+  if (compat_probs_) cudaFree(compat_probs_);
 }
 
 int Engine::load_tensor(const char* name, const float* src, const int64_t* dims, int ndim, cudaStream_t st) {
@@ -659,6 +662,7 @@ struct PlanBuilder {
       if (!make_attn_maps(p, qkv, 3 * C, HW, S, qkv + C, qkv + 2 * C, 3 * C, HW, S, H, d, o.bkv, E.err_)) failed = true;
       p.H = H; p.d = d; p.Nq = HW; p.Nkv = HW; p.scale_log2 = float(1.4426950408889634 / std::sqrt(double(d)));
       p.out = att; p.ldo = C;
+      o.cq = qkv; o.ck = qkv + C; o.cv = qkv + 2 * C; o.c_ldq = 3 * C; o.c_ldkv = 3 * C;
       push(o);
     }
     F(qkv);
@@ -683,6 +687,7 @@ struct PlanBuilder {
       if (!make_attn_maps(p, qc, C, HW, S, w.kv_cache, w.kv_cache + C, 2 * C, E.cfg_.ctx_len, E.maxCtx_, H, d, 80, E.err_)) failed = true;
       p.H = H; p.d = d; p.Nq = HW; p.Nkv = E.cfg_.ctx_len; p.scale_log2 = float(1.4426950408889634 / std::sqrt(double(d)));
       p.out = att; p.ldo = C;
+      o.cq = qc; o.ck = w.kv_cache; o.cv = w.kv_cache + C; o.c_ldq = C; o.c_ldkv = 2 * C;
       push(o);
     }
     F(qc);
@@ -866,12 +871,14 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
       launch_layernorm(op.f_in, op.gamma, op.beta, op.h_out, op.rows, op.C1, op.eps, st);
       break;
     case OP_SELF_ATTN: {
+      if (cc.probs_cb) return compat_attention(op, false, S, cc, st);
       AttnParams a = op.attn;
       if (cc.self_mask & (1u << op.tf_index)) { a.q_idx = cc.self_q; a.k_idx = cc.self_k; a.v_idx = cc.self_v; }
       CK(launch_self_attn(a, op.dch, S, st));
       break;
     }
     case OP_CROSS_ATTN: {
+      if (cc.probs_cb) return compat_attention(op, true, S, cc, st);
       AttnParams a = op.attn;
       a.unit_s0 = cc.unit_s0; a.unit_s1 = cc.unit_s1; a.unit_img = cc.unit_img; a.ctx_idx = cc.ctx_idx;
       a.mapper = cc.mapper; a.c_base = cc.c_base; a.c_tar = cc.c_tar; a.replace_m = cc.replace_m; a.is_replace = cc.is_replace;
@@ -898,6 +905,40 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
       break;
   }
   return 1;
+}
+
+// One attention layer the reference's way (p2p/ptp_utils.py:88-107): scores -> softmax (fp32, materialised) -> user hook -> P.V
+long Engine::compat_attention(const Op& op, bool is_cross, int S, const CallCtrl& cc, cudaStream_t st) {
+  const AttnParams& a = op.attn;
+  const size_t need = size_t(S) * a.H * a.Nq * a.Nkv * sizeof(float);
+  if (need > compat_probs_bytes_) {
+    if (compat_probs_) { CK(cudaStreamSynchronize(st)); cudaFree(compat_probs_); compat_probs_ = nullptr; compat_probs_bytes_ = 0; }
+    if (cudaMalloc(&compat_probs_, need) != cudaSuccess) { cudaGetLastError(); err_ = "compat attention: cudaMalloc of the probabilities buffer failed (" + std::to_string(need >> 20) + " MiB)"; return -1; }
+    compat_probs_bytes_ = need;
+  }
+  if (a.d > 160) { err_ = "compat attention: head dim > 160"; return -1; }
+  CompatAttnParams p;
+  p.q = op.cq; p.ldq = op.c_ldq; p.q_sample = size_t(a.Nq) * op.c_ldq;
+  p.k = op.ck; p.v = op.cv; p.ldkv = op.c_ldkv; p.kv_sample = size_t(a.Nkv) * op.c_ldkv;
+  p.kv_idx = is_cross ? cc.ctx_idx : nullptr;
+  p.probs = compat_probs_; p.out = a.out; p.ldo = a.ldo;
+  p.H = a.H; p.d = a.d; p.Nq = a.Nq; p.Nkv = a.Nkv;
+  p.scale = float(1.0 / std::sqrt(double(a.d)));
+  const int BH = S * a.H;
+  compat_scores_kernel<<<dim3((a.Nkv + 63) / 64, (a.Nq + 63) / 64, BH), 256, 0, st>>>(p);
+  const size_t rows = size_t(BH) * a.Nq;
+  compat_softmax_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(compat_probs_, rows, a.Nkv);
+  CK(cudaGetLastError());
+  if (cc.probs_cb(cc.probs_user, op.tf_index, is_cross ? 1 : 0, tf_place_[op.tf_index], compat_probs_, BH, a.Nq, a.Nkv) != 0) {
+    err_ = "compat attention: the probabilities hook failed";
+    return -1;
+  }
+  const dim3 g((a.Nq + 31) / 32, BH);
+  if (a.d <= 40) compat_pv_kernel<40><<<g, 256, 0, st>>>(p);
+  else if (a.d <= 80) compat_pv_kernel<80><<<g, 256, 0, st>>>(p);
+  else compat_pv_kernel<160><<<g, 256, 0, st>>>(p);
+  CK(cudaGetLastError());
+  return 3;
 }
 
 long Engine::forward(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st) {

@@ -60,6 +60,7 @@ struct Op {
   // generic payloads (only the ones relevant to `kind` are used)
   GemmParams gemm; int gemm_bn = 0;
   AttnParams attn; int dch = 0, bkv = 0, tf_index = 0, blend_layer = -1;
+  const bf16 *cq = nullptr, *ck = nullptr, *cv = nullptr; int c_ldq = 0, c_ldkv = 0;   // raw operand pointers for the compat attention path
   const float* f_in = nullptr; const float* f_in2 = nullptr; float* f_out = nullptr;
   const bf16* h_in = nullptr; bf16* h_out = nullptr; bf16* h_out2 = nullptr;
   const float* gamma = nullptr; const float* beta = nullptr; const float* w = nullptr; const float* b = nullptr;
@@ -70,6 +71,10 @@ struct Op {
   size_t count = 0;
   const char* tag = "";
 };
+
+// Compatibility hook: called on the host between softmax and P.V of every attention layer with the materialised fp32 probabilities
+// [(S*heads)][n_query][n_key] (device memory, edited in place on the call's stream).  place: 0 down, 1 mid, 2 up.  Non-zero = abort.
+typedef int (*AttnProbsFn)(void* user, int tf_index, int is_cross, int place, float* probs, int batch_heads, int n_query, int n_key);
 
 // Per-call attention control (device arrays prepared by the edit loop).
 struct CallCtrl {
@@ -86,6 +91,8 @@ struct CallCtrl {
   const int* mapper = nullptr; const float* c_base = nullptr; const float* c_tar = nullptr;
   const float* replace_m = nullptr; const int* is_replace = nullptr;
   float* blend_acc = nullptr; const float* blend_alpha = nullptr;
+  // compat path (compat_attn.cuh): materialised probabilities + host callback instead of the fused attention kernels
+  AttnProbsFn probs_cb = nullptr; void* probs_user = nullptr;
 };
 
 struct Plan {
@@ -121,6 +128,7 @@ class Engine {
   int n_blend_layers() const { return n_blend_layers_; }
   int n_tf() const { return int(tfs_.size()); }
   int tf_tokens(int i) const { return tf_tokens_[i]; }
+  int tf_place(int i) const { return tf_place_[i]; }
   int latent_elems() const { return cfg_.in_ch * cfg_.sample * cfg_.sample; }
   double flops_per_sample() const { return flops_per_sample_; }
   void* scratch_alloc(size_t bytes);     // persistent device allocations owned by the engine
@@ -145,7 +153,9 @@ class Engine {
   int tproj_total_ = 0;
   std::vector<ResW> res_;       // in forward order
   std::vector<TfW> tfs_;        // in forward order (== controller layer order / 2)
-  std::vector<int> tf_tokens_;
+  std::vector<int> tf_tokens_, tf_place_;
+  float* compat_probs_ = nullptr; size_t compat_probs_bytes_ = 0;
+  long compat_attention(const Op& op, bool is_cross, int S, const CallCtrl& cc, cudaStream_t st);
   std::vector<bf16*> down_w_, up_w_, up_wp_;
   std::vector<float*> down_b_, up_b_;
   int n_blend_layers_ = 0;

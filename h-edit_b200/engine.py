@@ -145,6 +145,47 @@ class UNetEngine:
         self.last_stats = {"kernel_launches": launches, "sample_forwards": S}
         return eps
 
+    def n_transformer_blocks(self) -> int:
+        """Transformer blocks of the SD-1.x layout (attention on every level but the deepest, plus the mid block): 16 for SD-1.5;
+        the reference's controllers count 2 attention layers per block (ptp_utils.py:277-295)."""
+        levels, lpb = len(self.config["block_out_channels"]) - 1, self.config["layers_per_block"]
+        return levels * lpb + 1 + levels * (lpb + 1)
+
+    # ---- compat path: attention probabilities materialised and handed to a Python hook (include/hedit_b200.h: hedit_unet_forward_compat)
+    def forward_compat(self, x: torch.Tensor, timesteps, ctx: torch.Tensor, probs_hook) -> torch.Tensor:
+        """eps = unet(x, t, ctx) with `probs_hook(tf_index, is_cross, place, probs)` called for every attention layer in the reference's
+        processor order; probs is a (S*heads, n_query, n_key) fp32 CUDA tensor VIEW of the engine's buffer, edited in place
+        (p2p/ptp_utils.py:96-107).  place is 0/1/2 = down/mid/up."""
+        dev = torch.device("cuda", self.device)
+        x = x.to(dev, torch.float32).contiguous()
+        S = x.shape[0]
+        assert S <= self.max_samples and ctx.shape[0] == S and S <= self.max_contexts
+        ts = np.ascontiguousarray(np.broadcast_to(np.asarray(timesteps, dtype=np.float32).reshape(-1), (S,)))
+        ctx = ctx.to(dev, torch.float32).contiguous()
+        eps = torch.empty_like(x)
+        failure = []
+
+        class _View:                      # zero-copy torch view of the device buffer
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+        def _cb(_user, tf_index, is_cross, place, ptr, bh, nq, nk):
+            try:
+                with torch.cuda.device(dev):
+                    probs_hook(tf_index, bool(is_cross), place, torch.as_tensor(_View(ptr, (bh, nq, nk)), device=dev))
+                return 0
+            except BaseException as ex:   # noqa: BLE001 -- re-raised below, on the caller's side of the C boundary
+                failure.append(ex)
+                return 1
+
+        cb = _lib.ATTN_PROBS_FN(_cb)
+        rc = self.lib.hedit_unet_forward_compat(self.handle, x.data_ptr(), ts.ctypes.data, ctx.data_ptr(), S, eps.data_ptr(), cb, None, self._stream())
+        if failure:
+            raise failure[0]
+        launches = _lib.check(rc, "unet forward (compat)")
+        self.last_stats = {"kernel_launches": launches, "sample_forwards": S}
+        return eps
+
     # ---- the bridge-sampling loop
     def edit(self, xT: torch.Tensor, zs: torch.Tensor, ctx: torch.Tensor, timesteps: Sequence[int], coef: np.ndarray,
              cfg_scales: Sequence[float], plan: Optional[EditPlan], weight_reconstruction: float = 0.1, optimization_steps: int = 1,

@@ -84,8 +84,17 @@ def _single(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstr
     x = xT.reshape(1, *xT.shape[-3:])
     steps = after_skip_steps
     z = zs[:steps].reshape(1, steps, *xT.shape[-3:])
-    # hand a real P2P controller to the fused path; a bare AttentionStore (no-P2P modes) carries no edit tables
-    ctrl = [controller] if (controller is not None and hasattr(controller, "cross_replace_alpha")) else None
+    # hand a stock P2P controller to the fused path; a bare AttentionStore (no-P2P modes) carries no edit tables; any other object only
+    # promises the reference's call protocol and is served by the compat path (materialised probabilities, compat.py)
+    from .compat import controller_kind, h_edit_p2p_implicit_compat
+    kind = controller_kind(controller)
+    if kind == "custom":
+        if explicit_form or variant != 0 or masactrl is not None or pnp is not None:
+            raise NotImplementedError("custom controller objects are served on the implicit h-Edit + P2P sampler only (compat path)")
+        edited, recon = h_edit_p2p_implicit_compat(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstruction,
+                                                   optimization_steps, after_skip_steps, is_ddim_inversion)
+        return edited.to(dev), recon.to(dev)
+    ctrl = [controller] if kind == "stock" else None
     use_cuda = torch.device(dev).type == "cuda"
     x, z = (x.cuda(), z.cuda()) if use_cuda else (x.cpu(), z.cpu())
     edited, recon = h_edit_p2p_batch(model, x, z, [prompts[:2]], cfg_scales, ctrl, eta, weight_reconstruction, optimization_steps, steps,

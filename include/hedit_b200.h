@@ -146,6 +146,18 @@ int hedit_unet_forward(hedit_engine* e, const float* x, const float* timesteps, 
 int hedit_unet_forward_indexed(hedit_engine* e, const float* x, const float* timesteps, const float* ctx, int n_ctx, const int32_t* ctx_idx,
                                int S, float* eps, void* stream);
 
+/* Compatibility path for ARBITRARY controller objects: the same UNet call with every attention layer run the reference processor's
+ * way (text-guided/p2p/ptp_utils.py:88-107): scores -> fp32 softmax, MATERIALISED -> probs_hook -> probs . V.  The hook is invoked on the
+ * calling thread, in layer order (attn1 then attn2 of each transformer block, down -> mid -> up = the order in which the reference's
+ * processors fire), with the device buffer probs[(S*heads)][n_query][n_key] (head_to_batch_dim order: sample-major) which it may edit
+ * in place with work queued on `stream`; place: 0 "down", 1 "mid", 2 "up"; return non-zero to abort.  This is what a maintainer binds
+ * `P2PCrossAttnProcessor.__call__`'s `self.controller(attention_probs, is_cross, self.place_in_unet, save_attn)` line to when the
+ * controller is not one of the stock classes (which compile to the fused kernels instead).  Slow by construction (CUDA-core kernels,
+ * 2.1 GB of probabilities for 4 samples at 64x64). */
+typedef int (*hedit_attn_probs_fn)(void* user, int tf_index, int is_cross, int place, float* probs, int batch_heads, int n_query, int n_key);
+int hedit_unet_forward_compat(hedit_engine* e, const float* x, const float* timesteps, const float* ctx, int S, float* eps,
+                              hedit_attn_probs_fn probs_hook, void* user, void* stream);
+
 /* the whole bridge-sampling loop for a batch of images */
 int hedit_edit_p2p(hedit_engine* e, hedit_edit_args* args, void* stream);
 

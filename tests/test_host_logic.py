@@ -109,6 +109,32 @@ def test_compile_edit_plan_accepts_reference_controller_objects():
     assert a.self_window == b.self_window and a.start_blend == b.start_blend and a.blend_th == b.blend_th
 
 
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_controller_kind_routes_reference_classes():
+    """Stock reference controllers (Reweight -> Refine chain, Replace) compile to the fused path; a bare AttentionStore / EmptyControl
+    carries no edit; a user subclass that overrides the cross replacement must go through the compat path."""
+    ref = load_reference()
+    tok = ToyTokenizer()
+    prompts = PAIRS[0][0]
+    kw = dict(cross_replace_steps=0.4, self_replace_steps=0.35, num_steps=8, tokenizer=tok)
+    chain = ref.ptp_controller_utils.make_controller(prompts=prompts, is_replace_controller=False, device="cpu", blend_word=(("lizard",), ("lizard",)),
+                                                     equilizer_params={"words": ("lizard",), "values": (2.0,)}, **kw)
+    assert type(chain).__name__ == "AttentionReweight" and hedit_b200.controller_kind(chain) == "stock"
+    rep = ref.ptp_controller_utils.make_controller(prompts=prompts, is_replace_controller=True, device="cpu", blend_word=None, equilizer_params=None, **kw)
+    assert hedit_b200.controller_kind(rep) == "stock"
+    assert hedit_b200.controller_kind(ref.ptp_classes.AttentionStore()) == "none"
+    assert hedit_b200.controller_kind(ref.ptp_classes.EmptyControl()) == "none"
+    assert hedit_b200.controller_kind(None) == "none"
+
+    class HalfStrength(ref.ptp_classes.AttentionRefine):
+        def replace_cross_attention(self, attn_base, att_replace):
+            return 0.5 * super().replace_cross_attention(attn_base, att_replace) + 0.5 * att_replace
+
+    user = HalfStrength(prompts, 8, cross_replace_steps=0.4, self_replace_steps=0.35, tokenizer=tok, device="cpu")
+    assert hedit_b200.controller_kind(user) == "custom"
+    assert hedit_b200.controller_kind(lambda probs, is_cross, place, save_attn: probs) == "custom"
+
+
 def test_batched_plan_stacks_images():
     tok = ToyTokenizer()
     ctrls = [hedit_b200.make_controller(p, False, 0.4, 0.35, blend_word=((s,), (t,)) if i % 2 == 0 else None,
