@@ -143,6 +143,13 @@ int hedit_engine_tensor_info(hedit_engine* h, int index, char* name_buf, int nam
   return int(shape.size());
 }
 
+int hedit_engine_set_graph_replay(hedit_engine* h, int on) {
+  if (!h) return fail("null engine");
+  h->E->set_graph_replay(on != 0);
+  if (!on) h->E->drop_graphs();
+  return 0;
+}
+
 int hedit_engine_profile_forward(hedit_engine* h, int S, int reps, char* out, int out_len) {
   if (!h) return fail("null engine");
   cudaSetDevice(h->device);

@@ -56,15 +56,12 @@ struct CallDesc {
 };
 
 // per-edit device allocations, released when the edit returns
+// The loop's device buffers live in engine-owned slots, requested in a fixed order: edits of the same shape get the same addresses
+// (no cudaMalloc / cudaFree per edit; the engine's CUDA graphs of the UNet launches stay valid from one edit to the next).
 struct TempPool {
-  std::vector<void*> ptrs;
-  void* get(size_t bytes) {
-    void* p = nullptr;
-    if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return nullptr;
-    ptrs.push_back(p);
-    return p;
-  }
-  ~TempPool() { for (void* p : ptrs) cudaFree(p); }
+  Engine* E = nullptr;
+  size_t next = 0;
+  void* get(size_t bytes) { return E->loop_slot(next++, bytes); }
 };
 
 static int upload_ints(Engine& E, TempPool& tp, const std::vector<int>& v, int** out, cudaStream_t st) {
@@ -84,7 +81,8 @@ static int finish_call(Engine& E, TempPool& tp, CallDesc& c, cudaStream_t st) {
 struct LoopBuffers {
   float *lat = 0, *eps = 0, *corr = 0, *xin = 0, *zs = 0, *blend_acc = 0, *c_base = 0, *c_tar = 0, *replace_m = 0, *blend_alpha = 0;
   float2* partial = 0;
-  int *mapper = 0, *is_replace = 0, *has_blend = 0, *tidx = 0;
+  int *mapper = 0, *is_replace = 0, *has_blend = 0, *tidx = 0, *tidx_cur = 0;
+  float *c_base_cur = 0, *c_tar_cur = 0;
   int *iuA = 0, *icA = 0, *iuA0 = 0, *icA0 = 0, *iu = 0, *ics = 0, *ict = 0;
 };
 
@@ -112,7 +110,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     E.err_ = "xt_is_pair (single-step use) needs schedule 0: the exact-reuse schedule carries UNet outputs across timesteps";
     return -1;
   }
-  TempPool tp;
+  TempPool tp; tp.E = &E;
 
   // ---- call descriptors.  latent pool slots: xt[b][row] = 2b+row ; xprev[b][row] = 2B+2b+row ; xopt[b] = 4B+b
   // contexts: 0 = "", 1+2b = src_b, 2+2b = tar_b
@@ -273,7 +271,10 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   const int nparts = 16;
   L.partial = reinterpret_cast<float2*>(tp.get(size_t(B) * nparts * sizeof(float2)));
   L.tidx = reinterpret_cast<int*>(tp.get(size_t(T + 1) * maxS * sizeof(int)));
-  if (!L.lat || !L.eps || !L.corr || !L.xin || !L.zs || !L.partial || !L.tidx) return -1;
+  // fixed-address copies of the CURRENT launch's time-index row and P2P coefficient rows (what the replayed graphs read)
+  L.tidx_cur = reinterpret_cast<int*>(tp.get(size_t(maxS) * sizeof(int)));
+  L.c_base_cur = fa(size_t(B) * 80); L.c_tar_cur = fa(size_t(B) * 80);
+  if (!L.lat || !L.eps || !L.corr || !L.xin || !L.zs || !L.partial || !L.tidx || !L.tidx_cur || !L.c_base_cur || !L.c_tar_cur) return -1;
   if (upload_ints(E, tp, iuA, &L.iuA, st) || upload_ints(E, tp, icA, &L.icA, st) || upload_ints(E, tp, iuA0, &L.iuA0, st) ||
       upload_ints(E, tp, icA0, &L.icA0, st) || upload_ints(E, tp, iu, &L.iu, st) || upload_ints(E, tp, ics, &L.ics, st) || upload_ints(E, tp, ict, &L.ict, st))
     return -1;
@@ -333,12 +334,15 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     gather_latents_kernel<<<g, 256, 0, st>>>(L.lat, cd.d_lat, L.xin, n / 4);
     ++launches;
     CallCtrl cc;
-    cc.ctx_idx = cd.d_ctx; cc.time_idx = L.tidx + size_t(tindex) * maxS;
+    CKE(cudaMemcpyAsync(L.tidx_cur, L.tidx + size_t(tindex) * maxS, size_t(cd.S) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    cc.ctx_idx = cd.d_ctx; cc.time_idx = L.tidx_cur;
     cc.unit_s0 = cd.d_us0; cc.unit_s1 = cd.d_us1; cc.unit_img = cd.d_uimg; cc.n_units = cd.n_units;
     if (cd.p2p && p2p) {
       if (a.self_lo <= a.ctrl_step0 + ctrl_step && a.ctrl_step0 + ctrl_step < a.self_hi) { cc.self_mask = mask_small; cc.self_q = cd.d_sq; cc.self_k = cd.d_sq; cc.self_v = nullptr; }
       cc.mapper = L.mapper; cc.is_replace = L.is_replace; cc.replace_m = L.replace_m;
-      cc.c_base = L.c_base + size_t(ctrl_step) * B * 80; cc.c_tar = L.c_tar + size_t(ctrl_step) * B * 80;
+      CKE(cudaMemcpyAsync(L.c_base_cur, L.c_base + size_t(ctrl_step) * B * 80, size_t(B) * 80 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      CKE(cudaMemcpyAsync(L.c_tar_cur, L.c_tar + size_t(ctrl_step) * B * 80, size_t(B) * 80 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      cc.c_base = L.c_base_cur; cc.c_tar = L.c_tar_cur;
       if (blend && save) { cc.blend_acc = L.blend_acc; cc.blend_alpha = L.blend_alpha; }
     } else if (cd.p2p && pnp) {
       if (a.pnp_qk_on[ctrl_step]) { cc.self_mask = a.pnp_self_mask; cc.self_q = cd.d_sq; cc.self_k = cd.d_sq; cc.self_v = nullptr; }
@@ -348,7 +352,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
       for (int l = std::max(0, a.masa_start_layer); l < E.n_tf(); ++l) m |= 1u << l;
       cc.self_mask = m; cc.self_q = nullptr; cc.self_k = cd.d_sk; cc.self_v = cd.d_sk;
     }
-    const long r = E.forward(L.xin, L.eps + size_t(cd.pool_off) * n, cd.S, cc, st);
+    const long r = E.forward_replayed(L.xin, L.eps + size_t(cd.pool_off) * n, cd.S, cc, st);
     if (r < 0) return -1;
     launches += r;
     fwd += cd.S;

@@ -132,6 +132,15 @@ class Engine {
   int latent_elems() const { return cfg_.in_ch * cfg_.sample * cfg_.sample; }
   double flops_per_sample() const { return flops_per_sample_; }
   void* scratch_alloc(size_t bytes);     // persistent device allocations owned by the engine
+  // Slot `i` of the sampling loop's buffer pool: same request sequence => same addresses across edits (no per-edit cudaMalloc /
+  // cudaFree, and the CUDA graphs below stay valid); a slot is re-allocated only when a larger size is asked for.
+  void* loop_slot(size_t index, size_t bytes);
+  // forward() replayed from a CUDA graph: a launch is identified by (x, eps, S, every field of cc); its first occurrence launches
+  // directly, its second is captured on a private stream and instantiated, later ones are a single cudaGraphLaunch.  Per-step tables must
+  // therefore sit at FIXED addresses (the loop stages the step's rows).  Calls with a probabilities hook are never captured.
+  long forward_replayed(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st);
+  void set_graph_replay(bool on) { graph_replay_ = on; }
+  void drop_graphs();
 
   std::string err_;
 
@@ -170,6 +179,11 @@ class Engine {
   bf16* ctx_bf16_ = 0;          // [max_ctx*77][ctx_dim]
   float* stage_ = 0; size_t stage_elems_ = 0;   // fp32 staging for weight upload
   std::map<int, std::unique_ptr<Plan>> plans_;
+  std::vector<std::pair<void*, size_t>> loop_pool_;
+  struct FwdGraph { std::vector<uint8_t> key; cudaGraphExec_t exec; long launches; bool bad; };
+  std::vector<FwdGraph> fwd_graphs_;
+  cudaStream_t cap_stream_ = nullptr;
+  bool graph_replay_ = true;
 };
 
 }  // namespace hedit

@@ -145,6 +145,10 @@ class UNetEngine:
         self.last_stats = {"kernel_launches": launches, "sample_forwards": S}
         return eps
 
+    def set_graph_replay(self, on: bool) -> None:
+        """CUDA-graph replay of the loop's UNet launches (default on); off = every kernel launched directly.  Bit-identical results."""
+        _lib.check(self.lib.hedit_engine_set_graph_replay(self.handle, int(bool(on))), "set_graph_replay")
+
     def n_transformer_blocks(self) -> int:
         """Transformer blocks of the SD-1.x layout (attention on every level but the deepest, plus the mid block): 16 for SD-1.5;
         the reference's controllers count 2 attention layers per block (ptp_utils.py:277-295)."""

@@ -134,6 +134,9 @@ const char* hedit_operand_dtype(void);
 /* enumerate the state-dict tensors the engine expects (diffusers parameter names): returns ndim, fills dims4 */
 int hedit_engine_tensor_count(hedit_engine* e);
 int hedit_engine_tensor_info(hedit_engine* e, int index, char* name_buf, int name_len, int64_t* dims4);
+/* The sampling loop replays each distinct UNet launch (same buffers, batch and control tables) from a CUDA graph from its third
+ * occurrence on (on by default; HEDIT_LOOP_GRAPH=0 or on=0 launches every kernel directly).  Results are bit-identical either way. */
+int hedit_engine_set_graph_replay(hedit_engine* e, int on);
 /* diagnostics: one UNet forward of S samples with CUDA events around every kernel; writes "tag:ms:launches;" records */
 int hedit_engine_profile_forward(hedit_engine* e, int S, int reps, char* out, int out_len);
 

@@ -97,6 +97,33 @@ def test_edit_loop_tiny_refine_blend():
     assert r_ed < TOL_LOOP                           # edit row passes through thresholded LocalBlend masks and hard P2P windows
 
 
+def test_graph_replay_is_bit_identical_to_direct_launches():
+    """The loop replays repeated UNet launches from CUDA graphs (engine.h forward_replayed); the same edit with replay off, on (first
+    edit: direct -> capture -> replay) and on again (second edit: replay from step 0, buffers at the same addresses) must agree bitwise."""
+    _fp32()
+    g = load_golden("tiny_refine_blend")
+    meta = g["meta"]
+    model = OraclePipeline(cfg_from_meta(meta), seed=0)
+    model.scheduler.set_timesteps(meta["T"])
+    eng = UNetEngine.from_unet(model.unet, max_samples=5, max_contexts=4)
+    bw = meta["blend_words"]
+    mk = lambda: hedit_b200.compile_edit_plan([hedit_b200.make_controller(
+        meta["prompts"], False, meta["xa"], meta["sa"], blend_word=((bw[0],), (bw[1],)),
+        equilizer_params={"words": (bw[1],), "values": (2.0,)}, num_steps=meta["T"], tokenizer=model.tokenizer)], meta["T"])
+    ts, coef = hedit_b200.step_tables(model.scheduler, meta["T"], meta["eta"], False)
+    ctx = torch.cat([g["ctx_uncond"], g["ctx_src"], g["ctx_tar"]]).cuda()
+    xT = g["xT"].reshape(1, *g["xT"].shape[-3:]).cuda()
+    zs = g["zs"].reshape(1, *g["zs"].shape).cuda()
+    run = lambda: eng.edit(xT, zs, ctx, ts, coef, meta["cfg_scales"], mk(), meta["weight_reconstruction"], 2, False, 1, trace=True)
+    eng.set_graph_replay(False)
+    ref = [t.clone() for t in run()]
+    eng.set_graph_replay(True)
+    for _ in range(3):
+        out = run()
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b)
+
+
 def test_edit_loop_tiny_reference_schedule():
     r_ed, r_rc, r_w0, st = _run_golden("tiny_refine_blend", schedule=0)
     assert st["sample_forwards"] == 10 * 9
