@@ -135,6 +135,7 @@ SYMBOLS = {
     "hedit_face_last_flops": (C.c_double, [_P]),
     "hedit_face_edit": (_I, [_P, C.POINTER(FaceArgsC), _P]),
     "hedit_op_linear": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "hedit_op_linear_geglu": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "hedit_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "hedit_op_self_attention": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "hedit_op_cross_attention_p2p": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),

@@ -581,8 +581,34 @@ int hedit_op_linear(const void* A, const void* W, const float* bias, const float
   if (!make_tmap_bf16(&g.tmA, A, 2, da, sa, ba) || !make_tmap_bf16(&g.tmB, W, 2, db, sb, bb)) return fail("tensor map encode failed");
   g.ep.bias = bias; g.ep.residual = residual; g.ep.ldr = N; g.ep.out_f32 = out_f32; g.ep.ldo = N;
   g.ep.out_bf16 = reinterpret_cast<op_t*>(out_bf16); g.ep.ldob = N; g.ep.rows_per_group = 1;
+  g.ep.diag_skip = getenv("HEDIT_GEMM_DIAG_SKIP") ? atoi(getenv("HEDIT_GEMM_DIAG_SKIP")) : 0;
   cudaError_t e = launch_gemm(g, bn, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "linear launch");
+  return 0;
+}
+
+int hedit_op_linear_geglu(const void* A, const void* W, const float* bias, void* out_h16, int M, int N2, int K, void* stream) {
+  if (N2 % 32) return fail("GEGLU width must be a multiple of 32");
+  if (!bias) {               // the kernel's GEGLU write-back always adds a bias: hand it zeros
+    static float* zeros = nullptr; static int zeros_n = 0;
+    if (zeros_n < N2) {
+      if (zeros) cudaFree(zeros);
+      if (cudaMalloc(&zeros, size_t(N2) * sizeof(float)) != cudaSuccess) { zeros = nullptr; zeros_n = 0; return fail("cudaMalloc"); }
+      cudaMemset(zeros, 0, size_t(N2) * sizeof(float)); zeros_n = N2;
+    }
+    bias = zeros;
+  }
+  GemmParams g; memset(&g, 0, sizeof g);
+  const int bn = pick_bn_op(M, N2);
+  g.M = M; g.N = N2; g.num_kb = (K + 63) / 64; g.a_mode = A_LINEAR;
+  uint64_t da[2] = {uint64_t(K), uint64_t(M)}, sa[1] = {uint64_t(K) * 2}; uint32_t ba[2] = {64, 128};
+  uint64_t db[2] = {uint64_t(K), uint64_t(N2)}, sb[1] = {uint64_t(K) * 2}; uint32_t bb[2] = {64, uint32_t(gemm_cluster() ? bn / 2 : bn)};
+  g.b_full_box = gemm_cluster() ? 0 : 1;
+  if (!make_tmap_bf16(&g.tmA, A, 2, da, sa, ba) || !make_tmap_bf16(&g.tmB, W, 2, db, sb, bb)) return fail("tensor map encode failed");
+  g.ep.bias = bias; g.ep.out_bf16 = reinterpret_cast<op_t*>(out_h16); g.ep.ldob = N2 / 2; g.ep.geglu = 1; g.ep.rows_per_group = 1;
+  g.ep.diag_skip = getenv("HEDIT_GEMM_DIAG_SKIP") ? atoi(getenv("HEDIT_GEMM_DIAG_SKIP")) : 0;
+  cudaError_t e = launch_gemm(g, bn, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "GEGLU linear launch");
   return 0;
 }
 

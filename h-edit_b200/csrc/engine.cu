@@ -359,10 +359,10 @@ static int num_sms() {
 // (default off: measured equal to the single-CTA kernel on B200 for every UNet shape -- the kernel is not bound by W traffic)
 bool gemm_cluster() { static const bool v = getenv("HEDIT_GEMM_CLUSTER") && atoi(getenv("HEDIT_GEMM_CLUSTER")) != 0; return v; }
 
-template <int BN, bool CL>
+template <int BN, bool CL, bool GG = false>
 static cudaError_t launch_gemm_t(const GemmParams& g, cudaStream_t st) {
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, CL>::SMEM_BYTES); attr_set = true; }
+  if (!attr_set) { cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CL, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, CL>::SMEM_BYTES); attr_set = true; }
   const int m_tiles = (g.M + 127) / 128, n_tiles = (g.N + BN - 1) / BN;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = GemmCfg<BN, CL>::SMEM_BYTES; cfg.stream = st;
@@ -375,11 +375,15 @@ static cudaError_t launch_gemm_t(const GemmParams& g, cudaStream_t st) {
   } else {
     cfg.gridDim = dim3(std::min(m_tiles * n_tiles, num_sms()));
   }
-  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CL>, g);
+  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CL, GG>, g);
 }
 
 cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st) {
   const bool cl = gemm_cluster() && g.M > 128;
+  if (g.ep.geglu) {          // GEGLU write-back: its own instantiations
+    if (bn == 256) return cl ? launch_gemm_t<256, true, true>(g, st) : launch_gemm_t<256, false, true>(g, st);
+    return cl ? launch_gemm_t<160, true, true>(g, st) : launch_gemm_t<160, false, true>(g, st);
+  }
   if (bn == 256) return cl ? launch_gemm_t<256, true>(g, st) : launch_gemm_t<256, false>(g, st);
   return cl ? launch_gemm_t<160, true>(g, st) : launch_gemm_t<160, false>(g, st);
 }
@@ -1038,7 +1042,11 @@ long Engine::forward_profiled(const float* x, float* eps, int S, const CallCtrl&
   for (size_t i = 0; i < plan->ops.size(); ++i) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-    auto& a = acc[plan->ops[i].tag];
+    std::string tag = plan->ops[i].tag;
+    static const bool shapes = getenv("HEDIT_PROFILE_SHAPES") && atoi(getenv("HEDIT_PROFILE_SHAPES")) != 0;
+    if (shapes && plan->ops[i].kind == OP_GEMM)      // per-shape records (diagnostics)
+      tag += "[" + std::to_string(plan->ops[i].gemm.M) + "x" + std::to_string(plan->ops[i].gemm.N) + "x" + std::to_string(plan->ops[i].gemm.num_kb * 64) + "]";
+    auto& a = acc[tag];
     a.first += ms; a.second += 1;
   }
   for (auto& e : ev) cudaEventDestroy(e);

@@ -29,6 +29,7 @@ struct GemmEpilogue {
   float* out_f32;           // [M][ldo] or null
   op_t* out_bf16;  // [M][ldob] or null
   int rows_per_group, ldrv, ldr, ldo, ldob;
+  int diag_skip;            // diagnostics only (op_bench): the write-back is skipped, accumulators are just released
   int geglu;                // 1: every 32-col chunk = 16 value | 16 gate -> bf16 out has N/2 columns
   int nchw_hw;              // >0: write out_f32 as [row / hw][N][row % hw] (NCHW latent layout; small-N generic path only)
   int up_W, up_H, up_py, up_px;   // up_W > 0: GEMM row (s,y,x) of a coarse up_H x up_W grid is written to fine row (s, 2y+up_py, 2x+up_px)
@@ -103,7 +104,10 @@ struct GemmCfg {
 // single-CTA kernel (SS-mode operand reads + TMA writes ~ 2 x 115 B/clk/SM at 128x160 tiles vs 128 B/clk/SM available).
 // Protocol: both CTAs' TMA loads complete on the LEADER's full barrier; the leader's MMA commits multicast to both CTAs'
 // empty / accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
-template <int BN, bool CLUSTER>
+// GEGLU = the fused GEGLU write-back as its own instantiation: the generic write-back's double-buffered bias / residual registers (64+)
+// are not allocated, which lets the compiler keep all 8 packed GELU evaluations of a chunk in flight (the K = 320 feed-forward
+// projection is bound by the latency of that epilogue, not by the tensor pipe).
+template <int BN, bool CLUSTER, bool GEGLU = false>
 __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN, CLUSTER>;
   constexpr int STAGES = Cfg::STAGES;
@@ -269,12 +273,11 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
     const GemmEpilogue& e = p.ep;
     float4* stg = reinterpret_cast<float4*>(smem + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * 256;   // [32 rows][8 quads]
     const int rq = lane & 7, rr = lane >> 3;           // read-back role (non-GEGLU): quad, row-in-group-of-4
-    const int gq = lane & 3, gr = lane >> 2;           // read-back role (GEGLU, 16 outputs): quad, row-in-group-of-8
     // feature combination of this launch -> specialised write-back loop (0 = generic path)
     const bool has_b = e.bias != nullptr, has_rv = e.rowvec != nullptr, has_res = e.residual != nullptr;
     const bool has32 = e.out_f32 != nullptr, has16 = e.out_bf16 != nullptr;
     int mode = 0;
-    if (!e.geglu) {
+    if (!GEGLU) {
       if (has_b && !has_rv && !has_res && has32 && !has16) mode = 1;
       else if (has_b && !has_rv && has_res && has32 && !has16) mode = 2;
       else if (has_b && has_rv && !has_res && has32 && !has16 && (e.rows_per_group & 31) == 0) mode = 3;
@@ -312,18 +315,75 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
         }
       };
       prefetch(n0 + half * 32, bb, rvv, rs);
-      // GEGLU: the bias of all columns this warp will touch in this tile (up to 4 chunks x 32), one float4 per lane, fetched while the
-      // accumulator is still being computed; the chunks below read it with shuffles instead of 8 exposed global loads per chunk
-      float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e.geglu && e.bias) {
-        const int gc = n0 + half * 32 + 64 * (lane >> 3) + 4 * (lane & 7);
-        if (gc + 4 <= p.N && half * 32 + 64 * (lane >> 3) < BN) gb = *reinterpret_cast<const float4*>(e.bias + gc);
-      }
+      // GEGLU: bias of this warp's first chunk, requested before the accumulator is ready (warp-uniform addresses: one broadcast line)
+      float4 gbias[8];
+      auto geglu_bias = [&](int col, float4 (&b_)[8]) {        // col: start of a chunk inside N (N % 32 == 0; GEGLU launches always carry a bias)
+        const float4* bp = reinterpret_cast<const float4*>(e.bias + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b_[j] = __ldg(bp + j);
+      };
+      if (GEGLU) geglu_bias(min(n0 + half * 32, p.N - 32), gbias);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       // 16-bit outputs without bias / residual (q|k|v, q, text k|v projections): 64 columns per iteration, converted to 16 bits BEFORE the
       // staging transpose (so the 4 KB tile holds 32 rows x 64 columns) and written back as full 128-byte lines -- half the latency-bound
       // iterations and half the store instructions of the 32-column path.
+      if (e.diag_skip) {
+      } else if (GEGLU) {
+        // chunk = 16 value columns followed by their 16 gate columns -> 16 outputs (bias applied before the gate), packed to 16 bits
+        // BEFORE the staging transpose ([32 rows][32 B], 16-byte slots XOR-swizzled) and written back as 16 rows x 32 B per instruction
+        uint4* stg16 = reinterpret_cast<uint4*>(stg);
+        const int hs = lane & 1, hr = lane >> 1;
+        // one chunk: bias + gate + pack + transposed write-back.  The TMEM read of the NEXT chunk is issued before this runs (two
+        // register buffers), so the 64 B/clk TMEM port works while the GELU math and the stores of the current chunk execute.
+        auto chunk = [&](int c0, const uint32_t (&raw)[32]) {
+          const int col = n0 + c0;
+          float4 gnext[8];
+          geglu_bias(min(col + 64, p.N - 32), gnext);                // next chunk's bias in flight during this chunk's math (clamped: a reload at the end)
+          uint32_t pk[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bv = gbias[q], bg = gbias[4 + q];
+            const float2 g0 = gelu_fast_f2(__fadd2_rn(make_float2(__uint_as_float(raw[16 + 4 * q]), __uint_as_float(raw[17 + 4 * q])), make_float2(bg.x, bg.y)));
+            const float2 g1 = gelu_fast_f2(__fadd2_rn(make_float2(__uint_as_float(raw[18 + 4 * q]), __uint_as_float(raw[19 + 4 * q])), make_float2(bg.z, bg.w)));
+            const float2 o0 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1])), make_float2(bv.x, bv.y)), g0);
+            const float2 o1 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3])), make_float2(bv.z, bv.w)), g1);
+            pk[2 * q] = pack_op2(o0.x, o0.y); pk[2 * q + 1] = pack_op2(o1.x, o1.y);
+          }
+          const int sw = (lane >> 2) & 1;
+          stg16[lane * 2 + (0 ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          stg16[lane * 2 + (1 ^ sw)] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          __syncwarp();
+          op_t* go = e.out_bf16 + size_t(rbase + hr) * e.ldob + (col >> 1) + 8 * hs;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int r = 16 * i + hr;
+            const uint4 a = stg16[r * 2 + (hs ^ ((r >> 2) & 1))];
+            if (rows_full || rbase + r < p.M) *reinterpret_cast<uint4*>(go + size_t(16 * i) * e.ldob) = a;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gbias[j] = gnext[j];
+        };
+        uint32_t rawA[32], rawB[32];
+        const int c_first = half * 32;
+        if (n0 + c_first < p.N) {
+          tmem_ld32(t_row + c_first, rawA);
+#pragma unroll 1
+          for (int c0 = c_first; c0 < BN; c0 += 128) {             // (all conditions warp-uniform)
+            const bool more1 = (c0 + 64 < BN) && (n0 + c0 + 64 < p.N);
+            tmem_ld_wait();
+            if (more1) tmem_ld32(t_row + c0 + 64, rawB);
+            chunk(c0, rawA);
+            if (!more1) break;
+            const bool more2 = (c0 + 128 < BN) && (n0 + c0 + 128 < p.N);
+            tmem_ld_wait();
+            if (more2) tmem_ld32(t_row + c0 + 128, rawA);
+            chunk(c0 + 64, rawB);
+            if (!more2) break;
+          }
+        }
+      } else {
       const bool wide16 = (BN == 256) && mode == 4 && rows_full && ((p.N - n0) >= BN || ((p.N - n0) & 63) == 0);
       if (wide16) {
         op_t* stg16 = reinterpret_cast<op_t*>(stg);
@@ -358,36 +418,6 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
         uint32_t raw[32];
         tmem_ld32(t_row + c0, raw);
         tmem_ld_wait();
-        if (e.geglu) {
-          // chunk = 16 value columns followed by their 16 gate columns -> 16 outputs (bias applied before the gate)
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (e.bias) {
-            const int src0 = ((c0 - half * 32) >> 6) << 3;        // lanes holding this chunk's 8 float4
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[4 * j] += __shfl_sync(0xffffffffu, gb.x, src0 + j); v[4 * j + 1] += __shfl_sync(0xffffffffu, gb.y, src0 + j);
-              v[4 * j + 2] += __shfl_sync(0xffffffffu, gb.z, src0 + j); v[4 * j + 3] += __shfl_sync(0xffffffffu, gb.w, src0 + j);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 g0 = gelu_fast_f2(make_float2(v[16 + 4 * q], v[17 + 4 * q])), g1 = gelu_fast_f2(make_float2(v[18 + 4 * q], v[19 + 4 * q]));
-            const float2 o0 = __fmul2_rn(make_float2(v[4 * q], v[4 * q + 1]), g0), o1 = __fmul2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), g1);
-            stg[lane * 8 + (q ^ (lane & 7))] = make_float4(o0.x, o0.y, o1.x, o1.y);
-          }
-          __syncwarp();
-          op_t* go = e.out_bf16 + size_t(rbase + gr) * e.ldob + (col >> 1) + 4 * gq;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = 8 * i + gr;
-            const float4 a = stg[r * 8 + (gq ^ (r & 7))];
-            if (rbase + r < p.M) *reinterpret_cast<uint2*>(go + size_t(8 * i) * e.ldob) = make_uint2(pack_op2(a.x, a.y), pack_op2(a.z, a.w));
-          }
-          __syncwarp();
-          continue;
-        }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
@@ -471,6 +501,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < 8; ++i) rs[i] = rsN[i];
       }
+      }   // !GEGLU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

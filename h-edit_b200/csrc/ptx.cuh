@@ -309,40 +309,29 @@ HEDIT_DEVICE float2 op2_to_float2(uint32_t u) {
 // x * sigmoid(x) with the fast reciprocal (2 ulp): the result is rounded to a 16-bit operand or feeds fp32 sums of thousands of terms
 HEDIT_DEVICE float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 HEDIT_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-// exact-GELU to |error| < 2e-7 with 2 MUFU + ~12 FMA-pipe instructions (Abramowitz-Stegun 7.1.26 for erf), so the
-// fused GEGLU epilogue is not issue-bound: gelu(x) = 0.5 x (1 + erf(x/sqrt2)).
-HEDIT_DEVICE float gelu_fast_f(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float ex;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * z * z));
-  const float erf_abs = fmaf(-poly, ex, 1.0f);
-  const float erf_s = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_s);
-}
-// The same formula on two values with the packed fp32x2 instructions of sm_100 (each lane of an FFMA2 rounds like a scalar FMA, so the
-// results are bit-identical to gelu_fast_f): the fused GEGLU epilogue of the K = 320 feed-forward layers is ALU-bound, not tensor-bound.
+// exact-GELU to |error| < 2e-7 (Abramowitz-Stegun 7.1.26 for erf; gelu(x) = 0.5 x (1 + erf(x / sqrt2))) on two values with the packed
+// fp32x2 instructions of sm_100: 11 FMA-pipe instructions + 4 MUFU per pair.  With z = |x| sqrt(log2(e) / 2):
+//   t = 1 / (1 + p' z)  (p' = 0.3275911 / sqrt(log2 e), bare rcp: the argument is >= 1),   exp(-x^2 / 2) = 2^(-z z),
+//   erf(|x| / sqrt2) = 1 - poly(t) 2^(-z z),   gelu = hx + |hx| erf(|x| / sqrt2)  with hx = x / 2  (the sign of x folded into |hx|).
+// The fused GEGLU epilogue of the K = 320 / 640 feed-forward layers is bound by the issue rate of its two warps per scheduler.
 HEDIT_DEVICE float2 gelu_fast_f2(float2 x) {
-  const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
-  const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
-  const float2 t = make_float2(__fdividef(1.0f, d.x), __fdividef(1.0f, d.y));
+  const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.8493218002880191f, 0.8493218002880191f));
+  const float2 d = __ffma2_rn(make_float2(0.2727374808792225f, 0.2727374808792225f), z, make_float2(1.0f, 1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
   float2 poly = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
   poly = __ffma2_rn(poly, t, make_float2(1.421413741f, 1.421413741f));
   poly = __ffma2_rn(poly, t, make_float2(-0.284496736f, -0.284496736f));
   poly = __ffma2_rn(poly, t, make_float2(0.254829592f, 0.254829592f));
   poly = __fmul2_rn(poly, t);
-  const float2 a = __fmul2_rn(__fmul2_rn(make_float2(-1.4426950408889634f, -1.4426950408889634f), z), z);
+  const float2 a = __fmul2_rn(make_float2(-z.x, -z.y), z);
   float ex0, ex1;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex0) : "f"(a.x));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex1) : "f"(a.y));
   const float2 ea = __ffma2_rn(make_float2(-poly.x, -poly.y), make_float2(ex0, ex1), make_float2(1.0f, 1.0f));
-  const float2 es = make_float2(copysignf(ea.x, x.x), copysignf(ea.y, x.y));
-  return __fmul2_rn(__fmul2_rn(make_float2(0.5f, 0.5f), x), __fadd2_rn(make_float2(1.0f, 1.0f), es));
+  const float2 hx = __fmul2_rn(make_float2(0.5f, 0.5f), x);
+  return __ffma2_rn(make_float2(fabsf(hx.x), fabsf(hx.y)), ea, hx);
 }
 
 }  // namespace hedit

@@ -96,8 +96,8 @@ class UNetEngine:
 
     def profile_forward(self, S: int, reps: int = 3):
         """{op tag: (ms per forward, launches per forward)} measured with CUDA events around every kernel."""
-        buf = C.create_string_buffer(8192)
-        _lib.check(self.lib.hedit_engine_profile_forward(self.handle, S, reps, buf, 8192), "profile")
+        buf = C.create_string_buffer(65536)
+        _lib.check(self.lib.hedit_engine_profile_forward(self.handle, S, reps, buf, 65536), "profile")
         out, self.last_profile_whole = {}, {}
         for rec in buf.value.decode().split(";"):
             if rec:

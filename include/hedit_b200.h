@@ -278,6 +278,10 @@ int hedit_face_edit(hedit_face* f, hedit_face_args* args, void* stream);
 int hedit_op_linear(const void* A_h16, const void* W_h16, const float* bias, const float* residual, float* out_f32, void* out_h16,
                     int M, int N, int K, void* stream);
 /* 3x3 conv, pad 1, stride 1 or 2, NHWC 16-bit in [S][Hin][Win][C], weights 16-bit [Cout][3][3][C] -> fp32 NHWC */
+/* GEGLU feed-forward projection (diffusers GEGLU: hidden, gate = proj(x).chunk(2); hidden * gelu(gate)) with the gate fused into the GEMM
+ * epilogue.  W [N2][K] and bias [N2] are in the engine's interleaved order: every 32 rows = 16 value rows followed by their 16 gate rows
+ * (row 32c+i <- value row 16c+i, row 32c+16+i <- gate row 16c+i).  out [M][N2/2] 16-bit. */
+int hedit_op_linear_geglu(const void* A_h16, const void* W_h16, const float* bias, void* out_h16, int M, int N2, int K, void* stream);
 int hedit_op_conv3x3(const void* x_h16, const void* w_h16, const float* bias, float* out_f32, int S, int Hin, int Win, int C, int Cout,
                      int stride, void* stream);
 /* softmax(Q K^T/sqrt(d)) V per (sample, head); q/k/v 16-bit [S][N][H*d] with row strides ldq/ldkv; idx arrays may be NULL */

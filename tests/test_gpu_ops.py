@@ -37,6 +37,25 @@ def test_linear(M, N, K):
     assert rb < 4e-3, rb             # + one bf16 rounding of the output
 
 
+@pytest.mark.parametrize("M,Nout,K", [(256, 1280, 320), (4096, 2560, 640), (1000, 512, 128), (130, 5120, 1280), (128, 16, 64)])
+def test_linear_geglu(M, Nout, K):
+    """diffusers GEGLU: hidden, gate = proj(x).chunk(2, -1); hidden * gelu(gate), exact (erf) GELU -- fused into the GEMM epilogue on
+    weights interleaved 16 value rows | 16 gate rows."""
+    _seed()
+    A = bf(torch.randn(M, K, device=DEV))
+    W = bf(torch.randn(2 * Nout, K, device=DEV) / math.sqrt(K))
+    bias = torch.randn(2 * Nout, device=DEV)
+    nc = Nout // 16
+    idx = torch.stack([torch.arange(Nout, device=DEV).view(nc, 16), Nout + torch.arange(Nout, device=DEV).view(nc, 16)], 1).reshape(-1)
+    Wi, bi = W[idx].contiguous(), bias[idx].contiguous()
+    out = torch.zeros(M, Nout, device=DEV, dtype=opdtype())
+    sync_check(lib().hedit_op_linear_geglu(P(A), P(Wi), P(bi), P(out), M, 2 * Nout, K, None), "geglu")
+    y = A.float() @ W.float().t() + bias
+    ref = y[:, :Nout] * F.gelu(y[:, Nout:])
+    r, m = rel_err(out, ref)
+    assert r < 1e-3, (r, m)          # one 16-bit rounding of the output; the GELU itself is accurate to 2e-7
+
+
 @pytest.mark.parametrize("S,H,W,C,Cout,stride", [(2, 64, 64, 64, 64, 1), (1, 64, 64, 320, 320, 1), (3, 32, 32, 128, 256, 1),
                                                  (5, 8, 8, 192, 160, 1), (4, 16, 16, 640, 320, 1), (2, 64, 64, 64, 128, 2),
                                                  (3, 32, 32, 128, 128, 2), (5, 16, 16, 256, 256, 2), (9, 4, 4, 64, 64, 1), (2, 64, 64, 960, 320, 1)])

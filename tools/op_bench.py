@@ -53,6 +53,17 @@ def bench_linear(iters):
         print(f"linear M={M} N={N} K={K} res={res} f32out={f32}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
 
 
+def bench_geglu(iters):
+    """Feed-forward GEGLU projections of the three UNet levels at 40 samples."""
+    for (M, N2, K) in [(163840, 2560, 320), (40960, 5120, 640), (10240, 10240, 1280)]:
+        A, W = bf(torch.randn(M, K, device=DEV)), bf(torch.randn(N2, K, device=DEV) * K ** -0.5)
+        bias = torch.randn(N2, device=DEV)
+        out = torch.empty(M, N2 // 2, device=DEV, dtype=A.dtype)
+        fn = lambda: lib().hedit_op_linear_geglu(P(A), P(W), P(bias), P(out), M, N2, K, None)
+        ms = timeit(fn, iters)
+        print(f"geglu M={M} N2={N2} K={K}: {ms:.3f} ms  {2.0 * M * N2 * K / ms / 1e9:.1f} TFLOP/s")
+
+
 def bench_conv(iters):
     for (S, H, C, Co, st) in [(16, 64, 320, 320, 1), (16, 32, 640, 640, 1), (16, 16, 1280, 1280, 1), (16, 8, 2560, 1280, 1), (16, 64, 960, 320, 1)]:
         x = bf(torch.randn(S, H, H, C, device=DEV))
@@ -147,5 +158,7 @@ if __name__ == "__main__":
         bench_cross(a.iters)
     if a.what in ("vae", "all"):
         bench_vae(a.iters)
+    if a.what in ("geglu", "all"):
+        bench_geglu(a.iters)
     if a.what in ("face", "all"):
         bench_face(a.iters)
