@@ -329,6 +329,18 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
       // staging transpose (so the 4 KB tile holds 32 rows x 64 columns) and written back as full 128-byte lines -- half the latency-bound
       // iterations and half the store instructions of the 32-column path.
       if (e.diag_skip) {
+        if (e.diag_skip == 2) {     // diagnostics: read the accumulator like a write-back would, discard it (TMEM-port contention probe)
+          uint32_t acc_x = 0;
+#pragma unroll 1
+          for (int c0 = half * 32; c0 < BN; c0 += 64) {
+            uint32_t raw[32];
+            tmem_ld32(t_row + c0, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc_x ^= raw[j];
+          }
+          if (acc_x == 0x7fc12345u && e.out_bf16) e.out_bf16[0] = to_op(1.f);
+        }
       } else if (GEGLU) {
         // chunk = 16 value columns followed by their 16 gate columns -> 16 outputs (bias applied before the gate), packed to 16 bits
         // BEFORE the staging transpose ([32 rows][32 B], 16-byte slots XOR-swizzled) and written back as 16 rows x 32 B per instruction
