@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
       // 16-bit outputs without bias / residual (q|k|v, q, text k|v projections): 64 columns per iteration, converted to 16 bits BEFORE the
       // staging transpose (so the 4 KB tile holds 32 rows x 64 columns) and written back as full 128-byte lines -- half the latency-bound
       // iterations and half the store instructions of the 32-column path.
-      if (e.diag_skip) {
+      if (e.diag_skip == 1 || e.diag_skip == 2) {
         if (e.diag_skip == 2) {     // diagnostics: read the accumulator like a write-back would, discard it (TMEM-port contention probe)
           uint32_t acc_x = 0;
 #pragma unroll 1
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
           for (int i = 0; i < 2; ++i) {
             const int r = 16 * i + hr;
             const uint4 a = stg16[r * 2 + (hs ^ ((r >> 2) & 1))];
-            if (rows_full || rbase + r < p.M) *reinterpret_cast<uint4*>(go + size_t(16 * i) * e.ldob) = a;
+            if ((rows_full || rbase + r < p.M) && e.diag_skip != 3) *reinterpret_cast<uint4*>(go + size_t(16 * i) * e.ldob) = a;   // (3: probe without the stores)
           }
           __syncwarp();
 #pragma unroll
