@@ -258,6 +258,7 @@ def run_gpu(args, rank, world, local_rank):
                        "schedule": {0: "reference (9 UNet sample-forwards/step)", 1: "exact-reuse (7 UNet sample-forwards/step)",
                                     2: "exact-reuse + skip-uncond at cfg_src=1 (5 UNet sample-forwards/step)"}[args.schedule],
                        "sample_forwards_per_image": fwd / (B * args.steps),
+                       "launch": "repeated UNet launches replayed from CUDA graphs (HEDIT_LOOP_GRAPH=0: direct); gpu_launches counts the kernels inside",
                        "l2": "working set per step (1.7 GB fp16 weights + GBs of activations) >> 126 MB L2; no explicit flush needed"},
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
