@@ -263,7 +263,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   if (maxS > E.max_samples()) { E.err_ = "batch needs more samples per launch than the engine was created for"; return -1; }
   if (1 + 2 * B > 4096) { E.err_ = "too many contexts"; return -1; }
 
-  // ---- device buffers (owned by the engine for its lifetime; an edit of the same shape re-allocates -- acceptable for round 1)
+  // ---- device buffers: engine-owned slots requested in a fixed order (an edit of the same shape reuses them at the same addresses)
   LoopBuffers L;
   auto fa = [&](size_t nf) { return reinterpret_cast<float*>(tp.get(nf * sizeof(float))); };
   L.lat = fa(size_t(5) * B * n); L.eps = fa(size_t(pool) * n); L.corr = fa(size_t(B) * n); L.xin = fa(size_t(maxS) * n);
