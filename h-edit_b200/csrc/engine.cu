@@ -365,7 +365,7 @@ static cudaError_t launch_gemm_t(const GemmParams& g, cudaStream_t st) {
   if (!attr_set) { cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CL, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, CL>::SMEM_BYTES); attr_set = true; }
   const int m_tiles = (g.M + 127) / 128, n_tiles = (g.N + BN - 1) / BN;
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = GemmCfg<BN, CL>::SMEM_BYTES; cfg.stream = st;
+  cfg.blockDim = dim3(GG ? 576 : 320); cfg.dynamicSmemBytes = GemmCfg<BN, CL>::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute at[1];
   if (CL) {
     const int pairs = ((m_tiles + 1) / 2) * n_tiles;

@@ -108,7 +108,8 @@ struct GemmCfg {
 // are not allocated, which lets the compiler keep all 8 packed GELU evaluations of a chunk in flight (the K = 320 feed-forward
 // projection is bound by the latency of that epilogue, not by the tensor pipe).
 template <int BN, bool CLUSTER, bool GEGLU = false>
-__global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(GEGLU ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int EW = GEGLU ? 16 : 8;      // epilogue warps: the GEGLU write-back is instruction-bound, so it gets 4 warps per scheduler
   using Cfg = GemmCfg<BN, CLUSTER>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CLUSTER ? 16 : 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CLUSTER ? 2 * EW : EW); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const GemmEpilogue& e = p.ep;
-    float4* stg = reinterpret_cast<float4*>(smem + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * 256;   // [32 rows][8 quads]
+    float4* stg = reinterpret_cast<float4*>(smem + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * (GEGLU ? 64 : 256);   // [32 rows][8 quads] (GEGLU: [32 rows][32 B])
     const int rq = lane & 7, rr = lane >> 3;           // read-back role (non-GEGLU): quad, row-in-group-of-4
     // feature combination of this launch -> specialised write-back loop (0 = generic path)
     const bool has_b = e.bias != nullptr, has_rv = e.rowvec != nullptr, has_res = e.residual != nullptr;
@@ -315,14 +316,6 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
         }
       };
       prefetch(n0 + half * 32, bb, rvv, rs);
-      // GEGLU: bias of this warp's first chunk, requested before the accumulator is ready (warp-uniform addresses: one broadcast line)
-      float4 gbias[8];
-      auto geglu_bias = [&](int col, float4 (&b_)[8]) {        // col: start of a chunk inside N (N % 32 == 0; GEGLU launches always carry a bias)
-        const float4* bp = reinterpret_cast<const float4*>(e.bias + col);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) b_[j] = __ldg(bp + j);
-      };
-      if (GEGLU) geglu_bias(min(n0 + half * 32, p.N - 32), gbias);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       // 16-bit outputs without bias / residual (q|k|v, q, text k|v projections): 64 columns per iteration, converted to 16 bits BEFORE the
@@ -346,12 +339,18 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
         // BEFORE the staging transpose ([32 rows][32 B], 16-byte slots XOR-swizzled) and written back as 16 rows x 32 B per instruction
         uint4* stg16 = reinterpret_cast<uint4*>(stg);
         const int hs = lane & 1, hr = lane >> 1;
-        // one chunk: bias + gate + pack + transposed write-back.  The TMEM read of the NEXT chunk is issued before this runs (two
-        // register buffers), so the 64 B/clk TMEM port works while the GELU math and the stores of the current chunk execute.
-        auto chunk = [&](int c0, const uint32_t (&raw)[32]) {
+        // warp (quarter, half = column group 0..3) owns every fourth 32-column chunk
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BN; c0 += 32 * (EW / 4)) {
           const int col = n0 + c0;
-          float4 gnext[8];
-          geglu_bias(min(col + 64, p.N - 32), gnext);                // next chunk's bias in flight during this chunk's math (clamped: a reload at the end)
+          if (col >= p.N) break;                      // warp-uniform
+          uint32_t raw[32];
+          tmem_ld32(t_row + c0, raw);
+          const float4* bp = reinterpret_cast<const float4*>(e.bias + col);     // (GEGLU launches always carry a bias; N % 32 == 0)
+          float4 gbias[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gbias[j] = __ldg(bp + j);
+          tmem_ld_wait();
           uint32_t pk[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -374,26 +373,6 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_tcgen05_kernel(const __grid_
             if ((rows_full || rbase + r < p.M) && e.diag_skip != 3) *reinterpret_cast<uint4*>(go + size_t(16 * i) * e.ldob) = a;   // (3: probe without the stores)
           }
           __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) gbias[j] = gnext[j];
-        };
-        uint32_t rawA[32], rawB[32];
-        const int c_first = half * 32;
-        if (n0 + c_first < p.N) {
-          tmem_ld32(t_row + c_first, rawA);
-#pragma unroll 1
-          for (int c0 = c_first; c0 < BN; c0 += 128) {             // (all conditions warp-uniform)
-            const bool more1 = (c0 + 64 < BN) && (n0 + c0 + 64 < p.N);
-            tmem_ld_wait();
-            if (more1) tmem_ld32(t_row + c0 + 64, rawB);
-            chunk(c0, rawA);
-            if (!more1) break;
-            const bool more2 = (c0 + 128 < BN) && (n0 + c0 + 128 < p.N);
-            tmem_ld_wait();
-            if (more2) tmem_ld32(t_row + c0 + 128, rawA);
-            chunk(c0 + 64, rawB);
-            if (!more2) break;
-          }
         }
       } else {
       const bool wide16 = (BN == 256) && mode == 4 && rows_full && ((p.N - n0) >= BN || ((p.N - n0) & 63) == 0);
