@@ -87,15 +87,17 @@ HEDIT_DEVICE void epi_store_rows(const float4* stg, int rq, int rr, const float4
   if (F32 && cst) epi_store_colstats(su, sq, rr, cst);      // cst is warp-uniform
 }
 
-template <int BN, bool PAIR>
+// EPI: 0 = generic write-back (8 epilogue warps), 1 = GEGLU (16 warps, 1 KB staging each), 2 = bias + fp32 residual -> fp32 of the small-K
+// projections (16 warps with 4 KB staging each, paid for with one pipeline stage)
+template <int BN, bool PAIR, int EPI = 0>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;     // PAIR: each CTA stages half of the W tile
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = PAIR ? (BN > 160 ? 6 : 7) : (BN > 160 ? 4 : 5);
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
-  static constexpr int THREADS = 320;
+  static constexpr int STAGES = (PAIR ? (BN > 160 ? 6 : 7) : (BN > 160 ? 4 : 5)) - (EPI == 2 ? 1 : 0);
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + (EPI == 2 ? 16 : 8) * 4096 /*epilogue staging*/;
+  static constexpr int THREADS = EPI ? 576 : 320;
 };
 
 // PAIR = true: cta_group::2.  Two CTAs of one cluster (an SM pair) own two consecutive M tiles of the same N tile and issue
@@ -107,10 +109,15 @@ struct GemmCfg {
 // GEGLU = the fused GEGLU write-back as its own instantiation: the generic write-back's double-buffered bias / residual registers (64+)
 // are not allocated, which lets the compiler keep all 8 packed GELU evaluations of a chunk in flight (the K = 320 feed-forward
 // projection is bound by the latency of that epilogue, not by the tensor pipe).
-template <int BN, bool CLUSTER, bool GEGLU = false>
-__global__ void __launch_bounds__(GEGLU ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  constexpr int EW = GEGLU ? 16 : 8;      // epilogue warps: the GEGLU write-back is instruction-bound, so it gets 4 warps per scheduler
-  using Cfg = GemmCfg<BN, CLUSTER>;
+template <int BN, bool CLUSTER, int EPI = 0>
+__global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  constexpr bool GEGLU = (EPI == 1);
+  // epilogue warps: the GEGLU write-back is instruction-bound and the fp32-residual write-back of the K <= 640 projections is bound by
+  // the bytes it keeps in flight (HBM latency), so both get 4 warps per scheduler; EPI == 2 then loads its bias / residual for the
+  // CURRENT chunk (thread-level parallelism instead of the generic path's register double-buffering: 112 registers per thread)
+  constexpr int EW = EPI ? 16 : 8;
+  constexpr int CSTEP = 32 * (EW / 4);    // column distance between two chunks of one warp
+  using Cfg = GemmCfg<BN, CLUSTER, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(GEGLU ? 576 : 320, 1) gemm_bf16_tcgen05_kernel
           }
         }
       };
-      prefetch(n0 + half * 32, bb, rvv, rs);
+      if (EPI != 2) prefetch(n0 + half * 32, bb, rvv, rs);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       // 16-bit outputs without bias / residual (q|k|v, q, text k|v projections): 64 columns per iteration, converted to 16 bits BEFORE the
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(GEGLU ? 576 : 320, 1) gemm_bf16_tcgen05_kernel
         const int hs = lane & 1, hr = lane >> 1;
         // warp (quarter, half = column group 0..3) owns every fourth 32-column chunk
 #pragma unroll 1
-        for (int c0 = half * 32; c0 < BN; c0 += 32 * (EW / 4)) {
+        for (int c0 = half * 32; c0 < BN; c0 += CSTEP) {
           const int col = n0 + c0;
           if (col >= p.N) break;                      // warp-uniform
           uint32_t raw[32];
@@ -403,11 +410,12 @@ __global__ void __launch_bounds__(GEGLU ? 576 : 320, 1) gemm_bf16_tcgen05_kernel
         }
       } else
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      for (int c0 = half * 32; c0 < BN; c0 += CSTEP) {
         const int col = n0 + c0;
         if (col >= p.N) break;                      // warp-uniform
         uint32_t raw[32];
         tmem_ld32(t_row + c0, raw);
+        if (EPI == 2) prefetch(col, bb, rvv, rs);   // this chunk's bias / residual, in flight during the TMEM read
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -441,7 +449,7 @@ __global__ void __launch_bounds__(GEGLU ? 576 : 320, 1) gemm_bf16_tcgen05_kernel
           __syncwarp();
           continue;
         }
-        if (c0 + 64 < BN) prefetch(col + 64, bbN, rvvN, rsN);      // next chunk of this warp (warp-uniform condition)
+        if (EPI != 2 && c0 + CSTEP < BN) prefetch(col + CSTEP, bbN, rvvN, rsN);      // next chunk of this warp (warp-uniform condition)
         const int cq = col + 4 * rq;
         if (mode != 0 && rows_full && col + 32 <= p.N) {
           float* o32 = has32 ? e.out_f32 + row0 * e.ldo + cq : nullptr;
@@ -488,9 +496,11 @@ __global__ void __launch_bounds__(GEGLU ? 576 : 320, 1) gemm_bf16_tcgen05_kernel
                                e.colstats + size_t(rbase >> 5) * p.N + cq);
         }
         __syncwarp();
-        bb = bbN; rvv = rvvN;
+        if (EPI != 2) {
+          bb = bbN; rvv = rvvN;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rs[i] = rsN[i];
+          for (int i = 0; i < 8; ++i) rs[i] = rsN[i];
+        }
       }
       }   // !GEGLU
       tc_fence_before();

@@ -35,6 +35,11 @@ def test_linear(M, N, K):
     assert r < 2e-5, (r, m)          # fp32 accumulate, order-of-summation only
     rb, _ = rel_err(outb, ref)
     assert rb < 4e-3, rb             # + one bf16 rounding of the output
+    # fp32-only output with bias + residual: the attention / projection-output form (small K takes the 16-epilogue-warp instantiation)
+    out2 = torch.full((M, N), float("nan"), device=DEV)
+    sync_check(lib().hedit_op_linear(P(A), P(W), P(bias), P(res), P(out2), None, M, N, K, None), "linear f32")
+    r2, m2 = rel_err(out2, ref)
+    assert r2 < 2e-5, (r2, m2)
 
 
 @pytest.mark.parametrize("M,Nout,K", [(256, 1280, 320), (4096, 2560, 640), (1000, 512, 128), (130, 5120, 1280), (128, 16, 64)])
