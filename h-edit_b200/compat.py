@@ -86,7 +86,9 @@ def h_edit_p2p_implicit_compat(model, xT, eta, prompts, cfg_scales, zs, controll
     from .samplers import encode_text
     steps = after_skip_steps if after_skip_steps is not None else model.scheduler.num_inference_steps
     unet = unet or register_attention_control_compat(model, controller)
-    dev = torch.device("cuda", unet.engine.device)
+    # `unet` is normally the CompatUNet over the native engine; any callable with the reference's `model.unet` protocol is accepted so
+    # that the loop arithmetic itself can be checked against the reference sampler (tests/test_oracle_pin.py does, on a torch UNet)
+    dev = torch.device("cuda", unet.engine.device) if hasattr(unet, "engine") else torch.as_tensor(xT).device
     w_src, w_src_edit, w_tar = (float(c) for c in cfg_scales)
     null = encode_text(model, [""]).float().to(dev)
     src_tar = encode_text(model, list(prompts[:2])).float().to(dev)

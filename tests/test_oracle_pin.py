@@ -168,3 +168,52 @@ assert err < 1e-5, err
     assert r.returncode == 0 and "FACE_REL_ERR" in r.stdout, r.stderr[-2000:]
     g = load_golden("tiny_face_k2")
     assert (g["no_reward"] - g["x0"]).abs().max().item() < 1e-4
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("is_replace,K", [(False, 2), (True, 1)])
+def test_compat_loop_and_protocol_controller_match_reference_sampler(is_replace, K):
+    """The compat sampler's loop arithmetic (hedit_b200/compat.py) and the user-side protocol controller of the GPU tests
+    (tests/protocol_controller.py), both on CPU on the oracle UNet with the REFERENCE's processors installed, against the unmodified
+    reference sampler driving the reference's own controller: same latents, same controller bookkeeping."""
+    import hedit_b200
+    from hedit_b200.compat import h_edit_p2p_implicit_compat
+    from oracle.sd_unet import UNetConfig
+    from protocol_controller import UserController
+    ref = load_reference()
+    torch.manual_seed(0)
+    T = 4
+    cfg = UNetConfig.tiny(sample_size=16)
+    model = OraclePipeline(cfg, seed=0)
+    model.scheduler.set_timesteps(T)
+    prompts = ["a green lizard is sitting on a branch", "a brown lizard is sitting on a branch"]
+    g = torch.Generator().manual_seed(5)
+    xT = torch.randn(1, cfg.in_channels, 16, 16, generator=g)
+    zs = torch.randn(T, cfg.in_channels, 16, 16, generator=g)
+    kw = dict(cross_replace_steps=0.4, self_replace_steps=0.5, blend_word=None, equilizer_params={"words": ("brown",), "values": (2.0,)},
+              num_steps=T, tokenizer=model.tokenizer)
+    args = dict(eta=1.0, prompts=prompts, cfg_scales=[1.0, 5.0, 7.5], zs=zs, weight_reconstruction=0.1, optimization_steps=K,
+                after_skip_steps=T, is_ddim_inversion=False)
+
+    c_ref = ref.ptp_controller_utils.make_controller(prompts=prompts, is_replace_controller=is_replace, device="cpu", **kw)
+    ref.ptp_utils.register_attention_control(model, c_ref)
+    ed_ref, rc_ref = ref.p2p_h_edit.h_Edit_p2p_implicit(model, xT=xT, prog_bar=False, controller=c_ref, **args)
+
+    user = UserController(hedit_b200.make_controller(prompts, is_replace, kw["cross_replace_steps"], kw["self_replace_steps"], None,
+                                                     kw["equilizer_params"], T, model.tokenizer), "cpu")
+    assert hedit_b200.controller_kind(user) == "custom"
+    ref.ptp_utils.register_attention_control(model, user)          # the reference's processors now call the user object
+
+    class TorchUNet:                                               # `model.unet` protocol on the oracle UNet
+        def __call__(self, sample, t, encoder_hidden_states=None, cross_attention_kwargs=None):
+            return model.unet(sample, t, encoder_hidden_states=encoder_hidden_states, cross_attention_kwargs=cross_attention_kwargs)
+
+    ed, rc = h_edit_p2p_implicit_compat(model, xT, controller=user, unet=TorchUNet(), **args)
+    assert (ed - ed_ref).abs().max().item() < 2e-5 and (rc - rc_ref).abs().max().item() < 2e-5
+    assert (ed_ref - rc_ref).abs().max().item() > 1e-2            # the edit really moved the latent
+    assert user.cur_step == c_ref.cur_step == T and user.cur_att_layer == c_ref.cur_att_layer == 0
+    assert user.num_att_layers == c_ref.num_att_layers
+    for key, items in c_ref.attention_store.items():
+        assert len(items) == len(user.attention_store[key])
+        for a, b in zip(items, user.attention_store[key]):
+            assert torch.allclose(a, b, atol=1e-5)
