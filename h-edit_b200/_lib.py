@@ -56,6 +56,9 @@ class StepCoefC(C.Structure):
 GUIDANCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int)
 # hedit_attn_probs_fn(user, tf_index, is_cross, place, probs, batch_heads, n_query, n_key)
 ATTN_PROBS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int)
+# hedit_attn_editor_fn(user, tf_index, is_cross, place, q, k, v, sim, attn, out, batch_heads, n_query, n_key, d)
+ATTN_EDITOR_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_int, C.c_int, C.c_int, C.c_int)
 
 
 class EditArgsC(C.Structure):
@@ -98,6 +101,7 @@ SYMBOLS = {
     "hedit_unet_forward": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "hedit_unet_forward_indexed": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _P]),
     "hedit_unet_forward_compat": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P]),
+    "hedit_unet_forward_editor": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P]),
     "hedit_edit_p2p": (_I, [_P, C.POINTER(EditArgsC), _P]),
     "hedit_vae_create": (_P, [C.POINTER(VaeConfigC), _I]),
     "hedit_vae_destroy": (None, [_P]),

@@ -51,8 +51,8 @@ class CompatUNet:
     """`model.unet` stand-in over the native engine honouring the reference's `cross_attention_kwargs` (`use_controller`, `save_attn`:
     ptp_utils.py:38-46).  Launches without a controller use the fused kernels."""
 
-    def __init__(self, engine, controller=None):
-        self.engine, self.controller = engine, controller
+    def __init__(self, engine, controller=None, editor=None):
+        self.engine, self.controller, self.editor = engine, controller, editor
         self.in_channels = engine.config["in_channels"]
         self.sample_size = engine.config["sample_size"]
 
@@ -61,6 +61,12 @@ class CompatUNet:
         use = kw.get("use_controller", True) and self.controller is not None
         save = kw.get("save_attn", True)
         t = timestep.detach().cpu().numpy() if torch.is_tensor(timestep) else timestep
+        if self.editor is not None and kw.get("use_editor", True):       # MasaCtrl protocol (masactrl_utils.py:40-89)
+            ed = self.editor
+
+            def hook(_layer, is_cross, place, q, k, v, sim, attn, heads):
+                return ed(q, k, v, sim, attn, is_cross, PLACES[place], heads, scale=float(q.shape[-1]) ** -0.5)
+            return _Out(self.engine.forward_editor(sample, t, encoder_hidden_states, hook))
         if not use:
             return _Out(self.engine.forward(sample, t, encoder_hidden_states))
         ctrl = self.controller
@@ -81,7 +87,7 @@ def register_attention_control_compat(model, controller):
 
 @torch.no_grad()
 def h_edit_p2p_implicit_compat(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstruction=0.075, optimization_steps=1,
-                               after_skip_steps: Optional[int] = None, is_ddim_inversion=False, unet=None):
+                               after_skip_steps: Optional[int] = None, is_ddim_inversion=False, unet=None, editor_mode=False):
     """Implicit h-Edit + P2P for one image with a protocol-only controller (p2p_h_edit.py:529-701).  Returns (edited, reconstructed)."""
     from .samplers import encode_text
     steps = after_skip_steps if after_skip_steps is not None else model.scheduler.num_inference_steps
@@ -96,7 +102,9 @@ def h_edit_p2p_implicit_compat(model, xT, eta, prompts, cfg_scales, zs, controll
     ctx_a = torch.cat([null, null, src, src])
     ctx_c = torch.cat([null, null, src, tar])
     ts, coef = step_tables(model.scheduler, steps, eta, is_ddim_inversion)
-    off = {"use_controller": False}
+    # launches A and B run without control; launch C with it: the P2P controller (`save_attn` per inner iteration) or, in editor mode,
+    # MasaCtrl's editor, which the reference leaves on by passing no kwargs at all (masactrl_h_edit.py:98,124,131)
+    off = {"use_editor": False} if editor_mode else {"use_controller": False}
     x = xT.reshape(1, *xT.shape[-3:]).to(dev, torch.float32)
     xt = torch.cat([x, x])
     zs = zs.to(dev, torch.float32)
@@ -114,11 +122,11 @@ def h_edit_p2p_implicit_compat(model, xT, eta, prompts, cfg_scales, zs, controll
             save = k == optimization_steps - 1                                            # :637-640
             c_src = unet(x_opt, tt, encoder_hidden_states=src, cross_attention_kwargs=off).sample                      # :644
             out = unet(torch.cat([x_orig, x_opt, x_orig, x_opt]), tt, encoder_hidden_states=ctx_c,                   # :652
-                       cross_attention_kwargs={"save_attn": save}).sample
+                       cross_attention_kwargs=None if editor_mode else {"save_attn": save}).sample
             u_tar, c_tar = out[1:2], out[3:4]
             corr = (u_tar + w_tar * (c_tar - u_tar)) - (u_tar + w_src_edit * (c_src - u_tar))                          # :659-667
             rec = x_opt
-            if k > 0:                                                                                                  # :670-686
+            if k > 0 and not editor_mode:                                                                              # :670-686 (the MasaCtrl sampler has no pull)
                 g = torch.sign(x_opt - x_base) / x_opt.numel()
                 rho = corr.pow(2).mean().sqrt() / (g.pow(2).mean().sqrt() + 1e-8) * weight_reconstruction
                 rec = x_opt - rho * g
@@ -127,3 +135,20 @@ def h_edit_p2p_implicit_compat(model, xT, eta, prompts, cfg_scales, zs, controll
         if controller is not None and hasattr(controller, "step_callback"):
             xt = controller.step_callback(xt)                                                                          # :698-699
     return xt[1:2].clone(), xt[0:1].clone()
+
+
+def register_attention_editor_compat(model, editor):
+    """masactrl_utils.py:35-107 for the compat path: the UNet callable whose attention layers hand q, k, v, sim, attn to `editor`."""
+    from .samplers import get_engine
+    eng = get_engine(model, max_samples=5)
+    editor.num_att_layers = 2 * eng.n_transformer_blocks()
+    return CompatUNet(eng, editor=editor)
+
+
+def h_edit_masactrl_implicit_compat(model, xT, eta, prompts, cfg_scales, zs, editor, optimization_steps=1, after_skip_steps=None,
+                                    is_ddim_inversion=True, unet=None):
+    """Implicit h-Edit with an ARBITRARY MasaCtrl-protocol editor object (masactrl_h_edit.py:14-160): the same three launches per step as
+    the P2P sampler, the third with the editor on, no reconstruction pull, no step callback."""
+    unet = unet or register_attention_editor_compat(model, editor)
+    return h_edit_p2p_implicit_compat(model, xT, eta, prompts, cfg_scales, zs, None, 0.0, optimization_steps, after_skip_steps,
+                                      is_ddim_inversion, unet=unet, editor_mode=True)

@@ -211,7 +211,8 @@ int hedit_engine_profile_forward(hedit_engine* h, int S, int reps, char* out, in
 }
 
 static int unet_forward_impl(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int n_ctx, const int32_t* ctx_idx,
-                             int S, float* eps, void* stream, hedit_attn_probs_fn probs_cb, void* probs_user) {
+                             int S, float* eps, void* stream, hedit_attn_probs_fn probs_cb, void* probs_user,
+                             hedit_attn_editor_fn editor_cb = nullptr, void* editor_user = nullptr) {
   if (!h) return fail("null engine");
   cudaSetDevice(h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -238,6 +239,7 @@ static int unet_forward_impl(hedit_engine* h, const float* x, const float* times
   CallCtrl cc;
   cc.ctx_idx = h->d_ctx_idx; cc.time_idx = h->d_tidx; cc.unit_s0 = h->d_unit0; cc.unit_s1 = h->d_unit1; cc.unit_img = h->d_uimg; cc.n_units = S;
   cc.probs_cb = probs_cb; cc.probs_user = probs_user;
+  cc.editor_cb = editor_cb; cc.editor_user = editor_user;
   const long r = E.forward(x, eps, S, cc, st);
   if (r < 0) return fail(E.error());
   cudaError_t e = cudaStreamSynchronize(st);
@@ -254,6 +256,12 @@ int hedit_unet_forward_compat(hedit_engine* h, const float* x, const float* time
                               hedit_attn_probs_fn probs_hook, void* user, void* stream) {
   if (!probs_hook) return fail("hedit_unet_forward_compat needs a probabilities hook");
   return unet_forward_impl(h, x, timesteps, ctx, S, nullptr, S, eps, stream, probs_hook, user);
+}
+
+int hedit_unet_forward_editor(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int S, float* eps,
+                              hedit_attn_editor_fn editor_hook, void* user, void* stream) {
+  if (!editor_hook) return fail("hedit_unet_forward_editor needs an editor hook");
+  return unet_forward_impl(h, x, timesteps, ctx, S, nullptr, S, eps, stream, nullptr, nullptr, editor_hook, user);
 }
 
 int hedit_unet_forward(hedit_engine* h, const float* x, const float* timesteps, const float* ctx, int S, float* eps, void* stream) {

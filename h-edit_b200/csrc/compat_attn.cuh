@@ -127,4 +127,24 @@ static __global__ void __launch_bounds__(256) compat_pv_kernel(const CompatAttnP
   }
 }
 
+// ---- editor protocol (masactrl/masactrl_utils.py:40-89): the hook receives q, k, v as fp32 [(S*H)][N][d], the scaled scores and the
+// probabilities, and returns the layer output [S][N][H*d]
+// 16-bit [samples][N][ld], head h at columns h*d  ->  fp32 [(s*H + h)][N][d]; grid (ceil(N*d / 256), S*H)
+static __global__ void compat_split_heads_kernel(const op_t* __restrict__ src, int ld, size_t sample_stride, const int* __restrict__ idx,
+                                                 float* __restrict__ dst, int H, int d, int N) {
+  const int b = blockIdx.y, s = b / H, h = b % H;
+  const int ss = idx ? idx[s] : s;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= N * d) return;
+  const int n = e / d, c = e % d;
+  dst[(size_t(b) * N + n) * d + c] = op_to_float(src[size_t(ss) * sample_stride + size_t(n) * ld + h * d + c]);
+}
+// fp32 [rows][C] -> 16-bit [rows][ldo]
+static __global__ void compat_store_out_kernel(const float* __restrict__ src, op_t* __restrict__ dst, int ldo, int C, size_t rows) {
+  const size_t e = size_t(blockIdx.x) * 256 + threadIdx.x;
+  if (e >= rows * C) return;
+  const size_t r = e / C; const int c = int(e % C);
+  dst[r * ldo + c] = to_op(src[e]);
+}
+
 }  // namespace hedit

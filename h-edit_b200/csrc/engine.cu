@@ -229,6 +229,7 @@ Engine::~Engine() {
   for (void* p : owned_) cudaFree(p);
   if (arena_) cudaFree(arena_);
   if (compat_probs_) cudaFree(compat_probs_);
+  if (compat_aux_) cudaFree(compat_aux_);
 }
 
 void Engine::drop_graphs() {
@@ -897,14 +898,14 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
       launch_layernorm(op.f_in, op.gamma, op.beta, op.h_out, op.rows, op.C1, op.eps, st);
       break;
     case OP_SELF_ATTN: {
-      if (cc.probs_cb) return compat_attention(op, false, S, cc, st);
+      if (cc.probs_cb || cc.editor_cb) return compat_attention(op, false, S, cc, st);
       AttnParams a = op.attn;
       if (cc.self_mask & (1u << op.tf_index)) { a.q_idx = cc.self_q; a.k_idx = cc.self_k; a.v_idx = cc.self_v; }
       CK(launch_self_attn(a, op.dch, S, st));
       break;
     }
     case OP_CROSS_ATTN: {
-      if (cc.probs_cb) return compat_attention(op, true, S, cc, st);
+      if (cc.probs_cb || cc.editor_cb) return compat_attention(op, true, S, cc, st);
       AttnParams a = op.attn;
       a.unit_s0 = cc.unit_s0; a.unit_s1 = cc.unit_s1; a.unit_img = cc.unit_img; a.ctx_idx = cc.ctx_idx;
       a.mapper = cc.mapper; a.c_base = cc.c_base; a.c_tar = cc.c_tar; a.replace_m = cc.replace_m; a.is_replace = cc.is_replace;
@@ -951,8 +952,35 @@ long Engine::compat_attention(const Op& op, bool is_cross, int S, const CallCtrl
   p.H = a.H; p.d = a.d; p.Nq = a.Nq; p.Nkv = a.Nkv;
   p.scale = float(1.0 / std::sqrt(double(a.d)));
   const int BH = S * a.H;
-  compat_scores_kernel<<<dim3((a.Nkv + 63) / 64, (a.Nq + 63) / 64, BH), 256, 0, st>>>(p);
   const size_t rows = size_t(BH) * a.Nq;
+  if (cc.editor_cb) {
+    // editor protocol: q, k, v split by head in fp32, scaled scores AND probabilities materialised, output returned by the hook
+    const size_t n_sim = size_t(BH) * a.Nq * a.Nkv, n_q = size_t(BH) * a.Nq * a.d, n_kv = size_t(BH) * a.Nkv * a.d, n_out = size_t(S) * a.Nq * a.H * a.d;
+    const size_t aux = (n_sim + n_q + 2 * n_kv + n_out) * sizeof(float);
+    if (aux > compat_aux_bytes_) {
+      if (compat_aux_) { CK(cudaStreamSynchronize(st)); cudaFree(compat_aux_); compat_aux_ = nullptr; compat_aux_bytes_ = 0; }
+      if (cudaMalloc(&compat_aux_, aux) != cudaSuccess) { cudaGetLastError(); err_ = "compat attention: cudaMalloc of the editor buffers failed (" + std::to_string(aux >> 20) + " MiB)"; return -1; }
+      compat_aux_bytes_ = aux;
+    }
+    float *sim = compat_aux_, *qf = sim + n_sim, *kf = qf + n_q, *vf = kf + n_kv, *of = vf + n_kv;
+    compat_split_heads_kernel<<<dim3((a.Nq * a.d + 255) / 256, BH), 256, 0, st>>>(p.q, p.ldq, p.q_sample, nullptr, qf, a.H, a.d, a.Nq);
+    compat_split_heads_kernel<<<dim3((a.Nkv * a.d + 255) / 256, BH), 256, 0, st>>>(p.k, p.ldkv, p.kv_sample, p.kv_idx, kf, a.H, a.d, a.Nkv);
+    compat_split_heads_kernel<<<dim3((a.Nkv * a.d + 255) / 256, BH), 256, 0, st>>>(p.v, p.ldkv, p.kv_sample, p.kv_idx, vf, a.H, a.d, a.Nkv);
+    p.probs = sim;
+    compat_scores_kernel<<<dim3((a.Nkv + 63) / 64, (a.Nq + 63) / 64, BH), 256, 0, st>>>(p);
+    CK(cudaMemcpyAsync(compat_probs_, sim, n_sim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    compat_softmax_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(compat_probs_, rows, a.Nkv);
+    CK(cudaGetLastError());
+    if (cc.editor_cb(cc.editor_user, op.tf_index, is_cross ? 1 : 0, tf_place_[op.tf_index], qf, kf, vf, sim, compat_probs_, of, BH, a.Nq, a.Nkv, a.d) != 0) {
+      err_ = "compat attention: the editor hook failed";
+      return -1;
+    }
+    const size_t orow = size_t(S) * a.Nq;
+    compat_store_out_kernel<<<unsigned((orow * a.H * a.d + 255) / 256), 256, 0, st>>>(of, a.out, a.ldo, a.H * a.d, orow);
+    CK(cudaGetLastError());
+    return 8;
+  }
+  compat_scores_kernel<<<dim3((a.Nkv + 63) / 64, (a.Nq + 63) / 64, BH), 256, 0, st>>>(p);
   compat_softmax_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(compat_probs_, rows, a.Nkv);
   CK(cudaGetLastError());
   if (cc.probs_cb(cc.probs_user, op.tf_index, is_cross ? 1 : 0, tf_place_[op.tf_index], compat_probs_, BH, a.Nq, a.Nkv) != 0) {
@@ -988,7 +1016,7 @@ long Engine::forward(const float* x, float* eps, int S, const CallCtrl& cc, cuda
 static bool loop_graphs_env() { static const bool v = !(getenv("HEDIT_LOOP_GRAPH") && atoi(getenv("HEDIT_LOOP_GRAPH")) == 0); return v; }
 
 long Engine::forward_replayed(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st) {
-  if (!graph_replay_ || !loop_graphs_env() || cc.probs_cb) return forward(x, eps, S, cc, st);
+  if (!graph_replay_ || !loop_graphs_env() || cc.probs_cb || cc.editor_cb) return forward(x, eps, S, cc, st);
   // identity of the launch: every pointer / flag the kernels' parameters are derived from, packed without struct padding
   std::vector<uint8_t> key;
   {

@@ -76,6 +76,11 @@ struct Op {
 // [(S*heads)][n_query][n_key] (device memory, edited in place on the call's stream).  place: 0 down, 1 mid, 2 up.  Non-zero = abort.
 typedef int (*AttnProbsFn)(void* user, int tf_index, int is_cross, int place, float* probs, int batch_heads, int n_query, int n_key);
 
+// Editor form of the hook (MasaCtrl's protocol): q [(S*heads)][n_query][d], k / v [(S*heads)][n_key][d], sim = scaled scores and
+// attn = softmax(sim), both [(S*heads)][n_query][n_key]; the hook writes the layer output [S][n_query][heads*d] into `out`.
+typedef int (*AttnEditorFn)(void* user, int tf_index, int is_cross, int place, float* q, float* k, float* v, float* sim, float* attn,
+                            float* out, int batch_heads, int n_query, int n_key, int d);
+
 // Per-call attention control (device arrays prepared by the edit loop).
 struct CallCtrl {
   const int* ctx_idx = nullptr;        // [S] index into the text K/V cache
@@ -93,6 +98,7 @@ struct CallCtrl {
   float* blend_acc = nullptr; const float* blend_alpha = nullptr;
   // compat path (compat_attn.cuh): materialised probabilities + host callback instead of the fused attention kernels
   AttnProbsFn probs_cb = nullptr; void* probs_user = nullptr;
+  AttnEditorFn editor_cb = nullptr; void* editor_user = nullptr;
 };
 
 struct Plan {
@@ -164,6 +170,7 @@ class Engine {
   std::vector<TfW> tfs_;        // in forward order (== controller layer order / 2)
   std::vector<int> tf_tokens_, tf_place_;
   float* compat_probs_ = nullptr; size_t compat_probs_bytes_ = 0;
+  float* compat_aux_ = nullptr; size_t compat_aux_bytes_ = 0;        // editor form: sim | q | k | v | out
   long compat_attention(const Op& op, bool is_cross, int S, const CallCtrl& cc, cudaStream_t st);
   std::vector<bf16*> down_w_, up_w_, up_wp_;
   std::vector<float*> down_b_, up_b_;

@@ -190,6 +190,46 @@ class UNetEngine:
         self.last_stats = {"kernel_launches": launches, "sample_forwards": S}
         return eps
 
+    def forward_editor(self, x: torch.Tensor, timesteps, ctx: torch.Tensor, editor_hook) -> torch.Tensor:
+        """eps = unet(x, t, ctx) with `editor_hook(tf_index, is_cross, place, q, k, v, sim, attn, heads) -> out` called for every attention
+        layer (MasaCtrl's editor protocol, masactrl/masactrl_utils.py:40-89): q/k/v (S*heads, n, d), sim/attn (S*heads, n, m) fp32 CUDA
+        views; the returned (S, n, heads*d) tensor becomes the layer's attention output."""
+        dev = torch.device("cuda", self.device)
+        x = x.to(dev, torch.float32).contiguous()
+        S = x.shape[0]
+        assert S <= self.max_samples and ctx.shape[0] == S and S <= self.max_contexts
+        ts = np.ascontiguousarray(np.broadcast_to(np.asarray(timesteps, dtype=np.float32).reshape(-1), (S,)))
+        ctx = ctx.to(dev, torch.float32).contiguous()
+        eps = torch.empty_like(x)
+        heads = self.config["heads"]
+        failure = []
+
+        class _View:
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+        def view(ptr, *shape):
+            return torch.as_tensor(_View(ptr, shape), device=dev)
+
+        def _cb(_user, tf_index, is_cross, place, q, k, v, sim, attn, out, bh, nq, nk, d):
+            try:
+                with torch.cuda.device(dev):
+                    res = editor_hook(tf_index, bool(is_cross), place, view(q, bh, nq, d), view(k, bh, nk, d), view(v, bh, nk, d),
+                                      view(sim, bh, nq, nk), view(attn, bh, nq, nk), heads)
+                    view(out, bh // heads, nq, heads * d).copy_(res)
+                return 0
+            except BaseException as ex:   # noqa: BLE001 -- re-raised below
+                failure.append(ex)
+                return 1
+
+        cb = _lib.ATTN_EDITOR_FN(_cb)
+        rc = self.lib.hedit_unet_forward_editor(self.handle, x.data_ptr(), ts.ctypes.data, ctx.data_ptr(), S, eps.data_ptr(), cb, None, self._stream())
+        if failure:
+            raise failure[0]
+        launches = _lib.check(rc, "unet forward (editor)")
+        self.last_stats = {"kernel_launches": launches, "sample_forwards": S}
+        return eps
+
     # ---- the bridge-sampling loop
     def edit(self, xT: torch.Tensor, zs: torch.Tensor, ctx: torch.Tensor, timesteps: Sequence[int], coef: np.ndarray,
              cfg_scales: Sequence[float], plan: Optional[EditPlan], weight_reconstruction: float = 0.1, optimization_steps: int = 1,

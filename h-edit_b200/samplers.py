@@ -155,6 +155,12 @@ def h_Edit_masactrl_implicit(model, xT, eta=1.0, prompts="", cfg_scales=None, pr
     """Reference signature (masactrl_h_edit.py:14)."""
     ed = getattr(model, "_hedit_masactrl_editor", None)
     assert ed is not None, "call regiter_attention_editor_diffusers(model, MutualSelfAttentionControl(...)) first"
+    if type(ed).__name__ != "MutualSelfAttentionControl":
+        # an editor object of the user's own class only promises the call protocol: compat path (materialised q, k, v, sim, attn)
+        from .compat import h_edit_masactrl_implicit_compat
+        edited, recon = h_edit_masactrl_implicit_compat(model, xT, eta, prompts, cfg_scales, zs, ed, optimization_steps, after_skip_steps,
+                                                        is_ddim_inversion)
+        return edited.to(xT.device), recon.to(xT.device)
     out = _single(model, xT, eta, prompts, cfg_scales, zs, None, 0.0, optimization_steps, after_skip_steps, is_ddim_inversion, False,
                   masactrl=(ed.start_step - ed.cur_step, ed.start_layer), mos_pull=False)
     ed.cur_step += after_skip_steps * optimization_steps

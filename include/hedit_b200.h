@@ -161,6 +161,16 @@ typedef int (*hedit_attn_probs_fn)(void* user, int tf_index, int is_cross, int p
 int hedit_unet_forward_compat(hedit_engine* e, const float* x, const float* timesteps, const float* ctx, int S, float* eps,
                               hedit_attn_probs_fn probs_hook, void* user, void* stream);
 
+/* The same for MasaCtrl's EDITOR protocol (text-guided/masactrl/masactrl_utils.py:40-89: `out = editor(q, k, v, sim, attn, is_cross,
+ * place_in_unet, self.heads, scale=self.scale)` replaces `attn @ v`): per attention layer the hook receives, as fp32 device buffers,
+ * q [(S*heads)][n_query][d], k and v [(S*heads)][n_key][d] (the 'b n (h d) -> (b h) n d' split), sim = q k^T * d^-1/2 and attn =
+ * softmax(sim), both [(S*heads)][n_query][n_key], and must write the layer output [S][n_query][heads*d] ('(b h) n d -> b n (h d)') into
+ * `out` with work queued on `stream`.  Serves editor objects that are not the stock MutualSelfAttentionControl. */
+typedef int (*hedit_attn_editor_fn)(void* user, int tf_index, int is_cross, int place, float* q, float* k, float* v, float* sim, float* attn,
+                                    float* out, int batch_heads, int n_query, int n_key, int d);
+int hedit_unet_forward_editor(hedit_engine* e, const float* x, const float* timesteps, const float* ctx, int S, float* eps,
+                              hedit_attn_editor_fn editor_hook, void* user, void* stream);
+
 /* the whole bridge-sampling loop for a batch of images */
 int hedit_edit_p2p(hedit_engine* e, hedit_edit_args* args, void* stream);
 

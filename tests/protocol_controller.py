@@ -97,3 +97,47 @@ class UserController:
                 v[1:] = base.unsqueeze(0).expand(tar.shape[0], *base.shape)
         if store_after:
             self.step_store[f"{place}_{'cross' if is_cross else 'self'}"].append(attn.clone())
+
+
+class UserMutualSelfAttention:
+    """A USER-SIDE MasaCtrl editor that relies on nothing but the editor call protocol (text-guided/masactrl/masactrl_utils.py:15-23, 72-75):
+    `out = editor(q, k, v, sim, attn, is_cross, place_in_unet, num_heads, scale=...)` with q/k/v (b*h, n, d), returning (b, n, h*d), and
+    counting layers itself.  From `start_step` on and in transformer blocks >= `start_layer`, both samples of the unconditional pair and
+    of the conditional pair attend to the keys / values of the FIRST sample of their pair (masactrl/masactrl.py:38-64).  Its class name
+    is its own, so the sampler must serve it through the compat path."""
+
+    def __init__(self, start_step, start_layer):
+        self.start_step, self.start_layer = start_step, start_layer
+        self.cur_step = 0
+        self.cur_att_layer = 0
+        self.num_att_layers = -1
+        self.calls = 0
+        self.controlled = 0
+
+    def __call__(self, q, k, v, sim, attn, is_cross, place_in_unet, num_heads, **kwargs):
+        self.calls += 1
+        out = self._forward(q, k, v, attn, is_cross, num_heads, kwargs.get("scale"))
+        self.cur_att_layer += 1
+        if self.cur_att_layer == self.num_att_layers:
+            self.cur_att_layer = 0
+            self.cur_step += 1
+        return out
+
+    @staticmethod
+    def _merge(x, heads):                        # (b*h, n, d) -> (b, n, h*d)
+        bh, n, d = x.shape
+        return x.view(bh // heads, heads, n, d).permute(0, 2, 1, 3).reshape(bh // heads, n, heads * d)
+
+    def _forward(self, q, k, v, attn, is_cross, heads, scale):
+        if is_cross or self.cur_step < self.start_step or self.cur_att_layer // 2 < self.start_layer:
+            return self._merge(torch.bmm(attn, v), heads)
+        self.controlled += 1
+        outs = []
+        for qp, kp, vp in zip(q.chunk(2), k.chunk(2), v.chunk(2)):          # unconditional pair, conditional pair
+            n, d = qp.shape[1], qp.shape[2]
+            qq = qp.view(-1, heads, n, d)
+            k1, v1 = kp[:heads], vp[:heads]                                  # the pair's first (source) sample
+            p = torch.softmax(torch.einsum("bhid,hjd->bhij", qq, k1) * scale, dim=-1)
+            o = torch.einsum("bhij,hjd->bhid", p, v1)
+            outs.append(o.permute(0, 2, 1, 3).reshape(qq.shape[0], n, heads * d))
+        return torch.cat(outs, dim=0)

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from oracle.pipeline import OraclePipeline  # noqa: E402
 from oracle_run import cfg_from_meta, load_golden  # noqa: E402
-from protocol_controller import UserController  # noqa: E402
+from protocol_controller import UserController, UserMutualSelfAttention  # noqa: E402
 
 import hedit_b200  # noqa: E402
 from gpu_util import rel_err  # noqa: E402
@@ -87,3 +87,32 @@ def test_custom_controller_through_sampler_matches_reference_golden(name):
     assert ctrl.cur_step == meta["T"] and ctrl.cur_att_layer == 0
     assert ctrl.calls == 32 * meta["T"] * meta["K"]
     assert len(ctrl.attention_store["down_cross"]) == 4 and len(ctrl.attention_store["up_cross"]) == 6
+
+
+def test_custom_editor_through_masactrl_sampler_matches_reference_golden():
+    """MasaCtrl's editor protocol on the compat path: a user-side editor (own class) registered with the reference's hook name and driven
+    through `h_Edit_masactrl_implicit` must reproduce the golden of the unmodified reference sampler + reference editor."""
+    g = load_golden("tiny_masactrl_mos2")
+    meta = g["meta"]
+    model = _model(meta)
+    T, K = meta["T"], meta["K"]
+    editor = UserMutualSelfAttention(meta["masa_start_step"], meta["masa_start_layer"])
+    hedit_b200.regiter_attention_editor_diffusers(model, editor)
+    ed, rc = hedit_b200.h_Edit_masactrl_implicit(model, g["xT"].cuda(), eta=meta["eta"], prompts=meta["prompts"], cfg_scales=meta["cfg_scales"],
+                                                 zs=g["zs"].cuda(), optimization_steps=K, after_skip_steps=T, is_ddim_inversion=False)
+    r_ed, m_ed = rel_err(ed.cpu(), g["edited"])
+    r_rc, m_rc = rel_err(rc.cpu(), g["recon"])
+    print(f"tiny_masactrl_mos2 via the editor compat path: edited rel {r_ed:.3e} max {m_ed:.3e} | recon rel {r_rc:.3e} | calls {editor.calls}, "
+          f"controlled {editor.controlled}, cur_step {editor.cur_step}")
+    assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
+    assert editor.calls == 32 * T * K and editor.cur_step == T * K and editor.cur_att_layer == 0
+    assert editor.controlled == (T * K - meta["masa_start_step"]) * (16 - meta["masa_start_layer"])
+
+    # the plain editor protocol (attn @ v) must reproduce the fused forward
+    eng = hedit_b200.get_engine(model, max_samples=5)
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 4, 64, 64, generator=gen).cuda()
+    ctx = torch.cat([g["ctx_src"], g["ctx_tar"]]).cuda()
+    plain = lambda layer, is_cross, place, q, k, v, sim, attn, heads: UserMutualSelfAttention._merge(torch.bmm(torch.softmax(sim, -1), v), heads)
+    r, _ = rel_err(eng.forward_editor(x, 301.0, ctx, plain), eng.forward(x, 301.0, ctx))
+    assert r < 3e-3, r

@@ -217,3 +217,47 @@ def test_compat_loop_and_protocol_controller_match_reference_sampler(is_replace,
         assert len(items) == len(user.attention_store[key])
         for a, b in zip(items, user.attention_store[key]):
             assert torch.allclose(a, b, atol=1e-5)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_compat_masactrl_loop_and_protocol_editor_match_reference_sampler():
+    """Editor form of the compat sampler (hedit_b200/compat.py, editor_mode) and the user-side editor of the GPU tests, on CPU on the
+    oracle UNet patched by the REFERENCE's `regiter_attention_editor_diffusers`, against the unmodified reference MasaCtrl sampler driving
+    the reference's own MutualSelfAttentionControl."""
+    import importlib
+    import sys
+    from hedit_b200.compat import h_edit_masactrl_implicit_compat
+    from oracle.sd_unet import UNetConfig
+    from protocol_controller import UserMutualSelfAttention
+    load_reference()
+    masa_pkg = importlib.import_module("masactrl")
+    sys.modules.setdefault("masa_ctrl", masa_pkg)                       # reference typo: masactrl.py imports `masa_ctrl`
+    mu = importlib.import_module("masactrl.masactrl_utils")
+    sys.modules.setdefault("masa_ctrl.masactrl_utils", mu)
+    masa = importlib.import_module("masactrl.masactrl")
+    mh = importlib.import_module("inversion.masactrl_h_edit")
+    T, K, start_step, start_layer = 3, 2, 1, 10
+    cfg = UNetConfig.tiny(sample_size=16)
+    model = OraclePipeline(cfg, seed=0)
+    model.scheduler.set_timesteps(T)
+    prompts = ["", "a brown lizard is sitting on a branch"]
+    g = torch.Generator().manual_seed(7)
+    xT = torch.randn(1, cfg.in_channels, 16, 16, generator=g)
+    zs = torch.randn(T, cfg.in_channels, 16, 16, generator=g)
+    args = dict(eta=1.0, prompts=prompts, cfg_scales=[1.0, 5.0, 7.5], zs=zs, optimization_steps=K, after_skip_steps=T, is_ddim_inversion=False)
+
+    e_ref = masa.MutualSelfAttentionControl(start_step, start_layer, total_steps=T * K)
+    mu.regiter_attention_editor_diffusers(model, e_ref)
+    ed_ref, rc_ref = mh.h_Edit_masactrl_implicit(model, xT=xT, prog_bar=False, **args)
+
+    user = UserMutualSelfAttention(start_step, start_layer)
+    mu.regiter_attention_editor_diffusers(model, user)               # the reference's patched forwards now call the user object
+    assert user.num_att_layers == e_ref.num_att_layers == 32
+
+    class TorchUNet:
+        def __call__(self, sample, t, encoder_hidden_states=None, cross_attention_kwargs=None):
+            return model.unet(sample, t, encoder_hidden_states=encoder_hidden_states, cross_attention_kwargs=cross_attention_kwargs)
+
+    ed, rc = h_edit_masactrl_implicit_compat(model, xT, editor=user, unet=TorchUNet(), **args)
+    assert (ed - ed_ref).abs().max().item() < 2e-5 and (rc - rc_ref).abs().max().item() < 2e-5
+    assert user.cur_step == e_ref.cur_step == T * K and user.controlled == (T * K - start_step) * (16 - start_layer)
