@@ -206,3 +206,56 @@ def test_face_step_tables_follow_the_reference_formulas():
         c2 = (1 - ab[tm1]).sqrt() * ((1 - 0.25) ** 0.5)
         want = [t, tm1, (1 - ab[t]) ** 0.5, ab[t] ** 0.5, (1 - ab[tm1]) ** 0.5, ab[tm1].sqrt(), c2, 1.0 * c1]
         assert np.allclose(tab[i], np.asarray([float(v) for v in want], dtype=np.float32), rtol=1e-6, atol=0)
+
+
+def test_compat_unet_routes_cross_attention_kwargs_like_the_reference_processors():
+    """`CompatUNet` must honour the reference's kwargs: P2P processors run the controller unless `use_controller` is False and pass
+    `save_attn` through (p2p/ptp_utils.py:38-46, 102-104); MasaCtrl's patched forward calls the editor unless `use_editor` is False
+    (masactrl/masactrl_utils.py:40, 72-78).  Checked on a stand-in engine that records which native entry point would run."""
+    from hedit_b200.compat import CompatUNet, PLACES
+
+    class FakeEngine:
+        config = {"in_channels": 4, "sample_size": 64}
+
+        def __init__(self):
+            self.log = []
+
+        def forward(self, x, t, ctx):
+            self.log.append(("fused", t))
+            return x
+
+        def forward_compat(self, x, t, ctx, hook):
+            self.log.append(("probs", t))
+            hook(3, True, 2, torch.zeros(16, 4, 77))
+            return x
+
+        def forward_editor(self, x, t, ctx, hook):
+            self.log.append(("editor", t))
+            out = hook(0, False, 0, torch.zeros(16, 4, 8), torch.zeros(16, 4, 8), torch.zeros(16, 4, 8), torch.zeros(16, 4, 4), torch.zeros(16, 4, 4), 8)
+            assert out.shape == (2, 4, 64)
+            return x
+
+    calls = []
+    ctrl = lambda probs, is_cross, place, save_attn: calls.append((tuple(probs.shape), is_cross, place, save_attn))
+    x, ctx = torch.zeros(2, 4, 64, 64), torch.zeros(2, 77, 8)
+    eng = FakeEngine()
+    unet = CompatUNet(eng, controller=ctrl)
+    assert unet(x, torch.tensor(481), encoder_hidden_states=ctx, cross_attention_kwargs={"use_controller": False}).sample is x
+    unet(x, 461, encoder_hidden_states=ctx, cross_attention_kwargs={"save_attn": False})
+    unet(x, 441, encoder_hidden_states=ctx)
+    assert [k for k, _ in eng.log] == ["fused", "probs", "probs"]
+    assert calls == [((16, 4, 77), True, PLACES[2], False), ((16, 4, 77), True, "up", True)]
+    assert CompatUNet(FakeEngine(), controller=None)(x, 1, encoder_hidden_states=ctx).sample is x
+
+    seen = []
+
+    def editor(q, k, v, sim, attn, is_cross, place, heads, scale=None):
+        seen.append((is_cross, place, heads, scale))
+        return torch.zeros(q.shape[0] // heads, q.shape[1], heads * q.shape[2])
+
+    eng2 = FakeEngine()
+    unet2 = CompatUNet(eng2, editor=editor)
+    unet2(x, 481, encoder_hidden_states=ctx, cross_attention_kwargs={"use_editor": False})
+    unet2(x, 461, encoder_hidden_states=ctx)
+    assert [k for k, _ in eng2.log] == ["fused", "editor"]
+    assert seen == [(False, "down", 8, 8 ** -0.5)]

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round deliverables v7
+# Round deliverables: GPU tests, smoke, default bench (+ per-op profile), ncu launch list, ncu --set full of the conv and attention kernels
 mkdir -p gpurun_out
 nvidia-smi > gpurun_out/nvidia_smi.txt 2>&1
 timeout 1200 python -m pytest tests -m gpu -q --tb=short > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
