@@ -1,6 +1,6 @@
 """ctypes binding of libhedit_b200.so (C ABI declared in include/hedit_b200.h).
 
-There is NO CPU fallback: if the shared library (built by `__graft_entry__.build()` / `make -C h-edit_b200/csrc`)
+There is NO CPU fallback: if the shared library (built by `__graft_entry__.build()` / `make -C hedit_b200/csrc`)
 is missing, or no sm_100a device is visible when an engine is created, this raises."""
 from __future__ import annotations
 
@@ -71,7 +71,7 @@ class EditArgsC(C.Structure):
         ("mapper", C.c_void_p), ("is_replace", C.c_void_p), ("replace_m", C.c_void_p), ("c_base", C.c_void_p), ("c_tar", C.c_void_p),
         ("self_lo", C.c_int32), ("self_hi", C.c_int32), ("self_max_tokens", C.c_int32),
         ("has_blend", C.c_void_p), ("blend_alpha", C.c_void_p), ("start_blend", C.c_int32), ("blend_th", C.c_float),
-        ("masa_start_step", C.c_int32), ("masa_start_layer", C.c_int32), ("mos_pull", C.c_int32),
+        ("masa", C.c_int32), ("masa_layer_mask", C.c_uint32), ("masa_step_on", C.c_void_p), ("mos_pull", C.c_int32),
         ("pnp", C.c_int32), ("pnp_self_mask", C.c_uint32), ("pnp_qk_on", C.c_void_p), ("pnp_feat_on", C.c_void_p),
         ("pre_step", C.c_int32), ("pre_coeff", C.c_float),
         ("guidance", C.c_void_p), ("guidance_user", C.c_void_p), ("guidance_weight", C.c_float), ("x0_coef", C.c_void_p),
@@ -158,7 +158,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"hedit_b200: native library not found at {LIB_PATH}. Build it with `python -c 'import __graft_entry__ as g; "
-            "g.build()'` or `make -C h-edit_b200/csrc`. There is no CPU fallback.")
+            "g.build()'` or `make -C hedit_b200/csrc`. There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)

@@ -90,7 +90,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   const UNetCfg& c = E.cfg();
   const int B = a.B, T = a.steps, K = a.explicit_form ? 1 : std::max(1, a.opt_steps);
   const int n = E.latent_elems();
-  const bool masa = a.masa_start_layer >= 0;
+  const bool masa = a.masa != 0;
   const bool p2p = a.use_p2p != 0 && a.variant == 0 && !masa;
   const bool pnp = a.pnp != 0;
   const bool ctrl = p2p || masa || pnp;   // launches C / BC / E run with attention control
@@ -102,6 +102,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     E.err_ = "Plug-and-Play runs the implicit form only (pnp_h_edit.py:33), without P2P / MasaCtrl, and needs both per-step flag arrays";
     return -1;
   }
+  if (masa && !a.masa_step_on) { E.err_ = "masa needs masa_step_on[steps * opt_steps]"; return -1; }
   if (a.guidance && (a.explicit_form || !a.x0_coef || !a.guid_x0 || !a.guid_grad)) {
     E.err_ = "reward guidance runs in the implicit form and needs x0_coef, guid_x0 and guid_grad";
     return -1;
@@ -347,10 +348,8 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     } else if (cd.p2p && pnp) {
       if (a.pnp_qk_on[ctrl_step]) { cc.self_mask = a.pnp_self_mask; cc.self_q = cd.d_sq; cc.self_k = cd.d_sq; cc.self_v = nullptr; }
       if (a.pnp_feat_on[ctrl_step]) cc.feat_src = cd.d_sq;
-    } else if (cd.p2p && masa && a.ctrl_step0 + masa_step >= a.masa_start_step) {
-      uint32_t m = 0;
-      for (int l = std::max(0, a.masa_start_layer); l < E.n_tf(); ++l) m |= 1u << l;
-      cc.self_mask = m; cc.self_q = nullptr; cc.self_k = cd.d_sk; cc.self_v = cd.d_sk;
+    } else if (cd.p2p && masa && a.masa_step_on[masa_step]) {
+      cc.self_mask = a.masa_layer_mask; cc.self_q = nullptr; cc.self_k = cd.d_sk; cc.self_v = cd.d_sk;
     }
     const long r = E.forward_replayed(L.xin, L.eps + size_t(cd.pool_off) * n, cd.S, cc, st);
     if (r < 0) return -1;

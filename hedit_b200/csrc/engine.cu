@@ -427,6 +427,30 @@ static cudaError_t launch_self2_t(const AttnParams& a, int S, cudaStream_t st) {
   self_attn2_kernel<DCH, NT, BKV, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
+template <int DCH, bool MMASUM, bool TWOPASS, int POLY16>
+static cudaError_t launch_self3_t(const AttnParams& a, int S, cudaStream_t st) {
+  using Cfg = SelfAttn2Cfg<DCH, 2, 64>;
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(self_attn3_kernel<DCH, MMASUM, TWOPASS, POLY16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
+  dim3 grid((a.Nq + 255) / 256, a.H, S);
+  self_attn3_kernel<DCH, MMASUM, TWOPASS, POLY16><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  return cudaGetLastError();
+}
+// tuning switch HEDIT_ATTN_V3 (self_attn3_kernel variants, head dims <= 128): 0 = round-1 kernel (self_attn2_kernel);
+//   1 = tensor-core row sum; 2 = + two-pass TMEM read; 3/4/5 = + 2/3/4 of every 8 exponential pairs on the FMA pipe
+static int attn_v3() { static const int v = getenv("HEDIT_ATTN_V3") ? atoi(getenv("HEDIT_ATTN_V3")) : 0; return v; }
+template <int DCH>
+static cudaError_t launch_self3(const AttnParams& a, int S, cudaStream_t st) {
+  switch (attn_v3()) {
+    case 1: return launch_self3_t<DCH, true, false, 0>(a, S, st);
+    case 2: return launch_self3_t<DCH, true, true, 0>(a, S, st);
+    case 3: return launch_self3_t<DCH, true, true, 2>(a, S, st);
+    case 4: return launch_self3_t<DCH, true, true, 3>(a, S, st);
+    case 5: return launch_self3_t<DCH, true, true, 4>(a, S, st);
+    case 6: return launch_self3_t<DCH, false, true, 3>(a, S, st);       // control: packed-add row sum kept
+    default: return launch_self3_t<DCH, true, false, 2>(a, S, st);      // 7: no two-pass, polynomial share (register-pressure control)
+  }
+}
 // tuning switch HEDIT_ATTN_POLY: how many of every 8 softmax exponentials run on the FMA pipe instead of the MUFU (0, 2 or 4)
 static int attn_poly() { static const int v = getenv("HEDIT_ATTN_POLY") ? atoi(getenv("HEDIT_ATTN_POLY")) : 0; return v; }
 // tuning switch HEDIT_ATTN_CFG for head dims <= 64 (measured on B200, N=4096, d=40, cycles per 128x128 block):
@@ -435,6 +459,8 @@ static int attn_poly() { static const int v = getenv("HEDIT_ATTN_POLY") ? atoi(g
 static int attn_cfg() { static const int v = getenv("HEDIT_ATTN_CFG") ? atoi(getenv("HEDIT_ATTN_CFG")) : 1; return v; }
 cudaError_t launch_self_attn(const AttnParams& a, int dch, int S, cudaStream_t st) {
   const int bkv2 = (dch == 1 && attn_cfg() == 0) ? 128 : 64;
+  if (a.Nq >= 256 && a.Nkv % 64 == 0 && attn_v3() > 0 && dch <= 2 && ((a.d + 15) & ~15) + 16 <= dch * 64)
+    return dch == 1 ? launch_self3<1>(a, S, st) : launch_self3<2>(a, S, st);
   if (a.Nq >= 256 && a.Nkv % bkv2 == 0) {      // several query tiles per CTA
     if (dch == 1) {
       if (attn_cfg() == 1) {

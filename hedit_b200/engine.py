@@ -236,7 +236,8 @@ class UNetEngine:
              explicit_form: bool = False, schedule: int = 1, trace: bool = False, variant: int = 0, masactrl=None, mos_pull: bool = True,
              xt_is_pair: bool = False, ctrl_step0: int = 0, blend_state: Optional[torch.Tensor] = None, pnp=None, pre_coeff=None, guidance=None):
         """xT (B,C,h,w), zs (B,steps,C,h,w), ctx (1+2B,77,D): all on the SAME side (all host or all on this device).
-        variant 1 = h_Edit_R_* (no attention control); masactrl = (start_step, start_layer) enables mutual self-attention;
+        variant 1 = h_Edit_R_* (no attention control); masactrl = (layer_mask, step_on[steps*K]) enables mutual self-attention in the
+        transformer blocks of layer_mask during the controlled launches flagged in step_on;
         pnp = (self_mask, qk_on[steps], feat_on[steps]) runs h_Edit_PnP_implicit (Plug-and-Play q/k and feature injection);
         guidance = (fn, weight, x0_coef[steps,2]) adds the reward-guided Langevin move: fn(x0 (B,C,h,w) cuda tensor) -> dLoss/dx0.
         Returns (edited, recon[, trace]) on that side."""
@@ -261,10 +262,16 @@ class UNetEngine:
         a.weight_reconstruction = float(weight_reconstruction)
         a.variant = int(variant)
         a.mos_pull = int(mos_pull)
-        a.masa_start_step, a.masa_start_layer = (int(masactrl[0]), int(masactrl[1])) if masactrl is not None else (0, -1)
+        keep = []
+        if masactrl is not None:
+            n_ctrl = steps * (1 if explicit_form else max(1, optimization_steps))
+            step_on = np.ascontiguousarray(np.asarray(masactrl[1], dtype=np.int32))
+            assert step_on.shape == (n_ctrl,), f"masactrl step flags must cover the {n_ctrl} controlled launches"
+            keep.append(step_on)
+            a.masa, a.masa_layer_mask, a.masa_step_on = 1, int(masactrl[0]), step_on.ctypes.data
         a.xt_is_pair, a.ctrl_step0 = int(xt_is_pair), int(ctrl_step0)
         a.blend_state = blend_state.data_ptr() if blend_state is not None else None
-        keep = [ts, coef, xT, zs, ctx]
+        keep += [ts, coef, xT, zs, ctx]
         cb_error = []
         if guidance is not None:
             fn, weight, x0_coef = guidance

@@ -131,16 +131,34 @@ def h_Edit_R_explicit(model, xT, eta=1.0, prompts="", cfg_scales=None, prog_bar=
 
 
 class MutualSelfAttentionControl:
-    """Holds MasaCtrl's schedule (masactrl/masactrl.py:11-36): mutual self-attention from `start_step` on, in transformer
-    blocks >= `start_layer` (of 16).  The control itself runs inside self_attn_kernel as a K/V source-sample swap."""
+    """MasaCtrl's schedule (masactrl/masactrl.py:11-36): mutual self-attention at the editor steps of `step_idx` (default
+    range(start_step, total_steps): the injection ENDS once cur_step reaches total_steps) in the transformer blocks of `layer_idx`
+    (default range(start_layer, 16)).  The control itself runs inside the self-attention kernel as a K/V source-sample swap; the
+    editor's cur_step advances once per attention-controlled UNet launch (masactrl_utils.py:15-23)."""
+    MODEL_TYPE = {"SD": 16, "SDXL": 70}
 
     def __init__(self, start_step=4, start_layer=10, layer_idx=None, step_idx=None, total_steps=50, model_type="SD"):
-        if layer_idx is not None or step_idx is not None:
-            raise NotImplementedError("explicit layer_idx / step_idx lists are not supported on the fused path")
-        self.start_step, self.start_layer, self.total_steps = start_step, start_layer, total_steps
+        self.total_steps = total_steps
+        self.total_layers = self.MODEL_TYPE.get(model_type, 16)
+        self.start_step, self.start_layer = start_step, start_layer
+        self.layer_idx = list(layer_idx) if layer_idx is not None else list(range(start_layer, self.total_layers))
+        self.step_idx = list(step_idx) if step_idx is not None else list(range(start_step, total_steps))
         self.cur_step = 0
         self.cur_att_layer = 0
         self.num_att_layers = -1
+
+    def reset(self):
+        self.cur_step = 0
+        self.cur_att_layer = 0
+
+    def launch_plan(self, n_launches: int, n_blocks: int = 16):
+        """(layer bit mask, per-launch on/off flags) for the next `n_launches` attention-controlled UNet launches."""
+        mask = 0
+        for l in self.layer_idx:
+            if 0 <= int(l) < min(n_blocks, 32):
+                mask |= 1 << int(l)
+        steps = set(int(v) for v in self.step_idx)
+        return mask, [int(self.cur_step + c in steps) for c in range(n_launches)]
 
 
 def regiter_attention_editor_diffusers(model, editor) -> None:
@@ -161,9 +179,10 @@ def h_Edit_masactrl_implicit(model, xT, eta=1.0, prompts="", cfg_scales=None, pr
         edited, recon = h_edit_masactrl_implicit_compat(model, xT, eta, prompts, cfg_scales, zs, ed, optimization_steps, after_skip_steps,
                                                         is_ddim_inversion)
         return edited.to(xT.device), recon.to(xT.device)
+    n_launches = after_skip_steps * max(1, optimization_steps)
     out = _single(model, xT, eta, prompts, cfg_scales, zs, None, 0.0, optimization_steps, after_skip_steps, is_ddim_inversion, False,
-                  masactrl=(ed.start_step - ed.cur_step, ed.start_layer), mos_pull=False)
-    ed.cur_step += after_skip_steps * optimization_steps
+                  masactrl=ed.launch_plan(n_launches, get_engine(model).n_transformer_blocks()), mos_pull=False)
+    ed.cur_step += n_launches
     return out
 
 
@@ -175,7 +194,7 @@ def h_Edit_masactrl_explicit(model, xT, eta=1.0, prompts="", cfg_scales=None, pr
     ed = getattr(model, "_hedit_masactrl_editor", None)
     assert ed is not None, "call regiter_attention_editor_diffusers(model, MutualSelfAttentionControl(...)) first"
     out = _single(model, xT, eta, prompts, cfg_scales, zs, None, 0.0, 1, after_skip_steps, is_ddim_inversion, True,
-                  masactrl=(ed.start_step - ed.cur_step, ed.start_layer), mos_pull=False)
+                  masactrl=ed.launch_plan(after_skip_steps, get_engine(model).n_transformer_blocks()), mos_pull=False)
     ed.cur_step += after_skip_steps
     return out
 

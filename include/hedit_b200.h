@@ -75,9 +75,14 @@ typedef struct hedit_edit_args {
   const float* blend_alpha;  /* [B][2][80]  LocalBlend.alpha_layers */
   int32_t start_blend;       /* LocalBlend.start_blend */
   float blend_th;            /* LocalBlend.th */
-  /* ---- MasaCtrl mutual self-attention (masactrl/masactrl.py:53-69): from controller step >= masa_start_step, in transformer
-   * blocks >= masa_start_layer, the edit samples attend to the K/V of their source samples.  masa_start_layer < 0: off */
-  int32_t masa_start_step, masa_start_layer;
+  /* ---- MasaCtrl mutual self-attention (masactrl/masactrl.py:11-69).  masa = 1: in the c-th attention-controlled UNet launch of this
+   * call (the editor's cur_step advances once per controlled launch, masactrl_utils.py:15-23, i.e. steps * opt_steps launches in the
+   * implicit form) the edit samples attend to the K/V of their source samples in the transformer blocks of masa_layer_mask
+   * (bit l = block l in forward order = the editor's layer_idx) iff masa_step_on[c] != 0 (= `cur_step in step_idx`, which also ends
+   * the injection once cur_step reaches total_steps).  masa = 0: off */
+  int32_t masa;
+  uint32_t masa_layer_mask;
+  const int32_t* masa_step_on;   /* host [steps * opt_steps] */
   int32_t mos_pull;          /* 1: apply the L1 reconstruction pull on MOS iterations k>0 (p2p_h_edit.py:670-686); 0: masactrl_h_edit.py */
   /* ---- Plug-and-Play (text-guided/plug_n_play/pnp_utils.py:29-164 driven by inversion/pnp_h_edit.py:33): pnp = 1 runs
    * h_Edit_PnP_implicit.  The attention-controlled call of a step is the pair ([x_orig,src],[x_opt,tar]) at the previous timestep tt;

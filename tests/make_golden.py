@@ -36,6 +36,19 @@ VARIANTS = {
     "tiny_R_implicit_skip2": (UNetConfig.tiny(sample_size=64), 6, 1, "R_implicit_skip"),
     "tiny_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "pnp"),
     "small32_pnp_mos2": (UNetConfig.tiny(sample_size=32), 4, 2, "pnp"),
+    # editor built with total_steps = T while K = 2: the reference's step_idx = range(start, total_steps) ENDS the injection after
+    # editor step 5 of 10 (masactrl.py:36,58)
+    "tiny_masactrl_mos2_stop": (UNetConfig.tiny(sample_size=64), 5, 2, "masactrl"),
+    # explicit layer_idx / step_idx lists (masactrl.py:33-36)
+    "tiny_masactrl_lists": (UNetConfig.tiny(sample_size=64), 6, 1, "masactrl"),
+    # BASELINE.json configs[2] at full SD-1.5 geometry: implicit h-Edit + MasaCtrl (the sampler the reference ships), T = 50
+    "sd15_config3_T50_masactrl": (UNetConfig.sd15(), 50, 1, "masactrl"),
+}
+# MutualSelfAttentionControl arguments per masactrl variant (default: start_step 2, start_layer 10, total_steps T*K)
+MASA_ARGS = {
+    "tiny_masactrl_mos2_stop": dict(start_step=2, start_layer=10, total_steps=5),
+    "tiny_masactrl_lists": dict(start_step=0, start_layer=0, layer_idx=[3, 8, 9, 12, 15], step_idx=[1, 2, 4]),
+    "sd15_config3_T50_masactrl": dict(start_step=4, start_layer=10, total_steps=50),
 }
 
 CASES = {
@@ -44,19 +57,33 @@ CASES = {
     "tiny_replace_mos2": (UNetConfig.tiny(sample_size=64), 6, 2, True, True),
     "tiny_refine_noblend": (UNetConfig.tiny(sample_size=64), 6, 1, False, False),
     "sd15_config1": (UNetConfig.sd15(), 10, 1, False, True),
+    # BASELINE.json configs[1] (the headline): full SD-1.5 geometry, T = 50; two images with different prompts / controllers / noise
+    # (Refine + Reweight + LocalBlend, and Replace + Reweight + LocalBlend) that the GPU test runs inside ONE mixed batch of 8
+    "sd15_config2_T50_refine_blend": (UNetConfig.sd15(), 50, 1, False, True),
+    "sd15_config2_T50_replace": (UNetConfig.sd15(), 50, 1, True, True),
     # fast fixtures for the CPU (-m "not gpu") suite: 32x32 latent (LocalBlend needs 64x64, so it is off here)
     "small32_refine": (UNetConfig.tiny(sample_size=32), 4, 1, False, False),
     "small32_replace_mos2": (UNetConfig.tiny(sample_size=32), 3, 2, True, False),
 }
 
 
+# per-case overrides of (prompts, blend words, seed of w0 / inversion noise)
+CASE_INPUTS = {
+    "sd15_config2_T50_replace": (["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"], ("cat", "dog"), 1),
+}
+
+
 def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
-    torch.set_num_threads(os.cpu_count())
+    global PROMPTS, BLEND
+    torch.set_num_threads(int(os.environ.get("GOLDEN_THREADS", os.cpu_count())))
+    seed = 0
+    if name in CASE_INPUTS:
+        PROMPTS, BLEND, seed = CASE_INPUTS[name]
     model = OraclePipeline(cfg, seed=0)
     model.scheduler.set_timesteps(T)
-    g = torch.Generator(device="cpu").manual_seed(0)
+    g = torch.Generator(device="cpu").manual_seed(seed)
     w0 = torch.randn(1, cfg.in_channels, cfg.sample_size, cfg.sample_size, generator=g) * 0.18215 * 5
-    torch.manual_seed(0)    # the reference draws its inversion noise from the global RNG (ddpm_inversion.py:48)
+    torch.manual_seed(seed)    # the reference draws its inversion noise from the global RNG (ddpm_inversion.py:48)
     t0 = time.time()
     _, zs, wts, _ = ref.ddpm_inversion.inversion_forward_process_ddpm(
         model, w0, etas=1.0, prog_bar=False, prompt=PROMPTS[0], cfg_scale_src=1.0, num_inference_steps=T)
@@ -88,7 +115,7 @@ def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
                      blend_words=BLEND, cfg_scales=[1.0, 5.0, 7.5], eta=1.0, weight_reconstruction=0.1,
                      unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
                                cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
-                     weights="oracle.sd_unet.seeded_init_(seed=0)", w0="randn(seed 0)*0.18215*5",
+                     weights="oracle.sd_unet.seeded_init_(seed=0)", w0=f"randn(seed {seed})*0.18215*5", seed=seed,
                      generator="tests/make_golden.py", seconds=dict(inversion=t_inv, edit=t_edit),
                      torch=torch.__version__, threads=torch.get_num_threads()),
         "w0": w0, "zs": zs[:T].clone(), "xT": wts[T].clone(),
@@ -118,7 +145,8 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
     """Other reference samplers on the same set-up: h_Edit_p2p_explicit (p2p_h_edit.py:380), h_Edit_R_implicit/explicit (:162,:21),
     h_Edit_masactrl_implicit (masactrl_h_edit.py:14)."""
     import importlib
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(int(os.environ.get("GOLDEN_THREADS", os.cpu_count())))
+    t_start = time.time()
     model = OraclePipeline(cfg, seed=0)
     model.scheduler.set_timesteps(T)
     g = torch.Generator(device="cpu").manual_seed(0)
@@ -155,11 +183,13 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
         sys.modules.setdefault("masa_ctrl.masactrl_utils", importlib.import_module("masactrl.masactrl_utils"))
         masa = importlib.import_module("masactrl.masactrl")
         mh = importlib.import_module("inversion.masactrl_h_edit")
-        start_step, start_layer = 2, 10
-        editor = masa.MutualSelfAttentionControl(start_step, start_layer, total_steps=T * K)
+        margs = dict(MASA_ARGS.get(name, dict(start_step=2, start_layer=10, total_steps=T * K)))
+        margs.setdefault("total_steps", T * K)
+        editor = masa.MutualSelfAttentionControl(**margs)
         importlib.import_module("masactrl.masactrl_utils").regiter_attention_editor_diffusers(model, editor)
         edited, recon = mh.h_Edit_masactrl_implicit(model, optimization_steps=K, **kw)
-        meta_extra = dict(masa_start_step=start_step, masa_start_layer=start_layer)
+        meta_extra = dict(masa_start_step=margs["start_step"], masa_start_layer=margs["start_layer"], masa_total_steps=margs["total_steps"],
+                          masa_layer_idx=margs.get("layer_idx"), masa_step_idx=margs.get("step_idx"), seconds=time.time() - t_start)
     elif mode == "pnp":
         # main_plugnplay.py:186-208 (h_edit_R_pnp), with the injection fractions raised so that short schedules have both
         # injected and un-injected steps
@@ -321,7 +351,7 @@ def run_face(name="tiny_face_k2", T=5, K=2, weight=50.0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
+    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "sd15_config1", "sd15_config2", "masa", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
     args = ap.parse_args()
     if args.config == "style":
         run_style()
@@ -335,8 +365,12 @@ def main():
         out = run_ddim_inversion(ref)
         torch.save(out, os.path.join(ROOT, "tests", "golden", "tiny_ddim_inversion.pt"))
         print("tiny_ddim_inversion |zs|", out["zs"].abs().mean().item(), flush=True)
-    if args.config in ("variants", "all", "pnp"):
+    if args.config in ("variants", "all", "pnp", "masa"):
         for name, (cfg, T, K, mode) in VARIANTS.items():
+            if args.config == "masa" and (mode != "masactrl" or os.path.exists(os.path.join(ROOT, "tests", "golden", f"{name}.pt"))):
+                continue
+            if args.config in ("variants", "all") and name.startswith("sd15") and os.path.exists(os.path.join(ROOT, "tests", "golden", f"{name}.pt")):
+                continue
             if args.config == "pnp" and mode not in ("pnp", "R_implicit_skip"):
                 continue
             if args.config == "pnp" and os.path.exists(os.path.join(ROOT, "tests", "golden", f"{name}.pt")):
@@ -346,7 +380,7 @@ def main():
             torch.save(out, path)
             print(name, "->", path, "|edited| %.4f" % out["edited"].abs().mean().item(), flush=True)
     for name, (cfg, T, K, rep, blend) in CASES.items():
-        if args.config in ("variants", "inversion", "pnp") or (args.config != "all" and not name.startswith(args.config)):
+        if args.config in ("variants", "inversion", "pnp", "masa") or (args.config != "all" and not name.startswith(args.config)):
             continue
         out = run_case(ref, name, cfg, T, K, rep, blend)
         path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")

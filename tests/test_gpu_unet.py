@@ -198,7 +198,8 @@ def _run_variant(name, eng_cache={}):
         ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, 1, explicit_form=True, variant=1)
         want_fwd = 3 * T
     elif mode == "masactrl":
-        ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, K, masactrl=(meta["masa_start_step"], meta["masa_start_layer"]), mos_pull=False)
+        editor = hedit_b200.MutualSelfAttentionControl(meta["masa_start_step"], meta["masa_start_layer"], total_steps=meta.get("masa_total_steps", T * K))
+        ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, K, masactrl=editor.launch_plan(T * K, eng.n_transformer_blocks()), mos_pull=False)
         want_fwd = (2 + 5 * K) * T
     elif mode == "pnp":
         # same registration calls as main_plugnplay.py:196-197, on the schedules the golden was generated with

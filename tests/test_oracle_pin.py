@@ -21,10 +21,11 @@ PAIRS = [
 def test_oracle_matches_reference_golden(name):
     g = load_golden(name)
     ed, rc, tr, spec = run_oracle_on_golden(g)
-    # same torch build, same op order as the reference loop -> bit-exact here; allow round-off across torch builds
-    assert (ed - g["edited"]).abs().max().item() <= 1e-4
-    assert (rc - g["recon"]).abs().max().item() <= 1e-4
-    assert (tr - g["trace"]).abs().max().item() <= 1e-4
+    # same torch build, same thread count, same op order as the reference loop -> bit-exact (0.0) here; a different CPU thread count
+    # or torch build changes the fp32 summation order inside the convolutions (measured 1.2e-4 with 2 instead of 8 threads)
+    assert (ed - g["edited"]).abs().max().item() <= 5e-4
+    assert (rc - g["recon"]).abs().max().item() <= 5e-4
+    assert (tr - g["trace"]).abs().max().item() <= 5e-4
     # intrinsic known answer: the reconstruction row returns the inverted latent
     assert (rc - g["w0"]).abs().max().item() < 1e-3
     tb = g["tables"]

@@ -39,7 +39,7 @@ if a.config == 3:
     ts, coef = hedit_b200.step_tables(sched, T, 1.0, True)       # h-Edit-D: eta 0 inversion, is_ddim_inversion = True
     xT = torch.randn(B, 4, 64, 64, generator=g, device=dev); zs = torch.randn(B, T, 4, 64, 64, generator=g, device=dev) * 0.01
     ctx = torch.randn(1 + 2 * B, 77, 768, generator=g, device=dev)
-    (ed, rc), ms = timed(lambda: eng.edit(xT, zs, ctx, ts, coef, [1.0, 5.0, 7.5], None, 0.0, 1, True, 1, masactrl=(4, 10), mos_pull=False))
+    (ed, rc), ms = timed(lambda: eng.edit(xT, zs, ctx, ts, coef, [1.0, 5.0, 7.5], None, 0.0, 1, True, 1, masactrl=hedit_b200.MutualSelfAttentionControl(4, 10, total_steps=T).launch_plan(T), mos_pull=False))
     fwd = eng.last_stats["sample_forwards"]
     print(json.dumps({"workload": f"explicit h-Edit-D + MasaCtrl (step 4, layer 10), SD-1.5 512^2, {T} steps, batch {B}, 1 GPU", "images_per_s": B / (ms / 1e3),
                       "unet_sample_forwards_per_image": fwd / B, "achieved_tflops": fwd * 0.8033 / (ms / 1e3), "finite": bool(torch.isfinite(ed).all())}))
