@@ -5,9 +5,18 @@
     python bench.py --gpus 1 --steps 2 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference's CPU path (oracle port of its loop) on the host cores
+    python bench.py --config 3 --gpus 8       # the other BASELINE.json configurations (3: MasaCtrl, 4: style, 5: face), same schema
 
-A "step" = one full 50-timestep edit of one batch of 8 synthetic images per GPU (weights: seeded random init of the
-SD-1.5 UNet geometry -- no pretrained weights exist offline; latents/noise: seeded Gaussians).
+A "step" = one full 50-timestep edit of one batch of 8 synthetic images per GPU (weights: seeded random init of the SD-1.5 UNet and
+CLIP ViT-L/14 text-tower geometries -- no pretrained weights exist offline; latents / noise: seeded Gaussians; prompts: fixed pairs).
+
+Three numbers per line:
+  value  = device-resident: latents, noise maps, text embeddings and the compiled edit plan already in HBM; only the native loop is timed.
+  e2e    = what a user of the reference-shaped API gets: every step runs make_controller x 8 -> register_attention_control ->
+           hedit_b200.h_edit_p2p_batch(pipeline, xT_host, zs_host, prompt_pairs, cfg_scales, controllers, ...) with PINNED HOST latents /
+           noise in and host results out, i.e. tokeniser, native text tower, sequence aligner, edit-plan compilation, step tables, H2D,
+           the loop and D2H are all inside the timed region.
+  single_image = the drop-in single-image signature h_Edit_p2p_implicit(model, xT, ...) called once per image (B = 1 launches).
 """
 import argparse
 import json
@@ -15,7 +24,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -23,12 +31,34 @@ sys.path.insert(0, ROOT)
 
 TFLOP_PER_SAMPLE_FORWARD = 0.8033            # SD-1.x UNet, 64x64 latent, 77 ctx tokens
 GEMM_TFLOP_PER_SAMPLE_FORWARD = 2 * (200.16 + 138.42) * 1e-3      # conv3x3 + linear/1x1 GMAC of one sample-forward
+TFLOP_PER_FACE_FORWARD = 0.497               # CelebA-HQ DDPM UNet, 256x256
+TFLOP_PER_STYLE_REWARD = 2.514 + 2.55 + 0.03  # VAE decode + its backward + CLIP-Gram fwd/bwd per image and Langevin step
 PROMPT_PAIRS = [
-    (["a green lizard is sitting on a branch", "a brown lizard is sitting on a branch"], ("lizard", "lizard")),
-    (["a cat sitting next to a mirror", "a silver cat sculpture sitting next to a mirror"], ("cat", "cat")),
-    (["a photo of a house on a hill", "a photo of a castle on a hill in winter"], ("house", "castle")),
-    (["two birds on a wire", "two parrots on a wire"], ("birds", "parrots")),
+    (["a green lizard is sitting on a branch", "a brown lizard is sitting on a branch"], ("lizard", "lizard"), False),
+    (["a cat sitting next to a mirror", "a silver cat sculpture sitting next to a mirror"], ("cat", "cat"), False),
+    (["a photo of a house on a hill", "a photo of a castle on a hill in winter"], ("house", "castle"), False),
+    (["two birds on a wire", "two parrots on a wire"], ("birds", "parrots"), True),
 ]
+METRIC = "edited images/sec @ SD-1.5 512^2, 50-step implicit h-Edit+P2P"
+CONFIGS = {
+    2: dict(metric=METRIC, gpus=1,
+            workload="implicit h-Edit-R + P2P (Refine / Replace + Reweight + LocalBlend), SD-1.5 UNet geometry random-init, 64x64 latent (512^2), "
+                     "50 DDIM steps, batch 8/GPU"),
+    3: dict(metric="edited images/sec @ SD-1.5 512^2, 50-step explicit h-Edit-D + MasaCtrl", gpus=8,
+            workload="explicit h-Edit-D + MasaCtrl (step 4, layer 10; composed sampler, the reference ships only the implicit form), SD-1.5 UNet geometry "
+                     "random-init, 64x64 latent (512^2), 50 DDIM steps, batch 8/GPU"),
+    4: dict(metric="edited images/sec @ SD-1.5 512^2, 50-step implicit h-Edit+P2P + CLIP-style reward, K=3", gpus=2,
+            workload="text+style implicit h-Edit + P2P + CLIP-Gram reward (native VAE decode fwd+bwd, native CLIP ViT-B/16 Gram), K = 3 Langevin steps, "
+                     "SD-1.5 geometry random-init, 512^2, 50 steps, batch 8/GPU"),
+    5: dict(metric="edited images/sec @ 256^2 face swapping, 100-step h-Edit-R + ArcFace/LPIPS rewards, K=3", gpus=4,
+            workload="face swapping h_Edit_R, CelebA-HQ DDPM UNet 256^2 random-init, 100 steps, K = 3, ArcFace IR-SE50 + LPIPS-VGG16 reward networks "
+                     "at full geometry (random-init), batch 8/GPU"),
+}
+
+
+def shared_config(cfg_id, B, world, T, K):
+    """The `config` object BOTH arms print (the driver compares them key by key)."""
+    return {"workload": CONFIGS[cfg_id]["workload"], "global_batch": B * world, "timesteps": T, "optimization_steps": K}
 
 
 def ncu_traffic(kernel_prefix):
@@ -95,7 +125,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_reference_sample(T, n_timesteps, threads):
     """Times the oracle port of the reference loop (its own h_Edit_p2p_implicit restated, fp32, torch CPU) on a bounded
-    sample: `n_timesteps` of the T-step schedule for ONE image (9 UNet sample-forwards each).  Returns sec/timestep."""
+    sample: `n_timesteps` of the T-step schedule for ONE image (9 UNet sample-forwards each).  Returns sec/timestep.
+    (tools/cpu_extrapolation_check.py validates the per-timestep extrapolation against a full T = 10 run: profiles/r02_cpu_extrapolation.json)"""
     import torch
     from oracle import h_edit as oh
     from oracle import p2p as op
@@ -105,7 +136,7 @@ def cpu_reference_sample(T, n_timesteps, threads):
     torch.set_num_threads(threads)
     model = OraclePipeline(UNetConfig.sd15(), seed=0)
     model.scheduler.set_timesteps(T)
-    prompts, (bs, bt) = PROMPT_PAIRS[0]
+    prompts, (bs, bt), _ = PROMPT_PAIRS[0]
     spec = op.make_edit_spec(prompts, False, 0.4, 0.35, ((bs,), (bt,)), {"words": (bt,), "values": (2.0,)}, T, model.tokenizer)
     enc = lambda p: model.text_encoder(model.tokenizer(p).input_ids)[0]
     g = torch.Generator().manual_seed(0)
@@ -120,6 +151,9 @@ def cpu_reference_sample(T, n_timesteps, threads):
 def run_reference(args, rank):
     if rank != 0:
         return
+    if args.config != 2:
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm times BASELINE configs[1] (the headline) only"}), flush=True)
+        return
     threads = os.cpu_count() or 1
     T = args.timesteps
     for _ in range(min(args.warmup, 1)):
@@ -131,11 +165,10 @@ def run_reference(args, rank):
     ips = 1.0 / (sec_ts * T)
     sample = f"1 of {T} timesteps of 1 image per step (9 UNet sample-forwards, fp32, torch CPU), extrapolated x{T}"
     line = {
-        "impl": "reference", "metric": "edited images/sec @ SD-1.5 512^2, 50-step implicit h-Edit+P2P", "value": ips, "unit": "images/s",
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_ts * T * 8 * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "implicit h-Edit-R + P2P (Refine+Reweight+LocalBlend), SD-1.5 UNet geometry random-init, 64x64 latent, 50 DDIM steps, batch 8/GPU",
-                   "global_batch": 8 * args.gpus, "timesteps": T},
+        "config": shared_config(2, 8, args.gpus, T, 1),
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -143,9 +176,216 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------------ GPU arm
+# ------------------------------------------------------------------------------------------------ GPU workloads
+class Headline:
+    """BASELINE configs[1]: implicit h-Edit-R + P2P through the native loop."""
+    cfg_id = 2
+
+    def __init__(self, args, rank, dev):
+        import torch
+
+        import hedit_b200
+        self.h, self.torch, self.args, self.dev = hedit_b200, torch, args, dev
+        B, T = args.batch, args.timesteps
+        self.B, self.T, self.K = B, T, 1
+        self.pipe = hedit_b200.SyntheticPipeline(max_batch=B, num_inference_steps=T, device=dev.index)
+        self.eng = hedit_b200.get_engine(self.pipe, max_samples=5 * B)
+        self.items = [PROMPT_PAIRS[(rank * B + b) % len(PROMPT_PAIRS)] for b in range(B)]
+        self.pairs = [it[0] for it in self.items]
+        g = torch.Generator().manual_seed(1234 + rank)
+        self.xT_h = torch.randn(B, 4, 64, 64, generator=g).pin_memory()
+        self.zs_h = torch.randn(B, T, 4, 64, 64, generator=g).pin_memory()
+        self.cfgs = [1.0, 5.0, 7.5]
+        # device-resident copies + everything precomputed (the `value` leg)
+        self.xT_d, self.zs_d = self.xT_h.to(dev), self.zs_h.to(dev)
+        self.ctx_d = hedit_b200.encode_prompts(self.pipe, [""] + [p for pp in self.pairs for p in pp]).float()
+        self.plan = hedit_b200.compile_edit_plan(self.controllers(), T)
+        self.ts, self.coef = hedit_b200.step_tables(self.pipe.scheduler, T, 1.0, False)
+        self.h2d = (self.xT_h.numel() + self.zs_h.numel()) * 4 + self.plan.c_base.nbytes + self.plan.c_tar.nbytes + self.plan.mapper.nbytes + \
+            self.plan.blend_alpha.nbytes + (1 + 2 * B) * 77 * 4
+        self.d2h = 2 * self.xT_h.numel() * 4
+
+    def controllers(self):
+        out = []
+        for prompts, (bs, bt), rep in self.items:
+            c = self.h.make_controller(prompts, rep, 0.4, 0.35, blend_word=((bs,), (bt,)), equilizer_params={"words": (bt,), "values": (2.0,)},
+                                       num_steps=self.T, tokenizer=self.pipe.tokenizer)
+            self.h.register_attention_control(self.pipe, c)
+            out.append(c)
+        return out
+
+    def step(self, host, schedule=None):
+        schedule = self.args.schedule if schedule is None else schedule
+        if host:       # the public, reference-shaped API on host buffers: set-up + text tower + plan + H2D + loop + D2H
+            ed, rc = self.h.h_edit_p2p_batch(self.pipe, self.xT_h, self.zs_h, self.pairs, self.cfgs, self.controllers(), eta=1.0, weight_reconstruction=0.1,
+                                             optimization_steps=1, after_skip_steps=self.T, is_ddim_inversion=False, schedule=schedule)
+        else:
+            ed, rc = self.eng.edit(self.xT_d, self.zs_d, self.ctx_d, self.ts, self.coef, self.cfgs, self.plan, 0.1, 1, False, schedule)
+        return ed, dict(self.eng.last_stats)
+
+    def tflop(self, stats):
+        return stats["sample_forwards"] * TFLOP_PER_SAMPLE_FORWARD
+
+    def single_image(self, n):
+        """The drop-in signature, one image per call (what INTEGRATION.md section 1 gives a maintainer who only swaps the import)."""
+        torch = self.torch
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n):
+            b = i % self.B
+            prompts, (bs, bt), rep = self.items[b]
+            c = self.h.make_controller(prompts, rep, 0.4, 0.35, blend_word=((bs,), (bt,)), equilizer_params={"words": (bt,), "values": (2.0,)},
+                                       num_steps=self.T, tokenizer=self.pipe.tokenizer)
+            self.h.register_attention_control(self.pipe, c)
+            ed, rc = self.h.h_Edit_p2p_implicit(self.pipe, self.xT_d[b:b + 1], eta=1.0, prompts=prompts, cfg_scales=self.cfgs, zs=self.zs_d[b], controller=c,
+                                                weight_reconstruction=0.1, optimization_steps=1, after_skip_steps=self.T, is_ddim_inversion=False)
+            ed.cpu()
+        torch.cuda.synchronize()
+        return n / (time.perf_counter() - t0)
+
+
+class MasaCtrlExplicit:
+    """BASELINE configs[2]."""
+    cfg_id = 3
+
+    def __init__(self, args, rank, dev):
+        import torch
+
+        import hedit_b200
+        self.h, self.args = hedit_b200, args
+        B, T = args.batch, args.timesteps
+        self.B, self.T, self.K = B, T, 1
+        self.pipe = hedit_b200.SyntheticPipeline(max_batch=B, num_inference_steps=T, steps_offset=0, device=dev.index)
+        self.eng = hedit_b200.get_engine(self.pipe, max_samples=5 * B)
+        g = torch.Generator().manual_seed(4321 + rank)
+        self.xT_h = torch.randn(B, 4, 64, 64, generator=g).pin_memory()
+        self.zs_h = (torch.randn(B, T, 4, 64, 64, generator=g) * 0.01).pin_memory()
+        self.xT_d, self.zs_d = self.xT_h.to(dev), self.zs_h.to(dev)
+        self.ctx_d = hedit_b200.encode_prompts(self.pipe, [""] + [p for b in range(B) for p in ("", PROMPT_PAIRS[b % 4][0][1])]).float()
+        self.ts, self.coef = hedit_b200.step_tables(self.pipe.scheduler, T, 1.0, True)       # h-Edit-D: eta-0 inversion, is_ddim_inversion = True
+        self.h2d = (self.xT_h.numel() + self.zs_h.numel()) * 4
+        self.d2h = 2 * self.xT_h.numel() * 4
+
+    def step(self, host, schedule=None):
+        masa = self.h.MutualSelfAttentionControl(4, 10, total_steps=self.T).launch_plan(self.T)
+        x, z = (self.xT_h, self.zs_h) if host else (self.xT_d, self.zs_d)
+        ed, rc = self.eng.edit(x, z, self.ctx_d, self.ts, self.coef, [1.0, 5.0, 7.5], None, 0.0, 1, True, 1, masactrl=masa, mos_pull=False)
+        return ed, dict(self.eng.last_stats)
+
+    def tflop(self, stats):
+        return stats["sample_forwards"] * TFLOP_PER_SAMPLE_FORWARD
+
+    single_image = None
+
+
+class StyleReward:
+    """BASELINE configs[3]."""
+    cfg_id = 4
+
+    def __init__(self, args, rank, dev):
+        import torch
+
+        import hedit_b200
+        self.h, self.args = hedit_b200, args
+        B, T, K = args.batch, args.timesteps, 3
+        self.B, self.T, self.K = B, T, K
+        self.pipe = hedit_b200.SyntheticPipeline(max_batch=B, num_inference_steps=T, device=dev.index)
+        self.eng = hedit_b200.get_engine(self.pipe, max_samples=5 * B)
+        vae = hedit_b200.VaeDecoderEngine(dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2, norm_groups=32),
+                                          device=dev.index)
+        vae.load_random_weights(1)
+        clip = hedit_b200.ClipGramEngine(224, 16, 768, 12, 3, device=dev.index)
+        g = torch.Generator(device=dev).manual_seed(2 + rank)
+        W, sd = 768, {}
+        rnd = lambda *s, scale=1.0: (torch.rand(*s, generator=g, device=dev) * 2 - 1) * scale
+        sd["conv1.weight"] = rnd(W, 3, 16, 16, scale=(3 / 768) ** 0.5)
+        sd["class_embedding"] = rnd(W, scale=0.05); sd["positional_embedding"] = rnd(197, W, scale=0.05)
+        sd["ln_pre.weight"] = 1 + rnd(W, scale=0.1); sd["ln_pre.bias"] = rnd(W, scale=0.1)
+        for i in range(3):
+            p = f"transformer.resblocks.{i}."
+            for n in ("ln_1", "ln_2"):
+                sd[p + n + ".weight"] = 1 + rnd(W, scale=0.1); sd[p + n + ".bias"] = rnd(W, scale=0.1)
+            sd[p + "attn.in_proj_weight"] = rnd(3 * W, W, scale=(3 / W) ** 0.5); sd[p + "attn.in_proj_bias"] = rnd(3 * W, scale=0.1)
+            sd[p + "attn.out_proj.weight"] = rnd(W, W, scale=(3 / W) ** 0.5); sd[p + "attn.out_proj.bias"] = rnd(W, scale=0.1)
+            sd[p + "mlp.c_fc.weight"] = rnd(4 * W, W, scale=(3 / W) ** 0.5); sd[p + "mlp.c_fc.bias"] = rnd(4 * W, scale=0.1)
+            sd[p + "mlp.c_proj.weight"] = rnd(W, 4 * W, scale=(3 / (4 * W)) ** 0.5); sd[p + "mlp.c_proj.bias"] = rnd(W, scale=0.1)
+        clip.load_state_dict(sd)
+        clip.set_reference(torch.randn(1, 3, 224, 224, generator=g, device=dev))
+        self.fn = hedit_b200.style.clip_gram_guidance_fused(vae, clip, vae_batch=2)
+        self.keep = (vae, clip)
+        prompts = PROMPT_PAIRS[0][0]
+        self.ctrl = lambda: [hedit_b200.make_controller(prompts, False, 0.4, 0.35, blend_word=None, equilizer_params=None, num_steps=T,
+                                                        tokenizer=self.pipe.tokenizer) for _ in range(B)]
+        self.plan = hedit_b200.compile_edit_plan(self.ctrl(), T)
+        gc = torch.Generator().manual_seed(99 + rank)
+        self.xT_h = torch.randn(B, 4, 64, 64, generator=gc).pin_memory()
+        self.zs_h = torch.randn(B, T, 4, 64, 64, generator=gc).pin_memory()
+        self.xT_d, self.zs_d = self.xT_h.to(dev), self.zs_h.to(dev)
+        self.ctx_d = hedit_b200.encode_prompts(self.pipe, [""] + list(prompts) * B).float()
+        self.ts, self.coef = hedit_b200.step_tables(self.pipe.scheduler, T, 1.0, False)
+        self.x0c = hedit_b200.x0_tables(self.pipe.scheduler, T)
+        self.h2d = (self.xT_h.numel() + self.zs_h.numel()) * 4
+        self.d2h = 2 * self.xT_h.numel() * 4
+
+    def step(self, host, schedule=None):
+        x, z = (self.xT_h, self.zs_h) if host else (self.xT_d, self.zs_d)
+        plan = self.h.compile_edit_plan(self.ctrl(), self.T) if host else self.plan
+        ed, rc = self.eng.edit(x, z, self.ctx_d, self.ts, self.coef, [1.0, 5.0, 7.5], plan, 0.0, self.K, False, 1, mos_pull=False,
+                               guidance=(self.fn, 0.5, self.x0c))
+        return ed, dict(self.eng.last_stats)
+
+    def tflop(self, stats):
+        return stats["sample_forwards"] * TFLOP_PER_SAMPLE_FORWARD + self.B * self.T * self.K * TFLOP_PER_STYLE_REWARD
+
+    single_image = None
+
+
+class FaceSwap:
+    """BASELINE configs[4]: native DDPM UNet + loop; ArcFace IR-SE50 and LPIPS-VGG16 at full geometry (hedit_b200.reward_nets)."""
+    cfg_id = 5
+
+    def __init__(self, args, rank, dev):
+        import numpy as np
+        import torch
+
+        import hedit_b200
+        from hedit_b200 import reward_nets
+        self.h, self.args = hedit_b200, args
+        B, T, K = args.batch, (100 if args.timesteps == 50 else args.timesteps), 3
+        self.B, self.T, self.K = B, T, K
+        self.eng = hedit_b200.FaceUNetEngine(dict(ch=128, ch_mult=(1, 1, 2, 2, 4, 4), num_res_blocks=2, attn_resolution=16, image_size=256, in_channels=3,
+                                                  out_ch=3), device=dev.index)
+        self.eng.load_random_weights(0)
+        betas = torch.linspace(0.0001, 0.02, 1000, dtype=torch.float64).float()
+        seq = (np.arange(0, 1000, 1000 // T) + 1)[::-1]
+        self.coef = hedit_b200.face.face_step_tables(betas, seq, T, T, 1.0)
+        g = torch.Generator().manual_seed(7 + rank)
+        self.xT_h = torch.randn(B, 3, 256, 256, generator=g).pin_memory()
+        self.zs_h = torch.randn(B, T, 3, 256, 256, generator=g).pin_memory()
+        self.xT_d, self.zs_d = self.xT_h.to(dev), self.zs_h.to(dev)
+        ref_img = torch.tanh(torch.randn(1, 3, 256, 256, generator=g)).to(dev)
+        src_img = torch.tanh(torch.randn(B, 3, 256, 256, generator=g)).to(dev)
+        self.id_grad, self.lp_grad, self.reward_kind = reward_nets.make_reward_grads(ref_img, src_img, dev, seed=3)
+        self.h2d = (self.xT_h.numel() + self.zs_h.numel()) * 4
+        self.d2h = self.xT_h.numel() * 4
+
+    def step(self, host, schedule=None):
+        x, z = (self.xT_h.to(self.xT_d.device, non_blocking=True), self.zs_h.to(self.xT_d.device, non_blocking=True)) if host else (self.xT_d, self.zs_d)
+        ed = self.eng.edit(x, z, self.coef, 50.0, self.K, id_grad=self.id_grad, lpips_grad=self.lp_grad)
+        if host:
+            ed = ed.cpu()
+        return ed, dict(self.eng.last_stats)
+
+    def tflop(self, stats):
+        return stats["sample_forwards"] * TFLOP_PER_FACE_FORWARD
+
+    single_image = None
+
+
+WORKLOADS = {2: Headline, 3: MasaCtrlExplicit, 4: StyleReward, 5: FaceSwap}
+
+
 def run_gpu(args, rank, world, local_rank):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -156,38 +396,14 @@ def run_gpu(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    B, T = args.batch, args.timesteps
-    cfg = dict(in_channels=4, out_channels=4, sample_size=64, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, heads=8,
-               cross_attention_dim=768, norm_groups=32, ctx_len=77)
-    eng = hedit_b200.UNetEngine(cfg, max_samples=5 * B, max_contexts=1 + 2 * B, device=local_rank)
-    eng.load_random_weights(seed=0)
-    tok = hedit_b200.WordTokenizer()
-    sched = hedit_b200.DDIMTables(T, steps_offset=1)
-    ts, coef = hedit_b200.step_tables(sched, T, 1.0, False)
-    ctrls = []
-    for b in range(B):
-        prompts, (bs, bt) = PROMPT_PAIRS[(rank * B + b) % len(PROMPT_PAIRS)]
-        ctrls.append(hedit_b200.make_controller(prompts, False, 0.4, 0.35, blend_word=((bs,), (bt,)),
-                                                equilizer_params={"words": (bt,), "values": (2.0,)}, num_steps=T, tokenizer=tok))
-    plan = hedit_b200.compile_edit_plan(ctrls, T)
-    g = torch.Generator().manual_seed(1234 + rank)
-    xT_h = torch.randn(B, 4, 64, 64, generator=g).pin_memory()
-    zs_h = torch.randn(B, T, 4, 64, 64, generator=g).pin_memory()
-    ctx_h = (torch.randn(1 + 2 * B, 77, 768, generator=g)).pin_memory()      # synthetic text-encoder outputs
-    xT_d, zs_d, ctx_d = xT_h.to(dev), zs_h.to(dev), ctx_h.to(dev)
-    cfgs = [1.0, 5.0, 7.5]
+    wl = WORKLOADS[args.config](args, rank, dev)
+    B, T = wl.B, wl.T
 
     def step(host, schedule=None):
-        schedule = args.schedule if schedule is None else schedule
-        if host:
-            ed, rc = eng.edit(xT_h, zs_h, ctx_h, ts, coef, cfgs, plan, 0.1, 1, False, schedule)
-            ed_dev = ed.to(dev, non_blocking=True) if world > 1 else ed
-        else:
-            ed, rc = eng.edit(xT_d, zs_d, ctx_d, ts, coef, cfgs, plan, 0.1, 1, False, schedule)
-            ed_dev = ed
+        ed, st = wl.step(host, schedule)
         if world > 1:
-            gather_results(ed_dev, B * world)      # the only collective: final result gather over NCCL
-        return eng.last_stats
+            gather_results(ed.to(dev, non_blocking=True) if not ed.is_cuda else ed, B * world)      # the only collective: final result gather over NCCL
+        return st
 
     def timed(host, n, schedule=None):
         if world > 1:
@@ -195,83 +411,99 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        tf = 0.0
         fwd = launches = 0
         for _ in range(n):
             st = step(host, schedule)
-            fwd += st["sample_forwards"]; launches += st["kernel_launches"]
+            fwd += st["sample_forwards"]; launches += st["kernel_launches"]; tf += wl.tflop(st)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         ms = max_over_ranks(e0.elapsed_time(e1), dev)
-        return ms, fwd, launches
+        return ms, fwd, launches, tf
 
     for _ in range(args.warmup):
         step(False)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms, fwd, launches = timed(False, args.steps)
+    ms, fwd, launches, tf = timed(False, args.steps)
     clocks = sampler.stop() if rank == 0 else {}
-    step(True)                                       # warm the host path once
-    ms_e2e, _, _ = timed(True, args.steps)
+    # ---- end to end through the public API on host buffers; set-up caches cold for the first call (reported), warm in the timed region
+    hedit_b200.clear_setup_cache(getattr(getattr(wl, 'pipe', None), 'tokenizer', None))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step(True)
+    torch.cuda.synchronize()
+    first_call_ms = (time.perf_counter() - t0) * 1e3
+    ms_e2e, _, _, _ = timed(True, args.steps)
     ips = B * world * args.steps / (ms / 1e3)
     ips_e2e = B * world * args.steps / (ms_e2e / 1e3)
     peak_tf, _, peak_src = measured_peaks()
-    achieved_tf = fwd * TFLOP_PER_SAMPLE_FORWARD / (ms / 1e3)          # this rank's UNet work / max-over-ranks time
-    h2d = (xT_h.numel() + zs_h.numel() + ctx_h.numel()) * 4 + plan.c_base.nbytes + plan.c_tar.nbytes + plan.mapper.nbytes + plan.blend_alpha.nbytes
-    d2h = 2 * xT_h.numel() * 4
-    # opt-in schedule 2 (cfg_src == 1: u + 1*(c-u) == c, 5 UNet sample-forwards per step), reported next to the headline
-    skip = None
-    if args.schedule == 1:
-        ms2, fwd2, _ = timed(False, 1, schedule=2)
-        skip = {"value": B * world / (ms2 / 1e3), "unit": "images/s", "sample_forwards_per_image": fwd2 / B,
-                "note": "schedule 2: same edit up to one fp32 rounding per element of the source-guided noise; not the headline"}
-    # live per-kernel timing (CUDA events around every launch of one UNet forward of 5B samples) -> the dominant kernel's roofline
-    prof = gemm = None
-    if rank == 0:
-        pf = eng.profile_forward(5 * B, 2)
-        prof = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(pf.items(), key=lambda kv: -kv[1][0])}
-        gemm_tags = [k for k in pf if k.startswith(("res.", "tf.", "upsample.conv", "downsample", "conv_out"))]
-        gemm_ms = sum(pf[k][0] for k in gemm_tags)
-        gemm_n = sum(pf[k][1] for k in gemm_tags)
-        total_ms = sum(v[0] for v in pf.values())
-        gemm_tf = 5 * B * GEMM_TFLOP_PER_SAMPLE_FORWARD / (gemm_ms / 1e3)
-        gemm = {"kernel": "gemm_bf16_tcgen05_kernel (implicit-GEMM conv3x3 + linear launches)", "launches_per_forward": gemm_n,
-                "avg_launch_us": 1e3 * gemm_ms / gemm_n, "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
-                "share_of_forward": gemm_ms / total_ms,
-                "algorithmic": "2*M*N*K per launch; 338.58 GMAC per UNet sample-forward over all GEMM launches (SURVEY 8d)"}
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        sec_ts = cpu_reference_sample(T, 1, threads)
-        cpu = {"value": 1.0 / (sec_ts * T), "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"1 of {T} timesteps of 1 image (9 UNet sample-forwards, fp32 torch CPU oracle port of the reference loop), extrapolated x{T}"}
+    achieved_tf = tf / (ms / 1e3)          # this rank's tensor work / max-over-ranks time
+    single = skip = prof = gemm = cpu = None
+    if args.config == 2:
+        # opt-in schedule 2 (cfg_src == 1: u + 1*(c-u) == c, 5 UNet sample-forwards per step), reported next to the headline
+        if args.schedule == 1:
+            ms2, fwd2, _, _ = timed(False, 1, schedule=2)
+            skip = {"value": B * world / (ms2 / 1e3), "unit": "images/s", "sample_forwards_per_image": fwd2 / B,
+                    "note": "schedule 2: same edit up to one fp32 rounding per element of the source-guided noise; not the headline"}
+        if rank == 0 and not args.no_single_image:
+            wl.single_image(1)
+            single = {"value": wl.single_image(max(2, min(4, args.steps * 2))), "unit": "images/s",
+                      "api": "hedit_b200.h_Edit_p2p_implicit(model, xT, eta, prompts, cfg_scales, zs=zs, controller=controller, ...) -- the reference's "
+                             "signature (p2p_h_edit.py:529), one image per call incl. make_controller and the text tower"}
+        # live per-kernel timing (CUDA events around every launch of one UNet forward of 5B samples) -> the dominant kernel's roofline
+        if rank == 0:
+            pf = wl.eng.profile_forward(5 * B, 2)
+            prof = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(pf.items(), key=lambda kv: -kv[1][0])}
+            gemm_tags = [k for k in pf if k.startswith(("res.", "tf.", "upsample.conv", "downsample", "conv_out"))]
+            gemm_ms = sum(pf[k][0] for k in gemm_tags)
+            gemm_n = sum(pf[k][1] for k in gemm_tags)
+            total_ms = sum(v[0] for v in pf.values())
+            gemm_tf = 5 * B * GEMM_TFLOP_PER_SAMPLE_FORWARD / (gemm_ms / 1e3)
+            gemm = {"kernel": "gemm_bf16_tcgen05_kernel (implicit-GEMM conv3x3 + linear launches)", "launches_per_forward": gemm_n,
+                    "avg_launch_us": 1e3 * gemm_ms / gemm_n, "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
+                    "share_of_forward": gemm_ms / total_ms, "forward_ms_40_samples": total_ms,
+                    "algorithmic": "2*M*N*K per launch; 338.58 GMAC per UNet sample-forward over all GEMM launches (SURVEY 8d)"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sec_ts = cpu_reference_sample(T, 1, threads)
+            cpu = {"value": 1.0 / (sec_ts * T), "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": f"1 of {T} timesteps of 1 image (9 UNet sample-forwards, fp32 torch CPU oracle port of the reference loop), extrapolated x{T}"}
     if rank == 0:
         line = {
-            "metric": "edited images/sec @ SD-1.5 512^2, 50-step implicit h-Edit+P2P", "value": ips, "unit": "images/s", "n_gpus": world,
+            "metric": CONFIGS[args.config]["metric"], "value": ips, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": f"{hedit_b200._lib.load().hedit_operand_dtype().decode()} operands, f32 accumulate/residual/softmax/scheduler",
             "data": "synthetic",
-            "config": {"workload": "implicit h-Edit-R + P2P (Refine+Reweight+LocalBlend), SD-1.5 UNet geometry random-init, 64x64 latent (512^2), 50 DDIM steps, batch 8/GPU",
-                       "global_batch": B * world, "timesteps": T, "optimization_steps": 1,
-                       "schedule": {0: "reference (9 UNet sample-forwards/step)", 1: "exact-reuse (7 UNet sample-forwards/step)",
-                                    2: "exact-reuse + skip-uncond at cfg_src=1 (5 UNet sample-forwards/step)"}[args.schedule],
-                       "sample_forwards_per_image": fwd / (B * args.steps),
-                       "launch": "repeated UNet launches replayed from CUDA graphs (HEDIT_LOOP_GRAPH=0: direct); gpu_launches counts the kernels inside",
-                       "l2": "working set per step (1.7 GB fp16 weights + GBs of activations) >> 126 MB L2; no explicit flush needed"},
-            "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "config": shared_config(args.config, B, world, T, wl.K),
+            "run": {"schedule": {0: "reference (9 UNet sample-forwards/step)", 1: "exact-reuse (7 UNet sample-forwards/step)",
+                                 2: "exact-reuse + skip-uncond at cfg_src=1 (5 UNet sample-forwards/step)"}[args.schedule] if args.config == 2 else None,
+                    "sample_forwards_per_image": fwd / (B * args.steps),
+                    "launch": "repeated UNet launches replayed from CUDA graphs (HEDIT_LOOP_GRAPH=0: direct); gpu_launches counts the kernels inside",
+                    "l2": "working set per step (1.7 GB fp16 weights + GBs of activations) >> 126 MB L2; no explicit flush needed",
+                    "baseline_gpus": CONFIGS[args.config]["gpus"]},
+            "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h),
+                    "api": "make_controller x B -> register_attention_control -> hedit_b200.h_edit_p2p_batch(pipeline, xT_host, zs_host, prompt_pairs, ...): "
+                           "tokeniser, native text tower, aligner, edit-plan compilation, step tables, H2D, loop, D2H inside the timed region"
+                           if args.config == 2 else "engine.edit on pinned host buffers (H2D, loop, D2H inside the timed region)",
+                    "first_call_ms_cold_setup_cache": first_call_ms},
+            "single_image": single,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                          "traffic": ncu_traffic("gemm_bf16_tcgen05_kernel"), "peak_source": peak_src, "dominant_kernel": gemm,
-                         "note": "achieved = executed UNet sample-forwards x 0.8033 TFLOP / device time of the timed region (per GPU), i.e. the whole "
-                                 "step incl. attention, norms and the h-step kernels; dominant_kernel = the GEMM/conv kernel alone, timed live with CUDA "
-                                 "events around each of its launches; traffic = dram read+write bytes of one conv launch (S=16, 64x64, 320->320: "
-                                 "algorithmic 42 MB in + 84 MB out, L2-absorbed writes) from the committed ncu --set full capture (profiles/)"},
+                         "note": "achieved = executed UNet sample-forwards x 0.8033 TFLOP (+ reward-branch flops for configs 4/5) / device time of the timed "
+                                 "region (per GPU), i.e. the whole step incl. attention, norms and the h-step kernels; dominant_kernel = the GEMM/conv kernel "
+                                 "alone, timed live with CUDA events around each of its launches; traffic = dram read+write bytes of one conv launch (S=16, "
+                                 "64x64, 320->320: algorithmic 42 MB in + 84 MB out, L2-absorbed writes) from the committed ncu --set full capture (profiles/)"},
             "skip_uncond_schedule": skip,
             "cpu_baseline": cpu,
         }
+        if args.config == 5:
+            line["run"]["reward_networks"] = wl.reward_kind
         if prof and args.profile:
             line["kernel_breakdown_ms_per_forward"] = prof
         print(json.dumps(line), flush=True)
@@ -285,11 +517,13 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configuration (1-based: 2 = the headline)")
     ap.add_argument("--batch", type=int, default=8, help="images per GPU")
     ap.add_argument("--timesteps", type=int, default=50)
     ap.add_argument("--schedule", type=int, default=1, choices=[0, 1, 2])
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-image", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

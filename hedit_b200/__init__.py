@@ -7,9 +7,10 @@ from .p2p import (EditController, LocalBlend, compile_edit_plan, get_equalizer, 
                   get_replacement_mapper, get_time_words_attention_alpha, get_word_inds, make_controller,
                   register_attention_control)
 from .schedule import DDIMTables, skip_pre_coeff, step_tables, x0_tables  # noqa: F401
+from .p2p import clear_setup_cache  # noqa: F401
 from .tokenizer import WordTokenizer  # noqa: F401
 from .engine import UNetEngine, unet_config_of  # noqa: F401
-from .samplers import (HEditStepper, h_edit_step, MutualSelfAttentionControl, encode_text, get_engine, h_Edit_masactrl_explicit, h_Edit_masactrl_implicit, h_Edit_p2p_explicit,  # noqa: F401
+from .samplers import (encode_prompts, invalidate_engines, HEditStepper, h_edit_step, MutualSelfAttentionControl, encode_text, get_engine, h_Edit_masactrl_explicit, h_Edit_masactrl_implicit, h_Edit_p2p_explicit,  # noqa: F401
                        h_Edit_p2p_implicit, h_Edit_R_explicit, h_Edit_R_implicit, h_edit_p2p_batch, regiter_attention_editor_diffusers,
                        h_Edit_PnP_implicit, pnp_self_mask, pnp_step_flags, register_attention_control_efficient, register_conv_control_efficient, register_time)
 
@@ -21,6 +22,7 @@ from . import face  # noqa: F401,E402
 from .face import FaceUNetEngine  # noqa: F401,E402
 from . import compat  # noqa: F401,E402
 from .compat import CompatUNet, controller_kind, h_edit_p2p_implicit_compat, register_attention_control_compat  # noqa: F401,E402
+from .pipeline import SyntheticPipeline, random_text_engine  # noqa: F401,E402
 from .inversion import ddim_inversion, inversion_forward_process_ddpm, sample_xts_from_x0  # noqa: F401,E402
 
 __all__ = ["inversion_forward_process_ddpm", "ddim_inversion", "UNetEngine", "unet_config_of", "make_controller", "register_attention_control", "compile_edit_plan",

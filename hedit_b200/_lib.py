@@ -68,9 +68,10 @@ class EditArgsC(C.Structure):
         ("xT", C.c_void_p), ("zs", C.c_void_p), ("ctx", C.c_void_p), ("timesteps", C.c_void_p), ("coef", C.c_void_p),
         ("w_src", C.c_float), ("w_src_edit", C.c_float), ("w_tar", C.c_float), ("weight_reconstruction", C.c_float),
         ("use_p2p", C.c_int32),
-        ("mapper", C.c_void_p), ("is_replace", C.c_void_p), ("replace_m", C.c_void_p), ("c_base", C.c_void_p), ("c_tar", C.c_void_p),
+        ("mapper", C.c_void_p), ("map_w", C.c_void_p), ("map_rows", C.c_int32), ("is_replace", C.c_void_p), ("replace_m", C.c_void_p), ("c_base", C.c_void_p), ("c_tar", C.c_void_p),
         ("self_lo", C.c_int32), ("self_hi", C.c_int32), ("self_max_tokens", C.c_int32),
         ("has_blend", C.c_void_p), ("blend_alpha", C.c_void_p), ("start_blend", C.c_int32), ("blend_th", C.c_float),
+        ("blend_rows", C.c_int32), ("blend_th_sub", C.c_float),
         ("masa", C.c_int32), ("masa_layer_mask", C.c_uint32), ("masa_step_on", C.c_void_p), ("mos_pull", C.c_int32),
         ("pnp", C.c_int32), ("pnp_self_mask", C.c_uint32), ("pnp_qk_on", C.c_void_p), ("pnp_feat_on", C.c_void_p),
         ("pre_step", C.c_int32), ("pre_coeff", C.c_float),

@@ -30,7 +30,11 @@ def controller_kind(controller) -> str:
         return "none"
     chain, c = [], controller
     while c is not None and len(chain) < 8:
-        chain.append(type(c).__name__)
+        # a stock class is recognised by name AND defining module (ours, or the reference's p2p/ptp_classes.py): a user class that merely
+        # reuses a stock name, or subclasses one to override a hook, only promises the protocol -> compat path
+        mod = type(c).__module__ or ""
+        stock_home = mod.endswith("ptp_classes") or mod.startswith("hedit_b200")
+        chain.append(type(c).__name__ if stock_home else "user:" + type(c).__name__)
         c = getattr(c, "prev_controller", None)
     if all(n in STOCK_CLASSES for n in chain) and hasattr(controller, "cross_replace_alpha"):
         return "stock"

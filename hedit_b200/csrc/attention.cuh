@@ -35,14 +35,19 @@ struct AttnParams {
   const int* unit_s1;             // second sample (P2P target) or -1
   const int* unit_img;            // image index for the edit tables
   const int* ctx_idx;             // per sample: index into the cached text K/V
-  const int* mapper;              // [img][80]      refine gather index (clamped to [0,77))
+  const int* mapper;              // [img][map_rows][80]  source-token indices of target token j (clamped to [0,77)); map_rows = 1: Refine gather
+  const float* map_w;             // [img][map_rows][80]  their weights, or null (= 1): base_j = sum_k w[k][j] * P_src[mapper[k][j]] -- the
+                                  //   non-zeros of AttentionReplace's 77x77 mapper column j (1-3 per column) in increasing row order, so the sum
+                                  //   equals the dense product bit for bit; Refine rows are (mapper[j], 1) padded with weight 0
+  int map_rows;                   // 0 / 1, or R <= 4
   const float* c_base;            // [img][80]      coefficient on mapped source prob (already includes alpha_words[step])
   const float* c_tar;             // [img][80]      coefficient on the target's own prob
   const float* replace_m;         // [img][77][80]  replacement matrix or null
   const int* is_replace;          // [img]
-  float* blend_acc;               // [img][2][n_blend_layers][H][Nq] fp32 accumulators or null
-  const float* blend_alpha;       // [img][2][80]
+  float* blend_acc;               // [img][blend_rows][n_blend_layers][H][Nq] fp32 accumulators or null
+  const float* blend_alpha;       // [img][blend_rows][80]: rows 0,1 = LocalBlend.alpha_layers (src, tar); rows 2,3 = substruct_layers (blend_rows == 4)
   int blend_layer, n_blend_layers;
+  int blend_rows;                 // 2, or 4 with LocalBlend substruct_words (ptp_classes.py:28-38,66-67)
   int tiles_per_cta;              // cross_attn2_kernel: query tiles handled by one CTA
 };
 
@@ -600,7 +605,14 @@ HEDIT_DEVICE void exp2_block16(const uint32_t* v, float scale, float neg_m, uint
   }
 }
 
-template <int DCH, bool MMASUM, bool TWOPASS, int POLY16>
+//   PINGPONG: the two softmax warpgroups of a CTA alternate their exponential phases through two named barriers (warpgroup t enters its
+//            exponential phase only after warpgroup 1-t has left its own), so that one warpgroup's MUFU work overlaps the other's
+//            wait-for-P.V / TMEM-read / row-max phase instead of both contending for the MUFU and then both idling (free-running
+//            warpgroups fall into lockstep because the MUFU is shared round-robin).
+HEDIT_DEVICE void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+HEDIT_DEVICE void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <int DCH, bool MMASUM, bool TWOPASS, int POLY16, bool PINGPONG = false>
 static __global__ void __launch_bounds__(SelfAttn2Cfg<DCH, 2, 64>::THREADS, SelfAttn2Cfg<DCH, 2, 64>::MIN_CTAS)
 self_attn3_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = SelfAttn2Cfg<DCH, 2, 64>;
@@ -744,6 +756,7 @@ self_attn3_kernel(const __grid_constant__ AttnParams p) {
     uint8_t* sPt = sP + tile * Cfg::PT_BYTES;
     const int DKL = MMASUM ? DK + 16 : DK;            // columns rescaled with O (the row sum rides along)
     float m_used = -INFINITY, l = 0.f;
+    if (PINGPONG && tile == 1) named_bar_arrive(1, 256);          // warpgroup 0 takes the first exponential phase
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full[tile], j & 1);
       tc_fence_after();
@@ -803,6 +816,7 @@ self_attn3_kernel(const __grid_constant__ AttnParams p) {
       float2 ls[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) ls[k] = make_float2(0.f, 0.f);
+      if (PINGPONG) named_bar_sync(1 + tile, 256);
 #pragma unroll
       for (int c = 0; c < BKV; c += 32) {
         if constexpr (TWOPASS) {
@@ -823,12 +837,14 @@ self_attn3_kernel(const __grid_constant__ AttnParams p) {
           *reinterpret_cast<uint4*>(sPt + sw128_off(r, (cc >> 3) + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
       }
+      if (PINGPONG) named_bar_arrive(1 + (tile ^ 1), 256);
       if (!MMASUM) l += ((ls[0].x + ls[0].y) + (ls[1].x + ls[1].y)) + ((ls[2].x + ls[2].y) + (ls[3].x + ls[3].y));
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[tile]);
     }
+    if (PINGPONG && tile == 0) named_bar_sync(1, 256);            // consume warpgroup 1's last hand-over
     mbar_wait(&pv_done[tile], (nblk - 1) & 1);
     tc_fence_after();
     if (MMASUM) {
@@ -989,8 +1005,10 @@ __global__ void __launch_bounds__(192) cross_attn_kernel(const __grid_constant__
       const float inv = 1.f / l;
       const bool edit = (ph == 1);
       const bool do_blend = p.blend_acc != nullptr && row < p.Nq;
-      const float* bal = p.blend_alpha ? p.blend_alpha + (size_t(img) * 2 + ph) * BKV : nullptr;
-      float bsum = 0.f;
+      const int brows = p.blend_rows > 2 ? 4 : 2;
+      const float* bal = p.blend_alpha ? p.blend_alpha + (size_t(img) * brows + ph) * BKV : nullptr;
+      const float* bal2 = (bal && brows == 4) ? bal + 2 * BKV : nullptr;
+      float bsum = 0.f, bsum2 = 0.f;
       // pass 3: normalised probabilities (+ P2P edit for the target) -> bf16 P tile
 #pragma unroll 1
       for (int c = 0; c < BKV; c += 16) {
@@ -1004,17 +1022,23 @@ __global__ void __launch_bounds__(192) cross_attn_kernel(const __grid_constant__
           float v = (jc < NKV) ? ex2f(__uint_as_float(raw[i]) * p.scale_log2 - mx) * inv : 0.f;
           if (edit && jc < NKV) {
             float base;
-            if (p.is_replace && p.is_replace[img]) {
+            const int R = p.map_rows > 1 ? p.map_rows : 1;
+            if (p.is_replace && p.is_replace[img] && p.map_w == nullptr) {       // dense fallback (columns with more than 4 non-zeros)
               const float* M = p.replace_m + size_t(img) * 77 * BKV + jc;
               base = 0.f;
               for (int w = 0; w < 77; ++w) base = fmaf(sPB[w * 128 + r], M[w * BKV], base);
-            } else {
+            } else if (p.map_w == nullptr) {
               base = sPB[p.mapper[img * BKV + jc] * 128 + r];
+            } else {
+              base = 0.f;
+              for (int k = 0; k < R; ++k)
+                base = fmaf(sPB[p.mapper[(img * R + k) * BKV + jc] * 128 + r], p.map_w[(img * R + k) * BKV + jc], base);
             }
             v = base * p.c_base[img * BKV + jc] + v * p.c_tar[img * BKV + jc];
           }
           pr[i] = v;
           if (bal && jc < NKV) bsum = fmaf(bal[jc], v, bsum);
+          if (bal2 && jc < NKV) bsum2 = fmaf(bal2[jc], v, bsum2);
         }
         if (nph == 2 && ph == 0) {
 #pragma unroll
@@ -1029,8 +1053,9 @@ __global__ void __launch_bounds__(192) cross_attn_kernel(const __grid_constant__
                          pack_op2(pr[8 * u + 4], pr[8 * u + 5]), pack_op2(pr[8 * u + 6], pr[8 * u + 7]));
       }
       if (do_blend && nph == 2) {
-        float* acc = p.blend_acc + (((size_t(img) * 2 + ph) * p.n_blend_layers + p.blend_layer) * p.H + h) * p.Nq + row;
+        float* acc = p.blend_acc + (((size_t(img) * brows + ph) * p.n_blend_layers + p.blend_layer) * p.H + h) * p.Nq + row;
         *acc += bsum;
+        if (bal2) acc[size_t(2) * p.n_blend_layers * p.H * p.Nq] += bsum2;
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -1082,7 +1107,8 @@ struct CrossAttn2Cfg {
   static constexpr uint32_t KV_BYTES = DCH * BKV * 128;           // K (or V) of one context
   static constexpr uint32_t P_BYTES = 2 * 128 * 128;
   static constexpr uint32_t PB_BYTES = BKV * 128 * 4;             // fp32 probabilities [col][row]: source (PB) and target scratch (PT)
-  static constexpr uint32_t SMEM_BYTES = NQ * Q_BYTES + 4 * KV_BYTES + P_BYTES + 2 * PB_BYTES + 256 + 1024;   // + barriers + edit tables
+  static constexpr int MAXR = 4;                                  // non-zeros per column of the replacement mapper served from shared memory
+  static constexpr uint32_t SMEM_BYTES = NQ * Q_BYTES + 4 * KV_BYTES + P_BYTES + 2 * PB_BYTES + 256 + (2 * MAXR + 2) * 320;   // + barriers + edit tables
   static constexpr uint32_t TMEM_COLS = 512;                      // S[2] at 0,128 ; O[2] at 256, 384
   static_assert(DCH <= 2, "cross v2 supports head dims <= 128");
 };
@@ -1109,9 +1135,11 @@ static __global__ void __launch_bounds__(192, 1) cross_attn2_kernel(const __grid
   uint64_t* o_free = bars + 11;        // 2 (4 arrivals)
   uint64_t* p_full = bars + 13;        // 1 (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  int* sMap = reinterpret_cast<int*>(bars + 32);          // [80] edit tables of this image, staged once per CTA
-  float* sCb = reinterpret_cast<float*>(sMap + 80);
+  int* sMap = reinterpret_cast<int*>(bars + 32);          // [R][80] edit tables of this image, staged once per CTA
+  float* sMw = reinterpret_cast<float*>(sMap + Cfg::MAXR * 80);   // [R][80]
+  float* sCb = sMw + Cfg::MAXR * 80;
   float* sCt = sCb + 80;
+  const int R = (p.map_w != nullptr && p.map_rows > 1) ? min(p.map_rows, Cfg::MAXR) : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, unit = blockIdx.z;
@@ -1134,7 +1162,10 @@ static __global__ void __launch_bounds__(192, 1) cross_attn2_kernel(const __grid
     fence_mbar_init();
   }
   if (nph == 2 && threadIdx.x < BKV) {
-    sMap[threadIdx.x] = p.mapper[img * BKV + threadIdx.x];
+    for (int k = 0; k < R; ++k) {
+      sMap[k * 80 + threadIdx.x] = p.mapper[(img * R + k) * BKV + threadIdx.x];
+      sMw[k * 80 + threadIdx.x] = p.map_w ? p.map_w[(img * R + k) * BKV + threadIdx.x] : 1.f;
+    }
     sCb[threadIdx.x] = p.c_base[img * BKV + threadIdx.x];
     sCt[threadIdx.x] = p.c_tar[img * BKV + threadIdx.x];
   }
@@ -1243,7 +1274,8 @@ static __global__ void __launch_bounds__(192, 1) cross_attn2_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[b]);
     };
-    const bool rep = p.is_replace && p.is_replace[img];
+    const bool rep = p.is_replace && p.is_replace[img] && (p.map_w == nullptr || p.map_rows > Cfg::MAXR);     // dense fallback only
+    const bool sparse = p.map_w != nullptr && !rep;
     for (int i = 0; i < n_items; ++i) {
       const int b = i & 1, tile = t0 + i / nph, ph = i % nph;
       const int row = tile * 128 + r;
@@ -1308,6 +1340,9 @@ static __global__ void __launch_bounds__(192, 1) cross_attn2_kernel(const __grid
                 base = 0.f;
 #pragma unroll 1
                 for (int w = 0; w < 77; ++w) base = fmaf(sPB[w * 128 + r], M[w * BKV], base);
+              } else if (sparse) {
+                base = 0.f;
+                for (int q = 0; q < R; ++q) base = fmaf(sPB[mp[q * 80 + jc] * 128 + r], sMw[q * 80 + jc], base);
               } else {
                 base = sPB[mp[jc] * 128 + r];
               }
@@ -1321,12 +1356,15 @@ static __global__ void __launch_bounds__(192, 1) cross_attn2_kernel(const __grid
         }
       }
       if (p.blend_acc != nullptr && nph == 2 && row < p.Nq) {
-        const float* bal = p.blend_alpha + (size_t(img) * 2 + ph) * BKV;
-        float bsum = 0.f;
+        const int brows = p.blend_rows > 2 ? 4 : 2;
+        for (int rr = ph; rr < brows; rr += 2) {            // word maps of LocalBlend's words, then of its substruct_words
+          const float* bal = p.blend_alpha + (size_t(img) * brows + rr) * BKV;
+          float bsum = 0.f;
 #pragma unroll 1
-        for (int j = 0; j < NKV; ++j) bsum = fmaf(bal[j], dstf[j * 128 + r], bsum);
-        float* acc = p.blend_acc + (((size_t(img) * 2 + ph) * p.n_blend_layers + p.blend_layer) * p.H + h) * p.Nq + row;
-        *acc += bsum;
+          for (int j = 0; j < NKV; ++j) bsum = fmaf(bal[j], dstf[j * 128 + r], bsum);
+          float* acc = p.blend_acc + (((size_t(img) * brows + rr) * p.n_blend_layers + p.blend_layer) * p.H + h) * p.Nq + row;
+          *acc += bsum;
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();

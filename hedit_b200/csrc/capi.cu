@@ -15,6 +15,22 @@
 #include "clip_text.h"
 #include "face.h"
 
+// Every entry point runs on its handle's device and restores the caller's current device on return: torch reads the current device from
+// the runtime, so leaving it switched would silently redirect the caller's later allocations and launches.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
 namespace hedit {
 int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st);
 int run_face_edit(FaceUNet& U, hedit_face_args& a, cudaStream_t st);
@@ -75,8 +91,8 @@ int hedit_device_count(void) {
 hedit_engine* hedit_engine_create(const hedit_unet_config* cfg, int max_samples, int max_contexts, int device) {
   if (!cfg) { fail("null config"); return nullptr; }
   if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  DeviceGuard guard_(device);
+  if (guard_.err != cudaSuccess) { cuda_fail(guard_.err, "cudaSetDevice"); return nullptr; }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor)); return nullptr; }
@@ -100,7 +116,7 @@ hedit_engine* hedit_engine_create(const hedit_unet_config* cfg, int max_samples,
 
 void hedit_engine_destroy(hedit_engine* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard_(h->device);
   cudaFree(h->d_ctx_idx); cudaFree(h->d_tidx); cudaFree(h->d_unit0); cudaFree(h->d_unit1); cudaFree(h->d_uimg);
   delete h->E;
   delete h;
@@ -108,7 +124,7 @@ void hedit_engine_destroy(hedit_engine* h) {
 
 int hedit_engine_load_tensor(hedit_engine* h, const char* name, const float* data, const int64_t* dims, int ndim) {
   if (!h) return fail("null engine");
-  cudaSetDevice(h->device);
+  DeviceGuard guard_(h->device);
   const int r = h->E->load_tensor(name, data, dims, ndim, 0);
   if (r) return fail(h->E->error(), r);
   return 0;
@@ -126,7 +142,7 @@ double hedit_engine_flops_per_sample(hedit_engine* h) { return h ? h->E->flops_p
 
 int hedit_engine_blend_state_elems(hedit_engine* h, int B) {
   if (!h) return fail("null engine");
-  return B * 2 * h->E->n_blend_layers() * h->E->cfg().heads * 256;
+  return B * 4 * h->E->n_blend_layers() * h->E->cfg().heads * 256;      // sized for blend_rows = 4 (substruct words)
 }
 
 const char* hedit_operand_dtype(void) { return HEDIT_OPERAND_NAME; }
@@ -152,7 +168,7 @@ int hedit_engine_set_graph_replay(hedit_engine* h, int on) {
 
 int hedit_engine_profile_forward(hedit_engine* h, int S, int reps, char* out, int out_len) {
   if (!h) return fail("null engine");
-  cudaSetDevice(h->device);
+  DeviceGuard guard_(h->device);
   Engine& E = *h->E;
   if (S > h->cap) return fail("S exceeds max_samples");
   const size_t lat = size_t(E.latent_elems());
@@ -214,7 +230,7 @@ static int unet_forward_impl(hedit_engine* h, const float* x, const float* times
                              int S, float* eps, void* stream, hedit_attn_probs_fn probs_cb, void* probs_user,
                              hedit_attn_editor_fn editor_cb = nullptr, void* editor_user = nullptr) {
   if (!h) return fail("null engine");
-  cudaSetDevice(h->device);
+  DeviceGuard guard_(h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   Engine& E = *h->E;
   if (S > h->cap) return fail("S exceeds max_samples");
@@ -272,8 +288,8 @@ int hedit_unet_forward(hedit_engine* h, const float* x, const float* timesteps, 
 hedit_vae* hedit_vae_create(const hedit_vae_config* cfg, int device) {
   if (!cfg) { fail("null config"); return nullptr; }
   if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  DeviceGuard guard_(device);
+  if (guard_.err != cudaSuccess) { cuda_fail(guard_.err, "cudaSetDevice"); return nullptr; }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only"); return nullptr; }
@@ -291,13 +307,13 @@ hedit_vae* hedit_vae_create(const hedit_vae_config* cfg, int device) {
 }
 void hedit_vae_destroy(hedit_vae* v) {
   if (!v) return;
-  cudaSetDevice(v->device);
+  DeviceGuard guard_(v->device);
   delete v->D;
   delete v;
 }
 int hedit_vae_load_tensor(hedit_vae* v, const char* name, const float* data, const int64_t* dims, int ndim) {
   if (!v) return fail("null vae");
-  cudaSetDevice(v->device);
+  DeviceGuard guard_(v->device);
   const int r = v->D->load_tensor(name, data, dims, ndim, 0);
   if (r) return fail(v->D->error(), r);
   return 0;
@@ -320,13 +336,13 @@ int hedit_vae_tensor_info(hedit_vae* v, int index, char* name_buf, int name_len,
 }
 int hedit_vae_decode(hedit_vae* v, const float* z, float* img, int B, int h, int w, void* stream) {
   if (!v) return fail("null vae");
-  cudaSetDevice(v->device);
+  DeviceGuard guard_(v->device);
   if (v->D->decode(z, img, B, h, w, reinterpret_cast<cudaStream_t>(stream))) return fail(v->D->error());
   return int(v->D->launches());
 }
 int hedit_vae_decode_backward(hedit_vae* v, const float* dimg, float* dz, void* stream) {
   if (!v) return fail("null vae");
-  cudaSetDevice(v->device);
+  DeviceGuard guard_(v->device);
   if (v->D->backward(dimg, dz, reinterpret_cast<cudaStream_t>(stream))) return fail(v->D->error());
   return int(v->D->launches());
 }
@@ -335,8 +351,8 @@ double hedit_vae_last_flops(hedit_vae* v) { return v ? v->D->flops() : 0.0; }
 hedit_vae_enc* hedit_vae_enc_create(const hedit_vae_config* cfg, int device) {
   if (!cfg) { fail("null config"); return nullptr; }
   if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  DeviceGuard guard_(device);
+  if (guard_.err != cudaSuccess) { cuda_fail(guard_.err, "cudaSetDevice"); return nullptr; }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only"); return nullptr; }
@@ -354,13 +370,13 @@ hedit_vae_enc* hedit_vae_enc_create(const hedit_vae_config* cfg, int device) {
 }
 void hedit_vae_enc_destroy(hedit_vae_enc* v) {
   if (!v) return;
-  cudaSetDevice(v->device);
+  DeviceGuard guard_(v->device);
   delete v->E;
   delete v;
 }
 int hedit_vae_enc_load_tensor(hedit_vae_enc* v, const char* name, const float* data, const int64_t* dims, int ndim) {
   if (!v) return fail("null vae encoder");
-  cudaSetDevice(v->device);
+  DeviceGuard guard_(v->device);
   const int r = v->E->load_tensor(name, data, dims, ndim, 0);
   if (r) return fail(v->E->error(), r);
   return 0;
@@ -373,7 +389,7 @@ int hedit_vae_enc_finalize(hedit_vae_enc* v) {
 }
 int hedit_vae_encode(hedit_vae_enc* v, const float* img, float* moments, int B, int H, int W, void* stream) {
   if (!v) return fail("null vae encoder");
-  cudaSetDevice(v->device);
+  DeviceGuard guard_(v->device);
   if (v->E->encode(img, moments, B, H, W, reinterpret_cast<cudaStream_t>(stream))) return fail(v->E->error());
   return int(v->E->launches());
 }
@@ -382,8 +398,8 @@ int hedit_vae_encode(hedit_vae_enc* v, const float* img, float* moments, int B, 
 hedit_text* hedit_text_create(const hedit_text_config* cfg, int device) {
   if (!cfg) { fail("null config"); return nullptr; }
   if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  DeviceGuard guard_(device);
+  if (guard_.err != cudaSuccess) { cuda_fail(guard_.err, "cudaSetDevice"); return nullptr; }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only"); return nullptr; }
@@ -401,13 +417,13 @@ hedit_text* hedit_text_create(const hedit_text_config* cfg, int device) {
 }
 void hedit_text_destroy(hedit_text* t) {
   if (!t) return;
-  cudaSetDevice(t->device);
+  DeviceGuard guard_(t->device);
   delete t->T;
   delete t;
 }
 int hedit_text_load_tensor(hedit_text* t, const char* name, const float* data, const int64_t* dims, int ndim) {
   if (!t) return fail("null text encoder");
-  cudaSetDevice(t->device);
+  DeviceGuard guard_(t->device);
   const int r = t->T->load_tensor(name, data, dims, ndim, 0);
   if (r < 0) return fail(t->T->error(), r);
   return r;
@@ -420,7 +436,7 @@ int hedit_text_finalize(hedit_text* t) {
 }
 int hedit_text_encode(hedit_text* t, const int32_t* ids, int B, float* out, void* stream) {
   if (!t) return fail("null text encoder");
-  cudaSetDevice(t->device);
+  DeviceGuard guard_(t->device);
   if (t->T->forward(ids, B, out, reinterpret_cast<cudaStream_t>(stream))) return fail(t->T->error());
   return int(t->T->launches());
 }
@@ -429,8 +445,8 @@ int hedit_text_encode(hedit_text* t, const int32_t* ids, int B, float* out, void
 hedit_face* hedit_face_create(const hedit_face_config* cfg, int device) {
   if (!cfg) { fail("null config"); return nullptr; }
   if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  DeviceGuard guard_(device);
+  if (guard_.err != cudaSuccess) { cuda_fail(guard_.err, "cudaSetDevice"); return nullptr; }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only"); return nullptr; }
@@ -452,13 +468,13 @@ hedit_face* hedit_face_create(const hedit_face_config* cfg, int device) {
 }
 void hedit_face_destroy(hedit_face* f) {
   if (!f) return;
-  cudaSetDevice(f->device);
+  DeviceGuard guard_(f->device);
   delete f->U;
   delete f;
 }
 int hedit_face_load_tensor(hedit_face* f, const char* name, const float* data, const int64_t* dims, int ndim) {
   if (!f) return fail("null face engine");
-  cudaSetDevice(f->device);
+  DeviceGuard guard_(f->device);
   const int r = f->U->load_tensor(name, data, dims, ndim, 0);
   if (r) return fail(f->U->error(), r);
   return 0;
@@ -481,14 +497,14 @@ int hedit_face_tensor_info(hedit_face* f, int index, char* name_buf, int name_le
 }
 int hedit_face_unet_forward(hedit_face* f, const float* x, const float* t, int S, float* eps, void* stream) {
   if (!f) return fail("null face engine");
-  cudaSetDevice(f->device);
+  DeviceGuard guard_(f->device);
   if (f->U->forward(x, t, eps, S, reinterpret_cast<cudaStream_t>(stream))) return fail(f->U->error());
   return int(f->U->launches());
 }
 double hedit_face_last_flops(hedit_face* f) { return f ? f->U->flops() : 0.0; }
 int hedit_face_edit(hedit_face* f, hedit_face_args* args, void* stream) {
   if (!f || !args) return fail("null face engine / args");
-  cudaSetDevice(f->device);
+  DeviceGuard guard_(f->device);
   if (run_face_edit(*f->U, *args, reinterpret_cast<cudaStream_t>(stream))) return fail(f->U->error().empty() ? "face edit failed" : f->U->error());
   return 0;
 }
@@ -497,8 +513,8 @@ int hedit_face_edit(hedit_face* f, hedit_face_args* args, void* stream) {
 hedit_clip* hedit_clip_create(const hedit_clip_config* cfg, int device) {
   if (!cfg) { fail("null config"); return nullptr; }
   if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return nullptr; }
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  DeviceGuard guard_(device);
+  if (guard_.err != cudaSuccess) { cuda_fail(guard_.err, "cudaSetDevice"); return nullptr; }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only"); return nullptr; }
@@ -518,13 +534,13 @@ hedit_clip* hedit_clip_create(const hedit_clip_config* cfg, int device) {
 }
 void hedit_clip_destroy(hedit_clip* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard guard_(c->device);
   delete c->C;
   delete c;
 }
 int hedit_clip_load_tensor(hedit_clip* c, const char* name, const float* data, const int64_t* dims, int ndim) {
   if (!c) return fail("null clip");
-  cudaSetDevice(c->device);
+  DeviceGuard guard_(c->device);
   const int r = c->C->load_tensor(name, data, dims, ndim, 0);
   if (r < 0) return fail(c->C->error(), r);
   return r;
@@ -537,26 +553,26 @@ int hedit_clip_finalize(hedit_clip* c) {
 }
 int hedit_clip_set_reference(hedit_clip* c, const float* ref, void* stream) {
   if (!c) return fail("null clip");
-  cudaSetDevice(c->device);
+  DeviceGuard guard_(c->device);
   if (c->C->set_reference(ref, reinterpret_cast<cudaStream_t>(stream))) return fail(c->C->error());
   return 0;
 }
 int hedit_clip_gram_loss(hedit_clip* c, const float* img, int B, int H, int W, float* loss, void* stream) {
   if (!c) return fail("null clip");
-  cudaSetDevice(c->device);
+  DeviceGuard guard_(c->device);
   if (c->C->forward(img, B, H, W, loss, reinterpret_cast<cudaStream_t>(stream))) return fail(c->C->error());
   return int(c->C->launches());
 }
 int hedit_clip_gram_backward(hedit_clip* c, float* dimg, void* stream) {
   if (!c) return fail("null clip");
-  cudaSetDevice(c->device);
+  DeviceGuard guard_(c->device);
   if (c->C->backward(dimg, reinterpret_cast<cudaStream_t>(stream))) return fail(c->C->error());
   return int(c->C->launches());
 }
 
 int hedit_edit_p2p(hedit_engine* h, hedit_edit_args* args, void* stream) {
   if (!h || !args) return fail("null engine/args");
-  cudaSetDevice(h->device);
+  DeviceGuard guard_(h->device);
   const int r = run_edit(*h->E, *args, reinterpret_cast<cudaStream_t>(stream));
   if (r) {
     cudaError_t e = cudaGetLastError();
@@ -689,7 +705,7 @@ int hedit_op_cross_attention_p2p(const void* q, const void* kv, int S, int n_ctx
   a.out = reinterpret_cast<op_t*>(out); a.ldo = C;
   a.unit_s0 = unit_s0; a.unit_s1 = unit_s1; a.unit_img = unit_img; a.ctx_idx = ctx_idx; a.mapper = mapper; a.c_base = c_base; a.c_tar = c_tar;
   a.replace_m = replace_m; a.is_replace = is_replace; a.blend_acc = blend_acc; a.blend_alpha = blend_alpha; a.blend_layer = blend_layer;
-  a.n_blend_layers = n_blend_layers;
+  a.n_blend_layers = n_blend_layers; a.blend_rows = 2; a.map_w = nullptr; a.map_rows = 1;
   cudaError_t e = launch_cross_attn(a, dch, n_units, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "cross attention launch");
   return 0;

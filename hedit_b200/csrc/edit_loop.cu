@@ -79,7 +79,7 @@ static int finish_call(Engine& E, TempPool& tp, CallDesc& c, cudaStream_t st) {
 }
 
 struct LoopBuffers {
-  float *lat = 0, *eps = 0, *corr = 0, *xin = 0, *zs = 0, *blend_acc = 0, *c_base = 0, *c_tar = 0, *replace_m = 0, *blend_alpha = 0;
+  float *lat = 0, *eps = 0, *corr = 0, *xin = 0, *zs = 0, *blend_acc = 0, *c_base = 0, *c_tar = 0, *replace_m = 0, *blend_alpha = 0, *map_w = 0;
   float2* partial = 0;
   int *mapper = 0, *is_replace = 0, *has_blend = 0, *tidx = 0, *tidx_cur = 0;
   float *c_base_cur = 0, *c_tar_cur = 0;
@@ -94,7 +94,14 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   const bool p2p = a.use_p2p != 0 && a.variant == 0 && !masa;
   const bool pnp = a.pnp != 0;
   const bool ctrl = p2p || masa || pnp;   // launches C / BC / E run with attention control
-  const bool blend = p2p && a.has_blend != nullptr && a.blend_alpha != nullptr && E.n_blend_layers() > 0 && c.sample == 64;
+  const bool blend = p2p && a.has_blend != nullptr && a.blend_alpha != nullptr;
+  if (blend && (E.n_blend_layers() == 0 || c.sample != 64)) {
+    // LocalBlend reads the 16x16 cross-attention maps of a 64x64 latent (ptp_classes.py:54-58 reshapes to 16x16); any other geometry makes
+    // the reference fail in that reshape, so it is an error here too rather than a silently unblended edit
+    E.err_ = "LocalBlend needs a 64x64 latent with 16x16 cross-attention layers (ptp_classes.py:54-58)";
+    return -1;
+  }
+  const int brows = (blend && a.blend_rows == 4) ? 4 : 2;     // 4: LocalBlend substruct_words maps ride along
   const cudaMemcpyKind kIn = a.buffers_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const cudaMemcpyKind kOut = a.buffers_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (B < 1 || T < 1) { E.err_ = "bad batch/steps"; return -1; }
@@ -286,10 +293,15 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     CKE(cudaStreamSynchronize(st));
   }
   if (p2p) {
-    L.mapper = reinterpret_cast<int*>(tp.get(size_t(B) * 80 * sizeof(int)));
+    const int mrows = (a.map_w != nullptr && a.map_rows > 1) ? a.map_rows : 1;
+    L.mapper = reinterpret_cast<int*>(tp.get(size_t(B) * mrows * 80 * sizeof(int)));
+    if (a.map_w) {
+      L.map_w = fa(size_t(B) * mrows * 80);
+      CKE(cudaMemcpyAsync(L.map_w, a.map_w, size_t(B) * mrows * 80 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
     L.is_replace = reinterpret_cast<int*>(tp.get(size_t(B) * sizeof(int)));
     L.c_base = fa(size_t(T + 1) * B * 80); L.c_tar = fa(size_t(T + 1) * B * 80);
-    CKE(cudaMemcpyAsync(L.mapper, a.mapper, size_t(B) * 80 * sizeof(int), cudaMemcpyHostToDevice, st));
+    CKE(cudaMemcpyAsync(L.mapper, a.mapper, size_t(B) * mrows * 80 * sizeof(int), cudaMemcpyHostToDevice, st));
     CKE(cudaMemcpyAsync(L.is_replace, a.is_replace, size_t(B) * sizeof(int), cudaMemcpyHostToDevice, st));
     CKE(cudaMemcpyAsync(L.c_base, a.c_base, size_t(T + 1) * B * 80 * sizeof(float), cudaMemcpyHostToDevice, st));
     CKE(cudaMemcpyAsync(L.c_tar, a.c_tar, size_t(T + 1) * B * 80 * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -299,10 +311,10 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     }
     if (blend) {
       L.has_blend = reinterpret_cast<int*>(tp.get(size_t(B) * sizeof(int)));
-      L.blend_alpha = fa(size_t(B) * 2 * 80);
-      const size_t accn = size_t(B) * 2 * E.n_blend_layers() * c.heads * 256;
+      L.blend_alpha = fa(size_t(B) * brows * 80);
+      const size_t accn = size_t(B) * brows * E.n_blend_layers() * c.heads * 256;
       CKE(cudaMemcpyAsync(L.has_blend, a.has_blend, size_t(B) * sizeof(int), cudaMemcpyHostToDevice, st));
-      CKE(cudaMemcpyAsync(L.blend_alpha, a.blend_alpha, size_t(B) * 2 * 80 * sizeof(float), cudaMemcpyHostToDevice, st));
+      CKE(cudaMemcpyAsync(L.blend_alpha, a.blend_alpha, size_t(B) * brows * 80 * sizeof(float), cudaMemcpyHostToDevice, st));
       if (a.blend_state) {
         L.blend_acc = a.blend_state;               // caller-owned, carried across single-step calls
       } else {
@@ -341,10 +353,11 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     if (cd.p2p && p2p) {
       if (a.self_lo <= a.ctrl_step0 + ctrl_step && a.ctrl_step0 + ctrl_step < a.self_hi) { cc.self_mask = mask_small; cc.self_q = cd.d_sq; cc.self_k = cd.d_sq; cc.self_v = nullptr; }
       cc.mapper = L.mapper; cc.is_replace = L.is_replace; cc.replace_m = L.replace_m;
+      cc.map_w = L.map_w; cc.map_rows = (a.map_w != nullptr && a.map_rows > 1) ? a.map_rows : 1;
       CKE(cudaMemcpyAsync(L.c_base_cur, L.c_base + size_t(ctrl_step) * B * 80, size_t(B) * 80 * sizeof(float), cudaMemcpyDeviceToDevice, st));
       CKE(cudaMemcpyAsync(L.c_tar_cur, L.c_tar + size_t(ctrl_step) * B * 80, size_t(B) * 80 * sizeof(float), cudaMemcpyDeviceToDevice, st));
       cc.c_base = L.c_base_cur; cc.c_tar = L.c_tar_cur;
-      if (blend && save) { cc.blend_acc = L.blend_acc; cc.blend_alpha = L.blend_alpha; }
+      if (blend && save) { cc.blend_acc = L.blend_acc; cc.blend_alpha = L.blend_alpha; cc.blend_rows = brows; }
     } else if (cd.p2p && pnp) {
       if (a.pnp_qk_on[ctrl_step]) { cc.self_mask = a.pnp_self_mask; cc.self_q = cd.d_sq; cc.self_k = cd.d_sq; cc.self_v = nullptr; }
       if (a.pnp_feat_on[ctrl_step]) cc.feat_src = cd.d_sq;
@@ -434,6 +447,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     if (blend && (a.ctrl_step0 + i + 1) > a.start_blend) {
       BlendParams bp;
       bp.acc = L.blend_acc; bp.has_blend = L.has_blend; bp.L = E.n_blend_layers(); bp.H = c.heads; bp.th = a.blend_th;
+      bp.rows = brows; bp.th_sub = a.blend_th_sub;
       bp.xt = xt; bp.C = c.in_ch; bp.hh = c.sample; bp.ww = c.sample;
       local_blend_kernel<<<B, 256, 0, st>>>(bp);
       ++launches;

@@ -427,13 +427,13 @@ static cudaError_t launch_self2_t(const AttnParams& a, int S, cudaStream_t st) {
   self_attn2_kernel<DCH, NT, BKV, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
-template <int DCH, bool MMASUM, bool TWOPASS, int POLY16>
+template <int DCH, bool MMASUM, bool TWOPASS, int POLY16, bool PINGPONG = false>
 static cudaError_t launch_self3_t(const AttnParams& a, int S, cudaStream_t st) {
   using Cfg = SelfAttn2Cfg<DCH, 2, 64>;
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(self_attn3_kernel<DCH, MMASUM, TWOPASS, POLY16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
+  if (!set) { cudaFuncSetAttribute(self_attn3_kernel<DCH, MMASUM, TWOPASS, POLY16, PINGPONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
   dim3 grid((a.Nq + 255) / 256, a.H, S);
-  self_attn3_kernel<DCH, MMASUM, TWOPASS, POLY16><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  self_attn3_kernel<DCH, MMASUM, TWOPASS, POLY16, PINGPONG><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
 // tuning switch HEDIT_ATTN_V3 (self_attn3_kernel variants, head dims <= 128): 0 = round-1 kernel (self_attn2_kernel);
@@ -448,6 +448,12 @@ static cudaError_t launch_self3(const AttnParams& a, int S, cudaStream_t st) {
     case 4: return launch_self3_t<DCH, true, true, 3>(a, S, st);
     case 5: return launch_self3_t<DCH, true, true, 4>(a, S, st);
     case 6: return launch_self3_t<DCH, false, true, 3>(a, S, st);       // control: packed-add row sum kept
+    case 8: return launch_self3_t<DCH, false, false, 0, true>(a, S, st);  // round-1 arithmetic + ping-pong
+    case 9: return launch_self3_t<DCH, false, true, 0, true>(a, S, st);
+    case 10: return launch_self3_t<DCH, false, true, 2, true>(a, S, st);
+    case 11: return launch_self3_t<DCH, false, true, 3, true>(a, S, st);
+    case 12: return launch_self3_t<DCH, false, true, 4, true>(a, S, st);
+    case 13: return launch_self3_t<DCH, true, true, 3, true>(a, S, st);
     default: return launch_self3_t<DCH, true, false, 2>(a, S, st);      // 7: no two-pass, polynomial share (register-pressure control)
   }
 }
@@ -539,7 +545,7 @@ int Engine::set_contexts(const float* ctx, int n_ctx, cudaStream_t st) {
 }
 
 int Engine::set_timesteps(const float* ts, int n, cudaStream_t st) {
-  if (n > maxT_) { err_ = "too many timesteps"; return -1; }
+  if (n > maxT_) { err_ = "too many timesteps in one edit (limit " + std::to_string(maxT_ - 1) + " steps)"; return -1; }
   const int temb = cfg_.boc[0] * 4;
   CK(cudaMemcpyAsync(ts_dev_, ts, n * sizeof(float), cudaMemcpyDefault, st));
   float* a1 = temb_act_; float* a2 = temb_act_ + size_t(maxT_) * temb;
@@ -935,7 +941,8 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
       AttnParams a = op.attn;
       a.unit_s0 = cc.unit_s0; a.unit_s1 = cc.unit_s1; a.unit_img = cc.unit_img; a.ctx_idx = cc.ctx_idx;
       a.mapper = cc.mapper; a.c_base = cc.c_base; a.c_tar = cc.c_tar; a.replace_m = cc.replace_m; a.is_replace = cc.is_replace;
-      a.blend_alpha = cc.blend_alpha; a.n_blend_layers = n_blend_layers_;
+      a.map_w = cc.map_w; a.map_rows = cc.map_rows;
+      a.blend_alpha = cc.blend_alpha; a.n_blend_layers = n_blend_layers_; a.blend_rows = cc.blend_rows;
       a.blend_layer = op.blend_layer;
       a.blend_acc = (op.blend_layer >= 0) ? cc.blend_acc : nullptr;
       CK(launch_cross_attn(a, op.dch, cc.n_units, st));
@@ -1046,9 +1053,9 @@ long Engine::forward_replayed(const float* x, float* eps, int S, const CallCtrl&
   // identity of the launch: every pointer / flag the kernels' parameters are derived from, packed without struct padding
   std::vector<uint8_t> key;
   {
-    const void* ptrs[18] = {cc.ctx_idx, cc.time_idx, cc.self_q, cc.self_k, cc.self_v, cc.feat_src, cc.unit_s0, cc.unit_s1, cc.unit_img,
+    const void* ptrs[19] = {cc.map_w, cc.ctx_idx, cc.time_idx, cc.self_q, cc.self_k, cc.self_v, cc.feat_src, cc.unit_s0, cc.unit_s1, cc.unit_img,
                             cc.mapper, cc.c_base, cc.c_tar, cc.replace_m, cc.is_replace, cc.blend_acc, cc.blend_alpha, x, eps};
-    const int32_t ints[3] = {int32_t(cc.self_mask), cc.n_units, S};
+    const int32_t ints[5] = {int32_t(cc.self_mask), cc.n_units, S, cc.blend_rows, cc.map_rows};
     key.assign(reinterpret_cast<const uint8_t*>(ptrs), reinterpret_cast<const uint8_t*>(ptrs) + sizeof ptrs);
     key.insert(key.end(), reinterpret_cast<const uint8_t*>(ints), reinterpret_cast<const uint8_t*>(ints) + sizeof ints);
   }

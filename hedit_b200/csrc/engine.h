@@ -95,7 +95,8 @@ struct CallCtrl {
   int n_units = 0;
   const int* mapper = nullptr; const float* c_base = nullptr; const float* c_tar = nullptr;
   const float* replace_m = nullptr; const int* is_replace = nullptr;
-  float* blend_acc = nullptr; const float* blend_alpha = nullptr;
+  const float* map_w = nullptr; int map_rows = 1;
+  float* blend_acc = nullptr; const float* blend_alpha = nullptr; int blend_rows = 2;
   // compat path (compat_attn.cuh): materialised probabilities + host callback instead of the fused attention kernels
   AttnProbsFn probs_cb = nullptr; void* probs_user = nullptr;
   AttnEditorFn editor_cb = nullptr; void* editor_user = nullptr;
@@ -182,7 +183,7 @@ class Engine {
   float* temb_table_ = 0;       // [maxT][tproj_total]
   float* temb_rows_ = 0;        // [maxS][tproj_total] gathered per call
   float* ts_dev_ = 0;
-  int maxT_ = 128, nT_ = 0;
+  int maxT_ = 1008, nT_ = 0;      // timesteps per edit (incl. the final previous timestep): the full 1000-step training schedule fits (81 MB of fp32 time projections)
   bf16* ctx_bf16_ = 0;          // [max_ctx*77][ctx_dim]
   float* stage_ = 0; size_t stage_elems_ = 0;   // fp32 staging for weight upload
   std::map<int, std::unique_ptr<Plan>> plans_;

@@ -209,45 +209,56 @@ static __global__ void hstep_guid_update_kernel(const GuidUpdateParams p) {
 // LocalBlend (ptp_classes.py:44-72): one CTA per image.  acc holds, per (src|tar, layer, head, pixel), the running sum
 // over steps of sum_j blend_alpha_j * prob_j for the 16x16 cross-attention layers.
 struct BlendParams {
-  const float* acc;       // [B][2][L][H][256]
+  const float* acc;       // [B][rows][L][H][256]
   const int* has_blend;   // [B]
   int L, H;
-  float th;
+  int rows;               // 2, or 4 with substruct_words (rows 2,3 = word maps of the words to EXCLUDE)
+  float th, th_sub;       // LocalBlend.th[0] (pooled word mask), th[1] (un-pooled substruct mask)
   float* xt;              // [B][2][C][hh][ww]: row 1 (edit) is blended towards row 0 (orig)
   int C, hh, ww;
 };
 
+// LocalBlend.__call__ / get_mask (ptp_classes.py:44-72): word maps averaged over the 16x16 cross-attention layers and heads, 3x3 max-pool,
+// normalised by the map maximum, thresholded, source | target; with substruct_words the same without pooling at th[1], negated and ANDed.
 static __global__ void local_blend_kernel(const BlendParams p) {
   const int b = blockIdx.x;
   if (!p.has_blend[b]) return;
   __shared__ float m[2][256], pooled[2][256], red[2][256];
   __shared__ unsigned char mask16[256];
   const int t = threadIdx.x;     // 256 threads
-  for (int which = 0; which < 2; ++which) {
-    const float* a = p.acc + ((size_t(b) * 2 + which) * p.L * p.H) * 256 + t;
-    float s = 0.f;
-    for (int k = 0; k < p.L * p.H; ++k) s += a[size_t(k) * 256];
-    m[which][t] = s / float(p.L * p.H);
-  }
-  __syncthreads();
-  const int y = t >> 4, x = t & 15;
-  for (int which = 0; which < 2; ++which) {
-    float mx = -INFINITY;
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int yy = y + dy, xx = x + dx;
-        if (yy >= 0 && yy < 16 && xx >= 0 && xx < 16) mx = fmaxf(mx, m[which][yy * 16 + xx]);
+  const int rows = p.rows > 2 ? 4 : 2;
+  for (int pass = 0; pass < rows / 2; ++pass) {          // pass 0: blend words (pooled); pass 1: substruct words (not pooled)
+    for (int which = 0; which < 2; ++which) {
+      const float* a = p.acc + ((size_t(b) * rows + 2 * pass + which) * p.L * p.H) * 256 + t;
+      float s = 0.f;
+      for (int k = 0; k < p.L * p.H; ++k) s += a[size_t(k) * 256];
+      m[which][t] = s / float(p.L * p.H);
+    }
+    __syncthreads();
+    const int y = t >> 4, x = t & 15;
+    for (int which = 0; which < 2; ++which) {
+      float mx = m[which][t];
+      if (pass == 0) {
+        mx = -INFINITY;
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int yy = y + dy, xx = x + dx;
+            if (yy >= 0 && yy < 16 && xx >= 0 && xx < 16) mx = fmaxf(mx, m[which][yy * 16 + xx]);
+          }
       }
-    pooled[which][t] = mx;
-    red[which][t] = mx;
-  }
-  __syncthreads();
-  for (int o = 128; o; o >>= 1) {
-    if (t < o) { red[0][t] = fmaxf(red[0][t], red[0][t + o]); red[1][t] = fmaxf(red[1][t], red[1][t + o]); }
+      pooled[which][t] = mx;
+      red[which][t] = mx;
+    }
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+      if (t < o) { red[0][t] = fmaxf(red[0][t], red[0][t + o]); red[1][t] = fmaxf(red[1][t], red[1][t + o]); }
+      __syncthreads();
+    }
+    const float th = pass == 0 ? p.th : p.th_sub;
+    const bool on = ((pooled[0][t] / red[0][0]) > th) || ((pooled[1][t] / red[1][0]) > th);
+    if (pass == 0) mask16[t] = on; else mask16[t] = mask16[t] && !on;
     __syncthreads();
   }
-  mask16[t] = ((pooled[0][t] / red[0][0]) > p.th) || ((pooled[1][t] / red[1][0]) > p.th);
-  __syncthreads();
   const int n = p.C * p.hh * p.ww;
   float* x0 = p.xt + size_t(b) * 2 * n;
   float* x1 = x0 + n;

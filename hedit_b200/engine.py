@@ -314,11 +314,16 @@ class UNetEngine:
                 rm = np.ascontiguousarray(plan.replace_m)
                 keep.append(rm)
                 a.replace_m = rm.ctypes.data
+            if getattr(plan, "map_w", None) is not None:
+                mw = np.ascontiguousarray(plan.map_w, dtype=np.float32)
+                keep.append(mw)
+                a.map_w, a.map_rows = mw.ctypes.data, int(mw.shape[1])
             if not plan.has_blend.any():
                 a.has_blend = None
             a.self_lo, a.self_hi = plan.self_window
             a.self_max_tokens = 32 * 32
             a.start_blend, a.blend_th = plan.start_blend, plan.blend_th
+            a.blend_rows, a.blend_th_sub = int(plan.blend_alpha.shape[1]), float(getattr(plan, "blend_th_sub", plan.blend_th))
         a.edited, a.recon = edited.data_ptr(), recon.data_ptr()
         a.trace = tr.data_ptr() if tr is not None else None
         rc = self.lib.hedit_edit_p2p(self.handle, C.byref(a), self._stream())

@@ -14,6 +14,7 @@ ptp_classes.py:178,209-213).
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -27,8 +28,54 @@ PAD = 80          # token axis padded to a multiple of 16 for the tensor-core ti
 # ----------------------------------------------------------------------------------------------------------------
 # token bookkeeping
 # ----------------------------------------------------------------------------------------------------------------
+# Set-up results are pure functions of (tokenizer, strings): the per-image Python work of the reference's driver (tokeniser round trips,
+# the Needleman-Wunsch aligner; main_p2p.py:176-209) is memoised so that a serving loop pays it once per distinct prompt pair
+# (SURVEY 8f.3).  The memo lives ON the tokenizer object (an id()-keyed global table could be hit by a different tokenizer that reuses a
+# freed object's address); tokenizers that refuse attributes are simply not cached.
+def _memo(tokenizer) -> Optional[dict]:
+    m = getattr(tokenizer, "_hedit_setup_memo", None)
+    if m is None:
+        try:
+            m = {}
+            tokenizer._hedit_setup_memo = m
+        except Exception:
+            return None
+    if len(m) > 65536:
+        m.clear()
+    return m
+
+
+def clear_setup_cache(tokenizer=None) -> None:
+    """Forget memoised set-up results (of one tokenizer, or the aligner's global table)."""
+    if tokenizer is not None and getattr(tokenizer, "_hedit_setup_memo", None) is not None:
+        tokenizer._hedit_setup_memo.clear()
+    _align_tokens_cached.cache_clear()
+
+
+def _encode(tokenizer, text: str) -> tuple:
+    m = _memo(tokenizer)
+    key = ("enc", text)
+    if m is not None and key in m:
+        return m[key]
+    ids = tuple(int(t) for t in tokenizer.encode(text))
+    if m is not None:
+        m[key] = ids
+    return ids
+
+
 def get_word_inds(text: str, word_place: Union[int, str], tokenizer) -> np.ndarray:
     """Token positions (BOS-shifted) covered by a word of `text` (ptp_utils.py:297-315 semantics)."""
+    m = _memo(tokenizer)
+    key = ("inds", text, word_place)
+    if m is not None and key in m:
+        return m[key].copy()
+    out = _get_word_inds(text, word_place, tokenizer)
+    if m is not None:
+        m[key] = out
+    return out.copy()
+
+
+def _get_word_inds(text: str, word_place: Union[int, str], tokenizer) -> np.ndarray:
     words = text.split(" ")
     if isinstance(word_place, str):
         wanted = {i for i, w in enumerate(words) if w == word_place}
@@ -36,7 +83,7 @@ def get_word_inds(text: str, word_place: Union[int, str], tokenizer) -> np.ndarr
         wanted = {int(word_place)}
     if not wanted:
         return np.zeros(0, dtype=np.int64)
-    ids = tokenizer.encode(text)[1:-1]
+    ids = _encode(tokenizer, text)[1:-1]
     lens = [len(tokenizer.decode([t]).strip("#")) for t in ids]
     out, w, filled = [], 0, 0
     for pos, ln in enumerate(lens):
@@ -49,6 +96,11 @@ def get_word_inds(text: str, word_place: Union[int, str], tokenizer) -> np.ndarr
 
 
 def _align_tokens(x: Sequence[int], y: Sequence[int]) -> np.ndarray:
+    return _align_tokens_cached(tuple(int(v) for v in x), tuple(int(v) for v in y)).copy()
+
+
+@functools.lru_cache(maxsize=4096)
+def _align_tokens_cached(x: tuple, y: tuple) -> np.ndarray:
     """Global alignment (match +1, mismatch -1, gap 0; ties prefer gap-in-x, then gap-in-y, then diagonal --
     seq_aligner.py:60-109).  Returns for every position of y the aligned position of x, or -1."""
     nx, ny = len(x), len(y)
@@ -81,7 +133,7 @@ def _align_tokens(x: Sequence[int], y: Sequence[int]) -> np.ndarray:
 
 def get_refinement_mapper(prompts: Sequence[str], tokenizer, max_len: int = MAX_WORDS):
     """(mapper[1,77] int64, alphas[1,77]) for prompts = [src, tar] (seq_aligner.py:112-133)."""
-    xs, ys = tokenizer.encode(prompts[0]), tokenizer.encode(prompts[1])
+    xs, ys = _encode(tokenizer, prompts[0]), _encode(tokenizer, prompts[1])
     al = _align_tokens(xs, ys)
     mapper = np.zeros(max_len, dtype=np.int64)
     alphas = np.ones(max_len, dtype=np.float32)
@@ -159,21 +211,84 @@ class LocalBlend:
     """Holds LocalBlend's constants (ptp_classes.py:17-42); the mask itself is computed on the GPU by
     local_blend_kernel from the accumulated 16x16 cross-attention word maps."""
 
-    def __init__(self, prompts, num_steps, words, start_blend=0.2, th=(0.3, 0.3), tokenizer=None, device=None):
-        al = torch.zeros(len(prompts), 1, 1, 1, 1, MAX_WORDS)
-        for r, (prompt, ws) in enumerate(zip(prompts, words)):
-            for w in ([ws] if isinstance(ws, str) else ws):
-                al[r, :, :, :, :, torch.as_tensor(get_word_inds(prompt, w, tokenizer), dtype=torch.int64)] = 1
-        self.alpha_layers = al
-        self.substruct_layers = None
+    def __init__(self, prompts, num_steps, words, substruct_words=None, start_blend=0.2, th=(0.3, 0.3), tokenizer=None, device=None):
+        def layers(word_lists):
+            al = torch.zeros(len(prompts), 1, 1, 1, 1, MAX_WORDS)
+            for r, (prompt, ws) in enumerate(zip(prompts, word_lists)):
+                for w in ([ws] if isinstance(ws, str) else ws):
+                    al[r, :, :, :, :, torch.as_tensor(get_word_inds(prompt, w, tokenizer), dtype=torch.int64)] = 1
+            return al
+        self.alpha_layers = layers(words)
+        # words whose (un-pooled) attention region is EXCLUDED from the blend mask (ptp_classes.py:28-38,66-67)
+        self.substruct_layers = layers(substruct_words) if substruct_words is not None else None
         self.start_blend = int(start_blend * num_steps)
         self.counter = 0
         self.th = th
 
 
+class LazyAttentionStore(dict):
+    """`controller.attention_store` after an edit that ran on the FUSED path.  The fused attention kernels never write the (heads, N, M)
+    probability maps to memory, so the per-layer sums the reference's AttentionStore accumulates (ptp_classes.py:135-160) do not exist yet
+    when the sampler returns.  This dict fills itself on first access by replaying the same edit through the compat path (materialised
+    probabilities, compat.py) with a reset copy of the controller, so `attention_store[...]` / `get_average_attention()` observe what the
+    reference's controller would hold -- paid for only by callers that look."""
+
+    def __init__(self, fill):
+        super().__init__()
+        self._fill_fn = fill
+
+    def _fill(self):
+        fn, self._fill_fn = self._fill_fn, None
+        if fn is not None:
+            super().update(fn())
+
+    def __deepcopy__(self, memo):
+        return {}
+
+    def __getitem__(self, k):
+        self._fill()
+        return super().__getitem__(k)
+
+    def __contains__(self, k):
+        self._fill()
+        return super().__contains__(k)
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __len__(self):
+        self._fill()
+        return super().__len__()
+
+    def __bool__(self):
+        return len(self) > 0
+
+    def keys(self):
+        self._fill()
+        return super().keys()
+
+    def values(self):
+        self._fill()
+        return super().values()
+
+    def items(self):
+        self._fill()
+        return super().items()
+
+    def get(self, k, default=None):
+        self._fill()
+        return super().get(k, default)
+
+
 class EditController:
     """One image's P2P controller: Refine or Replace, optional Reweight equalizer, optional LocalBlend.
-    Carries the reference controllers' observable attributes (cur_step, cur_att_layer, num_att_layers, ...)."""
+    Carries the reference controllers' observable attributes (cur_step, cur_att_layer, num_att_layers, attention_store, ...).
+
+    The samplers COMPILE it into device tables for the fused attention kernels (compile_edit_plan); it is also a complete implementation
+    of the reference's controller call protocol on materialised probabilities -- `controller(attn, is_cross, place_in_unet, save_attn)`,
+    `step_callback(x_t)`, `between_steps()`, `get_average_attention()` (ptp_classes.py:91-160,189-232) -- which is what the compat path
+    drives when the attention maps themselves are wanted (see LazyAttentionStore)."""
 
     def __init__(self, prompts, num_steps, cross_replace_steps, self_replace_steps, is_replace, local_blend=None,
                  equalizer=None, tokenizer=None, device=None):
@@ -196,25 +311,130 @@ class EditController:
         self.num_att_layers = -1
         self.cur_step = 0
         self.cur_att_layer = 0
+        self.step_store = self._empty_store()
         self.attention_store: Dict[str, list] = {}
 
-    # reference-compatible no-ops on the fast path (state is advanced by the fused kernels / the sampler)
-    def step_callback(self, x_t):
-        return x_t
+    @staticmethod
+    def _empty_store():
+        return {f"{p}_{k}": [] for p in ("down", "mid", "up") for k in ("cross", "self")}
+
+    # ---- the reference's controller protocol on materialised probabilities (compat path) -----------------------------------------
+    def __call__(self, attn, is_cross: bool, place_in_unet: str, save_attn: bool):
+        """attn (2*n_prompts*heads... , N, M): only the text-conditioned half is touched (ptp_classes.py:91-107)."""
+        half = attn.shape[0] // 2
+        self.forward(attn[half:], is_cross, place_in_unet, save_attn)
+        if not save_attn:
+            return attn
+        self.cur_att_layer += 1
+        if self.cur_att_layer == self.num_att_layers:
+            self.cur_att_layer = 0
+            self.cur_step += 1
+            self.between_steps()
+        return attn
+
+    def forward(self, attn, is_cross: bool, place_in_unet: str, save_attn: bool):
+        """AttentionStore.forward + AttentionControlEdit.forward (ptp_classes.py:135-142,202-227), editing `attn` in place."""
+        if is_cross or self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1]:
+            heads = attn.shape[0] // self.batch_size
+            v = attn.view(self.batch_size, heads, *attn.shape[1:])
+            base, tar = v[0], v[1:]
+            if is_cross:
+                dev = attn.device
+                aw = self.cross_replace_alpha[self.cur_step].to(dev)
+                if self.is_replace:
+                    mapped = torch.einsum("hpw,bwn->bhpn", base, self.mapper.to(dev))
+                else:
+                    ra = self.alphas.to(dev)
+                    mapped = base[:, :, self.mapper.to(dev)].permute(2, 0, 1, 3) * ra + tar * (1 - ra)
+                if self.equalizer is not None:
+                    mapped = mapped * self.equalizer.to(dev)[:, None, None, :]
+                v[1:] = mapped * aw + (1 - aw) * tar
+            elif tar.shape[2] <= 32 ** 2:
+                v[1:] = base.unsqueeze(0).expand(tar.shape[0], *base.shape)
+        if save_attn and attn.shape[1] <= 32 ** 2:
+            # the reference stores a VIEW of the (edited) probabilities; the engine reuses its buffer per layer, hence the copy
+            self.step_store[f"{place_in_unet}_{'cross' if is_cross else 'self'}"].append(attn.clone())
+        return attn
 
     def between_steps(self):
-        return
+        """AttentionStore.between_steps (ptp_classes.py:144-150): fold the step's maps into the running sums."""
+        if not any(self.step_store.values()):
+            return
+        store = self.__dict__.get("attention_store")
+        if not store:
+            self.__dict__["attention_store"] = self.step_store
+        else:
+            for key, items in store.items():
+                for i in range(len(items)):
+                    items[i] += self.step_store[key][i]
+        self.step_store = self._empty_store()
+
+    def step_callback(self, x_t):
+        """AttentionControlEdit.step_callback -> LocalBlend.__call__ (ptp_classes.py:44-72,189-192) on torch tensors.  The fused loop
+        blends on the device itself (local_blend_kernel) and never calls this; with no maps stored yet it is the identity."""
+        lb = self.local_blend
+        store = self.__dict__.get("attention_store") or {}
+        if lb is None or not store.get("down_cross"):
+            return x_t
+        lb.counter += 1
+        if lb.counter <= lb.start_blend:
+            return x_t
+        maps = store["down_cross"][2:4] + store["up_cross"][:3]
+        nw = lb.alpha_layers.shape[-1]
+        maps = torch.cat([m.reshape(lb.alpha_layers.shape[0], -1, 1, 16, 16, nw) for m in maps], dim=1)
+
+        def word_mask(alpha, pool, th):
+            m = (maps * alpha.to(maps.device)).sum(-1).mean(1)
+            if pool:
+                m = torch.nn.functional.max_pool2d(m, (3, 3), (1, 1), padding=(1, 1))
+            m = torch.nn.functional.interpolate(m, size=x_t.shape[2:])
+            m = m / m.amax(dim=(2, 3), keepdim=True)
+            m = m.gt(th)
+            return m[:1] + m
+
+        mask = word_mask(lb.alpha_layers, True, lb.th[0])
+        if lb.substruct_layers is not None:
+            mask = mask * ~word_mask(lb.substruct_layers, False, lb.th[1])
+        return x_t[:1] + mask.float() * (x_t - x_t[:1])
+
+    def get_average_attention(self):
+        """AttentionStore.get_average_attention (ptp_classes.py:152-154)."""
+        return {key: [item / self.cur_step for item in items] for key, items in self.attention_store.items()}
 
     def reset(self):
         self.cur_step = 0
         self.cur_att_layer = 0
+        self.step_store = self._empty_store()
         self.attention_store = {}
+        if self.local_blend is not None:
+            self.local_blend.counter = 0
+
+
+def attach_lazy_store(controller, replay) -> None:
+    """After a fused-path edit: `controller.attention_store` becomes a dict that materialises itself on first access by calling
+    `replay(fresh_controller)` (the compat-path run of the same edit) with a reset deep copy of `controller`."""
+    import copy
+
+    def fill():
+        twin = copy.deepcopy(controller)
+        if hasattr(twin, "reset"):
+            twin.reset()
+        c = twin
+        while c is not None:                                  # the reference's reset() leaves LocalBlend's counter alone
+            if getattr(c, "local_blend", None) is not None:
+                c.local_blend.counter = 0
+            c = getattr(c, "prev_controller", None)
+        replay(twin)
+        return dict(twin.attention_store)
+
+    controller.attention_store = LazyAttentionStore(fill)
 
 
 def make_controller(prompts: List[str], is_replace_controller: bool, cross_replace_steps, self_replace_steps,
-                    blend_word=None, equilizer_params=None, num_steps=None, tokenizer=None, device=None) -> EditController:
-    """Same signature as the reference's make_controller (ptp_controller_utils.py:106-133)."""
-    lb = LocalBlend(prompts, num_steps, blend_word, tokenizer=tokenizer, device=device) if blend_word is not None else None
+                    blend_word=None, equilizer_params=None, num_steps=None, tokenizer=None, device=None, substruct_words=None) -> EditController:
+    """Same signature as the reference's make_controller (ptp_controller_utils.py:106-133); `substruct_words` (optional, like blend_word:
+    one word list per prompt) is forwarded to LocalBlend, which the reference's helper leaves at None."""
+    lb = LocalBlend(prompts, num_steps, blend_word, substruct_words=substruct_words, tokenizer=tokenizer, device=device) if blend_word is not None else None
     eq = None
     if equilizer_params is not None:
         eq = get_equalizer(prompts[1], equilizer_params["words"], equilizer_params["values"], tokenizer)
@@ -237,16 +457,18 @@ class EditPlan:
     """Per-batch device tables (host numpy, uploaded by the C ABI)."""
     B: int
     steps: int
-    mapper: np.ndarray        # (B,80) int32, clamped
+    mapper: np.ndarray        # (B,80) int32, clamped; (B,R,80) with map_w
     is_replace: np.ndarray    # (B,) int32
     replace_m: Optional[np.ndarray]   # (B,77,80) float32 or None
     c_base: np.ndarray        # (steps+1,B,80)
     c_tar: np.ndarray         # (steps+1,B,80)
     self_window: Tuple[int, int]
     has_blend: np.ndarray     # (B,) int32
-    blend_alpha: np.ndarray   # (B,2,80)
+    blend_alpha: np.ndarray   # (B,2,80), or (B,4,80) with substruct words (rows 2,3)
     start_blend: int
     blend_th: float
+    blend_th_sub: float = 0.3
+    map_w: Optional[np.ndarray] = None   # (B,R,80) float32: sparse form of the replacement mappers (non-zeros per column), None for all-Refine batches
 
 
 def _flatten(ctrl):
@@ -267,7 +489,8 @@ def compile_edit_plan(controllers: Sequence, steps: int) -> EditPlan:
     c_base = np.zeros((steps + 1, B, PAD), dtype=np.float32)
     c_tar = np.zeros((steps + 1, B, PAD), dtype=np.float32)
     has_blend = np.zeros(B, dtype=np.int32)
-    blend_alpha = np.zeros((B, 2, PAD), dtype=np.float32)
+    has_sub = any(getattr(getattr(c, "local_blend", None), "substruct_layers", None) is not None for c in controllers)
+    blend_alpha = np.zeros((B, 4 if has_sub else 2, PAD), dtype=np.float32)
     windows, starts, ths = set(), set(), set()
     for b, c in enumerate(controllers):
         aw = torch.as_tensor(c.cross_replace_alpha).reshape(-1, MAX_WORDS).float().cpu().numpy()   # (T+1,77)
@@ -294,14 +517,33 @@ def compile_edit_plan(controllers: Sequence, steps: int) -> EditPlan:
         windows.add(tuple(int(v) for v in c.num_self_replace))
         lb = getattr(c, "local_blend", None)
         if lb is not None:
-            if getattr(lb, "substruct_layers", None) is not None:
-                raise NotImplementedError("LocalBlend substruct_words are not supported on the fused path")
             has_blend[b] = 1
-            blend_alpha[b, :, :MAX_WORDS] = torch.as_tensor(lb.alpha_layers).reshape(2, MAX_WORDS).float().cpu().numpy()
+            blend_alpha[b, :2, :MAX_WORDS] = torch.as_tensor(lb.alpha_layers).reshape(2, MAX_WORDS).float().cpu().numpy()
+            if getattr(lb, "substruct_layers", None) is not None:
+                blend_alpha[b, 2:, :MAX_WORDS] = torch.as_tensor(lb.substruct_layers).reshape(2, MAX_WORDS).float().cpu().numpy()
             starts.add(int(lb.start_blend))
-            ths.add(float(lb.th[0]))
+            ths.add((float(lb.th[0]), float(lb.th[1])))
     if len(windows) > 1 or len(starts) > 1 or len(ths) > 1:
         raise ValueError("all images of one batch must share the self-replace window and LocalBlend start/threshold")
-    return EditPlan(B=B, steps=steps, mapper=mapper, is_replace=is_rep, replace_m=rep_m, c_base=c_base, c_tar=c_tar,
+    map_w = None
+    if rep_m is not None:
+        # sparse form of the replacement mappers: per target token j the source tokens w with M[w, j] != 0 (the matrix is the identity except
+        # for the word-aligned blocks of the swapped words, seq_aligner.py:157-190), in increasing w -- the kernels then gather R <= 4 values
+        # per column instead of multiplying by the dense 77x77 matrix; Refine images ride along as (mapper[j], 1), padded with weight 0
+        R = max(1, int((rep_m[:, :, :MAX_WORDS] != 0).sum(axis=1).max()))
+        if R <= 4:
+            mp = np.zeros((B, R, PAD), dtype=np.int32)
+            map_w = np.zeros((B, R, PAD), dtype=np.float32)
+            for b in range(B):
+                if is_rep[b]:
+                    for j in range(MAX_WORDS):
+                        nz = np.nonzero(rep_m[b, :, j])[0]
+                        mp[b, :len(nz), j] = nz
+                        map_w[b, :len(nz), j] = rep_m[b, nz, j]
+                else:
+                    mp[b, 0], map_w[b, 0, :MAX_WORDS] = mapper[b], 1.0
+            mapper = mp
+    return EditPlan(B=B, steps=steps, mapper=mapper, map_w=map_w, is_replace=is_rep, replace_m=rep_m, c_base=c_base, c_tar=c_tar,
                     self_window=next(iter(windows)) if windows else (0, 0), has_blend=has_blend, blend_alpha=blend_alpha,
-                    start_blend=next(iter(starts)) if starts else 0, blend_th=next(iter(ths)) if ths else 0.3)
+                    start_blend=next(iter(starts)) if starts else 0, blend_th=next(iter(ths))[0] if ths else 0.3,
+                    blend_th_sub=next(iter(ths))[1] if ths else 0.3)

@@ -40,13 +40,53 @@ def encode_text(model, prompts: Union[str, List[str]]) -> torch.Tensor:
         return model.text_encoder(tok.input_ids.to(model.device))[0]
 
 
-def get_engine(model, max_samples: int = 5, device: int = 0) -> UNetEngine:
+def encode_prompts(model, prompts: List[str]) -> torch.Tensor:
+    """encode_text for a whole batch in ONE tokenizer call and ONE text-tower launch: identical strings (the unconditional "" of every
+    image, repeated source prompts) are encoded once.  Returns (len(prompts), 77, D) in prompt order."""
+    uniq = list(dict.fromkeys(prompts))
+    emb = encode_text(model, uniq)
+    if len(uniq) == len(prompts):
+        return emb
+    pos = {p: k for k, p in enumerate(uniq)}
+    return emb[torch.as_tensor([pos[p] for p in prompts], device=emb.device)]
+
+
+def _device_index(t: torch.Tensor, default: int = 0) -> int:
+    return t.device.index if (t.is_cuda and t.device.index is not None) else default
+
+
+def get_engine(model, max_samples: int = 5, device: Optional[int] = None) -> UNetEngine:
     """One persistent engine per pipeline object (replaces the per-image deepcopy at main_p2p.py:119)."""
     eng = getattr(model, "_hedit_b200_engine", None)
-    if eng is None or eng.max_samples < max_samples:
+    if device is None:                      # keep the engine's device; a first engine goes where the pipeline lives
+        mdev = getattr(model, "device", None)
+        device = eng.device if eng is not None else (torch.device(mdev).index or 0 if mdev is not None and torch.device(mdev).type == "cuda" else 0)
+    key = _weights_fingerprint(model.unet)
+    if eng is None or eng.max_samples < max_samples or eng.device != device or getattr(model, "_hedit_b200_engine_key", key) != key:
         eng = UNetEngine.from_unet(model.unet, max_samples=max_samples, max_contexts=max(8, 1 + 2 * (max_samples // 5 + 1)), device=device)
         model._hedit_b200_engine = eng
+    model._hedit_b200_engine_key = key
     return eng
+
+
+def _weights_fingerprint(unet):
+    """Cheap identity of the weights an engine was built from: the module object plus the in-place version counters of its parameters
+    (load_state_dict, LoRA merges and optimizer steps bump them), so a changed `model.unet` is re-ingested instead of silently ignored
+    (the reference always runs the live module).  `invalidate_engines(model)` forces it."""
+    params = getattr(unet, "parameters", None)
+    if params is None:
+        return (id(unet),)
+    try:
+        return (id(unet),) + tuple(int(p._version) for p in params())
+    except Exception:
+        return (id(unet),)
+
+
+def invalidate_engines(model) -> None:
+    """Drop the native engines cached on a pipeline object (after swapping or editing `model.unet`, `text_encoder` or `vae`)."""
+    for k in ("_hedit_b200_engine", "_hedit_b200_engine_key", "_hedit_b200_text", "_hedit_b200_vae", "_hedit_b200_face"):
+        if hasattr(model, k):
+            delattr(model, k)
 
 
 def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Sequence[Sequence[str]], cfg_scales, controllers,
@@ -57,16 +97,25 @@ def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Se
     controllers[b] = P2P controller of image b (ours or the reference's) or None for all (P2P off)."""
     B = xT.shape[0]
     steps = after_skip_steps if after_skip_steps is not None else model.scheduler.num_inference_steps
-    eng = engine or get_engine(model, max_samples=5 * B)
-    ctx = [encode_text(model, [""])]
+    eng = engine or get_engine(model, max_samples=5 * B, device=_device_index(xT, None) if xT.is_cuda else None)
+    flat = [""]
     for src, tar in prompt_pairs:
-        ctx.append(encode_text(model, [src, tar]))
-    ctx = torch.cat(ctx).float()
-    ctx = ctx.cpu() if not xT.is_cuda else ctx.to(xT.device)
+        flat += [src, tar]
+    ctx = encode_prompts(model, flat).float()        # stays where the text tower left it (the C ABI accepts a context pointer on either side)
+    if xT.is_cuda:
+        ctx = ctx.to(xT.device)
     ts, coef = step_tables(model.scheduler, steps, eta, is_ddim_inversion)
     plan = None
-    if controllers is not None and all(c is not None for c in controllers):
-        plan = compile_edit_plan(controllers, steps)
+    if controllers is not None:
+        from .compat import controller_kind
+        kinds = [controller_kind(c) for c in controllers]
+        if any(k == "custom" for k in kinds):
+            raise NotImplementedError("h_edit_p2p_batch compiles the stock P2P controllers only; a controller object with its own hooks "
+                                      "(controller_kind() == 'custom') is served per image by h_Edit_p2p_implicit (compat path)")
+        if any(k == "stock" for k in kinds):
+            if not all(k == "stock" for k in kinds):
+                raise ValueError("controllers mixes P2P controllers with None / passive stores: split the batch")
+            plan = compile_edit_plan(controllers, steps)
     out = eng.edit(xT, zs[:, :steps], ctx, ts, coef, cfg_scales, plan, weight_reconstruction, optimization_steps, explicit_form, schedule, trace,
                    variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp, pre_coeff=pre_coeff, guidance=guidance)
     if plan is not None:
@@ -88,6 +137,10 @@ def _single(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstr
     # promises the reference's call protocol and is served by the compat path (materialised probabilities, compat.py)
     from .compat import controller_kind, h_edit_p2p_implicit_compat
     kind = controller_kind(controller)
+    if kind == "none" and controller is not None and variant == 0 and masactrl is None and pnp is None and not explicit_form:
+        # a bare AttentionStore handed to the P2P sampler: the reference would fill its attention_store (ptp_classes.py:135-160); the fused
+        # path never materialises maps, so it is served by the compat path like any other object with observable state
+        kind = "custom"
     if kind == "custom":
         if explicit_form or variant != 0 or masactrl is not None or pnp is not None:
             raise NotImplementedError("custom controller objects are served on the implicit h-Edit + P2P sampler only (compat path)")
@@ -96,9 +149,15 @@ def _single(model, xT, eta, prompts, cfg_scales, zs, controller, weight_reconstr
         return edited.to(dev), recon.to(dev)
     ctrl = [controller] if kind == "stock" else None
     use_cuda = torch.device(dev).type == "cuda"
-    x, z = (x.cuda(), z.cuda()) if use_cuda else (x.cpu(), z.cpu())
+    x, z = (x, z.to(dev)) if use_cuda else (x.cpu(), z.cpu())
     edited, recon = h_edit_p2p_batch(model, x, z, [prompts[:2]], cfg_scales, ctrl, eta, weight_reconstruction, optimization_steps, steps,
                                      is_ddim_inversion, explicit_form, variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp, pre_coeff=pre_coeff)
+    if kind == "stock" and not explicit_form:
+        # observable controller state (SURVEY 8b ii): the maps the reference's AttentionStore would hold are materialised on first access
+        from .p2p import attach_lazy_store
+        xT_c, zs_c, prompts_c, cfgs_c = xT.detach().clone(), zs[:steps].detach().clone(), list(prompts[:2]), list(cfg_scales)
+        attach_lazy_store(controller, lambda twin: h_edit_p2p_implicit_compat(model, xT_c, eta, prompts_c, cfgs_c, zs_c, twin, weight_reconstruction,
+                                                                              optimization_steps, steps, is_ddim_inversion))
     return edited.to(dev), recon.to(dev)
 
 
@@ -246,12 +305,12 @@ def h_Edit_PnP_implicit(model, xT, eta=0, prompts="", cfg_scales=None, prog_bar=
     qk_on, feat_on = pnp_step_flags(model, after_skip_steps)
     L = getattr(getattr(model.unet, "cfg", None), "layers_per_block", 2)
     B = 1
-    eng = get_engine(model, max_samples=5 * B)
     dev = xT.device
+    eng = get_engine(model, max_samples=5 * B, device=_device_index(xT, None) if xT.is_cuda else None)
     x = xT.reshape(1, *xT.shape[-3:])
     z = zs[:after_skip_steps].reshape(1, after_skip_steps, *xT.shape[-3:])
     use_cuda = torch.device(dev).type == "cuda"
-    x, z = (x.cuda(), z.cuda()) if use_cuda else (x.cpu(), z.cpu())
+    x, z = (x, z.to(dev)) if use_cuda else (x.cpu(), z.cpu())
     edited, recon = h_edit_p2p_batch(model, x, z, [prompts[:2]], cfg_scales, None, eta, 0.0, optimization_steps, after_skip_steps,
                                      is_ddim_inversion, False, schedule=schedule, engine=eng, mos_pull=False,
                                      pnp=(pnp_self_mask(L), qk_on, feat_on))

@@ -87,6 +87,10 @@ class DDIMTables:
         self.config = DDIMTables._Cfg()
         self.config.num_train_timesteps = num_train_timesteps
         self.config.steps_offset = steps_offset
+        self.set_timesteps(num_inference_steps)
+
+    def set_timesteps(self, num_inference_steps: int, device=None) -> None:
+        """diffusers DDIMScheduler.set_timesteps with timestep_spacing="leading" (what the reference calls at main_p2p.py:148)."""
         self.num_inference_steps = num_inference_steps
-        ratio = num_train_timesteps // num_inference_steps
-        self.timesteps = (torch.arange(0, num_inference_steps) * ratio).round().flip(0).to(torch.int64) + steps_offset
+        ratio = self.config.num_train_timesteps // num_inference_steps
+        self.timesteps = (torch.arange(0, num_inference_steps) * ratio).round().flip(0).to(torch.int64) + self.config.steps_offset

@@ -138,9 +138,15 @@ def h_Edit_p2p_implicit(model, image_encoder, xT, eta=1.0, prompts="", cfg_scale
     """Reference signature (text-guided-n-style/inversion/h_edit.py:14).  Returns (edited, reconstructed), each (1,C,h,w)."""
     assert len(prompts) >= 2, "only support prompt editing"
     dev = xT.device
-    x = xT.reshape(1, *xT.shape[-3:]).cuda()
-    z = zs[:after_skip_steps].reshape(1, after_skip_steps, *xT.shape[-3:]).cuda()
-    ctrl = [controller] if (controller is not None and hasattr(controller, "cross_replace_alpha")) else None
+    cdev = dev if dev.type == "cuda" else torch.device("cuda", 0)
+    x = xT.reshape(1, *xT.shape[-3:]).to(cdev)
+    z = zs[:after_skip_steps].reshape(1, after_skip_steps, *xT.shape[-3:]).to(cdev)
+    from .compat import controller_kind
+    kind = controller_kind(controller)
+    if kind == "custom":
+        raise NotImplementedError("the style sampler compiles the stock P2P controllers only (controller_kind() == 'custom': a user class "
+                                  "with its own hooks); wrap the edit with hedit_b200.h_Edit_p2p_implicit's compat path instead")
+    ctrl = [controller] if kind == "stock" else None
     edited, recon = h_edit_style_batch(model, image_encoder, x, z, [prompts[:2]], cfg_scales, ctrl, eta, weight_edit_clip, optimization_steps,
                                        after_skip_steps, is_ddim_inversion, autocast=autocast, native_vae=native_vae, native_clip=native_clip)
     return edited.to(dev), recon.to(dev)

@@ -64,7 +64,11 @@ typedef struct hedit_edit_args {
   float weight_reconstruction;
   /* ---- Prompt-to-Prompt tables (host pointers); use_p2p = 0 runs every UNet call with use_controller=False */
   int32_t use_p2p;
-  const int32_t* mapper;     /* [B][80]  AttentionRefine.mapper (clamped to [0,77)) */
+  const int32_t* mapper;     /* [B][map_rows][80]  source-token index lists: row 0 = AttentionRefine.mapper (clamped to [0,77)) */
+  const float* map_w;        /* [B][map_rows][80] or NULL: weights of those indices.  With map_w the cross edit's base term is
+                                sum_k map_w[k][j] * P_src[mapper[k][j]]: the non-zeros of AttentionReplace's 77x77 mapper, column by column
+                                (seq_aligner.py:157-190: 1-3 per column), instead of the dense product with replace_m */
+  int32_t map_rows;          /* R (<= 4 served from shared memory); 0 / 1 without map_w */
   const int32_t* is_replace; /* [B]      1: AttentionReplace matrix form */
   const float* replace_m;    /* [B][77][80] or NULL */
   const float* c_base;       /* [steps+1][B][80]  coefficient on the mapped source probability at controller step s */
@@ -72,9 +76,11 @@ typedef struct hedit_edit_args {
   int32_t self_lo, self_hi;  /* AttentionControlEdit.num_self_replace */
   int32_t self_max_tokens;   /* 32*32 (ptp_classes.py:196) */
   const int32_t* has_blend;  /* [B] or NULL */
-  const float* blend_alpha;  /* [B][2][80]  LocalBlend.alpha_layers */
+  const float* blend_alpha;  /* [B][blend_rows][80]  rows 0,1 = LocalBlend.alpha_layers (src, tar); rows 2,3 = substruct_layers */
   int32_t start_blend;       /* LocalBlend.start_blend */
-  float blend_th;            /* LocalBlend.th */
+  float blend_th;            /* LocalBlend.th[0]: threshold of the max-pooled word mask */
+  int32_t blend_rows;        /* 0 / 2: no substruct_words; 4: mask *= ~mask(substruct word maps, no pooling, th[1]) (ptp_classes.py:28-38,66-67) */
+  float blend_th_sub;        /* LocalBlend.th[1] */
   /* ---- MasaCtrl mutual self-attention (masactrl/masactrl.py:11-69).  masa = 1: in the c-th attention-controlled UNet launch of this
    * call (the editor's cur_step advances once per controlled launch, masactrl_utils.py:15-23, i.e. steps * opt_steps launches in the
    * implicit form) the edit samples attend to the K/V of their source samples in the transformer blocks of masa_layer_mask

@@ -57,6 +57,8 @@ CASES = {
     "tiny_replace_mos2": (UNetConfig.tiny(sample_size=64), 6, 2, True, True),
     "tiny_refine_noblend": (UNetConfig.tiny(sample_size=64), 6, 1, False, False),
     "sd15_config1": (UNetConfig.sd15(), 10, 1, False, True),
+    # LocalBlend with substruct_words (ptp_classes.py:28-38,66-67): the region of "branch" is excluded from the blend mask
+    "tiny_refine_blend_substruct": (UNetConfig.tiny(sample_size=64), 6, 1, False, True),
     # BASELINE.json configs[1] (the headline): full SD-1.5 geometry, T = 50; two images with different prompts / controllers / noise
     # (Refine + Reweight + LocalBlend, and Replace + Reweight + LocalBlend) that the GPU test runs inside ONE mixed batch of 8
     "sd15_config2_T50_refine_blend": (UNetConfig.sd15(), 50, 1, False, True),
@@ -71,6 +73,9 @@ CASES = {
 CASE_INPUTS = {
     "sd15_config2_T50_replace": (["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"], ("cat", "dog"), 1),
 }
+
+
+SUBSTRUCT = {"tiny_refine_blend_substruct": (("branch",), ("branch",))}
 
 
 def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
@@ -93,6 +98,9 @@ def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
     controller = ref.ptp_controller_utils.make_controller(
         prompts=PROMPTS, is_replace_controller=is_replace, cross_replace_steps=xa, self_replace_steps=sa,
         blend_word=blend_word, equilizer_params=eq, num_steps=T, tokenizer=model.tokenizer, device=model.device)
+    substruct = SUBSTRUCT.get(name)
+    if substruct is not None:      # the reference's make_controller never passes substruct_words; its LocalBlend class takes them
+        controller.local_blend = ref.ptp_classes.LocalBlend(PROMPTS, T, blend_word, substruct_words=substruct, tokenizer=model.tokenizer, device=model.device)
     ref.ptp_utils.register_attention_control(model, controller)
     trace = []
     orig_cb = controller.step_callback
@@ -111,7 +119,7 @@ def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
     t_edit = time.time() - t0
     enc = ref.inversion_utils.encode_text
     out = {
-        "meta": dict(name=name, T=T, K=K, is_replace=is_replace, blend=blend, xa=xa, sa=sa, prompts=PROMPTS,
+        "meta": dict(name=name, T=T, K=K, is_replace=is_replace, blend=blend, xa=xa, sa=sa, prompts=PROMPTS, substruct_words=substruct,
                      blend_words=BLEND, cfg_scales=[1.0, 5.0, 7.5], eta=1.0, weight_reconstruction=0.1,
                      unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
                                cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),

@@ -116,3 +116,63 @@ def test_custom_editor_through_masactrl_sampler_matches_reference_golden():
     plain = lambda layer, is_cross, place, q, k, v, sim, attn, heads: UserMutualSelfAttention._merge(torch.bmm(torch.softmax(sim, -1), v), heads)
     r, _ = rel_err(eng.forward_editor(x, 301.0, ctx, plain), eng.forward(x, 301.0, ctx))
     assert r < 3e-3, r
+
+
+def test_attention_store_is_materialised_lazily_after_a_fused_edit():
+    """after an edit on the FUSED path the stock controller's `attention_store` / `get_average_attention()` must hold
+    what the reference's AttentionStore would (ptp_classes.py:135-160).  The fused kernels never write the maps, so the store fills
+    itself on first access by replaying the edit through the compat path; it must equal the store a user-side protocol controller
+    accumulates when it drives the same edit itself."""
+    g = load_golden("tiny_refine_blend")
+    meta = g["meta"]
+    model = _model(meta)
+    bw = meta["blend_words"]
+    mk = lambda: hedit_b200.make_controller(meta["prompts"], False, meta["xa"], meta["sa"], blend_word=((bw[0],), (bw[1],)),
+                                            equilizer_params={"words": (bw[1],), "values": (2.0,)}, num_steps=meta["T"], tokenizer=model.tokenizer)
+    kw = dict(eta=meta["eta"], prompts=meta["prompts"], cfg_scales=meta["cfg_scales"], zs=g["zs"].cuda(), weight_reconstruction=meta["weight_reconstruction"],
+              optimization_steps=meta["K"], after_skip_steps=meta["T"], is_ddim_inversion=False)
+    stock = mk()
+    assert hedit_b200.controller_kind(stock) == "stock"
+    ed, rc = hedit_b200.h_Edit_p2p_implicit(model, g["xT"].cuda(), controller=stock, **kw)
+    assert hedit_b200.get_engine(model).last_stats["sample_forwards"] == 7 * meta["T"]        # ran fused (exact-reuse schedule)
+    assert stock.cur_step == meta["T"]
+    user = UserController(mk(), "cuda")
+    hedit_b200.h_Edit_p2p_implicit(model, g["xT"].cuda(), controller=user, **kw)
+    store = stock.attention_store                       # first access: replay through the compat path
+    assert set(store.keys()) == set(user.attention_store.keys())
+    for key, items in user.attention_store.items():
+        assert len(store[key]) == len(items), key
+        for a, b in zip(store[key], items):
+            assert a.shape == b.shape and rel_err(a, b)[0] < 1e-5, key
+    avg = stock.get_average_attention()
+    assert rel_err(avg["down_cross"][0], user.attention_store["down_cross"][0] / meta["T"])[0] < 1e-5
+    assert len(store["down_cross"]) == 4 and len(store["up_cross"]) == 6 and len(store["mid_self"]) == 1
+
+
+def test_bare_attention_store_passed_to_the_p2p_sampler_is_filled():
+    """A passive store handed to h_Edit_p2p_implicit (no edit tables) must not be silently ignored: it is served by the compat path and
+    ends up holding the maps (the reference fills it in call C, p2p_h_edit.py:652)."""
+    g = load_golden("tiny_refine_noblend")
+    meta = g["meta"]
+    model = _model(meta)
+
+    class AttentionStore:               # user-side passive recorder with the reference's class name and protocol
+        def __init__(self):
+            self.num_att_layers, self.cur_att_layer, self.cur_step, self.maps = -1, 0, 0, 0
+
+        def __call__(self, attn, is_cross, place, save_attn):
+            self.maps += int(save_attn and attn.shape[1] <= 32 ** 2)
+            self.cur_att_layer += 1
+            if self.cur_att_layer == self.num_att_layers:
+                self.cur_att_layer, self.cur_step = 0, self.cur_step + 1
+            return attn
+
+        def step_callback(self, x):
+            return x
+
+    store = AttentionStore()
+    ed, rc = hedit_b200.h_Edit_p2p_implicit(model, g["xT"].cuda(), eta=meta["eta"], prompts=meta["prompts"], cfg_scales=meta["cfg_scales"], zs=g["zs"].cuda(),
+                                            controller=store, weight_reconstruction=meta["weight_reconstruction"], optimization_steps=1,
+                                            after_skip_steps=meta["T"], is_ddim_inversion=False)
+    assert store.cur_step == meta["T"] and store.maps > 0
+    assert torch.isfinite(ed).all() and rel_err(rc.cpu(), g["recon"])[0] < TOL_LOOP

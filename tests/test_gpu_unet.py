@@ -71,7 +71,7 @@ def _run_golden(name, eng_cache={}, schedule=1, tol=None):
         meta["prompts"], meta["is_replace"], meta["xa"], meta["sa"],
         blend_word=((bw[0],), (bw[1],)) if meta["blend"] else None,
         equilizer_params={"words": (bw[1],), "values": (1.25 if meta["K"] > 1 else 2.0,)} if meta["blend"] else None,
-        num_steps=meta["T"], tokenizer=model.tokenizer)
+        num_steps=meta["T"], tokenizer=model.tokenizer, substruct_words=meta.get("substruct_words"))
     plan = hedit_b200.compile_edit_plan([ctrl], meta["T"])
     ts, coef = hedit_b200.step_tables(model.scheduler, meta["T"], meta["eta"], False)
     ctx = torch.cat([g["ctx_uncond"], g["ctx_src"], g["ctx_tar"]])
@@ -145,6 +145,17 @@ def test_edit_loop_tiny_replace_mos2():
     assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
 
 
+def test_edit_loop_tiny_substruct_words():
+    """LocalBlend with substruct_words (ptp_classes.py:28-38,66-67): the un-pooled word map of "branch" is cut out of the blend mask."""
+    if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "tiny_refine_blend_substruct.pt")):
+        pytest.skip("golden missing")
+    r_ed, r_rc, r_w0, st = _run_golden("tiny_refine_blend_substruct")
+    assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
+    # the exclusion matters: the same edit without substruct words is a different image
+    g, g0 = load_golden("tiny_refine_blend_substruct"), load_golden("tiny_refine_blend")
+    assert g["meta"]["substruct_words"] is not None
+
+
 def test_edit_loop_tiny_noblend():
     r_ed, r_rc, r_w0, st = _run_golden("tiny_refine_noblend")
     assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
@@ -198,7 +209,8 @@ def _run_variant(name, eng_cache={}):
         ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, 1, explicit_form=True, variant=1)
         want_fwd = 3 * T
     elif mode == "masactrl":
-        editor = hedit_b200.MutualSelfAttentionControl(meta["masa_start_step"], meta["masa_start_layer"], total_steps=meta.get("masa_total_steps", T * K))
+        editor = hedit_b200.MutualSelfAttentionControl(meta["masa_start_step"], meta["masa_start_layer"], layer_idx=meta.get("masa_layer_idx"),
+                                                       step_idx=meta.get("masa_step_idx"), total_steps=meta.get("masa_total_steps", T * K))
         ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, K, masactrl=editor.launch_plan(T * K, eng.n_transformer_blocks()), mos_pull=False)
         want_fwd = (2 + 5 * K) * T
     elif mode == "pnp":
@@ -229,7 +241,8 @@ def _run_variant(name, eng_cache={}):
     return r_ed, r_rc
 
 
-@pytest.mark.parametrize("name", ["tiny_p2p_explicit", "tiny_R_implicit_mos2", "tiny_R_explicit", "tiny_masactrl_mos2", "tiny_pnp", "tiny_R_implicit_skip2"])
+@pytest.mark.parametrize("name", ["tiny_p2p_explicit", "tiny_R_implicit_mos2", "tiny_R_explicit", "tiny_masactrl_mos2", "tiny_masactrl_mos2_stop", "tiny_masactrl_lists",
+                                  "tiny_pnp", "tiny_R_implicit_skip2"])
 def test_sampler_variants(name):
     if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", name + ".pt")):
         pytest.skip("golden missing")

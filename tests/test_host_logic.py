@@ -259,3 +259,77 @@ def test_compat_unet_routes_cross_attention_kwargs_like_the_reference_processors
     unet2(x, 461, encoder_hidden_states=ctx)
     assert [k for k, _ in eng2.log] == ["fused", "editor"]
     assert seen == [(False, "down", 8, 8 ** -0.5)]
+
+
+def test_controller_kind_checks_the_defining_module_not_only_the_name():
+    """A user class that merely reuses a stock class NAME (or overrides a hook in a subclass) only promises the protocol."""
+    tok = ToyTokenizer()
+    own = hedit_b200.make_controller(PAIRS[0][0], False, 0.4, 0.35, num_steps=8, tokenizer=tok)
+    assert hedit_b200.controller_kind(own) == "stock"
+
+    class AttentionRefine:          # same name as the reference's class, defined elsewhere
+        cross_replace_alpha = own.cross_replace_alpha
+        prev_controller = None
+
+        def __call__(self, attn, is_cross, place, save_attn):
+            return attn
+
+    assert hedit_b200.controller_kind(AttentionRefine()) == "custom"
+
+    class AttentionStore:
+        pass
+    assert hedit_b200.controller_kind(AttentionStore()) == "custom"      # a user-side recorder: must see its maps (compat path)
+
+
+def test_masactrl_launch_plan_follows_the_reference_schedule():
+    """masactrl.py:33-36,57: active iff cur_step in step_idx and block in layer_idx; step_idx defaults to range(start, total_steps)."""
+    ed = hedit_b200.MutualSelfAttentionControl(4, 10, total_steps=50)
+    mask, on = ed.launch_plan(70)                     # 35 timesteps x K = 2 controlled launches
+    assert mask == sum(1 << l for l in range(10, 16))
+    assert on == [0] * 4 + [1] * 46 + [0] * 20        # the injection ENDS at total_steps
+    ed.cur_step = 48
+    assert ed.launch_plan(4)[1] == [1, 1, 0, 0]
+    ed2 = hedit_b200.MutualSelfAttentionControl(layer_idx=[3, 8, 15], step_idx=[1, 2, 4], total_steps=6)
+    mask, on = ed2.launch_plan(6)
+    assert mask == (1 << 3) | (1 << 8) | (1 << 15) and on == [0, 1, 1, 0, 1, 0]
+
+
+def test_substruct_words_and_sparse_replacement_plan():
+    tok = ToyTokenizer()
+    c = hedit_b200.make_controller(PAIRS[0][0], False, 0.4, 0.35, blend_word=(("lizard",), ("lizard",)), substruct_words=(("branch",), ("branch",)),
+                                   num_steps=8, tokenizer=tok)
+    plan = hedit_b200.compile_edit_plan([c], 8)
+    assert plan.blend_alpha.shape == (1, 4, 80) and plan.blend_alpha[0, 2:].sum() == 2 and plan.blend_alpha[0, :2].sum() == 2
+    assert not np.array_equal(plan.blend_alpha[0, 0], plan.blend_alpha[0, 2])
+    # replacement mapper: the sparse (index, weight) rows reproduce the dense 77x77 product exactly
+    rep = hedit_b200.make_controller(PAIRS[3][0], True, 0.4, 0.35, num_steps=8, tokenizer=tok)
+    plan = hedit_b200.compile_edit_plan([rep, c], 8)
+    assert plan.map_w is not None and plan.mapper.shape == plan.map_w.shape and plan.mapper.shape[1] <= 4
+    P = np.random.default_rng(0).random(77).astype(np.float32)
+    dense = P @ plan.replace_m[0, :, :77]
+    sparse = sum(P[plan.mapper[0, k, :77]] * plan.map_w[0, k, :77] for k in range(plan.map_w.shape[1]))
+    assert np.array_equal(dense.astype(np.float32), sparse.astype(np.float32))
+    # the Refine image rides along as (mapper[j], 1)
+    single = hedit_b200.compile_edit_plan([c], 8)
+    assert np.array_equal(plan.mapper[1, 0], single.mapper[0]) and (plan.map_w[1, 0, :77] == 1).all() and (plan.map_w[1, 1:] == 0).all()
+
+
+def test_edit_controller_implements_the_reference_protocol_and_lazy_store():
+    """EditController is itself a protocol controller (used by the compat replay): counters, store, cross edit on materialised maps."""
+    from hedit_b200.p2p import LazyAttentionStore
+    tok = ToyTokenizer()
+    c = hedit_b200.make_controller(PAIRS[0][0], False, 0.4, 0.35, num_steps=4, tokenizer=tok)
+    c.num_att_layers = 2
+    g = torch.Generator().manual_seed(0)
+    cross = torch.softmax(torch.randn(4 * 8, 256, 77, generator=g), -1)
+    before = cross.clone()
+    c(cross, True, "down", True)
+    assert torch.equal(cross[:24], before[:24]) and not torch.equal(cross[24:], before[24:])      # only the cond-target rows change
+    c(torch.softmax(torch.randn(32, 256, 256, generator=g), -1), False, "down", True)
+    assert c.cur_step == 1 and c.cur_att_layer == 0
+    assert len(c.attention_store["down_cross"]) == 1 and c.attention_store["down_cross"][0].shape == (16, 256, 77)
+    assert torch.equal(c.attention_store["down_cross"][0], cross[16:])                              # the stored map is the EDITED one
+    calls = []
+    lazy = LazyAttentionStore(lambda: calls.append(1) or {"down_cross": [torch.ones(1)]})
+    assert calls == []
+    assert len(lazy["down_cross"]) == 1 and "down_cross" in lazy and len(lazy) == 1 and calls == [1]

@@ -38,7 +38,7 @@ __global__ void tmem_read_kernel(int iters, unsigned long long* clk_out, float* 
         : "r"(base + col)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    acc += __uint_as_float(v[i & 31]);
+    acc += __uint_as_float(v[0] ^ v[7] ^ v[13] ^ v[22] ^ v[31]);      // static indices: the values stay in registers
   }
   __syncthreads();
   const unsigned long long t1 = clock64();

@@ -27,8 +27,8 @@ def timeit(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
-def bench_attn(iters):
-    for (S, N, H, d) in [(8, 4096, 8, 40), (8, 1024, 8, 80), (8, 256, 8, 160)]:
+def bench_attn(iters, S=8):
+    for (S, N, H, d) in [(S, 4096, 8, 40), (S, 1024, 8, 80), (S, 256, 8, 160)]:
         C = H * d
         qkv = bf(torch.randn(S, N, 3 * C, device=DEV))
         out = torch.zeros(S, N, C, device=DEV, dtype=qkv.dtype)
@@ -150,10 +150,11 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--samples", type=int, default=8, help="attn: samples per launch (40 = the bench's UNet launch: 17.3 CTA waves instead of 3.5)")
     a = ap.parse_args()
     torch.manual_seed(0)
     if a.what in ("attn", "all"):
-        bench_attn(a.iters)
+        bench_attn(a.iters, a.samples)
     if a.what in ("linear", "all"):
         bench_linear(a.iters)
     if a.what in ("conv", "all"):
