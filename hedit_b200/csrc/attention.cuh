@@ -881,6 +881,283 @@ self_attn3_kernel(const __grid_constant__ AttnParams p) {
   if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
+// ------------------------------------------------------------------------------------------------------- v4
+// Probabilities in TENSOR MEMORY.  v2 / v3 hand P to the tensor core through shared memory: 8 STS.128 + address arithmetic per thread and
+// block, a MEMBAR + proxy fence before every hand-over, and a second barrier (pv_done) before the P tile may be rewritten.  Here the
+// softmax thread overwrites ITS OWN row of S in TMEM with the 16-bit probabilities (tcgen05.st, lane == row: no cross-thread hazard) and
+// P.V takes its A operand from TMEM.  The MMA warp issues  P_t(j).V(j)  and then  S_t(j+1) = Q_t K(j+1)^T  back to back: the tensor pipe
+// executes in issue order, so S(j+1) may overwrite the S/P columns, and the completion of S(j+1) (s_full) also tells the warpgroup that
+// P.V(j) is done and O is stable -- one wait and one arrive per block and warpgroup instead of three waits and two arrives.  Shared
+// memory per CTA drops by the two P tiles (32 KB), which pays for a fourth K/V stage.  TMEM: S_t/P_t at t*64, O_t at 128 + t*O_STRIDE.
+template <int DCH, int NT_ = 2>
+struct SelfAttn4Cfg {
+  static constexpr int NT = NT_, BKV = 64;                       // NT query tiles (= softmax warpgroups) per CTA
+  static constexpr int KSTAGES = (DCH == 1) ? (NT == 2 ? 4 : 3) : (NT == 2 ? 3 : 2);
+  static constexpr uint32_t QT_BYTES = DCH * 128 * 128;
+  static constexpr uint32_t KV_BYTES = DCH * BKV * 128;
+  static constexpr uint32_t SMEM_BYTES = NT * QT_BYTES + 2 * KSTAGES * KV_BYTES + 512;
+  static constexpr uint32_t O_COL0 = NT * BKV, O_STRIDE = DCH * 64;
+  static constexpr uint32_t USED_COLS = O_COL0 + NT * O_STRIDE;
+  static constexpr uint32_t TMEM_COLS = USED_COLS <= 128 ? 128 : (USED_COLS <= 256 ? 256 : 512);
+  static constexpr int BY_TMEM = 512 / TMEM_COLS, BY_SMEM = int((227u * 1024u) / (SMEM_BYTES + 1024u));
+  static constexpr int MIN_CTAS = BY_TMEM < BY_SMEM ? BY_TMEM : (BY_SMEM < 1 ? 1 : BY_SMEM);
+  static constexpr int THREADS = 128 * NT + 64;
+};
+
+// TWOPASS: the scores are read from TMEM twice in 32-column chunks (row max, then exponentials; upper chunk first, so that the packed
+// probabilities of both chunks are written over S only after all of S has been consumed) instead of being held in 64 registers: the
+// ~40 registers this frees are what lets POLY16 = 3 / 4 run without spilling at two CTAs per SM.
+template <int DCH, bool MMASUM, int POLY16, int NT_ = 2, bool TWOPASS = false>
+static __global__ void __launch_bounds__(SelfAttn4Cfg<DCH, NT_>::THREADS, SelfAttn4Cfg<DCH, NT_>::MIN_CTAS)
+self_attn4_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = SelfAttn4Cfg<DCH, NT_>;
+  constexpr int BKV = Cfg::BKV, KSTAGES = Cfg::KSTAGES, NT = Cfg::NT;
+  constexpr int MMA_WARP = 4 * NT, TMA_WARP = 4 * NT + 1;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;                               // [NT tiles][DCH][128 rows][128 B]
+  uint8_t* sK = sQ + NT * Cfg::QT_BYTES;             // [KSTAGES][DCH][BKV rows][128 B]
+  uint8_t* sV = sK + KSTAGES * Cfg::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KSTAGES * Cfg::KV_BYTES);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* k_full = bars + 1;              // KSTAGES
+  uint64_t* v_full = k_full + KSTAGES;
+  uint64_t* kv_empty = v_full + KSTAGES;
+  uint64_t* s_full = kv_empty + KSTAGES;    // NT: S_t(j) complete (and with it P_t(j-1).V(j-1))
+  uint64_t* p_full = s_full + NT;           // NT (4 arrivals each): P_t(j) is in TMEM
+  uint64_t* o_done = p_full + NT;           // NT: the last P.V of tile t has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + NT);
+  uint32_t* sOnes = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);   // 128 B: one 8x8 core matrix of 16-bit ones
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (128 * NT), h = blockIdx.y, s = blockIdx.z;
+  const int sq = p.q_idx ? p.q_idx[s] : s;
+  const int sk = p.k_idx ? p.k_idx[s] : s;
+  const int sv = p.v_idx ? p.v_idx[s] : s;
+  const int nblk = p.Nkv / BKV;
+  const int DK = (p.d + 15) & ~15;
+  if (MMASUM && DK + 16 > DCH * 64) __trap();
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < NT; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_done[i], 1); }
+    fence_mbar_init();
+  }
+  if (MMASUM && threadIdx.x < 32) { sOnes[threadIdx.x] = pack_op2(1.f, 1.f); fence_proxy_async_smem(); }
+  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == TMA_WARP) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, NT * Cfg::QT_BYTES);
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + t * Cfg::QT_BYTES + c * 16384, &p.tmQ, q_full, c * 64, h, q0 + t * 128, sq);
+      int st = 0; uint32_t ph = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sK + st * Cfg::KV_BYTES + c * BKV * 128, &p.tmK, &k_full[st], c * 64, h, j * BKV, sk);
+        mbar_expect_tx(&v_full[st], Cfg::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sV + st * Cfg::KV_BYTES + c * BKV * 128, &p.tmV, &v_full[st], c * 64, h, j * BKV, sv);
+        if (++st == KSTAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)
+    const uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
+    const uint32_t idesc_o = umma_idesc_bf16(128, DK, 0, 1);
+    const uint32_t idesc_l = umma_idesc_bf16(128, 16, 0, 0);
+    const int ks = DK >> 4;
+    const uint32_t q_lo = umma_desc_lo_kmajor(smem_u32(sQ));
+    const uint32_t k_lo = umma_desc_lo_kmajor(smem_u32(sK));
+    const uint32_t v_lo = umma_desc_lo(smem_u32(sV), BKV * 128);
+    const uint64_t ones_desc = uint64_t((smem_u32(sOnes) >> 4) & 0x3FFFu) | (1ull << 46);
+    auto issue_s = [&](int tile, int st) {
+      const uint32_t qa = q_lo + tile * (Cfg::QT_BYTES >> 4), kb = k_lo + st * (Cfg::KV_BYTES >> 4);
+      const uint32_t d = tmem_base + tile * BKV;
+#pragma unroll
+      for (int k = 0; k < 4 * DCH; ++k)
+        if (k < ks)
+          umma_f16_ss(d, umma_desc_make(qa + (k >> 2) * (16384 >> 4) + 2 * (k & 3)),
+                      umma_desc_make(kb + (k >> 2) * ((BKV * 128) >> 4) + 2 * (k & 3)), idesc_s, k != 0);
+      umma_commit(&s_full[tile]);
+    };
+    auto issue_pv = [&](int tile, int st, bool accumulate) {   // O_tile += P_tile (TMEM, 8 columns per K step) . V_st
+      const uint32_t pa = tmem_base + tile * BKV, vb = v_lo + st * (Cfg::KV_BYTES >> 4);
+      const uint32_t d = tmem_base + Cfg::O_COL0 + tile * Cfg::O_STRIDE;
+#pragma unroll
+      for (int k = 0; k < BKV / 16; ++k) {
+        umma_f16_ts(d, pa + 8 * k, umma_desc_make(vb + k * (2048 >> 4)), idesc_o, (accumulate || k != 0) ? 1u : 0u);
+        if (MMASUM) umma_f16_ts(d + DK, pa + 8 * k, ones_desc, idesc_l, (accumulate || k != 0) ? 1u : 0u);
+      }
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) issue_s(t, 0);
+    }
+    __syncwarp();
+    int st = 0; uint32_t ph = 0;
+    for (int j = 0; j < nblk; ++j) {
+      int st1 = st + 1; uint32_t ph1 = ph;
+      if (st1 == KSTAGES) { st1 = 0; ph1 ^= 1; }
+      const bool more = (j + 1 < nblk);
+      if (more) mbar_wait(&k_full[st1], ph1);
+      mbar_wait(&v_full[st], ph);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        mbar_wait(&p_full[t], j & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_pv(t, st, j != 0);
+          if (more) issue_s(t, st1);          // in issue order behind P.V(j): may overwrite the S/P columns of tile t
+          else umma_commit(&o_done[t]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&kv_empty[st]);
+      __syncwarp();
+      st = st1; ph = ph1;
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warpgroups (warps 4t..4t+3 own query tile t)
+    const int tile = warp >> 2;
+    const int r = threadIdx.x & 127;
+    const uint32_t lane_sel = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + tile * BKV + lane_sel;
+    const uint32_t tO = tmem_base + Cfg::O_COL0 + tile * Cfg::O_STRIDE + lane_sel;
+    const int DKL = MMASUM ? DK + 16 : DK;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[tile], j & 1);               // S(j) complete => P.V(j-1) complete: O is stable, the S/P columns are ours
+      tc_fence_after();
+      uint32_t v[TWOPASS ? 32 : BKV];
+      float bmax;
+      {
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if constexpr (TWOPASS) {
+#pragma unroll
+          for (int c = 0; c < BKV; c += 32) {
+            tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mx[k] = fmax3(mx[k], __uint_as_float(v[i + 2 * k]), __uint_as_float(v[i + 2 * k + 1]));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < BKV; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < BKV; i += 8)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mx[k] = fmax3(mx[k], __uint_as_float(v[i + 2 * k]), __uint_as_float(v[i + 2 * k + 1]));
+        }
+        bmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      }
+      bmax *= p.scale_log2;
+      float alpha = 1.f;
+      bool bump = false;
+      if (j == 0) {
+        m_used = bmax;
+      } else if (bmax > m_used + 8.f) {
+        alpha = ex2f(m_used - bmax);
+        m_used = bmax;
+        l *= alpha;
+        bump = true;
+      }
+      if (__any_sync(0xffffffffu, bump)) {
+#pragma unroll 1
+        for (int c = 0; c < DKL; c += 16) {
+          uint32_t o[16];
+          tmem_ld16(tO + c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tO + c, o);
+        }
+      }
+      const float neg_m = -m_used;
+      float2 ls[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ls[k] = make_float2(0.f, 0.f);
+      if constexpr (TWOPASS) {
+        uint32_t pkA[16], pkB[16];
+        tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));           // upper 32 scores first
+        tmem_ld_wait();
+        exp2_block16<POLY16, !MMASUM>(&v[0], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pkB[0]), ls);
+        exp2_block16<POLY16, !MMASUM>(&v[16], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pkB[8]), ls);
+        tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_wait();
+        exp2_block16<POLY16, !MMASUM>(&v[0], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pkA[0]), ls);
+        exp2_block16<POLY16, !MMASUM>(&v[16], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pkA[8]), ls);
+        tmem_st16(tS, pkA);                     // all of S(j) has been read: P(j) over its first 32 columns (this thread's own row)
+        tmem_st16(tS + 16, pkB);
+      } else {
+#pragma unroll
+        for (int hlf = 0; hlf < BKV; hlf += 32) {       // P(j) over the first 32 columns of S(j) (this thread's own row), 16 columns at a time
+          uint32_t pk[16];
+          exp2_block16<POLY16, !MMASUM>(&v[hlf], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pk[0]), ls);
+          exp2_block16<POLY16, !MMASUM>(&v[hlf + 16], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pk[8]), ls);
+          tmem_st16(tS + hlf / 2, pk);
+        }
+      }
+      if (!MMASUM) l += ((ls[0].x + ls[0].y) + (ls[1].x + ls[1].y)) + ((ls[2].x + ls[2].y) + (ls[3].x + ls[3].y));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[tile]);
+    }
+    mbar_wait(&o_done[tile], 0);
+    tc_fence_after();
+    if (MMASUM) {
+      uint32_t o[16];
+      tmem_ld16(tO + DK, o);
+      tmem_ld_wait();
+      l = __uint_as_float(o[0]);
+    }
+    const float inv = 1.f / l;
+    const int row = q0 + tile * 128 + r;
+#pragma unroll 1
+    for (int c = 0; c < DK; c += 16) {
+      uint32_t o[16];
+      tmem_ld16(tO + c, o);
+      tmem_ld_wait();
+      if (row < p.Nq) {
+        op_t* dst = p.out + (size_t(s) * p.Nq + row) * p.ldo + h * p.d + c;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c + g * 8 < p.d) {
+            const int b = g * 8;
+            *reinterpret_cast<uint4*>(dst + b) = make_uint4(
+                pack_op2(__uint_as_float(o[b]) * inv, __uint_as_float(o[b + 1]) * inv),
+                pack_op2(__uint_as_float(o[b + 2]) * inv, __uint_as_float(o[b + 3]) * inv),
+                pack_op2(__uint_as_float(o[b + 4]) * inv, __uint_as_float(o[b + 5]) * inv),
+                pack_op2(__uint_as_float(o[b + 6]) * inv, __uint_as_float(o[b + 7]) * inv));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
 // ======================================================================================================= cross
 template <int DCH>
 struct CrossAttnCfg {
@@ -1108,7 +1385,9 @@ struct CrossAttn2Cfg {
   static constexpr uint32_t P_BYTES = 2 * 128 * 128;
   static constexpr uint32_t PB_BYTES = BKV * 128 * 4;             // fp32 probabilities [col][row]: source (PB) and target scratch (PT)
   static constexpr int MAXR = 4;                                  // non-zeros per column of the replacement mapper served from shared memory
-  static constexpr uint32_t SMEM_BYTES = NQ * Q_BYTES + 4 * KV_BYTES + P_BYTES + 2 * PB_BYTES + 256 + (2 * MAXR + 2) * 320;   // + barriers + edit tables
+  static constexpr uint32_t TAB_BYTES = MAXR * 80 + MAXR * 320 + 2 * 320;     // 8-bit source-token indices, fp32 weights, c_base, c_tar
+  static constexpr uint32_t SMEM_BYTES = NQ * Q_BYTES + 4 * KV_BYTES + P_BYTES + 2 * PB_BYTES + 256 + TAB_BYTES;   // + barriers + edit tables
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory budget");
   static constexpr uint32_t TMEM_COLS = 512;                      // S[2] at 0,128 ; O[2] at 256, 384
   static_assert(DCH <= 2, "cross v2 supports head dims <= 128");
 };
@@ -1135,10 +1414,10 @@ static __global__ void __launch_bounds__(192, 1) cross_attn2_kernel(const __grid
   uint64_t* o_free = bars + 11;        // 2 (4 arrivals)
   uint64_t* p_full = bars + 13;        // 1 (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  int* sMap = reinterpret_cast<int*>(bars + 32);          // [R][80] edit tables of this image, staged once per CTA
-  float* sMw = reinterpret_cast<float*>(sMap + Cfg::MAXR * 80);   // [R][80]
+  float* sMw = reinterpret_cast<float*>(bars + 32);       // [R][80] edit tables of this image, staged once per CTA
   float* sCb = sMw + Cfg::MAXR * 80;
   float* sCt = sCb + 80;
+  uint8_t* sMap = reinterpret_cast<uint8_t*>(sCt + 80);   // [R][80] source-token indices (< 77)
   const int R = (p.map_w != nullptr && p.map_rows > 1) ? min(p.map_rows, Cfg::MAXR) : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1163,7 +1442,7 @@ static __global__ void __launch_bounds__(192, 1) cross_attn2_kernel(const __grid
   }
   if (nph == 2 && threadIdx.x < BKV) {
     for (int k = 0; k < R; ++k) {
-      sMap[k * 80 + threadIdx.x] = p.mapper[(img * R + k) * BKV + threadIdx.x];
+      sMap[k * 80 + threadIdx.x] = uint8_t(p.mapper[(img * R + k) * BKV + threadIdx.x]);
       sMw[k * 80 + threadIdx.x] = p.map_w ? p.map_w[(img * R + k) * BKV + threadIdx.x] : 1.f;
     }
     sCb[threadIdx.x] = p.c_base[img * BKV + threadIdx.x];
@@ -1323,7 +1602,7 @@ static __global__ void __launch_bounds__(192, 1) cross_attn2_kernel(const __grid
         // P2P target: stage own probabilities, then a ROLLED edit loop (keeps the kernel small enough for the I-cache)
 #pragma unroll
         for (int j = 0; j < BKV; ++j) dstf[j * 128 + r] = __uint_as_float(v[j]) * inv;
-        const int* mp = sMap;
+        const uint8_t* mp = sMap;
         const float* cb = sCb;
         const float* ct = sCt;
 #pragma unroll 1

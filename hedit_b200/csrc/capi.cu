@@ -165,6 +165,12 @@ int hedit_engine_set_graph_replay(hedit_engine* h, int on) {
   if (!on) h->E->drop_graphs();
   return 0;
 }
+int hedit_engine_set_prefix_dedup(hedit_engine* h, int on) {
+  if (!h) return fail("null engine");
+  h->E->set_prefix_dedup(on != 0);
+  if (!on) h->E->drop_graphs();
+  return 0;
+}
 
 int hedit_engine_profile_forward(hedit_engine* h, int S, int reps, char* out, int out_len) {
   if (!h) return fail("null engine");

@@ -47,9 +47,9 @@ __global__ void gather_latents_kernel(const float* __restrict__ pool, const int*
 struct CallDesc {
   int S = 0;
   int pool_off = 0;                 // first sample of this call inside the eps pool
-  std::vector<int> lat, ctx, us0, us1, uimg, sq, sk;
-  int *d_lat = 0, *d_ctx = 0, *d_us0 = 0, *d_us1 = 0, *d_uimg = 0, *d_sq = 0, *d_sk = 0;
-  int n_units = 0;
+  std::vector<int> lat, ctx, us0, us1, uimg, sq, sk, ufirst, uof;
+  int *d_lat = 0, *d_ctx = 0, *d_us0 = 0, *d_us1 = 0, *d_uimg = 0, *d_sq = 0, *d_sk = 0, *d_ufirst = 0, *d_uof = 0;
+  int n_units = 0, n_uniq = 0;
   bool p2p = false;      // attention control active in this launch (P2P edit / MasaCtrl)
   void add(int l, int c) { lat.push_back(l); ctx.push_back(c); sq.push_back(S); sk.push_back(S); ++S; }
   void unit(int a, int b, int img) { us0.push_back(a); us1.push_back(b); uimg.push_back(img); ++n_units; }
@@ -71,6 +71,16 @@ static int upload_ints(Engine& E, TempPool& tp, const std::vector<int>& v, int**
   return 0;
 }
 static int finish_call(Engine& E, TempPool& tp, CallDesc& c, cudaStream_t st) {
+  // distinct latents of this launch (samples that differ only in their text context share the context-free prefix of the UNet)
+  c.ufirst.clear(); c.uof.assign(c.S, 0);
+  for (int s = 0; s < c.S; ++s) {
+    int u = -1;
+    for (size_t k = 0; k < c.ufirst.size(); ++k) if (c.lat[c.ufirst[k]] == c.lat[s]) { u = int(k); break; }
+    if (u < 0) { u = int(c.ufirst.size()); c.ufirst.push_back(s); }
+    c.uof[s] = u;
+  }
+  c.n_uniq = int(c.ufirst.size());
+  if (upload_ints(E, tp, c.ufirst, &c.d_ufirst, st) || upload_ints(E, tp, c.uof, &c.d_uof, st)) return -1;
   if (upload_ints(E, tp, c.lat, &c.d_lat, st) || upload_ints(E, tp, c.ctx, &c.d_ctx, st) || upload_ints(E, tp, c.us0, &c.d_us0, st) ||
       upload_ints(E, tp, c.us1, &c.d_us1, st) || upload_ints(E, tp, c.uimg, &c.d_uimg, st) || upload_ints(E, tp, c.sq, &c.d_sq, st) ||
       upload_ints(E, tp, c.sk, &c.d_sk, st))
@@ -349,6 +359,8 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     CallCtrl cc;
     CKE(cudaMemcpyAsync(L.tidx_cur, L.tidx + size_t(tindex) * maxS, size_t(cd.S) * sizeof(int), cudaMemcpyDeviceToDevice, st));
     cc.ctx_idx = cd.d_ctx; cc.time_idx = L.tidx_cur;
+    static const bool prefix_dedup = !(getenv("HEDIT_PREFIX_DEDUP") && atoi(getenv("HEDIT_PREFIX_DEDUP")) == 0);
+    if (prefix_dedup && E.prefix_dedup() && cd.n_uniq < cd.S) { cc.uniq_first = cd.d_ufirst; cc.uniq_of = cd.d_uof; cc.n_uniq = cd.n_uniq; }   // one timestep per launch here
     cc.unit_s0 = cd.d_us0; cc.unit_s1 = cd.d_us1; cc.unit_img = cd.d_uimg; cc.n_units = cd.n_units;
     if (cd.p2p && p2p) {
       if (a.self_lo <= a.ctrl_step0 + ctrl_step && a.ctrl_step0 + ctrl_step < a.self_hi) { cc.self_mask = mask_small; cc.self_q = cd.d_sq; cc.self_k = cd.d_sq; cc.self_v = nullptr; }

@@ -417,6 +417,14 @@ static __global__ void small_linear_kernel(const float* __restrict__ in, int ld_
   }
 }
 
+// whole samples gathered by index: dst[s][:] = src[idx[s]][:]  (n16 = 16-byte words per sample); broadcasts the de-duplicated prefix
+static __global__ void gather_samples_kernel(const uint4* __restrict__ src, const int* __restrict__ idx, uint4* __restrict__ dst, size_t n16) {
+  const int s = blockIdx.y;
+  const uint4* from = src + size_t(idx[s]) * n16;
+  uint4* to = dst + size_t(s) * n16;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n16; i += size_t(gridDim.x) * blockDim.x) to[i] = from[i];
+}
+
 // rows of a table gathered by index: out[r][:] = table[idx[r]][:]
 static __global__ void gather_rows_kernel(const float* __restrict__ table, const int* __restrict__ idx, float* __restrict__ out, int ld4) {
   const int r = blockIdx.y;

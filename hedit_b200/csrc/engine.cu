@@ -436,12 +436,24 @@ static cudaError_t launch_self3_t(const AttnParams& a, int S, cudaStream_t st) {
   self_attn3_kernel<DCH, MMASUM, TWOPASS, POLY16, PINGPONG><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
+template <int DCH, bool MMASUM, int POLY16, int NT = 2, bool TWOPASS = false>
+static cudaError_t launch_self4_t(const AttnParams& a, int S, cudaStream_t st) {
+  using Cfg = SelfAttn4Cfg<DCH, NT>;
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(self_attn4_kernel<DCH, MMASUM, POLY16, NT, TWOPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
+  dim3 grid((a.Nq + 128 * NT - 1) / (128 * NT), a.H, S);
+  self_attn4_kernel<DCH, MMASUM, POLY16, NT, TWOPASS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  return cudaGetLastError();
+}
 // tuning switch HEDIT_ATTN_V3 (self_attn3_kernel variants, head dims <= 128): 0 = round-1 kernel (self_attn2_kernel);
 //   1 = tensor-core row sum; 2 = + two-pass TMEM read; 3/4/5 = + 2/3/4 of every 8 exponential pairs on the FMA pipe
-static int attn_v3() { static const int v = getenv("HEDIT_ATTN_V3") ? atoi(getenv("HEDIT_ATTN_V3")) : 0; return v; }
+static int attn_v3() { static const int v = getenv("HEDIT_ATTN_V3") ? atoi(getenv("HEDIT_ATTN_V3")) : -1; return v; }
 template <int DCH>
 static cudaError_t launch_self3(const AttnParams& a, int S, cudaStream_t st) {
   switch (attn_v3()) {
+    // default (measured on B200 at 40 samples, round 2): probabilities in TMEM; d <= 64: tensor-core row sum + 2 of 8 exponential pairs on
+    // the FMA pipe (1.405 ms at N = 4096, d = 40 vs 1.67 for the round-1 kernel and 1.396 for cuDNN's SDPA); d = 80: plain (0.189 vs 0.220)
+    case -1: return DCH == 1 ? launch_self4_t<DCH, true, 2>(a, S, st) : launch_self4_t<DCH, false, 0>(a, S, st);
     case 1: return launch_self3_t<DCH, true, false, 0>(a, S, st);
     case 2: return launch_self3_t<DCH, true, true, 0>(a, S, st);
     case 3: return launch_self3_t<DCH, true, true, 2>(a, S, st);
@@ -454,6 +466,19 @@ static cudaError_t launch_self3(const AttnParams& a, int S, cudaStream_t st) {
     case 11: return launch_self3_t<DCH, false, true, 3, true>(a, S, st);
     case 12: return launch_self3_t<DCH, false, true, 4, true>(a, S, st);
     case 13: return launch_self3_t<DCH, true, true, 3, true>(a, S, st);
+    case 20: return launch_self4_t<DCH, false, 0>(a, S, st);             // v4: probabilities in TMEM
+    case 21: return launch_self4_t<DCH, false, 2>(a, S, st);
+    case 22: return launch_self4_t<DCH, false, 3>(a, S, st);
+    case 23: return launch_self4_t<DCH, true, 0>(a, S, st);
+    case 24: return launch_self4_t<DCH, true, 2>(a, S, st);
+    case 25: return launch_self4_t<DCH, true, 3>(a, S, st);
+    case 26: return launch_self4_t<DCH, true, 1>(a, S, st);
+    case 27: return launch_self4_t<DCH, false, 0, 1>(a, S, st);          // one query tile per CTA (measured: 2.10 ms vs 1.57 at d = 40)
+    case 31: return launch_self4_t<DCH, true, 2, 2, true>(a, S, st);     // two-pass TMEM read: no spills with larger FMA-pipe shares
+    case 32: return launch_self4_t<DCH, true, 3, 2, true>(a, S, st);
+    case 33: return launch_self4_t<DCH, true, 4, 2, true>(a, S, st);
+    case 34: return launch_self4_t<DCH, false, 3, 2, true>(a, S, st);
+    case 35: return launch_self4_t<DCH, true, 5, 2, true>(a, S, st);
     default: return launch_self3_t<DCH, true, false, 2>(a, S, st);      // 7: no two-pass, polynomial share (register-pressure control)
   }
 }
@@ -465,7 +490,7 @@ static int attn_poly() { static const int v = getenv("HEDIT_ATTN_POLY") ? atoi(g
 static int attn_cfg() { static const int v = getenv("HEDIT_ATTN_CFG") ? atoi(getenv("HEDIT_ATTN_CFG")) : 1; return v; }
 cudaError_t launch_self_attn(const AttnParams& a, int dch, int S, cudaStream_t st) {
   const int bkv2 = (dch == 1 && attn_cfg() == 0) ? 128 : 64;
-  if (a.Nq >= 256 && a.Nkv % 64 == 0 && attn_v3() > 0 && dch <= 2 && ((a.d + 15) & ~15) + 16 <= dch * 64)
+  if (a.Nq >= 256 && a.Nkv % 64 == 0 && attn_v3() != 0 && dch <= 2 && ((a.d + 15) & ~15) + 16 <= dch * 64)
     return dch == 1 ? launch_self3<1>(a, S, st) : launch_self3<2>(a, S, st);
   if (a.Nq >= 256 && a.Nkv % bkv2 == 0) {      // several query tiles per CTA
     if (dch == 1) {
@@ -596,6 +621,7 @@ struct PlanBuilder {
   Engine& E;
   Plan* plan;         // null in the sizing pass
   int S;
+  int U = 0;          // > 0: the context-free prefix is built for U distinct latents and broadcast to the S samples (CallCtrl::n_uniq)
   Arena ar;
   bool failed = false;
   double flops = 0;
@@ -612,7 +638,7 @@ struct PlanBuilder {
     auto it = colstats_of.find(reinterpret_cast<const void*>(p));
     if (it != colstats_of.end()) { ar.release(size_t(reinterpret_cast<uint8_t*>(it->second) - E.arena_)); colstats_of.erase(it); }
   }
-  void push(const Op& op) { if (plan) plan->ops.push_back(op); }
+  void push(Op op) { op.nS = S; if (plan) plan->ops.push_back(op); }
   // GroupNorm statistics fused into the producer: fp32 tensors whose every 32-row block lies inside one sample get a
   // [M/32][N] (sum, sumsq) side buffer written by the GEMM epilogue; it lives exactly as long as the tensor.
   std::map<const void*, float2*> colstats_of;
@@ -698,8 +724,17 @@ struct PlanBuilder {
     return out;
   }
 
-  // Transformer2DModel with one BasicTransformerBlock: returns a new fp32 buffer
-  float* transformer(int ti, const float* x, int Hh, int Ww) {
+  // samples broadcast: dst[s] = src[uniq_of[s]] (fp32 [S][HW][C])
+  float* expand(const float* src, int HW, int C) {
+    float* dst = A<float>(size_t(S) * HW * C);
+    Op o{}; o.kind = OP_EXPAND; o.f_in = src; o.f_out = dst; o.count = size_t(HW) * C * sizeof(float) / 16; o.tag = "prefix_expand";
+    push(o);
+    return dst;
+  }
+
+  // Transformer2DModel with one BasicTransformerBlock: returns a new fp32 buffer.  The context-free head (GroupNorm, proj_in, self-attention
+  // incl. its residual add) can be built separately (`transformer_head`) and its result passed in as `t_in`.
+  float* transformer_head(int ti, const float* x, int Hh, int Ww) {
     const TfW& w = E.tfs_[ti];
     const int C = w.C, HW = Hh * Ww, M = S * HW, H = E.cfg_.heads, d = C / H;
     bf16* a = A<bf16>(size_t(M) * C);
@@ -727,6 +762,17 @@ struct PlanBuilder {
     F(qkv);
     memset(&e, 0, sizeof e); e.bias = w.b_o1; e.residual = t; e.ldr = C; e.out_f32 = t; e.ldo = C;
     gemm("tf.attn1.out", att, C, A_LINEAR, nullptr, w.w_o1, M, C, C, e);
+    F(att);
+    F(a);
+    return t;
+  }
+  float* transformer(int ti, const float* x, int Hh, int Ww, float* t_in = nullptr) {
+    float* t = t_in ? t_in : transformer_head(ti, x, Hh, Ww);
+    const TfW& w = E.tfs_[ti];
+    const int C = w.C, HW = Hh * Ww, M = S * HW, H = E.cfg_.heads, d = C / H;
+    GemmEpilogue e;
+    bf16* a = A<bf16>(size_t(M) * C);
+    bf16* att = A<bf16>(size_t(M) * C);
     // ---- cross-attention
     ln(t, w.ln2g, w.ln2b, a, M, C);
     bf16* qc = A<bf16>(size_t(M) * C);
@@ -776,14 +822,32 @@ struct PlanBuilder {
     x_in = A<float>(size_t(S) * c.in_ch * Hh * Ww);
     eps_out = A<float>(size_t(S) * c.out_ch * Hh * Ww);
     std::vector<std::pair<float*, int>> skips;
+    const bool dedup = U > 0 && U < S;
+    const int Sfull = S;
+    if (dedup) S = U;               // the context-free prefix is built for the distinct latents only
     float* x = A<float>(size_t(S) * Hh * Ww * c.boc[0]);
-    { Op o{}; o.kind = OP_CONV_IN; o.f_in = x_in; o.f_out = x; o.H = Hh; o.W = Ww; o.C1 = c.boc[0]; o.tag = "conv_in"; push(o); }
-    skips.push_back({x, c.boc[0]});
+    float* x_in_u = dedup ? A<float>(size_t(S) * c.in_ch * Hh * Ww) : x_in;
+    { Op o{}; o.kind = OP_CONV_IN; o.f_in = x_in_u; o.f_out = x; o.H = Hh; o.W = Ww; o.C1 = c.boc[0]; o.rows = dedup ? 1 : 0; o.tag = "conv_in"; push(o); }
+    if (!dedup) skips.push_back({x, c.boc[0]});
     int ri = 0, ti = 0, C = c.boc[0];
     for (int i = 0; i < 4; ++i) {
       for (int l = 0; l < c.layers; ++l) {
         float* y = resblock(E.res_[ri++], x, C, nullptr, 0, Hh, Ww);
         C = c.boc[i];
+        if (dedup && i == 0 && l == 0) {
+          // prefix done on U samples: resnets[0] output y and the transformer state t after its self-attention; broadcast both (and the
+          // conv_in output, a skip connection) to the S samples and continue per sample from the first cross-attention on
+          float* t_u = transformer_head(ti, y, Hh, Ww);
+          S = Sfull;
+          float* x_s = expand(x, Hh * Ww, c.boc[0]); F(x); F(x_in_u);
+          float* y_s = expand(y, Hh * Ww, C); F(y);
+          float* t_s = expand(t_u, Hh * Ww, C); F(t_u);
+          skips.push_back({x_s, c.boc[0]});
+          float* z = transformer(ti++, y_s, Hh, Ww, t_s); F(y_s);
+          x = z;
+          skips.push_back({x, C});
+          continue;
+        }
         if (i < 3) { float* z = transformer(ti++, y, Hh, Ww); F(y); y = z; }
         x = y;
         skips.push_back({x, C});
@@ -867,34 +931,54 @@ struct PlanBuilder {
   }
 };
 
-Plan* Engine::get_plan(int S) {
-  auto it = plans_.find(S);
+Plan* Engine::get_plan(int S, int U) {
+  if (U >= S || U < 0 || cfg_.layers < 1) U = 0;
+  const int key = S * 4096 + U;
+  auto it = plans_.find(key);
   if (it != plans_.end()) return it->second.get();
   if (S > maxS_) { err_ = "batch exceeds max_samples"; return nullptr; }
   if (!arena_) {   // sizing pass at the maximum batch
     PlanBuilder sz(*this, nullptr, maxS_);
     sz.build();
-    arena_bytes_ = sz.ar.peak + (size_t(1) << 20);
+    size_t peak = sz.ar.peak;
+    for (int u : {maxS_ - 1, (maxS_ + 1) / 2}) {        // plans with a de-duplicated prefix hold distinct-latent and per-sample buffers at once
+      if (u < 1 || u >= maxS_) continue;
+      PlanBuilder szu(*this, nullptr, maxS_);
+      szu.U = u;
+      szu.build();
+      peak = std::max(peak, szu.ar.peak);
+    }
+    arena_bytes_ = peak + (size_t(1) << 20);
     flops_per_sample_ = sz.flops / maxS_;
     if (cudaMalloc(&arena_, arena_bytes_) != cudaSuccess) { err_ = "arena cudaMalloc failed"; arena_ = nullptr; return nullptr; }
   }
   std::unique_ptr<Plan> p(new Plan());
   p->S = S;
   PlanBuilder b(*this, p.get(), S);
+  b.U = U;
   b.build();
   if (b.failed || b.ar.peak > arena_bytes_) { if (err_.empty()) err_ = "plan build failed"; return nullptr; }
   Plan* raw = p.get();
-  plans_[S] = std::move(p);
+  plans_[key] = std::move(p);
   return raw;
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl& cc, cudaStream_t st) {
+long Engine::launch_op(Op& op, int S_call, const float* x, float* eps, const CallCtrl& cc, cudaStream_t st) {
   const UNetCfg& c = cfg_;
   const size_t lat = size_t(c.in_ch) * c.sample * c.sample;
+  const int S = op.nS > 0 ? op.nS : S_call;          // ops of the de-duplicated prefix run on the distinct latents only
   switch (op.kind) {
+    case OP_EXPAND:
+      gather_samples_kernel<<<dim3(unsigned(std::min<size_t>((op.count + 255) / 256, 64)), S), 256, 0, st>>>(
+          reinterpret_cast<const uint4*>(op.f_in), cc.uniq_of, reinterpret_cast<uint4*>(op.f_out), op.count);
+      break;
     case OP_CONV_IN: {
-      CK(cudaMemcpyAsync(const_cast<float*>(op.f_in), x, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (op.rows == 1)    // de-duplicated prefix: one latent per distinct value
+        gather_samples_kernel<<<dim3(unsigned(std::min<size_t>((lat * 4 / 16 + 255) / 256, 64)), S), 256, 0, st>>>(
+            reinterpret_cast<const uint4*>(x), cc.uniq_first, reinterpret_cast<uint4*>(const_cast<float*>(op.f_in)), lat * sizeof(float) / 16);
+      else
+        CK(cudaMemcpyAsync(const_cast<float*>(op.f_in), x, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
       const size_t sm = (36 * size_t(op.C1) + 4 * (kConvInRows + 2) * (op.W + 2)) * sizeof(float);
       static bool set = false;
       if (!set) { cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
@@ -932,7 +1016,7 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
     case OP_SELF_ATTN: {
       if (cc.probs_cb || cc.editor_cb) return compat_attention(op, false, S, cc, st);
       AttnParams a = op.attn;
-      if (cc.self_mask & (1u << op.tf_index)) { a.q_idx = cc.self_q; a.k_idx = cc.self_k; a.v_idx = cc.self_v; }
+      if ((cc.self_mask & (1u << op.tf_index)) && S == S_call) { a.q_idx = cc.self_q; a.k_idx = cc.self_k; a.v_idx = cc.self_v; }
       CK(launch_self_attn(a, op.dch, S, st));
       break;
     }
@@ -957,7 +1041,7 @@ long Engine::launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl
       cast_bf16_kernel<<<int(std::min<size_t>((op.count + 255) / 256, 8192)), 256, 0, st>>>(op.f_in, op.h_out, op.count);
       break;
     case OP_CONV_OUT:
-      CK(cudaMemcpyAsync(eps, op.f_out, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(eps, op.f_out, S_call * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
       break;
     case OP_FEAT_COPY:
       if (!cc.feat_src) return 0;
@@ -1029,7 +1113,8 @@ long Engine::compat_attention(const Op& op, bool is_cross, int S, const CallCtrl
 }
 
 long Engine::forward(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st) {
-  Plan* plan = get_plan(S);
+  const bool dedup = cc.n_uniq > 0 && cc.n_uniq < S && cc.uniq_first && cc.uniq_of && !(cc.self_mask & 1u) && !cc.probs_cb && !cc.editor_cb;
+  Plan* plan = get_plan(S, dedup ? cc.n_uniq : 0);
   if (!plan) return -1;
   long launches = 0;
   {   // per-call time-embedding rows
@@ -1053,9 +1138,9 @@ long Engine::forward_replayed(const float* x, float* eps, int S, const CallCtrl&
   // identity of the launch: every pointer / flag the kernels' parameters are derived from, packed without struct padding
   std::vector<uint8_t> key;
   {
-    const void* ptrs[19] = {cc.map_w, cc.ctx_idx, cc.time_idx, cc.self_q, cc.self_k, cc.self_v, cc.feat_src, cc.unit_s0, cc.unit_s1, cc.unit_img,
+    const void* ptrs[21] = {cc.uniq_first, cc.uniq_of, cc.map_w, cc.ctx_idx, cc.time_idx, cc.self_q, cc.self_k, cc.self_v, cc.feat_src, cc.unit_s0, cc.unit_s1, cc.unit_img,
                             cc.mapper, cc.c_base, cc.c_tar, cc.replace_m, cc.is_replace, cc.blend_acc, cc.blend_alpha, x, eps};
-    const int32_t ints[5] = {int32_t(cc.self_mask), cc.n_units, S, cc.blend_rows, cc.map_rows};
+    const int32_t ints[6] = {int32_t(cc.self_mask), cc.n_units, S, cc.blend_rows, cc.map_rows, cc.n_uniq};
     key.assign(reinterpret_cast<const uint8_t*>(ptrs), reinterpret_cast<const uint8_t*>(ptrs) + sizeof ptrs);
     key.insert(key.end(), reinterpret_cast<const uint8_t*>(ints), reinterpret_cast<const uint8_t*>(ints) + sizeof ints);
   }

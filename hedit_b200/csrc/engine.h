@@ -53,7 +53,7 @@ struct WeightSlot {
   bool loaded = false;
 };
 
-enum OpKind { OP_CONV_IN, OP_GN_STATS, OP_GN_FINALIZE, OP_GN_APPLY, OP_GEMM, OP_LN, OP_SELF_ATTN, OP_CROSS_ATTN, OP_UPSAMPLE, OP_CAST, OP_CONV_OUT, OP_FEAT_COPY };
+enum OpKind { OP_CONV_IN, OP_GN_STATS, OP_GN_FINALIZE, OP_GN_APPLY, OP_GEMM, OP_LN, OP_SELF_ATTN, OP_CROSS_ATTN, OP_UPSAMPLE, OP_CAST, OP_CONV_OUT, OP_FEAT_COPY, OP_EXPAND };
 
 struct Op {
   OpKind kind;
@@ -69,6 +69,7 @@ struct Op {
   int C1 = 0, C2 = 0, HW = 0, H = 0, W = 0, rows = 0, chunk = 0, nchunks = 0, silu = 0;
   float eps = 0.f;
   size_t count = 0;
+  int nS = 0;              // samples this op runs on (the de-duplicated prefix runs on fewer than the launch's S)
   const char* tag = "";
 };
 
@@ -97,6 +98,12 @@ struct CallCtrl {
   const float* replace_m = nullptr; const int* is_replace = nullptr;
   const float* map_w = nullptr; int map_rows = 1;
   float* blend_acc = nullptr; const float* blend_alpha = nullptr; int blend_rows = 2;
+  // Context-free prefix de-duplication: samples of one launch that share a LATENT (e.g. [x,null] [x,src] [x,tar]) compute identical
+  // activations until the first cross-attention (conv_in, down_blocks[0].resnets[0], the first transformer block up to and including its
+  // self-attention).  With n_uniq > 0 that prefix runs once per distinct latent and is broadcast: uniq_first[u] = a sample holding
+  // distinct latent u, uniq_of[s] = the distinct latent of sample s (device arrays).  Requires one timestep for the whole launch and no
+  // self-attention control on transformer block 0.  Bit-identical to the full evaluation (every kernel is batch-invariant).
+  const int *uniq_first = nullptr, *uniq_of = nullptr; int n_uniq = 0;
   // compat path (compat_attn.cuh): materialised probabilities + host callback instead of the fused attention kernels
   AttnProbsFn probs_cb = nullptr; void* probs_user = nullptr;
   AttnEditorFn editor_cb = nullptr; void* editor_user = nullptr;
@@ -147,13 +154,15 @@ class Engine {
   // therefore sit at FIXED addresses (the loop stages the step's rows).  Calls with a probabilities hook are never captured.
   long forward_replayed(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st);
   void set_graph_replay(bool on) { graph_replay_ = on; }
+  void set_prefix_dedup(bool on) { prefix_dedup_ = on; }
+  bool prefix_dedup() const { return prefix_dedup_; }
   void drop_graphs();
 
   std::string err_;
 
  private:
   friend struct PlanBuilder;
-  Plan* get_plan(int S);
+  Plan* get_plan(int S, int U = 0);
   long launch_op(Op& op, int S, const float* x, float* eps, const CallCtrl& cc, cudaStream_t st);
   void reg(const std::string& name, WeightSlot::Kind k, void* dst, size_t off, std::vector<int64_t> shape);
   template <typename T> T* dalloc(size_t n);
@@ -192,6 +201,7 @@ class Engine {
   std::vector<FwdGraph> fwd_graphs_;
   cudaStream_t cap_stream_ = nullptr;
   bool graph_replay_ = true;
+  bool prefix_dedup_ = true;
 };
 
 }  // namespace hedit

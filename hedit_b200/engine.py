@@ -149,6 +149,10 @@ class UNetEngine:
         """CUDA-graph replay of the loop's UNet launches (default on); off = every kernel launched directly.  Bit-identical results."""
         _lib.check(self.lib.hedit_engine_set_graph_replay(self.handle, int(bool(on))), "set_graph_replay")
 
+    def set_prefix_dedup(self, on: bool) -> None:
+        """Evaluate the UNet's context-free prefix once per distinct latent of a launch (default on).  Bit-identical results."""
+        _lib.check(self.lib.hedit_engine_set_prefix_dedup(self.handle, int(bool(on))), "set_prefix_dedup")
+
     def n_transformer_blocks(self) -> int:
         """Transformer blocks of the SD-1.x layout (attention on every level but the deepest, plus the mid block): 16 for SD-1.5;
         the reference's controllers count 2 attention layers per block (ptp_utils.py:277-295)."""

@@ -148,6 +148,11 @@ int hedit_engine_tensor_info(hedit_engine* e, int index, char* name_buf, int nam
 /* The sampling loop replays each distinct UNet launch (same buffers, batch and control tables) from a CUDA graph from its third
  * occurrence on (on by default; HEDIT_LOOP_GRAPH=0 or on=0 launches every kernel directly).  Results are bit-identical either way. */
 int hedit_engine_set_graph_replay(hedit_engine* e, int on);
+/* Samples of one UNet launch that share a latent and differ only in their text context (the [x,null] [x,src] [x,tar] evaluations of
+ * classifier-free guidance, p2p_h_edit.py:606-652) compute identical activations up to the first cross-attention; the loop evaluates that
+ * context-free prefix (conv_in, down_blocks[0].resnets[0], the first transformer block's self-attention) once per distinct latent and
+ * broadcasts it.  On by default (HEDIT_PREFIX_DEDUP=0 or on=0: every sample evaluates it).  Bit-identical results either way. */
+int hedit_engine_set_prefix_dedup(hedit_engine* e, int on);
 /* diagnostics: one UNet forward of S samples with CUDA events around every kernel; writes "tag:ms:launches;" records */
 int hedit_engine_profile_forward(hedit_engine* e, int S, int reps, char* out, int out_len);
 

@@ -57,6 +57,11 @@ CASES = {
     "tiny_replace_mos2": (UNetConfig.tiny(sample_size=64), 6, 2, True, True),
     "tiny_refine_noblend": (UNetConfig.tiny(sample_size=64), 6, 1, False, False),
     "sd15_config1": (UNetConfig.sd15(), 10, 1, False, True),
+    # LocalBlend with a NON-TRIVIAL mask: at the reference's default threshold 0.3 the word maps of a random-init UNet are so flat that the
+    # mask covers the whole latent (4096 of 4096 pixels in every golden above); th = 0.9 cuts it to a partial region that grows step by step,
+    # which is what makes "number of mask pixels that differ" a real check (ptp_classes.py:17,40-42: `th` is a LocalBlend argument)
+    "tiny_refine_blend_th09": (UNetConfig.tiny(sample_size=64), 10, 1, False, True),
+    "sd15_config2_T50_refine_blend_th09": (UNetConfig.sd15(), 50, 1, False, True),
     # LocalBlend with substruct_words (ptp_classes.py:28-38,66-67): the region of "branch" is excluded from the blend mask
     "tiny_refine_blend_substruct": (UNetConfig.tiny(sample_size=64), 6, 1, False, True),
     # BASELINE.json configs[1] (the headline): full SD-1.5 geometry, T = 50; two images with different prompts / controllers / noise
@@ -76,6 +81,7 @@ CASE_INPUTS = {
 
 
 SUBSTRUCT = {"tiny_refine_blend_substruct": (("branch",), ("branch",))}
+BLEND_TH = {"tiny_refine_blend_th09": (0.9, 0.9), "sd15_config2_T50_refine_blend_th09": (0.9, 0.9)}
 
 
 def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
@@ -99,8 +105,10 @@ def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
         prompts=PROMPTS, is_replace_controller=is_replace, cross_replace_steps=xa, self_replace_steps=sa,
         blend_word=blend_word, equilizer_params=eq, num_steps=T, tokenizer=model.tokenizer, device=model.device)
     substruct = SUBSTRUCT.get(name)
-    if substruct is not None:      # the reference's make_controller never passes substruct_words; its LocalBlend class takes them
-        controller.local_blend = ref.ptp_classes.LocalBlend(PROMPTS, T, blend_word, substruct_words=substruct, tokenizer=model.tokenizer, device=model.device)
+    blend_th = BLEND_TH.get(name)
+    if substruct is not None or blend_th is not None:   # the reference's make_controller never passes substruct_words / th; its LocalBlend class takes them
+        controller.local_blend = ref.ptp_classes.LocalBlend(PROMPTS, T, blend_word, substruct_words=substruct, th=blend_th or (0.3, 0.3),
+                                                            tokenizer=model.tokenizer, device=model.device)
     ref.ptp_utils.register_attention_control(model, controller)
     trace = []
     orig_cb = controller.step_callback
@@ -119,7 +127,7 @@ def run_case(ref, name, cfg, T, K, is_replace, blend, xa=0.4, sa=0.35):
     t_edit = time.time() - t0
     enc = ref.inversion_utils.encode_text
     out = {
-        "meta": dict(name=name, T=T, K=K, is_replace=is_replace, blend=blend, xa=xa, sa=sa, prompts=PROMPTS, substruct_words=substruct,
+        "meta": dict(name=name, T=T, K=K, is_replace=is_replace, blend=blend, xa=xa, sa=sa, prompts=PROMPTS, substruct_words=substruct, blend_th=blend_th,
                      blend_words=BLEND, cfg_scales=[1.0, 5.0, 7.5], eta=1.0, weight_reconstruction=0.1,
                      unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
                                cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
@@ -359,7 +367,7 @@ def run_face(name="tiny_face_k2", T=5, K=2, weight=50.0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "sd15_config1", "sd15_config2", "masa", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
+    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "sd15_config1", "sd15_config2", "sd15_config2_T50_refine_blend_th09", "tiny_refine_blend_th09", "masa", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
     args = ap.parse_args()
     if args.config == "style":
         run_style()

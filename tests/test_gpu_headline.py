@@ -72,12 +72,12 @@ def _metrics(ed, rc, tr, g):
     return m
 
 
-def _oracle_on_gpu(model, g, emulate):
+def _oracle_on_gpu(model, g, emulate, spec_fn=spec_from_meta):
     """The oracle port of the reference loop (oracle/h_edit.py) evaluated with torch on the GPU, fp32 (TF32 off), optionally with
     operand rounding."""
     meta = g["meta"]
     dev = torch.device("cuda")
-    spec = spec_from_meta(meta, model.tokenizer)
+    spec = spec_fn(meta, model.tokenizer)
     for k in ("alpha_words", "mapper", "refine_alpha", "replace_matrix", "equalizer", "blend_alpha"):
         v = getattr(spec, k, None)
         if torch.is_tensor(v):
@@ -210,3 +210,78 @@ def test_headline_localblend_mask_flips(headline, b):
     worst_e = max(e["mask_flips"])
     bad = [(i, f) for i, f in enumerate(c["mask_flips"]) if f > FACTOR * worst_e + FLOOR_FLIPS]
     assert not bad, (bad[:5], worst_e)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2] at full geometry: implicit h-Edit + MasaCtrl (the sampler the reference ships), SD-1.5 UNet, T = 50, against the
+# golden of the unmodified `h_Edit_masactrl_implicit` + `MutualSelfAttentionControl(4, 10)` (tests/make_golden.py --config masa).
+MASA = "sd15_config3_T50_masactrl"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLDEN_DIR, MASA + ".pt")), reason="golden missing")
+def test_config3_masactrl_full_geometry():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = load_golden(MASA)
+    meta = g["meta"]
+    T = meta["T"]
+    model = OraclePipeline(UNetConfig.sd15(), seed=0)
+    model.scheduler.set_timesteps(T)
+    hedit_b200.regiter_attention_editor_diffusers(model, hedit_b200.MutualSelfAttentionControl(meta["masa_start_step"], meta["masa_start_layer"],
+                                                                                              total_steps=meta["masa_total_steps"]))
+    ed, rc = hedit_b200.h_Edit_masactrl_implicit(model, g["xT"].cuda(), eta=meta["eta"], prompts=meta["prompts"], cfg_scales=meta["cfg_scales"],
+                                                 zs=g["zs"].cuda(), optimization_steps=meta["K"], after_skip_steps=T, is_ddim_inversion=False)
+    r_ed, m_ed = rel_err(ed.cpu(), g["edited"])
+    r_rc, m_rc = rel_err(rc.cpu(), g["recon"])
+    print(f"{MASA}: edited rel {r_ed:.3e} max-abs {m_ed:.3e} (|latent| max {g['edited'].abs().max().item():.1f}) | recon rel {r_rc:.3e} max-abs {m_rc:.3e}")
+    assert hedit_b200.get_engine(model).last_stats["sample_forwards"] == 7 * T
+    # same operand-rounding process as the headline loop (50 chained steps, 16-bit operands): the calibrated headline levels x 3
+    assert r_ed < 2e-2 and r_rc < 1.5e-1 and m_rc < 0.6
+
+
+TH09 = "sd15_config2_T50_refine_blend_th09"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLDEN_DIR, TH09 + ".pt")), reason="golden missing")
+def test_headline_partial_localblend_mask_full_geometry():
+    """The headline loop with LocalBlend th = 0.9 (a genuinely partial, step-dependent mask at SD-1.5 geometry; at the default 0.3 the mask
+    of a random-init UNet covers the whole latent): mask pixels on the other side than in the reference are counted against the
+    16-bit-operand-emulated oracle run."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = load_golden(TH09)
+    meta = g["meta"]
+    T = meta["T"]
+    model = OraclePipeline(UNetConfig.sd15(), seed=0)
+    model.scheduler.set_timesteps(T)
+    eng = UNetEngine.from_unet(model.unet, max_samples=5, max_contexts=4)
+    bw = meta["blend_words"]
+    ctrl = hedit_b200.make_controller(meta["prompts"], False, meta["xa"], meta["sa"], blend_word=((bw[0],), (bw[1],)),
+                                      equilizer_params={"words": (bw[1],), "values": (2.0,)}, num_steps=T, tokenizer=model.tokenizer)
+    ctrl.local_blend.th = tuple(meta["blend_th"])
+    plan = hedit_b200.compile_edit_plan([ctrl], T)
+    ts, coef = hedit_b200.step_tables(model.scheduler, T, 1.0, False)
+    ctx = torch.cat([g["ctx_uncond"], g["ctx_src"], g["ctx_tar"]]).cuda()
+    ed, rc, tr = eng.edit(g["xT"].reshape(1, 4, 64, 64).cuda(), g["zs"].reshape(1, T, 4, 64, 64).cuda(), ctx, ts, coef, meta["cfg_scales"], plan,
+                          meta["weight_reconstruction"], 1, False, 1, trace=True)
+    del eng
+    torch.cuda.empty_cache()
+    c = _metrics(ed.cpu(), rc.cpu(), tr.cpu()[:, 0], g)
+    model.unet.cuda()
+    import oracle_run
+    spec0 = oracle_run.spec_from_meta
+    oracle_run_spec = lambda m, tok: _with_th(spec0(m, tok), meta["blend_th"])
+    e = _metrics(*_oracle_on_gpu(model, g, emulate=True, spec_fn=oracle_run_spec), g)
+    model.unet.cpu()
+    print(f"{TH09}: golden mask px (every 7th) {c['mask_pixels_golden'][::7]}")
+    print(f"  cuda : edited rel {c['ed_rel']:.3e} max {c['ed_max']:.3e} recon rel {c['rc_rel']:.3e} | mask flips (every 7th) {c['mask_flips'][::7]} max {max(c['mask_flips'])}")
+    print(f"  16-bit-operand oracle: edited rel {e['ed_rel']:.3e} max {e['ed_max']:.3e} recon rel {e['rc_rel']:.3e} | mask flips max {max(e['mask_flips'])}")
+    assert 0 < min(c["mask_pixels_golden"][12:]) and max(c["mask_pixels_golden"][12:]) < 4096
+    assert max(c["mask_flips"]) <= FACTOR * max(e["mask_flips"]) + 2 * 16          # + two 16x16 cells
+    assert c["rc_rel"] <= FACTOR * e["rc_rel"] + FLOOR_REL
+    assert c["ed_rel"] <= FACTOR * e["ed_rel"] + FLOOR_REL
+
+
+def _with_th(spec, th):
+    spec.blend_th = float(th[0])
+    return spec
