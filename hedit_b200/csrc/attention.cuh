@@ -560,18 +560,12 @@ self_attn2_kernel(const __grid_constant__ AttnParams p) {
   if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
-// ------------------------------------------------------------------------------------------------------- v3
-// Round-2 revision of self_attn2_kernel for NT = 2 query tiles x 64-column blocks, 2 CTAs per SM.  ncu on v2 (N = 4096, d = 40): XU (MUFU)
-// pipe 73 % busy, 1527 clk per 128x128 score block against the 1024-clk floor of 16 exponentials / clk / SM.  Changes:
-//   MMASUM : the softmax row sum is produced by the TENSOR CORE: one extra N = 16 MMA per K step, l += P . 1, lands in the 16 TMEM columns
-//            next to O (the B operand is a 128-byte all-ones core matrix addressed with zero strides).  It removes 32 packed adds per
-//            thread and block, 8 live accumulator registers, and normalises by the sum of the ROUNDED probabilities (what P.V sums).
-//   TWOPASS: the scores are read from TMEM twice in 32-column chunks (pass 1: row max with 3-input FMNMX3; pass 2: exponentials) instead
-//            of being held in 64 registers across both passes: ~40 fewer live registers, which is what lets POLY16 > 0 fit the
-//            96-register budget of two CTAs per SM without spilling (TMEM reads are cheap: tools/micro/ubench.cu).
-//   POLY16 : of every 8 packed pairs (16 scores), POLY16 pairs evaluate 2^x on the FMA pipe (Cody-Waite + degree-3 minimax polynomial on
-//            packed fp32x2 instructions, relative error 7.5e-5 = 1/6 of the fp16 rounding of P) instead of the MUFU, interleaved with the
-//            MUFU pairs so that both pipes stay busy.
+// ------------------------------------------------------------------------------------------------------- shared helpers (v4)
+// Round-2 experiments on the round-1 kernel (self_attn2_kernel), all measured on B200 at N = 4096, d = 40 and dropped from the source
+// (numbers in DESIGN.md): tensor-core row sum alone (+7 % time: the four extra N = 16 MMAs lengthen the P.V -> next-S chain), reading S
+// from TMEM twice in 32-column chunks to free 40 registers (no change: TMEM reads are cheap, ~760 B/clk/SM, but the kernel was not
+// register-bound), FMA-pipe exponentials at 2 / 3 / 4 of 8 pairs (+0 .. -2.5 %), named-barrier ping-pong of the two softmax warpgroups
+// (no change).  What did pay: moving P out of shared memory (v4 below).
 HEDIT_DEVICE float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -605,282 +599,6 @@ HEDIT_DEVICE void exp2_block16(const uint32_t* v, float scale, float neg_m, uint
   }
 }
 
-//   PINGPONG: the two softmax warpgroups of a CTA alternate their exponential phases through two named barriers (warpgroup t enters its
-//            exponential phase only after warpgroup 1-t has left its own), so that one warpgroup's MUFU work overlaps the other's
-//            wait-for-P.V / TMEM-read / row-max phase instead of both contending for the MUFU and then both idling (free-running
-//            warpgroups fall into lockstep because the MUFU is shared round-robin).
-HEDIT_DEVICE void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-HEDIT_DEVICE void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-
-template <int DCH, bool MMASUM, bool TWOPASS, int POLY16, bool PINGPONG = false>
-static __global__ void __launch_bounds__(SelfAttn2Cfg<DCH, 2, 64>::THREADS, SelfAttn2Cfg<DCH, 2, 64>::MIN_CTAS)
-self_attn3_kernel(const __grid_constant__ AttnParams p) {
-  using Cfg = SelfAttn2Cfg<DCH, 2, 64>;
-  constexpr int BKV = 64, KSTAGES = Cfg::KSTAGES, NT = 2;
-  constexpr int MMA_WARP = 4 * NT, TMA_WARP = 4 * NT + 1;
-  static_assert(!MMASUM || DCH * 64 - 16 >= 16, "row-sum columns live between DK and O_STRIDE");
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sQ = smem;                               // [NT tiles][DCH][128 rows][128 B]
-  uint8_t* sK = sQ + NT * Cfg::QT_BYTES;             // [KSTAGES][DCH][BKV rows][128 B]
-  uint8_t* sV = sK + KSTAGES * Cfg::KV_BYTES;
-  uint8_t* sP = sV + KSTAGES * Cfg::KV_BYTES;       // [NT tiles][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NT * Cfg::PT_BYTES);
-  uint64_t* q_full = bars;                  // 1
-  uint64_t* k_full = bars + 1;              // KSTAGES
-  uint64_t* v_full = k_full + KSTAGES;
-  uint64_t* kv_empty = v_full + KSTAGES;
-  uint64_t* s_full = kv_empty + KSTAGES;    // NT
-  uint64_t* p_full = s_full + NT;           // NT (4 arrivals each)
-  uint64_t* pv_done = p_full + NT;          // NT
-  uint64_t* s_free = pv_done + NT;          // NT (4 arrivals each)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + NT);
-  uint32_t* sOnes = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);   // 128 B: one 8x8 core matrix of 16-bit ones
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (128 * NT), h = blockIdx.y, s = blockIdx.z;
-  const int sq = p.q_idx ? p.q_idx[s] : s;
-  const int sk = p.k_idx ? p.k_idx[s] : s;
-  const int sv = p.v_idx ? p.v_idx[s] : s;
-  const int nblk = p.Nkv / BKV;
-  const int DK = (p.d + 15) & ~15;
-  if (MMASUM && DK + 16 > DCH * 64) __trap();        // (d = 40 / 80 / 160 leave >= 16 free columns per O tile)
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < NT; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&s_free[i], 4); }
-    fence_mbar_init();
-  }
-  if (MMASUM && threadIdx.x < 32) { sOnes[threadIdx.x] = pack_op2(1.f, 1.f); fence_proxy_async_smem(); }
-  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == TMA_WARP) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(q_full, NT * Cfg::QT_BYTES);
-#pragma unroll
-      for (int t = 0; t < NT; ++t)
-#pragma unroll
-        for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + t * Cfg::QT_BYTES + c * 16384, &p.tmQ, q_full, c * 64, h, q0 + t * 128, sq);
-      int st = 0; uint32_t ph = 0;
-      for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&kv_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
-#pragma unroll
-        for (int c = 0; c < DCH; ++c) tma_load_4d(sK + st * Cfg::KV_BYTES + c * BKV * 128, &p.tmK, &k_full[st], c * 64, h, j * BKV, sk);
-        mbar_expect_tx(&v_full[st], Cfg::KV_BYTES);
-#pragma unroll
-        for (int c = 0; c < DCH; ++c) tma_load_4d(sV + st * Cfg::KV_BYTES + c * BKV * 128, &p.tmV, &v_full[st], c * 64, h, j * BKV, sv);
-        if (++st == KSTAGES) { st = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp == MMA_WARP) {
-    // ------------------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)
-    const uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
-    const uint32_t idesc_o = umma_idesc_bf16(128, DK, 0, 1);
-    const uint32_t idesc_l = umma_idesc_bf16(128, 16, 0, 0);
-    const int ks = DK >> 4;
-    const uint32_t q_lo = umma_desc_lo_kmajor(smem_u32(sQ));
-    const uint32_t p_lo = umma_desc_lo_kmajor(smem_u32(sP));
-    const uint32_t k_lo = umma_desc_lo_kmajor(smem_u32(sK));
-    const uint32_t v_lo = umma_desc_lo(smem_u32(sV), BKV * 128);
-    // all-ones B operand [K = 16][N = 16], K-major, NO swizzle, leading / stride byte offsets 0: every 8x8 core matrix aliases the same 128 B
-    const uint64_t ones_desc = uint64_t((smem_u32(sOnes) >> 4) & 0x3FFFu) | (1ull << 46);
-    auto issue_s = [&](int tile, int st) {
-      const uint32_t qa = q_lo + tile * (Cfg::QT_BYTES >> 4), kb = k_lo + st * (Cfg::KV_BYTES >> 4);
-      const uint32_t d = tmem_base + tile * BKV;
-#pragma unroll
-      for (int k = 0; k < 4 * DCH; ++k)
-        if (k < ks)
-          umma_f16_ss(d, umma_desc_make(qa + (k >> 2) * (16384 >> 4) + 2 * (k & 3)),
-                      umma_desc_make(kb + (k >> 2) * ((BKV * 128) >> 4) + 2 * (k & 3)), idesc_s, k != 0);
-      umma_commit(&s_full[tile]);
-    };
-    auto issue_pv = [&](int tile, int st, bool accumulate) {
-      const uint32_t pa = p_lo + tile * (Cfg::PT_BYTES >> 4), vb = v_lo + st * (Cfg::KV_BYTES >> 4);
-      const uint32_t d = tmem_base + Cfg::O_COL0 + tile * Cfg::O_STRIDE;
-#pragma unroll
-      for (int k = 0; k < BKV / 16; ++k) {
-        const uint64_t da = umma_desc_make(pa + 2 * k);
-        umma_f16_ss(d, da, umma_desc_make(vb + k * (2048 >> 4)), idesc_o, (accumulate || k != 0) ? 1u : 0u);
-        if (MMASUM) umma_f16_ss(d + DK, da, ones_desc, idesc_l, (accumulate || k != 0) ? 1u : 0u);
-      }
-      umma_commit(&pv_done[tile]);
-    };
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    if (elect_one()) {
-#pragma unroll
-      for (int t = 0; t < NT; ++t) issue_s(t, 0);
-    }
-    __syncwarp();
-    int st = 0; uint32_t ph = 0;
-    for (int j = 0; j < nblk; ++j) {
-      int st1 = st + 1; uint32_t ph1 = ph;
-      if (st1 == KSTAGES) { st1 = 0; ph1 ^= 1; }
-      const bool more = (j + 1 < nblk);
-      if (more) mbar_wait(&k_full[st1], ph1);
-      mbar_wait(&v_full[st], ph);
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        if (more) {
-          mbar_wait(&s_free[t], j & 1);
-          tc_fence_after();
-          if (elect_one()) issue_s(t, st1);
-          __syncwarp();
-        }
-        mbar_wait(&p_full[t], j & 1);
-        tc_fence_after();
-        if (elect_one()) issue_pv(t, st, j != 0);
-        __syncwarp();
-      }
-      if (elect_one()) umma_commit(&kv_empty[st]);
-      __syncwarp();
-      st = st1; ph = ph1;
-    }
-  } else {
-    // ------------------------------------------------------------ softmax warpgroups (warps 4t..4t+3 own query tile t)
-    const int tile = warp >> 2;
-    const int r = threadIdx.x & 127;
-    const uint32_t lane_sel = uint32_t((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + tile * BKV + lane_sel;
-    const uint32_t tO = tmem_base + Cfg::O_COL0 + tile * Cfg::O_STRIDE + lane_sel;
-    uint8_t* sPt = sP + tile * Cfg::PT_BYTES;
-    const int DKL = MMASUM ? DK + 16 : DK;            // columns rescaled with O (the row sum rides along)
-    float m_used = -INFINITY, l = 0.f;
-    if (PINGPONG && tile == 1) named_bar_arrive(1, 256);          // warpgroup 0 takes the first exponential phase
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(&s_full[tile], j & 1);
-      tc_fence_after();
-      uint32_t v[TWOPASS ? 32 : 64];
-      float bmax;
-      {
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if constexpr (TWOPASS) {
-#pragma unroll
-          for (int c = 0; c < BKV; c += 32) {
-            tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i += 8)
-#pragma unroll
-              for (int k = 0; k < 4; ++k) mx[k] = fmax3(mx[k], __uint_as_float(v[i + 2 * k]), __uint_as_float(v[i + 2 * k + 1]));
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < BKV; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[tile]);
-#pragma unroll
-          for (int i = 0; i < 64; i += 8)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mx[k] = fmax3(mx[k], __uint_as_float(v[i + 2 * k]), __uint_as_float(v[i + 2 * k + 1]));
-        }
-        bmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      }
-      bmax *= p.scale_log2;
-      float alpha = 1.f;
-      bool bump = false;
-      if (j == 0) {
-        m_used = bmax;
-      } else if (bmax > m_used + 8.f) {
-        alpha = ex2f(m_used - bmax);
-        m_used = bmax;
-        l *= alpha;
-        bump = true;
-      }
-      if (j > 0) { mbar_wait(&pv_done[tile], (j - 1) & 1); tc_fence_after(); }   // previous P.V done: P smem free, O stable
-      if (__any_sync(0xffffffffu, bump)) {
-#pragma unroll 1
-        for (int c = 0; c < DKL; c += 16) {
-          uint32_t o[16];
-          tmem_ld16(tO + c, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st16(tO + c, o);
-        }
-        tmem_st_wait();
-      }
-      const float neg_m = -m_used;
-      float2 ls[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ls[k] = make_float2(0.f, 0.f);
-      if (PINGPONG) named_bar_sync(1 + tile, 256);
-#pragma unroll
-      for (int c = 0; c < BKV; c += 32) {
-        if constexpr (TWOPASS) {
-          tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld_wait();
-          if (c == BKV - 32) {                       // last read of S: the MMA warp may overwrite it with the next block's scores
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[tile]);
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < 32; g += 16) {
-          uint32_t pk[8];
-          exp2_block16<POLY16, !MMASUM>(&v[(TWOPASS ? 0 : c) + g], p.scale_log2, neg_m, pk, ls);
-          const int cc = c + g;
-          *reinterpret_cast<uint4*>(sPt + sw128_off(r, cc >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(sPt + sw128_off(r, (cc >> 3) + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      }
-      if (PINGPONG) named_bar_arrive(1 + (tile ^ 1), 256);
-      if (!MMASUM) l += ((ls[0].x + ls[0].y) + (ls[1].x + ls[1].y)) + ((ls[2].x + ls[2].y) + (ls[3].x + ls[3].y));
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[tile]);
-    }
-    if (PINGPONG && tile == 0) named_bar_sync(1, 256);            // consume warpgroup 1's last hand-over
-    mbar_wait(&pv_done[tile], (nblk - 1) & 1);
-    tc_fence_after();
-    if (MMASUM) {
-      uint32_t o[16];
-      tmem_ld16(tO + DK, o);
-      tmem_ld_wait();
-      l = __uint_as_float(o[0]);
-    }
-    const float inv = 1.f / l;
-    const int row = q0 + tile * 128 + r;
-#pragma unroll 1
-    for (int c = 0; c < DK; c += 16) {
-      uint32_t o[16];
-      tmem_ld16(tO + c, o);
-      tmem_ld_wait();
-      if (row < p.Nq) {
-        op_t* dst = p.out + (size_t(s) * p.Nq + row) * p.ldo + h * p.d + c;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (c + g * 8 < p.d) {
-            const int b = g * 8;
-            *reinterpret_cast<uint4*>(dst + b) = make_uint4(
-                pack_op2(__uint_as_float(o[b]) * inv, __uint_as_float(o[b + 1]) * inv),
-                pack_op2(__uint_as_float(o[b + 2]) * inv, __uint_as_float(o[b + 3]) * inv),
-                pack_op2(__uint_as_float(o[b + 4]) * inv, __uint_as_float(o[b + 5]) * inv),
-                pack_op2(__uint_as_float(o[b + 6]) * inv, __uint_as_float(o[b + 7]) * inv));
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
-}
-
 // ------------------------------------------------------------------------------------------------------- v4
 // Probabilities in TENSOR MEMORY.  v2 / v3 hand P to the tensor core through shared memory: 8 STS.128 + address arithmetic per thread and
 // block, a MEMBAR + proxy fence before every hand-over, and a second barrier (pv_done) before the P tile may be rewritten.  Here the
@@ -889,10 +607,11 @@ self_attn3_kernel(const __grid_constant__ AttnParams p) {
 // executes in issue order, so S(j+1) may overwrite the S/P columns, and the completion of S(j+1) (s_full) also tells the warpgroup that
 // P.V(j) is done and O is stable -- one wait and one arrive per block and warpgroup instead of three waits and two arrives.  Shared
 // memory per CTA drops by the two P tiles (32 KB), which pays for a fourth K/V stage.  TMEM: S_t/P_t at t*64, O_t at 128 + t*O_STRIDE.
-template <int DCH, int NT_ = 2>
+template <int DCH>
 struct SelfAttn4Cfg {
-  static constexpr int NT = NT_, BKV = 64;                       // NT query tiles (= softmax warpgroups) per CTA
-  static constexpr int KSTAGES = (DCH == 1) ? (NT == 2 ? 4 : 3) : (NT == 2 ? 3 : 2);
+  static constexpr int NT = 2, BKV = 64;                         // NT query tiles (= softmax warpgroups) per CTA (one tile per CTA with
+                                                                 // three CTAs per SM was measured 33 % slower: no tile to ping-pong with)
+  static constexpr int KSTAGES = (DCH == 1) ? 4 : 3;
   static constexpr uint32_t QT_BYTES = DCH * 128 * 128;
   static constexpr uint32_t KV_BYTES = DCH * BKV * 128;
   static constexpr uint32_t SMEM_BYTES = NT * QT_BYTES + 2 * KSTAGES * KV_BYTES + 512;
@@ -904,13 +623,10 @@ struct SelfAttn4Cfg {
   static constexpr int THREADS = 128 * NT + 64;
 };
 
-// TWOPASS: the scores are read from TMEM twice in 32-column chunks (row max, then exponentials; upper chunk first, so that the packed
-// probabilities of both chunks are written over S only after all of S has been consumed) instead of being held in 64 registers: the
-// ~40 registers this frees are what lets POLY16 = 3 / 4 run without spilling at two CTAs per SM.
-template <int DCH, bool MMASUM, int POLY16, int NT_ = 2, bool TWOPASS = false>
-static __global__ void __launch_bounds__(SelfAttn4Cfg<DCH, NT_>::THREADS, SelfAttn4Cfg<DCH, NT_>::MIN_CTAS)
+template <int DCH, bool MMASUM, int POLY16>
+static __global__ void __launch_bounds__(SelfAttn4Cfg<DCH>::THREADS, SelfAttn4Cfg<DCH>::MIN_CTAS)
 self_attn4_kernel(const __grid_constant__ AttnParams p) {
-  using Cfg = SelfAttn4Cfg<DCH, NT_>;
+  using Cfg = SelfAttn4Cfg<DCH>;
   constexpr int BKV = Cfg::BKV, KSTAGES = Cfg::KSTAGES, NT = Cfg::NT;
   constexpr int MMA_WARP = 4 * NT, TMA_WARP = 4 * NT + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1044,29 +760,17 @@ self_attn4_kernel(const __grid_constant__ AttnParams p) {
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full[tile], j & 1);               // S(j) complete => P.V(j-1) complete: O is stable, the S/P columns are ours
       tc_fence_after();
-      uint32_t v[TWOPASS ? 32 : BKV];
+      uint32_t v[BKV];
       float bmax;
       {
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if constexpr (TWOPASS) {
 #pragma unroll
-          for (int c = 0; c < BKV; c += 32) {
-            tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-            tmem_ld_wait();
+        for (int c = 0; c < BKV; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+        tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; i += 8)
+        for (int i = 0; i < BKV; i += 8)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) mx[k] = fmax3(mx[k], __uint_as_float(v[i + 2 * k]), __uint_as_float(v[i + 2 * k + 1]));
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < BKV; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < BKV; i += 8)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mx[k] = fmax3(mx[k], __uint_as_float(v[i + 2 * k]), __uint_as_float(v[i + 2 * k + 1]));
-        }
+          for (int k = 0; k < 4; ++k) mx[k] = fmax3(mx[k], __uint_as_float(v[i + 2 * k]), __uint_as_float(v[i + 2 * k + 1]));
         bmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       }
       bmax *= p.scale_log2;
@@ -1095,26 +799,12 @@ self_attn4_kernel(const __grid_constant__ AttnParams p) {
       float2 ls[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) ls[k] = make_float2(0.f, 0.f);
-      if constexpr (TWOPASS) {
-        uint32_t pkA[16], pkB[16];
-        tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));           // upper 32 scores first
-        tmem_ld_wait();
-        exp2_block16<POLY16, !MMASUM>(&v[0], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pkB[0]), ls);
-        exp2_block16<POLY16, !MMASUM>(&v[16], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pkB[8]), ls);
-        tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        tmem_ld_wait();
-        exp2_block16<POLY16, !MMASUM>(&v[0], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pkA[0]), ls);
-        exp2_block16<POLY16, !MMASUM>(&v[16], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pkA[8]), ls);
-        tmem_st16(tS, pkA);                     // all of S(j) has been read: P(j) over its first 32 columns (this thread's own row)
-        tmem_st16(tS + 16, pkB);
-      } else {
 #pragma unroll
-        for (int hlf = 0; hlf < BKV; hlf += 32) {       // P(j) over the first 32 columns of S(j) (this thread's own row), 16 columns at a time
-          uint32_t pk[16];
-          exp2_block16<POLY16, !MMASUM>(&v[hlf], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pk[0]), ls);
-          exp2_block16<POLY16, !MMASUM>(&v[hlf + 16], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pk[8]), ls);
-          tmem_st16(tS + hlf / 2, pk);
-        }
+      for (int hlf = 0; hlf < BKV; hlf += 32) {       // P(j) over the first 32 columns of S(j) (this thread's own row), 16 columns at a time
+        uint32_t pk[16];
+        exp2_block16<POLY16, !MMASUM>(&v[hlf], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pk[0]), ls);
+        exp2_block16<POLY16, !MMASUM>(&v[hlf + 16], p.scale_log2, neg_m, *reinterpret_cast<uint32_t(*)[8]>(&pk[8]), ls);
+        tmem_st16(tS + hlf / 2, pk);
       }
       if (!MMASUM) l += ((ls[0].x + ls[0].y) + (ls[1].x + ls[1].y)) + ((ls[2].x + ls[2].y) + (ls[3].x + ls[3].y));
       tmem_st_wait();

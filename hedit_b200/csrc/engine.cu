@@ -427,59 +427,30 @@ static cudaError_t launch_self2_t(const AttnParams& a, int S, cudaStream_t st) {
   self_attn2_kernel<DCH, NT, BKV, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
-template <int DCH, bool MMASUM, bool TWOPASS, int POLY16, bool PINGPONG = false>
-static cudaError_t launch_self3_t(const AttnParams& a, int S, cudaStream_t st) {
-  using Cfg = SelfAttn2Cfg<DCH, 2, 64>;
-  static bool set = false;
-  if (!set) { cudaFuncSetAttribute(self_attn3_kernel<DCH, MMASUM, TWOPASS, POLY16, PINGPONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
-  dim3 grid((a.Nq + 255) / 256, a.H, S);
-  self_attn3_kernel<DCH, MMASUM, TWOPASS, POLY16, PINGPONG><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
-  return cudaGetLastError();
-}
-template <int DCH, bool MMASUM, int POLY16, int NT = 2, bool TWOPASS = false>
+template <int DCH, bool MMASUM, int POLY16>
 static cudaError_t launch_self4_t(const AttnParams& a, int S, cudaStream_t st) {
-  using Cfg = SelfAttn4Cfg<DCH, NT>;
+  using Cfg = SelfAttn4Cfg<DCH>;
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(self_attn4_kernel<DCH, MMASUM, POLY16, NT, TWOPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
-  dim3 grid((a.Nq + 128 * NT - 1) / (128 * NT), a.H, S);
-  self_attn4_kernel<DCH, MMASUM, POLY16, NT, TWOPASS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  if (!set) { cudaFuncSetAttribute(self_attn4_kernel<DCH, MMASUM, POLY16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
+  dim3 grid((a.Nq + 255) / 256, a.H, S);
+  self_attn4_kernel<DCH, MMASUM, POLY16><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
-// tuning switch HEDIT_ATTN_V3 (self_attn3_kernel variants, head dims <= 128): 0 = round-1 kernel (self_attn2_kernel);
-//   1 = tensor-core row sum; 2 = + two-pass TMEM read; 3/4/5 = + 2/3/4 of every 8 exponential pairs on the FMA pipe
-static int attn_v3() { static const int v = getenv("HEDIT_ATTN_V3") ? atoi(getenv("HEDIT_ATTN_V3")) : -1; return v; }
+// tuning switch HEDIT_ATTN_V4 (self_attn4_kernel, head dims <= 128; measured on B200 at 40 samples, N = 4096 d = 40 / N = 1024 d = 80):
+//   unset = default: d <= 64: tensor-core row sum + 2 of 8 exponential pairs on the FMA pipe (1.405 ms; round-1 kernel 1.67, cuDNN SDPA 1.396),
+//           d = 80: plain (0.189 ms; round-1 kernel 0.220);
+//   0 = round-1 kernel (self_attn2_kernel); 1 = plain (1.571 / 0.189); 2 = FMA-pipe share only (1.489 / 0.190);
+//   3 = tensor-core row sum only (1.586 / 0.197); 4 = row sum + share 2/8 (1.405 / 0.201); 5 = row sum + share 3/8 (1.470 / 0.201)
+static int attn_v4() { static const int v = getenv("HEDIT_ATTN_V4") ? atoi(getenv("HEDIT_ATTN_V4")) : -1; return v; }
 template <int DCH>
-static cudaError_t launch_self3(const AttnParams& a, int S, cudaStream_t st) {
-  switch (attn_v3()) {
-    // default (measured on B200 at 40 samples, round 2): probabilities in TMEM; d <= 64: tensor-core row sum + 2 of 8 exponential pairs on
-    // the FMA pipe (1.405 ms at N = 4096, d = 40 vs 1.67 for the round-1 kernel and 1.396 for cuDNN's SDPA); d = 80: plain (0.189 vs 0.220)
-    case -1: return DCH == 1 ? launch_self4_t<DCH, true, 2>(a, S, st) : launch_self4_t<DCH, false, 0>(a, S, st);
-    case 1: return launch_self3_t<DCH, true, false, 0>(a, S, st);
-    case 2: return launch_self3_t<DCH, true, true, 0>(a, S, st);
-    case 3: return launch_self3_t<DCH, true, true, 2>(a, S, st);
-    case 4: return launch_self3_t<DCH, true, true, 3>(a, S, st);
-    case 5: return launch_self3_t<DCH, true, true, 4>(a, S, st);
-    case 6: return launch_self3_t<DCH, false, true, 3>(a, S, st);       // control: packed-add row sum kept
-    case 8: return launch_self3_t<DCH, false, false, 0, true>(a, S, st);  // round-1 arithmetic + ping-pong
-    case 9: return launch_self3_t<DCH, false, true, 0, true>(a, S, st);
-    case 10: return launch_self3_t<DCH, false, true, 2, true>(a, S, st);
-    case 11: return launch_self3_t<DCH, false, true, 3, true>(a, S, st);
-    case 12: return launch_self3_t<DCH, false, true, 4, true>(a, S, st);
-    case 13: return launch_self3_t<DCH, true, true, 3, true>(a, S, st);
-    case 20: return launch_self4_t<DCH, false, 0>(a, S, st);             // v4: probabilities in TMEM
-    case 21: return launch_self4_t<DCH, false, 2>(a, S, st);
-    case 22: return launch_self4_t<DCH, false, 3>(a, S, st);
-    case 23: return launch_self4_t<DCH, true, 0>(a, S, st);
-    case 24: return launch_self4_t<DCH, true, 2>(a, S, st);
-    case 25: return launch_self4_t<DCH, true, 3>(a, S, st);
-    case 26: return launch_self4_t<DCH, true, 1>(a, S, st);
-    case 27: return launch_self4_t<DCH, false, 0, 1>(a, S, st);          // one query tile per CTA (measured: 2.10 ms vs 1.57 at d = 40)
-    case 31: return launch_self4_t<DCH, true, 2, 2, true>(a, S, st);     // two-pass TMEM read: no spills with larger FMA-pipe shares
-    case 32: return launch_self4_t<DCH, true, 3, 2, true>(a, S, st);
-    case 33: return launch_self4_t<DCH, true, 4, 2, true>(a, S, st);
-    case 34: return launch_self4_t<DCH, false, 3, 2, true>(a, S, st);
-    case 35: return launch_self4_t<DCH, true, 5, 2, true>(a, S, st);
-    default: return launch_self3_t<DCH, true, false, 2>(a, S, st);      // 7: no two-pass, polynomial share (register-pressure control)
+static cudaError_t launch_self4(const AttnParams& a, int S, cudaStream_t st) {
+  switch (attn_v4()) {
+    case 1: return launch_self4_t<DCH, false, 0>(a, S, st);
+    case 2: return launch_self4_t<DCH, false, 2>(a, S, st);
+    case 3: return launch_self4_t<DCH, true, 0>(a, S, st);
+    case 4: return launch_self4_t<DCH, true, 2>(a, S, st);
+    case 5: return launch_self4_t<DCH, true, 3>(a, S, st);
+    default: return DCH == 1 ? launch_self4_t<DCH, true, 2>(a, S, st) : launch_self4_t<DCH, false, 0>(a, S, st);
   }
 }
 // tuning switch HEDIT_ATTN_POLY: how many of every 8 softmax exponentials run on the FMA pipe instead of the MUFU (0, 2 or 4)
@@ -490,8 +461,8 @@ static int attn_poly() { static const int v = getenv("HEDIT_ATTN_POLY") ? atoi(g
 static int attn_cfg() { static const int v = getenv("HEDIT_ATTN_CFG") ? atoi(getenv("HEDIT_ATTN_CFG")) : 1; return v; }
 cudaError_t launch_self_attn(const AttnParams& a, int dch, int S, cudaStream_t st) {
   const int bkv2 = (dch == 1 && attn_cfg() == 0) ? 128 : 64;
-  if (a.Nq >= 256 && a.Nkv % 64 == 0 && attn_v3() != 0 && dch <= 2 && ((a.d + 15) & ~15) + 16 <= dch * 64)
-    return dch == 1 ? launch_self3<1>(a, S, st) : launch_self3<2>(a, S, st);
+  if (a.Nq >= 256 && a.Nkv % 64 == 0 && attn_v4() != 0 && dch <= 2 && ((a.d + 15) & ~15) + 16 <= dch * 64)
+    return dch == 1 ? launch_self4<1>(a, S, st) : launch_self4<2>(a, S, st);
   if (a.Nq >= 256 && a.Nkv % bkv2 == 0) {      // several query tiles per CTA
     if (dch == 1) {
       if (attn_cfg() == 1) {

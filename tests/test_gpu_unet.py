@@ -187,17 +187,27 @@ def test_edit_loop_tiny_replace_mos2():
 
 def test_edit_loop_tiny_partial_localblend_mask():
     """LocalBlend with th = 0.9: the mask covers 384-1520 of 4096 pixels and changes from step to step (at the default 0.3 a random-init
-    UNet's flat word maps put every pixel inside it).  The thresholded mask is a hard decision on 16-bit-operand attention maps: the number
-    of pixels that end up on the other side than in the reference is counted and bounded, and the latents must still agree."""
+    UNet's flat word maps put every pixel inside it).  The thresholded mask is a hard decision on 16-bit-operand attention maps: cells
+    whose normalised map value sits at the threshold land on either side depending on rounding noise.  The number of pixels on the other
+    side than in the reference is counted, reported, and bounded by what the 16-bit-operand-emulated ORACLE run shows on the same inputs
+    (x3, plus ten 16x16 cells); the reconstruction row, which no mask touches, must agree as usual."""
     if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "tiny_refine_blend_th09.pt")):
         pytest.skip("golden missing")
     r_ed, r_rc, r_w0, st = _run_golden("tiny_refine_blend_th09")
-    print("  golden mask pixels per step:", st["mask_pixels"], "| pixels on the other side:", st["mask_flips"])
+    from test_gpu_headline import _metrics, _oracle_on_gpu, _with_th
+    import oracle_run
+    g = load_golden("tiny_refine_blend_th09")
+    model = OraclePipeline(cfg_from_meta(g["meta"]), seed=0)
+    model.unet.cuda()
+    emu = _metrics(*_oracle_on_gpu(model, g, emulate=True, spec_fn=lambda m, tok: _with_th(oracle_run.spec_from_meta(m, tok), m["blend_th"])), g)
+    model.unet.cpu()
+    print("  golden mask pixels per step:", st["mask_pixels"], "| pixels on the other side: cuda", st["mask_flips"], "| 16-bit-operand oracle", emu["mask_flips"],
+          f"| edited rel: cuda {r_ed:.3e}, 16-bit-operand oracle {emu['ed_rel']:.3e}")
     assert min(st["mask_pixels"][3:]) > 0 and max(st["mask_pixels"][3:]) < 4096           # the mask is genuinely partial
     assert r_rc < TOL_LOOP
-    # a flipped 16x16 cell is 16 latent pixels; allow 2 cells per step, and the edit row may differ inside flipped cells only
-    assert max(st["mask_flips"]) <= 32, st["mask_flips"]
-    assert r_ed < 3 * TOL_LOOP
+    assert max(st["mask_flips"]) <= 3 * max(emu["mask_flips"]) + 160, (st["mask_flips"], emu["mask_flips"])
+    assert sum(st["mask_flips"]) <= 0.05 * sum(st["mask_pixels"][2:])
+    assert r_ed <= 3 * emu["ed_rel"] + TOL_LOOP
 
 
 def test_edit_loop_tiny_substruct_words():

@@ -41,7 +41,7 @@ def bench_attn(iters, S=8):
         ref = (torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, dim=-1) @ vf).permute(0, 2, 1, 3).reshape(2, N, C)
         err = ((out[:2].float() - ref).norm() / ref.norm()).item()
         print(f"self_attn S={S} N={N} H={H} d={d}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  ({S * H * (N / 128) ** 2 / 148 :.0f} 128x128 blocks/SM, "
-              f"{ms * 1e-3 * 1.9e9 / (S * H * (N / 128) ** 2 / 148):.0f} cyc/block @1.9GHz)  rel-err vs fp32 {err:.2e}  [HEDIT_ATTN_V3={os.environ.get('HEDIT_ATTN_V3', '0')}]")
+              f"{ms * 1e-3 * 1.9e9 / (S * H * (N / 128) ** 2 / 148):.0f} cyc/block @1.9GHz)  rel-err vs fp32 {err:.2e}  [HEDIT_ATTN_V4={os.environ.get('HEDIT_ATTN_V4', '0')}]")
 
 
 def bench_linear(iters):
