@@ -140,6 +140,21 @@ SYMBOLS = {
     "hedit_face_unet_forward": (_I, [_P, _P, _P, _I, _P, _P]),
     "hedit_face_last_flops": (C.c_double, [_P]),
     "hedit_face_edit": (_I, [_P, C.POINTER(FaceArgsC), _P]),
+    "hedit_arcface_create": (_P, [_I]),
+    "hedit_arcface_destroy": (None, [_P]),
+    "hedit_arcface_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
+    "hedit_arcface_finalize": (_I, [_P]),
+    "hedit_arcface_features": (_I, [_P, _P, _I, _P, _P]),
+    "hedit_arcface_set_reference": (_I, [_P, _P, _P]),
+    "hedit_arcface_loss_grad": (_I, [_P, _P, _I, _P, _P, _P]),
+    "hedit_arcface_last_flops": (C.c_double, [_P]),
+    "hedit_lpips_create": (_P, [_I]),
+    "hedit_lpips_destroy": (None, [_P]),
+    "hedit_lpips_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
+    "hedit_lpips_finalize": (_I, [_P]),
+    "hedit_lpips_set_source": (_I, [_P, _P, _I, _I, _P]),
+    "hedit_lpips_loss_grad": (_I, [_P, _P, _I, _P, _P, _P]),
+    "hedit_lpips_last_flops": (C.c_double, [_P]),
     "hedit_op_linear": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "hedit_op_linear_geglu": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "hedit_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -14,6 +14,7 @@
 #include "clip.h"
 #include "clip_text.h"
 #include "face.h"
+#include "reward.h"
 
 // Every entry point runs on its handle's device and restores the caller's current device on return: torch reads the current device from
 // the runtime, so leaving it switched would silently redirect the caller's later allocations and launches.
@@ -514,6 +515,103 @@ int hedit_face_edit(hedit_face* f, hedit_face_args* args, void* stream) {
   if (run_face_edit(*f->U, *args, reinterpret_cast<cudaStream_t>(stream))) return fail(f->U->error().empty() ? "face edit failed" : f->U->error());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ face-swapping reward networks
+struct hedit_arcface { ArcFaceNet* N; int device; };
+struct hedit_lpips { LpipsNet* N; int device; };
+
+static bool reward_device_ok(int device) {
+  if (hedit_device_count() <= device) { fail("hedit_b200 requires a CUDA device (sm_100a); none visible"); return false; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) { fail("hedit_b200 kernels are built for sm_100a only"); return false; }
+  return true;
+}
+hedit_arcface* hedit_arcface_create(int device) {
+  if (!reward_device_ok(device)) return nullptr;
+  DeviceGuard guard_(device);
+  if (guard_.err != cudaSuccess) { cuda_fail(guard_.err, "cudaSetDevice"); return nullptr; }
+  hedit_arcface* a = new hedit_arcface();
+  a->device = device; a->N = new ArcFaceNet();
+  return a;
+}
+void hedit_arcface_destroy(hedit_arcface* a) {
+  if (!a) return;
+  DeviceGuard guard_(a->device);
+  delete a->N;
+  delete a;
+}
+int hedit_arcface_load_tensor(hedit_arcface* a, const char* name, const float* data, const int64_t* dims, int ndim) {
+  if (!a) return fail("null arcface handle");
+  DeviceGuard guard_(a->device);
+  if (a->N->load_tensor(name, data, dims, ndim, 0)) return fail(a->N->error());
+  return 0;
+}
+int hedit_arcface_finalize(hedit_arcface* a) {
+  if (!a) return fail("null arcface handle");
+  DeviceGuard guard_(a->device);
+  if (a->N->finalize(0)) return fail(a->N->error());
+  return 0;
+}
+int hedit_arcface_features(hedit_arcface* a, const float* img, int B, float* feat, void* stream) {
+  if (!a) return fail("null arcface handle");
+  DeviceGuard guard_(a->device);
+  if (a->N->features(img, B, feat, reinterpret_cast<cudaStream_t>(stream))) return fail(a->N->error());
+  return int(a->N->launches());
+}
+int hedit_arcface_set_reference(hedit_arcface* a, const float* img, void* stream) {
+  if (!a) return fail("null arcface handle");
+  DeviceGuard guard_(a->device);
+  if (a->N->set_reference(img, reinterpret_cast<cudaStream_t>(stream))) return fail(a->N->error());
+  return 0;
+}
+int hedit_arcface_loss_grad(hedit_arcface* a, const float* img, int B, float* loss, float* grad, void* stream) {
+  if (!a) return fail("null arcface handle");
+  DeviceGuard guard_(a->device);
+  if (a->N->loss_grad(img, B, loss, grad, reinterpret_cast<cudaStream_t>(stream))) return fail(a->N->error());
+  return int(a->N->launches());
+}
+double hedit_arcface_last_flops(hedit_arcface* a) { return a ? a->N->flops() : 0.0; }
+
+hedit_lpips* hedit_lpips_create(int device) {
+  if (!reward_device_ok(device)) return nullptr;
+  DeviceGuard guard_(device);
+  if (guard_.err != cudaSuccess) { cuda_fail(guard_.err, "cudaSetDevice"); return nullptr; }
+  hedit_lpips* l = new hedit_lpips();
+  l->device = device; l->N = new LpipsNet();
+  return l;
+}
+void hedit_lpips_destroy(hedit_lpips* l) {
+  if (!l) return;
+  DeviceGuard guard_(l->device);
+  delete l->N;
+  delete l;
+}
+int hedit_lpips_load_tensor(hedit_lpips* l, const char* name, const float* data, const int64_t* dims, int ndim) {
+  if (!l) return fail("null lpips handle");
+  DeviceGuard guard_(l->device);
+  if (l->N->load_tensor(name, data, dims, ndim, 0)) return fail(l->N->error());
+  return 0;
+}
+int hedit_lpips_finalize(hedit_lpips* l) {
+  if (!l) return fail("null lpips handle");
+  DeviceGuard guard_(l->device);
+  if (l->N->finalize(0)) return fail(l->N->error());
+  return 0;
+}
+int hedit_lpips_set_source(hedit_lpips* l, const float* img, int n, int R, void* stream) {
+  if (!l) return fail("null lpips handle");
+  DeviceGuard guard_(l->device);
+  if (l->N->set_source(img, n, R, reinterpret_cast<cudaStream_t>(stream))) return fail(l->N->error());
+  return 0;
+}
+int hedit_lpips_loss_grad(hedit_lpips* l, const float* img, int B, float* loss, float* grad, void* stream) {
+  if (!l) return fail("null lpips handle");
+  DeviceGuard guard_(l->device);
+  if (l->N->loss_grad(img, B, loss, grad, reinterpret_cast<cudaStream_t>(stream))) return fail(l->N->error());
+  return int(l->N->launches());
+}
+double hedit_lpips_last_flops(hedit_lpips* l) { return l ? l->N->flops() : 0.0; }
 
 // ------------------------------------------------------------------------------------------------ CLIP-Gram style reward
 hedit_clip* hedit_clip_create(const hedit_clip_config* cfg, int device) {

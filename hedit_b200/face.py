@@ -6,6 +6,7 @@ caller's torch modules, differentiated by torch.autograd on the same CUDA stream
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -125,8 +126,11 @@ class FaceUNetEngine:
 
         def _cb(_user, which, step, opt_step):
             try:
-                g = (id_grad if which == 0 else lpips_grad)(x0_buf)
-                grad_buf.copy_(g.reshape(xT.shape).to(torch.float32))
+                f = id_grad if which == 0 else lpips_grad
+                if hasattr(f, "engine"):           # native reward network: writes the gradient in place
+                    f(x0_buf, out=grad_buf)
+                else:
+                    grad_buf.copy_(f(x0_buf).reshape(xT.shape).to(torch.float32))
                 return 0
             except Exception as exc:
                 errs.append(exc)
@@ -196,9 +200,14 @@ def h_Edit_R(model, lpipsloss, idloss, xT, betas, seq, eta=1.0, zs=None, weight_
     z = zs[:after_skip_steps]
     z = z.reshape(1, after_skip_steps, *x.shape[-3:]).expand(B, -1, -1, -1, -1) if z.dim() == 4 else z
     coef = face_step_tables(betas, seq, num_inference_steps, after_skip_steps, eta)
-    out = eng.edit(x, z, coef, weight_edit_face, optimization_steps,
-                   id_grad=_reward_grad(idloss.get_cosine_loss if idloss else None),
-                   lpips_grad=_reward_grad(lpipsloss.get_lpips_loss if lpipsloss else None), mask=soft_face_mask)
+    # the reference's own reward modules (IR-SE50 IDLoss, VGG16 LPIPS_Loss) run on the native kernels (reward.py: loss + image gradient,
+    # no autograd); any other object keeps the reward-model protocol and is differentiated by torch.autograd
+    from .reward import native_id_grad, native_lpips_grad
+    native = os.environ.get("HEDIT_NATIVE_REWARD", "1") != "0" and tuple(x.shape[-2:]) == (256, 256)
+    id_fn = (native_id_grad(idloss, eng.device) if (idloss and native) else None) or _reward_grad(idloss.get_cosine_loss if idloss else None)
+    lp_fn = (native_lpips_grad(lpipsloss, eng.device) if (lpipsloss and native) else None) or _reward_grad(lpipsloss.get_lpips_loss if lpipsloss else None)
+    out = eng.edit(x, z, coef, weight_edit_face, optimization_steps, id_grad=id_fn, lpips_grad=lp_fn, mask=soft_face_mask)
+    eng.last_stats["native_rewards"] = (hasattr(id_fn, "engine"), hasattr(lp_fn, "engine"))
     return out.to(dev)
 
 

@@ -30,37 +30,37 @@ class _SE(nn.Module):
 
 
 class _IRSEUnit(nn.Module):
-    """bottleneck_IR_SE: BN -> 3x3 -> PReLU -> 3x3 (stride) -> BN -> SE, plus a max-pool(1, stride) or 1x1-conv+BN shortcut."""
+    """bottleneck_IR_SE (helpers.py:100-125): BN -> 3x3 -> PReLU -> 3x3 (stride) -> BN -> SE, plus a strided-identity (MaxPool2d(1, s)) or
+    1x1-conv+BN shortcut.  Attribute names give the reference's state_dict keys (`shortcut_layer.0.weight`, `res_layer.5.fc1.weight`)."""
 
     def __init__(self, cin, cout, stride):
         super().__init__()
-        self.short = None if cin == cout else nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
-        self.stride = stride
-        self.res = nn.Sequential(nn.BatchNorm2d(cin), nn.Conv2d(cin, cout, 3, 1, 1, bias=False), nn.PReLU(cout),
-                                 nn.Conv2d(cout, cout, 3, stride, 1, bias=False), nn.BatchNorm2d(cout), _SE(cout))
+        self.shortcut_layer = nn.MaxPool2d(1, stride) if cin == cout else nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+        self.res_layer = nn.Sequential(nn.BatchNorm2d(cin), nn.Conv2d(cin, cout, 3, 1, 1, bias=False), nn.PReLU(cout),
+                                       nn.Conv2d(cout, cout, 3, stride, 1, bias=False), nn.BatchNorm2d(cout), _SE(cout))
 
     def forward(self, x):
-        s = self.short(x) if self.short is not None else (x if self.stride == 1 else x[:, :, ::self.stride, ::self.stride])
-        return self.res(x) + s
+        return self.res_layer(x) + self.shortcut_layer(x)
 
 
 class IRSE50(nn.Module):
-    """IR-SE50 face-recognition backbone: 112x112 input, stages of (3, 4, 14, 3) units at 64/128/256/512 channels, 512-d output."""
+    """IR-SE50 face-recognition backbone (model_irse.py:9-56 with num_layers=50, mode='ir_se'): 112x112 input, stages of (3, 4, 14, 3)
+    units at 64/128/256/512 channels, 512-d l2-normalised output.  state_dict-compatible with the reference's `Backbone`."""
 
     def __init__(self):
         super().__init__()
-        self.stem = nn.Sequential(nn.Conv2d(3, 64, 3, 1, 1, bias=False), nn.BatchNorm2d(64), nn.PReLU(64))
+        self.input_layer = nn.Sequential(nn.Conv2d(3, 64, 3, 1, 1, bias=False), nn.BatchNorm2d(64), nn.PReLU(64))
+        self.output_layer = nn.Sequential(nn.BatchNorm2d(512), nn.Dropout(0.6), nn.Flatten(), nn.Linear(512 * 7 * 7, 512), nn.BatchNorm1d(512))
         units, cin = [], 64
         for cout, n in ((64, 3), (128, 4), (256, 14), (512, 3)):
             for k in range(n):
                 units.append(_IRSEUnit(cin, cout, 2 if k == 0 else 1))
                 cin = cout
         self.body = nn.Sequential(*units)
-        self.head = nn.Sequential(nn.BatchNorm2d(512), nn.Flatten(), nn.Linear(512 * 7 * 7, 512), nn.BatchNorm1d(512))
 
     def forward(self, x):
-        f = self.head(self.body(self.stem(x)))
-        return f / f.norm(dim=1, keepdim=True)            # l2_norm (model_irse.py:77-84)
+        f = self.output_layer(self.body(self.input_layer(x)))
+        return f / f.norm(dim=1, keepdim=True)            # l2_norm (helpers.py:15-18)
 
 
 class LPIPSVGG16(nn.Module):
@@ -116,6 +116,38 @@ def _seed_init(m: nn.Module, seed: int):
             elif isinstance(mod, nn.PReLU):
                 mod.weight.copy_(0.1 + 0.3 * torch.rand(mod.weight.shape, generator=g))
     return m.eval().requires_grad_(False)
+
+
+class SyntheticIDLoss(nn.Module):
+    """Same protocol and attribute layout as the reference's IDLoss (arcface_model.py:12-70: `.facenet`, `.ref`, `get_cosine_loss`), with
+    seeded random weights and a given reference face instead of model_ir_se50.pth / a jpg."""
+
+    def __init__(self, ref_img: torch.Tensor, seed: int = 0):
+        super().__init__()
+        self.facenet = _seed_init(IRSE50(), seed)
+        self.ref = ref_img.detach().reshape(-1, 3, 256, 256)[:1].clone()
+
+    def extract_feats(self, x):
+        return id_features(self.facenet, x)
+
+    def get_cosine_loss(self, image):
+        return (1 - F.cosine_similarity(F.normalize(self.extract_feats(self.ref.to(image.device)), dim=-1),
+                                        F.normalize(self.extract_feats(image), dim=-1), dim=-1)).mean()
+
+
+class SyntheticLPIPSLoss(nn.Module):
+    """Same protocol and attribute layout as the reference's LPIPS_Loss (arcface_model.py:72-95: `.lpips_loss`, `.src`, `get_lpips_loss`)."""
+
+    def __init__(self, src_img: torch.Tensor, seed: int = 1):
+        super().__init__()
+        self.lpips_loss = _seed_init(LPIPSVGG16(), seed)
+        self.src = src_img.detach().clone()
+
+    def get_lpips_loss(self, x):
+        src = self.src.to(x.device)
+        with torch.no_grad():
+            taps = [f / (f.pow(2).sum(1, keepdim=True).sqrt() + 1e-10) for f in self.lpips_loss.taps(src)]
+        return self.lpips_loss(x, taps).mean()
 
 
 def id_features(net: IRSE50, img: torch.Tensor) -> torch.Tensor:

@@ -299,6 +299,37 @@ typedef struct hedit_face_args {
 } hedit_face_args;
 int hedit_face_edit(hedit_face* f, hedit_face_args* args, void* stream);
 
+/* ---- face-swapping reward networks, forward + input gradient (no autograd) ------------------------------------
+ * hedit_arcface replaces `IDLoss.get_cosine_loss` + `torch.autograd.grad` (face-swapping/arcface/arcface_model.py:41-70; IR-SE50
+ * backbone arcface/facial_recognition/model_irse.py:9-56, helpers.py:47-125; call site inversion/h_edit_R.py:109-110).
+ * Tensors are loaded under the state_dict keys of the reference's `Backbone(112, 50, mode='ir_se')` ("input_layer.0.weight",
+ * "body.3.res_layer.4.running_var", "output_layer.3.weight", ...); BatchNorm folding happens in hedit_arcface_finalize.
+ * hedit_lpips replaces `LPIPS_Loss.get_lpips_loss` + autograd (arcface_model.py:72-95; lpips package 0.1, net='vgg'; call site
+ * h_edit_R.py:128-129).  Tensor names: "conv0".."conv12" .weight/.bias (the 13 VGG16 convs in order), "lin0".."lin4" .weight ([C]),
+ * "shift", "scale" ([3], the ScalingLayer). */
+typedef struct hedit_arcface hedit_arcface;
+hedit_arcface* hedit_arcface_create(int device);
+void hedit_arcface_destroy(hedit_arcface* a);
+int hedit_arcface_load_tensor(hedit_arcface* a, const char* name, const float* data, const int64_t* dims, int ndim);
+int hedit_arcface_finalize(hedit_arcface* a);
+/* img [B][3][256][256] device fp32 in [-1, 1] -> unit-norm embedding [B][512] (device) */
+int hedit_arcface_features(hedit_arcface* a, const float* img, int B, float* feat, void* stream);
+/* the face whose identity is transferred (IDLoss.ref): img [1][3][256][256] device */
+int hedit_arcface_set_reference(hedit_arcface* a, const float* img, void* stream);
+/* loss[b] = 1 - cos(ref, f(img[b])) (device [B] or NULL); grad [B][3][256][256] = d loss[b] / d img[b].  Returns kernels launched. */
+int hedit_arcface_loss_grad(hedit_arcface* a, const float* img, int B, float* loss, float* grad, void* stream);
+double hedit_arcface_last_flops(hedit_arcface* a);
+typedef struct hedit_lpips hedit_lpips;
+hedit_lpips* hedit_lpips_create(int device);
+void hedit_lpips_destroy(hedit_lpips* l);
+int hedit_lpips_load_tensor(hedit_lpips* l, const char* name, const float* data, const int64_t* dims, int ndim);
+int hedit_lpips_finalize(hedit_lpips* l);
+/* anchor image(s) (LPIPS_Loss.src): img [n][3][R][R] device, n = 1 (shared) or the batch size; R = 128, 256 or 512 */
+int hedit_lpips_set_source(hedit_lpips* l, const float* img, int n, int R, void* stream);
+/* loss[b] = LPIPS(img[b], src) (device [B] or NULL); grad [B][3][R][R] = d loss[b] / d img[b].  Returns kernels launched. */
+int hedit_lpips_loss_grad(hedit_lpips* l, const float* img, int B, float* loss, float* grad, void* stream);
+double hedit_lpips_last_flops(hedit_lpips* l);
+
 /* ---- single operators, exposed for parity tests (device pointers) ------------------------------------------- */
 /* D[M][N] = A[M][K] W[N][K]^T (+bias) (+residual) -> fp32 and/or 16-bit; A, W in the operand dtype (hedit_operand_dtype) */
 int hedit_op_linear(const void* A_h16, const void* W_h16, const float* bias, const float* residual, float* out_f32, void* out_h16,
