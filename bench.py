@@ -33,6 +33,32 @@ TFLOP_PER_SAMPLE_FORWARD = 0.8033            # SD-1.x UNet, 64x6
 GEMM_TFLOP_PER_SAMPLE_FORWARD = 2 * (200.16 + 138.42) * 1e-3      # conv3x3 + linear/1x1 GMAC of one sample-forward
 TFLOP_PER_FACE_FORWARD = 0.497               # CelebA-HQ DDPM UNet, 256x256
 TFLOP_PER_STYLE_REWARD = 2.514 + 2.55 + 0.03  # VAE decode + its backward + CLIP-Gram fwd/bwd per image and Langevin step
+
+
+def _irse50_tflop():
+    """conv flops of one IR-SE50 forward + input-gradient backward on a 112x112 crop (model_irse.py / helpers.py get_blocks(50))"""
+    f, v, cin = 2.0 * 112 * 112 * 27 * 64, 112, 64
+    for depth, n in ((64, 3), (128, 4), (256, 14), (512, 3)):
+        for k in range(n):
+            s = 2 if k == 0 else 1
+            f += 2.0 * v * v * 9 * cin * depth + 2.0 * (v // s) ** 2 * 9 * depth * depth + (2.0 * (v // s) ** 2 * cin * depth if cin != depth else 0.0)
+            v //= s
+            cin = depth
+    return 2 * (f + 2.0 * 25088 * 512) * 1e-12
+
+
+def _vgg16_lpips_tflop(R=256):
+    """conv flops of one VGG16 feature forward + input-gradient backward at R x R (the LPIPS network)"""
+    f, h, cin = 0.0, R, 3
+    for i, c in enumerate((64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512)):
+        f += 2.0 * h * h * 9 * cin * c
+        cin = c
+        if i in (1, 3, 6, 9):
+            h //= 2
+    return 2 * f * 1e-12
+
+
+TFLOP_PER_FACE_REWARDS = _irse50_tflop() + _vgg16_lpips_tflop()      # one identity + one LPIPS gradient of one image
 PROMPT_PAIRS = [
     (["a green lizard is sitting on a branch", "a brown lizard is sitting on a branch"], ("lizard", "lizard"), False),
     (["a cat sitting next to a mirror", "a silver cat sculpture sitting next to a mirror"], ("cat", "cat"), False),
@@ -365,7 +391,16 @@ class FaceSwap:
         self.xT_d, self.zs_d = self.xT_h.to(dev), self.zs_h.to(dev)
         ref_img = torch.tanh(torch.randn(1, 3, 256, 256, generator=g)).to(dev)
         src_img = torch.tanh(torch.randn(B, 3, 256, 256, generator=g)).to(dev)
-        self.id_grad, self.lp_grad, self.reward_kind = reward_nets.make_reward_grads(ref_img, src_img, dev, seed=3)
+        if os.environ.get("HEDIT_NATIVE_REWARD", "1") != "0":
+            # reward objects with the reference's IDLoss / LPIPS_Loss layout -> native IR-SE50 / VGG16 forward + input gradient (reward.cu)
+            from hedit_b200 import reward
+            self.idl = reward_nets.SyntheticIDLoss(ref_img, seed=3).to(dev)
+            self.lpl = reward_nets.SyntheticLPIPSLoss(src_img, seed=4).to(dev)
+            self.id_grad, self.lp_grad = reward.native_id_grad(self.idl, dev.index), reward.native_lpips_grad(self.lpl, dev.index)
+            assert self.id_grad is not None and self.lp_grad is not None
+            self.reward_kind = "IR-SE50 (112x112 crop) + LPIPS-VGG16 (256x256) at full geometry, seeded random weights, native kernels (csrc/reward.cu)"
+        else:
+            self.id_grad, self.lp_grad, self.reward_kind = reward_nets.make_reward_grads(ref_img, src_img, dev, seed=3)
         self.h2d = (self.xT_h.numel() + self.zs_h.numel()) * 4
         self.d2h = self.xT_h.numel() * 4
 
@@ -377,7 +412,7 @@ class FaceSwap:
         return ed, dict(self.eng.last_stats)
 
     def tflop(self, stats):
-        return stats["sample_forwards"] * TFLOP_PER_FACE_FORWARD
+        return stats["sample_forwards"] * TFLOP_PER_FACE_FORWARD + self.B * (self.T - 1) * self.K * TFLOP_PER_FACE_REWARDS
 
     single_image = None
 

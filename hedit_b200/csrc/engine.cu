@@ -297,7 +297,7 @@ int Engine::finalize_weights(std::string* missing) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM descriptors
-static int pick_bn(int M, int N) {
+static int pick_bn(int M, int N, bool narrow_ok) {
   static const int force = getenv("HEDIT_GEMM_BN") ? atoi(getenv("HEDIT_GEMM_BN")) : 0;     // tuning switch
   if (force == 160 || force == 256) return force;
   // Measured on B200: one 128 x BN x 16 MMA step costs ~ BN/2 + 90 cycles (operand fetch + TMA refill share the SM's shared-
@@ -306,13 +306,21 @@ static int pick_bn(int M, int N) {
     const long tiles = long((M + 127) / 128) * ((N + bn - 1) / bn);
     return double((tiles + 147) / 148) * (bn / 2 + 90);
   };
-  return cost(256) < cost(160) ? 256 : 160;
+  int best = cost(256) < cost(160) ? 256 : 160;
+  // narrow tiles (round 2): N = 64 / 128 layers of the face-swapping networks (DDPM UNet at 128 channels, IR-SE50, VGG16) waste
+  // 20-60 % of a 160-column tile, and launches with fewer tiles than SMs get more CTAs.  Ties keep the wider tile.
+  static const bool narrow_off = getenv("HEDIT_GEMM_NARROW") && atoi(getenv("HEDIT_GEMM_NARROW")) == 0;
+  if (narrow_ok && !narrow_off) {
+    if (cost(128) < cost(best)) best = 128;
+    if (cost(64) < cost(best)) best = 64;
+  }
+  return best;
 }
 
 bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode, const ConvGeom* cg, const bf16* Wt, int M, int N,
                int Ktot, const GemmEpilogue& ep, std::string& err, int ldw) {
   memset(&g, 0, sizeof g);
-  bn = pick_bn(M, N);
+  bn = pick_bn(M, N, !ep.geglu && !gemm_cluster());
   g.M = M; g.N = N; g.a_mode = a_mode; g.ep = ep;
   g.num_kb = (Ktot + 63) / 64;
   bool ok = true;
@@ -347,6 +355,14 @@ bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode, const
   uint64_t dimsB[2] = {uint64_t(Ktot), uint64_t(N)}; uint64_t strB[1] = {uint64_t(ldw > 0 ? ldw : Ktot) * 2}; uint32_t boxB[2] = {64, uint32_t(gemm_cluster() ? bn / 2 : bn)};
   g.b_full_box = gemm_cluster() ? 0 : 1;
   if (!make_tmap_bf16(&g.tmB, Wt, 2, dimsB, strB, boxB)) { err = "tensor map (B) encode failed"; return false; }
+  // 16-bit outputs without bias / residual on 256-column tiles (q|k|v, q, text k|v projections): bulk tensor stores of the staged tile.
+  // HEDIT_GEMM_TMA_STORE=0 keeps the per-lane 16-byte stores.
+  static const bool tmd_on = !(getenv("HEDIT_GEMM_TMA_STORE") && atoi(getenv("HEDIT_GEMM_TMA_STORE")) == 0);
+  if (tmd_on && bn == 256 && ep.out_bf16 && !ep.out_f32 && !ep.bias && !ep.rowvec && !ep.residual && !ep.geglu && (N % 64) == 0 && (ep.ldob % 8) == 0 &&
+      (reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0) {
+    uint64_t dimsD[2] = {uint64_t(N), uint64_t(M)}; uint64_t strD[1] = {uint64_t(ep.ldob) * 2}; uint32_t boxD[2] = {64, 32};
+    g.use_tmd = make_tmap_bf16(&g.tmD, ep.out_bf16, 2, dimsD, strD, boxD) ? 1 : 0;
+  }
   return true;
 }
 
@@ -389,6 +405,8 @@ cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st) {
   // (EPI == 2, a 16-warp write-back for the bias + fp32 residual -> fp32 projections at K <= 640, was measured at 0.112 vs 0.114 ms on the
   // 163840 x 320 x 320 case: those launches already move 4.7 TB/s, so it is not instantiated)
   if (bn == 256) return cl ? launch_gemm_t<256, true>(g, st) : launch_gemm_t<256, false>(g, st);
+  if (bn == 128 && !cl) return launch_gemm_t<128, false>(g, st);
+  if (bn == 64 && !cl) return launch_gemm_t<64, false>(g, st);
   return cl ? launch_gemm_t<160, true>(g, st) : launch_gemm_t<160, false>(g, st);
 }
 

@@ -40,6 +40,8 @@ struct GemmEpilogue {
 
 struct GemmParams {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmD;          // 16-bit output [M][ldob] as boxes of 64 columns x 32 rows (128B swizzle) when use_tmd (bulk tensor stores)
+  int use_tmd;
   int M, N, num_kb;
   int a_mode, conv_W, conv_H, conv_cin, cin_blocks;
   int conv_ox, conv_oy;     // A_CONV2X2 only: first tap offset per axis (-1 for output phase 0, 0 for phase 1)
@@ -95,7 +97,7 @@ struct GemmCfg {
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;     // PAIR: each CTA stages half of the W tile
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (PAIR ? (BN > 160 ? 6 : 7) : (BN > 160 ? 4 : 5)) - (EPI == 2 ? 1 : 0);
+  static constexpr int STAGES = (PAIR ? (BN > 160 ? 6 : 7) : (BN > 160 ? 4 : (BN > 128 ? 5 : (BN > 64 ? 6 : 8)))) - (EPI == 2 ? 1 : 0);
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + (EPI == 2 ? 16 : 8) * 4096 /*epilogue staging*/;
   static constexpr int THREADS = EPI ? 576 : 320;
 };
@@ -122,7 +124,8 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();     // 128B-swizzle tiles need 1024-byte alignment
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  constexpr uint32_t STG_BYTES = (EPI == 2 ? 16 : 8) * 4096;      // epilogue staging: right after the ring, so every 4 KB slice is 1024-byte aligned (TMA store source)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const GemmEpilogue& e = p.ep;
-    float4* stg = reinterpret_cast<float4*>(smem + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * (GEGLU ? 64 : 256);   // [32 rows][8 quads] (GEGLU: [32 rows][32 B])
+    float4* stg = reinterpret_cast<float4*>(smem + STAGES * Cfg::STAGE_BYTES) + (warp - 2) * (GEGLU ? 64 : 256);   // [32 rows][8 quads] (GEGLU: [32 rows][32 B])
     const int rq = lane & 7, rr = lane >> 3;           // read-back role (non-GEGLU): quad, row-in-group-of-4
     // feature combination of this launch -> specialised write-back loop (0 = generic path)
     const bool has_b = e.bias != nullptr, has_rv = e.rowvec != nullptr, has_res = e.residual != nullptr;
@@ -394,20 +397,32 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
           tmem_ld32(t_row + c0, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
           tmem_ld32(t_row + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
           tmem_ld_wait();
+          if (p.use_tmd) { if (lane == 0) tma_store_wait_read0(); __syncwarp(); }      // the previous bulk store has read the staging tile
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             *reinterpret_cast<uint4*>(stg16 + lane * 64 + ((u ^ (lane & 7)) << 3)) =
                 make_uint4(pack_op2(__uint_as_float(raw[8 * u]), __uint_as_float(raw[8 * u + 1])), pack_op2(__uint_as_float(raw[8 * u + 2]), __uint_as_float(raw[8 * u + 3])),
                            pack_op2(__uint_as_float(raw[8 * u + 4]), __uint_as_float(raw[8 * u + 5])), pack_op2(__uint_as_float(raw[8 * u + 6]), __uint_as_float(raw[8 * u + 7])));
-          __syncwarp();
-          op_t* o16 = e.out_bf16 + size_t(rbase + wr) * e.ldob + col + 8 * wu;
+          if (p.use_tmd) {
+            // the staging tile IS the 128B-swizzled box layout (16-byte slot ^ (row & 7)): one bulk tensor store per 32 x 64 tile instead
+            // of 8 STG.128 per lane; the source is reused only after the TMA engine has read it (wait at the top of the next iteration,
+            // so the store overlaps the next chunk's TMEM read)
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&p.tmD, stg16, col, rbase); tma_store_commit(); }
+            __syncwarp();
+          } else {
+            __syncwarp();
+            op_t* o16 = e.out_bf16 + size_t(rbase + wr) * e.ldob + col + 8 * wu;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + wr;
-            *reinterpret_cast<uint4*>(o16 + size_t(4 * i) * e.ldob) = *reinterpret_cast<const uint4*>(stg16 + r * 64 + ((wu ^ (r & 7)) << 3));
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + wr;
+              *reinterpret_cast<uint4*>(o16 + size_t(4 * i) * e.ldob) = *reinterpret_cast<const uint4*>(stg16 + r * 64 + ((wu ^ (r & 7)) << 3));
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
+        if (p.use_tmd && lane == 0) tma_store_wait0();      // global writes of this tile are complete before the kernel can end
       } else
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BN; c0 += CSTEP) {
