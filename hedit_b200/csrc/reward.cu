@@ -224,7 +224,7 @@ int ArcFaceNet::run_forward(const float* img, int B) {
     float* gate = A<float>(size_t(B) * d);
     if (!dry_) {
       rw_pool_partial_kernel<<<dim3(nch, B), 256, 512 * sizeof(float4), st_>>>(r, nullptr, partial, nullptr, Po, Vo, d);
-      rw_se_fc_kernel<<<B, 128, 0, st_>>>(partial, nch, u.se_w1, u.se_w2, h, gate, d, 1.f / float(Vo * Vo));
+      rw_se_fc_kernel<<<B, 512, 0, st_>>>(partial, nch, u.se_w1, u.se_w2, h, gate, d, 1.f / float(Vo * Vo));
       launches_ += 2;
     }
     const float* sc = x; int sc_stride = u.stride;
@@ -251,7 +251,7 @@ int ArcFaceNet::run_forward(const float* img, int B) {
   feat_ = A<float>(size_t(B) * 512);
   if (!dry_) {
     for (int b0 = 0; b0 < B; b0 += RW_HEAD_MAXB) {
-      rw_head_fwd_kernel<<<512 / 4 / 4, 128, 0, st_>>>(x + size_t(b0) * 64 * 512, wh_, bh_, feat_ + size_t(b0) * 512, std::min(RW_HEAD_MAXB, B - b0));
+      rw_head_fwd_kernel<<<256, 256, 0, st_>>>(x + size_t(b0) * 64 * 512, wh_, bh_, feat_ + size_t(b0) * 512, std::min(RW_HEAD_MAXB, B - b0));
       ++launches_;
     }
     RCK(cudaGetLastError());
@@ -279,7 +279,7 @@ int ArcFaceNet::run_backward(float* grad, int B) {
     op_t* dr16 = A<op_t>(size_t(B) * P * P * d);          // (P = 2 Po when up)
     if (!dry_) {
       rw_pool_partial_kernel<<<dim3(nch, B), 256, 512 * sizeof(float4), st_>>>(dout, tp.r, partial, sqpart, Po, Vo, d);
-      rw_se_bwd_kernel<<<B, 128, 0, st_>>>(partial, sqpart, nch, u.se_w1, u.se_w2, tp.h, tp.gate, dmean, gscale, d, 1.f / float(Vo * Vo));
+      rw_se_bwd_kernel<<<B, 512, 0, st_>>>(partial, sqpart, nch, u.se_w1, u.se_w2, tp.h, tp.gate, dmean, gscale, d, 1.f / float(Vo * Vo));
       rw_dr_kernel<<<pw_grid(P, d, B), 256, 0, st_>>>(dout, tp.gate, dmean, gscale, dr16, Po, Vo, d, up);
       launches_ += 3;
     }
@@ -419,7 +419,7 @@ int LpipsNet::finalize(cudaStream_t st) {
     float h_ss[13] = {0};
     for (int i = 1; i < 13; ++i) {
       const Conv& c = conv_[i];
-      rw_sumsq_kernel<<<1, 256, 0, st>>>(raw_.get("conv" + std::to_string(i) + ".weight", size_t(c.cout) * c.cin * 9, err_), size_t(c.cout) * c.cin * 9, d_ss + i);
+      rw_sumsq_kernel<<<1, 1024, 0, st>>>(raw_.get("conv" + std::to_string(i) + ".weight", size_t(c.cout) * c.cin * 9, err_), size_t(c.cout) * c.cin * 9, d_ss + i);
     }
     RCK(cudaMemcpyAsync(h_ss, d_ss, sizeof h_ss, cudaMemcpyDeviceToHost, st));
     RCK(cudaStreamSynchronize(st));

@@ -207,7 +207,7 @@ static __global__ void rw_gather2_kernel(const float* __restrict__ x, op_t* __re
 
 // per-sample channel sums over the valid corner: partial[b][chunk][c] = sum_{pixels of chunk} a * (w ? w : 1); chunk = RW_POOL_ROWS rows.
 // blockDim = 256 = (C/4 quads) x nsub pixel lanes; fixed summation order (no atomics).
-constexpr int RW_POOL_ROWS = 8;
+constexpr int RW_POOL_ROWS = 2;
 // sq (optional): per-channel sums of a^2 in the same layout (the backward's per-sample gradient magnitude, see rw_se_bwd_kernel).
 static __global__ void rw_pool_partial_kernel(const float* __restrict__ a, const float* __restrict__ w, float* __restrict__ partial,
                                               float* __restrict__ sq, int P, int V, int C) {
@@ -245,12 +245,19 @@ static __global__ void rw_pool_partial_kernel(const float* __restrict__ a, const
 // squeeze-excitation gate (helpers.py SEModule): m = mean(r); h = relu(W1 m); gate = sigmoid(W2 h).  grid B, block 128.  C <= 512.
 static __global__ void rw_se_fc_kernel(const float* __restrict__ partial, int nch, const float* __restrict__ w1, const float* __restrict__ w2,
                                        float* __restrict__ hbuf, float* __restrict__ gate, int C, float inv_n) {
-  __shared__ float m[512], h[32];
+  __shared__ float m[512], h[32], red[512];
   const int b = blockIdx.x, Cr = C / 16;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  {   // blockDim = 512 = C channels x (512 / C) chunk lanes; lanes are combined in a fixed order
+    const int lanes = blockDim.x / C, c = threadIdx.x % C, kl = threadIdx.x / C;
     float s = 0.f;
-    for (int k = 0; k < nch; ++k) s += partial[(size_t(b) * nch + k) * C + c];
-    m[c] = s * inv_n;
+    for (int k = kl; k < nch; k += lanes) s += partial[(size_t(b) * nch + k) * C + c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float t = red[c];
+      for (int l = 1; l < lanes; ++l) t += red[l * C + c];
+      m[c] = t * inv_n;
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -275,22 +282,32 @@ static __global__ void rw_se_fc_kernel(const float* __restrict__ partial, int nc
 static __global__ void rw_se_bwd_kernel(const float* __restrict__ partial, const float* __restrict__ sq, int nch, const float* __restrict__ w1,
                                         const float* __restrict__ w2, const float* __restrict__ hbuf, const float* __restrict__ gate,
                                         float* __restrict__ dmean, float* __restrict__ gscale, int C, float inv_n) {
-  __shared__ float dz[512], dh[32], sred[128];
+  __shared__ float dz[512], dh[32], red[512], red2[512];
   const int b = blockIdx.x, Cr = C / 16;
-  float ss = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < nch; ++k) { s += partial[(size_t(b) * nch + k) * C + c]; ss += sq[(size_t(b) * nch + k) * C + c]; }
-    const float g = gate[size_t(b) * C + c];
-    dz[c] = s * g * (1.f - g);
-  }
-  sred[threadIdx.x] = ss;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int k = 0; k < int(blockDim.x); ++k) t += sred[k];
-    const float ms = t * inv_n / float(C);
-    gscale[b] = ms > 1e-36f ? rsqrtf(ms) : 1.f;
+  {   // blockDim = 512 = C channels x (512 / C) chunk lanes
+    const int lanes = blockDim.x / C, c = threadIdx.x % C, kl = threadIdx.x / C;
+    float s = 0.f, ss = 0.f;
+    for (int k = kl; k < nch; k += lanes) { s += partial[(size_t(b) * nch + k) * C + c]; ss += sq[(size_t(b) * nch + k) * C + c]; }
+    red[threadIdx.x] = s; red2[threadIdx.x] = ss;
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float t = red[c], t2 = red2[c];
+      for (int l = 1; l < lanes; ++l) { t += red[l * C + c]; t2 += red2[l * C + c]; }
+      const float g = gate[size_t(b) * C + c];
+      dz[c] = t * g * (1.f - g);
+      red2[c] = t2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {      // sum of the per-channel squares in a fixed order: lane strides, then a shuffle tree
+      float t = 0.f;
+      for (int cc = threadIdx.x; cc < C; cc += 32) t += red2[cc];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (threadIdx.x == 0) {
+        const float ms = t * inv_n / float(C);
+        gscale[b] = ms > 1e-36f ? rsqrtf(ms) : 1.f;
+      }
+    }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int j = warp; j < Cr; j += blockDim.x >> 5) {
@@ -397,23 +414,26 @@ static __global__ void rw_cast_masked_kernel(const float* __restrict__ x, const 
 
 // ------------------------------------------------------------------------------------------------ IR-SE50 embedding layer
 // output_layer (model_irse.py:23-27) with both BatchNorms folded: f[b][o] = bias[o] + sum_{pos < 49, c < 512} W[o][pos][c] * x[b][pos][c];
-// x [B][8][8][512] fp32 (7 x 7 valid), W 16-bit [512][49][512].  One warp per (4 outputs); B <= RW_HEAD_MAXB per launch.
+// x [B][8][8][512] fp32 (7 x 7 valid), W 16-bit [512][49][512].  B <= RW_HEAD_MAXB per launch.
 constexpr int RW_HEAD_MAXB = 8;
+// one block (256 threads) per 2 outputs: the 25088-long dot products are split over the 8 warps and combined in a fixed order
 static __global__ void rw_head_fwd_kernel(const float* __restrict__ x, const op_t* __restrict__ W, const float* __restrict__ bias,
                                           float* __restrict__ f, int B) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int o0 = warp * 4;
-  if (o0 >= 512) return;
-  float acc[4][RW_HEAD_MAXB];
+  __shared__ float part[8][2][RW_HEAD_MAXB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o0 = blockIdx.x * 2;
+  float acc[2][RW_HEAD_MAXB];
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int j = 0; j < 2; ++j)
 #pragma unroll
     for (int b = 0; b < RW_HEAD_MAXB; ++b) acc[j][b] = 0.f;
-  for (int k = lane * 4; k < 49 * 512; k += 128) {
+  constexpr int KW = 49 * 512 / 8;       // 3136 inputs per warp
+#pragma unroll 2
+  for (int k = warp * KW + lane * 4; k < (warp + 1) * KW; k += 128) {
     const int pos = k >> 9, c = k & 511, cell = (pos / 7) * 8 + (pos % 7);
-    float wv[4][4];
+    float wv[2][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 2; ++j) {
       const uint2 u = *reinterpret_cast<const uint2*>(W + size_t(o0 + j) * 49 * 512 + k);
       const float2 a = op2_to_float2(u.x), bq = op2_to_float2(u.y);
       wv[j][0] = a.x; wv[j][1] = a.y; wv[j][2] = bq.x; wv[j][3] = bq.y;
@@ -423,19 +443,29 @@ static __global__ void rw_head_fwd_kernel(const float* __restrict__ x, const op_
       if (b < B) {
         const float4 xv = *reinterpret_cast<const float4*>(x + (size_t(b) * 64 + cell) * 512 + c);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j][b] = fmaf(wv[j][0], xv.x, fmaf(wv[j][1], xv.y, fmaf(wv[j][2], xv.z, fmaf(wv[j][3], xv.w, acc[j][b]))));
+        for (int j = 0; j < 2; ++j) acc[j][b] = fmaf(wv[j][0], xv.x, fmaf(wv[j][1], xv.y, fmaf(wv[j][2], xv.z, fmaf(wv[j][3], xv.w, acc[j][b]))));
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int j = 0; j < 2; ++j)
 #pragma unroll
     for (int b = 0; b < RW_HEAD_MAXB; ++b) {
       float v = acc[j][b];
 #pragma unroll
       for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && b < B) f[size_t(b) * 512 + o0 + j] = v + bias[o0 + j];
+      if (lane == 0) part[warp][j][b] = v;
     }
+  __syncthreads();
+  if (threadIdx.x < 2 * RW_HEAD_MAXB) {
+    const int j = threadIdx.x / RW_HEAD_MAXB, b = threadIdx.x % RW_HEAD_MAXB;
+    if (b < B) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += part[w][j][b];
+      f[size_t(b) * 512 + o0 + j] = v + bias[o0 + j];
+    }
+  }
 }
 
 // dx[b][cell][c] = sum_o df[b][o] W[o][pos][c] (zero at the padded cells).  grid (64 cells, ceil(B / MAXB)), block 256 = channel pairs.
@@ -453,6 +483,7 @@ static __global__ void rw_head_bwd_kernel(const float* __restrict__ df, const op
   float2 acc[RW_HEAD_MAXB];
 #pragma unroll
   for (int b = 0; b < RW_HEAD_MAXB; ++b) acc[b] = make_float2(0.f, 0.f);
+#pragma unroll 16
   for (int o = 0; o < 512; ++o) {
     const float2 w = op2_to_float2(*reinterpret_cast<const uint32_t*>(W + (size_t(o) * 49 + pos) * 512 + c));
 #pragma unroll
@@ -697,7 +728,7 @@ static __global__ void rw_scale_rows_kernel(float* __restrict__ w, const float* 
 }
 // out[0] = sum w^2 (one block)
 static __global__ void rw_sumsq_kernel(const float* __restrict__ w, size_t n, float* __restrict__ out) {
-  __shared__ double red[256];
+  __shared__ double red[1024];
   double a = 0.0;
   for (size_t i = threadIdx.x; i < n; i += blockDim.x) a += double(w[i]) * double(w[i]);
   red[threadIdx.x] = a;

@@ -262,3 +262,54 @@ def test_compat_masactrl_loop_and_protocol_editor_match_reference_sampler():
     ed, rc = h_edit_masactrl_implicit_compat(model, xT, editor=user, unet=TorchUNet(), **args)
     assert (ed - ed_ref).abs().max().item() < 2e-5 and (rc - rc_ref).abs().max().item() < 2e-5
     assert user.cur_step == e_ref.cur_step == T * K and user.controlled == (T * K - start_step) * (16 - start_layer)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_irse50_restatement_matches_reference_backbone():
+    """hedit_b200/reward_nets.py `IRSE50` (the torch yardstick of the native ArcFace kernels, tests/test_gpu_reward.py) vs the reference's own
+    `Backbone(112, 50, mode='ir_se')` (face-swapping/arcface/facial_recognition/model_irse.py:9): identical state_dict keys and shapes --
+    the native loader (csrc/reward.cu) consumes exactly these keys -- and bit-identical embeddings on the same seeded weights; and
+    `id_features` = `IDLoss.extract_feats` (arcface_model.py:41-47: crop [35:223, 32:220], adaptive pool to 112)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, torch
+sys.path[:0] = [%r, "/root/reference/face-swapping"]
+from hedit_b200 import reward_nets as R
+from arcface.facial_recognition.model_irse import Backbone
+ours = R._seed_init(R.IRSE50(), 0)
+ref = Backbone(input_size=112, num_layers=50, drop_ratio=0.6, mode='ir_se')
+a, b = ours.state_dict(), ref.state_dict()
+assert set(a) == set(b) and all(a[k].shape == b[k].shape for k in a)
+ref.load_state_dict(a); ref.eval()
+x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(1)).clamp(-1, 1)
+pool = torch.nn.AdaptiveAvgPool2d((112, 112))
+with torch.no_grad():
+    want = ref(pool(x[:, :, 35:223, 32:220]))
+    got = R.id_features(ours, x)
+print("IRSE_MAX_ABS", (want - got).abs().max().item())
+assert torch.equal(want, got)
+""" % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "IRSE_MAX_ABS" in r.stdout, r.stderr[-2000:]
+
+
+def test_lpips_vgg_restatement_matches_torchvision_vgg16_slices():
+    """The `lpips` package (0.1.x; not installed offline, no copy under /root/reference) taps torchvision's vgg16().features after modules
+    3 / 8 / 15 / 22 / 29 (relu1_2 .. relu5_3).  `reward_nets.LPIPSVGG16` must be that network: same `features.N` keys, same five tensors."""
+    tv = pytest.importorskip("torchvision")
+    from hedit_b200 import reward_nets as R
+    ours = R._seed_init(R.LPIPSVGG16(), 1)
+    vgg = tv.models.vgg16(weights=None).features.eval()
+    vgg.load_state_dict({k[len("features."):]: v for k, v in ours.state_dict().items() if k.startswith("features.")})
+    x = torch.randn(1, 3, 64, 64, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        h, want = (x - ours.shift) / ours.scale, []
+        for i, m in enumerate(vgg):
+            h = m(h)
+            if i in (3, 8, 15, 22, 29):
+                want.append(h)
+        got = ours.taps(x)
+    assert len(got) == 5 and all(torch.equal(a, b) for a, b in zip(got, want))
