@@ -12,4 +12,8 @@ for k in conv:gemm_bf16 attn:self_attn4; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$rx -s 2 -c 1 -o gpurun_out/prof_$what -f python tools/op_bench.py $what --iters 1 > gpurun_out/ncu_$what.log 2>&1; echo "ncu $what rc=$?"
   ncu -i gpurun_out/prof_$what.ncu-rep --page raw --csv > gpurun_out/prof_${what}_raw.csv 2>/dev/null
 done
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/forward_dram.csv python tools/forward_dram.py > gpurun_out/forward_dram.log 2>&1; echo "ncu forward dram rc=$?"
+python tools/forward_dram.py --summarise gpurun_out/forward_dram.csv > gpurun_out/forward_dram_summary.txt 2>&1; head -3 gpurun_out/forward_dram_summary.txt | cut -c1-400
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 0 -c 1 -o gpurun_out/prof_qkv -f python tools/op_bench.py linear --iters 1 > gpurun_out/ncu_qkv.log 2>&1; echo "ncu qkv rc=$?"
+ncu -i gpurun_out/prof_qkv.ncu-rep --page raw --csv > gpurun_out/prof_qkv_raw.csv 2>/dev/null
 python tools/show_bench.py gpurun_out/bench_default.json 2>/dev/null | head -30 | cut -c1-500
