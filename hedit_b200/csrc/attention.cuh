@@ -102,6 +102,7 @@ struct SelfAttnCfg {
 
 template <int DCH, int BKV>
 __global__ void __launch_bounds__(192) self_attn_kernel(const __grid_constant__ AttnParams p) {
+  pdl_wait(); pdl_launch();
   using Cfg = SelfAttnCfg<DCH, BKV>;
   constexpr int KSTAGES = Cfg::KSTAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -331,6 +332,7 @@ struct SelfAttn2Cfg {
 template <int DCH, int NT_, int BKV_, int POLY = 0>
 static __global__ void __launch_bounds__(SelfAttn2Cfg<DCH, NT_, BKV_>::THREADS, SelfAttn2Cfg<DCH, NT_, BKV_>::MIN_CTAS)
 self_attn2_kernel(const __grid_constant__ AttnParams p) {
+  pdl_wait(); pdl_launch();
   using Cfg = SelfAttn2Cfg<DCH, NT_, BKV_>;
   constexpr int BKV = Cfg::BKV, KSTAGES = Cfg::KSTAGES, NT = Cfg::NT;
   constexpr int MMA_WARP = 4 * NT, TMA_WARP = 4 * NT + 1;
@@ -626,6 +628,7 @@ struct SelfAttn4Cfg {
 template <int DCH, bool MMASUM, int POLY16>
 static __global__ void __launch_bounds__(SelfAttn4Cfg<DCH>::THREADS, SelfAttn4Cfg<DCH>::MIN_CTAS)
 self_attn4_kernel(const __grid_constant__ AttnParams p) {
+  pdl_wait(); pdl_launch();
   using Cfg = SelfAttn4Cfg<DCH>;
   constexpr int BKV = Cfg::BKV, KSTAGES = Cfg::KSTAGES, NT = Cfg::NT;
   constexpr int MMA_WARP = 4 * NT, TMA_WARP = 4 * NT + 1;
@@ -862,6 +865,7 @@ struct CrossAttnCfg {
 
 template <int DCH>
 __global__ void __launch_bounds__(192) cross_attn_kernel(const __grid_constant__ AttnParams p) {
+  pdl_wait(); pdl_launch();
   using Cfg = CrossAttnCfg<DCH>;
   constexpr int BKV = Cfg::BKV;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1084,6 +1088,7 @@ struct CrossAttn2Cfg {
 
 template <int DCH>
 static __global__ void __launch_bounds__(192, 1) cross_attn2_kernel(const __grid_constant__ AttnParams p) {
+  pdl_wait(); pdl_launch();
   using Cfg = CrossAttn2Cfg<DCH>;
   constexpr int BKV = Cfg::BKV, NQ = Cfg::NQ;
   extern __shared__ __align__(1024) uint8_t smem_raw[];

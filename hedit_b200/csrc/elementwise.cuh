@@ -1,6 +1,7 @@
 // HBM-bound glue kernels of the UNet (coalesced, vectorised; fp32 residual stream in, bf16 GEMM operands out).
 // Activations are NHWC ("tokens x channels") everywhere inside the engine.
 #pragma once
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace hedit {
@@ -15,6 +16,7 @@ struct GNStatsParams {
 };
 
 static __global__ void gn_stats_kernel(const GNStatsParams p) {
+  pdl_wait(); pdl_launch();
   // Deterministic: every thread parks the sums of its two channel pairs in shared memory and one thread per group adds
   // them in channel order (no atomics), so the whole UNet is run-to-run bit-reproducible.
   __shared__ float2 tsum[2][640];                      // [pair-in-quad][quad]  (C <= 2560)
@@ -69,6 +71,7 @@ struct GNFinalizeParams {
 };
 
 static __global__ void gn_finalize_kernel(const GNFinalizeParams p) {
+  pdl_wait(); pdl_launch();
   __shared__ double ssu[512], ssq[512];
   const int C = p.C1 + p.C2, cpg = C / p.groups;
   const int g = blockIdx.x, s = blockIdx.y, nrb = p.HW >> 5;
@@ -119,6 +122,7 @@ struct GNApplyParams {
 };
 
 static __global__ void gn_apply_kernel(const GNApplyParams p) {
+  pdl_wait(); pdl_launch();
   __shared__ float smean[32], srstd[32];
   const int C = p.C1 + p.C2, cpg = C / p.groups, quads = C >> 2;
   const int s = blockIdx.y;
@@ -193,6 +197,7 @@ static __global__ void gn_apply_kernel(const GNApplyParams p) {
 template <int NV>   // float2 per lane; NV > 0: exactly C/64, NV == 0: runtime count (<= 32)
 static __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  op_t* __restrict__ out, int rows, int C, float eps) {
+  pdl_wait(); pdl_launch();
   constexpr int MAXV = NV > 0 ? NV : 32;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -231,15 +236,16 @@ static __global__ void layernorm_kernel(const float* __restrict__ x, const float
 static inline void launch_layernorm(const float* x, const float* g, const float* b, op_t* out, int rows, int C, float eps, cudaStream_t st) {
   const int grid = (rows + 7) / 8;
   switch (C) {
-    case 320: layernorm_kernel<5><<<grid, 256, 0, st>>>(x, g, b, out, rows, C, eps); break;
-    case 640: layernorm_kernel<10><<<grid, 256, 0, st>>>(x, g, b, out, rows, C, eps); break;
-    case 1280: layernorm_kernel<20><<<grid, 256, 0, st>>>(x, g, b, out, rows, C, eps); break;
-    default: layernorm_kernel<0><<<grid, 256, 0, st>>>(x, g, b, out, rows, C, eps); break;
+    case 320: launch_k(layernorm_kernel<5>, dim3(grid), dim3(256), 0, st, x, g, b, out, rows, C, eps); break;
+    case 640: launch_k(layernorm_kernel<10>, dim3(grid), dim3(256), 0, st, x, g, b, out, rows, C, eps); break;
+    case 1280: launch_k(layernorm_kernel<20>, dim3(grid), dim3(256), 0, st, x, g, b, out, rows, C, eps); break;
+    default: launch_k(layernorm_kernel<0>, dim3(grid), dim3(256), 0, st, x, g, b, out, rows, C, eps); break;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ casts / resampling
 static __global__ void cast_bf16_kernel(const float* __restrict__ x, op_t* __restrict__ y, size_t n4) {
+  pdl_wait(); pdl_launch();
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
     const float4 t = reinterpret_cast<const float4*>(x)[i];
     reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_op2(t.x, t.y), pack_op2(t.z, t.w));
@@ -250,6 +256,7 @@ static __global__ void cast_bf16_kernel(const float* __restrict__ x, op_t* __res
 // src[s] (rows whose src[s] == s are left alone).  Applied to conv2's INPUT, which makes conv2's output of the two samples identical,
 // exactly what the reference's copy of conv2's output produces.  n16 = 16-byte words per sample.
 static __global__ void copy_samples_kernel(op_t* __restrict__ buf, const int* __restrict__ src, size_t n16) {
+  pdl_wait(); pdl_launch();
   const int s = blockIdx.y, f = src[s];
   if (f == s || f < 0) return;
   const uint4* from = reinterpret_cast<const uint4*>(buf) + size_t(f) * n16;
@@ -277,6 +284,7 @@ static __global__ void cvt_upconv_phases_kernel(const float* __restrict__ src, o
 
 // nearest 2x upsample, fp32 NHWC -> bf16 NHWC (operand of the following 3x3 conv)
 static __global__ void upsample2x_bf16_kernel(const float* __restrict__ x, op_t* __restrict__ y, int S, int H, int W, int C) {
+  pdl_wait(); pdl_launch();
   const int quads = C >> 2;
   const size_t total = size_t(S) * (2 * H) * (2 * W) * quads;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
@@ -297,6 +305,7 @@ static __global__ void upsample2x_bf16_kernel(const float* __restrict__ x, op_t*
 constexpr int kConvInRows = 4;
 static __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                float* __restrict__ y, int H, int W, int C0) {
+  pdl_wait(); pdl_launch();
   extern __shared__ float sm[];
   float* sw = sm;                       // [36][C0] (tap-major: consecutive threads read consecutive float4)
   float* sx = sm + 36 * C0;             // [4][RB+2][W+2]
@@ -419,6 +428,7 @@ static __global__ void small_linear_kernel(const float* __restrict__ in, int ld_
 
 // whole samples gathered by index: dst[s][:] = src[idx[s]][:]  (n16 = 16-byte words per sample); broadcasts the de-duplicated prefix
 static __global__ void gather_samples_kernel(const uint4* __restrict__ src, const int* __restrict__ idx, uint4* __restrict__ dst, size_t n16) {
+  pdl_wait(); pdl_launch();
   const int s = blockIdx.y;
   const uint4* from = src + size_t(idx[s]) * n16;
   uint4* to = dst + size_t(s) * n16;
@@ -427,6 +437,7 @@ static __global__ void gather_samples_kernel(const uint4* __restrict__ src, cons
 
 // rows of a table gathered by index: out[r][:] = table[idx[r]][:]
 static __global__ void gather_rows_kernel(const float* __restrict__ table, const int* __restrict__ idx, float* __restrict__ out, int ld4) {
+  pdl_wait(); pdl_launch();
   const int r = blockIdx.y;
   const float4* src = reinterpret_cast<const float4*>(table) + size_t(idx[r]) * ld4;
   float4* dst = reinterpret_cast<float4*>(out) + size_t(r) * ld4;

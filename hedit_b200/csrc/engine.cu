@@ -10,6 +10,7 @@
 
 #include "compat_attn.cuh"
 #include "elementwise.cuh"
+#include "launch.h"
 #include "tmap.h"
 
 namespace hedit {
@@ -384,15 +385,18 @@ static cudaError_t launch_gemm_t(const GemmParams& g, cudaStream_t st) {
   const int m_tiles = (g.M + 127) / 128, n_tiles = (g.N + BN - 1) / BN;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
+  int nat = 0;
   if (CL) {
     const int pairs = ((m_tiles + 1) / 2) * n_tiles;
     cfg.gridDim = dim3(2 * std::min(pairs, num_sms() / 2));
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[nat].id = cudaLaunchAttributeClusterDimension; at[nat].val.clusterDim.x = 2; at[nat].val.clusterDim.y = 1; at[nat].val.clusterDim.z = 1;
+    ++nat;
   } else {
     cfg.gridDim = dim3(std::min(m_tiles * n_tiles, num_sms()));
   }
+  if (pdl_enabled()) { at[nat].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[nat].val.programmaticStreamSerializationAllowed = 1; ++nat; }
+  cfg.attrs = at; cfg.numAttrs = nat;
   return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CL, EPI>, g);
 }
 
@@ -432,8 +436,7 @@ static cudaError_t launch_self_t(const AttnParams& a, int S, cudaStream_t st) {
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(self_attn_kernel<DCH, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SelfAttnCfg<DCH, BKV>::SMEM_BYTES); set = true; }
   dim3 grid((a.Nq + 127) / 128, a.H, S);
-  self_attn_kernel<DCH, BKV><<<grid, 192, SelfAttnCfg<DCH, BKV>::SMEM_BYTES, st>>>(a);
-  return cudaGetLastError();
+  return launch_k(self_attn_kernel<DCH, BKV>, grid, dim3(192), SelfAttnCfg<DCH, BKV>::SMEM_BYTES, st, a);
 }
 template <int DCH, int NT, int BKV, int POLY = 0>
 static cudaError_t launch_self2_t(const AttnParams& a, int S, cudaStream_t st) {
@@ -442,8 +445,7 @@ static cudaError_t launch_self2_t(const AttnParams& a, int S, cudaStream_t st) {
   if (!set) { cudaFuncSetAttribute(self_attn2_kernel<DCH, NT, BKV, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
   constexpr int rows = 128 * NT;
   dim3 grid((a.Nq + rows - 1) / rows, a.H, S);
-  self_attn2_kernel<DCH, NT, BKV, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
-  return cudaGetLastError();
+  return launch_k(self_attn2_kernel<DCH, NT, BKV, POLY>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, a);
 }
 template <int DCH, bool MMASUM, int POLY16>
 static cudaError_t launch_self4_t(const AttnParams& a, int S, cudaStream_t st) {
@@ -451,8 +453,7 @@ static cudaError_t launch_self4_t(const AttnParams& a, int S, cudaStream_t st) {
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(self_attn4_kernel<DCH, MMASUM, POLY16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); set = true; }
   dim3 grid((a.Nq + 255) / 256, a.H, S);
-  self_attn4_kernel<DCH, MMASUM, POLY16><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
-  return cudaGetLastError();
+  return launch_k(self_attn4_kernel<DCH, MMASUM, POLY16>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, a);
 }
 // tuning switch HEDIT_ATTN_V4 (self_attn4_kernel, head dims <= 128; measured on B200 at 40 samples, N = 4096 d = 40 / N = 1024 d = 80):
 //   unset = default: d <= 64: tensor-core row sum + 2 of 8 exponential pairs on the FMA pipe (1.405 ms; round-1 kernel 1.67, cuDNN SDPA 1.396),
@@ -503,8 +504,7 @@ static cudaError_t launch_cross_t(const AttnParams& a, int units, cudaStream_t s
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(cross_attn_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, CrossAttnCfg<DCH>::SMEM_BYTES); set = true; }
   dim3 grid((a.Nq + 127) / 128, a.H, units);
-  cross_attn_kernel<DCH><<<grid, 192, CrossAttnCfg<DCH>::SMEM_BYTES, st>>>(a);
-  return cudaGetLastError();
+  return launch_k(cross_attn_kernel<DCH>, grid, dim3(192), CrossAttnCfg<DCH>::SMEM_BYTES, st, a);
 }
 template <int DCH>
 static cudaError_t launch_cross2_t(AttnParams a, int units, cudaStream_t st) {
@@ -516,8 +516,7 @@ static cudaError_t launch_cross2_t(AttnParams a, int units, cudaStream_t st) {
   while (groups < ntiles && groups * a.H * units < 2 * 148 && ntiles / (groups * 2) >= 2) groups *= 2;
   a.tiles_per_cta = (ntiles + groups - 1) / groups;
   dim3 grid((ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta, a.H, units);
-  cross_attn2_kernel<DCH><<<grid, 192, CrossAttn2Cfg<DCH>::SMEM_BYTES, st>>>(a);
-  return cudaGetLastError();
+  return launch_k(cross_attn2_kernel<DCH>, grid, dim3(192), CrossAttn2Cfg<DCH>::SMEM_BYTES, st, a);
 }
 cudaError_t launch_cross_attn(const AttnParams& a, int dch, int units, cudaStream_t st) {
   static const bool force_v1 = getenv("HEDIT_CROSS_V1") != nullptr;      // tuning switch: single-tile kernel
@@ -959,31 +958,31 @@ long Engine::launch_op(Op& op, int S_call, const float* x, float* eps, const Cal
   const int S = op.nS > 0 ? op.nS : S_call;          // ops of the de-duplicated prefix run on the distinct latents only
   switch (op.kind) {
     case OP_EXPAND:
-      gather_samples_kernel<<<dim3(unsigned(std::min<size_t>((op.count + 255) / 256, 64)), S), 256, 0, st>>>(
-          reinterpret_cast<const uint4*>(op.f_in), cc.uniq_of, reinterpret_cast<uint4*>(op.f_out), op.count);
+      CK(launch_k(gather_samples_kernel, dim3(unsigned(std::min<size_t>((op.count + 255) / 256, 64)), S), dim3(256), 0, st,
+                  reinterpret_cast<const uint4*>(op.f_in), cc.uniq_of, reinterpret_cast<uint4*>(op.f_out), op.count));
       break;
     case OP_CONV_IN: {
       if (op.rows == 1)    // de-duplicated prefix: one latent per distinct value
-        gather_samples_kernel<<<dim3(unsigned(std::min<size_t>((lat * 4 / 16 + 255) / 256, 64)), S), 256, 0, st>>>(
-            reinterpret_cast<const uint4*>(x), cc.uniq_first, reinterpret_cast<uint4*>(const_cast<float*>(op.f_in)), lat * sizeof(float) / 16);
+        CK(launch_k(gather_samples_kernel, dim3(unsigned(std::min<size_t>((lat * 4 / 16 + 255) / 256, 64)), S), dim3(256), 0, st,
+                    reinterpret_cast<const uint4*>(x), cc.uniq_first, reinterpret_cast<uint4*>(const_cast<float*>(op.f_in)), lat * sizeof(float) / 16));
       else
         CK(cudaMemcpyAsync(const_cast<float*>(op.f_in), x, S * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
       const size_t sm = (36 * size_t(op.C1) + 4 * (kConvInRows + 2) * (op.W + 2)) * sizeof(float);
       static bool set = false;
       if (!set) { cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
-      conv_in_kernel<<<dim3((op.H + kConvInRows - 1) / kConvInRows, S), 256, sm, st>>>(op.f_in, conv_in_w_, conv_in_b_, op.f_out, op.H, op.W, op.C1);
+      CK(launch_k(conv_in_kernel, dim3((op.H + kConvInRows - 1) / kConvInRows, S), dim3(256), sm, st, op.f_in, conv_in_w_, conv_in_b_, op.f_out, op.H, op.W, op.C1));
       break;
     }
     case OP_GN_STATS: {
       GNStatsParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, op.chunk, op.partial};
       const int quads = (op.C1 + op.C2) / 4;
       const int threads = std::min(640, ((quads + 31) / 32) * 32);
-      gn_stats_kernel<<<dim3(op.nchunks, S), threads, 0, st>>>(p);
+      CK(launch_k(gn_stats_kernel, dim3(op.nchunks, S), dim3(threads), 0, st, p));
       break;
     }
     case OP_GN_FINALIZE: {
       GNFinalizeParams p{op.cs1, op.cs2, op.C1, op.C2, op.HW, c.groups, op.eps, op.stats};
-      gn_finalize_kernel<<<dim3(c.groups, S), (op.HW >= 16384 ? 512 : 128), 0, st>>>(p);
+      CK(launch_k(gn_finalize_kernel, dim3(c.groups, S), dim3(op.HW >= 16384 ? 512 : 128), 0, st, p));
       break;
     }
     case OP_GN_APPLY: {
@@ -993,7 +992,7 @@ long Engine::launch_op(Op& op, int S_call, const float* x, float* eps, const Cal
       const int quads_ = C / 4;
       const int threads = std::max(256, quads_ * std::max(1, (256 + quads_ - 1) / quads_));      // quads * nsub (<= 640)
       GNApplyParams p{op.f_in, op.f_in2, op.C1, op.C2, op.HW, c.groups, chunk, op.nchunks, op.partial, op.gamma, op.beta, op.eps, op.silu, op.h_out, op.h_out2, op.stats};
-      gn_apply_kernel<<<dim3((op.HW + chunk - 1) / chunk, S), threads, 0, st>>>(p);
+      CK(launch_k(gn_apply_kernel, dim3((op.HW + chunk - 1) / chunk, S), dim3(threads), 0, st, p));
       break;
     }
     case OP_GEMM:
@@ -1023,18 +1022,18 @@ long Engine::launch_op(Op& op, int S_call, const float* x, float* eps, const Cal
     }
     case OP_UPSAMPLE: {
       const size_t total = size_t(S) * 4 * op.H * op.W * (op.C1 / 4);
-      upsample2x_bf16_kernel<<<int(std::min<size_t>((total + 255) / 256, 8192)), 256, 0, st>>>(op.f_in, op.h_out, S, op.H, op.W, op.C1);
+      CK(launch_k(upsample2x_bf16_kernel, dim3(unsigned(std::min<size_t>((total + 255) / 256, 8192))), dim3(256), 0, st, op.f_in, op.h_out, S, op.H, op.W, op.C1));
       break;
     }
     case OP_CAST:
-      cast_bf16_kernel<<<int(std::min<size_t>((op.count + 255) / 256, 8192)), 256, 0, st>>>(op.f_in, op.h_out, op.count);
+      CK(launch_k(cast_bf16_kernel, dim3(unsigned(std::min<size_t>((op.count + 255) / 256, 8192))), dim3(256), 0, st, op.f_in, op.h_out, op.count));
       break;
     case OP_CONV_OUT:
       CK(cudaMemcpyAsync(eps, op.f_out, S_call * lat * sizeof(float), cudaMemcpyDeviceToDevice, st));
       break;
     case OP_FEAT_COPY:
       if (!cc.feat_src) return 0;
-      copy_samples_kernel<<<dim3(unsigned(std::min<size_t>((op.count + 255) / 256, 64)), S), 256, 0, st>>>(op.h_out, cc.feat_src, op.count);
+      CK(launch_k(copy_samples_kernel, dim3(unsigned(std::min<size_t>((op.count + 255) / 256, 64)), S), dim3(256), 0, st, op.h_out, cc.feat_src, op.count));
       break;
   }
   return 1;

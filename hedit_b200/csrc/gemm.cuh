@@ -158,6 +158,10 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
   if (CLUSTER) cluster_sync_all();        // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barriers, tensor memory, descriptor prefetch) ran while the previous kernel was
+  // still finishing; from here on the kernel reads what that kernel wrote
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp runs the loop so the

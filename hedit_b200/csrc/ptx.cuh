@@ -87,6 +87,10 @@ HEDIT_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma reading smem)
+// programmatic dependent launch (launch.h): block until the preceding grid in the stream has completed and flushed its memory; then let
+// the following grid become resident
+HEDIT_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+HEDIT_DEVICE void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 HEDIT_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------- TMA
