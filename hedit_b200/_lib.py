@@ -80,6 +80,7 @@ class EditArgsC(C.Structure):
         ("xt_is_pair", C.c_int32), ("ctrl_step0", C.c_int32), ("blend_state", C.c_void_p),
         ("edited", C.c_void_p), ("recon", C.c_void_p), ("trace", C.c_void_p),
         ("n_sample_forwards", C.c_int64), ("n_kernel_launches", C.c_int64),
+        ("coef_edit", C.c_void_p),
     ]
 
 

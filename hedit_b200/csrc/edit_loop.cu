@@ -101,7 +101,8 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   const int B = a.B, T = a.steps, K = a.explicit_form ? 1 : std::max(1, a.opt_steps);
   const int n = E.latent_elems();
   const bool masa = a.masa != 0;
-  const bool p2p = a.use_p2p != 0 && a.variant == 0 && !masa;
+  const bool baseline = a.variant == 2;        // ef_or_pnp_inv_w_p2p / ef_or_pnp_inv_w_masactrl
+  const bool p2p = a.use_p2p != 0 && (a.variant == 0 || baseline) && !masa;
   const bool pnp = a.pnp != 0;
   const bool ctrl = p2p || masa || pnp;   // launches C / BC / E run with attention control
   const bool blend = p2p && a.has_blend != nullptr && a.blend_alpha != nullptr;
@@ -120,6 +121,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     return -1;
   }
   if (masa && !a.masa_step_on) { E.err_ = "masa needs masa_step_on[steps * opt_steps]"; return -1; }
+  if (baseline && (pnp || a.guidance || a.pre_step || a.xt_is_pair)) { E.err_ = "variant 2 (baseline samplers) runs without PnP, reward guidance, pre_step or xt_is_pair"; return -1; }
   if (a.guidance && (a.explicit_form || !a.x0_coef || !a.guid_x0 || !a.guid_grad)) {
     E.err_ = "reward guidance runs in the implicit form and needs x0_coef, guid_x0 and guid_grad";
     return -1;
@@ -190,6 +192,21 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     }
     pool = A.S + BC.S;
     calls.push_back(A); calls.push_back(BC);
+  } else if (baseline) {
+    // p2p_baselines.py:153-165: torch.cat([xt] * 2) with [uncond, uncond, src, tar] -> [xo,null] [xe,null] [xo,src] [xe,tar], P2P pair = (2, 3)
+    CallDesc e; e.p2p = ctrl; e.pool_off = 0;
+    for (int b = 0; b < B; ++b) {
+      const int s = e.S;
+      e.add(XT(b, 0), 0); e.add(XT(b, 1), 0); e.add(XT(b, 0), 1 + 2 * b); e.add(XT(b, 1), 2 + 2 * b);
+      e.unit(s, -1, b); e.unit(s + 1, -1, b);
+      if (p2p) { e.unit(s + 2, s + 3, b); e.sq[s + 3] = s + 2; } else { e.unit(s + 2, -1, b); e.unit(s + 3, -1, b); }
+      e.sk[s + 1] = s; e.sk[s + 3] = s + 2;
+      iuA[2 * b] = iuA0[2 * b] = s; iuA[2 * b + 1] = iuA0[2 * b + 1] = s + 1;
+      icA[2 * b] = icA0[2 * b] = s + 2; icA[2 * b + 1] = icA0[2 * b + 1] = s + 3;
+      iu[b] = s + 1; ics[b] = s + 2; ict[b] = s + 3;
+    }
+    calls.push_back(e);
+    pool = e.S;
   } else if (a.explicit_form) {
     CallDesc e; e.p2p = ctrl; e.pool_off = 0;
     for (int b = 0; b < B; ++b) {
@@ -413,11 +430,17 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     rp.w_src = a.w_src;
     rp.k.sqrt_1m_at = hc.sqrt_1m_at; rp.k.sqrt_at = hc.sqrt_at; rp.k.sqrt_ap = hc.sqrt_ap; rp.k.dir = hc.dir; rp.k.noise = hc.noise; rp.k.coeff = hc.coeff;
     rp.x_prev = xprev; rp.n = n;
+    rp.per_row = 0; rp.w_row1 = a.w_src; rp.k1 = rp.k;
+    if (baseline) {
+      const hedit_step_coef& he = a.coef_edit ? a.coef_edit[i] : hc;
+      rp.per_row = 1; rp.w_row1 = a.w_tar;
+      rp.k1.sqrt_1m_at = he.sqrt_1m_at; rp.k1.sqrt_at = he.sqrt_at; rp.k1.sqrt_ap = he.sqrt_ap; rp.k1.dir = he.dir; rp.k1.noise = he.noise; rp.k1.coeff = he.coeff;
+    }
     hstep_reverse_kernel<<<dim3(std::max(1, n / 4 / 256), B, 2), 256, 0, st>>>(rp);
     ++launches;
     // x_opt <- x_base
     CKE(cudaMemcpy2DAsync(xopt, size_t(n) * sizeof(float), xprev + n, size_t(2) * n * sizeof(float), size_t(n) * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < (baseline ? 0 : K); ++k) {
       const bool save = (k == K - 1);
       if (!a.explicit_form) {
         if (a.variant == 0 && a.schedule == 0 && !pnp) { if (run_call(calls[1], i + 1, i, false)) return -1; if (run_call(calls[2], i + 1, i, save)) return -1; }

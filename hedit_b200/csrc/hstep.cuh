@@ -31,6 +31,9 @@ struct ReverseParams {
   StepCoef k;
   float* x_prev;          // [B][2][n]  (orig_{t-1}, base_{t-1})
   int n;
+  int per_row;            // 1: row 1 (edit) uses its own guidance weight and scalars (the baseline samplers, p2p_baselines.py:172-184)
+  float w_row1;
+  StepCoef k1;
 };
 
 static __global__ void hstep_reverse_kernel(const ReverseParams p) {
@@ -40,15 +43,18 @@ static __global__ void hstep_reverse_kernel(const ReverseParams p) {
   const float* x = p.xt + (size_t(b) * 2 + row) * p.n;
   const float* z = p.z + size_t(b) * p.z_stride;
   float* o = p.x_prev + (size_t(b) * 2 + row) * p.n;
+  const bool own = p.per_row && row == 1;
+  const float w = own ? p.w_row1 : p.w_src;
+  const StepCoef k = own ? p.k1 : p.k;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < p.n; i += gridDim.x * blockDim.x * 4) {
     const float4 u = *reinterpret_cast<const float4*>(eu + i), c = *reinterpret_cast<const float4*>(ec + i);
     const float4 xv = *reinterpret_cast<const float4*>(x + i), zv = *reinterpret_cast<const float4*>(z + i);
     float4 r;
 #define HEDIT_REV(f)                                                          \
     {                                                                         \
-      const float eps = u.f + p.w_src * (c.f - u.f);                          \
-      const float x0 = (xv.f - p.k.sqrt_1m_at * eps) / p.k.sqrt_at;           \
-      r.f = (p.k.sqrt_ap * x0 + p.k.dir * eps) + p.k.noise * zv.f;            \
+      const float eps = u.f + w * (c.f - u.f);                                \
+      const float x0 = (xv.f - k.sqrt_1m_at * eps) / k.sqrt_at;               \
+      r.f = (k.sqrt_ap * x0 + k.dir * eps) + k.noise * zv.f;                  \
     }
     HEDIT_REV(x) HEDIT_REV(y) HEDIT_REV(z) HEDIT_REV(w)
 #undef HEDIT_REV

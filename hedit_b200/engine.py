@@ -238,9 +238,11 @@ class UNetEngine:
     def edit(self, xT: torch.Tensor, zs: torch.Tensor, ctx: torch.Tensor, timesteps: Sequence[int], coef: np.ndarray,
              cfg_scales: Sequence[float], plan: Optional[EditPlan], weight_reconstruction: float = 0.1, optimization_steps: int = 1,
              explicit_form: bool = False, schedule: int = 1, trace: bool = False, variant: int = 0, masactrl=None, mos_pull: bool = True,
-             xt_is_pair: bool = False, ctrl_step0: int = 0, blend_state: Optional[torch.Tensor] = None, pnp=None, pre_coeff=None, guidance=None):
+             xt_is_pair: bool = False, ctrl_step0: int = 0, blend_state: Optional[torch.Tensor] = None, pnp=None, pre_coeff=None, guidance=None,
+             coef_edit: Optional[np.ndarray] = None):
         """xT (B,C,h,w), zs (B,steps,C,h,w), ctx (1+2B,77,D): all on the SAME side (all host or all on this device).
-        variant 1 = h_Edit_R_* (no attention control); masactrl = (layer_mask, step_on[steps*K]) enables mutual self-attention in the
+        variant 1 = h_Edit_R_* (no attention control); variant 2 = the EF / PnP-Inversion baseline samplers (coef_edit = reverse-step
+        scalars of the edit row when they differ from the orig row's); masactrl = (layer_mask, step_on[steps*K]) enables mutual self-attention in the
         transformer blocks of layer_mask during the controlled launches flagged in step_on;
         pnp = (self_mask, qk_on[steps], feat_on[steps]) runs h_Edit_PnP_implicit (Plug-and-Play q/k and feature injection);
         guidance = (fn, weight, x0_coef[steps,2]) adds the reward-guided Langevin move: fn(x0 (B,C,h,w) cuda tensor) -> dLoss/dx0.
@@ -267,6 +269,11 @@ class UNetEngine:
         a.variant = int(variant)
         a.mos_pull = int(mos_pull)
         keep = []
+        if coef_edit is not None:
+            coef_edit = np.ascontiguousarray(coef_edit, dtype=np.float32)
+            assert coef_edit.shape == (steps, 6)
+            keep.append(coef_edit)
+            a.coef_edit = coef_edit.ctypes.data
         if masactrl is not None:
             n_ctrl = steps * (1 if explicit_form else max(1, optimization_steps))
             step_on = np.ascontiguousarray(np.asarray(masactrl[1], dtype=np.int32))

@@ -92,7 +92,7 @@ def invalidate_engines(model) -> None:
 def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Sequence[Sequence[str]], cfg_scales, controllers,
                      eta=1.0, weight_reconstruction=0.075, optimization_steps=1, after_skip_steps=None, is_ddim_inversion=False,
                      explicit_form=False, schedule=1, engine: Optional[UNetEngine] = None, trace=False, variant=0, masactrl=None,
-                     mos_pull=True, pnp=None, pre_coeff=None, guidance=None):
+                     mos_pull=True, pnp=None, pre_coeff=None, guidance=None, coef_edit=None):
     """B independent edits in one native call.  xT (B,C,h,w); zs (B,steps,C,h,w); prompt_pairs[b] = [src, tar];
     controllers[b] = P2P controller of image b (ours or the reference's) or None for all (P2P off)."""
     B = xT.shape[0]
@@ -117,7 +117,7 @@ def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Se
                 raise ValueError("controllers mixes P2P controllers with None / passive stores: split the batch")
             plan = compile_edit_plan(controllers, steps)
     out = eng.edit(xT, zs[:, :steps], ctx, ts, coef, cfg_scales, plan, weight_reconstruction, optimization_steps, explicit_form, schedule, trace,
-                   variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp, pre_coeff=pre_coeff, guidance=guidance)
+                   variant=variant, masactrl=masactrl, mos_pull=mos_pull, pnp=pnp, pre_coeff=pre_coeff, guidance=guidance, coef_edit=coef_edit)
     if plan is not None:
         for c in controllers:       # keep the controller's observable counters consistent with the reference
             c.cur_step = getattr(c, "cur_step", 0) + steps
@@ -356,3 +356,53 @@ class HEditStepper:
 def h_edit_step(stepper: HEditStepper, xt: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
     """One reverse-time bridge step [x_orig_t, x_edit_t] -> [x_orig_{t-1}, x_edit_{t-1}] (incl. P2P injection and LocalBlend)."""
     return stepper.step(xt, z)
+
+
+# ---- baseline samplers of the reference's drivers (main_p2p.py --mode ef / ef_p2p / pnp_inv_p2p, main_masactrl.py) ----------------
+def _baseline(model, xT, etas, prompts, cfg_scales, zs, controller, is_ddim_inversion, masactrl=None):
+    """One native call of loop variant 2 (csrc/edit_loop.cu): per timestep ONE attention-controlled launch [xo,null] [xe,null] [xo,src]
+    [xe,tar], the orig row stepped with the source-guided noise and the edit row with the target-guided noise."""
+    assert len(prompts) >= 2 and len(cfg_scales) >= 2
+    dev = xT.device
+    steps = zs.shape[0]
+    x = xT.reshape(1, *xT.shape[-3:])
+    z = zs.reshape(1, steps, *xT.shape[-3:])
+    from .compat import controller_kind
+    kind = controller_kind(controller)
+    if kind == "custom":
+        raise NotImplementedError("the baseline samplers run stock P2P controllers (or none) on the fused path")
+    use_cuda = torch.device(dev).type == "cuda"
+    x, z = (x, z.to(dev)) if use_cuda else (x.cpu(), z.cpu())
+    # PnP Inversion steps the edit row deterministically (eta = 0) while the orig row keeps eta (p2p_baselines.py:176-184)
+    coef_edit = step_tables(model.scheduler, steps, 0.0, True)[1] if is_ddim_inversion else None
+    w_src, w_tar = float(cfg_scales[0]), float(cfg_scales[1])
+    edited, recon = h_edit_p2p_batch(model, x, z, [prompts[:2]], [w_src, w_src, w_tar], [controller] if kind == "stock" else None, etas, 0.0, 1, steps,
+                                     is_ddim_inversion, False, variant=2, masactrl=masactrl, mos_pull=False, coef_edit=coef_edit)
+    return edited.to(dev), recon.to(dev)
+
+
+def ef_or_pnp_inv_w_p2p(model, xT, etas=0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None, is_ddim_inversion=False):
+    """Reference signature (inversion/p2p_baselines.py:103): Edit Friendly (is_ddim_inversion=False) / PnP Inversion (True) with P2P.
+    Returns (edited, reconstructed), each (1,C,h,w)."""
+    return _baseline(model, xT, etas, prompts, cfg_scales, zs, controller, is_ddim_inversion)
+
+
+def ef_wo_p2p(model, xT, etas=0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None, is_ddim_inversion=False):
+    """Reference signature (inversion/p2p_baselines.py:19): Edit Friendly without P2P -- only the target prompt is denoised from xT with the
+    inverted noise maps.  Returns the edited sample (1,C,h,w) like the reference (its `controller` only ever stores maps)."""
+    assert len(prompts) == 1 and len(cfg_scales) == 1, "ef_wo_p2p takes the target prompt only (p2p_baselines.py:35)"
+    edited, _ = _baseline(model, xT, etas, [prompts[0], prompts[0]], [cfg_scales[0], cfg_scales[0]], zs, None, is_ddim_inversion)
+    return edited
+
+
+def ef_or_pnp_inv_w_masactrl(model, xT, etas=0, prompts="", cfg_scales=None, prog_bar=False, zs=None, is_ddim_inversion=False):
+    """Reference signature (inversion/masactrl_baselines.py:15): Edit Friendly / PnP Inversion with the registered MasaCtrl editor."""
+    ed = getattr(model, "_hedit_masactrl_editor", None)
+    assert ed is not None, "call regiter_attention_editor_diffusers(model, MutualSelfAttentionControl(...)) first"
+    if type(ed).__name__ != "MutualSelfAttentionControl":
+        raise NotImplementedError("the baseline samplers run the stock MutualSelfAttentionControl editor on the fused path")
+    steps = zs.shape[0]
+    out = _baseline(model, xT, etas, prompts, cfg_scales, zs, None, is_ddim_inversion,
+                    masactrl=ed.launch_plan(steps, get_engine(model).n_transformer_blocks()))
+    ed.cur_step += steps
+    return out

@@ -54,7 +54,11 @@ typedef struct hedit_edit_args {
   int32_t buffers_on_host;   /* 1: xT, zs, ctx, edited, recon, trace are host pointers (copies are part of the call) */
   int32_t variant;           /* 0: P2P-family samplers (orig and edit rows both denoised: h_Edit_p2p_*, h_Edit_masactrl_implicit);
                                 1: h_Edit_R_implicit / h_Edit_R_explicit (p2p_h_edit.py:162,21): no attention control, both rows are
-                                   stepped with the edit row's source-guided noise prediction */
+                                   stepped with the edit row's source-guided noise prediction;
+                                2: the baseline samplers ef_or_pnp_inv_w_p2p / ef_or_pnp_inv_w_masactrl (inversion/p2p_baselines.py:103,
+                                   masactrl_baselines.py:15; Edit Friendly and PnP Inversion): one attention-controlled launch
+                                   [xo,null] [xe,null] [xo,src] [xe,tar] per timestep, then the ORIG row steps with the source-guided
+                                   noise (coef) and the EDIT row with the target-guided noise (w_tar, coef_edit); no h-term */
   const float* xT;           /* [B][C][h][w] */
   const float* zs;           /* [B][steps][C][h][w]; zs[b][idx] as in the reference (idx = steps-1-i at step i) */
   const float* ctx;          /* [1+2B][ctx_len][cross_dim]: row 0 = "", then (src_b, tar_b) pairs (encode_text) */
@@ -125,6 +129,9 @@ typedef struct hedit_edit_args {
   float* trace;              /* [steps][B][2][C][h][w] or NULL: xt after every timestep */
   int64_t n_sample_forwards; /* out */
   int64_t n_kernel_launches; /* out */
+  /* ---- variant 2 only: reverse-step scalars of the EDIT row (host [steps]); NULL = coef.  PnP Inversion steps the edit row with
+   * eta = 0 while the orig row keeps eta = 1 (p2p_baselines.py:180-184) */
+  const hedit_step_coef* coef_edit;
 } hedit_edit_args;
 
 const char* hedit_last_error(void);

@@ -43,6 +43,11 @@ VARIANTS = {
     "tiny_masactrl_lists": (UNetConfig.tiny(sample_size=64), 6, 1, "masactrl"),
     # BASELINE.json configs[2] at full SD-1.5 geometry: implicit h-Edit + MasaCtrl (the sampler the reference ships), T = 50
     "sd15_config3_T50_masactrl": (UNetConfig.sd15(), 50, 1, "masactrl"),
+    # baseline samplers of main_p2p.py --mode ef_p2p / pnp_inv_p2p / ef and main_masactrl.py (inversion/p2p_baselines.py, masactrl_baselines.py)
+    "tiny_ef_p2p": (UNetConfig.tiny(sample_size=64), 6, 1, "ef_p2p"),
+    "tiny_pnpinv_p2p": (UNetConfig.tiny(sample_size=64), 6, 1, "pnpinv_p2p"),
+    "tiny_ef": (UNetConfig.tiny(sample_size=64), 6, 1, "ef"),
+    "tiny_ef_masactrl": (UNetConfig.tiny(sample_size=64), 6, 1, "ef_masactrl"),
 }
 # MutualSelfAttentionControl arguments per masactrl variant (default: start_step 2, start_layer 10, total_steps T*K)
 MASA_ARGS = {
@@ -168,7 +173,7 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
     g = torch.Generator(device="cpu").manual_seed(0)
     w0 = torch.randn(1, cfg.in_channels, cfg.sample_size, cfg.sample_size, generator=g) * 0.18215 * 5
     prompts = list(PROMPTS)
-    if mode == "masactrl":
+    if mode in ("masactrl", "ef_masactrl"):
         prompts[0] = ""                      # main_masactrl.py:180
     torch.manual_seed(0)
     _, zs, wts, _ = ref.ddpm_inversion.inversion_forward_process_ddpm(
@@ -217,12 +222,38 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
         pu.register_conv_control_efficient(model, conv_ts)
         edited, recon = ph.h_Edit_PnP_implicit(model, optimization_steps=K, **kw)
         meta_extra = dict(pnp_qk_timesteps=[int(t) for t in qk_ts], pnp_conv_timesteps=[int(t) for t in conv_ts])
+    elif mode in ("ef_p2p", "pnpinv_p2p", "ef", "ef_masactrl"):
+        # main_p2p.py:245-255 / main_masactrl.py: the Edit Friendly and PnP Inversion baselines
+        pb = importlib.import_module("inversion.p2p_baselines")
+        bkw = dict(xT=wts[T], etas=1.0, prog_bar=False, zs=zs[:T], is_ddim_inversion=(mode == "pnpinv_p2p"))
+        if mode in ("ef_p2p", "pnpinv_p2p"):
+            controller = ref.ptp_controller_utils.make_controller(
+                prompts=prompts, is_replace_controller=False, cross_replace_steps=xa, self_replace_steps=sa,
+                blend_word=((BLEND[0],), (BLEND[1],)), equilizer_params={"words": (BLEND[1],), "values": (2.0,)}, num_steps=T,
+                tokenizer=model.tokenizer, device=model.device)
+            ref.ptp_utils.register_attention_control(model, controller)
+            edited, recon = pb.ef_or_pnp_inv_w_p2p(model, prompts=prompts, cfg_scales=[1.0, 7.5], controller=controller, **bkw)
+        elif mode == "ef":
+            ref.ptp_utils.register_attention_control(model, ref.ptp_classes.EmptyControl())
+            edited = pb.ef_wo_p2p(model, prompts=[prompts[1]], cfg_scales=[7.5], controller=None, **bkw)
+            recon = edited
+        else:
+            masa_pkg = importlib.import_module("masactrl")
+            sys.modules.setdefault("masa_ctrl", masa_pkg)
+            sys.modules.setdefault("masa_ctrl.masactrl_utils", importlib.import_module("masactrl.masactrl_utils"))
+            masa = importlib.import_module("masactrl.masactrl")
+            mb = importlib.import_module("inversion.masactrl_baselines")
+            editor = masa.MutualSelfAttentionControl(start_step=2, start_layer=10, total_steps=T)
+            importlib.import_module("masactrl.masactrl_utils").regiter_attention_editor_diffusers(model, editor)
+            edited, recon = mb.ef_or_pnp_inv_w_masactrl(model, prompts=prompts, cfg_scales=[1.0, 7.5], **bkw)
+            meta_extra = dict(masa_start_step=2, masa_start_layer=10, masa_total_steps=T, masa_layer_idx=None, masa_step_idx=None)
+        meta_extra = dict(meta_extra, baseline_cfg_scales=[1.0, 7.5], is_ddim_inversion=(mode == "pnpinv_p2p"))
     else:
         raise ValueError(mode)
     enc = ref.inversion_utils.encode_text
     return {
         "meta": dict(name=name, mode=mode, T=T, K=K, xa=xa, sa=sa, prompts=prompts, blend_words=BLEND, cfg_scales=[1.0, 5.0, 7.5], eta=1.0,
-                     weight_reconstruction=0.1, is_replace=False, blend=(mode == "p2p_explicit"),
+                     weight_reconstruction=0.1, is_replace=False, blend=(mode in ("p2p_explicit", "ef_p2p", "pnpinv_p2p")),
                      unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
                                cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
                      weights="oracle.sd_unet.seeded_init_(seed=0)", generator="tests/make_golden.py", torch=torch.__version__, **meta_extra),
@@ -367,7 +398,7 @@ def run_face(name="tiny_face_k2", T=5, K=2, weight=50.0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["tiny", "sd15", "sd15_config1", "sd15_config2", "sd15_config2_T50_refine_blend_th09", "tiny_refine_blend_th09", "masa", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
+    ap.add_argument("--config", default="tiny", choices=["baselines", "tiny", "sd15", "sd15_config1", "sd15_config2", "sd15_config2_T50_refine_blend_th09", "tiny_refine_blend_th09", "masa", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
     args = ap.parse_args()
     if args.config == "style":
         run_style()
@@ -381,8 +412,10 @@ def main():
         out = run_ddim_inversion(ref)
         torch.save(out, os.path.join(ROOT, "tests", "golden", "tiny_ddim_inversion.pt"))
         print("tiny_ddim_inversion |zs|", out["zs"].abs().mean().item(), flush=True)
-    if args.config in ("variants", "all", "pnp", "masa"):
+    if args.config in ("variants", "all", "pnp", "masa", "baselines"):
         for name, (cfg, T, K, mode) in VARIANTS.items():
+            if args.config == "baselines" and mode not in ("ef_p2p", "pnpinv_p2p", "ef", "ef_masactrl"):
+                continue
             if args.config == "masa" and (mode != "masactrl" or os.path.exists(os.path.join(ROOT, "tests", "golden", f"{name}.pt"))):
                 continue
             if args.config in ("variants", "all") and name.startswith("sd15") and os.path.exists(os.path.join(ROOT, "tests", "golden", f"{name}.pt")):
@@ -396,7 +429,7 @@ def main():
             torch.save(out, path)
             print(name, "->", path, "|edited| %.4f" % out["edited"].abs().mean().item(), flush=True)
     for name, (cfg, T, K, rep, blend) in CASES.items():
-        if args.config in ("variants", "inversion", "pnp", "masa") or (args.config != "all" and not name.startswith(args.config)):
+        if args.config in ("variants", "inversion", "pnp", "masa", "baselines") or (args.config != "all" and not name.startswith(args.config)):
             continue
         out = run_case(ref, name, cfg, T, K, rep, blend)
         path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
