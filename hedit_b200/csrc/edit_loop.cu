@@ -116,12 +116,12 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   const cudaMemcpyKind kIn = a.buffers_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const cudaMemcpyKind kOut = a.buffers_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (B < 1 || T < 1) { E.err_ = "bad batch/steps"; return -1; }
-  if (pnp && (a.explicit_form || a.variant != 0 || a.use_p2p || masa || !a.pnp_qk_on || !a.pnp_feat_on || a.xt_is_pair)) {
+  if (pnp && (a.explicit_form || (a.variant != 0 && a.variant != 2) || a.use_p2p || masa || !a.pnp_qk_on || !a.pnp_feat_on || a.xt_is_pair)) {
     E.err_ = "Plug-and-Play runs the implicit form only (pnp_h_edit.py:33), without P2P / MasaCtrl, and needs both per-step flag arrays";
     return -1;
   }
   if (masa && !a.masa_step_on) { E.err_ = "masa needs masa_step_on[steps * opt_steps]"; return -1; }
-  if (baseline && (pnp || a.guidance || a.pre_step || a.xt_is_pair)) { E.err_ = "variant 2 (baseline samplers) runs without PnP, reward guidance, pre_step or xt_is_pair"; return -1; }
+  if (baseline && (a.guidance || a.pre_step || a.xt_is_pair)) { E.err_ = "variant 2 (baseline samplers) runs without reward guidance, pre_step or xt_is_pair"; return -1; }
   if (a.guidance && (a.explicit_form || !a.x0_coef || !a.guid_x0 || !a.guid_grad)) {
     E.err_ = "reward guidance runs in the implicit form and needs x0_coef, guid_x0 and guid_grad";
     return -1;
@@ -165,7 +165,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
       pool += C.S;
       calls.push_back(C);
     }
-  } else if (pnp) {
+  } else if (pnp && !baseline) {
     // h_Edit_PnP_implicit (pnp_h_edit.py:104-160).  Reference pattern per step: A (4) at t, then at tt [x_opt,src], [x_opt,null] and
     // the injected pair ([xo',src],[x_opt,tar]) = 8 sample-forwards.  schedule 1 reuses the pair's untouched source sample
     // [xo',src] as the next step's [xo,src] (injection only ever writes the target sample): 7 per step.
@@ -200,6 +200,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
       e.add(XT(b, 0), 0); e.add(XT(b, 1), 0); e.add(XT(b, 0), 1 + 2 * b); e.add(XT(b, 1), 2 + 2 * b);
       e.unit(s, -1, b); e.unit(s + 1, -1, b);
       if (p2p) { e.unit(s + 2, s + 3, b); e.sq[s + 3] = s + 2; } else { e.unit(s + 2, -1, b); e.unit(s + 3, -1, b); }
+      if (pnp) e.sq[s + 3] = s + 2;             // Plug-and-Play baselines (pnp_baselines.py:317): the target of the pair takes the source's q, k and features
       e.sk[s + 1] = s; e.sk[s + 3] = s + 2;
       iuA[2 * b] = iuA0[2 * b] = s; iuA[2 * b + 1] = iuA0[2 * b + 1] = s + 1;
       icA[2 * b] = icA0[2 * b] = s + 2; icA[2 * b + 1] = icA0[2 * b + 1] = s + 3;

@@ -92,13 +92,14 @@ def invalidate_engines(model) -> None:
 def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Sequence[Sequence[str]], cfg_scales, controllers,
                      eta=1.0, weight_reconstruction=0.075, optimization_steps=1, after_skip_steps=None, is_ddim_inversion=False,
                      explicit_form=False, schedule=1, engine: Optional[UNetEngine] = None, trace=False, variant=0, masactrl=None,
-                     mos_pull=True, pnp=None, pre_coeff=None, guidance=None, coef_edit=None):
+                     mos_pull=True, pnp=None, pre_coeff=None, guidance=None, coef_edit=None, null_prompts=None):
     """B independent edits in one native call.  xT (B,C,h,w); zs (B,steps,C,h,w); prompt_pairs[b] = [src, tar];
     controllers[b] = P2P controller of image b (ours or the reference's) or None for all (P2P off)."""
     B = xT.shape[0]
     steps = after_skip_steps if after_skip_steps is not None else model.scheduler.num_inference_steps
     eng = engine or get_engine(model, max_samples=5 * B, device=_device_index(xT, None) if xT.is_cuda else None)
-    flat = [""]
+    # context 0 is the unconditional one: "" -- or, for Negative-Prompt inversion, whatever the caller substitutes for it
+    flat = [null_prompts if isinstance(null_prompts, str) else ""]
     for src, tar in prompt_pairs:
         flat += [src, tar]
     ctx = encode_prompts(model, flat).float()        # stays where the text tower left it (the C ABI accepts a context pointer on either side)
@@ -359,7 +360,7 @@ def h_edit_step(stepper: HEditStepper, xt: torch.Tensor, z: torch.Tensor) -> tor
 
 
 # ---- baseline samplers of the reference's drivers (main_p2p.py --mode ef / ef_p2p / pnp_inv_p2p, main_masactrl.py) ----------------
-def _baseline(model, xT, etas, prompts, cfg_scales, zs, controller, is_ddim_inversion, masactrl=None):
+def _baseline(model, xT, etas, prompts, cfg_scales, zs, controller, is_ddim_inversion, masactrl=None, pnp=None, null_prompt=None):
     """One native call of loop variant 2 (csrc/edit_loop.cu): per timestep ONE attention-controlled launch [xo,null] [xe,null] [xo,src]
     [xe,tar], the orig row stepped with the source-guided noise and the edit row with the target-guided noise."""
     assert len(prompts) >= 2 and len(cfg_scales) >= 2
@@ -377,7 +378,8 @@ def _baseline(model, xT, etas, prompts, cfg_scales, zs, controller, is_ddim_inve
     coef_edit = step_tables(model.scheduler, steps, 0.0, True)[1] if is_ddim_inversion else None
     w_src, w_tar = float(cfg_scales[0]), float(cfg_scales[1])
     edited, recon = h_edit_p2p_batch(model, x, z, [prompts[:2]], [w_src, w_src, w_tar], [controller] if kind == "stock" else None, etas, 0.0, 1, steps,
-                                     is_ddim_inversion, False, variant=2, masactrl=masactrl, mos_pull=False, coef_edit=coef_edit)
+                                     is_ddim_inversion, False, variant=2, masactrl=masactrl, mos_pull=False, coef_edit=coef_edit, pnp=pnp,
+                                     null_prompts=null_prompt)
     return edited.to(dev), recon.to(dev)
 
 
@@ -406,3 +408,32 @@ def ef_or_pnp_inv_w_masactrl(model, xT, etas=0, prompts="", cfg_scales=None, pro
                     masactrl=ed.launch_plan(steps, get_engine(model).n_transformer_blocks()))
     ed.cur_step += steps
     return out
+
+
+def pnp_step_flags_at_t(model, after_skip_steps: int):
+    """(qk_on, feat_on) per executed timestep for samplers whose injected pair call runs at the CURRENT timestep t (pnp_baselines.py:367
+    register_time(model, t)): `self.t in injection_schedule or self.t == 1000` (pnp_utils.py:43-44,132)."""
+    op = [int(t) for t in model.scheduler.timesteps[-after_skip_steps:]]
+    on = lambda sched: [int(sched is not None and (t in sched or t == 1000)) for t in op]
+    return on(getattr(model, "_hedit_pnp_qk", None)), on(getattr(model, "_hedit_pnp_conv", None))
+
+
+def _pnp_tuple(model, steps):
+    qk_on, feat_on = pnp_step_flags_at_t(model, steps)
+    return (pnp_self_mask(getattr(getattr(model.unet, "cfg", None), "layers_per_block", 2)), qk_on, feat_on)
+
+
+def ef_or_pnp_inv_w_pnp(model, xT, etas=0, prompts="", cfg_scales=None, prog_bar=False, zs=None, is_ddim_inversion=False):
+    """Reference signature (inversion/pnp_baselines.py:317): Edit Friendly / PnP Inversion with Plug-and-Play injection (register the
+    injection schedules with register_attention_control_efficient / register_conv_control_efficient first).  The reference's two
+    single-sample unconditional calls and its injected pair call are one 4-sample launch here (injection only ever writes the pair's
+    target sample)."""
+    assert len(prompts) >= 2 and etas == 0, "PnP requires source and target prompts, with eta is set to 0"      # reference assert (:340)
+    return _baseline(model, xT, etas, prompts, cfg_scales, zs, None, is_ddim_inversion, pnp=_pnp_tuple(model, zs.shape[0]))
+
+
+def negative_prompt_pnp(model, xT, etas=0, prompts="", cfg_scales=None, prog_bar=False, zs=None):
+    """Reference signature (inversion/pnp_baselines.py:244): Negative-Prompt inversion with Plug-and-Play -- the unconditional embedding is
+    replaced by the SOURCE prompt's, both rows use the target guidance scale (:290-291) and step deterministically (eta = 0)."""
+    assert len(prompts) >= 2 and etas == 0, "PnP requires source and target prompts, with eta is set to 0"      # reference assert (:263)
+    return _baseline(model, xT, 0, prompts, [cfg_scales[1], cfg_scales[1]], zs, None, False, pnp=_pnp_tuple(model, zs.shape[0]), null_prompt=prompts[0])

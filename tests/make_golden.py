@@ -48,6 +48,9 @@ VARIANTS = {
     "tiny_pnpinv_p2p": (UNetConfig.tiny(sample_size=64), 6, 1, "pnpinv_p2p"),
     "tiny_ef": (UNetConfig.tiny(sample_size=64), 6, 1, "ef"),
     "tiny_ef_masactrl": (UNetConfig.tiny(sample_size=64), 6, 1, "ef_masactrl"),
+    # Plug-and-Play baselines (inversion/pnp_baselines.py:317,244)
+    "tiny_ef_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "ef_pnp"),
+    "tiny_np_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "np_pnp"),
 }
 # MutualSelfAttentionControl arguments per masactrl variant (default: start_step 2, start_layer 10, total_steps T*K)
 MASA_ARGS = {
@@ -222,6 +225,19 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
         pu.register_conv_control_efficient(model, conv_ts)
         edited, recon = ph.h_Edit_PnP_implicit(model, optimization_steps=K, **kw)
         meta_extra = dict(pnp_qk_timesteps=[int(t) for t in qk_ts], pnp_conv_timesteps=[int(t) for t in conv_ts])
+    elif mode in ("ef_pnp", "np_pnp"):
+        pu = importlib.import_module("plug_n_play.pnp_utils")
+        pnb = importlib.import_module("inversion.pnp_baselines")
+        f_t, attn_t = int(T * 0.8), int(T * 0.5)
+        qk_ts, conv_ts = model.scheduler.timesteps[:attn_t], model.scheduler.timesteps[:f_t]
+        pu.register_attention_control_efficient(model, qk_ts)
+        pu.register_conv_control_efficient(model, conv_ts)
+        if mode == "ef_pnp":
+            edited, recon = pnb.ef_or_pnp_inv_w_pnp(model, xT=wts[T], etas=0, prompts=prompts, cfg_scales=[1.0, 7.5], prog_bar=False, zs=zs[:T], is_ddim_inversion=False)
+        else:
+            edited, recon = pnb.negative_prompt_pnp(model, xT=wts[T], etas=0, prompts=prompts, cfg_scales=[1.0, 7.5], prog_bar=False, zs=zs[:T])
+        meta_extra = dict(pnp_qk_timesteps=[int(t) for t in qk_ts], pnp_conv_timesteps=[int(t) for t in conv_ts], baseline_cfg_scales=[1.0, 7.5],
+                          is_ddim_inversion=False)
     elif mode in ("ef_p2p", "pnpinv_p2p", "ef", "ef_masactrl"):
         # main_p2p.py:245-255 / main_masactrl.py: the Edit Friendly and PnP Inversion baselines
         pb = importlib.import_module("inversion.p2p_baselines")
@@ -414,7 +430,9 @@ def main():
         print("tiny_ddim_inversion |zs|", out["zs"].abs().mean().item(), flush=True)
     if args.config in ("variants", "all", "pnp", "masa", "baselines"):
         for name, (cfg, T, K, mode) in VARIANTS.items():
-            if args.config == "baselines" and mode not in ("ef_p2p", "pnpinv_p2p", "ef", "ef_masactrl"):
+            if args.config == "baselines" and os.path.exists(os.path.join(ROOT, "tests", "golden", f"{name}.pt")):
+                continue
+            if args.config == "baselines" and mode not in ("ef_p2p", "pnpinv_p2p", "ef", "ef_masactrl", "ef_pnp", "np_pnp"):
                 continue
             if args.config == "masa" and (mode != "masactrl" or os.path.exists(os.path.join(ROOT, "tests", "golden", f"{name}.pt"))):
                 continue

@@ -75,3 +75,25 @@ def test_ef_with_masactrl():
     print(f"tiny_ef_masactrl: edited rel {r_ed:.3e} max {m_ed:.3e} | recon rel {r_rc:.3e} | editor cur_step {editor.cur_step}")
     assert editor.cur_step == meta["T"]
     assert r_ed < TOL_LOOP and r_rc < TOL_LOOP
+
+
+@pytest.mark.parametrize("name", ["tiny_ef_pnp", "tiny_np_pnp"])
+def test_plug_and_play_baselines(name):
+    """ef_or_pnp_inv_w_pnp / negative_prompt_pnp (inversion/pnp_baselines.py:317,244) with the injection schedules registered through the
+    pnp_utils-shaped functions; a run with injection switched off must differ (the injection is live)."""
+    g, meta, model = _setup(name)
+    fn = hedit_b200.ef_or_pnp_inv_w_pnp if name == "tiny_ef_pnp" else hedit_b200.negative_prompt_pnp
+    kw = dict(etas=0, prompts=meta["prompts"], cfg_scales=meta["baseline_cfg_scales"], zs=g["zs"].cuda())
+    if name == "tiny_ef_pnp":
+        kw["is_ddim_inversion"] = False
+    hedit_b200.register_attention_control_efficient(model, torch.tensor(meta["pnp_qk_timesteps"]))
+    hedit_b200.register_conv_control_efficient(model, torch.tensor(meta["pnp_conv_timesteps"]))
+    ed, rc = fn(model, g["xT"].cuda(), **kw)
+    r_ed, m_ed = rel_err(ed.cpu(), g["edited"])
+    r_rc, _ = rel_err(rc.cpu(), g["recon"])
+    hedit_b200.register_attention_control_efficient(model, None)
+    hedit_b200.register_conv_control_efficient(model, None)
+    ed_off, _ = fn(model, g["xT"].cuda(), **kw)
+    off = rel_err(ed_off.cpu(), g["edited"])[0]
+    print(f"{name}: edited rel {r_ed:.3e} max {m_ed:.3e} | recon rel {r_rc:.3e} | injection off: {off:.3e}")
+    assert r_ed < TOL_LOOP and r_rc < TOL_LOOP and off > 3 * r_ed
