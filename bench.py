@@ -430,6 +430,8 @@ def run_gpu(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     wl = WORKLOADS[args.config](args, rank, dev)
     B, T = wl.B, wl.T
