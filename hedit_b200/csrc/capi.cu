@@ -173,6 +173,12 @@ int hedit_engine_set_prefix_dedup(hedit_engine* h, int on) {
   return 0;
 }
 
+int hedit_engine_set_splitk(hedit_engine* h, int on) {
+  if (!h) return fail("null engine");
+  h->E->set_splitk(on != 0);
+  return 0;
+}
+
 int hedit_engine_profile_forward(hedit_engine* h, int S, int reps, char* out, int out_len) {
   if (!h) return fail("null engine");
   DeviceGuard guard_(h->device);
@@ -698,6 +704,22 @@ static int pick_bn_op(int M, int N) {
   return cost(256) < cost(160) ? 256 : 160;
 }
 
+// launch a prepared GEMM, through the split-K path when the engine's planner would choose it (operator-level tests cover both)
+static cudaError_t launch_gemm_op(GemmParams& g, int bn, cudaStream_t st) {
+  const int splits = gemm_splitk_splits(g, bn);
+  if (splits <= 1) return launch_gemm(g, bn, st);
+  float* ws = nullptr;
+  cudaError_t e = cudaMalloc(&ws, size_t(splits) * g.M * g.N * sizeof(float));
+  if (e != cudaSuccess) return e;
+  SplitKReduceParams red;
+  enable_splitk(g, splits, ws, red);
+  e = launch_gemm(g, bn, st);
+  if (e == cudaSuccess) e = launch_splitk_reduce(red, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(ws);
+  return e;
+}
+
 int hedit_op_linear(const void* A, const void* W, const float* bias, const float* residual, float* out_f32, void* out_bf16, int M, int N,
                     int K, void* stream) {
   GemmParams g; memset(&g, 0, sizeof g);
@@ -710,7 +732,7 @@ int hedit_op_linear(const void* A, const void* W, const float* bias, const float
   g.ep.bias = bias; g.ep.residual = residual; g.ep.ldr = N; g.ep.out_f32 = out_f32; g.ep.ldo = N;
   g.ep.out_bf16 = reinterpret_cast<op_t*>(out_bf16); g.ep.ldob = N; g.ep.rows_per_group = 1;
   g.ep.diag_skip = getenv("HEDIT_GEMM_DIAG_SKIP") ? atoi(getenv("HEDIT_GEMM_DIAG_SKIP")) : 0;
-  cudaError_t e = launch_gemm(g, bn, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_gemm_op(g, bn, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "linear launch");
   return 0;
 }
@@ -766,7 +788,7 @@ int hedit_op_conv3x3(const void* x, const void* w, const float* bias, float* out
   g.b_full_box = gemm_cluster() ? 0 : 1;
   if (!ok || !make_tmap_bf16(&g.tmB, w, 2, db, sb, bb)) return fail("tensor map encode failed");
   g.ep.bias = bias; g.ep.out_f32 = out; g.ep.ldo = Cout; g.ep.rows_per_group = 1;
-  cudaError_t e = launch_gemm(g, bn, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_gemm_op(g, bn, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "conv launch");
   return 0;
 }

@@ -22,6 +22,7 @@
 #include "../../include/hedit_b200.h"
 #include "engine.h"
 #include "hstep.cuh"
+#include "nvtx.h"
 
 namespace hedit {
 
@@ -97,6 +98,7 @@ struct LoopBuffers {
 };
 
 int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
+  NvtxRange nvtx_edit_("hedit.edit B=%d steps=%d", a.B, a.steps);
   const UNetCfg& c = E.cfg();
   const int B = a.B, T = a.steps, K = a.explicit_form ? 1 : std::max(1, a.opt_steps);
   const int n = E.latent_elems();
@@ -421,6 +423,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
 
   for (int i = 0; i < T; ++i) {
     const int idx = T - 1 - i;                     // zs index (p2p_h_edit.py:599)
+    NvtxRange nvtx_step_("hedit.edit.step %d of %d", i, T);
     const hedit_step_coef& hc = a.coef[i];
     // ---- call A (or the single explicit-form call) at t
     if (run_call(calls[0], i, i, true)) return -1;

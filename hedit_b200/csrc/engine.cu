@@ -11,6 +11,7 @@
 #include "compat_attn.cuh"
 #include "elementwise.cuh"
 #include "launch.h"
+#include "nvtx.h"
 #include "tmap.h"
 
 namespace hedit {
@@ -367,6 +368,33 @@ bool make_gemm(GemmParams& g, int& bn, const bf16* A, int lda, int a_mode, const
   return true;
 }
 
+// ---- split-K ------------------------------------------------------------------------------------------------------------------
+int gemm_splitk_splits(const GemmParams& g, int bn) {
+  static const bool off = getenv("HEDIT_GEMM_SPLITK") && atoi(getenv("HEDIT_GEMM_SPLITK")) == 0;
+  const GemmEpilogue& e = g.ep;
+  if (off || gemm_cluster() || e.geglu || e.nchw_hw || e.up_W > 0 || e.diag_skip || (g.N & 3) || (e.ldo & 3) || (e.ldob & 3) || (e.ldr & 3)) return 1;
+  const int tiles = ((g.M + 127) / 128) * ((g.N + bn - 1) / bn);
+  if (tiles * 2 > 148 || g.num_kb < 16) return 1;
+  int splits = std::min(std::min(8, 148 / tiles), g.num_kb / 8);
+  if (splits < 2) return 1;
+  const int per = (g.num_kb + splits - 1) / splits;
+  splits = (g.num_kb + per - 1) / per;          // no empty split
+  return splits;
+}
+void enable_splitk(GemmParams& g, int splits, float* ws, SplitKReduceParams& red) {
+  memset(&red, 0, sizeof red);
+  red.ws = ws; red.split_stride = size_t(g.M) * g.N; red.splits = splits; red.M = g.M; red.N = g.N; red.ep = g.ep;
+  if (red.ep.rows_per_group == 0) red.ep.rows_per_group = 1;
+  g.splits = splits; g.kb_per_split = (g.num_kb + splits - 1) / splits; g.split_stride = red.split_stride;
+  GemmEpilogue pe; memset(&pe, 0, sizeof pe);
+  pe.out_f32 = ws; pe.ldo = g.N; pe.rows_per_group = 1;
+  g.ep = pe;
+  g.use_tmd = 0;
+}
+cudaError_t launch_splitk_reduce(const SplitKReduceParams& red, cudaStream_t st) {
+  return launch_k(splitk_reduce_kernel, dim3((red.N + 31) / 32, (red.M + 31) / 32), dim3(256), 0, st, red);
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
@@ -393,7 +421,7 @@ static cudaError_t launch_gemm_t(const GemmParams& g, cudaStream_t st) {
     at[nat].id = cudaLaunchAttributeClusterDimension; at[nat].val.clusterDim.x = 2; at[nat].val.clusterDim.y = 1; at[nat].val.clusterDim.z = 1;
     ++nat;
   } else {
-    cfg.gridDim = dim3(std::min(m_tiles * n_tiles, num_sms()));
+    cfg.gridDim = dim3(std::min(m_tiles * n_tiles * std::max(1, g.splits), num_sms()));
   }
   if (pdl_enabled()) { at[nat].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[nat].val.programmaticStreamSerializationAllowed = 1; ++nat; }
   cfg.attrs = at; cfg.numAttrs = nat;
@@ -644,6 +672,16 @@ struct PlanBuilder {
     Op op{}; op.kind = OP_GEMM; op.tag = tag;
     if (ep.rows_per_group == 0) ep.rows_per_group = 1;
     if (!make_gemm(op.gemm, op.gemm_bn, Ain, lda, mode, cg, Wt, M, N, K, ep, E.err_)) { failed = true; return; }
+    const int splits = E.splitk() ? gemm_splitk_splits(op.gemm, op.gemm_bn) : 1;
+    if (splits > 1) {
+      float* ws = A<float>(size_t(splits) * M * N);
+      Op red{}; red.kind = OP_SPLITK_REDUCE; red.tag = tag;
+      enable_splitk(op.gemm, splits, ws, red.red);
+      push(op);
+      push(red);
+      F(ws);
+      return;
+    }
     push(op);
   }
   void gn(const float* x1, int C1, const float* x2, int C2, int HW, const float* g, const float* b, float eps, int silu, bf16* out, bf16* raw) {
@@ -921,7 +959,7 @@ struct PlanBuilder {
 
 Plan* Engine::get_plan(int S, int U) {
   if (U >= S || U < 0 || cfg_.layers < 1) U = 0;
-  const int key = S * 4096 + U;
+  const int key = (S * 4096 + U) * 2 + (splitk_ ? 1 : 0);
   auto it = plans_.find(key);
   if (it != plans_.end()) return it->second.get();
   if (S > maxS_) { err_ = "batch exceeds max_samples"; return nullptr; }
@@ -997,6 +1035,9 @@ long Engine::launch_op(Op& op, int S_call, const float* x, float* eps, const Cal
     }
     case OP_GEMM:
       CK(launch_gemm(op.gemm, op.gemm_bn, st));
+      break;
+    case OP_SPLITK_REDUCE:
+      CK(launch_splitk_reduce(op.red, st));
       break;
     case OP_LN:
       launch_layernorm(op.f_in, op.gamma, op.beta, op.h_out, op.rows, op.C1, op.eps, st);
@@ -1101,6 +1142,7 @@ long Engine::compat_attention(const Op& op, bool is_cross, int S, const CallCtrl
 }
 
 long Engine::forward(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st) {
+  NvtxRange nvtx_("hedit.unet_forward S=%d uniq=%d", S, cc.n_uniq);
   const bool dedup = cc.n_uniq > 0 && cc.n_uniq < S && cc.uniq_first && cc.uniq_of && !(cc.self_mask & 1u) && !cc.probs_cb && !cc.editor_cb;
   Plan* plan = get_plan(S, dedup ? cc.n_uniq : 0);
   if (!plan) return -1;
@@ -1123,12 +1165,13 @@ static bool loop_graphs_env() { static const bool v = !(getenv("HEDIT_LOOP_GRAPH
 
 long Engine::forward_replayed(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st) {
   if (!graph_replay_ || !loop_graphs_env() || cc.probs_cb || cc.editor_cb) return forward(x, eps, S, cc, st);
+  NvtxRange nvtx_("hedit.unet_forward_replayed S=%d uniq=%d", S, cc.n_uniq);
   // identity of the launch: every pointer / flag the kernels' parameters are derived from, packed without struct padding
   std::vector<uint8_t> key;
   {
     const void* ptrs[21] = {cc.uniq_first, cc.uniq_of, cc.map_w, cc.ctx_idx, cc.time_idx, cc.self_q, cc.self_k, cc.self_v, cc.feat_src, cc.unit_s0, cc.unit_s1, cc.unit_img,
                             cc.mapper, cc.c_base, cc.c_tar, cc.replace_m, cc.is_replace, cc.blend_acc, cc.blend_alpha, x, eps};
-    const int32_t ints[6] = {int32_t(cc.self_mask), cc.n_units, S, cc.blend_rows, cc.map_rows, cc.n_uniq};
+    const int32_t ints[7] = {int32_t(cc.self_mask), cc.n_units, S, cc.blend_rows, cc.map_rows, cc.n_uniq, int32_t(splitk_)};
     key.assign(reinterpret_cast<const uint8_t*>(ptrs), reinterpret_cast<const uint8_t*>(ptrs) + sizeof ptrs);
     key.insert(key.end(), reinterpret_cast<const uint8_t*>(ints), reinterpret_cast<const uint8_t*>(ints) + sizeof ints);
   }

@@ -21,6 +21,11 @@ struct ConvGeom { int S, H, W, C; int stride; int pad01; int ox, oy; };   // H,W
 bool make_gemm(GemmParams& g, int& bn, const op_t* A, int lda, int a_mode, const ConvGeom* cg, const op_t* Wt, int M, int N, int Ktot,
                const GemmEpilogue& ep, std::string& err, int ldw = 0);
 cudaError_t launch_gemm(const GemmParams& g, int bn, cudaStream_t st);
+// Split-K plan for a prepared launch: 1 = launch as is.  > 1: call enable_splitk with a workspace of splits * M * N floats; it rewrites
+// g to write fp32 partials and fills `red` for launch_splitk_reduce (which applies the original epilogue).  HEDIT_GEMM_SPLITK=0: never.
+int gemm_splitk_splits(const GemmParams& g, int bn);
+void enable_splitk(GemmParams& g, int splits, float* ws, SplitKReduceParams& red);
+cudaError_t launch_splitk_reduce(const SplitKReduceParams& red, cudaStream_t st);
 bool gemm_cluster();      // HEDIT_GEMM_CLUSTER=1: cta_group::2 pair variant (W boxes of BN/2 rows)
 
 struct UNetCfg {
@@ -53,12 +58,13 @@ struct WeightSlot {
   bool loaded = false;
 };
 
-enum OpKind { OP_CONV_IN, OP_GN_STATS, OP_GN_FINALIZE, OP_GN_APPLY, OP_GEMM, OP_LN, OP_SELF_ATTN, OP_CROSS_ATTN, OP_UPSAMPLE, OP_CAST, OP_CONV_OUT, OP_FEAT_COPY, OP_EXPAND };
+enum OpKind { OP_CONV_IN, OP_GN_STATS, OP_GN_FINALIZE, OP_GN_APPLY, OP_GEMM, OP_LN, OP_SELF_ATTN, OP_CROSS_ATTN, OP_UPSAMPLE, OP_CAST, OP_CONV_OUT, OP_FEAT_COPY, OP_EXPAND, OP_SPLITK_REDUCE };
 
 struct Op {
   OpKind kind;
   // generic payloads (only the ones relevant to `kind` are used)
   GemmParams gemm; int gemm_bn = 0;
+  SplitKReduceParams red;
   AttnParams attn; int dch = 0, bkv = 0, tf_index = 0, blend_layer = -1;
   const bf16 *cq = nullptr, *ck = nullptr, *cv = nullptr; int c_ldq = 0, c_ldkv = 0;   // raw operand pointers for the compat attention path
   const float* f_in = nullptr; const float* f_in2 = nullptr; float* f_out = nullptr;
@@ -155,6 +161,10 @@ class Engine {
   long forward_replayed(const float* x, float* eps, int S, const CallCtrl& cc, cudaStream_t st);
   void set_graph_replay(bool on) { graph_replay_ = on; }
   void set_prefix_dedup(bool on) { prefix_dedup_ = on; }
+  // split-K for launches with far fewer tiles than SMs (single-image use).  Off by default: a split changes the fp32 summation order of
+  // the affected layers, so results stop being bit-identical ACROSS batch sizes (they stay run-to-run reproducible)
+  void set_splitk(bool on) { splitk_ = on; }
+  bool splitk() const { return splitk_; }
   bool prefix_dedup() const { return prefix_dedup_; }
   void drop_graphs();
 
@@ -202,6 +212,7 @@ class Engine {
   cudaStream_t cap_stream_ = nullptr;
   bool graph_replay_ = true;
   bool prefix_dedup_ = true;
+  bool splitk_ = false;
 };
 
 }  // namespace hedit

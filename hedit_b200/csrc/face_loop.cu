@@ -2,6 +2,7 @@
 // one denoiser call at t and the DDPM-style step to x_{t-1}^base (:72-88), then per implicit-loop iteration two reward-guided moves on
 // the Tweedie prediction -- identity loss (optionally masked) and LPIPS -- each preceded by a fresh denoiser call at t-1 (:96-131).
 // The reward gradients come through the hook (the caller's ArcFace / LPIPS modules); everything else runs here without host syncs.
+#include "nvtx.h"
 #include "../../include/hedit_b200.h"
 #include "face.h"
 
@@ -33,6 +34,7 @@ __global__ void face_update_kernel(float* __restrict__ x, const float* __restric
 }
 
 int run_face_edit(FaceUNet& U, hedit_face_args& a, cudaStream_t st) {
+  NvtxRange nvtx_edit_("hedit.face.edit B=%d steps=%d", a.B, a.steps);
   const FaceCfg& c = U.cfg();
   const int B = a.B, T = a.steps, n = c.in_ch * c.resolution * c.resolution;
   if (B < 1 || T < 1 || !a.xT || !a.zs || !a.coef || !a.edited) { U.err_ = "bad face edit arguments"; return -1; }

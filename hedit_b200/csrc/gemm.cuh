@@ -42,6 +42,12 @@ struct GemmParams {
   CUtensorMap tmA, tmB;
   CUtensorMap tmD;          // 16-bit output [M][ldob] as boxes of 64 columns x 32 rows (128B swizzle) when use_tmd (bulk tensor stores)
   int use_tmd;
+  // split-K (launches with far fewer tiles than SMs and a long K loop: the deep 8x8 / 16x16 levels at 1-5 samples).  splits > 1: work
+  // item = (tile, split); split s accumulates K blocks [s * kb_per_split, ...) and writes its fp32 partial tile to
+  // ep.out_f32 + s * split_stride (ep then carries no bias / residual / statistics); splitk_reduce_kernel adds the partials in a fixed
+  // order and applies the real epilogue
+  int splits, kb_per_split;
+  size_t split_stride;
   int M, N, num_kb;
   int a_mode, conv_W, conv_H, conv_cin, cin_blocks;
   int conv_ox, conv_oy;     // A_CONV2X2 only: first tap offset per axis (-1 for output phase 0, 0 for phase 1)
@@ -141,6 +147,11 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
   const int tile0 = CLUSTER ? int(blockIdx.x >> 1) : int(blockIdx.x);
   const int tstep = CLUSTER ? int(gridDim.x >> 1) : int(gridDim.x);
   auto tile_m0 = [&](int tile) { return CLUSTER ? (((tile / n_tiles) * 2 + int(rank)) << 7) : ((tile / n_tiles) << 7); };
+  // split-K: the loops below iterate WORK items w = split * num_tiles + tile (splits == 1: w == tile)
+  const int nsplit = (!CLUSTER && p.splits > 1) ? p.splits : 1;
+  const int num_work = num_tiles * nsplit;
+  auto work_kb0 = [&](int w) { return (w / num_tiles) * p.kb_per_split; };
+  auto work_kb1 = [&](int w) { return nsplit > 1 ? min(p.num_kb, (w / num_tiles + 1) * p.kb_per_split) : p.num_kb; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -167,7 +178,9 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
     // ------------------------------------------------------------------ TMA producer (whole warp runs the loop so the
     // addressing stays in uniform registers; one elected lane issues the copies)
     int stage = 0; uint32_t phase = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tstep) {
+    for (int work = tile0; work < num_work; work += tstep) {
+      const int tile = work % num_tiles;
+      const int kb0 = nsplit > 1 ? work_kb0(work) : 0, kb1 = work_kb1(work);
       const int m0 = tile_m0(tile);
       const int n0 = (tile % n_tiles) * BN;
       int s0 = 0, y0 = 0, x0 = 0;
@@ -182,8 +195,8 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
       auto k_loop = [&](auto mode_c) {
         constexpr int MODE = decltype(mode_c)::value;
         constexpr int KW = (MODE == A_CONV2X2) ? 2 : 3;
-        int tap = 0, cb = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        int tap = (MODE == A_LINEAR) ? 0 : kb0 / p.cin_blocks, cb = (MODE == A_LINEAR) ? 0 : kb0 % p.cin_blocks;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -240,31 +253,32 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
       // The issue thread is the critical resource at 128x160 tiles (4 MMAs = 320 tensor cycles per K block): probe the NEXT
       // stage's barrier (non-blocking) before issuing the current stage's MMAs so its latency hides behind them.
       bool ready = mbar_test(&full_bar[0], 0);
-      for (int tile = tile0; tile < num_tiles; tile += tstep, ++it) {
+      for (int work = tile0; work < num_work; work += tstep, ++it) {
+        const int kb0 = nsplit > 1 ? work_kb0(work) : 0, kb1 = work_kb1(work);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        const bool last_tile = (tile + tstep >= num_tiles);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const bool last_tile = (work + tstep >= num_work);
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (!ready) mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           int nstage = stage + 1; uint32_t nphase = phase;
           if (nstage == STAGES) { nstage = 0; nphase ^= 1; }
-          const bool more = !(last_tile && kb + 1 == p.num_kb);
+          const bool more = !(last_tile && kb + 1 == kb1);
           ready = more ? mbar_test(&full_bar[nstage], nphase) : false;
           if (elect_one()) {
             const uint32_t la = a_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
             const uint32_t lb = b_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
             if (CLUSTER) {
-              umma_f16_ss_2sm(d_tmem, umma_desc_make(la), umma_desc_make(lb), idesc, kb != 0);
+              umma_f16_ss_2sm(d_tmem, umma_desc_make(la), umma_desc_make(lb), idesc, kb != kb0);
               umma_f16_ss_2sm(d_tmem, umma_desc_make(la + 2), umma_desc_make(lb + 2), idesc, 1);
               umma_f16_ss_2sm(d_tmem, umma_desc_make(la + 4), umma_desc_make(lb + 4), idesc, 1);
               umma_f16_ss_2sm(d_tmem, umma_desc_make(la + 6), umma_desc_make(lb + 6), idesc, 1);
               umma_commit_2sm(&empty_bar[stage], 3);
             } else {
-              umma_f16_ss(d_tmem, umma_desc_make(la), umma_desc_make(lb), idesc, kb != 0);
+              umma_f16_ss(d_tmem, umma_desc_make(la), umma_desc_make(lb), idesc, kb != kb0);
               umma_f16_ss(d_tmem, umma_desc_make(la + 2), umma_desc_make(lb + 2), idesc, 1);
               umma_f16_ss(d_tmem, umma_desc_make(la + 4), umma_desc_make(lb + 4), idesc, 1);
               umma_f16_ss(d_tmem, umma_desc_make(la + 6), umma_desc_make(lb + 6), idesc, 1);
@@ -303,7 +317,9 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
       else if (!has_b && !has_rv && has_res && has32 && !has16) mode = 8;
     }
     int it = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tstep, ++it) {
+    for (int work = tile0; work < num_work; work += tstep, ++it) {
+      const int tile = work % num_tiles;
+      float* const out_f32 = e.out_f32 ? e.out_f32 + (nsplit > 1 ? size_t(work / num_tiles) * p.split_stride : size_t(0)) : nullptr;
       const int m0 = tile_m0(tile);
       const int n0 = (tile % n_tiles) * BN;
       const int acc = it & 1;
@@ -456,7 +472,7 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
             if (m < p.M && cols_ok) {
               const int sm_ = m / hw, rem = m - sm_ * hw, y = rem / e.up_W, x = rem - y * e.up_W;
               const size_t frow = (size_t(sm_) * 2 * e.up_H + 2 * y + e.up_py) * (2 * e.up_W) + 2 * x + e.up_px;
-              *reinterpret_cast<float4*>(e.out_f32 + frow * e.ldo + cq) = a;
+              *reinterpret_cast<float4*>(out_f32 + frow * e.ldo + cq) = a;
               su.x += a.x; su.y += a.y; su.z += a.z; su.w += a.w;
               sq.x = fmaf(a.x, a.x, sq.x); sq.y = fmaf(a.y, a.y, sq.y); sq.z = fmaf(a.z, a.z, sq.z); sq.w = fmaf(a.w, a.w, sq.w);
             }
@@ -471,7 +487,7 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
         if (EPI != 2 && c0 + CSTEP < BN) prefetch(col + CSTEP, bbN, rvvN, rsN);      // next chunk of this warp (warp-uniform condition)
         const int cq = col + 4 * rq;
         if (mode != 0 && rows_full && col + 32 <= p.N) {
-          float* o32 = has32 ? e.out_f32 + row0 * e.ldo + cq : nullptr;
+          float* o32 = has32 ? out_f32 + row0 * e.ldo + cq : nullptr;
           op_t* o16 = has16 ? e.out_bf16 + row0 * e.ldob + cq : nullptr;
           const size_t l32 = size_t(4) * e.ldo, l16 = size_t(4) * e.ldob;
           float2* cst = e.colstats ? e.colstats + size_t(rbase >> 5) * p.N + cq : nullptr;
@@ -502,9 +518,9 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
                 if (e.rowvec) x += e.rowvec[size_t(row / e.rows_per_group) * e.ldrv + cc];
                 if (e.residual) x += e.residual[size_t(row) * e.ldr + cc];
                 gsu[k] += x; gsq[k] = fmaf(x, x, gsq[k]);
-                if (e.out_f32) {
-                  if (e.nchw_hw) e.out_f32[(size_t(row / e.nchw_hw) * p.N + cc) * e.nchw_hw + (row % e.nchw_hw)] = x;
-                  else e.out_f32[size_t(row) * e.ldo + cc] = x;
+                if (out_f32) {
+                  if (e.nchw_hw) out_f32[(size_t(row / e.nchw_hw) * p.N + cc) * e.nchw_hw + (row % e.nchw_hw)] = x;
+                  else out_f32[size_t(row) * e.ldo + cc] = x;
                 }
                 if (e.out_bf16) e.out_bf16[size_t(row) * e.ldob + cc] = to_op(x);
               }
@@ -537,6 +553,53 @@ __global__ void __launch_bounds__(EPI ? 576 : 320, 1) gemm_bf16_tcgen05_kernel(c
   if (warp == 1) {
     tc_fence_after();
     if (CLUSTER) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Split-K second pass: out = sum_s ws[s] (fixed order) + bias + time-embedding row + residual -> fp32 and / or 16-bit, plus the column
+// statistics of the fp32 output per 32-row block (same layout as the GEMM epilogue's).  block = 256 threads = 32 rows x 8 column quads;
+// grid (ceil(N / 32), ceil(M / 32)).
+struct SplitKReduceParams {
+  const float* ws; size_t split_stride; int splits;
+  int M, N;
+  GemmEpilogue ep;
+};
+static __global__ void splitk_reduce_kernel(const SplitKReduceParams p) {
+  pdl_wait(); pdl_launch();
+  __shared__ float4 ssu[32][8], ssq[32][8];
+  const int q = threadIdx.x & 7, r = threadIdx.x >> 3;
+  const int row = blockIdx.y * 32 + r, col = blockIdx.x * 32 + 4 * q;
+  const GemmEpilogue& e = p.ep;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool ok = row < p.M && col + 4 <= p.N;
+  if (ok) {
+    const float* w = p.ws + size_t(row) * p.N + col;
+    a = *reinterpret_cast<const float4*>(w);
+    for (int s = 1; s < p.splits; ++s) {
+      const float4 t = *reinterpret_cast<const float4*>(w + size_t(s) * p.split_stride);
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    if (e.bias) { const float4 b = *reinterpret_cast<const float4*>(e.bias + col); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    if (e.rowvec) { const float4 b = *reinterpret_cast<const float4*>(e.rowvec + size_t(row / e.rows_per_group) * e.ldrv + col); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    if (e.residual) { const float4 b = *reinterpret_cast<const float4*>(e.residual + size_t(row) * e.ldr + col); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + size_t(row) * e.ldo + col) = a;
+    if (e.out_bf16) *reinterpret_cast<uint2*>(e.out_bf16 + size_t(row) * e.ldob + col) = make_uint2(pack_op2(a.x, a.y), pack_op2(a.z, a.w));
+  }
+  if (e.colstats) {
+    ssu[r][q] = ok ? a : make_float4(0.f, 0.f, 0.f, 0.f);
+    ssq[r][q] = ok ? make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (r == 0 && col + 4 <= p.N && blockIdx.y * 32 < p.M) {
+      float4 su = ssu[0][q], sq = ssq[0][q];
+      for (int k = 1; k < 32; ++k) {
+        const float4 u = ssu[k][q], v = ssq[k][q];
+        su.x += u.x; su.y += u.y; su.z += u.z; su.w += u.w;
+        sq.x += v.x; sq.y += v.y; sq.z += v.z; sq.w += v.w;
+      }
+      float2* dst = e.colstats + size_t(blockIdx.y) * p.N + col;
+      reinterpret_cast<float4*>(dst)[0] = make_float4(su.x, sq.x, su.y, sq.y);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(su.z, sq.z, su.w, sq.w);
+    }
   }
 }
 

@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "elementwise.cuh"
+#include "nvtx.h"
 #include "reward.cuh"
 #include "tmap.h"
 #include "vae.cuh"
@@ -353,6 +354,7 @@ int ArcFaceNet::set_reference(const float* img, cudaStream_t st) {
 }
 
 int ArcFaceNet::loss_grad(const float* img, int B, float* loss, float* grad, cudaStream_t st) {
+  NvtxRange nvtx_("hedit.arcface.loss_grad B=%d%.0d", B, 0);
   if (!ready_ || !have_ref_) { err_ = "ArcFace: finalize() and set_reference() first"; return -1; }
   if (B < 1 || !img || !grad) { err_ = "bad arguments"; return -1; }
   if (ensure_arena(B, true)) return -1;
@@ -563,6 +565,7 @@ int LpipsNet::set_source(const float* img, int n, int R, cudaStream_t st) {
 }
 
 int LpipsNet::loss_grad(const float* img, int B, float* loss, float* grad, cudaStream_t st) {
+  NvtxRange nvtx_("hedit.lpips.loss_grad B=%d%.0d", B, 0);
   if (!ready_ || !nsrc_) { err_ = "LPIPS: finalize() and set_source() first"; return -1; }
   if (B < 1 || !img || !grad || (nsrc_ != 1 && nsrc_ != B)) { err_ = "LPIPS: batch must match the number of source images (or use one source)"; return -1; }
   uint8_t* saved = arena_;

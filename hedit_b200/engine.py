@@ -153,6 +153,11 @@ class UNetEngine:
         """Evaluate the UNet's context-free prefix once per distinct latent of a launch (default on).  Bit-identical results."""
         _lib.check(self.lib.hedit_engine_set_prefix_dedup(self.handle, int(bool(on))), "set_prefix_dedup")
 
+    def set_splitk(self, on: bool) -> None:
+        """Split-K for launches with far fewer tiles than SMs (1-5 samples at the deep levels).  Off by default: with it the low bits of a
+        result depend on the batch size (results stay run-to-run reproducible); the one-image samplers switch it on."""
+        _lib.check(self.lib.hedit_engine_set_splitk(self.handle, int(bool(on))), "set_splitk")
+
     def n_transformer_blocks(self) -> int:
         """Transformer blocks of the SD-1.x layout (attention on every level but the deepest, plus the mid block): 16 for SD-1.5;
         the reference's controllers count 2 attention layers per block (ptp_utils.py:277-295)."""

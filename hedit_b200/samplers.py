@@ -98,6 +98,10 @@ def h_edit_p2p_batch(model, xT: torch.Tensor, zs: torch.Tensor, prompt_pairs: Se
     B = xT.shape[0]
     steps = after_skip_steps if after_skip_steps is not None else model.scheduler.num_inference_steps
     eng = engine or get_engine(model, max_samples=5 * B, device=_device_index(xT, None) if xT.is_cuda else None)
+    if engine is None:
+        # one image per call (the reference's signature): 2-5 samples per launch leave most SMs idle in the deep levels -> split-K.  Batches
+        # keep it off so that an image's result does not depend on what it is batched with.
+        eng.set_splitk(B == 1)
     # context 0 is the unconditional one: "" -- or, for Negative-Prompt inversion, whatever the caller substitutes for it
     flat = [null_prompts if isinstance(null_prompts, str) else ""]
     for src, tar in prompt_pairs:
@@ -308,6 +312,7 @@ def h_Edit_PnP_implicit(model, xT, eta=0, prompts="", cfg_scales=None, prog_bar=
     B = 1
     dev = xT.device
     eng = get_engine(model, max_samples=5 * B, device=_device_index(xT, None) if xT.is_cuda else None)
+    eng.set_splitk(True)       # one image per call: see h_edit_p2p_batch
     x = xT.reshape(1, *xT.shape[-3:])
     z = zs[:after_skip_steps].reshape(1, after_skip_steps, *xT.shape[-3:])
     use_cuda = torch.device(dev).type == "cuda"

@@ -160,6 +160,10 @@ int hedit_engine_set_graph_replay(hedit_engine* e, int on);
  * context-free prefix (conv_in, down_blocks[0].resnets[0], the first transformer block's self-attention) once per distinct latent and
  * broadcasts it.  On by default (HEDIT_PREFIX_DEDUP=0 or on=0: every sample evaluates it).  Bit-identical results either way. */
 int hedit_engine_set_prefix_dedup(hedit_engine* e, int on);
+/* split-K for the launches of the deep UNet levels at 1-5 samples (8 / 20 tiles on 148 SMs otherwise): K is cut into <= 8 ranges whose
+ * fp32 partial tiles are added in a fixed order by a second kernel that applies the epilogue.  Off by default -- with it the low bits
+ * of a result depend on the batch size; the one-image samplers (h_Edit_p2p_implicit(model, xT, ...), main_p2p.py:224) switch it on. */
+int hedit_engine_set_splitk(hedit_engine* e, int on);
 /* diagnostics: one UNet forward of S samples with CUDA events around every kernel; writes "tag:ms:launches;" records */
 int hedit_engine_profile_forward(hedit_engine* e, int S, int reps, char* out, int out_len);
 

@@ -22,7 +22,8 @@ def _seed(s=0):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 160, 64), (256, 320, 320), (4096, 960, 320), (1000, 1280, 1280), (77 * 3, 2560, 768),
-                                   (64, 64, 64), (4096 * 2, 320, 2880), (130, 48, 200)])
+                                   (64, 64, 64), (4096 * 2, 320, 2880), (130, 48, 200),
+                                   (128, 1280, 5120), (320, 1280, 2560), (512, 640, 4096 + 64)])       # few tiles, long K: the split-K path
 def test_linear(M, N, K):
     _seed()
     A, W = bf(torch.randn(M, K, device=DEV)), bf(torch.randn(N, K, device=DEV) / math.sqrt(K))
@@ -63,7 +64,8 @@ def test_linear_geglu(M, Nout, K):
 
 @pytest.mark.parametrize("S,H,W,C,Cout,stride", [(2, 64, 64, 64, 64, 1), (1, 64, 64, 320, 320, 1), (3, 32, 32, 128, 256, 1),
                                                  (5, 8, 8, 192, 160, 1), (4, 16, 16, 640, 320, 1), (2, 64, 64, 64, 128, 2),
-                                                 (3, 32, 32, 128, 128, 2), (5, 16, 16, 256, 256, 2), (9, 4, 4, 64, 64, 1), (2, 64, 64, 960, 320, 1)])
+                                                 (3, 32, 32, 128, 128, 2), (5, 16, 16, 256, 256, 2), (9, 4, 4, 64, 64, 1), (2, 64, 64, 960, 320, 1),
+                                                 (2, 8, 8, 1280, 1280, 1), (5, 8, 8, 2560, 1280, 1), (2, 16, 16, 640, 640, 2)])     # split-K (1-5 samples at the deep levels)
 def test_conv3x3(S, H, W, C, Cout, stride):
     _seed(1)
     x = bf(torch.randn(S, H, W, C, device=DEV))
