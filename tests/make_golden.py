@@ -295,7 +295,7 @@ def run_ddim_inversion(ref, name="tiny_ddim_inversion", T=6):
             "w0": w0, "latent": latent.clone(), "zs": zs.clone(), "latents": torch.cat(latents).clone()}
 
 
-def run_style(name="tiny_style_mos2", T=4, K=2, weight=0.5):
+def run_style(name="tiny_style_mos2", T=4, K=2, weight=0.5, full=False):
     """The UNMODIFIED style sampler (text-guided-n-style/inversion/h_edit.py:14 `h_Edit_p2p_implicit(model, image_encoder, ...)`) with the
     reference's own `CLIPEncoder.get_gram_matrix_residual` (clip_guidance/base_clip.py:55) on a small seeded CLIP ViT and the oracle's
     small VAE decoder.  Must run in its own process: the style tree has its own `inversion` / `p2p` packages."""
@@ -315,15 +315,18 @@ def run_style(name="tiny_style_mos2", T=4, K=2, weight=0.5):
     import torchvision
 
     torch.set_num_threads(os.cpu_count())
-    cfg = UNetConfig.tiny(sample_size=64)
+    # full = True: BASELINE.json configs[3] geometry -- SD-1.5 UNet, SD VAE decoder (128, 256, 512, 512), CLIP ViT-B/16 width (768, 12 heads;
+    # the Gram residual only reads the first three transformer blocks, base_clip.py:55-66, so three are built)
+    cfg = UNetConfig.sd15() if full else UNetConfig.tiny(sample_size=64)
+    vw = 768 if full else 64
     model = OraclePipeline(cfg, seed=0)
-    model.vae = AutoencoderKLDecoder(VAEConfig.tiny())
+    model.vae = AutoencoderKLDecoder(VAEConfig() if full else VAEConfig.tiny())
     model.scheduler.set_timesteps(T)
-    tiny = tiny_style_encoder()
+    tiny = tiny_style_encoder(width=vw)
     # the reference's CLIPEncoder, constructed without its weight download (base_clip.py:31-52), carrying the same seeded weights
     enc = bc.CLIPEncoder.__new__(bc.CLIPEncoder)
     torch.nn.Module.__init__(enc)
-    enc.clip_model = clip_model.CLIP(embed_dim=32, image_resolution=224, vision_layers=3, vision_width=64, vision_patch_size=16, context_length=8,
+    enc.clip_model = clip_model.CLIP(embed_dim=32, image_resolution=224, vision_layers=3, vision_width=vw, vision_patch_size=16, context_length=8,
                                      vocab_size=64, transformer_width=64, transformer_heads=1, transformer_layers=1)
     enc.clip_model.visual.load_state_dict(tiny.visual.state_dict())
     enc.preprocess = torchvision.transforms.Normalize((0.48145466 * 2 - 1, 0.4578275 * 2 - 1, 0.40821073 * 2 - 1),
@@ -355,7 +358,8 @@ def run_style(name="tiny_style_mos2", T=4, K=2, weight=0.5):
                         weight_edit_clip=weight, is_replace=False, blend=False,
                         unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
                                   cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
-                        vae="oracle.vae.AutoencoderKLDecoder(VAEConfig.tiny(), seed 7)", clip="oracle.clip_visual.tiny_style_encoder(seed 11)",
+                        vae="oracle.vae.AutoencoderKLDecoder(VAEConfig%s, seed 7)" % ("()" if full else ".tiny()"),
+                        clip="oracle.clip_visual.tiny_style_encoder(seed 11, width %d)" % vw, full_geometry=bool(full), clip_width=vw,
                         generator="tests/make_golden.py --config style", torch=torch.__version__),
            "w0": w0, "zs": zs[:T].clone(), "xT": wts[T].clone(),
            "ctx_uncond": enc_t(model, [""]), "ctx_src": enc_t(model, [PROMPTS[0]]), "ctx_tar": enc_t(model, [PROMPTS[1]]),
@@ -414,10 +418,13 @@ def run_face(name="tiny_face_k2", T=5, K=2, weight=50.0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["baselines", "tiny", "sd15", "sd15_config1", "sd15_config2", "sd15_config2_T50_refine_blend_th09", "tiny_refine_blend_th09", "masa", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
+    ap.add_argument("--config", default="tiny", choices=["style_sd15", "baselines", "tiny", "sd15", "sd15_config1", "sd15_config2", "sd15_config2_T50_refine_blend_th09", "tiny_refine_blend_th09", "masa", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
     args = ap.parse_args()
     if args.config == "style":
         run_style()
+        return
+    if args.config == "style_sd15":
+        run_style(name="sd15_config4_T10_style_k3", T=10, K=3, weight=0.5, full=True)
         return
     if args.config == "face":
         run_face()

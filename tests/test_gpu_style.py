@@ -86,3 +86,33 @@ def test_guidance_callback_errors_surface():
     zs = g["zs"].reshape(1, *g["zs"].shape).cuda()
     with pytest.raises(ValueError, match="boom"):
         hedit_b200.style.h_edit_style_batch(model, None, xT, zs, [meta["prompts"]], meta["cfg_scales"], None, after_skip_steps=T, guidance_fn=bad)
+
+
+def test_style_sampler_full_geometry_golden():
+    """BASELINE.json configs[3] geometry (SD-1.5 UNet, SD VAE decoder, CLIP ViT-B/16 width), T = 10, K = 3 Langevin steps per timestep: the
+    native loop + native VAE decode / backward + native CLIP-Gram reward against the UNMODIFIED reference sampler's output
+    (tests/make_golden.py --config style_sd15)."""
+    if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "sd15_config4_T10_style_k3.pt")):
+        pytest.skip("full-size golden missing")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = load_golden("sd15_config4_T10_style_k3")
+    meta = g["meta"]
+    T, K = meta["T"], meta["K"]
+    model = OraclePipeline(cfg_from_meta(meta), seed=0)
+    model.scheduler.set_timesteps(T)
+    model.vae = AutoencoderKLDecoder(VAEConfig()).cuda()
+    enc = tiny_style_encoder(width=meta["clip_width"]).cuda()
+    ctrl = hedit_b200.make_controller(meta["prompts"], False, meta["xa"], meta["sa"], blend_word=None, equilizer_params=None, num_steps=T,
+                                      tokenizer=model.tokenizer)
+    ed, rc = hedit_b200.style.h_Edit_p2p_implicit(model, enc, xT=g["xT"].cuda(), eta=meta["eta"], prompts=meta["prompts"],
+                                                  cfg_scales=meta["cfg_scales"], zs=g["zs"].cuda(), controller=ctrl,
+                                                  weight_edit_clip=meta["weight_edit_clip"], optimization_steps=K, after_skip_steps=T,
+                                                  is_ddim_inversion=False, autocast=False, native_vae=True, native_clip=True)
+    r_ed, m_ed = rel_err(ed.cpu(), g["edited"])
+    r_rc, m_rc = rel_err(rc.cpu(), g["recon"])
+    r_ns, _ = rel_err(ed.cpu(), g["edited_no_style"])
+    print(f"sd15_config4_T10_style_k3: edited rel {r_ed:.3e} max {m_ed:.3e} (|latent| max {float(g['edited'].abs().max()):.1f}) | recon rel {r_rc:.3e} max {m_rc:.3e} | "
+          f"distance to the no-style edit {r_ns:.3e}")
+    assert r_ed < TOL_STYLE and r_rc < TOL_STYLE
+    assert r_ns > 3 * r_ed            # the style term is live at this geometry too
