@@ -234,6 +234,41 @@ def test_edit_loop_sd15_config1():
     assert r_rc < TOL_LOOP and r_ed < TOL_LOOP
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "sd15_config1.pt")), reason="full-size golden missing")
+def test_one_image_signature_sd15_config1_with_splitk():
+    """The reference's one-image call `h_Edit_p2p_implicit(model, xT, ...)` (main_p2p.py:224) at full SD-1.5 geometry: the public sampler
+    switches split-K on for B = 1 (2-5 samples per launch leave the 8x8 / 16x16 levels with 8-60 tiles).  Same golden, same tolerance; and
+    against the batch path of the same edit the split changes only fp32 summation order (small but non-zero difference)."""
+    _fp32()
+    g = load_golden("sd15_config1")
+    meta = g["meta"]
+    model = OraclePipeline(cfg_from_meta(meta), seed=0)
+    model.scheduler.set_timesteps(meta["T"])
+    bw = meta["blend_words"]
+    mk = lambda: hedit_b200.make_controller(meta["prompts"], meta["is_replace"], meta["xa"], meta["sa"], blend_word=((bw[0],), (bw[1],)),
+                                            equilizer_params={"words": (bw[1],), "values": (1.25 if meta["K"] > 1 else 2.0,)},
+                                            num_steps=meta["T"], tokenizer=model.tokenizer)
+    kw = dict(eta=meta["eta"], prompts=meta["prompts"], cfg_scales=meta["cfg_scales"], zs=g["zs"].cuda(), weight_reconstruction=meta["weight_reconstruction"],
+              optimization_steps=meta["K"], after_skip_steps=meta["T"], is_ddim_inversion=False)
+    ed, rc = hedit_b200.h_Edit_p2p_implicit(model, g["xT"].cuda(), controller=mk(), **kw)
+    eng = hedit_b200.get_engine(model)
+    split_launches = eng.last_stats["kernel_launches"]
+    r_ed, m_ed = rel_err(ed.cpu(), g["edited"])
+    r_rc, _ = rel_err(rc.cpu(), g["recon"])
+    # the same edit as a batch of one through the batch entry point with an explicit engine: split-K stays off
+    eng.set_splitk(False)
+    x = g["xT"].reshape(1, *g["xT"].shape[-3:]).cuda()
+    z = g["zs"][:meta["T"]].reshape(1, meta["T"], *g["xT"].shape[-3:]).cuda()
+    ed_b, rc_b = hedit_b200.h_edit_p2p_batch(model, x, z, [meta["prompts"][:2]], meta["cfg_scales"], [mk()], meta["eta"], meta["weight_reconstruction"],
+                                            meta["K"], meta["T"], False, False, engine=eng)
+    plain_launches = eng.last_stats["kernel_launches"]
+    d, _ = rel_err(ed, ed_b)
+    print(f"one-image signature, sd15_config1: edited rel {r_ed:.3e} max {m_ed:.3e} | recon rel {r_rc:.3e} | split-K vs plain: rel {d:.3e} | launches {split_launches} vs {plain_launches}")
+    assert r_ed < TOL_LOOP and r_rc < TOL_LOOP
+    assert split_launches > plain_launches            # the reduce kernels of the split launches
+    assert d < 0.25 * TOL_LOOP
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # other reference samplers on the same hot path (SURVEY 8a rows 2 and 10), each against a golden produced by the
 # unmodified reference function (tests/make_golden.py --config variants)
