@@ -115,6 +115,8 @@ def _seed_init(m: nn.Module, seed: int):
                 mod.running_var.copy_(0.8 + 0.4 * torch.rand(mod.bias.shape, generator=g))
             elif isinstance(mod, nn.PReLU):
                 mod.weight.copy_(0.1 + 0.3 * torch.rand(mod.weight.shape, generator=g))
+        for p in getattr(m, "lins", []):           # LPIPS 1x1 heads: non-negative, like the trained ones (the constructor draws them unseeded)
+            p.copy_(torch.rand(p.shape, generator=g) * 0.02)
     return m.eval().requires_grad_(False)
 
 

@@ -370,6 +370,74 @@ def run_style(name="tiny_style_mos2", T=4, K=2, weight=0.5, full=False):
           "| style term moved the edit by %.4f (rel)" % ((edited - edited_ns).norm() / edited_ns.norm()).item(), flush=True)
 
 
+def run_face_full(name="face256_irse50_lpips_k2", T=4, K=2, weight=1500.0, lin_gain=100.0):
+    """The UNMODIFIED face-swapping sampler `h_Edit_R` (face-swapping/inversion/h_edit_R.py:7) driving the reference's OWN reward classes:
+    `IDLoss` (arcface/arcface_model.py:12) around the reference `Backbone(112, 50, 'ir_se')` and `LPIPS_Loss` (:72) around `lpips.LPIPS`
+    (tests/refshim/lpips: the package itself is not available offline), both with seeded random weights and seeded images instead of
+    model_ir_se50.pth / the jpg files their constructors open.  256 x 256 images (the crop [35:223, 32:220] the identity network sees
+    needs them), a 4-level DDPM UNet carrying the oracle's seeded weights."""
+    import importlib
+    import numpy as np
+    for p in (os.path.join(ROOT, "tests", "refshim"), "/root/reference/face-swapping"):
+        sys.path.insert(0, p)
+    from oracle.face_unet import FaceUNet, FaceUNetConfig
+    from hedit_b200 import reward_nets
+    ref_model = importlib.import_module("diffusion.diffusion")
+    du = importlib.import_module("diffusion.diffusion_utils")
+    inv = importlib.import_module("inversion.sde_inversion")
+    he = importlib.import_module("inversion.h_edit_R")
+    am = importlib.import_module("arcface.arcface_model")
+    irse = importlib.import_module("arcface.facial_recognition.model_irse")
+    import lpips
+    torch.set_num_threads(os.cpu_count())
+    cfg = FaceUNetConfig(ch=64, ch_mult=(1, 1, 2, 2), image_size=256, attn_resolutions=(32,))
+    model = ref_model.Model(cfg.as_reference_dict())
+    model.load_state_dict(FaceUNet(cfg).state_dict())
+    model.eval()
+    betas = torch.from_numpy(du.get_beta_schedule(beta_schedule="linear", beta_start=0.0001, beta_end=0.02, num_diffusion_timesteps=1000)).float()
+    seq = (np.arange(0, 1000, 1000 // T) + 1)[::-1]
+    g = torch.Generator(device="cpu").manual_seed(0)
+    smooth = lambda: torch.nn.functional.interpolate(torch.randn(1, 3, 32, 32, generator=g), size=(256, 256), mode="bicubic", align_corners=False).mul(0.6).clamp(-1, 1)
+    x0, ref_img = smooth(), smooth()
+    # the reference classes without their file-reading constructors, same attributes (arcface_model.py:16-39, 76-90)
+    idloss = am.IDLoss.__new__(am.IDLoss)
+    torch.nn.Module.__init__(idloss)
+    idloss.facenet = irse.Backbone(input_size=112, num_layers=50, drop_ratio=0.6, mode="ir_se")
+    idloss.facenet.load_state_dict(reward_nets._seed_init(reward_nets.IRSE50(), 3).state_dict())
+    idloss.facenet.eval().requires_grad_(False)
+    idloss.pool, idloss.face_pool, idloss.ref = torch.nn.AdaptiveAvgPool2d((256, 256)), torch.nn.AdaptiveAvgPool2d((112, 112)), ref_img
+    lpipsloss = am.LPIPS_Loss.__new__(am.LPIPS_Loss)
+    torch.nn.Module.__init__(lpipsloss)
+    lpipsloss.lpips_loss = lpips.LPIPS(net="vgg")
+    vsd = reward_nets._seed_init(reward_nets.LPIPSVGG16(), 4).state_dict()
+    for k in vsd:                                   # random `lin` heads are tiny (0..0.02): scaled so that the LPIPS move is visible next to the identity move
+        if k.startswith("lins."):
+            vsd[k] = vsd[k] * lin_gain
+    lpipsloss.lpips_loss.net.load_state_dict(vsd)
+    lpipsloss.lpips_loss.eval().requires_grad_(False)
+    lpipsloss.src = x0.clone()
+    with torch.no_grad():
+        _, zs, xts, _ = inv.inversion_forward_process_sde(model, x0, betas, seq, etas=1.0, num_inference_steps=T, device="cpu")
+    kw = dict(eta=1.0, zs=zs[:T], weight_edit_face=weight, optimization_steps=K, after_skip_steps=T, num_inference_steps=T, soft_face_mask=None)
+    edited = he.h_Edit_R(model, lpipsloss, idloss, xts[T].clone(), betas, seq, **kw)
+    only_id = he.h_Edit_R(model, None, idloss, xts[T].clone(), betas, seq, **kw)
+    recon = he.h_Edit_R(model, None, None, xts[T].clone(), betas, seq, **kw)
+    out = {"meta": dict(name=name, mode="face_full", T=T, K=K, weight_edit_face=weight, seq=[int(v) for v in seq],
+                        unet=dict(ch=cfg.ch, ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks, attn_resolutions=list(cfg.attn_resolutions),
+                                  image_size=cfg.image_size),
+                        rewards="reference IDLoss around Backbone(112, 50, 'ir_se') with reward_nets._seed_init(IRSE50(), 3) weights; reference LPIPS_Loss "
+                                "around tests/refshim/lpips.LPIPS('vgg') with reward_nets._seed_init(LPIPSVGG16(), 4) weights, lin heads x lin_gain",
+                        lin_gain=lin_gain, irse_seed=3, vgg_seed=4,
+                        generator="tests/make_golden.py --config face_full", torch=torch.__version__),
+           "x0": x0, "ref_img": ref_img, "zs": zs[:T].clone(), "xT": xts[T].clone(), "betas": betas,
+           "edited": edited.detach().clone(), "edited_id_only": only_id.detach().clone(), "no_reward": recon.detach().clone()}
+    path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
+    torch.save(out, path)
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    print(name, "->", path, "| both rewards moved the result by %.4f (rel), identity alone by %.4f | no-reward run returns x0 to %.2e" %
+          (rel(edited, recon), rel(only_id, recon), (recon - x0).abs().max().item()), flush=True)
+
+
 def run_face(name="tiny_face_k2", T=5, K=2, weight=50.0):
     """The UNMODIFIED face-swapping sampler (face-swapping/inversion/h_edit_R.py:7 `h_Edit_R`) and inversion
     (inversion/sde_inversion.py:54) on the reference's own `Model` class (diffusion/diffusion.py:193) in a small configuration carrying
@@ -418,7 +486,7 @@ def run_face(name="tiny_face_k2", T=5, K=2, weight=50.0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["style_sd15", "baselines", "tiny", "sd15", "sd15_config1", "sd15_config2", "sd15_config2_T50_refine_blend_th09", "tiny_refine_blend_th09", "masa", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
+    ap.add_argument("--config", default="tiny", choices=["face_full", "style_sd15", "baselines", "tiny", "sd15", "sd15_config1", "sd15_config2", "sd15_config2_T50_refine_blend_th09", "tiny_refine_blend_th09", "masa", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
     args = ap.parse_args()
     if args.config == "style":
         run_style()
@@ -428,6 +496,9 @@ def main():
         return
     if args.config == "face":
         run_face()
+        return
+    if args.config == "face_full":
+        run_face_full()
         return
     ref = load_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)

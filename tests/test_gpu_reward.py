@@ -164,3 +164,51 @@ def test_face_h_edit_R_native_rewards_match_autograd_plugins():
     moved = rel_err(outs["0"], none)[0]
     print(f"h_Edit_R native vs autograd rewards: rel {r:.3e} max {m:.3e} | the rewards move the image by {moved:.3e}")
     assert moved > 1e-3 and r < 0.1 * moved + 2e-3
+
+
+def test_face_h_edit_R_against_reference_sampler_with_reference_reward_classes():
+    """Golden `face256_irse50_lpips_k2` = the UNMODIFIED reference `h_Edit_R` driving the reference's own `IDLoss` (around its `Backbone(112,
+    50, 'ir_se')`) and `LPIPS_Loss` classes on CPU (tests/make_golden.py --config face_full; seeded weights).  Here: the native loop, the
+    native DDPM UNet and the NATIVE reward networks with their image gradients, fed the same weights through reward objects of the same
+    layout.  The rewards move the result by 50 %; the bound is the loop tolerance plus the calibrated gradient deviation (3-7 %) of that move."""
+    import numpy as np
+    from oracle.face_unet import FaceUNet, FaceUNetConfig
+    from oracle_run import load_golden
+    if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "face256_irse50_lpips_k2.pt")):
+        pytest.skip("golden missing")
+    _fp32()
+    g = load_golden("face256_irse50_lpips_k2")
+    meta, u = g["meta"], g["meta"]["unet"]
+    cfg = FaceUNetConfig(ch=u["ch"], ch_mult=tuple(u["ch_mult"]), image_size=u["image_size"], attn_resolutions=tuple(u["attn_resolutions"]))
+    model = FaceUNet(cfg).cuda()
+    T, K = meta["T"], meta["K"]
+    idl = reward_nets.SyntheticIDLoss(g["ref_img"], seed=meta["irse_seed"]).cuda()
+    lpl = reward_nets.SyntheticLPIPSLoss(g["x0"], seed=meta["vgg_seed"]).cuda()
+    with torch.no_grad():
+        for p in lpl.lpips_loss.lins:
+            p.mul_(meta["lin_gain"])
+    kw = dict(eta=1.0, zs=g["zs"].cuda(), weight_edit_face=meta["weight_edit_face"], optimization_steps=K, after_skip_steps=T, num_inference_steps=T)
+    betas, seq = g["betas"].cuda(), np.asarray(meta["seq"])
+    ed = hedit_b200.face.h_Edit_R(model, lpl, idl, g["xT"].cuda(), betas, seq, **kw)
+    assert hedit_b200.face.get_face_engine(model).last_stats["native_rewards"] == (True, True)
+    ed_id = hedit_b200.face.h_Edit_R(model, None, idl, g["xT"].cuda(), betas, seq, **kw)
+    none = hedit_b200.face.h_Edit_R(model, None, None, g["xT"].cuda(), betas, seq, **kw)
+    # the same loop with the reward modules differentiated by torch autograd (fp32): separates the reward networks' 16-bit operands from
+    # the denoiser's in the deviation from the golden
+    os.environ["HEDIT_NATIVE_REWARD"] = "0"
+    try:
+        ed_ag = hedit_b200.face.h_Edit_R(model, lpl, idl, g["xT"].cuda(), betas, seq, **kw)
+    finally:
+        os.environ.pop("HEDIT_NATIVE_REWARD", None)
+    r_ag, _ = rel_err(ed_ag.cpu(), g["edited"])
+    r_ed, m_ed = rel_err(ed.cpu(), g["edited"])
+    r_id, _ = rel_err(ed_id.cpu(), g["edited_id_only"])
+    r_no, _ = rel_err(none.cpu(), g["no_reward"])
+    moved = rel_err(g["edited"], g["no_reward"])[0]
+    lp_effect = rel_err(g["edited"], g["edited_id_only"])[0]
+    print(f"face256_irse50_lpips_k2: edited rel {r_ed:.3e} max {m_ed:.3e} (fp32 autograd rewards on the same native loop: {r_ag:.3e}) | identity only rel {r_id:.3e} | no reward rel {r_no:.3e} | "
+          f"rewards move the result by {moved:.3e}, LPIPS alone by {lp_effect:.3e}")
+    assert r_no < 4e-2
+    assert r_ed < 4e-2 + 0.07 * moved and r_id < 4e-2 + 0.07 * moved
+    assert r_ed < 1.25 * r_ag + 5e-3          # the native reward networks add next to nothing to what the denoiser's 16-bit operands already cost
+    assert lp_effect > 2 * r_ed or lp_effect > 1e-2          # the LPIPS term is visible in the golden
