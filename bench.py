@@ -429,9 +429,13 @@ def run_gpu(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE JSON line: for the duration of the run file descriptor 1 points at stderr, so whatever a library prints
+    # there (NCCL's "NCCL version ..." banner and NCCL_DEBUG output, warnings of native code) lands on stderr; the JSON line is written
+    # to the saved descriptor at the end
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     wl = WORKLOADS[args.config](args, rank, dev)
     B, T = wl.B, wl.T
@@ -543,9 +547,13 @@ def run_gpu(args, rank, world, local_rank):
             line["run"]["reward_networks"] = wl.reward_kind
         if prof and args.profile:
             line["kernel_breakdown_ms_per_forward"] = prof
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(out_fd, 1)
+    os.close(out_fd)
 
 
 def main():
