@@ -48,6 +48,10 @@ VARIANTS = {
     "tiny_pnpinv_p2p": (UNetConfig.tiny(sample_size=64), 6, 1, "pnpinv_p2p"),
     "tiny_ef": (UNetConfig.tiny(sample_size=64), 6, 1, "ef"),
     "tiny_ef_masactrl": (UNetConfig.tiny(sample_size=64), 6, 1, "ef_masactrl"),
+    # full SD-1.5 geometry, T = 10, for the samplers that had tiny-width goldens only
+    "sd15_pnp_T10": (UNetConfig.sd15(), 10, 1, "pnp"),
+    "sd15_p2p_explicit_T10": (UNetConfig.sd15(), 10, 1, "p2p_explicit"),
+    "sd15_ef_p2p_T10": (UNetConfig.sd15(), 10, 1, "ef_p2p"),
     # Plug-and-Play baselines (inversion/pnp_baselines.py:317,244)
     "tiny_ef_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "ef_pnp"),
     "tiny_np_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "np_pnp"),
@@ -370,7 +374,7 @@ def run_style(name="tiny_style_mos2", T=4, K=2, weight=0.5, full=False):
           "| style term moved the edit by %.4f (rel)" % ((edited - edited_ns).norm() / edited_ns.norm()).item(), flush=True)
 
 
-def run_face_full(name="face256_irse50_lpips_k2", T=4, K=2, weight=1500.0, lin_gain=100.0):
+def run_face_full(name="face256_irse50_lpips_k2", T=4, K=2, weight=1500.0, lin_gain=100.0, celebahq=False):
     """The UNMODIFIED face-swapping sampler `h_Edit_R` (face-swapping/inversion/h_edit_R.py:7) driving the reference's OWN reward classes:
     `IDLoss` (arcface/arcface_model.py:12) around the reference `Backbone(112, 50, 'ir_se')` and `LPIPS_Loss` (:72) around `lpips.LPIPS`
     (tests/refshim/lpips: the package itself is not available offline), both with seeded random weights and seeded images instead of
@@ -390,7 +394,8 @@ def run_face_full(name="face256_irse50_lpips_k2", T=4, K=2, weight=1500.0, lin_g
     irse = importlib.import_module("arcface.facial_recognition.model_irse")
     import lpips
     torch.set_num_threads(os.cpu_count())
-    cfg = FaceUNetConfig(ch=64, ch_mult=(1, 1, 2, 2), image_size=256, attn_resolutions=(32,))
+    # celebahq = True: the denoiser at BASELINE.json configs[4] geometry (ch 128 x (1, 1, 2, 2, 4, 4), attention at 16 x 16)
+    cfg = FaceUNetConfig() if celebahq else FaceUNetConfig(ch=64, ch_mult=(1, 1, 2, 2), image_size=256, attn_resolutions=(32,))
     model = ref_model.Model(cfg.as_reference_dict())
     model.load_state_dict(FaceUNet(cfg).state_dict())
     model.eval()
@@ -486,8 +491,17 @@ def run_face(name="tiny_face_k2", T=5, K=2, weight=50.0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="tiny", choices=["face_full", "style_sd15", "baselines", "tiny", "sd15", "sd15_config1", "sd15_config2", "sd15_config2_T50_refine_blend_th09", "tiny_refine_blend_th09", "masa", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
+    ap.add_argument("--config", default="tiny", choices=["face_full", "face_full_celebahq", "style_sd15", "baselines", "tiny", "sd15", "sd15_config1", "sd15_config2", "sd15_config2_T50_refine_blend_th09", "tiny_refine_blend_th09", "masa", "small32", "variants", "inversion", "pnp", "style", "face", "all"])
+    ap.add_argument("--only", default=None, help="generate just this VARIANTS entry")
     args = ap.parse_args()
+    if args.only:
+        ref = load_reference()
+        cfg, T, K, mode = VARIANTS[args.only]
+        out = run_variant(ref, args.only, cfg, T, K, mode)
+        path = os.path.join(ROOT, "tests", "golden", f"{args.only}.pt")
+        torch.save(out, path)
+        print(args.only, "->", path, "|edited| %.4f" % out["edited"].abs().mean().item(), flush=True)
+        return
     if args.config == "style":
         run_style()
         return
@@ -499,6 +513,9 @@ def main():
         return
     if args.config == "face_full":
         run_face_full()
+        return
+    if args.config == "face_full_celebahq":
+        run_face_full(name="celebahq_config5_T5_irse50_lpips_k3", T=5, K=3, celebahq=True)
         return
     ref = load_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)

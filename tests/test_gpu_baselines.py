@@ -30,7 +30,7 @@ def _setup(name):
     return g, meta, model
 
 
-@pytest.mark.parametrize("name", ["tiny_ef_p2p", "tiny_pnpinv_p2p"])
+@pytest.mark.parametrize("name", ["tiny_ef_p2p", "tiny_pnpinv_p2p", "sd15_ef_p2p_T10"])
 def test_ef_and_pnp_inversion_with_p2p(name):
     g, meta, model = _setup(name)
     bw = meta["blend_words"]

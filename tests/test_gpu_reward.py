@@ -166,18 +166,19 @@ def test_face_h_edit_R_native_rewards_match_autograd_plugins():
     assert moved > 1e-3 and r < 0.1 * moved + 2e-3
 
 
-def test_face_h_edit_R_against_reference_sampler_with_reference_reward_classes():
+@pytest.mark.parametrize("name", ["face256_irse50_lpips_k2", "celebahq_config5_T5_irse50_lpips_k3"])
+def test_face_h_edit_R_against_reference_sampler_with_reference_reward_classes(name):
     """Golden `face256_irse50_lpips_k2` = the UNMODIFIED reference `h_Edit_R` driving the reference's own `IDLoss` (around its `Backbone(112,
-    50, 'ir_se')`) and `LPIPS_Loss` classes on CPU (tests/make_golden.py --config face_full; seeded weights).  Here: the native loop, the
+    50, 'ir_se')`) and `LPIPS_Loss` classes on CPU (tests/make_golden.py --config face_full; seeded weights); `celebahq_config5_T5_irse50_lpips_k3` is the same at BASELINE.json configs[4] geometry (CelebA-HQ DDPM UNet, K = 3).  Here: the native loop, the
     native DDPM UNet and the NATIVE reward networks with their image gradients, fed the same weights through reward objects of the same
     layout.  The rewards move the result by 50 %; the bound is the loop tolerance plus the calibrated gradient deviation (3-7 %) of that move."""
     import numpy as np
     from oracle.face_unet import FaceUNet, FaceUNetConfig
     from oracle_run import load_golden
-    if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "face256_irse50_lpips_k2.pt")):
+    if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", name + ".pt")):
         pytest.skip("golden missing")
     _fp32()
-    g = load_golden("face256_irse50_lpips_k2")
+    g = load_golden(name)
     meta, u = g["meta"], g["meta"]["unet"]
     cfg = FaceUNetConfig(ch=u["ch"], ch_mult=tuple(u["ch_mult"]), image_size=u["image_size"], attn_resolutions=tuple(u["attn_resolutions"]))
     model = FaceUNet(cfg).cuda()
@@ -206,7 +207,7 @@ def test_face_h_edit_R_against_reference_sampler_with_reference_reward_classes()
     r_no, _ = rel_err(none.cpu(), g["no_reward"])
     moved = rel_err(g["edited"], g["no_reward"])[0]
     lp_effect = rel_err(g["edited"], g["edited_id_only"])[0]
-    print(f"face256_irse50_lpips_k2: edited rel {r_ed:.3e} max {m_ed:.3e} (fp32 autograd rewards on the same native loop: {r_ag:.3e}) | identity only rel {r_id:.3e} | no reward rel {r_no:.3e} | "
+    print(f"{name}: edited rel {r_ed:.3e} max {m_ed:.3e} (fp32 autograd rewards on the same native loop: {r_ag:.3e}) | identity only rel {r_id:.3e} | no reward rel {r_no:.3e} | "
           f"rewards move the result by {moved:.3e}, LPIPS alone by {lp_effect:.3e}")
     assert r_no < 4e-2
     assert r_ed < 4e-2 + 0.07 * moved and r_id < 4e-2 + 0.07 * moved

@@ -277,10 +277,11 @@ def _run_variant(name, eng_cache={}):
     g = load_golden(name)
     meta = g["meta"]
     cfg = cfg_from_meta(meta)
-    if "m" not in eng_cache:
+    ckey = (tuple(cfg.block_out_channels), cfg.sample_size)
+    if ckey not in eng_cache:
         model = OraclePipeline(cfg, seed=0)
-        eng_cache["m"] = (model, UNetEngine.from_unet(model.unet, max_samples=5, max_contexts=4))
-    model, eng = eng_cache["m"]
+        eng_cache[ckey] = (model, UNetEngine.from_unet(model.unet, max_samples=5, max_contexts=4))
+    model, eng = eng_cache[ckey]
     T, K, mode = meta["T"], meta["K"], meta["mode"]
     model.scheduler.set_timesteps(T)
     ts, coef = hedit_b200.step_tables(model.scheduler, T, meta["eta"], False)
@@ -331,7 +332,9 @@ def _run_variant(name, eng_cache={}):
         # the injection matters: with it switched off the edit differs from the golden by far more than the tolerance
         off = (0, [0] * T, [0] * T)
         ed_off, _ = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, K, schedule=1, mos_pull=False, pnp=off)
-        assert rel_err(ed_off.cpu(), g["edited"])[0] > 5 * TOL_LOOP
+        r_off = rel_err(ed_off.cpu(), g["edited"])[0]
+        print(f"  {name}: injection off -> rel {r_off:.3e} (with injection {r0:.3e})")
+        assert r_off > max(2.5 * TOL_LOOP, 5 * r0)
         ed, rc = eng.edit(xT, zs, ctx, ts, coef, cfgs, None, 0.0, K, schedule=1, mos_pull=False, pnp=pnp)
     r_ed, m_ed = rel_err(ed.cpu(), g["edited"])
     r_rc, m_rc = rel_err(rc.cpu(), g["recon"])
@@ -342,7 +345,7 @@ def _run_variant(name, eng_cache={}):
 
 
 @pytest.mark.parametrize("name", ["tiny_p2p_explicit", "tiny_R_implicit_mos2", "tiny_R_explicit", "tiny_masactrl_mos2", "tiny_masactrl_mos2_stop", "tiny_masactrl_lists",
-                                  "tiny_pnp", "tiny_R_implicit_skip2"])
+                                  "tiny_pnp", "tiny_R_implicit_skip2", "sd15_pnp_T10", "sd15_p2p_explicit_T10"])
 def test_sampler_variants(name):
     if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", name + ".pt")):
         pytest.skip("golden missing")
