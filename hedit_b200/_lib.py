@@ -102,6 +102,7 @@ SYMBOLS = {
     "hedit_engine_set_graph_replay": (_I, [_P, _I]),
     "hedit_engine_set_prefix_dedup": (_I, [_P, _I]),
     "hedit_engine_set_splitk": (_I, [_P, _I]),
+    "hedit_abi_sizeof": (_I, [C.c_char_p]),
     "hedit_unet_forward": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "hedit_unet_forward_indexed": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _P]),
     "hedit_unet_forward_compat": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P]),

@@ -691,6 +691,16 @@ int hedit_edit_p2p(hedit_engine* h, hedit_edit_args* args, void* stream) {
   return 0;
 }
 
+int hedit_abi_sizeof(const char* name) {
+  if (!name) return -1;
+  const std::string n(name);
+#define HEDIT_SZ(T) if (n == #T) return int(sizeof(T));
+  HEDIT_SZ(hedit_edit_args) HEDIT_SZ(hedit_step_coef) HEDIT_SZ(hedit_unet_config) HEDIT_SZ(hedit_vae_config) HEDIT_SZ(hedit_clip_config)
+  HEDIT_SZ(hedit_text_config) HEDIT_SZ(hedit_face_config) HEDIT_SZ(hedit_face_step_coef) HEDIT_SZ(hedit_face_args)
+#undef HEDIT_SZ
+  return -1;
+}
+
 // ------------------------------------------------------------------------------------------------ single operators
 static int pick_bn_op(int M, int N) {
   static const int force = getenv("HEDIT_GEMM_BN") ? atoi(getenv("HEDIT_GEMM_BN")) : 0;     // tuning switch

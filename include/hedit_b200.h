@@ -135,6 +135,9 @@ typedef struct hedit_edit_args {
 } hedit_edit_args;
 
 const char* hedit_last_error(void);
+/* sizeof() of the argument / configuration structs of this header by name ("hedit_edit_args", "hedit_face_args", "hedit_unet_config",
+ * ...), -1 for an unknown name: lets a binding (ctypes, cgo, JNI) verify its struct layout against the library it loaded. */
+int hedit_abi_sizeof(const char* struct_name);
 int hedit_device_count(void);
 
 /* engine lifetime: replaces copy.deepcopy(pipeline).to(device) per image (text-guided/main_p2p.py:119) with

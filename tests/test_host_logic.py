@@ -333,3 +333,17 @@ def test_edit_controller_implements_the_reference_protocol_and_lazy_store():
     lazy = LazyAttentionStore(lambda: calls.append(1) or {"down_cross": [torch.ones(1)]})
     assert calls == []
     assert len(lazy["down_cross"]) == 1 and "down_cross" in lazy and len(lazy) == 1 and calls == [1]
+
+
+def test_ctypes_struct_layouts_match_the_library():
+    """The ctypes mirrors of the C-ABI structs (hedit_b200/_lib.py) have exactly the sizes the loaded library was compiled with
+    (`hedit_abi_sizeof`): a field added on one side only would shift every later field of hedit_edit_args silently."""
+    import ctypes as C
+    from hedit_b200 import _lib
+    lib = _lib.load()
+    pairs = {"hedit_edit_args": _lib.EditArgsC, "hedit_step_coef": _lib.StepCoefC, "hedit_unet_config": _lib.UNetConfigC,
+             "hedit_vae_config": _lib.VaeConfigC, "hedit_clip_config": _lib.ClipConfigC, "hedit_text_config": _lib.TextConfigC,
+             "hedit_face_config": _lib.FaceConfigC, "hedit_face_step_coef": _lib.FaceStepCoefC, "hedit_face_args": _lib.FaceArgsC}
+    for name, cls in pairs.items():
+        assert lib.hedit_abi_sizeof(name.encode()) == C.sizeof(cls), name
+    assert lib.hedit_abi_sizeof(b"no_such_struct") == -1
