@@ -347,3 +347,52 @@ def test_ctypes_struct_layouts_match_the_library():
     for name, cls in pairs.items():
         assert lib.hedit_abi_sizeof(name.encode()) == C.sizeof(cls), name
     assert lib.hedit_abi_sizeof(b"no_such_struct") == -1
+
+
+def test_reward_module_recognition_and_name_mapping():
+    """Host side of the native reward networks (hedit_b200/reward.py): the IR-SE50 state_dict test, and the LPIPS tensor-name mapping for both
+    key layouts (the lpips package's `net.slice3.12.weight` / `lin2.model.1.weight` / `scaling_layer.shift` and reward_nets' own)."""
+    import torch
+    from hedit_b200 import reward, reward_nets
+    irse = reward_nets.IRSE50()
+    assert reward.ArcFaceEngine.is_irse50_state_dict(irse.state_dict())
+    sd = dict(irse.state_dict()); sd.pop("body.23.res_layer.5.fc2.weight")
+    assert not reward.ArcFaceEngine.is_irse50_state_dict(sd)                         # another depth / mode: not IR-SE50
+    net = reward_nets._seed_init(reward_nets.LPIPSVGG16(), 1)
+    ours = reward.lpips_native_tensors(net.state_dict())
+    want = {f"conv{i}.{k}" for i in range(13) for k in ("weight", "bias")} | {f"lin{k}.weight" for k in range(5)} | {"shift", "scale"}
+    assert set(ours) == want
+    slices = {0: 1, 2: 1, 5: 2, 7: 2, 10: 3, 12: 3, 14: 3, 17: 4, 19: 4, 21: 4, 24: 5, 26: 5, 28: 5}
+    pkg = {}
+    for k, v in net.state_dict().items():
+        if k.startswith("features."):
+            idx = int(k.split(".")[1])
+            pkg[f"net.slice{slices[idx]}.{idx}.{k.split('.')[2]}"] = v
+        elif k.startswith("lins."):
+            pkg[f"lin{k.split('.')[1]}.model.1.weight"] = v
+            pkg[f"lins.{k.split('.')[1]}.model.1.weight"] = v
+        else:
+            pkg[f"scaling_layer.{k}"] = v
+    theirs = reward.lpips_native_tensors(pkg)
+    assert set(theirs) == want and all(torch.equal(theirs[k].reshape(-1), ours[k].reshape(-1)) for k in want)
+    # seeded construction is reproducible, incl. the `lin` heads (drawn from the global RNG by the constructor)
+    again = reward_nets._seed_init(reward_nets.LPIPSVGG16(), 1)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), again.state_dict().values()))
+    # a reward object whose loss method is overridden is NOT taken over by the native path (it keeps the autograd plug-in route)
+    class MyID(reward_nets.SyntheticIDLoss):
+        def get_cosine_loss(self, image):
+            return super().get_cosine_loss(image) * 2
+    assert reward._stock_class(MyID.__new__(MyID), "SyntheticIDLoss") is reward_nets.SyntheticIDLoss
+
+
+def test_pnp_flags_at_current_timestep():
+    """Plug-and-Play baselines inject at the CURRENT timestep (pnp_baselines.py:367), h_Edit_PnP_implicit at the previous one."""
+    import types
+    import hedit_b200
+    model = types.SimpleNamespace(scheduler=types.SimpleNamespace(timesteps=torch.tensor([801, 601, 401, 201, 1])))
+    hedit_b200.register_attention_control_efficient(model, [801, 601])
+    hedit_b200.register_conv_control_efficient(model, [801, 601, 401])
+    from hedit_b200.samplers import pnp_step_flags_at_t
+    assert pnp_step_flags_at_t(model, 5) == ([1, 1, 0, 0, 0], [1, 1, 1, 0, 0])
+    assert hedit_b200.pnp_step_flags(model, 5) == ([1, 0, 0, 0, 0], [1, 1, 0, 0, 0])
+    assert pnp_step_flags_at_t(model, 3) == ([0, 0, 0], [1, 0, 0])
