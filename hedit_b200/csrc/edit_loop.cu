@@ -123,7 +123,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
     return -1;
   }
   if (masa && !a.masa_step_on) { E.err_ = "masa needs masa_step_on[steps * opt_steps]"; return -1; }
-  if (baseline && (a.guidance || a.pre_step || a.xt_is_pair)) { E.err_ = "variant 2 (baseline samplers) runs without reward guidance, pre_step or xt_is_pair"; return -1; }
+  if (baseline && (a.guidance || a.pre_step)) { E.err_ = "variant 2 (baseline samplers) runs without reward guidance or pre_step"; return -1; }
   if (a.guidance && (a.explicit_form || !a.x0_coef || !a.guid_x0 || !a.guid_grad)) {
     E.err_ = "reward guidance runs in the implicit form and needs x0_coef, guid_x0 and guid_grad";
     return -1;

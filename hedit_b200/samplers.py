@@ -442,3 +442,65 @@ def negative_prompt_pnp(model, xT, etas=0, prompts="", cfg_scales=None, prog_bar
     replaced by the SOURCE prompt's, both rows use the target guidance scale (:290-291) and step deterministically (eta = 0)."""
     assert len(prompts) >= 2 and etas == 0, "PnP requires source and target prompts, with eta is set to 0"      # reference assert (:263)
     return _baseline(model, xT, 0, prompts, [cfg_scales[1], cfg_scales[1]], zs, None, False, pnp=_pnp_tuple(model, zs.shape[0]), null_prompt=prompts[0])
+
+
+def nmg_p2p(model, xT, xT_ori, etas: float = 0.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None,
+            guidance_noise_map: float = 10.0, grad_scale: float = 5e+3):
+    """Reference signature (inversion/p2p_baselines.py:195): Noise Map Guidance with P2P.  HYBRID: per timestep the reference takes
+    `torch.autograd.grad` of an L1 loss THROUGH one unconditional UNet forward (w.r.t. the latent, :218-228); there is no native UNet
+    backward yet, so that single differentiable forward runs on the CALLER's own `model.unet` torch module under autograd,
+    exactly as the reference does, and everything else -- the attention-controlled 4-sample launch, both reverse steps, LocalBlend -- is one
+    single-step call of the native loop (variant 2, controller state carried across calls).  Returns (edited, reconstructed)."""
+    import dataclasses
+    import torch.nn.functional as F
+    assert len(prompts) >= 2 and etas == 0, "P2P requires source and target prompts, with eta is set to 0 for NMG"      # reference assert (:216)
+    from .compat import controller_kind
+    kind = controller_kind(controller)
+    if kind == "custom":
+        raise NotImplementedError("nmg_p2p runs stock P2P controllers (or none) on the fused path")
+    steps = zs.shape[0]
+    eng = get_engine(model, max_samples=5, device=_device_index(xT, None) if xT.is_cuda else None)
+    eng.set_splitk(True)
+    dev = torch.device("cuda", eng.device)
+    ctx = encode_prompts(model, ["", prompts[0], prompts[1]]).float().to(dev)
+    ts, coef = step_tables(model.scheduler, steps, 0.0, False)          # reverse_step(..., eta = 0.0, variance_noise = None) everywhere (:226,231,246-247)
+    plan = compile_edit_plan([controller], steps) if kind == "stock" else None
+    blend_state = eng.new_blend_state(1) if plan is not None and plan.has_blend.any() else None
+    unet = model.unet
+    udev = next(unet.parameters()).device
+    uncond = encode_text(model, [""]).to(udev)
+    ac = model.scheduler.alphas_cumprod
+    w_tar = float(cfg_scales[1])                                          # both rows use the TARGET scale (:243-244)
+    x = xT.reshape(1, *xT.shape[-3:]).to(dev, torch.float32)
+    xt = torch.stack([x, x], dim=1).contiguous()                          # (1, 2, C, h, w): rows (recon, target)
+    zero = torch.zeros_like(x)[:, None]
+
+    def reverse0(eps, sample, c):                                         # reverse_step with eta = 0 from the step's scalar row
+        x0 = (sample - c[0] * eps) / c[1]
+        return c[2] * x0 + c[3] * eps
+
+    for i in range(steps):
+        t = int(ts[i])
+        c = [float(v) for v in coef[i]]
+        xt_ori = xT_ori[len(xT_ori) - i - 2].reshape(1, *xT.shape[-3:]).to(udev, torch.float32)
+        with torch.enable_grad():
+            x_in = xt[:, 0].detach().to(udev).requires_grad_(True)
+            try:
+                eps_u = unet(x_in, t, encoder_hidden_states=uncond, cross_attention_kwargs={"use_controller": False}).sample
+            except TypeError:                                             # a UNet with stock attention processors takes no P2P keyword
+                eps_u = unet(x_in, t, encoder_hidden_states=uncond).sample
+            loss = F.l1_loss(reverse0(eps_u, x_in, c), xt_ori)
+            grad = -torch.autograd.grad(loss, x_in)[0]
+        eps_u = eps_u.detach()
+        eps_c = eps_u - (1 - ac[t]).sqrt().to(udev) * grad * grad_scale
+        eps = eps_u + guidance_noise_map * (eps_c - eps_u)
+        xt[:, 0] = reverse0(eps, xt[:, 0].to(udev), c).to(dev)
+        p = None if plan is None else dataclasses.replace(plan, steps=1, c_base=plan.c_base[i:i + 2], c_tar=plan.c_tar[i:i + 2])
+        ed, rc = eng.edit(xt.contiguous(), zero, ctx, ts[i:i + 2], coef[i:i + 1], [w_tar, w_tar, w_tar], p, 0.0, 1, False, 1, variant=2,
+                          xt_is_pair=True, ctrl_step0=i, blend_state=blend_state, mos_pull=False)
+        xt = torch.stack([rc, ed], dim=1)
+    if kind == "stock":
+        controller.cur_step = getattr(controller, "cur_step", 0) + steps
+        if getattr(controller, "local_blend", None) is not None:
+            controller.local_blend.counter += steps
+    return xt[:, 1].to(xT.device), xt[:, 0].to(xT.device)

@@ -54,6 +54,8 @@ VARIANTS = {
     "sd15_ef_p2p_T10": (UNetConfig.sd15(), 10, 1, "ef_p2p"),
     # Plug-and-Play baselines (inversion/pnp_baselines.py:317,244)
     "tiny_ef_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "ef_pnp"),
+    # Noise Map Guidance with P2P (p2p_baselines.py:195): differentiates through one UNet forward per step
+    "tiny_nmg_p2p": (UNetConfig.tiny(sample_size=64), 6, 1, "nmg_p2p"),
     "tiny_np_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "np_pnp"),
 }
 # MutualSelfAttentionControl arguments per masactrl variant (default: start_step 2, start_layer 10, total_steps T*K)
@@ -229,6 +231,17 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
         pu.register_conv_control_efficient(model, conv_ts)
         edited, recon = ph.h_Edit_PnP_implicit(model, optimization_steps=K, **kw)
         meta_extra = dict(pnp_qk_timesteps=[int(t) for t in qk_ts], pnp_conv_timesteps=[int(t) for t in conv_ts])
+    elif mode == "nmg_p2p":
+        pb = importlib.import_module("inversion.p2p_baselines")
+        controller = ref.ptp_controller_utils.make_controller(
+            prompts=prompts, is_replace_controller=False, cross_replace_steps=xa, self_replace_steps=sa,
+            blend_word=((BLEND[0],), (BLEND[1],)), equilizer_params={"words": (BLEND[1],), "values": (2.0,)}, num_steps=T,
+            tokenizer=model.tokenizer, device=model.device)
+        ref.ptp_utils.register_attention_control(model, controller)
+        edited, recon = pb.nmg_p2p(model, xT=wts[T], xT_ori=wts[:T + 1], etas=0.0, prompts=prompts, cfg_scales=[1.0, 7.5], prog_bar=False,
+                                   zs=zs[:T], controller=controller, guidance_noise_map=10.0, grad_scale=5e+3)
+        meta_extra = dict(baseline_cfg_scales=[1.0, 7.5], is_ddim_inversion=False, guidance_noise_map=10.0, grad_scale=5e+3)
+        nmg_extra = {"xT_ori": torch.stack([w for w in wts[:T + 1]]).clone()}
     elif mode in ("ef_pnp", "np_pnp"):
         pu = importlib.import_module("plug_n_play.pnp_utils")
         pnb = importlib.import_module("inversion.pnp_baselines")
@@ -272,8 +285,9 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
         raise ValueError(mode)
     enc = ref.inversion_utils.encode_text
     return {
+        **(nmg_extra if mode == "nmg_p2p" else {}),
         "meta": dict(name=name, mode=mode, T=T, K=K, xa=xa, sa=sa, prompts=prompts, blend_words=BLEND, cfg_scales=[1.0, 5.0, 7.5], eta=1.0,
-                     weight_reconstruction=0.1, is_replace=False, blend=(mode in ("p2p_explicit", "ef_p2p", "pnpinv_p2p")),
+                     weight_reconstruction=0.1, is_replace=False, blend=(mode in ("p2p_explicit", "ef_p2p", "pnpinv_p2p", "nmg_p2p")),
                      unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
                                cross_attention_dim=cfg.cross_attention_dim, heads=cfg.attention_head_dim),
                      weights="oracle.sd_unet.seeded_init_(seed=0)", generator="tests/make_golden.py", torch=torch.__version__, **meta_extra),

@@ -97,3 +97,21 @@ def test_plug_and_play_baselines(name):
     off = rel_err(ed_off.cpu(), g["edited"])[0]
     print(f"{name}: edited rel {r_ed:.3e} max {m_ed:.3e} | recon rel {r_rc:.3e} | injection off: {off:.3e}")
     assert r_ed < TOL_LOOP and r_rc < TOL_LOOP and off > 3 * r_ed
+
+
+def test_nmg_p2p_hybrid():
+    """nmg_p2p (inversion/p2p_baselines.py:195).  The reference differentiates an L1 loss through one unconditional UNet forward per step;
+    hedit_b200.nmg_p2p runs that one differentiable forward on the caller's `model.unet` torch module (no native UNet backward yet) and
+    everything else -- the 4-sample P2P launch, both reverse steps, LocalBlend -- as single-step calls of the native loop."""
+    g, meta, model = _setup("tiny_nmg_p2p")
+    model.unet.cuda()
+    bw = meta["blend_words"]
+    controller = hedit_b200.make_controller(meta["prompts"], False, meta["xa"], meta["sa"], blend_word=((bw[0],), (bw[1],)),
+                                            equilizer_params={"words": (bw[1],), "values": (2.0,)}, num_steps=meta["T"], tokenizer=model.tokenizer)
+    ed, rc = hedit_b200.nmg_p2p(model, g["xT"].cuda(), g["xT_ori"].cuda(), etas=0.0, prompts=meta["prompts"], cfg_scales=meta["baseline_cfg_scales"],
+                                zs=g["zs"].cuda(), controller=controller, guidance_noise_map=meta["guidance_noise_map"], grad_scale=meta["grad_scale"])
+    r_ed, m_ed = rel_err(ed.cpu(), g["edited"])
+    r_rc, m_rc = rel_err(rc.cpu(), g["recon"])
+    print(f"tiny_nmg_p2p: edited rel {r_ed:.3e} max {m_ed:.3e} | recon rel {r_rc:.3e} max {m_rc:.3e}")
+    assert controller.cur_step == meta["T"]
+    assert r_ed < TOL_LOOP and r_rc < TOL_LOOP
