@@ -12,7 +12,7 @@ from .tokenizer import WordTokenizer  # noqa: F401
 from .engine import UNetEngine, unet_config_of  # noqa: F401
 from .samplers import (encode_prompts, invalidate_engines, HEditStepper, h_edit_step, MutualSelfAttentionControl, encode_text, get_engine, h_Edit_masactrl_explicit, h_Edit_masactrl_implicit, h_Edit_p2p_explicit,  # noqa: F401
                        h_Edit_p2p_implicit, h_Edit_R_explicit, h_Edit_R_implicit, h_edit_p2p_batch, regiter_attention_editor_diffusers,
-                       h_Edit_PnP_implicit, ef_or_pnp_inv_w_p2p, ef_wo_p2p, ef_or_pnp_inv_w_masactrl, ef_or_pnp_inv_w_pnp, negative_prompt_pnp, nmg_p2p, pnp_self_mask, pnp_step_flags, register_attention_control_efficient, register_conv_control_efficient, register_time)
+                       h_Edit_PnP_implicit, ef_or_pnp_inv_w_p2p, ef_wo_p2p, ef_or_pnp_inv_w_masactrl, ef_or_pnp_inv_w_pnp, negative_prompt_pnp, nmg_p2p, nmg_pnp, nulltext_pnp, pnp_self_mask, pnp_step_flags, register_attention_control_efficient, register_conv_control_efficient, register_time)
 
 from . import style  # noqa: F401,E402
 from .vae import VaeDecoderEngine, VaeEncoderEngine, vae_config_of  # noqa: F401,E402

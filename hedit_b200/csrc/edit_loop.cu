@@ -118,7 +118,7 @@ int run_edit(Engine& E, hedit_edit_args& a, cudaStream_t st) {
   const cudaMemcpyKind kIn = a.buffers_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const cudaMemcpyKind kOut = a.buffers_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (B < 1 || T < 1) { E.err_ = "bad batch/steps"; return -1; }
-  if (pnp && (a.explicit_form || (a.variant != 0 && a.variant != 2) || a.use_p2p || masa || !a.pnp_qk_on || !a.pnp_feat_on || a.xt_is_pair)) {
+  if (pnp && (a.explicit_form || (a.variant != 0 && a.variant != 2) || a.use_p2p || masa || !a.pnp_qk_on || !a.pnp_feat_on || (a.xt_is_pair && a.variant != 2))) {
     E.err_ = "Plug-and-Play runs the implicit form only (pnp_h_edit.py:33), without P2P / MasaCtrl, and needs both per-step flag arrays";
     return -1;
   }

@@ -444,63 +444,110 @@ def negative_prompt_pnp(model, xT, etas=0, prompts="", cfg_scales=None, prog_bar
     return _baseline(model, xT, 0, prompts, [cfg_scales[1], cfg_scales[1]], zs, None, False, pnp=_pnp_tuple(model, zs.shape[0]), null_prompt=prompts[0])
 
 
-def nmg_p2p(model, xT, xT_ori, etas: float = 0.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None,
-            guidance_noise_map: float = 10.0, grad_scale: float = 5e+3):
-    """Reference signature (inversion/p2p_baselines.py:195): Noise Map Guidance with P2P.  HYBRID: per timestep the reference takes
-    `torch.autograd.grad` of an L1 loss THROUGH one unconditional UNet forward (w.r.t. the latent, :218-228); there is no native UNet
-    backward yet, so that single differentiable forward runs on the CALLER's own `model.unet` torch module under autograd,
-    exactly as the reference does, and everything else -- the attention-controlled 4-sample launch, both reverse steps, LocalBlend -- is one
-    single-step call of the native loop (variant 2, controller state carried across calls).  Returns (edited, reconstructed)."""
+def _unet_sample(unet, x, t, emb):
+    """One forward of the CALLER's differentiable torch UNet (diffusers call convention)."""
+    try:
+        return unet(x, t, encoder_hidden_states=emb, cross_attention_kwargs={"use_controller": False}).sample
+    except TypeError:                                             # a UNet with stock attention processors takes no P2P keyword
+        return unet(x, t, encoder_hidden_states=emb).sample
+
+
+def _grad_guided(model, xT, xT_ori, prompts, cfg_scales, zs, controller, pnp_on, mode, guidance_noise_map=10.0, grad_scale=5e+3,
+                 optimization_steps=10, epsilon=1e-5):
+    """Shared body of the three reference samplers that differentiate THROUGH the UNet once (or a few times) per timestep
+    (p2p_baselines.py:195 nmg_p2p, pnp_baselines.py:32 nmg_pnp, :134 nulltext_pnp).  HYBRID: there is no native UNet backward yet
+    (DESIGN 10.1), so those differentiable forwards run on the caller's own `model.unet` torch module under autograd, exactly as the
+    reference does; everything else -- the attention-controlled / feature-injected 4-sample launch, both reverse steps, LocalBlend -- is a
+    single-step call of the native loop (variant 2, controller state carried across calls).
+      mode "nmg":      the recon row is first moved by noise-map guidance (gradient of an L1 loss w.r.t. the latent);
+      mode "nulltext": the unconditional embedding is optimised with Adam for this step (gradient w.r.t. the embedding) and replaces
+                       context 0 of the native launch."""
     import dataclasses
     import torch.nn.functional as F
-    assert len(prompts) >= 2 and etas == 0, "P2P requires source and target prompts, with eta is set to 0 for NMG"      # reference assert (:216)
     from .compat import controller_kind
     kind = controller_kind(controller)
     if kind == "custom":
-        raise NotImplementedError("nmg_p2p runs stock P2P controllers (or none) on the fused path")
+        raise NotImplementedError("the baseline samplers run stock P2P controllers (or none) on the fused path")
     steps = zs.shape[0]
     eng = get_engine(model, max_samples=5, device=_device_index(xT, None) if xT.is_cuda else None)
     eng.set_splitk(True)
     dev = torch.device("cuda", eng.device)
     ctx = encode_prompts(model, ["", prompts[0], prompts[1]]).float().to(dev)
-    ts, coef = step_tables(model.scheduler, steps, 0.0, False)          # reverse_step(..., eta = 0.0, variance_noise = None) everywhere (:226,231,246-247)
+    ts, coef = step_tables(model.scheduler, steps, 0.0, False)          # reverse_step(..., eta = 0.0, variance_noise = None) everywhere
     plan = compile_edit_plan([controller], steps) if kind == "stock" else None
     blend_state = eng.new_blend_state(1) if plan is not None and plan.has_blend.any() else None
+    pnp_mask, (qk_on, feat_on) = (pnp_self_mask(getattr(getattr(model.unet, "cfg", None), "layers_per_block", 2)), pnp_step_flags_at_t(model, steps)) \
+        if pnp_on else (0, (None, None))
     unet = model.unet
     udev = next(unet.parameters()).device
-    uncond = encode_text(model, [""]).to(udev)
+    uncond = encode_text(model, [""]).to(udev).float()
+    cond_src = encode_text(model, [prompts[0]]).to(udev).float()
     ac = model.scheduler.alphas_cumprod
-    w_tar = float(cfg_scales[1])                                          # both rows use the TARGET scale (:243-244)
+    w_tar = float(cfg_scales[1])                                          # both rows use the TARGET scale (p2p_baselines.py:243-244)
     x = xT.reshape(1, *xT.shape[-3:]).to(dev, torch.float32)
     xt = torch.stack([x, x], dim=1).contiguous()                          # (1, 2, C, h, w): rows (recon, target)
     zero = torch.zeros_like(x)[:, None]
 
     def reverse0(eps, sample, c):                                         # reverse_step with eta = 0 from the step's scalar row
-        x0 = (sample - c[0] * eps) / c[1]
-        return c[2] * x0 + c[3] * eps
+        return c[2] * ((sample - c[0] * eps) / c[1]) + c[3] * eps
 
     for i in range(steps):
         t = int(ts[i])
         c = [float(v) for v in coef[i]]
-        xt_ori = xT_ori[len(xT_ori) - i - 2].reshape(1, *xT.shape[-3:]).to(udev, torch.float32)
-        with torch.enable_grad():
-            x_in = xt[:, 0].detach().to(udev).requires_grad_(True)
-            try:
-                eps_u = unet(x_in, t, encoder_hidden_states=uncond, cross_attention_kwargs={"use_controller": False}).sample
-            except TypeError:                                             # a UNet with stock attention processors takes no P2P keyword
-                eps_u = unet(x_in, t, encoder_hidden_states=uncond).sample
-            loss = F.l1_loss(reverse0(eps_u, x_in, c), xt_ori)
-            grad = -torch.autograd.grad(loss, x_in)[0]
-        eps_u = eps_u.detach()
-        eps_c = eps_u - (1 - ac[t]).sqrt().to(udev) * grad * grad_scale
-        eps = eps_u + guidance_noise_map * (eps_c - eps_u)
-        xt[:, 0] = reverse0(eps, xt[:, 0].to(udev), c).to(dev)
+        x_ori = xT_ori[len(xT_ori) - i - 2].reshape(1, *xT.shape[-3:]).to(udev, torch.float32)
+        step_ctx = ctx
+        if mode == "nmg":
+            with torch.enable_grad():
+                x_in = xt[:, 0].detach().to(udev).requires_grad_(True)
+                eps_u = _unet_sample(unet, x_in, t, uncond)
+                loss = F.l1_loss(reverse0(eps_u, x_in, c), x_ori)
+                grad = -torch.autograd.grad(loss, x_in)[0]
+            eps_u = eps_u.detach()
+            eps_c = eps_u - (1 - ac[t]).sqrt().to(udev) * grad * grad_scale
+            eps = eps_u + guidance_noise_map * (eps_c - eps_u)
+            xt[:, 0] = reverse0(eps, xt[:, 0].to(udev), c).to(dev)
+        else:
+            x_rec = xt[:, 0].detach().to(udev)
+            with torch.no_grad():
+                eps_cond = _unet_sample(unet, x_rec, t, cond_src)
+            with torch.enable_grad():
+                emb = uncond.detach().clone().requires_grad_(True)
+                opt = torch.optim.Adam([emb], lr=1e-2 * (1. - i / 100.))
+                for _ in range(optimization_steps):
+                    eps_u = _unet_sample(unet, x_rec, t, emb)
+                    loss = F.mse_loss(reverse0(eps_u + w_tar * (eps_cond - eps_u), x_rec, c), x_ori)
+                    opt.zero_grad()
+                    loss.backward()
+                    opt.step()
+                    if loss.item() < epsilon + i * 2e-5:
+                        break
+            step_ctx = torch.cat([emb.detach().to(dev), ctx[1:]])
         p = None if plan is None else dataclasses.replace(plan, steps=1, c_base=plan.c_base[i:i + 2], c_tar=plan.c_tar[i:i + 2])
-        ed, rc = eng.edit(xt.contiguous(), zero, ctx, ts[i:i + 2], coef[i:i + 1], [w_tar, w_tar, w_tar], p, 0.0, 1, False, 1, variant=2,
-                          xt_is_pair=True, ctrl_step0=i, blend_state=blend_state, mos_pull=False)
+        pnp = (pnp_mask, qk_on[i:i + 1], feat_on[i:i + 1]) if pnp_on else None
+        ed, rc = eng.edit(xt.contiguous(), zero, step_ctx, ts[i:i + 2], coef[i:i + 1], [w_tar, w_tar, w_tar], p, 0.0, 1, False, 1, variant=2,
+                          xt_is_pair=True, ctrl_step0=i, blend_state=blend_state, mos_pull=False, pnp=pnp)
         xt = torch.stack([rc, ed], dim=1)
     if kind == "stock":
         controller.cur_step = getattr(controller, "cur_step", 0) + steps
         if getattr(controller, "local_blend", None) is not None:
             controller.local_blend.counter += steps
     return xt[:, 1].to(xT.device), xt[:, 0].to(xT.device)
+
+
+def nmg_p2p(model, xT, xT_ori, etas: float = 0.0, prompts="", cfg_scales=None, prog_bar=False, zs=None, controller=None,
+            guidance_noise_map: float = 10.0, grad_scale: float = 5e+3):
+    """Reference signature (inversion/p2p_baselines.py:195): Noise Map Guidance with P2P (hybrid, see _grad_guided).  Returns (edited, reconstructed)."""
+    assert len(prompts) >= 2 and etas == 0, "P2P requires source and target prompts, with eta is set to 0 for NMG"      # reference assert (:216)
+    return _grad_guided(model, xT, xT_ori, prompts, cfg_scales, zs, controller, False, "nmg", guidance_noise_map, grad_scale)
+
+
+def nmg_pnp(model, xT, xT_ori, etas=0, prompts="", cfg_scales=None, prog_bar=False, zs=None, guidance_noise_map=10.0, grad_scale: float = 5e+3):
+    """Reference signature (inversion/pnp_baselines.py:32): Noise Map Guidance with Plug-and-Play injection (hybrid, see _grad_guided)."""
+    assert len(prompts) >= 2 and etas == 0, "PnP requires source and target prompts, with eta is set to 0 for NMG"      # reference assert (:53)
+    return _grad_guided(model, xT, xT_ori, prompts, cfg_scales, zs, None, True, "nmg", guidance_noise_map, grad_scale)
+
+
+def nulltext_pnp(model, xT, xT_ori, etas=0, prompts="", cfg_scales=None, prog_bar=False, zs=None, optimization_steps: int = 10, epsilon: float = 1e-5):
+    """Reference signature (inversion/pnp_baselines.py:134): Null-Text Inversion with Plug-and-Play injection (hybrid, see _grad_guided)."""
+    assert len(prompts) >= 2 and etas == 0, "PnP requires source and target prompts, with eta is set to 0"
+    return _grad_guided(model, xT, xT_ori, prompts, cfg_scales, zs, None, True, "nulltext", optimization_steps=optimization_steps, epsilon=epsilon)

@@ -56,6 +56,8 @@ VARIANTS = {
     "tiny_ef_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "ef_pnp"),
     # Noise Map Guidance with P2P (p2p_baselines.py:195): differentiates through one UNet forward per step
     "tiny_nmg_p2p": (UNetConfig.tiny(sample_size=64), 6, 1, "nmg_p2p"),
+    "tiny_nmg_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "nmg_pnp"),
+    "tiny_nulltext_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "nulltext_pnp"),
     "tiny_np_pnp": (UNetConfig.tiny(sample_size=64), 6, 1, "np_pnp"),
 }
 # MutualSelfAttentionControl arguments per masactrl variant (default: start_step 2, start_layer 10, total_steps T*K)
@@ -242,6 +244,21 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
                                    zs=zs[:T], controller=controller, guidance_noise_map=10.0, grad_scale=5e+3)
         meta_extra = dict(baseline_cfg_scales=[1.0, 7.5], is_ddim_inversion=False, guidance_noise_map=10.0, grad_scale=5e+3)
         nmg_extra = {"xT_ori": torch.stack([w for w in wts[:T + 1]]).clone()}
+    elif mode in ("nmg_pnp", "nulltext_pnp"):
+        pu = importlib.import_module("plug_n_play.pnp_utils")
+        pnb = importlib.import_module("inversion.pnp_baselines")
+        f_t, attn_t = int(T * 0.8), int(T * 0.5)
+        qk_ts, conv_ts = model.scheduler.timesteps[:attn_t], model.scheduler.timesteps[:f_t]
+        pu.register_attention_control_efficient(model, qk_ts)
+        pu.register_conv_control_efficient(model, conv_ts)
+        bkw = dict(xT=wts[T], xT_ori=wts[:T + 1], etas=0.0, prompts=prompts, cfg_scales=[1.0, 7.5], prog_bar=False, zs=zs[:T])
+        if mode == "nmg_pnp":
+            edited, recon = pnb.nmg_pnp(model, guidance_noise_map=10.0, grad_scale=5e+3, **bkw)
+        else:
+            edited, recon = pnb.nulltext_pnp(model, optimization_steps=3, epsilon=1e-5, **bkw)
+        meta_extra = dict(pnp_qk_timesteps=[int(t) for t in qk_ts], pnp_conv_timesteps=[int(t) for t in conv_ts], baseline_cfg_scales=[1.0, 7.5],
+                          is_ddim_inversion=False, guidance_noise_map=10.0, grad_scale=5e+3, nulltext_steps=3)
+        nmg_extra = {"xT_ori": torch.stack([w for w in wts[:T + 1]]).clone()}
     elif mode in ("ef_pnp", "np_pnp"):
         pu = importlib.import_module("plug_n_play.pnp_utils")
         pnb = importlib.import_module("inversion.pnp_baselines")
@@ -285,7 +302,7 @@ def run_variant(ref, name, cfg, T, K, mode, xa=0.4, sa=0.35):
         raise ValueError(mode)
     enc = ref.inversion_utils.encode_text
     return {
-        **(nmg_extra if mode == "nmg_p2p" else {}),
+        **(nmg_extra if mode in ("nmg_p2p", "nmg_pnp", "nulltext_pnp") else {}),
         "meta": dict(name=name, mode=mode, T=T, K=K, xa=xa, sa=sa, prompts=prompts, blend_words=BLEND, cfg_scales=[1.0, 5.0, 7.5], eta=1.0,
                      weight_reconstruction=0.1, is_replace=False, blend=(mode in ("p2p_explicit", "ef_p2p", "pnpinv_p2p", "nmg_p2p")),
                      unet=dict(block_out_channels=list(cfg.block_out_channels), sample_size=cfg.sample_size,
