@@ -58,7 +58,9 @@ typedef struct hedit_edit_args {
                                 2: the baseline samplers ef_or_pnp_inv_w_p2p / ef_or_pnp_inv_w_masactrl (inversion/p2p_baselines.py:103,
                                    masactrl_baselines.py:15; Edit Friendly and PnP Inversion): one attention-controlled launch
                                    [xo,null] [xe,null] [xo,src] [xe,tar] per timestep, then the ORIG row steps with the source-guided
-                                   noise (coef) and the EDIT row with the target-guided noise (w_tar, coef_edit); no h-term */
+                                   noise (coef) and the EDIT row with the target-guided noise (w_tar, coef_edit); no h-term.  Accepts
+                                   xt_is_pair / ctrl_step0 / blend_state for single-step use (the gradient-guided baselines nmg_p2p,
+                                   nmg_pnp, nulltext_pnp call it once per timestep) */
   const float* xT;           /* [B][C][h][w] */
   const float* zs;           /* [B][steps][C][h][w]; zs[b][idx] as in the reference (idx = steps-1-i at step i) */
   const float* ctx;          /* [1+2B][ctx_len][cross_dim]: row 0 = "", then (src_b, tar_b) pairs (encode_text) */
@@ -98,7 +100,9 @@ typedef struct hedit_edit_args {
    * h_Edit_PnP_implicit.  The attention-controlled call of a step is the pair ([x_orig,src],[x_opt,tar]) at the previous timestep tt;
    * when pnp_qk_on[i] != 0 (tt in the qk injection schedule) the target takes the source's self-attention q and k in the transformer
    * blocks of pnp_self_mask (bit = block index in forward order), and when pnp_feat_on[i] != 0 it takes the source's conv2 output at
-   * up_blocks[1].resnets[1].  Requires explicit_form = 0, variant = 0, use_p2p = 0. */
+   * up_blocks[1].resnets[1].  Requires explicit_form = 0, use_p2p = 0 and variant = 0 -- or variant = 2 (the Plug-and-Play baselines
+   * ef_or_pnp_inv_w_pnp / negative_prompt_pnp / nmg_pnp / nulltext_pnp, inversion/pnp_baselines.py), where the injected pair is samples
+   * 2, 3 of the step's single launch at the CURRENT timestep and the flags are indexed by that timestep. */
   int32_t pnp;
   uint32_t pnp_self_mask;
   const int32_t* pnp_qk_on;   /* host [steps] */
