@@ -93,9 +93,13 @@ class ArcFaceEngine(_Engine):
     def loss_grad(self, img: torch.Tensor, grad_out: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None):
         """(loss (B,), grad (B,3,256,256)): loss[b] = 1 - cos(ref, f(img[b])) = `get_cosine_loss(img[b:b+1])`, grad = its image gradient."""
         x = img if (img.is_cuda and img.dtype == torch.float32 and img.is_contiguous()) else self._img(img)
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 256, 256) or x.device.index != self.device:
+            raise ValueError(f"ArcFaceEngine takes (B,3,256,256) images on cuda:{self.device}, got {tuple(x.shape)} on {x.device}")
         B = x.shape[0]
         grad = torch.empty_like(x) if grad_out is None else grad_out
         loss = torch.empty(B, device=x.device, dtype=torch.float32) if loss_out is None else loss_out
+        if grad.shape != x.shape or not grad.is_contiguous() or grad.dtype != torch.float32 or loss.numel() != B:
+            raise ValueError("grad_out / loss_out must be contiguous fp32 buffers of the image's / batch's shape")
         n = _lib.check(self.lib.hedit_arcface_loss_grad(self.handle, x.data_ptr(), B, loss.data_ptr(), grad.data_ptr(), self._stream()), "arcface loss_grad")
         self.last_stats = {"kernel_launches": n, "flops": self.lib.hedit_arcface_last_flops(self.handle)}
         return loss, grad
@@ -147,9 +151,17 @@ class LpipsEngine(_Engine):
 
     def loss_grad(self, img: torch.Tensor, grad_out: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None):
         x = img if (img.is_cuda and img.dtype == torch.float32 and img.is_contiguous()) else self._img(img)
+        src = getattr(self, "_src", None)
+        if src is None:
+            raise RuntimeError("LpipsEngine.set_source(...) first")
+        if x.dim() != 4 or tuple(x.shape[1:]) != tuple(src.shape[1:]) or src.shape[0] not in (1, x.shape[0]) or x.device.index != self.device:
+            raise ValueError(f"LpipsEngine: images must be (B,{','.join(str(v) for v in src.shape[1:])}) on cuda:{self.device} with B matching the "
+                             f"{src.shape[0]} source image(s), got {tuple(x.shape)} on {x.device}")
         B = x.shape[0]
         grad = torch.empty_like(x) if grad_out is None else grad_out
         loss = torch.empty(B, device=x.device, dtype=torch.float32) if loss_out is None else loss_out
+        if grad.shape != x.shape or not grad.is_contiguous() or grad.dtype != torch.float32 or loss.numel() != B:
+            raise ValueError("grad_out / loss_out must be contiguous fp32 buffers of the image's / batch's shape")
         n = _lib.check(self.lib.hedit_lpips_loss_grad(self.handle, x.data_ptr(), B, loss.data_ptr(), grad.data_ptr(), self._stream()), "lpips loss_grad")
         self.last_stats = {"kernel_launches": n, "flops": self.lib.hedit_lpips_last_flops(self.handle)}
         return loss, grad
